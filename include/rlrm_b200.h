@@ -1,0 +1,228 @@
+/*
+ * rlrm_b200.h — C ABI of the B200-native lockstep hot path of multiagent-rl-rm
+ * (grid-world transition -> event label -> Reward Machine transition -> tabular Q / QRM / Q(lambda) update)
+ * over large batches of independent environment instances.
+ *
+ * The reference (Alee08/multiagent-rl-rm v0.3.0) is pure Python and has no FFI layer; each entry point
+ * below names the reference Python interface it replaces (R/ = multiagent_rlrm/ in the reference tree).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch / C++ types in any signature
+ *   - every pointer inside rlrm_state_t / rlrm_step_out_t is a DEVICE pointer owned by the caller
+ *     (the Python host layer allocates them as torch tensors); the library never frees them
+ *   - rlrm_tables_t holds HOST pointers; rlrm_create copies those small tables to the device once
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - all functions return 0 on success, <0 on error (rlrm_last_error() gives the message); they never throw
+ *   - there is no CPU fallback: without a CUDA device rlrm_create fails with RLRM_ERR_CUDA
+ *
+ * Indexing
+ *   instance i in [0,N), agent a in [0,A), slot = i*A + a
+ *   cell = y*W + x                                     (R/environments/frozen_lake/state_encoder_frozen_lake.py:32)
+ *   enc  = cell*nQ + q                                 (same file :35; office: state_encoder_office.py:23-24)
+ *   Q[slot][enc][action] fp32, action order 0 up, 1 down, 2 left, 3 right
+ *                                                      (R/environments/frozen_lake/action_encoder_frozen_lake.py:14-17)
+ */
+#ifndef RLRM_B200_H
+#define RLRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLRM_ABI_VERSION 1
+
+#define RLRM_MAX_AGENTS 8      /* agents per instance (lane group = next power of two) */
+#define RLRM_MAX_CELLS 1024    /* W*H */
+#define RLRM_MAX_RM_STATES 32
+#define RLRM_MAX_EVENTS 63     /* distinct detector positions; column nEv of delta is the "None" event */
+#define RLRM_N_ACTIONS 4
+#define RLRM_ACTION_WAIT 4
+#define RLRM_EVENT_NONE 255    /* label value: position is not in the event detector's set */
+#define RLRM_NO_TRANSITION 255 /* delta value: (q, event) not in RewardMachine.transitions */
+
+/* error codes */
+#define RLRM_OK 0
+#define RLRM_ERR_ARG (-1)
+#define RLRM_ERR_CUDA (-2)
+#define RLRM_ERR_UNSUPPORTED (-3)
+
+/* environments: R/environments/frozen_lake/ma_frozen_lake.py, R/environments/office_world/ma_office.py */
+#define RLRM_ENV_FROZEN_LAKE 0
+#define RLRM_ENV_OFFICE_WORLD 1
+
+/* learners: R/learning_algorithms/qlearning.py (use_qrm False/True), qlearning_lambda.py */
+#define RLRM_ALGO_QL 0
+#define RLRM_ALGO_QRM 1
+#define RLRM_ALGO_QLAMBDA 2
+
+/* episode-loop semantics: R/environments/frozen_lake/frozen_lake_main.py:336-376,
+ * R/environments/office_world/office_main.py:1696-1749 */
+#define RLRM_DRIVER_FROZEN_LAKE_MAIN 0
+#define RLRM_DRIVER_OFFICE_MAIN 1
+
+/* rlrm_state_t.slot packing: one 64-bit word per (instance, agent) */
+#define RLRM_SLOT_CELL_SHIFT 0       /* 16 bits: y*W + x */
+#define RLRM_SLOT_STEPS_SHIFT 16     /* 16 bits: env.agent_steps[agent] */
+#define RLRM_SLOT_TIME_SHIFT 32      /* 16 bits: env.timestep (replicated in every agent of the instance) */
+#define RLRM_SLOT_RMSTATE_SHIFT 48   /*  8 bits: RewardMachine.current_state as index */
+#define RLRM_SLOT_FLAGS_SHIFT 56     /*  8 bits: RLRM_FLAG_* */
+#define RLRM_FLAG_ACTIVE 1u          /* env.active_agents[agent] */
+#define RLRM_FLAG_FAIL 2u            /* env.agent_fail[agent] */
+#define RLRM_FLAG_DONE 4u            /* last wrapper `terminations[agent]` */
+#define RLRM_FLAG_TRUNC 8u           /* last `truncations[agent]` */
+#define RLRM_FLAG_FIRST 16u          /* no step since reset: the FrozenLake driver's `states` still alias agent.state */
+
+typedef struct rlrm_config {
+  int32_t abi_version;  /* RLRM_ABI_VERSION */
+  int32_t env_kind;     /* RLRM_ENV_* */
+  int32_t driver;       /* RLRM_DRIVER_* */
+  int32_t algo;         /* RLRM_ALGO_* */
+  int32_t width, height;
+  int32_t n_agents;     /* A */
+  int32_t n_rm_states;  /* nQ = RewardMachine.numbers_state() (reward_machine.py:130-138) */
+  int32_t n_events;     /* nEv = number of detector positions with an event id */
+  int32_t rm_final;     /* index of RewardMachine.get_final_state() (reward_machine.py:152-163), -1 if none */
+  int32_t n_qrm_states; /* len(get_all_states()[:-1]) (rm_environment_wrapper.py:144) */
+  int32_t max_steps;    /* 1000: `> 1000` tests in ma_frozen_lake.py:202 / ma_office.py:254 */
+  /* dynamics */
+  int32_t stochastic;          /* env.frozen_lake_stochastic / env.stochastic */
+  int32_t slip_n;              /* outcomes per intended action (3 or 4); 1 when deterministic */
+  uint64_t slip_thr[3];        /* draw k (u32) falls in outcome j = #{T in slip_thr[0..slip_n-2] : k >= T};
+                                  T = ceil(cdf_j * 2^32) of numpy Generator.choice(p=...) */
+  uint8_t slip_outcome[4][4];  /* [intended action][j] -> executed action (0..3) or RLRM_ACTION_WAIT */
+  int32_t terminate_on_plants; /* office only (ma_office.py:217) */
+  int32_t terminate_hit_walls; /* office only (ma_office.py:322) */
+  double hole_penalty;         /* env.penalty_amount (ma_frozen_lake.py:185) / env.plants_penalty_value (ma_office.py:219) */
+  double wall_penalty;         /* env.wall_penalty_value (ma_office.py:324); 0 for FrozenLake */
+  /* learner (qlearning.py:9-39, qlearning_lambda.py:6-31) */
+  double learning_rate;        /* < 0: None => 1/visits (needs rlrm_state_t.visits) */
+  double gamma;
+  double lambd;
+  double epsilon_start, epsilon_end, epsilon_decay;
+  int32_t decay_on_reset;      /* 1: env.reset() calls learn_done_episode() (isinstance QLearning; false for Q(lambda)) */
+  int32_t shared_q;            /* 0: one table per (instance, agent); 1: one per agent index shared by all instances */
+  /* randomness: Philox4x32-10, key = (seed_lo, seed_hi), counter = (t_lo, t_hi, instance_offset + i, a) */
+  uint32_t seed_lo, seed_hi;
+  uint32_t instance_offset;    /* global id of local instance 0 (multi-GPU sharding keeps draws independent of G) */
+  int32_t reserved;
+} rlrm_config_t;
+
+/* host pointers; copied at rlrm_create */
+typedef struct rlrm_tables {
+  const uint16_t* next_cell;  /* [W*H][4] cell reached by action a, == cell when blocked (bounds, office walls)
+                                 (ma_frozen_lake.py:224-242; ma_office.py:269-289 + config_office.py:12-39) */
+  const uint8_t* cell_flags;  /* [W*H] bit0: hole (FrozenLake) / plant (OfficeWorld) */
+  const uint8_t* label;       /* [W*H] event id of the position, RLRM_EVENT_NONE otherwise (detect_event.py:18-33) */
+  const uint8_t* delta;       /* [nQ][nEv+1] next RM state index, RLRM_NO_TRANSITION = stay, reward 0 (reward_machine.py:45-59) */
+  const double* rq;           /* [nQ][nEv+1] transition reward * wrapper.reward_modifier (rm_environment_wrapper.py:65-69) */
+  const double* rcf;          /* [nQ][nEv+1] transition reward for QRM counterfactuals (unscaled, :150-153) */
+  const uint8_t* qrm_states;  /* [n_qrm_states] RM state indices, in get_all_states()[:-1] order */
+  const uint16_t* start_cell; /* [A] agent.initial_position */
+} rlrm_tables_t;
+
+/* per-(instance, agent) episode statistics, 32 bytes */
+typedef struct rlrm_stats {
+  uint64_t active_steps;  /* sum of env.agent_steps increments = the headline "agent-steps" */
+  uint32_t episodes;      /* episodes finished */
+  uint32_t successes;     /* episodes that ended with the RM in its final state */
+  double return_sum;      /* sum over finished episodes of the undiscounted episode return */
+  float last_return;      /* return of the last finished episode */
+  uint32_t last_length;   /* env.timestep at the end of the last finished episode */
+} rlrm_stats_t;
+
+/* device pointers, caller-owned */
+typedef struct rlrm_state {
+  int64_t n_instances;  /* N (local to this GPU) */
+  uint64_t* slot;       /* [N*A] packed env + RM state, see RLRM_SLOT_* */
+  double* epsilon;      /* [N*A] learner.epsilon */
+  float* q;             /* [N*A*S*4] (shared_q: [A*S*4]) learner.q_table, S = W*H*nQ */
+  float* e;             /* Q(lambda) only: learner.e_table, same shape as q; else NULL */
+  uint32_t* visits;     /* optional [same shape as q]: learner.visits; required when learning_rate < 0 */
+  double* ep_return;    /* [N*A] running (undiscounted) return of the current episode */
+  rlrm_stats_t* stats;  /* [N*A] or NULL */
+} rlrm_state_t;
+
+/* device pointers, caller-owned, each [N*A]; any may be NULL (not written) */
+typedef struct rlrm_step_out {
+  uint16_t* prev_cell;  /* infos[agent]["prev_s"] as cell index */
+  uint16_t* cell;       /* observations[agent] / infos["s"] */
+  uint8_t* prev_q;      /* infos["prev_q"] as index */
+  uint8_t* q;           /* infos["q"] as index */
+  uint8_t* event;       /* event id detected on the new position, RLRM_EVENT_NONE if none */
+  uint8_t* executed;    /* action actually executed after slip / wall (0..3, RLRM_ACTION_WAIT), 5 = agent skipped */
+  double* renv;         /* infos["Renv"] */
+  double* rq;           /* infos["RQ"] */
+  double* reward;       /* rewards[agent] = Renv + RQ */
+  uint8_t* env_term;    /* infos["env_terminated"] */
+  uint8_t* rm_term;     /* infos["rm_terminated"] */
+  uint8_t* term;        /* terminations[agent] */
+  uint8_t* trunc;       /* truncations[agent] */
+} rlrm_step_out_t;
+
+typedef struct rlrm_handle rlrm_handle_t;
+
+/* library / device */
+int rlrm_abi_version(void);
+const char* rlrm_last_error(void);
+int rlrm_device_count(void);
+
+/* Builds the device-side constant block for one configuration on CUDA device `device`.
+ * Replaces object construction in frozen_lake_main.py:200-295 / office_main.py:400-717 (env, RM, encoder, learner). */
+int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tables, int device, rlrm_handle_t** out);
+int rlrm_destroy(rlrm_handle_t* h);
+/* learner hyper-parameters may be changed between calls (the reference mutates attributes in place) */
+int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double gamma, double lambd);
+
+/* RMEnvironmentWrapper.reset (rm_environment_wrapper.py:28-41) -> env.reset (ma_frozen_lake.py:43-94,
+ * ma_office.py:77-120): positions, RM state, counters, epsilon decay, Q(lambda) trace wipe.
+ * mask: device uint8 [N] selecting instances, or NULL for all. */
+int rlrm_reset(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, void* stream);
+
+/* AgentRL.select_action (agent_rl.py:80-106) -> QLearning.choose_action (qlearning.py:112-143).
+ * draws: device uint32 [N*A*4] injected Philox words (w0 explore, w1 random action, w2 tie-break, w3 slip)
+ * or NULL to generate them in-kernel for lockstep iteration t. best != 0: argmax, no randomness. */
+int rlrm_select_action(rlrm_handle_t* h, const rlrm_state_t* st, const uint32_t* draws, uint64_t t, int best,
+                       uint8_t* actions_out, void* stream);
+
+/* RMEnvironmentWrapper.step (rm_environment_wrapper.py:43-107): env.step (ma_frozen_lake.py:96-154 /
+ * ma_office.py:122-202) + RewardMachine.step (reward_machine.py:45-59) per agent + reward / termination merge.
+ * actions: device uint8 [N*A]. with_rm == 0 runs the bare env.step (RM state is read for FrozenLake's rm_done
+ * test but not advanced). */
+int rlrm_step(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* actions, const uint32_t* draws, uint64_t t,
+              int with_rm, const rlrm_step_out_t* out, void* stream);
+
+/* RewardMachine.step (reward_machine.py:45-59) on explicit positions: q[N*A] in/out, cell[N*A] in, reward[N*A] out */
+int rlrm_rm_step(rlrm_handle_t* h, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
+                 double* reward_out, void* stream);
+
+/* AgentRL.update_policy (agent_rl.py:117-192) -> QLearning.update (qlearning.py:41-110, incl. the QRM
+ * counterfactual loop fed by rm_environment_wrapper.py:122-183) or QLearningLambda.update (qlearning_lambda.py:33-84).
+ * obs_cell: device uint16 [N*A], the `state` argument the driver passes (previous observation);
+ * term_arg: device uint8 [N*A], the `terminated` argument the driver passes. `out` is the record rlrm_step wrote. */
+int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_cell, const uint8_t* actions,
+                const uint8_t* term_arg, const rlrm_step_out_t* out, void* stream);
+
+/* One launch = n_iters lockstep iterations of the driver loop (select for all agents -> wrapper step -> update for
+ * all agents -> per-instance auto reset when the episode ends), state in registers, Philox draws for iterations
+ * t0 .. t0+n_iters-1. Replaces the while-loop body of frozen_lake_main.py:345-376 / office_main.py:1709-1749.
+ * trace (optional, device): uint32 [n_iters][N*A] packed per-iteration record for replay through the oracle:
+ *   bits 0-2 action, 3-5 executed, 6-15 cell after, 16-20 rm state after, 21 term, 22 trunc, 23 active-step. */
+int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
+               uint32_t* trace, void* stream);
+
+/* Same call with HOST buffers (the end-to-end path): uploads `slot`/`epsilon` control state from host_slot /
+ * host_epsilon when non-NULL, runs rlrm_train, downloads the statistics block into host_stats ([N*A]) and
+ * synchronises the stream. Device copies inside this call are part of the measured end-to-end time. */
+int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
+                    const uint64_t* host_slot, const double* host_epsilon, rlrm_stats_t* host_stats, void* stream);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t rlrm_launch_count(const rlrm_handle_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLRM_B200_H */

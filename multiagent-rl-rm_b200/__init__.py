@@ -1,0 +1,24 @@
+"""multiagent-rl-rm_b200 — B200-native lockstep hot path of multiagent-rl-rm (env step + RM transition + Q update).
+
+Host side is Python/PyTorch (device memory, streams, torch.distributed); the compute is hand-written CUDA for
+sm_100a behind the C ABI in include/rlrm_b200.h (csrc/rlrm_b200.cu). There is no CPU fallback.
+"""
+from . import _abi as abi  # noqa: F401
+from .maps import (  # noqa: F401
+    frozen_lake_grid,
+    office_world_grid,
+    parse_map_emoji,
+    parse_office_world,
+)
+from .reward_machine import PositionEventDetector, RewardMachine  # noqa: F401
+from .tables import (  # noqa: F401
+    Scenario,
+    compile_scenario,
+    scenario_config1,
+    scenario_config2,
+    scenario_config3,
+    scenario_config4,
+    scenario_config5,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,345 @@
+"""Host-side table compiler: (grid, dynamics flags, reward machine, learner settings) -> flat device tables.
+
+Everything the kernels index at run time is produced here, once, on the host:
+
+  next_cell[W*H][4]   move table   ma_frozen_lake.py:224-242 ; ma_office.py:269-289 + config_office.py:12-39
+  cell_flags[W*H]     hole / plant ma_frozen_lake.py:174-187 ; ma_office.py:204-220
+  slip thresholds     numpy Generator.choice(p=...) == one uniform + right-searchsorted on the normalised cdf
+                      (ma_frozen_lake.py:257-262, 283-296 ; ma_office.py:327-379)
+  label/delta/rq/rcf  RewardMachine.compile_tables (reward_machine.py in this package)
+
+A :class:`Scenario` is plain data (JSON-able through ``to_dict``) so the same description drives the reference
+harness (oracle/ref_harness.py), the C oracle and the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from fractions import Fraction
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi as abi
+from .maps import GridSpec, frozen_lake_grid, office_world_grid
+from .reward_machine import PositionEventDetector, RewardMachine
+
+UP, DOWN, LEFT, RIGHT, WAIT = 0, 1, 2, 3, 4
+_NAME_TO_ACTION = {"up": UP, "down": DOWN, "left": LEFT, "right": RIGHT, "wait": WAIT}
+
+
+@dataclass
+class Scenario:
+    env: str = "frozen_lake"  # "frozen_lake" | "office_world"
+    map_name: str = "map1"
+    starts: List[Tuple[int, int]] = field(default_factory=lambda: [(5, 0), (0, 0)])
+    # reward machine as an ordered transition list [(src, event_pos | None, dst, reward)] (dict order matters)
+    rm_transitions: List[Tuple[str, Optional[Tuple[int, int]], str, float]] = field(default_factory=list)
+    detector_positions: Optional[List[Tuple[int, int]]] = None  # default: the positions used by transitions
+    reward_modifier: float = 1
+    # dynamics
+    stochastic: bool = False
+    delay_action: bool = False
+    all_slip: bool = False
+    high_prob: float = 0.8
+    penalty_amount: float = 0  # FrozenLake hole penalty
+    plants_penalty: float = -100
+    wall_penalty: float = 0
+    terminate_on_plants: bool = False
+    terminate_hit_walls: bool = False
+    max_steps: int = 1000
+    # learner
+    algo: str = "qrm"  # "ql" | "qrm" | "qlambda"
+    learning_rate: Optional[float] = 1.0
+    gamma: float = 0.99
+    lambd: float = 0.0
+    epsilon_start: float = 0.01
+    epsilon_end: float = 0.01
+    epsilon_decay: float = 0.9995
+    q_init: float = 2.0
+    driver: str = "frozen_lake_main"  # "frozen_lake_main" | "office_main"
+    shared_q: bool = False
+    seed: int = 1234
+
+    def to_dict(self):
+        import dataclasses
+
+        d = dataclasses.asdict(self)
+        d["starts"] = [list(p) for p in self.starts]
+        d["rm_transitions"] = [[s, None if e is None else list(e), t, r] for (s, e, t, r) in self.rm_transitions]
+        if self.detector_positions is not None:
+            d["detector_positions"] = [list(p) for p in self.detector_positions]
+        return d
+
+    @staticmethod
+    def from_dict(d):
+        d = dict(d)
+        d["starts"] = [tuple(p) for p in d["starts"]]
+        d["rm_transitions"] = [(s, None if e is None else tuple(e), t, r) for (s, e, t, r) in d["rm_transitions"]]
+        if d.get("detector_positions") is not None:
+            d["detector_positions"] = [tuple(p) for p in d["detector_positions"]]
+        return Scenario(**d)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def grid(self) -> GridSpec:
+        return frozen_lake_grid(self.map_name) if self.env == "frozen_lake" else office_world_grid(self.map_name)
+
+    def reward_machine(self) -> RewardMachine:
+        transitions = {(s, e): (t, r) for (s, e, t, r) in self.rm_transitions}
+        if self.detector_positions is not None:
+            positions = set(self.detector_positions)
+        else:
+            positions = {e for (_s, e, _t, _r) in self.rm_transitions if e is not None}
+        return RewardMachine(transitions, PositionEventDetector(positions))
+
+
+# --------------------------------------------------------------------------------------------------
+# geometry
+# --------------------------------------------------------------------------------------------------
+def build_next_cell(grid: GridSpec) -> np.ndarray:
+    W, H = grid.width, grid.height
+    nxt = np.zeros((W * H, 4), dtype=np.uint16)
+    walls = set(grid.walls)
+    for y in range(H):
+        for x in range(W):
+            here = y * W + x
+            if grid.env == "frozen_lake":  # (0,0) top-left, "up" is y-1
+                cand = {UP: (x, y - 1), DOWN: (x, y + 1), LEFT: (x - 1, y), RIGHT: (x + 1, y)}
+            else:  # OfficeWorld: "up" is y+1 (ma_office.py:280-287)
+                cand = {UP: (x, y + 1), DOWN: (x, y - 1), LEFT: (x - 1, y), RIGHT: (x + 1, y)}
+            for a, (nx, ny) in cand.items():
+                ok = 0 <= nx < W and 0 <= ny < H and ((x, y), (nx, ny)) not in walls
+                nxt[here, a] = ny * W + nx if ok else here
+    return nxt
+
+
+def build_cell_flags(grid: GridSpec) -> np.ndarray:
+    flags = np.zeros(grid.width * grid.height, dtype=np.uint8)
+    for (x, y) in grid.hazards:
+        if 0 <= x < grid.width and 0 <= y < grid.height:
+            flags[y * grid.width + x] |= 1
+    return flags
+
+
+# --------------------------------------------------------------------------------------------------
+# slip model
+# --------------------------------------------------------------------------------------------------
+def slip_table(env: str, stochastic: bool, delay_action: bool, all_slip: bool, high_prob: float):
+    """(outcomes[4][n], probabilities[n]) with action indices; n == 1 when deterministic."""
+    if not stochastic:
+        return [[a] for a in range(4)], [1.0]
+    perp = {UP: (LEFT, RIGHT), DOWN: (LEFT, RIGHT), LEFT: (UP, DOWN), RIGHT: (UP, DOWN)}
+    opposite = {UP: DOWN, DOWN: UP, LEFT: RIGHT, RIGHT: LEFT}
+    if delay_action:
+        return [[WAIT, a, perp[a][0], perp[a][1]] for a in range(4)], [0.6, 0.36, 0.02, 0.02]
+    if env == "frozen_lake":
+        return [[a, perp[a][0], perp[a][1]] for a in range(4)], [0.8, 0.1, 0.1]
+    hp = high_prob
+    if all_slip:
+        lp = (1 - hp) / 3
+        outs = [[a, opposite[a]] + [b for b in (UP, DOWN, LEFT, RIGHT) if b not in (a, opposite[a])] for a in range(4)]
+        # reference order: left->[left,right,up,down], right->[right,left,up,down], up->[up,down,left,right], down->[down,up,left,right]
+        return outs, [hp, lp, lp, lp]
+    lp = (1 - hp) / 2
+    return [[a, perp[a][0], perp[a][1]] for a in range(4)], [hp, lp, lp]
+
+
+def slip_thresholds(probabilities: Sequence[float]) -> List[int]:
+    """Integer thresholds T_j = ceil(cdf_j * 2^32): for a 32-bit draw k, u = k / 2^32,
+    numpy's ``cdf.searchsorted(u, side='right')`` equals ``#{j : k >= T_j}`` exactly."""
+    cdf = np.cumsum(np.array(probabilities, dtype=np.float64))
+    cdf /= cdf[-1]
+    out = []
+    for c in cdf[:-1]:
+        fr = Fraction(float(c)) * (1 << 32)
+        out.append(int(-((-fr.numerator) // fr.denominator)))  # ceil
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# compiled scenario
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class Compiled:
+    scenario: Scenario
+    grid: GridSpec
+    rm: RewardMachine
+    next_cell: np.ndarray
+    cell_flags: np.ndarray
+    label: np.ndarray
+    delta: np.ndarray
+    rq: np.ndarray
+    rcf: np.ndarray
+    qrm_states: np.ndarray
+    start_cell: np.ndarray
+    events: List[Tuple[int, int]]
+    config: abi.Config
+
+    @property
+    def n_agents(self):
+        return self.config.n_agents
+
+    @property
+    def n_rm_states(self):
+        return self.config.n_rm_states
+
+    @property
+    def state_space(self):
+        return self.config.width * self.config.height * self.config.n_rm_states
+
+    def tables_struct(self) -> abi.Tables:
+        t = abi.Tables()
+        for name in ("next_cell", "cell_flags", "label", "delta", "rq", "rcf", "qrm_states", "start_cell"):
+            arr = np.ascontiguousarray(getattr(self, name))
+            setattr(self, name, arr)  # keep alive
+            setattr(t, name, arr.ctypes.data if arr.size else None)
+        return t
+
+
+_ALGO = {"ql": abi.ALGO_QL, "qrm": abi.ALGO_QRM, "qlambda": abi.ALGO_QLAMBDA}
+_DRIVER = {"frozen_lake_main": abi.DRIVER_FROZEN_LAKE_MAIN, "office_main": abi.DRIVER_OFFICE_MAIN}
+
+
+def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional[RewardMachine] = None,
+                     instance_offset: int = 0) -> Compiled:
+    grid = grid or sc.grid()
+    rm = rm or sc.reward_machine()
+    W, H = grid.width, grid.height
+    if W * H > abi.MAX_CELLS:
+        raise ValueError(f"grid {W}x{H} exceeds {abi.MAX_CELLS} cells")
+    if not (1 <= len(sc.starts) <= abi.MAX_AGENTS):
+        raise ValueError("1..8 agents per instance")
+    t = rm.compile_tables(W, H, sc.reward_modifier)
+
+    cfg = abi.Config()
+    cfg.abi_version = abi.ABI_VERSION
+    cfg.env_kind = abi.ENV_FROZEN_LAKE if grid.env == "frozen_lake" else abi.ENV_OFFICE_WORLD
+    cfg.driver = _DRIVER[sc.driver]
+    cfg.algo = _ALGO[sc.algo]
+    cfg.width, cfg.height = W, H
+    cfg.n_agents = len(sc.starts)
+    cfg.n_rm_states = t["n_states"]
+    cfg.n_events = t["n_events"]
+    cfg.rm_final = t["final"]
+    cfg.n_qrm_states = len(t["qrm_states"])
+    cfg.max_steps = sc.max_steps
+    cfg.stochastic = int(bool(sc.stochastic))
+    outs, probs = slip_table(grid.env, sc.stochastic, sc.delay_action, sc.all_slip, sc.high_prob)
+    cfg.slip_n = len(probs)
+    thr = slip_thresholds(probs)
+    for j in range(3):
+        cfg.slip_thr[j] = thr[j] if j < len(thr) else (1 << 32)
+    for a in range(4):
+        for j in range(4):
+            cfg.slip_outcome[a][j] = outs[a][j] if j < len(outs[a]) else outs[a][-1]
+    cfg.terminate_on_plants = int(bool(sc.terminate_on_plants))
+    cfg.terminate_hit_walls = int(bool(sc.terminate_hit_walls))
+    cfg.hole_penalty = float(sc.penalty_amount if grid.env == "frozen_lake" else sc.plants_penalty)
+    cfg.wall_penalty = float(0 if grid.env == "frozen_lake" else sc.wall_penalty)
+    cfg.learning_rate = -1.0 if sc.learning_rate is None else float(sc.learning_rate)
+    cfg.gamma = float(sc.gamma)
+    cfg.lambd = float(sc.lambd)
+    cfg.epsilon_start = float(sc.epsilon_start)
+    cfg.epsilon_end = float(sc.epsilon_end)
+    cfg.epsilon_decay = float(sc.epsilon_decay)
+    # env.reset() decays epsilon only for `isinstance(l_algo, QLearning)` (ma_frozen_lake.py:87-88, ma_office.py:107-108)
+    cfg.decay_on_reset = int(sc.algo in ("ql", "qrm"))
+    cfg.shared_q = int(bool(sc.shared_q))
+    cfg.seed_lo = sc.seed & 0xFFFFFFFF
+    cfg.seed_hi = (sc.seed >> 32) & 0xFFFFFFFF
+    cfg.instance_offset = instance_offset
+    start_cell = np.array([y * W + x for (x, y) in sc.starts], dtype=np.uint16)
+    return Compiled(
+        scenario=sc, grid=grid, rm=rm,
+        next_cell=build_next_cell(grid), cell_flags=build_cell_flags(grid),
+        label=t["label"], delta=t["delta"], rq=t["rq"], rcf=t["rcf"], qrm_states=t["qrm_states"],
+        start_cell=start_cell, events=t["events"], config=cfg,
+    )
+
+
+# --------------------------------------------------------------------------------------------------
+# the BASELINE.json configurations as scenarios
+# --------------------------------------------------------------------------------------------------
+def frozen_lake_abc_transitions(map_name="map1"):
+    g = frozen_lake_grid(map_name).goals
+    return [("state0", g["A"], "state1", 10), ("state1", g["B"], "state2", 15), ("state2", g["C"], "state3", 20)]
+
+
+def scenario_config1() -> Scenario:
+    """frozen_lake_main --map map1: 2 agents, deterministic, built-in A->B->C, QLearning(use_qrm=True)."""
+    return Scenario(env="frozen_lake", starts=[(5, 0), (0, 0)], rm_transitions=frozen_lake_abc_transitions(),
+                    stochastic=False, algo="qrm", learning_rate=1.0, gamma=0.99, epsilon_start=0.01,
+                    epsilon_end=0.01, epsilon_decay=0.9995, q_init=2.0, driver="frozen_lake_main", seed=111)
+
+
+def scenario_config3(use_qrm=True) -> Scenario:
+    """65,536 batched FrozenLake map1 instances x 2 agents, slippery, per-instance Q-tables."""
+    sc = scenario_config1()
+    sc.stochastic = True
+    sc.seed = 1234
+    if not use_qrm:
+        sc.algo, sc.learning_rate = "ql", 0.1
+    return sc
+
+
+def office_acbd_transitions(complete=False):
+    """'A -> C -> B -> D, reward on D' on OfficeWorld map1 (authored fixture)."""
+    g = office_world_grid("map1").goals
+    chain = [("q0", g["A"], "q1", 0.0), ("q1", g["C"], "q2", 0.0), ("q2", g["B"], "q3", 0.0), ("q3", g["D"], "q4", 1.0)]
+    if not complete:
+        return chain
+    events = [g["A"], g["C"], g["B"], g["D"]]
+    have = {(s, e) for (s, e, _t, _r) in chain}
+    out = list(chain)
+    for s in ("q0", "q1", "q2", "q3", "q4"):
+        for e in events:
+            if (s, e) not in have:
+                out.append((s, e, s, 0.0))
+    return out
+
+
+def scenario_config2(stochastic=False) -> Scenario:
+    return Scenario(env="office_world", starts=[(2, 7)], rm_transitions=office_acbd_transitions(),
+                    detector_positions=sorted(set(office_world_grid("map1").goals.values())
+                                              | set(office_world_grid("map1").coffee)
+                                              | set(office_world_grid("map1").letters)),
+                    stochastic=stochastic, high_prob=0.8, algo="ql", learning_rate=0.1 if stochastic else 1.0,
+                    gamma=0.9, epsilon_start=0.1, epsilon_end=0.1, epsilon_decay=1.0, q_init=2.0,
+                    driver="office_main", seed=100)
+
+
+def office_chain12_transitions():
+    """Synthetic 12-state completed chain A,B,C,D,E,coffee,letter,O,A,C,B: 108 transitions."""
+    gr = office_world_grid("map1")
+    g = gr.goals
+    vocab = [("A", [g["A"]]), ("B", [g["B"]]), ("C", [g["C"]]), ("D", [g["D"]]), ("E", [g["E"]]),
+             ("coffee", list(gr.coffee)), ("letter", list(gr.letters)), ("O", [g["O"]])]
+    byname = dict(vocab)
+    chain_events = ["A", "B", "C", "D", "E", "coffee", "letter", "O", "A", "C", "B"]
+    out, have = [], set()
+    for i, ev in enumerate(chain_events):
+        r = 1.0 if i == len(chain_events) - 1 else 0.0
+        for pos in byname[ev]:
+            out.append((f"q{i}", pos, f"q{i + 1}", r))
+            have.add((f"q{i}", pos))
+    for i in range(12):
+        for _name, poss in vocab:
+            for pos in poss:
+                if (f"q{i}", pos) not in have:
+                    out.append((f"q{i}", pos, f"q{i}", 0.0))
+                    have.add((f"q{i}", pos))
+    return out
+
+
+def scenario_config4() -> Scenario:
+    return Scenario(env="office_world", starts=[(2, 7), (0, 0), (6, 3), (11, 8)],
+                    rm_transitions=office_chain12_transitions(), stochastic=True, high_prob=0.8,
+                    algo="qlambda", learning_rate=0.1, gamma=0.9, lambd=0.9, epsilon_start=0.1, epsilon_end=0.1,
+                    epsilon_decay=1.0, q_init=0.0, driver="office_main", seed=1234)
+
+
+def scenario_config5(shared=True) -> Scenario:
+    sc = scenario_config3(use_qrm=True)
+    sc.starts = [(5, 0), (0, 0), (9, 0), (7, 3)]
+    sc.shared_q = shared
+    return sc

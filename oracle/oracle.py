@@ -1,0 +1,149 @@
+"""TEST INFRASTRUCTURE — ctypes front-end of the CPU oracle (oracle/rlrm_oracle.c). Not part of the product path.
+
+``Oracle(compiled, n_instances, real="f32")`` owns numpy state with exactly the layout the CUDA library uses
+(include/rlrm_b200.h), so tests compare raw buffers. ``real="f64"`` is the reference's native float64 arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+import multiagent_rlrm_b200  # noqa: E402  (struct layouts only)
+from multiagent_rlrm_b200 import _abi as abi  # noqa: E402
+
+STATS_DTYPE = np.dtype([("active_steps", "<u8"), ("episodes", "<u4"), ("successes", "<u4"), ("return_sum", "<f8"),
+                        ("last_return", "<f4"), ("last_length", "<u4")])
+assert STATS_DTYPE.itemsize == 32
+
+_libs = {}
+
+
+def build(force=False):
+    """Compile both oracle flavours with gcc (oracle/Makefile)."""
+    targets = [os.path.join(_HERE, f"liboracle_{k}.so") for k in ("f32", "f64")]
+    src = os.path.join(_HERE, "rlrm_oracle.c")
+    hdr = os.path.join(_ROOT, "include", "rlrm_b200.h")
+    stale = force or any((not os.path.exists(t)) or os.path.getmtime(t) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+                         for t in targets)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "all"], check=True, capture_output=True)
+    return targets
+
+
+def lib(real="f32"):
+    if real not in _libs:
+        path = os.path.join(_HERE, f"liboracle_{real}.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        assert L.oracle_real_size() == (4 if real == "f32" else 8)
+        _libs[real] = L
+    return _libs[real]
+
+
+def _p(arr):
+    return None if arr is None else arr.ctypes.data
+
+
+class Oracle:
+    def __init__(self, compiled, n_instances, real="f32", track_visits=False):
+        self.c = compiled
+        self.cfg = compiled.config
+        self.tables = compiled.tables_struct()
+        self.N, self.A = int(n_instances), compiled.n_agents
+        self.S = compiled.state_space
+        self.real = real
+        self.L = lib(real)
+        dt = np.float32 if real == "f32" else np.float64
+        n_tab = self.A if self.cfg.shared_q else self.N * self.A
+        self.slot = np.zeros(self.N * self.A, dtype=np.uint64)
+        self.epsilon = np.full(self.N * self.A, self.cfg.epsilon_start, dtype=np.float64)
+        self.q = np.full((n_tab, self.S, 4), compiled.scenario.q_init, dtype=dt)
+        self.e = np.zeros((n_tab, self.S, 4), dtype=dt) if self.cfg.algo == abi.ALGO_QLAMBDA else None
+        need_visits = track_visits or self.cfg.learning_rate < 0
+        self.visits = np.zeros((n_tab, self.S, 4), dtype=np.uint32) if need_visits else None
+        self.ep_return = np.zeros(self.N * self.A, dtype=np.float64)
+        self.stats = np.zeros(self.N * self.A, dtype=STATS_DTYPE)
+        self.state = abi.State(self.N, _p(self.slot), _p(self.epsilon), _p(self.q), _p(self.e), _p(self.visits),
+                               _p(self.ep_return), _p(self.stats))
+
+    # -- C calls -------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.L.oracle_reset(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(m)))
+
+    def select_action(self, t=0, draws=None, best=False):
+        out = np.zeros(self.N * self.A, dtype=np.uint8)
+        d = None if draws is None else np.ascontiguousarray(draws, dtype=np.uint32)
+        self.L.oracle_select_action(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(d)),
+                                    C.c_uint64(t), C.c_int(int(best)), C.c_void_p(_p(out)))
+        return out.reshape(self.N, self.A)
+
+    def step(self, actions, t=0, draws=None, with_rm=True):
+        acts = np.ascontiguousarray(actions, dtype=np.uint8).reshape(-1)
+        d = None if draws is None else np.ascontiguousarray(draws, dtype=np.uint32)
+        rec = {k: np.zeros(self.N * self.A, dtype=np.dtype(v)) for k, v in abi.STEP_OUT_FIELDS.items()}
+        so = abi.StepOut(*[_p(rec[k]) for k in abi.STEP_OUT_FIELDS])
+        self.L.oracle_step(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(acts)),
+                           C.c_void_p(_p(d)), C.c_uint64(t), C.c_int(int(with_rm)), C.byref(so))
+        return rec
+
+    def rm_step(self, q, cell):
+        q = np.ascontiguousarray(q, dtype=np.uint8).copy()
+        cell = np.ascontiguousarray(cell, dtype=np.uint16)
+        ev = np.zeros(q.size, dtype=np.uint8)
+        r = np.zeros(q.size, dtype=np.float64)
+        self.L.oracle_rm_step(C.byref(self.cfg), C.byref(self.tables), C.c_int64(q.size), C.c_void_p(_p(q)),
+                              C.c_void_p(_p(cell)), C.c_void_p(_p(ev)), C.c_void_p(_p(r)))
+        return q, ev, r
+
+    def update(self, obs_cell, actions, term_arg, rec):
+        obs = np.ascontiguousarray(obs_cell, dtype=np.uint16).reshape(-1)
+        acts = np.ascontiguousarray(actions, dtype=np.uint8).reshape(-1)
+        term = np.ascontiguousarray(term_arg, dtype=np.uint8).reshape(-1)
+        so = abi.StepOut(*[_p(rec[k]) for k in abi.STEP_OUT_FIELDS])
+        self.L.oracle_update(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(obs)),
+                             C.c_void_p(_p(acts)), C.c_void_p(_p(term)), C.byref(so))
+
+    def train(self, t0, n_iters, learn=True, trace=False):
+        tr = np.zeros((n_iters, self.N * self.A), dtype=np.uint32) if trace else None
+        self.L.oracle_train(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_uint64(t0),
+                            C.c_int32(n_iters), C.c_int32(int(learn)), C.c_void_p(_p(tr)))
+        return tr
+
+    # -- views ---------------------------------------------------------------------------------
+    def unpack(self):
+        return unpack_slots(self.slot, self.N, self.A)
+
+
+def unpack_slots(slot, N, A):
+    s = np.asarray(slot, dtype=np.uint64).reshape(N, A)
+    return {
+        "cell": ((s >> np.uint64(abi.SLOT_CELL_SHIFT)) & np.uint64(0xFFFF)).astype(np.int32),
+        "agent_steps": ((s >> np.uint64(abi.SLOT_STEPS_SHIFT)) & np.uint64(0xFFFF)).astype(np.int32),
+        "timestep": ((s >> np.uint64(abi.SLOT_TIME_SHIFT)) & np.uint64(0xFFFF)).astype(np.int32),
+        "q": ((s >> np.uint64(abi.SLOT_RMSTATE_SHIFT)) & np.uint64(0xFF)).astype(np.int32),
+        "flags": ((s >> np.uint64(abi.SLOT_FLAGS_SHIFT)) & np.uint64(0xFF)).astype(np.int32),
+    }
+
+
+def unpack_trace(tr, N, A):
+    t = np.asarray(tr, dtype=np.uint32).reshape(-1, N, A)
+    return {
+        "action": (t & 7).astype(np.int32),
+        "executed": ((t >> 3) & 7).astype(np.int32),
+        "cell": ((t >> 6) & 1023).astype(np.int32),
+        "q": ((t >> 16) & 31).astype(np.int32),
+        "term": ((t >> 21) & 1).astype(np.int32),
+        "trunc": ((t >> 22) & 1).astype(np.int32),
+        "stepped": ((t >> 23) & 1).astype(np.int32),
+    }

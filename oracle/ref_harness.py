@@ -1,0 +1,270 @@
+"""TEST INFRASTRUCTURE — not part of the product path.
+
+Drives the LIVE reference (/root/reference, imported under oracle/ref_shim) through a verbatim restatement of its
+two driver loops and records everything the hot path produces, with the randomness INJECTED from Philox words
+(oracle/philox.py) through stand-in ``rng`` objects. Used to (1) generate the golden fixtures under tests/golden/
+(oracle/gen_golden.py) and (2) validate the C oracle (oracle/rlrm_oracle.c) in this container.
+It is never imported by the package, and cannot run on the GPU box (no /root/reference there).
+
+Loop restated:
+  FrozenLake  /root/reference/multiagent_rlrm/environments/frozen_lake/frozen_lake_main.py:312, 336-376
+  OfficeWorld /root/reference/multiagent_rlrm/environments/office_world/office_main.py:1696-1749
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.environ.get("RLRM_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "multiagent_rlrm"))
+
+
+def _import_reference():
+    shim = os.path.join(_HERE, "ref_shim")
+    for p in (REFERENCE_ROOT, shim):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    sys.path.insert(0, _HERE)
+
+
+ACTIONS = ("up", "down", "left", "right")
+
+
+class DrawSource:
+    """Philox words per (t, instance, agent); t is set by the loop before each lockstep iteration."""
+
+    def __init__(self, seed, n_instances, n_agents, instance_offset=0):
+        import philox
+
+        self._philox = philox
+        self.seed, self.n, self.a, self.off = seed, n_instances, n_agents, instance_offset
+        self.t = 0
+        self._cache = {}
+
+    def words(self, i, a):
+        w = self._cache.get(self.t)
+        if w is None:
+            if len(self._cache) > 4096:
+                self._cache.clear()
+            w = self._cache[self.t] = self._philox.draws(self.seed, self.t, self.n, self.a, self.off)
+        return w[i, a]
+
+
+class LearnerRNG:
+    """Stands in for learner.rng (numpy Generator) inside QLearning.choose_action (qlearning.py:118-143)."""
+
+    def __init__(self, src, i, a):
+        self.src, self.i, self.a = src, i, a
+
+    def uniform(self, lo=0.0, hi=1.0):
+        return lo + (hi - lo) * (int(self.src.words(self.i, self.a)[0]) / 4294967296.0)
+
+    def choice(self, seq, p=None):
+        w = self.src.words(self.i, self.a)
+        if isinstance(seq, range):  # rng.choice(range(A)): uniform random action
+            return seq[(int(w[1]) * len(seq)) >> 32]
+        seq = list(seq)  # rng.choice(maxs): uniform tie-break
+        return seq[(int(w[2]) * len(seq)) >> 32]
+
+
+class EnvRNG:
+    """Stands in for env.rng inside get_stochastic_action (ma_frozen_lake.py:257-262 ; ma_office.py:376-379):
+    numpy's Generator.choice(a, p=p) is one uniform + searchsorted(cdf, u, side='right')."""
+
+    def __init__(self, src, i):
+        self.src, self.i = src, i
+        self.agent_index = 0
+
+    def choice(self, actions, p=None):
+        u = int(self.src.words(self.i, self.agent_index)[3]) / 4294967296.0
+        cdf = np.cumsum(np.array(p, dtype=np.float64))
+        cdf /= cdf[-1]
+        return actions[int(np.searchsorted(cdf, u, side="right"))]
+
+
+def build_reference(sc: dict, table_dtype=np.float32):
+    """Reference objects for one environment instance of scenario dict `sc` (tables.Scenario.to_dict())."""
+    _import_reference()
+    from multiagent_rlrm.learning_algorithms.qlearning import QLearning
+    from multiagent_rlrm.learning_algorithms.qlearning_lambda import QLearningLambda
+    from multiagent_rlrm.multi_agent.agent_rl import AgentRL
+    from multiagent_rlrm.multi_agent.reward_machine import RewardMachine
+    from multiagent_rlrm.multi_agent.wrappers.rm_environment_wrapper import RMEnvironmentWrapper
+    from multiagent_rlrm.utils.utils import parse_map_emoji, parse_office_world
+
+    if sc["env"] == "frozen_lake":
+        from multiagent_rlrm.environments.frozen_lake.action_encoder_frozen_lake import ActionEncoderFrozenLake as AEnc
+        from multiagent_rlrm.environments.frozen_lake.config_frozen_lake import config as fl_config
+        from multiagent_rlrm.environments.frozen_lake.detect_event import PositionEventDetector
+        from multiagent_rlrm.environments.frozen_lake.ma_frozen_lake import MultiAgentFrozenLake
+        from multiagent_rlrm.environments.frozen_lake.state_encoder_frozen_lake import StateEncoderFrozenLake as SEnc
+
+        holes, goals, (w, h) = parse_map_emoji(fl_config["maps"][sc["map_name"]]["layout"])
+        env = MultiAgentFrozenLake(width=w, height=h, holes=holes)
+        env.frozen_lake_stochastic = bool(sc["stochastic"])
+        env.penalty_amount = sc["penalty_amount"]
+        env.delay_action = bool(sc["delay_action"])
+    else:
+        from multiagent_rlrm.environments.office_world.action_encoder_office_world import ActionEncoderOfficeWorld as AEnc
+        from multiagent_rlrm.environments.office_world.config_office import config as ow_config
+        from multiagent_rlrm.environments.office_world.detect_event import PositionEventDetector
+        from multiagent_rlrm.environments.office_world.ma_office import MultiAgentOfficeWorld
+        from multiagent_rlrm.environments.office_world.state_encoder_office import StateEncoderOfficeWorld as SEnc
+
+        m = ow_config["maps"][sc["map_name"]]
+        coords, goals, walls = parse_office_world(m["layout"])
+        walls = walls + [(b, a) for (a, b) in walls]  # office_main.py:416
+        env = MultiAgentOfficeWorld(
+            width=m["grid_size"][1], height=m["grid_size"][0], plants=coords["plant"], coffee=coords["coffee"],
+            letters=coords["letter"], walls=walls, plants_penalty_value=sc["plants_penalty"],
+            wall_penalty_value=sc["wall_penalty"], terminate_on_plants=bool(sc["terminate_on_plants"]),
+            terminate_hit_walls=bool(sc["terminate_hit_walls"]))
+        env.all_slip = bool(sc["all_slip"])
+        env.stochastic = bool(sc["stochastic"])
+        env.high_prob = sc["high_prob"]
+        env.delay_action = bool(sc["delay_action"])
+    env.max_steps_unused = sc["max_steps"]
+    assert sc["max_steps"] == 1000, "the reference hard-codes the 1000-step cap"
+
+    transitions = {}
+    for (s, e, t, r) in sc["rm_transitions"]:
+        transitions[(s, None if e is None else tuple(e))] = (t, r)
+    if sc.get("detector_positions") is not None:
+        positions = {tuple(p) for p in sc["detector_positions"]}
+    else:
+        positions = {ev for (_s, ev) in transitions if ev is not None}
+
+    agents = []
+    for k, (x, y) in enumerate(sc["starts"]):
+        ag = AgentRL(f"a{k + 1}", env)
+        ag.set_initial_position(x, y)
+        ag.add_state_encoder(SEnc(ag))
+        ag.add_action_encoder(AEnc(ag))
+        rm = RewardMachine(dict(transitions), PositionEventDetector(set(positions)))
+        ag.set_reward_machine(rm)
+        env.add_agent(ag)
+        n_states = env.grid_width * env.grid_height * rm.numbers_state()
+        common = dict(state_space_size=n_states, action_space_size=4, learning_rate=sc["learning_rate"],
+                      gamma=sc["gamma"], action_selection="greedy", epsilon_start=sc["epsilon_start"],
+                      epsilon_end=sc["epsilon_end"], epsilon_decay=sc["epsilon_decay"])
+        if sc["algo"] == "qlambda":
+            learner = QLearningLambda(lambd=sc["lambd"], **common)
+            learner.e_table = learner.e_table.astype(table_dtype)
+        else:
+            if sc["learning_rate"] is None:
+                # QLearning.__init__ formats learning_rate with :0.2f (qlearning.py:37) and cannot take None
+                common["learning_rate"] = 0.0
+            learner = QLearning(qtable_init=sc["q_init"], use_qrm=(sc["algo"] == "qrm"), **common)
+            learner.learning_rate = sc["learning_rate"]
+        learner.q_table = np.full(learner.q_table.shape, sc["q_init"], dtype=table_dtype)
+        ag.set_learning_algorithm(learner)
+        agents.append(ag)
+    rm_env = RMEnvironmentWrapper(env, agents)
+    rm_env.reward_modifier = sc["reward_modifier"]
+    return rm_env, env, agents
+
+
+FIELDS_U8 = ("action", "q", "prev_q", "env_term", "rm_term", "term", "trunc", "active", "fail")
+FIELDS_I32 = ("cell", "prev_cell", "event_cell", "agent_steps", "timestep")
+FIELDS_F64 = ("renv", "rq", "reward", "epsilon", "q_sa")
+
+
+def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float32, pre_resets: int = 1,
+                  instance_offset: int = 0, learn: bool = True, snapshot_iters=()):
+    """Run `n_iters` lockstep iterations (episodes restart back-to-back) for each of `n_instances` independent
+    reference environments. Returns dict of arrays shaped [T, N, A] plus final tables [N, A, S, 4]."""
+    n_agents = len(sc["starts"])
+    src = DrawSource(sc["seed"], n_instances, n_agents, instance_offset)
+    out = {k: np.zeros((n_iters, n_instances, n_agents), dtype=np.uint8) for k in FIELDS_U8}
+    out.update({k: np.full((n_iters, n_instances, n_agents), -1, dtype=np.int32) for k in FIELDS_I32})
+    out.update({k: np.zeros((n_iters, n_instances, n_agents), dtype=np.float64) for k in FIELDS_F64})
+    out["episode_end"] = np.zeros((n_iters, n_instances), dtype=np.uint8)
+    q_final, e_final, snaps = [], [], {int(t): [] for t in snapshot_iters}
+    fl_driver = sc["driver"] == "frozen_lake_main"
+
+    for i in range(n_instances):
+        rm_env, env, agents = build_reference(sc, table_dtype)
+        W = env.grid_width
+        for k, ag in enumerate(agents):
+            ag.get_learning_algorithm().rng = LearnerRNG(src, i, k)
+        index_of = {ag.name: k for k, ag in enumerate(agents)}
+        orig_gsa = env.get_stochastic_action
+
+        def gsa(agent, intended, _orig=orig_gsa, _env=env, _idx=index_of):
+            _env.rng.agent_index = _idx[agent.name]
+            return _orig(agent, intended)
+
+        env.get_stochastic_action = gsa
+        for _ in range(pre_resets):
+            rm_env.reset(sc["seed"])
+        t = 0
+        while t < n_iters:
+            states, infos = rm_env.reset(sc["seed"])
+            env.rng = EnvRNG(src, i)  # reset() re-created env.rng (ma_frozen_lake.py:59 ; ma_office.py:96)
+            if not fl_driver:
+                states = copy.deepcopy(states)  # office_main.py:1700
+            while t < n_iters:
+                src.t = t
+                actions = {}
+                for ag in rm_env.agents:
+                    actions[ag.name] = ag.select_action(rm_env.env.get_state(ag))
+                new_states, rewards, terminated, truncated, infos = rm_env.step(actions)
+                for k, ag in enumerate(rm_env.agents):
+                    name = ag.name
+                    term_arg = (terminated[name] or truncated[name]) if fl_driver else terminated[name]
+                    info = infos[name]
+                    rm = ag.get_reward_machine()
+                    if learn:
+                        ag.update_policy(state=states[name], action=actions[name], reward=rewards[name],
+                                         next_state=new_states[name], terminated=term_arg, infos=info)
+                    a_idx = ag.actions_idx(actions[name])
+                    prev_s = info.get("prev_s", new_states[name])
+                    o = (t, i, k)
+                    out["action"][o] = a_idx
+                    out["cell"][o] = new_states[name]["pos_y"] * W + new_states[name]["pos_x"]
+                    out["prev_cell"][o] = prev_s["pos_y"] * W + prev_s["pos_x"]
+                    out["q"][o] = rm.get_state_index(info["q"])
+                    out["prev_q"][o] = rm.get_state_index(info["prev_q"])
+                    ev = rm.event_detector.detect_event(new_states[name])
+                    out["event_cell"][o] = -1 if ev is None else ev[1] * W + ev[0]
+                    out["renv"][o] = info.get("Renv", 0)
+                    out["rq"][o] = info["RQ"]
+                    out["reward"][o] = rewards[name]
+                    out["env_term"][o] = info["env_terminated"]
+                    out["rm_term"][o] = info["rm_terminated"]
+                    out["term"][o] = terminated[name]
+                    out["trunc"][o] = truncated[name]
+                    out["active"][o] = env.active_agents[name]
+                    out["fail"][o] = env.agent_fail[name]
+                    out["agent_steps"][o] = env.agent_steps[name]
+                    out["timestep"][o] = env.timestep
+                    out["epsilon"][o] = getattr(ag.get_learning_algorithm(), "epsilon", 0.0)
+                    enc = out["prev_cell"][o] * rm.numbers_state() + out["prev_q"][o]
+                    out["q_sa"][o] = ag.get_learning_algorithm().q_table[enc, a_idx]
+                states = copy.deepcopy(new_states)
+                t += 1
+                if t in snaps:
+                    snaps[t].append(np.stack([ag.get_learning_algorithm().q_table.copy() for ag in agents]))
+                if fl_driver:
+                    over = all(terminated.values()) or all(truncated.values())
+                else:
+                    over = all(terminated.values()) or all(truncated.values())
+                if over:
+                    out["episode_end"][t - 1, i] = 1
+                    break
+        q_final.append(np.stack([ag.get_learning_algorithm().q_table for ag in agents]))
+        if sc["algo"] == "qlambda":
+            e_final.append(np.stack([ag.get_learning_algorithm().e_table for ag in agents]))
+    out["q_final"] = np.stack(q_final)
+    if e_final:
+        out["e_final"] = np.stack(e_final)
+    for t, lst in snaps.items():
+        out[f"q_at_{t}"] = np.stack(lst)
+    return out
