@@ -1,0 +1,96 @@
+"""Build + load the CUDA C-ABI library (csrc/rlrm_b200.cu -> librlrm_b200.so, in-tree).
+
+There is no CPU fallback: :func:`load` raises if the shared library is missing or a symbol of
+include/rlrm_b200.h is not exported, and ``rlrm_create`` itself fails without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+from . import _abi as abi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "librlrm_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", "rlrm_b200.cu")]
+HEADERS = [os.path.join(_ROOT, "include", "rlrm_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC"]
+
+_lib = None
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc cross-compiles for sm_100a; works without a GPU."""
+    if force or is_stale():
+        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """ctypes handle with argtypes set; raises RuntimeError when the extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "multiagent-rl-rm_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    missing = [s for s in abi.EXPORTED_SYMBOLS if not hasattr(L, s)]
+    if missing:
+        raise RuntimeError(f"{LIB_PATH} does not export {missing}")
+    vp, u64, i32, i64 = C.c_void_p, C.c_uint64, C.c_int32, C.c_int64
+    L.rlrm_abi_version.restype = C.c_int
+    L.rlrm_last_error.restype = C.c_char_p
+    L.rlrm_device_count.restype = C.c_int
+    L.rlrm_create.argtypes = [C.POINTER(abi.Config), C.POINTER(abi.Tables), C.c_int, C.POINTER(vp)]
+    L.rlrm_destroy.argtypes = [vp]
+    L.rlrm_set_learner.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    L.rlrm_reset.argtypes = [vp, C.POINTER(abi.State), vp, vp]
+    L.rlrm_select_action.argtypes = [vp, C.POINTER(abi.State), vp, u64, C.c_int, vp, vp]
+    L.rlrm_step.argtypes = [vp, C.POINTER(abi.State), vp, vp, u64, C.c_int, C.POINTER(abi.StepOut), vp]
+    L.rlrm_rm_step.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.rlrm_update.argtypes = [vp, C.POINTER(abi.State), vp, vp, vp, C.POINTER(abi.StepOut), vp]
+    L.rlrm_train.argtypes = [vp, C.POINTER(abi.State), u64, i32, i32, vp, vp]
+    L.rlrm_train_host.argtypes = [vp, C.POINTER(abi.State), u64, i32, i32, vp, vp, vp, vp]
+    L.rlrm_launch_count.argtypes = [vp]
+    L.rlrm_launch_count.restype = i64
+    for name in ("rlrm_create", "rlrm_destroy", "rlrm_set_learner", "rlrm_reset", "rlrm_select_action", "rlrm_step",
+                 "rlrm_rm_step", "rlrm_update", "rlrm_train", "rlrm_train_host"):
+        getattr(L, name).restype = C.c_int
+    if L.rlrm_abi_version() != abi.ABI_VERSION:
+        raise RuntimeError("librlrm_b200.so ABI version mismatch: rebuild")
+    _lib = L
+    return L
+
+
+class RlrmError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RlrmError(f"rlrm error {rc}: {load().rlrm_last_error().decode()}")

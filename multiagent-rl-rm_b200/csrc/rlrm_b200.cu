@@ -1,0 +1,1001 @@
+// rlrm_b200.cu — hand-written CUDA (sm_100a) for the lockstep hot path of multiagent-rl-rm and its C ABI
+// (include/rlrm_b200.h). One thread per (environment instance, agent); the map / label / Reward-Machine tables are
+// staged once per block in shared memory; Q rows are 16-byte vector gathers/scatters on per-instance tables in HBM;
+// randomness is Philox4x32-10 on (iteration, instance, agent) counters; per-instance episode termination is a warp
+// ballot over the instance's lane group. No tensor cores (nothing here is a contraction), no CPU fallback.
+//
+// Reference semantics restated per function (R/ = /root/reference/multiagent_rlrm/):
+//   env.step      R/environments/frozen_lake/ma_frozen_lake.py:96-154,189-215 ; office_world/ma_office.py:122-257
+//   RM step       R/multi_agent/reward_machine.py:45-59
+//   wrapper       R/multi_agent/wrappers/rm_environment_wrapper.py:43-107,122-183
+//   select        R/learning_algorithms/qlearning.py:112-143
+//   update        R/learning_algorithms/qlearning.py:70-110 ; qlearning_lambda.py:33-84
+//   driver loops  R/environments/frozen_lake/frozen_lake_main.py:336-376 ; office_world/office_main.py:1696-1749
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/rlrm_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameter block (passed by value)
+// ------------------------------------------------------------------------------------------------
+struct KP {
+  int env_kind, driver, algo;
+  int A, G, g_shift;  // agents, lane-group size (power of two >= A), log2(G)
+  int nQ, nEv, rm_final, n_qrm, max_steps, ncell;
+  int stochastic, slip_n;
+  unsigned long long slip_thr[3];
+  unsigned char slip_outcome[16];
+  int terminate_on_plants, terminate_hit_walls;
+  double hole_penalty, wall_penalty;
+  double lr, gamma, eps_end, eps_decay;
+  float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
+  int decay_on_reset, shared_q;
+  unsigned seed_lo, seed_hi, instance_offset;
+  long long S4;  // W*H*nQ*4 floats per table
+  // table blob in global memory and section offsets (bytes) inside it / inside the shared-memory copy
+  const unsigned char* blob;
+  int blob_bytes;
+  int off_next, off_flags, off_label, off_delta, off_rq, off_rcf, off_qrm, off_start;
+};
+
+struct Tab {
+  const unsigned short* next_cell;
+  const unsigned char* cell_flags;
+  const unsigned char* label;
+  const unsigned char* delta;
+  const double* rq;
+  const double* rcf;
+  const unsigned char* qrm_states;
+  const unsigned short* start_cell;
+};
+
+struct DState {  // rlrm_state_t by value
+  long long N;
+  unsigned long long* slot;
+  double* epsilon;
+  float* q;
+  float* e;
+  unsigned* visits;
+  double* ep_return;
+  rlrm_stats_t* stats;
+};
+
+struct DOut {  // rlrm_step_out_t by value
+  unsigned short *prev_cell, *cell;
+  unsigned char *prev_q, *q, *event, *executed;
+  double *renv, *rq, *reward;
+  unsigned char *env_term, *rm_term, *term, *trunc;
+};
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+__device__ __forceinline__ Tab stage_tables(const KP& p) {
+  // cooperative 16-byte copy of the (<= ~45 KB, typically 1-3 KB) table blob into shared memory
+  const uint4* src = reinterpret_cast<const uint4*>(p.blob);
+  uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+  for (int k = threadIdx.x; k < p.blob_bytes / 16; k += blockDim.x) dst[k] = __ldg(src + k);
+  __syncthreads();
+  Tab t;
+  t.next_cell = reinterpret_cast<const unsigned short*>(smem_raw + p.off_next);
+  t.cell_flags = smem_raw + p.off_flags;
+  t.label = smem_raw + p.off_label;
+  t.delta = smem_raw + p.off_delta;
+  t.rq = reinterpret_cast<const double*>(smem_raw + p.off_rq);
+  t.rcf = reinterpret_cast<const double*>(smem_raw + p.off_rcf);
+  t.qrm_states = smem_raw + p.off_qrm;
+  t.start_cell = reinterpret_cast<const unsigned short*>(smem_raw + p.off_start);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Random123): counter (t_lo, t_hi, instance, agent), key (seed_lo, seed_hi)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned w[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-agent pieces
+// ------------------------------------------------------------------------------------------------
+struct Slot {
+  unsigned cell, steps, time, rm, flags;
+};
+__device__ __forceinline__ Slot unpack_slot(unsigned long long w) {
+  Slot s;
+  s.cell = (unsigned)(w >> RLRM_SLOT_CELL_SHIFT) & 0xFFFFu;
+  s.steps = (unsigned)(w >> RLRM_SLOT_STEPS_SHIFT) & 0xFFFFu;
+  s.time = (unsigned)(w >> RLRM_SLOT_TIME_SHIFT) & 0xFFFFu;
+  s.rm = (unsigned)(w >> RLRM_SLOT_RMSTATE_SHIFT) & 0xFFu;
+  s.flags = (unsigned)(w >> RLRM_SLOT_FLAGS_SHIFT) & 0xFFu;
+  return s;
+}
+__device__ __forceinline__ unsigned long long pack_slot(const Slot& s) {
+  return ((unsigned long long)s.cell << RLRM_SLOT_CELL_SHIFT) | ((unsigned long long)s.steps << RLRM_SLOT_STEPS_SHIFT) |
+         ((unsigned long long)s.time << RLRM_SLOT_TIME_SHIFT) | ((unsigned long long)s.rm << RLRM_SLOT_RMSTATE_SHIFT) |
+         ((unsigned long long)s.flags << RLRM_SLOT_FLAGS_SHIFT);
+}
+
+// explore iff w0 / 2^32 < epsilon  <=>  w0 < ceil(epsilon * 2^32)   (w0 integer; the scaling by 2^32 is exact)
+__device__ __forceinline__ unsigned long long explore_threshold(double eps) {
+  if (!(eps > 0.0)) return 0ull;
+  if (eps >= 1.0) return 1ull << 32;
+  return (unsigned long long)ceil(eps * 4294967296.0);
+}
+
+// QLearning.choose_action / choose_action_greedy (qlearning.py:112-143)
+__device__ __forceinline__ int select_action(const float4& row, unsigned long long explore_thr, const unsigned w[4], bool best) {
+  float v[4] = {row.x, row.y, row.z, row.w};
+  int va = 0;
+#pragma unroll
+  for (int j = 1; j < 4; j++)
+    if (v[j] > v[va]) va = j;  // np.argmax: first maximum
+  if (best) return va;
+  if ((unsigned long long)w[0] < explore_thr) return (int)__umulhi(w[1], 4u);  // rng.choice(range(4))
+  float m = v[va];
+  int n = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) n += (v[j] == m);
+  int pick = (int)__umulhi(w[2], (unsigned)n);  // rng.choice(maxs)
+  int a = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (v[j] == m) {
+      if (pick == 0) a = j;
+      pick--;
+    }
+  }
+  return a;
+}
+
+__device__ __forceinline__ int slip_outcome(const KP& p, int intended, unsigned k) {
+  int idx = 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) idx += (j + 1 < p.slip_n) && ((unsigned long long)k >= p.slip_thr[j]);
+  return p.slip_outcome[intended * 4 + idx];
+}
+
+struct Rec {
+  unsigned prev_cell, cell, prev_q, q, event, executed;
+  bool env_term, rm_term, term, trunc, stepped;
+  double renv, rq, reward;
+};
+
+// env.step + check_terminations + RewardMachine.step + wrapper merge for ONE agent. Every quantity an agent needs is
+// its own (the shared env.timestep is replicated per agent), so lanes never exchange data here.
+template <int ENV>
+__device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, int action, unsigned w3, bool with_rm, Rec& r) {
+  r.prev_cell = s.cell;
+  r.executed = 5;
+  r.stepped = false;
+  r.renv = 0.0;
+  r.rq = 0.0;
+  const bool active = (s.flags & RLRM_FLAG_ACTIVE) != 0;
+  if (ENV == RLRM_ENV_FROZEN_LAKE) {
+    const bool rm_done = p.rm_final >= 0 && (int)s.rm == p.rm_final;  // ma_frozen_lake.py:107-115
+    if (active && !rm_done) {
+      int ex = action;
+      if (p.stochastic) ex = slip_outcome(p, action, w3);
+      if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
+      if (tb.cell_flags[s.cell] & 1) {  // holes_in_the_ice
+        s.flags |= RLRM_FLAG_FAIL;
+        r.renv = p.hole_penalty;
+      }
+      s.steps++;
+      r.executed = ex;
+      r.stepped = true;
+    }
+  } else {
+    if (active) {  // ma_office.py:143-186
+      int ex = action;
+      double wall_pen = 0.0;
+      if (tb.next_cell[s.cell * 4 + action] == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
+        if (p.terminate_hit_walls) s.flags |= RLRM_FLAG_FAIL;
+        wall_pen = p.wall_penalty;
+        ex = RLRM_ACTION_WAIT;
+      }
+      if (p.stochastic && ex != RLRM_ACTION_WAIT) ex = slip_outcome(p, ex, w3);
+      if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
+      double plant = 0.0;
+      if (tb.cell_flags[s.cell] & 1) {  // plants_in_the_office
+        if (p.terminate_on_plants) s.flags |= RLRM_FLAG_FAIL;
+        plant = p.hole_penalty;
+      }
+      r.renv = __dadd_rn(wall_pen, plant);
+      s.steps++;
+      r.executed = ex;
+      r.stepped = true;
+    }
+  }
+  r.cell = s.cell;
+  s.time++;
+  const bool fail = (s.flags & RLRM_FLAG_FAIL) != 0;
+  if (ENV == RLRM_ENV_FROZEN_LAKE) {  // ma_frozen_lake.py:189-215 (RM state as of BEFORE this step's RM update)
+    r.trunc = ((int)s.steps > p.max_steps) || ((int)s.time > p.max_steps);
+    r.env_term = r.trunc || (p.rm_final >= 0 && (int)s.rm == p.rm_final) || fail;
+    if (r.env_term) s.flags &= ~RLRM_FLAG_ACTIVE;
+  } else {  // ma_office.py:240-257
+    r.trunc = (int)s.time > p.max_steps;
+    r.env_term = fail;
+    if (r.env_term || r.trunc) s.flags &= ~RLRM_FLAG_ACTIVE;
+  }
+  // rm_environment_wrapper.py:57-107
+  r.prev_q = s.rm;
+  r.event = tb.label[s.cell];
+  r.rm_term = false;
+  if (with_rm) {
+    const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+    const unsigned d = tb.delta[s.rm * (p.nEv + 1) + col];
+    if (d != RLRM_NO_TRANSITION) {
+      r.rq = tb.rq[s.rm * (p.nEv + 1) + col];
+      s.rm = d;
+    }
+    r.rm_term = p.rm_final >= 0 && (int)s.rm == p.rm_final;
+  }
+  r.q = s.rm;
+  r.reward = __dadd_rn(r.renv, r.rq);
+  r.term = r.env_term || r.rm_term;
+  s.flags &= ~(RLRM_FLAG_DONE | RLRM_FLAG_TRUNC | RLRM_FLAG_FIRST);
+  if (r.term) s.flags |= RLRM_FLAG_DONE;
+  if (r.trunc) s.flags |= RLRM_FLAG_TRUNC;
+}
+
+__device__ __forceinline__ void set_component(float4& v, unsigned c, float x) {
+  if (c == 0) v.x = x;
+  else if (c == 1) v.y = x;
+  else if (c == 2) v.z = x;
+  else v.w = x;
+}
+
+__device__ __forceinline__ float row_max(const float4& v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
+
+// update_q (qlearning.py:70-79) in the float32 arithmetic numpy performs on a float32 table: weak Python scalars are
+// rounded to float32 first, every operation rounds separately (no FMA contraction).
+__device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, unsigned s, int a, double r, unsigned sn, bool terminated) {
+  const float cur = Q[s * 4 + a];
+  const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
+  const float mf = __fmul_rn(terminated ? 0.0f : 1.0f, row_max(nrow));
+  const float inner = __fadd_rn(__double2float_rn(r), __fmul_rn(p.gamma_f, mf));
+  float out;
+  if (p.lr < 0.0) {  // lr = 1/visits is an np.float64: the outer expression is evaluated in double
+    const unsigned v = V[s * 4 + a] + 1;
+    V[s * 4 + a] = v;
+    const double lr = __ddiv_rn(1.0, (double)v);
+    out = __double2float_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, lr), (double)cur), __dmul_rn(lr, (double)inner)));
+  } else {
+    if (V) V[s * 4 + a] += 1;
+    out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+  }
+  Q[s * 4 + a] = out;
+}
+
+// QL / QRM update of one agent (agent_rl.py:117-192 -> qlearning.py:41-110; QRM experiences rm_environment_wrapper.py:122-183)
+template <int ALGO>
+__device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, float* Q, unsigned* V, unsigned obs_cell, int action,
+                                             bool term_arg, const Rec& r) {
+  if (ALGO == RLRM_ALGO_QRM) {
+    const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+    for (int j = 0; j < p.n_qrm; j++) {
+      const unsigned u = tb.qrm_states[j];
+      const unsigned d = tb.delta[u * (p.nEv + 1) + col];
+      const unsigned un = d == RLRM_NO_TRANSITION ? u : d;
+      const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
+      const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
+      update_q(p, Q, V, r.prev_cell * p.nQ + u, action, __dadd_rn(r.renv, ru), r.cell * p.nQ + un, done);
+    }
+  } else {
+    update_q(p, Q, V, obs_cell * p.nQ + r.prev_q, action, r.reward, r.cell * p.nQ + r.q, term_arg);
+  }
+}
+
+__device__ __forceinline__ void reset_slot(const KP& p, const Tab& tb, int a, Slot& s, double& eps) {
+  s.cell = tb.start_cell[a];
+  s.steps = 0;
+  s.time = 0;
+  s.rm = 0;  // the initial RM state has index 0 (reward_machine.py:32-36)
+  s.flags = RLRM_FLAG_ACTIVE | RLRM_FLAG_FIRST;
+  if (p.decay_on_reset) eps = fmax(p.eps_end, __dmul_rn(eps, p.eps_decay));  // learn_done_episode (qlearning.py:153-155)
+}
+
+__device__ __forceinline__ size_t table_base(const KP& p, long long i, int a) {
+  return (size_t)(p.shared_q ? (long long)a : i * p.A + a) * (size_t)p.S4;
+}
+
+// ------------------------------------------------------------------------------------------------
+// unfused kernels (the reference's call-by-call API; also the parity path with injected draws)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsigned char* mask) {
+  Tab tb = stage_tables(p);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  if (mask && !mask[i]) return;
+  Slot s;
+  double eps = st.epsilon[k];
+  reset_slot(p, tb, a, s, eps);
+  st.slot[k] = pack_slot(s);
+  st.epsilon[k] = eps;
+  if (st.ep_return) st.ep_return[k] = 0.0;
+}
+
+// Q(lambda): reset_e_table for the masked instances (ma_frozen_lake.py:80-81 ; ma_office.py:101-102)
+__global__ void __launch_bounds__(256) clear_traces_kernel(KP p, DState st, const unsigned char* mask) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of one slot's table
+  const long long per = p.S4 / 4;
+  if (g >= st.N * p.A * per) return;
+  const long long slot = g / per;
+  if (mask && !mask[slot / p.A]) return;
+  reinterpret_cast<float4*>(st.e)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) select_kernel(KP p, DState st, const unsigned* draws, unsigned long long t, int best,
+                                                    unsigned char* actions_out) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  const Slot s = unpack_slot(st.slot[k]);
+  const float* Q = st.q + table_base(p, i, a);
+  const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+  unsigned w[4];
+  if (draws) {
+    const uint4 d = reinterpret_cast<const uint4*>(draws)[k];
+    w[0] = d.x; w[1] = d.y; w[2] = d.z; w[3] = d.w;
+  } else {
+    philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+  }
+  actions_out[k] = (unsigned char)select_action(row, explore_threshold(st.epsilon[k]), w, best != 0);
+}
+
+__device__ __forceinline__ void store_rec(const DOut& o, long long k, const Rec& r) {
+  if (o.prev_cell) o.prev_cell[k] = (unsigned short)r.prev_cell;
+  if (o.cell) o.cell[k] = (unsigned short)r.cell;
+  if (o.prev_q) o.prev_q[k] = (unsigned char)r.prev_q;
+  if (o.q) o.q[k] = (unsigned char)r.q;
+  if (o.event) o.event[k] = (unsigned char)r.event;
+  if (o.executed) o.executed[k] = (unsigned char)r.executed;
+  if (o.renv) o.renv[k] = r.renv;
+  if (o.rq) o.rq[k] = r.rq;
+  if (o.reward) o.reward[k] = r.reward;
+  if (o.env_term) o.env_term[k] = r.env_term;
+  if (o.rm_term) o.rm_term[k] = r.rm_term;
+  if (o.term) o.term[k] = r.term;
+  if (o.trunc) o.trunc[k] = r.trunc;
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(256) step_kernel(KP p, DState st, const unsigned char* actions, const unsigned* draws,
+                                                  unsigned long long t, int with_rm, DOut out) {
+  Tab tb = stage_tables(p);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  Slot s = unpack_slot(st.slot[k]);
+  unsigned w3 = 0;
+  if (p.stochastic) {
+    if (draws) {
+      w3 = draws[k * 4 + 3];
+    } else {
+      unsigned w[4];
+      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      w3 = w[3];
+    }
+  }
+  Rec r;
+  agent_step<ENV>(p, tb, s, actions[k], w3, with_rm != 0, r);
+  st.slot[k] = pack_slot(s);
+  store_rec(out, k, r);
+}
+
+// RewardMachine.step on explicit (state, position) pairs (reward_machine.py:45-59)
+__global__ void __launch_bounds__(256) rm_step_kernel(KP p, long long n, unsigned char* q, const unsigned short* cell,
+                                                     unsigned char* event_out, double* reward_out) {
+  Tab tb = stage_tables(p);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const unsigned ev = tb.label[cell[k]];
+  const int col = ev == RLRM_EVENT_NONE ? p.nEv : (int)ev;
+  const unsigned cur = q[k];
+  const unsigned d = tb.delta[cur * (p.nEv + 1) + col];
+  double r = 0.0;
+  if (d != RLRM_NO_TRANSITION) {
+    r = tb.rq[cur * (p.nEv + 1) + col];
+    q[k] = (unsigned char)d;
+  }
+  if (event_out) event_out[k] = (unsigned char)ev;
+  if (reward_out) reward_out[k] = r;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(256) update_kernel(KP p, DState st, const unsigned short* obs_cell, const unsigned char* actions,
+                                                    const unsigned char* term_arg, DOut o) {
+  Tab tb = stage_tables(p);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  Rec r;
+  r.prev_cell = o.prev_cell[k]; r.cell = o.cell[k]; r.prev_q = o.prev_q[k]; r.q = o.q[k]; r.event = o.event[k];
+  r.env_term = o.env_term[k] != 0; r.renv = o.renv[k]; r.reward = o.reward[k];
+  const size_t base = table_base(p, i, a);
+  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, obs_cell[k], actions[k], term_arg[k] != 0, r);
+}
+
+// QLearningLambda.update (qlearning_lambda.py:33-84), dense sweep exactly as written: one block per (instance, agent).
+// q += (lr*td) * e ; e = terminated ? 0 : e * (gamma*lambda), with e[s,a] replaced by 1 first.
+__device__ __forceinline__ void qlambda_sweep(const KP& p, float* Q, float* E, unsigned s, int a, double reward, unsigned sn,
+                                              bool terminated, int tid, int nthreads) {
+  // every thread reads the two scalars before anyone writes
+  const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
+  const float qsa = Q[s * 4 + a];
+  __syncthreads();
+  const double best = terminated ? 0.0 : (double)row_max(nrow);
+  const float td = __fsub_rn(__double2float_rn(__dadd_rn(reward, __dmul_rn(p.gamma, best))), qsa);
+  const float c = __fmul_rn(p.lr_f, td);
+  const unsigned hot = s * 4 + a;
+  float4* Q4 = reinterpret_cast<float4*>(Q);
+  float4* E4 = reinterpret_cast<float4*>(E);
+  for (long long j = tid; j < p.S4 / 4; j += nthreads) {
+    float4 e = E4[j], q = Q4[j];
+    if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);  // replacing trace
+    q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
+    q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
+    q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
+    q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+    if (terminated) {
+      e = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {  // next_action defaults to argmax Q[s'] => greedy => decay (qlearning_lambda.py:71-81)
+      e.x = __fmul_rn(e.x, p.trace_decay_f);
+      e.y = __fmul_rn(e.y, p.trace_decay_f);
+      e.z = __fmul_rn(e.z, p.trace_decay_f);
+      e.w = __fmul_rn(e.w, p.trace_decay_f);
+    }
+    Q4[j] = q;
+    E4[j] = e;
+  }
+}
+
+__global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, const unsigned short* obs_cell,
+                                                            const unsigned char* actions, const unsigned char* term_arg, DOut o) {
+  const long long k = blockIdx.x;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  const size_t base = table_base(p, i, a);
+  if (st.visits && threadIdx.x == 0) st.visits[base + (size_t)(obs_cell[k] * p.nQ + o.prev_q[k]) * 4 + actions[k]] += 1;
+  qlambda_sweep(p, st.q + base, st.e + base, obs_cell[k] * p.nQ + o.prev_q[k], actions[k], o.reward[k],
+                o.cell[k] * p.nQ + o.q[k], term_arg[k] != 0, threadIdx.x, blockDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused persistent kernel: n_iters lockstep iterations, state in registers
+// ------------------------------------------------------------------------------------------------
+#define TRAIN_BLOCK 128
+
+template <int ENV, int ALGO>
+__global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                           unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0;
+  float* Q = nullptr;
+  unsigned* V = nullptr;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  double return_sum = 0.0;
+  float last_return = 0.f;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    const size_t base = table_base(p, i, a);
+    Q = st.q + base;
+    V = st.visits ? st.visits + base : nullptr;
+  }
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    Rec r;
+    int action = 0;
+    if (valid) {
+      unsigned w[4];
+      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      // every agent selects on every iteration, finished ones included (frozen_lake_main.py:350-352)
+      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      action = select_action(row, explore_thr, w, learn == 0);
+      const unsigned before = s.cell;
+      const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      if (learn) {
+        // FrozenLake driver: on an episode's first iteration `states` still aliases agent.state, so update_policy
+        // receives the NEW position as `state` (frozen_lake_main.py:337,359 ; office_main.py:1700 deep-copies)
+        const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+        const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+        agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r);
+      }
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      active_steps += r.stepped ? 1u : 0u;
+      if (trace)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    // episode over when all agents terminated, or all truncated (frozen_lake_main.py:345,375 ; office_main.py:1748)
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (valid && over) {
+      episodes++;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, a, s, eps);  // next episode starts with rm_env.reset (frozen_lake_main.py:337)
+      explore_thr = explore_threshold(eps);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// Q(lambda) fused: one block per instance, one warp per agent; the dense trace sweep is cooperative over the warp.
+template <int ENV>
+__global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                           unsigned* trace) {
+  Tab tb = stage_tables(p);
+  __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
+  const long long i = blockIdx.x;
+  const int a = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long k = i * p.A + a;
+  Slot s = unpack_slot(st.slot[k]);
+  double eps = st.epsilon[k];
+  double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
+  const size_t base = table_base(p, i, a);
+  float* Q = st.q + base;
+  float* E = st.e + base;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  bool had_episode = false;
+  rlrm_stats_t z;
+  if (st.stats) z = st.stats[k];
+  double return_sum_add = st.stats ? z.return_sum : 0.0;
+  unsigned long long explore_thr = explore_threshold(eps);
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    unsigned w[4];
+    philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+    __syncwarp();
+    const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+    const int action = select_action(row, explore_thr, w, learn == 0);
+    const unsigned before = s.cell;
+    const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+    Rec r;
+    agent_step<ENV>(p, tb, s, action, w[3], true, r);  // all 32 lanes compute the same scalars
+    if (learn) {
+      const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+      const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+      // warp-cooperative dense sweep (the __syncthreads inside qlambda_sweep is replaced by __syncwarp here)
+      const unsigned sidx = obs * p.nQ + r.prev_q, snidx = r.cell * p.nQ + r.q;
+      const float4 nrow = *reinterpret_cast<const float4*>(Q + snidx * 4);
+      const float qsa = Q[sidx * 4 + action];
+      __syncwarp();
+      const double best = term_arg ? 0.0 : (double)row_max(nrow);
+      const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
+      const float c = __fmul_rn(p.lr_f, td);
+      const unsigned hot = sidx * 4 + action;
+      float4* Q4 = reinterpret_cast<float4*>(Q);
+      float4* E4 = reinterpret_cast<float4*>(E);
+      for (long long j = lane; j < p.S4 / 4; j += 32) {
+        float4 e = E4[j], q = Q4[j];
+        if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);
+        q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
+        q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
+        q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
+        q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+        if (term_arg) {
+          e = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          e.x = __fmul_rn(e.x, p.trace_decay_f);
+          e.y = __fmul_rn(e.y, p.trace_decay_f);
+          e.z = __fmul_rn(e.z, p.trace_decay_f);
+          e.w = __fmul_rn(e.w, p.trace_decay_f);
+        }
+        Q4[j] = q;
+        E4[j] = e;
+      }
+      __syncwarp();
+    }
+    ep_ret = __dadd_rn(ep_ret, r.reward);
+    active_steps += r.stepped ? 1u : 0u;
+    if (trace && lane == 0)
+      trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                           ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                           ((unsigned)r.stepped << 23);
+    if (lane == 0) {
+      sh_term[a] = r.term;
+      sh_trunc[a] = r.trunc;
+    }
+    __syncthreads();
+    bool all_term = true, all_trunc = true;
+    for (int b = 0; b < p.A; b++) {
+      all_term = all_term && sh_term[b];
+      all_trunc = all_trunc && sh_trunc[b];
+    }
+    __syncthreads();
+    if (all_term || all_trunc) {
+      episodes++;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum_add = __dadd_rn(return_sum_add, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, a, s, eps);
+      explore_thr = explore_threshold(eps);
+      // reset_e_table (ma_office.py:101-102)
+      float4* E4 = reinterpret_cast<float4*>(E);
+      for (long long j = lane; j < p.S4 / 4; j += 32) E4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum_add;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: handle + C ABI
+// ------------------------------------------------------------------------------------------------
+struct rlrm_handle {
+  KP kp;
+  rlrm_config_t cfg;
+  int device;
+  unsigned char* d_blob;
+  int smem_bytes;
+  long long launches;
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return fail(RLRM_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+static int align16(int x) { return (x + 15) & ~15; }
+
+extern "C" int rlrm_abi_version(void) { return RLRM_ABI_VERSION; }
+extern "C" const char* rlrm_last_error(void) { return g_err; }
+extern "C" int rlrm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static void fill_learner(KP& kp, double lr, double gamma, double lambd) {
+  kp.lr = lr;
+  kp.gamma = gamma;
+  kp.lr_f = (float)lr;
+  kp.one_minus_lr_f = (float)(1.0 - lr);
+  kp.gamma_f = (float)gamma;
+  kp.trace_decay_f = (float)(gamma * lambd);
+}
+
+extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int device, rlrm_handle_t** out) {
+  if (!cfg || !tb || !out) return fail(RLRM_ERR_ARG, "null argument");
+  if (cfg->abi_version != RLRM_ABI_VERSION) return fail(RLRM_ERR_ARG, "abi_version mismatch");
+  const int ncell = cfg->width * cfg->height;
+  if (ncell <= 0 || ncell > RLRM_MAX_CELLS) return fail(RLRM_ERR_ARG, "width*height out of range");
+  if (cfg->n_agents < 1 || cfg->n_agents > RLRM_MAX_AGENTS) return fail(RLRM_ERR_ARG, "n_agents out of range");
+  if (cfg->n_rm_states < 1 || cfg->n_rm_states > RLRM_MAX_RM_STATES) return fail(RLRM_ERR_ARG, "n_rm_states out of range");
+  if (cfg->n_events < 0 || cfg->n_events > RLRM_MAX_EVENTS) return fail(RLRM_ERR_ARG, "n_events out of range");
+  if (cfg->n_qrm_states < 0 || cfg->n_qrm_states > RLRM_MAX_RM_STATES) return fail(RLRM_ERR_ARG, "n_qrm_states out of range");
+  if (cfg->slip_n < 1 || cfg->slip_n > 4) return fail(RLRM_ERR_ARG, "slip_n out of range");
+  if (cfg->algo < 0 || cfg->algo > RLRM_ALGO_QLAMBDA) return fail(RLRM_ERR_ARG, "unknown algo");
+  if (cfg->env_kind != RLRM_ENV_FROZEN_LAKE && cfg->env_kind != RLRM_ENV_OFFICE_WORLD) return fail(RLRM_ERR_ARG, "unknown env_kind");
+  if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->learning_rate < 0)
+    return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) with learning_rate=None is not supported");
+  if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->shared_q) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) with a shared table is not supported");
+  if (!tb->next_cell || !tb->cell_flags || !tb->label || !tb->delta || !tb->rq || !tb->rcf || !tb->start_cell)
+    return fail(RLRM_ERR_ARG, "null table");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(RLRM_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(RLRM_ERR_ARG, "device out of range");
+  CUDA_TRY(cudaSetDevice(device));
+
+  rlrm_handle* h = new (std::nothrow) rlrm_handle();
+  if (!h) return fail(RLRM_ERR_ARG, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  KP& kp = h->kp;
+  kp.env_kind = cfg->env_kind; kp.driver = cfg->driver; kp.algo = cfg->algo;
+  kp.A = cfg->n_agents;
+  kp.G = 1; kp.g_shift = 0;
+  while (kp.G < kp.A) { kp.G <<= 1; kp.g_shift++; }
+  kp.nQ = cfg->n_rm_states; kp.nEv = cfg->n_events; kp.rm_final = cfg->rm_final; kp.n_qrm = cfg->n_qrm_states;
+  kp.max_steps = cfg->max_steps; kp.ncell = ncell;
+  kp.stochastic = cfg->stochastic; kp.slip_n = cfg->slip_n;
+  for (int j = 0; j < 3; j++) kp.slip_thr[j] = cfg->slip_thr[j];
+  for (int a = 0; a < 4; a++)
+    for (int j = 0; j < 4; j++) kp.slip_outcome[a * 4 + j] = cfg->slip_outcome[a][j];
+  kp.terminate_on_plants = cfg->terminate_on_plants; kp.terminate_hit_walls = cfg->terminate_hit_walls;
+  kp.hole_penalty = cfg->hole_penalty; kp.wall_penalty = cfg->wall_penalty;
+  kp.eps_end = cfg->epsilon_end; kp.eps_decay = cfg->epsilon_decay;
+  fill_learner(kp, cfg->learning_rate, cfg->gamma, cfg->lambd);
+  kp.decay_on_reset = cfg->decay_on_reset; kp.shared_q = cfg->shared_q;
+  kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;
+  kp.S4 = (long long)ncell * kp.nQ * 4;
+
+  // pack the tables into one 16-byte aligned blob
+  const int nd = kp.nQ * (kp.nEv + 1);
+  int off = 0;
+  kp.off_rq = off; off = align16(off + nd * 8);
+  kp.off_rcf = off; off = align16(off + nd * 8);
+  kp.off_next = off; off = align16(off + ncell * 4 * 2);
+  kp.off_start = off; off = align16(off + RLRM_MAX_AGENTS * 2);
+  kp.off_flags = off; off = align16(off + ncell);
+  kp.off_label = off; off = align16(off + ncell);
+  kp.off_delta = off; off = align16(off + nd);
+  kp.off_qrm = off; off = align16(off + RLRM_MAX_RM_STATES);
+  kp.blob_bytes = off;
+  unsigned char* host = new (std::nothrow) unsigned char[off];
+  if (!host) { delete h; return fail(RLRM_ERR_ARG, "out of host memory"); }
+  memset(host, 0, off);
+  memcpy(host + kp.off_rq, tb->rq, (size_t)nd * 8);
+  memcpy(host + kp.off_rcf, tb->rcf, (size_t)nd * 8);
+  memcpy(host + kp.off_next, tb->next_cell, (size_t)ncell * 8);
+  memcpy(host + kp.off_start, tb->start_cell, (size_t)kp.A * 2);
+  memcpy(host + kp.off_flags, tb->cell_flags, ncell);
+  memcpy(host + kp.off_label, tb->label, ncell);
+  memcpy(host + kp.off_delta, tb->delta, nd);
+  if (kp.n_qrm > 0 && tb->qrm_states) memcpy(host + kp.off_qrm, tb->qrm_states, kp.n_qrm);
+  cudaError_t e = cudaMalloc(&h->d_blob, off);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, host, off, cudaMemcpyHostToDevice);
+  delete[] host;
+  if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
+  kp.blob = h->d_blob;
+  h->smem_bytes = off;
+  *out = h;
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_destroy(rlrm_handle_t* h) {
+  if (!h) return RLRM_OK;
+  cudaSetDevice(h->device);
+  if (h->d_blob) cudaFree(h->d_blob);
+  delete h;
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double gamma, double lambd) {
+  if (!h) return fail(RLRM_ERR_ARG, "null handle");
+  if (h->cfg.algo == RLRM_ALGO_QLAMBDA && learning_rate < 0) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) needs a fixed learning rate");
+  h->cfg.learning_rate = learning_rate; h->cfg.gamma = gamma; h->cfg.lambd = lambd;
+  fill_learner(h->kp, learning_rate, gamma, lambd);
+  return RLRM_OK;
+}
+
+extern "C" int64_t rlrm_launch_count(const rlrm_handle_t* h) { return h ? (int64_t)h->launches : 0; }
+
+static DState dstate(const rlrm_state_t* st) {
+  DState d;
+  d.N = st->n_instances; d.slot = (unsigned long long*)st->slot; d.epsilon = st->epsilon; d.q = st->q; d.e = st->e;
+  d.visits = st->visits; d.ep_return = st->ep_return; d.stats = st->stats;
+  return d;
+}
+static DOut dout(const rlrm_step_out_t* o) {
+  DOut d;
+  memset(&d, 0, sizeof(d));
+  if (o) {
+    d.prev_cell = o->prev_cell; d.cell = o->cell; d.prev_q = o->prev_q; d.q = o->q; d.event = o->event; d.executed = o->executed;
+    d.renv = o->renv; d.rq = o->rq; d.reward = o->reward; d.env_term = o->env_term; d.rm_term = o->rm_term; d.term = o->term;
+    d.trunc = o->trunc;
+  }
+  return d;
+}
+
+static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need_q) {
+  if (!h || !st) return fail(RLRM_ERR_ARG, "null handle/state");
+  if (st->n_instances <= 0) return fail(RLRM_ERR_ARG, "n_instances must be positive");
+  if (!st->slot || !st->epsilon) return fail(RLRM_ERR_ARG, "state.slot / state.epsilon are required");
+  if (need_q && !st->q) return fail(RLRM_ERR_ARG, "state.q is required");
+  if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e");
+  if (need_q && h->cfg.learning_rate < 0 && !st->visits) return fail(RLRM_ERR_ARG, "learning_rate=None needs state.visits");
+  return RLRM_OK;
+}
+
+#define LAUNCH_CHECK(h)                                                                     \
+  do {                                                                                      \
+    (h)->launches++;                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) return fail(RLRM_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+static unsigned blocks_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" int rlrm_reset(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, void* stream) {
+  int rc = check_state(h, st, false);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = st->n_instances * h->kp.A;
+  reset_kernel<<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), mask);
+  LAUNCH_CHECK(h);
+  if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->e) {
+    clear_traces_kernel<<<blocks_for(n * (h->kp.S4 / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask);
+    LAUNCH_CHECK(h);
+  }
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_select_action(rlrm_handle_t* h, const rlrm_state_t* st, const uint32_t* draws, uint64_t t, int best,
+                                  uint8_t* actions_out, void* stream) {
+  int rc = check_state(h, st, true);
+  if (rc) return rc;
+  if (!actions_out) return fail(RLRM_ERR_ARG, "actions_out is null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = st->n_instances * h->kp.A;
+  select_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_step(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* actions, const uint32_t* draws, uint64_t t,
+                         int with_rm, const rlrm_step_out_t* out, void* stream) {
+  int rc = check_state(h, st, false);
+  if (rc) return rc;
+  if (!actions) return fail(RLRM_ERR_ARG, "actions is null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = st->n_instances * h->kp.A;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE)
+    step_kernel<RLRM_ENV_FROZEN_LAKE><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), actions, draws, t, with_rm, dout(out));
+  else
+    step_kernel<RLRM_ENV_OFFICE_WORLD><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), actions, draws, t, with_rm, dout(out));
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_rm_step(rlrm_handle_t* h, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
+                            double* reward_out, void* stream) {
+  if (!h || !q || !cell) return fail(RLRM_ERR_ARG, "null argument");
+  if (n_slots <= 0) return RLRM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rm_step_kernel<<<blocks_for(n_slots, 256), 256, h->smem_bytes, (cudaStream_t)stream>>>(h->kp, n_slots, q, cell, event_out, reward_out);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_cell, const uint8_t* actions,
+                           const uint8_t* term_arg, const rlrm_step_out_t* out, void* stream) {
+  int rc = check_state(h, st, true);
+  if (rc) return rc;
+  if (!obs_cell || !actions || !term_arg || !out) return fail(RLRM_ERR_ARG, "null argument");
+  if (!out->prev_cell || !out->cell || !out->prev_q || !out->q || !out->event || !out->env_term || !out->renv || !out->reward)
+    return fail(RLRM_ERR_ARG, "step record is missing fields the update needs");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = st->n_instances * h->kp.A;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.algo == RLRM_ALGO_QLAMBDA)
+    update_qlambda_kernel<<<(unsigned)n, 256, 0, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
+  else if (h->kp.algo == RLRM_ALGO_QRM)
+    update_kernel<RLRM_ALGO_QRM><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
+  else
+    update_kernel<RLRM_ALGO_QL><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+template <int ENV>
+static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int n_iters, int learn, uint32_t* trace, cudaStream_t s) {
+  const KP& kp = h->kp;
+  if (kp.algo == RLRM_ALGO_QLAMBDA) {
+    train_qlambda_kernel<ENV><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+  } else {
+    const long long threads = st->n_instances * kp.G;
+    const unsigned grid = blocks_for(threads, TRAIN_BLOCK);
+    if (kp.algo == RLRM_ALGO_QRM)
+      train_kernel<ENV, RLRM_ALGO_QRM><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    else
+      train_kernel<ENV, RLRM_ALGO_QL><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+  }
+}
+
+extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn, uint32_t* trace,
+                          void* stream) {
+  int rc = check_state(h, st, true);
+  if (rc) return rc;
+  if (n_iters < 0) return fail(RLRM_ERR_ARG, "n_iters < 0");
+  if (n_iters == 0) return RLRM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t0, n_iters, learn, trace, s);
+  else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t0, n_iters, learn, trace, s);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
+                               const uint64_t* host_slot, const double* host_epsilon, rlrm_stats_t* host_stats, void* stream) {
+  int rc = check_state(h, st, true);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)st->n_instances * h->kp.A;
+  if (host_slot) CUDA_TRY(cudaMemcpyAsync(st->slot, host_slot, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(st->epsilon, host_epsilon, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  rc = rlrm_train(h, st, t0, n_iters, learn, nullptr, stream);
+  if (rc) return rc;
+  if (host_stats) {
+    if (!st->stats) return fail(RLRM_ERR_ARG, "host_stats requested but state.stats is null");
+    CUDA_TRY(cudaMemcpyAsync(host_stats, st->stats, n * sizeof(rlrm_stats_t), cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return RLRM_OK;
+}

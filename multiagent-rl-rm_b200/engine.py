@@ -1,0 +1,174 @@
+"""Batched engine: torch-owned device state + thin calls into the C ABI (include/rlrm_b200.h).
+
+This is the batched counterpart of the object graph the reference drivers build
+(frozen_lake_main.py:200-295 / office_main.py:400-717): N independent environment instances x A agents, each
+agent with its own Reward-Machine state, learner table and epsilon. torch is used for memory, streams and
+(in dist.py) torch.distributed only; every computation below is a kernel of csrc/rlrm_b200.cu.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _abi as abi
+from ._lib import check, load
+from .tables import Compiled
+
+_TORCH_DT = {"uint16": torch.int16, "uint8": torch.uint8, "float64": torch.float64}
+
+STATS_DTYPE = np.dtype([("active_steps", "<u8"), ("episodes", "<u4"), ("successes", "<u4"), ("return_sum", "<f8"),
+                        ("last_return", "<f4"), ("last_length", "<u4")])
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    def __init__(self, compiled: Compiled, n_instances: int, device="cuda:0", track_visits: bool = False,
+                 with_stats: bool = True):
+        self.L = load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("multiagent-rl-rm_b200 needs a CUDA device (no CPU fallback)")
+        self.c = compiled
+        self.cfg = compiled.config
+        self.device = torch.device(device)
+        self.N, self.A, self.S = int(n_instances), compiled.n_agents, compiled.state_space
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._tables = compiled.tables_struct()
+        h = C.c_void_p()
+        check(self.L.rlrm_create(C.byref(self.cfg), C.byref(self._tables), dev_index, C.byref(h)))
+        self.h = h
+        n_slots = self.N * self.A
+        n_tab = self.A if self.cfg.shared_q else n_slots
+        d = self.device
+        self.slot = torch.zeros(n_slots, dtype=torch.int64, device=d)
+        self.epsilon = torch.full((n_slots,), float(self.cfg.epsilon_start), dtype=torch.float64, device=d)
+        self.q = torch.full((n_tab, self.S, 4), float(compiled.scenario.q_init), dtype=torch.float32, device=d)
+        self.e = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if self.cfg.algo == abi.ALGO_QLAMBDA else None
+        need_visits = track_visits or self.cfg.learning_rate < 0
+        self.visits = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if need_visits else None
+        self.ep_return = torch.zeros(n_slots, dtype=torch.float64, device=d)
+        self.stats = torch.zeros((n_slots, 32), dtype=torch.uint8, device=d) if with_stats else None
+        self.state = abi.State(self.N, _ptr(self.slot), _ptr(self.epsilon), _ptr(self.q), _ptr(self.e), _ptr(self.visits),
+                               _ptr(self.ep_return), _ptr(self.stats))
+        self.t = 0  # lockstep iteration counter (Philox counter word)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.rlrm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_learner(self, learning_rate, gamma, lambd=0.0):
+        check(self.L.rlrm_set_learner(self.h, -1.0 if learning_rate is None else float(learning_rate), float(gamma), float(lambd)))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.rlrm_launch_count(self.h))
+
+    # -- C ABI calls -----------------------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None):
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self.L.rlrm_reset(self.h, C.byref(self.state), _ptr(mask), self._stream()))
+
+    def select_action(self, t: Optional[int] = None, draws: Optional[torch.Tensor] = None, best: bool = False) -> torch.Tensor:
+        out = torch.empty(self.N * self.A, dtype=torch.uint8, device=self.device)
+        if draws is not None:
+            draws = draws.to(device=self.device).contiguous()
+        check(self.L.rlrm_select_action(self.h, C.byref(self.state), _ptr(draws), self.t if t is None else t, int(best),
+                                        _ptr(out), self._stream()))
+        return out.view(self.N, self.A)
+
+    def new_record(self) -> Dict[str, torch.Tensor]:
+        return {k: torch.zeros(self.N * self.A, dtype=_TORCH_DT[v], device=self.device) for k, v in abi.STEP_OUT_FIELDS.items()}
+
+    def step(self, actions: torch.Tensor, t: Optional[int] = None, draws: Optional[torch.Tensor] = None, with_rm: bool = True,
+             rec: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        if draws is not None:
+            draws = draws.to(device=self.device).contiguous()
+        rec = rec or self.new_record()
+        so = abi.StepOut(*[_ptr(rec[k]) for k in abi.STEP_OUT_FIELDS])
+        check(self.L.rlrm_step(self.h, C.byref(self.state), _ptr(actions), _ptr(draws), self.t if t is None else t,
+                               int(with_rm), C.byref(so), self._stream()))
+        return rec
+
+    def rm_step(self, q: torch.Tensor, cell: torch.Tensor):
+        q = q.to(device=self.device, dtype=torch.uint8).contiguous().clone()
+        cell = cell.to(device=self.device, dtype=torch.int16).contiguous()
+        ev = torch.empty_like(q)
+        r = torch.empty(q.numel(), dtype=torch.float64, device=self.device)
+        check(self.L.rlrm_rm_step(self.h, q.numel(), _ptr(q), _ptr(cell), _ptr(ev), _ptr(r), self._stream()))
+        return q, ev, r
+
+    def update(self, obs_cell: torch.Tensor, actions: torch.Tensor, term_arg: torch.Tensor, rec: Dict[str, torch.Tensor]):
+        obs_cell = obs_cell.to(device=self.device, dtype=torch.int16).contiguous()
+        actions = actions.to(device=self.device, dtype=torch.uint8).contiguous()
+        term_arg = term_arg.to(device=self.device, dtype=torch.uint8).contiguous()
+        so = abi.StepOut(*[_ptr(rec[k]) for k in abi.STEP_OUT_FIELDS])
+        check(self.L.rlrm_update(self.h, C.byref(self.state), _ptr(obs_cell), _ptr(actions), _ptr(term_arg), C.byref(so),
+                                 self._stream()))
+
+    def train(self, n_iters: int, learn: bool = True, trace: bool = False, t0: Optional[int] = None):
+        """n_iters fused lockstep iterations (select -> env/RM step -> update -> auto reset)."""
+        t0 = self.t if t0 is None else t0
+        tr = torch.zeros((n_iters, self.N * self.A), dtype=torch.int32, device=self.device) if trace else None
+        check(self.L.rlrm_train(self.h, C.byref(self.state), t0, n_iters, int(learn), _ptr(tr), self._stream()))
+        self.t = t0 + n_iters
+        return tr
+
+    def train_host(self, n_iters: int, host_stats: torch.Tensor, host_slot: Optional[torch.Tensor] = None,
+                   host_epsilon: Optional[torch.Tensor] = None, learn: bool = True, t0: Optional[int] = None):
+        """End-to-end call on HOST (pinned) buffers: H2D control state, fused iterations, D2H statistics, sync."""
+        t0 = self.t if t0 is None else t0
+        check(self.L.rlrm_train_host(self.h, C.byref(self.state), t0, n_iters, int(learn), _ptr(host_slot),
+                                     _ptr(host_epsilon), _ptr(host_stats), self._stream()))
+        self.t = t0 + n_iters
+
+    # -- views ---------------------------------------------------------------------------------
+    def slots_numpy(self):
+        s = self.slot.cpu().numpy().view(np.uint64).reshape(self.N, self.A)
+        g = lambda sh, m: ((s >> np.uint64(sh)) & np.uint64(m)).astype(np.int32)  # noqa: E731
+        return {"cell": g(abi.SLOT_CELL_SHIFT, 0xFFFF), "agent_steps": g(abi.SLOT_STEPS_SHIFT, 0xFFFF),
+                "timestep": g(abi.SLOT_TIME_SHIFT, 0xFFFF), "q": g(abi.SLOT_RMSTATE_SHIFT, 0xFF),
+                "flags": g(abi.SLOT_FLAGS_SHIFT, 0xFF)}
+
+    def stats_numpy(self):
+        return self.stats.cpu().numpy().view(STATS_DTYPE).reshape(-1)
+
+    def total_active_steps(self) -> int:
+        """Sum of env.agent_steps increments over all slots, reduced on the device."""
+        return int(self.stats.view(torch.int64)[:, 0].sum().item())
+
+    # -- the driver loop, call by call (reference API granularity) ----------------------------------
+    def iterate_unfused(self, learn: bool = True, draws: Optional[torch.Tensor] = None, auto_reset: bool = True):
+        """One lockstep iteration through the separate entry points, in the reference drivers' order
+        (frozen_lake_main.py:345-376 / office_main.py:1709-1749): select for every agent -> wrapper step -> update for
+        every agent -> reset of the instances whose episode ended. Bit-identical to one iteration of :meth:`train`."""
+        fl_driver = self.cfg.driver == abi.DRIVER_FROZEN_LAKE_MAIN
+        cell_before = (self.slot & 0xFFFF).to(torch.int16)
+        first = ((self.slot >> abi.SLOT_FLAGS_SHIFT) & abi.FLAG_FIRST) != 0
+        actions = self.select_action(self.t, draws, best=not learn)
+        rec = self.step(actions, self.t, draws)
+        if learn:
+            obs = torch.where(first, rec["cell"], cell_before) if fl_driver else cell_before
+            term_arg = (rec["term"] | rec["trunc"]) if fl_driver else rec["term"]
+            self.update(obs, actions.reshape(-1), term_arg, rec)
+        term = rec["term"].view(self.N, self.A).bool()
+        trunc = rec["trunc"].view(self.N, self.A).bool()
+        over = term.all(dim=1) | trunc.all(dim=1)
+        if auto_reset:
+            self.reset(over)
+        self.t += 1
+        return actions, rec, over

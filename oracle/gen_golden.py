@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz from the LIVE reference (needs /root/reference; run here, not on
+the GPU box):   python oracle/gen_golden.py
+
+Each fixture holds the scenario (JSON), the run shape and every per-iteration quantity the reference produced
+(oracle/ref_harness.py) with Philox-injected randomness, plus the final Q / trace tables.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+sys.path.insert(0, _HERE)
+
+import multiagent_rlrm_b200 as P  # noqa: E402
+import ref_harness as H  # noqa: E402
+from multiagent_rlrm_b200.maps import office_world_grid  # noqa: E402
+from multiagent_rlrm_b200.tables import Scenario, frozen_lake_abc_transitions  # noqa: E402
+
+
+def scenarios():
+    S = {}
+    S["cfg1_det_qrm"] = (P.scenario_config1(), 4, 600, "f32", 1)
+    S["cfg1_det_qrm_f64"] = (P.scenario_config1(), 2, 400, "f64", 1)
+    S["cfg3_slip_qrm"] = (P.scenario_config3(True), 4, 800, "f32", 1)
+    S["cfg3_slip_ql"] = (P.scenario_config3(False), 4, 800, "f32", 1)
+    S["cfg3_slip_ql_f64"] = (P.scenario_config3(False), 2, 500, "f64", 1)
+
+    sc = P.scenario_config3(False)
+    sc.delay_action, sc.penalty_amount, sc.learning_rate = True, -5, 0.5
+    sc.epsilon_start, sc.epsilon_end, sc.epsilon_decay, sc.seed = 0.5, 0.05, 0.9, 77
+    S["fl_delay_penalty_epsdecay_ql"] = (sc, 3, 700, "f32", 1)
+
+    sc = P.scenario_config3(False)
+    sc.learning_rate, sc.seed, sc.penalty_amount = None, 5, -1.5
+    S["fl_lr_none_ql"] = (sc, 3, 600, "f32", 0)
+
+    sc = P.scenario_config3(True)
+    sc.learning_rate, sc.seed = None, 6
+    S["fl_lr_none_qrm"] = (sc, 2, 600, "f32", 1)
+
+    sc = P.scenario_config3(False)
+    sc.algo, sc.lambd, sc.learning_rate, sc.q_init, sc.epsilon_start, sc.epsilon_end = "qlambda", 0.8, 0.2, 0.0, 0.2, 0.2
+    sc.seed = 9
+    S["fl_qlambda"] = (sc, 2, 500, "f32", 1)
+
+    sc = P.scenario_config3(True)
+    sc.reward_modifier, sc.seed = 0.5, 10
+    S["fl_reward_modifier_qrm"] = (sc, 2, 500, "f32", 1)
+
+    sc = P.scenario_config3(False)
+    sc.rm_transitions = [("state0", None, "state0", -0.125)] + frozen_lake_abc_transitions()
+    sc.detector_positions = [tuple(e) for (_s, e, _t, _r) in frozen_lake_abc_transitions()]
+    sc.seed = 11
+    S["fl_none_event_step_cost_ql"] = (sc, 2, 500, "f32", 1)
+
+    S["cfg5_fl_4agents_qrm"] = (P.scenario_config5(False), 2, 500, "f32", 1)
+
+    S["cfg2_office_det_ql"] = (P.scenario_config2(False), 2, 1500, "f32", 1)
+    S["cfg2_office_slip_ql"] = (P.scenario_config2(True), 2, 1500, "f32", 1)
+
+    g = office_world_grid("map1")
+    coffee, letter, office = g.coffee, g.letters[0], g.goals["O"]
+    exp3 = [("state0", letter, "state1", 0), ("state0", coffee[0], "state2", 0), ("state0", coffee[1], "state2", 0),
+            ("state2", letter, "state3", 0), ("state1", coffee[0], "state3", 0), ("state1", coffee[1], "state3", 0),
+            ("state3", office, "state4", 1)]
+    det = sorted(set(g.goals.values()) | set(g.coffee) | set(g.letters))
+    sc = Scenario(env="office_world", starts=[(2, 7), (5, 4)], rm_transitions=exp3, detector_positions=det,
+                  stochastic=True, all_slip=True, high_prob=0.7, wall_penalty=-1, algo="qrm", learning_rate=0.5,
+                  gamma=0.9, epsilon_start=0.3, epsilon_end=0.3, epsilon_decay=1.0, q_init=2.0, driver="office_main",
+                  seed=21)
+    S["ow_allslip_wallpen_exp3_qrm"] = (sc, 2, 1300, "f32", 1)
+
+    sc = Scenario(env="office_world", starts=[(2, 7), (5, 0)], rm_transitions=exp3, detector_positions=det,
+                  stochastic=True, high_prob=0.8, wall_penalty=-2, plants_penalty=-100, terminate_on_plants=True,
+                  terminate_hit_walls=True, algo="ql", learning_rate=0.25, gamma=0.9, epsilon_start=0.4,
+                  epsilon_end=0.1, epsilon_decay=0.95, q_init=1.0, driver="office_main", seed=22)
+    S["ow_terminate_plants_walls_ql"] = (sc, 3, 600, "f32", 1)
+
+    sc = Scenario(env="office_world", starts=[(2, 7)], rm_transitions=P.tables.office_acbd_transitions(True),
+                  detector_positions=det, stochastic=True, delay_action=True, algo="qrm", learning_rate=1.0,
+                  gamma=0.9, epsilon_start=0.1, epsilon_end=0.1, epsilon_decay=1.0, q_init=2.0, driver="office_main",
+                  seed=23)
+    S["ow_delay_completed_acbd_qrm"] = (sc, 2, 1300, "f32", 1)
+
+    S["cfg4_office_chain12_qlambda"] = (P.scenario_config4(), 1, 1300, "f32", 1)
+    S["cfg4_office_chain12_qlambda_f64"] = (P.scenario_config4(), 1, 300, "f64", 1)
+
+    sc = P.scenario_config4()
+    sc.algo, sc.learning_rate, sc.q_init, sc.map_name = "qrm", 0.1, 2.0, "map1"
+    sc.starts = sc.starts[:2]
+    S["ow_chain12_qrm"] = (sc, 1, 1100, "f32", 1)
+    return S
+
+
+def main(only=None):
+    out_dir = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (sc, n, t, real, pre) in scenarios().items():
+        if only and name not in only:
+            continue
+        ref = H.run_reference(sc.to_dict(), n, t, table_dtype=np.float32 if real == "f32" else np.float64, pre_resets=pre)
+        meta = {"scenario": sc.to_dict(), "n_instances": n, "n_iters": t, "real": real, "pre_resets": pre,
+                "generator": "oracle/gen_golden.py", "reference": "Alee08/multiagent-rl-rm v0.3.0"}
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), meta=json.dumps(meta), **ref)
+        print(f"{name}: N={n} T={t} {real} episodes={int(ref['episode_end'].sum())} "
+              f"size={os.path.getsize(os.path.join(out_dir, name + '.npz')) // 1024} KiB")
+
+
+if __name__ == "__main__":
+    main(set(sys.argv[1:]) or None)
