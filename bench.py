@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/sec (env step + RM transition + Q update) of the fused lockstep kernel.
+
+Workload (BASELINE.json configs[2]): 65,536 batched FrozenLake map1 instances x 2 agents PER GPU, slippery (80/10/10),
+built-in A->B->C reward machine, per-instance Q tables (QLearning lr=1, gamma=.99, eps=.01, init 2, use_qrm=True — the
+reference driver's learner). One bench "step" = one fused launch of `--iters` lockstep iterations over the whole batch.
+Multi-GPU (`torchrun`, one rank per GPU) shards independent instances: no data-path collective, weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--iters T] [--instances N] [--impl reference]
+
+Prints ONE JSON line (see the keys in main()).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "agent-steps/sec (env+RM+Q update)"
+UNIT = "agent-steps/s"
+QRM_BYTES_PER_STEP = 140  # read cell block s (64) + read cell block s' (64) + 3 writes x 4 B, nQ = 4
+QL_BYTES_PER_STEP = 36    # read Q[s,:] 16 + read Q[s',:] 16 + write 4
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=2048, help="lockstep iterations per launch (= per bench step)")
+    ap.add_argument("--instances", type=int, default=65536, help="environment instances per GPU")
+    ap.add_argument("--algo", default="qrm", choices=["qrm", "ql"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def scenario(algo):
+    import multiagent_rlrm_b200 as P
+
+    return P.scenario_config3(use_qrm=(algo == "qrm"))
+
+
+def workload_config(args, world):
+    return {
+        "workload": "FrozenLake map1 (10x10), 2 agents, slippery 80/10/10, RM A->B->C (10/15/20), "
+                    + ("QLearning lr=1 gamma=.99 eps=.01 init=2 use_qrm=True" if args.algo == "qrm"
+                       else "QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False")
+                    + ", per-instance Q tables, auto-reset",
+        "baseline_config": "configs[2]: 65,536 batched FrozenLake map1 instances x 2 agents, slippery, per-instance Q-tables",
+        "instances_per_gpu": args.instances,
+        "agents": 2,
+        "iters_per_step": args.iters,
+        "q_table_bytes_per_gpu": args.instances * 2 * 400 * 4 * 4,
+        "l2_policy": "inputs larger than L2 (Q tables 839 MB per GPU vs 126 MB L2); no explicit flush",
+        "sharding": f"independent instances, {world} rank(s), no data-path collective",
+    }
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is pure Python and does not travel to the GPU box; oracle/rlrm_oracle.c is
+# its plain-C restatement, pinned bit-exactly to the live reference by tests/golden)
+# --------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    algo, n_inst, iters, offset = job
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    c = P.compile_scenario(scenario(algo), instance_offset=offset)
+    o = O.Oracle(c, n_inst, "f32")
+    o.reset()
+    t0 = time.perf_counter()
+    o.train(0, iters)
+    dt = time.perf_counter() - t0
+    return int(o.stats["active_steps"].sum()), n_inst * c.n_agents * iters, dt
+
+
+def cpu_port_throughput(algo, seconds, procs):
+    """All `procs` host cores, each an independent batch of instances through the C oracle (the only way the reference
+    'batches' is independent processes)."""
+    import multiprocessing as mp
+
+    import oracle as O
+
+    O.build()
+    # calibrate one core
+    a, s, dt = _cpu_worker((algo, 256, 256, 0))
+    rate = s / max(dt, 1e-6)  # slot-steps/s/core
+    iters = 512
+    n_inst = max(64, int(rate * seconds / (iters * 2)))
+    jobs = [(algo, n_inst, iters, k * n_inst) for k in range(procs)]
+    t0 = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    else:
+        res = [_cpu_worker(jobs[0])]
+    wall = time.perf_counter() - t0
+    active = sum(r[0] for r in res)
+    slots = sum(r[1] for r in res)
+    busy = max(r[2] for r in res)
+    return {
+        "value": active / busy,
+        "unit": UNIT,
+        "cores": procs,
+        "kind": "port",
+        "sample": f"{procs} process(es) x {n_inst} instances x 2 agents x {iters} iterations of the same workload through "
+                  f"oracle/rlrm_oracle.c (float32 tables); {slots / busy:.3e} slot-steps/s; wall {wall:.1f}s",
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = os.cpu_count() or 1
+    per_step = max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    vals, last = [], None
+    for k in range(args.warmup + args.steps):
+        last = cpu_port_throughput(args.algo, per_step, procs)
+        if k >= args.warmup:
+            vals.append(last["value"])
+    value = sum(vals) / len(vals)
+    last["value"] = value
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1), "cpu_baseline": last,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is pure Python/NumPy (≈1e4 agent-steps/s/core, BASELINE.md §2) and cannot travel to the GPU box; "
+                "this arm times its bit-exact plain-C restatement on all host cores",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = f"/tmp/rlrm_clocks_{os.getpid()}.csv"
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(algo):
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return d.get(algo)
+    except Exception:
+        return None
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import multiagent_rlrm_b200 as P
+    from multiagent_rlrm_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+
+    sc = scenario(args.algo)
+    c = P.compile_scenario(sc, instance_offset=rank * args.instances)  # Philox keyed on the GLOBAL instance id
+    eng = Engine(c, args.instances, device=dev)
+    eng.reset()
+    n_slots = args.instances * c.n_agents
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        eng.train(args.iters)
+    barrier()
+    launches0, steps0 = eng.launches, eng.total_active_steps()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        eng.train(args.iters)
+        ev[k + 1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    active = eng.total_active_steps() - steps0
+    launches = eng.launches - launches0
+
+    # ---- end to end: the public API call on HOST (pinned) buffers, copies inside the timed region --------------------
+    host_slot = torch.empty(n_slots, dtype=torch.int64).pin_memory()
+    host_eps = torch.empty(n_slots, dtype=torch.float64).pin_memory()
+    host_stats = torch.empty((n_slots, 32), dtype=torch.uint8).pin_memory()
+    host_slot.copy_(eng.slot); host_eps.copy_(eng.epsilon)
+    e2e_steps = max(3, args.steps // 2)
+    eng.train_host(args.iters, host_stats, host_slot, host_eps)  # warm
+    barrier()
+    a0 = int(host_stats.view(torch.int64)[:, 0].sum())
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.train_host(args.iters, host_stats, host_slot, host_eps)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    e2e_active = int(host_stats.view(torch.int64)[:, 0].sum()) - a0
+    h2d = host_slot.numel() * 8 + host_eps.numel() * 8
+    d2h = host_stats.numel() + host_slot.numel() * 8 + host_eps.numel() * 8
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_s = float(t[0]), float(t[1])
+        cnt = torch.tensor([active, e2e_active, launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        active, e2e_active, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
+
+    if rank == 0:
+        value = active / (elapsed_ms * 1e-3)
+        bytes_per = QRM_BYTES_PER_STEP if args.algo == "qrm" else QL_BYTES_PER_STEP
+        peak, peak_src = measured_peak()
+        kernel_ms = sum(per_launch_ms) / len(per_launch_ms)          # this rank's average launch duration (CUDA events)
+        active_per_launch_rank = (active / world) / args.steps
+        achieved = bytes_per * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_port_throughput(args.algo, args.cpu_seconds, os.cpu_count() or 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "slot_steps_per_s": world * n_slots * args.iters * args.steps / (elapsed_ms * 1e-3),
+            "active_fraction": active / (world * n_slots * args.iters * args.steps),
+            "clocks": clocks,
+            "e2e": {"value": e2e_active / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "Engine.train_host -> rlrm_train_host (pinned host slot/epsilon in+out, stats out)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.algo), "peak_source": peak_src,
+                         "kernel": f"train_kernel<FrozenLake,{args.algo.upper()}>",
+                         "algorithmic_bytes_per_active_agent_step": bytes_per,
+                         "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

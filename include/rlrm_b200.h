@@ -107,7 +107,7 @@ typedef struct rlrm_config {
   /* randomness: Philox4x32-10, key = (seed_lo, seed_hi), counter = (t_lo, t_hi, instance_offset + i, a) */
   uint32_t seed_lo, seed_hi;
   uint32_t instance_offset;    /* global id of local instance 0 (multi-GPU sharding keeps draws independent of G) */
-  int32_t reserved;
+  int32_t reserved;            /* bit 0: force the generic kernels (testing: generic vs specialised must agree) */
 } rlrm_config_t;
 
 /* host pointers; copied at rlrm_create */
@@ -213,11 +213,12 @@ int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_ce
 int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
                uint32_t* trace, void* stream);
 
-/* Same call with HOST buffers (the end-to-end path): uploads `slot`/`epsilon` control state from host_slot /
- * host_epsilon when non-NULL, runs rlrm_train, downloads the statistics block into host_stats ([N*A]) and
- * synchronises the stream. Device copies inside this call are part of the measured end-to-end time. */
+/* Same call with HOST buffers (the end-to-end path). host_slot / host_epsilon ([N*A], in/out, may be NULL): the
+ * environment / RM state and epsilon to resume from are uploaded before the launch and the updated values are
+ * downloaded after it; host_stats ([N*A], out, may be NULL) receives the statistics block. The stream is synchronised
+ * before returning. All copies are inside this call and therefore inside any end-to-end timing of it. */
 int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
-                    const uint64_t* host_slot, const double* host_epsilon, rlrm_stats_t* host_stats, void* stream);
+                    uint64_t* host_slot, double* host_epsilon, rlrm_stats_t* host_stats, void* stream);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t rlrm_launch_count(const rlrm_handle_t* h);

@@ -138,26 +138,25 @@ __device__ __forceinline__ unsigned long long explore_threshold(double eps) {
 
 // QLearning.choose_action / choose_action_greedy (qlearning.py:112-143)
 __device__ __forceinline__ int select_action(const float4& row, unsigned long long explore_thr, const unsigned w[4], bool best) {
-  float v[4] = {row.x, row.y, row.z, row.w};
+  // np.argmax: first maximum
   int va = 0;
-#pragma unroll
-  for (int j = 1; j < 4; j++)
-    if (v[j] > v[va]) va = j;  // np.argmax: first maximum
+  float m = row.x;
+  if (row.y > m) { m = row.y; va = 1; }
+  if (row.z > m) { m = row.z; va = 2; }
+  if (row.w > m) { m = row.w; va = 3; }
   if (best) return va;
   if ((unsigned long long)w[0] < explore_thr) return (int)__umulhi(w[1], 4u);  // rng.choice(range(4))
-  float m = v[va];
-  int n = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) n += (v[j] == m);
-  int pick = (int)__umulhi(w[2], (unsigned)n);  // rng.choice(maxs)
-  int a = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    if (v[j] == m) {
-      if (pick == 0) a = j;
-      pick--;
-    }
-  }
+  const int e0 = row.x == m, e1 = row.y == m, e2 = row.z == m, e3 = row.w == m;
+  const int n = e0 + e1 + e2 + e3;
+  if (n == 1) return va;
+  const int pick = (int)__umulhi(w[2], (unsigned)n);  // rng.choice(maxs): the pick-th maximal index
+  // rank of each maximal index among the maxima
+  const int r1 = e0, r2 = e0 + e1, r3 = e0 + e1 + e2;
+  int a = va;
+  if (e1 && r1 == pick) a = 1;
+  if (e2 && r2 == pick) a = 2;
+  if (e3 && r3 == pick) a = 3;
+  if (e0 && pick == 0) a = 0;
   return a;
 }
 
@@ -582,6 +581,169 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast path: QRM with nQ == 4 (BASELINE configs 1/3/5). The 64-byte cell block Q[cell, 0..3, 0..3] lives in registers
+// between iterations: it is fetched with two 256-bit loads only when the agent changes cell, the counterfactual
+// updates run on registers, and the dirty rows go back with one 256-bit + one 128-bit store. Requires
+// qrm_states == [0, 1, .., n_qrm-1] (so a static unroll over rows is the reference's update order), per-instance
+// tables, fixed learning rate, no visit counts; anything else takes train_kernel.
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ float sel4(float a, float b, float c, float d, unsigned k) {
+  const float lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
+  return (k & 2u) ? hi : lo;
+}
+__device__ __forceinline__ void load_block4(const float* Q, unsigned cell, float B[16], float bmax[4]) {
+  const F8 lo = ldg256(Q + (size_t)cell * 16), hi = ldg256(Q + (size_t)cell * 16 + 8);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    B[j] = lo.v[j];
+    B[8 + j] = hi.v[j];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) bmax[r] = fmaxf(fmaxf(B[4 * r], B[4 * r + 1]), fmaxf(B[4 * r + 2], B[4 * r + 3]));
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                                unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
+  float* Q = st.q;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  float B[16], bmax[4];  // carried cell block Q[cell, rm state, action] and its row maxima
+#pragma unroll
+  for (int j = 0; j < 16; j++) B[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; j++) bmax[j] = 0.f;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    Q = st.q + table_base(p, i, a);
+    load_block4(Q, s.cell, B, bmax);
+  }
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    if (valid) {
+      unsigned w[4];
+      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      float4 row;
+      row.x = sel4(B[0], B[4], B[8], B[12], s.rm);
+      row.y = sel4(B[1], B[5], B[9], B[13], s.rm);
+      row.z = sel4(B[2], B[6], B[10], B[14], s.rm);
+      row.w = sel4(B[3], B[7], B[11], B[15], s.rm);
+      const int action = select_action(row, explore_thr, w, learn == 0);
+      const unsigned before = s.cell;
+      Rec r;
+      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      const bool moved = r.cell != before;
+      // values the updates overwrite, read before the carried block is replaced
+      const float cur0 = sel4(B[0], B[1], B[2], B[3], (unsigned)action);
+      const float cur1 = sel4(B[4], B[5], B[6], B[7], (unsigned)action);
+      const float cur2 = sel4(B[8], B[9], B[10], B[11], (unsigned)action);
+      if (moved) load_block4(Q, r.cell, B, bmax);  // the carried block becomes the NEXT cell's block
+      if (learn) {
+        // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106),
+        // in get_all_states()[:-1] order == row order 0..n_qrm-1 on this path. The next state's row maximum comes from
+        // the carried block: a different block when the agent moved, else the live one including earlier updates.
+        const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+        float* dst = Q + (size_t)before * 16 + action;  // infos["prev_s"] is the position before the move
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          if (u < p.n_qrm) {
+            const unsigned d = tb.delta[u * (p.nEv + 1) + col];
+            const unsigned un = d == RLRM_NO_TRANSITION ? (unsigned)u : d;
+            const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
+            const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
+            const float mx = sel4(bmax[0], bmax[1], bmax[2], bmax[3], un);
+            const float cur = u == 0 ? cur0 : (u == 1 ? cur1 : cur2);
+            const float mf = __fmul_rn(done ? 0.0f : 1.0f, mx);
+            const float inner = __fadd_rn(__double2float_rn(__dadd_rn(r.renv, ru)), __fmul_rn(p.gamma_f, mf));
+            const float nv = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+            dst[4 * u] = nv;
+            if (!moved) {  // same cell: the carried block is the one just written
+#pragma unroll
+              for (int c = 0; c < 4; c++) B[4 * u + c] = (c == action) ? nv : B[4 * u + c];
+              bmax[u] = fmaxf(fmaxf(B[4 * u], B[4 * u + 1]), fmaxf(B[4 * u + 2], B[4 * u + 3]));
+            }
+          }
+        }
+      }
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      active_steps += r.stepped ? 1u : 0u;
+      if (trace)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (valid && over) {
+      episodes++;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, a, s, eps);
+      explore_thr = explore_threshold(eps);
+      load_block4(Q, s.cell, B, bmax);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
 // Q(lambda) fused: one block per instance, one warp per agent; the dense trace sweep is cooperative over the warp.
 template <int ENV>
 __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
@@ -713,6 +875,8 @@ struct rlrm_handle {
   unsigned char* d_blob;
   int smem_bytes;
   long long launches;
+  int qrm4_fast;  // train_qrm4_kernel is applicable (see its header comment)
+  int force_generic;
 };
 
 static thread_local char g_err[512] = "";
@@ -821,6 +985,10 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   kp.blob = h->d_blob;
   h->smem_bytes = off;
+  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm <= 3 && !kp.shared_q && cfg->learning_rate >= 0.0 &&
+                  !(cfg->reserved & 1));
+  for (int j = 0; j < kp.n_qrm; j++)
+    if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
   *out = h;
   return RLRM_OK;
 }
@@ -838,6 +1006,7 @@ extern "C" int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double g
   if (h->cfg.algo == RLRM_ALGO_QLAMBDA && learning_rate < 0) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) needs a fixed learning rate");
   h->cfg.learning_rate = learning_rate; h->cfg.gamma = gamma; h->cfg.lambd = lambd;
   fill_learner(h->kp, learning_rate, gamma, lambd);
+  if (learning_rate < 0.0) h->qrm4_fast = 0;
   return RLRM_OK;
 }
 
@@ -960,7 +1129,9 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
   } else {
     const long long threads = st->n_instances * kp.G;
     const unsigned grid = blocks_for(threads, TRAIN_BLOCK);
-    if (kp.algo == RLRM_ALGO_QRM)
+    if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits)
+      train_qrm4_kernel<ENV><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    else if (kp.algo == RLRM_ALGO_QRM)
       train_kernel<ENV, RLRM_ALGO_QRM><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
     else
       train_kernel<ENV, RLRM_ALGO_QL><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
@@ -982,7 +1153,7 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
 }
 
 extern "C" int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
-                               const uint64_t* host_slot, const double* host_epsilon, rlrm_stats_t* host_stats, void* stream) {
+                               uint64_t* host_slot, double* host_epsilon, rlrm_stats_t* host_stats, void* stream) {
   int rc = check_state(h, st, true);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -996,6 +1167,8 @@ extern "C" int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_
     if (!st->stats) return fail(RLRM_ERR_ARG, "host_stats requested but state.stats is null");
     CUDA_TRY(cudaMemcpyAsync(host_stats, st->stats, n * sizeof(rlrm_stats_t), cudaMemcpyDeviceToHost, s));
   }
+  if (host_slot) CUDA_TRY(cudaMemcpyAsync(host_slot, st->slot, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(host_epsilon, st->epsilon, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return RLRM_OK;
 }

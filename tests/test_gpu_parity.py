@@ -100,6 +100,23 @@ def test_fused_kernel_matches_oracle(name, cuda_device):
     _compare_with_oracle(eng, o, name)
 
 
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg5_qrm_4agents"])
+def test_generic_kernel_equals_specialised(name, cuda_device):
+    """config.reserved bit 0 forces train_kernel<.., QRM>; it must agree bit-for-bit with train_qrm4_kernel."""
+    import multiagent_rlrm_b200 as P
+
+    sc, n, t = _scenarios_medium()[name]
+    c_fast, c_gen = P.compile_scenario(sc), P.compile_scenario(sc)
+    c_gen.config.reserved = 1
+    a, b = _engine(c_fast, n), _engine(c_gen, n)
+    a.reset(); b.reset()
+    ta, tb = a.train(t, trace=True), b.train(t, trace=True)
+    assert np.array_equal(ta.cpu().numpy(), tb.cpu().numpy())
+    assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy())
+    assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
+    assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+
+
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda"])
 def test_unfused_entry_points_equal_fused(name, cuda_device):
     """select -> step -> update -> reset through the separate C-ABI calls == the fused persistent kernel."""
