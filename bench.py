@@ -300,7 +300,7 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.algo), "peak_source": peak_src,
-                         "kernel": f"train_kernel<FrozenLake,{args.algo.upper()}>",
+                         "kernel": "train_qrm4_kernel<FrozenLake>" if args.algo == "qrm" else "train_kernel<FrozenLake,QL>",
                          "algorithmic_bytes_per_active_agent_step": bytes_per,
                          "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms},
             "cpu_baseline": cpu,
