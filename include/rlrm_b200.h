@@ -107,6 +107,7 @@ typedef struct rlrm_config {
   /* randomness: Philox4x32-10, key = (seed_lo, seed_hi), counter = (t_lo, t_hi, instance_offset + i, a) */
   uint32_t seed_lo, seed_hi;
   uint32_t instance_offset;    /* global id of local instance 0 (multi-GPU sharding keeps draws independent of G) */
+  int32_t n_actions;           /* 1..4 usable actions (exploration draws (w1*n_actions)>>32); tables are always 4 wide */
   int32_t reserved;            /* bit 0: force the generic kernels (testing: generic vs specialised must agree) */
 } rlrm_config_t;
 

@@ -22,3 +22,9 @@ from .tables import (  # noqa: F401
 )
 
 __version__ = "0.1.0"
+from .actions import ActionEncoderFrozenLake, ActionEncoderOfficeWorld, ActionRL  # noqa: E402,F401
+from .agent import AgentRL, UPValueError  # noqa: E402,F401
+from .encoders import StateEncoderFrozenLake, StateEncoderOfficeWorld, encode_state  # noqa: E402,F401
+from .envs import MultiAgentFrozenLake, MultiAgentOfficeWorld  # noqa: E402,F401
+from .learners import QLearning, QLearningLambda  # noqa: E402,F401
+from .wrapper import RMEnvironmentWrapper  # noqa: E402,F401

@@ -57,6 +57,7 @@ class Config(C.Structure):
         ("seed_lo", C.c_uint32),
         ("seed_hi", C.c_uint32),
         ("instance_offset", C.c_uint32),
+        ("n_actions", C.c_int32),
         ("reserved", C.c_int32),
     ]
 

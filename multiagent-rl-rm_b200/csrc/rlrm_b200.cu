@@ -35,7 +35,7 @@ struct KP {
   double lr, gamma, eps_end, eps_decay;
   float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
   int decay_on_reset, shared_q;
-  unsigned seed_lo, seed_hi, instance_offset;
+  unsigned seed_lo, seed_hi, instance_offset, n_actions;
   long long S4;  // W*H*nQ*4 floats per table
   // table blob in global memory and section offsets (bytes) inside it / inside the shared-memory copy
   const unsigned char* blob;
@@ -137,7 +137,8 @@ __device__ __forceinline__ unsigned long long explore_threshold(double eps) {
 }
 
 // QLearning.choose_action / choose_action_greedy (qlearning.py:112-143)
-__device__ __forceinline__ int select_action(const float4& row, unsigned long long explore_thr, const unsigned w[4], bool best) {
+__device__ __forceinline__ int select_action(const float4& row, unsigned long long explore_thr, const unsigned w[4], bool best,
+                                             unsigned n_actions) {
   // np.argmax: first maximum
   int va = 0;
   float m = row.x;
@@ -145,7 +146,7 @@ __device__ __forceinline__ int select_action(const float4& row, unsigned long lo
   if (row.z > m) { m = row.z; va = 2; }
   if (row.w > m) { m = row.w; va = 3; }
   if (best) return va;
-  if ((unsigned long long)w[0] < explore_thr) return (int)__umulhi(w[1], 4u);  // rng.choice(range(4))
+  if ((unsigned long long)w[0] < explore_thr) return (int)__umulhi(w[1], n_actions);  // rng.choice(range(A))
   const int e0 = row.x == m, e1 = row.y == m, e2 = row.z == m, e3 = row.w == m;
   const int n = e0 + e1 + e2 + e3;
   if (n == 1) return va;
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(256) select_kernel(KP p, DState st, const unsi
   } else {
     philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
   }
-  actions_out[k] = (unsigned char)select_action(row, explore_threshold(st.epsilon[k]), w, best != 0);
+  actions_out[k] = (unsigned char)select_action(row, explore_threshold(st.epsilon[k]), w, best != 0, p.n_actions);
 }
 
 __device__ __forceinline__ void store_rec(const DOut& o, long long k, const Rec& r) {
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
       philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
       // every agent selects on every iteration, finished ones included (frozen_lake_main.py:350-352)
       const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
-      action = select_action(row, explore_thr, w, learn == 0);
+      action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
       const unsigned before = s.cell;
       const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
       agent_step<ENV>(p, tb, s, action, w[3], true, r);
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       row.y = sel4(B[1], B[5], B[9], B[13], s.rm);
       row.z = sel4(B[2], B[6], B[10], B[14], s.rm);
       row.w = sel4(B[3], B[7], B[11], B[15], s.rm);
-      const int action = select_action(row, explore_thr, w, learn == 0);
+      const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
       const unsigned before = s.cell;
       Rec r;
       agent_step<ENV>(p, tb, s, action, w[3], true, r);
@@ -775,7 +776,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
     philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
     __syncwarp();
     const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
-    const int action = select_action(row, explore_thr, w, learn == 0);
+    const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
     const unsigned before = s.cell;
     const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
     Rec r;
@@ -919,6 +920,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (cfg->n_events < 0 || cfg->n_events > RLRM_MAX_EVENTS) return fail(RLRM_ERR_ARG, "n_events out of range");
   if (cfg->n_qrm_states < 0 || cfg->n_qrm_states > RLRM_MAX_RM_STATES) return fail(RLRM_ERR_ARG, "n_qrm_states out of range");
   if (cfg->slip_n < 1 || cfg->slip_n > 4) return fail(RLRM_ERR_ARG, "slip_n out of range");
+  if (cfg->n_actions < 1 || cfg->n_actions > RLRM_N_ACTIONS) return fail(RLRM_ERR_ARG, "n_actions out of range");
   if (cfg->algo < 0 || cfg->algo > RLRM_ALGO_QLAMBDA) return fail(RLRM_ERR_ARG, "unknown algo");
   if (cfg->env_kind != RLRM_ENV_FROZEN_LAKE && cfg->env_kind != RLRM_ENV_OFFICE_WORLD) return fail(RLRM_ERR_ARG, "unknown env_kind");
   if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->learning_rate < 0)
@@ -954,6 +956,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   fill_learner(kp, cfg->learning_rate, cfg->gamma, cfg->lambd);
   kp.decay_on_reset = cfg->decay_on_reset; kp.shared_q = cfg->shared_q;
   kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;
+  kp.n_actions = (unsigned)cfg->n_actions;
   kp.S4 = (long long)ncell * kp.nQ * 4;
 
   // pack the tables into one 16-byte aligned blob

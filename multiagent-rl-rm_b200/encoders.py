@@ -1,0 +1,56 @@
+"""State encoders: enc = (pos_y * W + pos_x) * nQ + q — mirrors multi_agent/state_encoder.py:4-36,
+environments/frozen_lake/state_encoder_frozen_lake.py:7-86, environments/office_world/state_encoder_office.py:7-66 and
+utils/utils.py:5-35 (encode_state). Index arithmetic on host scalars (configuration-time / N=1 API glue); the batched
+kernels compute the same expression per thread."""
+from __future__ import annotations
+
+
+class StateEncoder:
+    def __init__(self, agent):
+        self.agent = agent
+
+    def encode(self, state, state_rm=None):
+        raise NotImplementedError("This method should be overridden by subclasses.")
+
+    def encode_rm_state(self, state_rm):
+        rm = self.agent.get_reward_machine()
+        return rm.get_state_index(rm.get_current_state() if state_rm is None else state_rm)
+
+
+class _GridStateEncoder(StateEncoder):
+    def _dims(self):
+        p = self.agent.ma_problem
+        return p.grid_width, p.grid_height, self.agent.get_reward_machine().numbers_state()
+
+    def encode(self, state, state_rm=None):
+        width, height, n_rm = self._dims()
+        q = self.encode_rm_state(state_rm)
+        s = state["pos_y"] * width + state["pos_x"]
+        enc = s * n_rm + q
+        if enc >= width * height * n_rm:
+            raise ValueError("Encoded state index exceeds total state space size.")
+        return enc, {"s": s, "q": q}
+
+    def decode(self, encoded_state):
+        width, _height, n_rm = self._dims()
+        q, s = encoded_state % n_rm, encoded_state // n_rm
+        label = self.agent.get_reward_machine().get_state_from_index(q)
+        return {"pos_x": s % width, "pos_y": s // width}, {"q": label}
+
+
+class StateEncoderFrozenLake(_GridStateEncoder):
+    pass
+
+
+class StateEncoderOfficeWorld(_GridStateEncoder):
+    pass
+
+
+def encode_state(agent, state, state_reward_machine):
+    rm = agent.get_reward_machine()
+    n_rm = rm.numbers_state()
+    width, height = agent.ma_problem.grid_width, agent.ma_problem.grid_height
+    enc = (state["pos_y"] * width + state["pos_x"]) * n_rm + rm.get_state_index(state_reward_machine)
+    if enc >= width * height * n_rm:
+        raise ValueError("Encoded state index exceeds total state space size", enc, ">=", width * height * n_rm)
+    return enc

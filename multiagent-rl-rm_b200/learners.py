@@ -1,0 +1,281 @@
+"""Tabular learners with the reference's object API, backed by the CUDA library.
+
+Mirrors learning_algorithms/learning_algorithm.py:6-84, qlearning.py:6-160 and qlearning_lambda.py:5-132.
+``q_table`` / ``e_table`` / ``visits`` are torch tensors on the GPU; ``update`` and ``choose_action`` launch the same
+device functions the fused kernel uses (rlrm_update / rlrm_select_action on a one-slot handle whose "grid" is just
+the encoded state space). There is no CPU fallback: constructing a learner without a CUDA device raises.
+
+Randomness: the reference consumes a numpy PCG64 stream in data-dependent order, which cannot be reproduced by a
+batched device generator; here every ``choose_action`` call consumes four 32-bit words (explore test, random action,
+tie-break, unused) taken from ``rng`` — ``rng.words()`` if it has that hook (trace injection), else
+``rng.integers(0, 2**32, 4)``. Decisions given the words are identical to the reference's.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi as abi
+from ._lib import check, load
+
+
+def _factor_state_space(S):
+    """(cells, nq) with cells * nq >= S, cells <= MAX_CELLS, nq <= MAX_RM_STATES."""
+    nq = max(1, -(-S // abi.MAX_CELLS))
+    if nq > abi.MAX_RM_STATES:
+        raise ValueError(f"state_space_size {S} exceeds {abi.MAX_CELLS * abi.MAX_RM_STATES}")
+    return -(-S // nq), nq
+
+
+class _TableHandle:
+    """One-slot C-ABI handle over a learner's own tables: grid = (cells x 1), nQ = nq, enc = cell*nq + q."""
+
+    def __init__(self, S, algo, learning_rate, gamma, lambd, device, n_actions=4):
+        if not torch.cuda.is_available():
+            raise RuntimeError("multiagent-rl-rm_b200 learners need a CUDA device (no CPU fallback)")
+        self.L = load()
+        self.device = torch.device(device)
+        self.cells, self.nq = _factor_state_space(S)
+        self.S_pad = self.cells * self.nq
+        cfg = abi.Config()
+        cfg.abi_version = abi.ABI_VERSION
+        cfg.env_kind, cfg.driver, cfg.algo = abi.ENV_FROZEN_LAKE, abi.DRIVER_OFFICE_MAIN, algo
+        cfg.width, cfg.height, cfg.n_agents = self.cells, 1, 1
+        cfg.n_rm_states, cfg.n_events, cfg.rm_final, cfg.n_qrm_states = self.nq, 0, -1, 0
+        cfg.max_steps, cfg.stochastic, cfg.slip_n = 1000, 0, 1
+        for j in range(3):
+            cfg.slip_thr[j] = 1 << 32
+        cfg.learning_rate = -1.0 if learning_rate is None else float(learning_rate)
+        cfg.gamma, cfg.lambd = float(gamma), float(lambd)
+        cfg.epsilon_start = cfg.epsilon_end = cfg.epsilon_decay = 1.0
+        cfg.n_actions = n_actions
+        self.cfg = cfg
+        n = self.cells
+        self._arrs = dict(
+            next_cell=np.repeat(np.arange(n, dtype=np.uint16)[:, None], 4, axis=1).copy(),
+            cell_flags=np.zeros(n, np.uint8), label=np.full(n, abi.EVENT_NONE, np.uint8),
+            delta=np.full((self.nq, 1), abi.NO_TRANSITION, np.uint8), rq=np.zeros((self.nq, 1)), rcf=np.zeros((self.nq, 1)),
+            qrm_states=np.zeros(1, np.uint8), start_cell=np.zeros(1, np.uint16))
+        t = abi.Tables(*[self._arrs[k].ctypes.data for k in ("next_cell", "cell_flags", "label", "delta", "rq", "rcf",
+                                                            "qrm_states", "start_cell")])
+        h = C.c_void_p()
+        dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(self.L.rlrm_create(C.byref(cfg), C.byref(t), dev, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.rlrm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+
+class BaseLearningAlgorithm:
+    def __init__(self, state_space_size, action_space_size, gamma=0.99, seed=2020, max_steps=400, device="cuda:0"):
+        if not (1 <= action_space_size <= 4):
+            raise ValueError("the CUDA path implements the reference's grid worlds: at most 4 actions (up, down, left, right)")
+        self.state_space_size = state_space_size
+        self.action_space_size = action_space_size
+        self.episode = 0
+        self.max_steps = max_steps
+        self.verbose = 0
+        self.seed = seed
+        self.gamma = gamma
+        self.rleval = None
+        self.user_quit = False
+        self.agent_quit = False
+        self.rng = np.random.default_rng(seed=self.seed)
+        self.tosave = ["rng"]
+        self.device = torch.device(device)
+
+    def learn_init(self):
+        pass
+
+    def learn_init_episode(self):
+        pass
+
+    def learn_done_episode(self):
+        pass
+
+    def learn_end(self):
+        pass
+
+
+class _TabularBase(BaseLearningAlgorithm):
+    _ALGO = abi.ALGO_QL
+
+    def _setup(self, q_init, lambd=0.0):
+        S = self.state_space_size
+        self._th = _TableHandle(S, self._ALGO, self.learning_rate, self.gamma, lambd, self.device, self.action_space_size)
+        d, Sp = self.device, self._th.S_pad
+        self._q = torch.full((Sp, 4), float(q_init), dtype=torch.float32, device=d)
+        if self.action_space_size < 4:  # tables are 4 wide on the device; unused actions can never be a maximum
+            self._q[:, self.action_space_size:] = float("-inf")
+        self._e = torch.zeros((Sp, 4), dtype=torch.float32, device=d) if self._ALGO == abi.ALGO_QLAMBDA else None
+        self._visits = torch.zeros((Sp, 4), dtype=torch.int32, device=d)
+        self._slot = torch.zeros(1, dtype=torch.int64, device=d)
+        self._eps = torch.zeros(1, dtype=torch.float64, device=d)
+        self._hp = (self.learning_rate, self.gamma, lambd)
+
+    # tables as views of exactly (S, A)
+    @property
+    def q_table(self):
+        return self._q[: self.state_space_size, : self.action_space_size]
+
+    @q_table.setter
+    def q_table(self, value):
+        self._q[: self.state_space_size, : self.action_space_size].copy_(torch.as_tensor(value, dtype=torch.float32))
+
+    @property
+    def visits(self):
+        return self._visits[: self.state_space_size, : self.action_space_size]
+
+    def _state(self):
+        return abi.State(1, self._slot.data_ptr(), self._eps.data_ptr(), self._q.data_ptr(),
+                         None if self._e is None else self._e.data_ptr(), self._visits.data_ptr(), None, None)
+
+    def _sync_hyper(self):
+        hp = (self.learning_rate, self.gamma, getattr(self, "lambd", 0.0))
+        if hp != self._hp:  # the reference lets callers mutate these attributes in place
+            check(self._th.L.rlrm_set_learner(self._th.h, -1.0 if hp[0] is None else float(hp[0]), float(hp[1]), float(hp[2])))
+            self._hp = hp
+
+    def _split(self, enc):
+        enc = int(enc)
+        if not (0 <= enc < self.state_space_size):
+            raise IndexError(f"encoded state {enc} out of range for state_space_size {self.state_space_size}")
+        return enc // self._th.nq, enc % self._th.nq
+
+    def _device_update(self, s, sn, action, reward, terminated):
+        """One update_q / Q(lambda) update on the device (rlrm_update on a synthesised one-slot step record)."""
+        self._sync_hyper()
+        (c0, q0), (c1, q1) = self._split(s), self._split(sn)
+        d = self.device
+        u16 = lambda v: torch.tensor([v], dtype=torch.int16, device=d)  # noqa: E731
+        u8 = lambda v: torch.tensor([v], dtype=torch.uint8, device=d)  # noqa: E731
+        f64 = lambda v: torch.tensor([float(v)], dtype=torch.float64, device=d)  # noqa: E731
+        rec = dict(prev_cell=u16(c0), cell=u16(c1), prev_q=u8(q0), q=u8(q1), event=u8(abi.EVENT_NONE), executed=u8(5),
+                   renv=f64(0.0), rq=f64(0.0), reward=f64(reward), env_term=u8(0), rm_term=u8(0), term=u8(int(bool(terminated))),
+                   trunc=u8(0))
+        so = abi.StepOut(*[rec[k].data_ptr() for k in abi.STEP_OUT_FIELDS])
+        st = self._state()
+        check(self._th.L.rlrm_update(self._th.h, C.byref(st), rec["prev_cell"].data_ptr(), u8(int(action)).data_ptr(),
+                                     rec["term"].data_ptr(), C.byref(so), self._th.stream()))
+        torch.cuda.current_stream(d).synchronize()  # the temporaries above must outlive the kernel
+
+    def _words(self, rng):
+        if hasattr(rng, "words"):
+            w = rng.words()
+        else:
+            w = rng.integers(0, 1 << 32, size=4, dtype=np.uint64)
+        return torch.tensor([int(x) & 0xFFFFFFFF for x in w], dtype=torch.int64).to(torch.int32)
+
+    def choose_action(self, encoded_state, best=False, rng=None, **kwargs):
+        """epsilon-greedy with uniform tie-break (qlearning.py:112-143); best=True -> first argmax."""
+        if not best and self.action_selection != "greedy":
+            if self.action_selection == "softmax":
+                raise NotImplementedError("softmax selection is out of scope (no reference driver uses it; DESIGN.md §8)")
+            raise ValueError("Unsupported action selection method")
+        cell, q = self._split(encoded_state)
+        self._slot[0] = (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT)
+        self._eps[0] = float(self.epsilon)
+        draws = None
+        if not best:
+            draws = self._words(self.rng if rng is None else rng).to(self.device)
+        out = torch.zeros(1, dtype=torch.uint8, device=self.device)
+        st = self._state()
+        check(self._th.L.rlrm_select_action(self._th.h, C.byref(st), None if draws is None else draws.data_ptr(), 0, int(bool(best)),
+                                            out.data_ptr(), self._th.stream()))
+        return int(out.item())
+
+    def learn_done_episode(self):
+        """Decay epsilon after each episode (qlearning.py:153-155)."""
+        self.epsilon = max(self.epsilon_end, self.epsilon * self.epsilon_decay)
+
+    def reset_epsilon(self):
+        self.epsilon = self.epsilon_start
+
+
+class QLearning(_TabularBase):
+    """Tabular Q-learning with optional QRM counterfactual experiences (qlearning.py:6-160)."""
+
+    _ALGO = abi.ALGO_QL
+
+    def __init__(self, gamma, action_selection, learning_rate=None, epsilon_start=1.0, epsilon_end=0.2, epsilon_decay=0.99,
+                 qtable_init=1, use_qrm=False, use_rsh=False, **kwargs):
+        super().__init__(gamma=gamma, **kwargs)
+        self.learning_rate = learning_rate
+        self.action_selection = action_selection
+        self.epsilon_start, self.epsilon_end, self.epsilon_decay = epsilon_start, epsilon_end, epsilon_decay
+        self.epsilon = self.epsilon_start
+        self.use_qrm = use_qrm
+        self.use_rsh = use_rsh
+        self.qtable_init = qtable_init
+        self.param_str = f"{learning_rate:0.2f},{gamma:0.2f}" if learning_rate is not None else f"None,{gamma:0.2f}"
+        self.tosave += ["q_table", "visits", "epsilon"]
+        self._setup(qtable_init)
+
+    def update(self, encoded_state, encoded_next_state, action, reward, terminated, **kwargs):
+        info = kwargs.get("info", {}) or {}
+        rm = info.get("reward_machine", None)
+        shaping = self.use_rsh and rm is not None and getattr(rm, "potentials", None) is not None
+        if shaping:  # R' = R + gamma*Phi(q') - Phi(q)  (qlearning.py:51-66)
+            pq, nq = info.get("prev_q", None), info.get("q", None)
+            if pq is not None and nq is not None:
+                reward += self.gamma * rm.potentials.get(nq, 0) - rm.potentials.get(pq, 0)
+        if self.use_qrm:  # only the counterfactual list is applied (qlearning.py:82-106)
+            for exp in info.get("qrm_experience", []):
+                _s, _a, _r, _sn, _done, _, cur_q, _, nxt_q, _ = exp
+                if shaping:
+                    _r += self.gamma * rm.potentials.get(rm.get_state_from_index(nxt_q), 0) - rm.potentials.get(
+                        rm.get_state_from_index(cur_q), 0)
+                self._device_update(_s, _sn, _a, _r, _done)
+        else:
+            self._device_update(encoded_state, encoded_next_state, action, reward, terminated)
+        return False
+
+
+class QLearningLambda(_TabularBase):
+    """Watkins-style Q(lambda) with replacing traces, dense sweep (qlearning_lambda.py:5-132)."""
+
+    _ALGO = abi.ALGO_QLAMBDA
+
+    def __init__(self, gamma, lambd, action_selection, learning_rate=None, epsilon_start=1.0, epsilon_end=0.2,
+                 epsilon_decay=0.99, **kwargs):
+        super().__init__(gamma=gamma, **kwargs)
+        if learning_rate is None:
+            raise NotImplementedError("Q(lambda) with learning_rate=None (1/visits) is not supported on the CUDA path")
+        self.learning_rate = learning_rate
+        self.lambd = lambd
+        self.action_selection = action_selection
+        self.epsilon_start, self.epsilon_end, self.epsilon_decay = epsilon_start, epsilon_end, epsilon_decay
+        self.epsilon = self.epsilon_start
+        self.tosave += ["q_table", "visits", "epsilon"]
+        self._setup(0.0, lambd)
+
+    @property
+    def e_table(self):
+        return self._e[: self.state_space_size, : self.action_space_size]
+
+    def update(self, encoded_state, encoded_next_state, action, reward, terminated, next_action=None, **kwargs):
+        self._device_update(encoded_state, encoded_next_state, action, reward, terminated)
+        if not terminated and next_action is not None:
+            # The "cut traces on an exploratory next action" branch (qlearning_lambda.py:82-84) is unreachable through
+            # AgentRL.update_policy (next_action defaults to the argmax); honour it when a caller passes next_action.
+            # The kernel applied the greedy-branch decay; an exploratory next action wipes the traces instead.
+            row = self.q_table[int(encoded_next_state)]
+            if not bool((row[int(next_action)] == row.max()).item()):
+                self._e.zero_()
+
+    def learn_init_episode(self):
+        self.reset_e_table()
+
+    def reset_e_table(self):
+        self._e.zero_()

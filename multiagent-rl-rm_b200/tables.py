@@ -248,6 +248,7 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
     cfg.seed_lo = sc.seed & 0xFFFFFFFF
     cfg.seed_hi = (sc.seed >> 32) & 0xFFFFFFFF
     cfg.instance_offset = instance_offset
+    cfg.n_actions = 4
     start_cell = np.array([y * W + x for (x, y) in sc.starts], dtype=np.uint16)
     return Compiled(
         scenario=sc, grid=grid, rm=rm,

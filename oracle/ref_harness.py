@@ -66,6 +66,10 @@ class LearnerRNG:
     def uniform(self, lo=0.0, hi=1.0):
         return lo + (hi - lo) * (int(self.src.words(self.i, self.a)[0]) / 4294967296.0)
 
+    def words(self):
+        """Hook used by this repo's learners (learners.py): the four words of the current (t, instance, agent)."""
+        return self.src.words(self.i, self.a)
+
     def choice(self, seq, p=None):
         w = self.src.words(self.i, self.a)
         if isinstance(seq, range):  # rng.choice(range(A)): uniform random action
@@ -81,6 +85,10 @@ class EnvRNG:
     def __init__(self, src, i):
         self.src, self.i = src, i
         self.agent_index = 0
+
+    def words(self, agent_index):
+        """Hook used by this repo's environments (envs.py)."""
+        return self.src.words(self.i, agent_index)
 
     def choice(self, actions, p=None):
         u = int(self.src.words(self.i, self.agent_index)[3]) / 4294967296.0
@@ -176,8 +184,12 @@ FIELDS_I32 = ("cell", "prev_cell", "event_cell", "agent_steps", "timestep")
 FIELDS_F64 = ("renv", "rq", "reward", "epsilon", "q_sa")
 
 
+def _np(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
 def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float32, pre_resets: int = 1,
-                  instance_offset: int = 0, learn: bool = True, snapshot_iters=()):
+                  instance_offset: int = 0, learn: bool = True, snapshot_iters=(), builder=None):
     """Run `n_iters` lockstep iterations (episodes restart back-to-back) for each of `n_instances` independent
     reference environments. Returns dict of arrays shaped [T, N, A] plus final tables [N, A, S, 4]."""
     n_agents = len(sc["starts"])
@@ -190,7 +202,7 @@ def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float
     fl_driver = sc["driver"] == "frozen_lake_main"
 
     for i in range(n_instances):
-        rm_env, env, agents = build_reference(sc, table_dtype)
+        rm_env, env, agents = (builder or build_reference)(sc, table_dtype)
         W = env.grid_width
         for k, ag in enumerate(agents):
             ag.get_learning_algorithm().rng = LearnerRNG(src, i, k)
@@ -247,11 +259,11 @@ def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float
                     out["timestep"][o] = env.timestep
                     out["epsilon"][o] = getattr(ag.get_learning_algorithm(), "epsilon", 0.0)
                     enc = out["prev_cell"][o] * rm.numbers_state() + out["prev_q"][o]
-                    out["q_sa"][o] = ag.get_learning_algorithm().q_table[enc, a_idx]
+                    out["q_sa"][o] = float(ag.get_learning_algorithm().q_table[int(enc), int(a_idx)])
                 states = copy.deepcopy(new_states)
                 t += 1
                 if t in snaps:
-                    snaps[t].append(np.stack([ag.get_learning_algorithm().q_table.copy() for ag in agents]))
+                    snaps[t].append(np.stack([_np(ag.get_learning_algorithm().q_table).copy() for ag in agents]))
                 if fl_driver:
                     over = all(terminated.values()) or all(truncated.values())
                 else:
@@ -259,9 +271,9 @@ def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float
                 if over:
                     out["episode_end"][t - 1, i] = 1
                     break
-        q_final.append(np.stack([ag.get_learning_algorithm().q_table for ag in agents]))
+        q_final.append(np.stack([_np(ag.get_learning_algorithm().q_table) for ag in agents]))
         if sc["algo"] == "qlambda":
-            e_final.append(np.stack([ag.get_learning_algorithm().e_table for ag in agents]))
+            e_final.append(np.stack([_np(ag.get_learning_algorithm().e_table) for ag in agents]))
     out["q_final"] = np.stack(q_final)
     if e_final:
         out["e_final"] = np.stack(e_final)

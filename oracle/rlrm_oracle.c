@@ -108,7 +108,7 @@ static int select_one(const rlrm_config_t* cfg, const real* row, double eps, con
   for (int j = 1; j < 4; j++) if (row[j] > row[va]) va = j;
   if (best) return va;
   double u = (double)w[0] / 4294967296.0; /* rng.uniform(0,1) < epsilon */
-  if (u < eps) return (int)(((uint64_t)w[1] * 4u) >> 32); /* rng.choice(range(4)) */
+  if (u < eps) return (int)(((uint64_t)w[1] * (uint32_t)cfg->n_actions) >> 32); /* rng.choice(range(A)) */
   int maxs[4], n = 0;
   for (int j = 0; j < 4; j++) if (row[j] == row[va]) maxs[n++] = j;
   return maxs[((uint64_t)w[2] * (uint32_t)n) >> 32]; /* rng.choice(maxs) */

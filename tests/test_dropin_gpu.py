@@ -1,0 +1,202 @@
+"""GPU: the reference-shaped object API (envs.py / wrapper.py / agent.py / learners.py) is a drop-in — the reference's
+own driver loop (restated once in oracle/ref_harness.run_reference) runs UNCHANGED over these classes and reproduces,
+bit for bit, what the live reference produced (tests/golden). Also the reference's known-answer unit tests for this
+path, restated against the CUDA-backed classes."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DROPIN_CASES = [
+    ("cfg1_det_qrm", 160), ("cfg3_slip_ql", 200), ("cfg3_slip_qrm", 160), ("fl_qlambda", 120),
+    ("fl_delay_penalty_epsdecay_ql", 200), ("fl_lr_none_ql", 160), ("fl_reward_modifier_qrm", 120),
+    ("fl_none_event_step_cost_ql", 120), ("cfg2_office_slip_ql", 200), ("ow_allslip_wallpen_exp3_qrm", 150),
+    ("ow_terminate_plants_walls_ql", 250), ("cfg4_office_chain12_qlambda", 60),
+]
+
+
+@pytest.mark.parametrize("name,iters", DROPIN_CASES)
+def test_reference_driver_loop_over_dropin_classes(name, iters, cuda_device):
+    import ref_harness as H
+    from dropin_builder import build_b200
+
+    meta, ref = load_golden(name)
+    n = min(2, meta["n_instances"])
+    out = H.run_reference(meta["scenario"], n, iters, pre_resets=meta["pre_resets"], builder=build_b200)
+    for k in ("action", "cell", "prev_cell", "q", "prev_q", "event_cell", "env_term", "rm_term", "term", "trunc", "active",
+              "fail", "agent_steps", "timestep", "renv", "rq", "reward", "epsilon"):
+        assert np.array_equal(out[k], ref[k][:iters, :n]), f"{name}: {k}"
+    # Q value written by each update (float32): pins the learner arithmetic step by step
+    assert np.array_equal(out["q_sa"].astype(np.float32), ref["q_sa"][:iters, :n].astype(np.float32)), f"{name}: q_sa"
+    assert np.array_equal(out["episode_end"], ref["episode_end"][:iters, :n])
+
+
+# ---- the reference's known-answer unit tests, restated ------------------------------------------------------------
+def test_qlearning_update_greedy(cuda_device):
+    """/root/reference/tests/test_qlearning.py:6-27"""
+    import multiagent_rlrm_b200 as P
+
+    ql = P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=1.0, state_space_size=2, action_space_size=2,
+                     qtable_init=1.0)
+    ql.update(encoded_state=0, encoded_next_state=1, action=0, reward=1.0, terminated=False, info={})
+    assert np.isclose(float(ql.q_table[0, 0]), 1.0 + 0.9 * 1.0)
+    assert float(ql.visits[0, 0]) == 1
+
+
+def test_qlearning_epsilon_decay_and_choice(cuda_device):
+    """/root/reference/tests/test_qlearning.py:30-53"""
+    import multiagent_rlrm_b200 as P
+
+    ql = P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=0.5, state_space_size=1, action_space_size=2,
+                     epsilon_start=0.5, epsilon_end=0.1, epsilon_decay=0.5)
+    ql.q_table[0] = np.array([0.2, 0.8])
+    assert ql.choose_action(encoded_state=0, best=True) == 1
+    ql.learn_done_episode()
+    assert np.isclose(ql.epsilon, 0.25)
+    ql.learn_done_episode()
+    assert np.isclose(ql.epsilon, 0.125)
+    ql.learn_done_episode()
+    assert np.isclose(ql.epsilon, 0.1)
+    # epsilon-greedy only ever returns usable actions, and exploits the maximum when epsilon is 0
+    ql.epsilon = 0.0
+    assert all(ql.choose_action(0) == 1 for _ in range(20))
+    ql.epsilon = 1.0
+    assert {ql.choose_action(0) for _ in range(64)} == {0, 1}
+
+
+def test_qlearning_lambda_update_and_traces_decay(cuda_device):
+    """/root/reference/tests/test_qlearning_lambda.py:6-27"""
+    import multiagent_rlrm_b200 as P
+
+    ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=1.0, state_space_size=2,
+                           action_space_size=1)
+    ql.update(encoded_state=0, encoded_next_state=1, action=0, reward=1.0, terminated=False, next_action=0)
+    assert np.isclose(float(ql.q_table[0, 0]), 1.0)
+    assert np.isclose(float(ql.e_table[0, 0]), 0.9 * 0.5)
+
+
+def test_qlearning_lambda_reset_traces(cuda_device):
+    """/root/reference/tests/test_qlearning_lambda.py:30-41"""
+    import multiagent_rlrm_b200 as P
+
+    ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=0.5, state_space_size=1,
+                           action_space_size=1)
+    ql.e_table[0, 0] = 0.7
+    ql.learn_init_episode()
+    assert float(ql.e_table[0, 0]) == 0.0
+
+
+class _StubAgent:
+    """/root/reference/tests/test_ma_frozen_lake.py:18-43"""
+
+    def __init__(self, name, pos):
+        self.name = name
+        self.position = pos
+        self.initial_position = pos
+        self.state = {"pos_x": pos[0], "pos_y": pos[1]}
+        self.reward_machine = None
+
+    def get_position(self):
+        return self.position
+
+    def set_position(self, x, y):
+        self.position = (x, y)
+        self.state["pos_x"], self.state["pos_y"] = x, y
+
+    def set_initial_position(self, x, y):
+        self.initial_position = (x, y)
+        self.set_position(x, y)
+
+    def get_state(self):
+        return self.state
+
+    def reset(self):
+        self.set_position(*self.initial_position)
+
+    def get_learning_algorithm(self):
+        return None
+
+
+def test_frozen_lake_apply_action_bounds(cuda_device):
+    """/root/reference/tests/test_ma_frozen_lake.py:46-58"""
+    import multiagent_rlrm_b200 as P
+
+    env = P.MultiAgentFrozenLake(width=2, height=2, holes=[])
+    ag = _StubAgent("a1", (0, 0))
+    env.add_agent(ag)
+    env.apply_action(ag, "left"); assert ag.get_position() == (0, 0)
+    env.apply_action(ag, "up"); assert ag.get_position() == (0, 0)
+    env.apply_action(ag, "right"); assert ag.get_position() == (1, 0)
+    env.apply_action(ag, "down"); assert ag.get_position() == (1, 1)
+
+
+def test_frozen_lake_stochastic_outcome_sets(cuda_device):
+    """/root/reference/tests/test_ma_frozen_lake.py:61-72"""
+    import multiagent_rlrm_b200 as P
+
+    env = P.MultiAgentFrozenLake(width=3, height=3, holes=[])
+    ag = _StubAgent("a1", (1, 1))
+    env.add_agent(ag)
+    env.frozen_lake_stochastic = True
+    env.reset(7)
+    assert {str(env.get_stochastic_action(ag, "left")) for _ in range(200)} <= {"left", "up", "down"}
+    env.delay_action = True
+    assert {str(env.get_stochastic_action(ag, "up")) for _ in range(400)} <= {"wait", "up", "left", "right"}
+    # and the device-side step only ever lands on the cells those outcomes allow
+    env.delay_action = False
+    seen = set()
+    for seed in range(60):
+        env.reset(seed)
+        obs, rew, term, trunc, infos = env.step({"a1": "left"})
+        seen.add((obs["a1"]["pos_x"], obs["a1"]["pos_y"]))
+    assert seen <= {(0, 1), (1, 0), (1, 2)} and (0, 1) in seen
+
+
+def test_reset_returns_dicts_keyed_by_agent(cuda_device):
+    """/root/reference/tests/test_ma_frozen_lake.py:75-83 ; tests/test_officeworld_environment.py:5-25"""
+    import multiagent_rlrm_b200 as P
+
+    env = P.MultiAgentFrozenLake(width=2, height=2, holes=[])
+    env.agents.append(_StubAgent("a1", (0, 0)))
+    obs, infos = env.reset(1)
+    assert set(obs) == {"a1"} and set(infos) == {"a1"} and obs["a1"] == {"pos_x": 0, "pos_y": 0}
+    ow = P.MultiAgentOfficeWorld(width=3, height=3, plants=[], coffee=[], letters=[], walls=[], plants_penalty_value=-1,
+                                 wall_penalty_value=0, terminate_on_plants=False, terminate_hit_walls=False)
+    ow.agents.append(_StubAgent("a1", (1, 1)))
+    obs, infos = ow.reset(1)
+    assert set(obs) == {"a1"} and set(infos) == {"a1"}
+    obs, rew, term, trunc, infos = ow.step({"a1": "up"})
+    assert (obs["a1"]["pos_x"], obs["a1"]["pos_y"]) == (1, 2)  # OfficeWorld: up is y+1 (ma_office.py:280-281)
+
+
+def test_wrapper_merges_env_and_rm_reward(cuda_device):
+    """/root/reference/tests/test_rm_environment_wrapper.py:70-87: reward = env 0.5 + RM 1.0, termination on RM final,
+    infos prev_q / q. (The env reward comes from a hole penalty here, the reference test uses a dummy env.)"""
+    import multiagent_rlrm_b200 as P
+
+    env = P.MultiAgentFrozenLake(width=2, height=1, holes=[(1, 0)])
+    env.penalty_amount = 0.5
+    ag = P.AgentRL("a1", env)
+    ag.set_initial_position(0, 0)
+    ag.add_state_encoder(P.StateEncoderFrozenLake(ag))
+    ag.add_action_encoder(P.ActionEncoderFrozenLake(ag))
+    ag.set_reward_machine(P.RewardMachine({("q0", (1, 0)): ("qf", 1.0)}, P.PositionEventDetector({(1, 0)})))
+    ag.set_learning_algorithm(P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=1.0, state_space_size=4,
+                                          action_space_size=4, use_qrm=True))
+    env.add_agent(ag)
+    wrap = P.RMEnvironmentWrapper(env, [ag])
+    wrap.reset(0)
+    obs, rewards, terms, truncs, infos = wrap.step({"a1": ag.action("right")})
+    assert rewards["a1"] == 1.5
+    assert terms["a1"] is True and truncs["a1"] is False
+    assert infos["a1"]["prev_q"] == "q0" and infos["a1"]["q"] == "qf"
+    assert infos["a1"]["env_terminated"] is True and infos["a1"]["rm_terminated"] is True
+    # /root/reference/tests/test_rm_environment_wrapper.py:94-107: one experience per state in get_all_states()[:-1]
+    assert len(infos["a1"]["qrm_experience"]) == len(ag.get_reward_machine().get_all_states()) - 1
+    # reward_modifier scales the RM reward only (:110-130)
+    wrap.reset(0)
+    wrap.reward_modifier = 0.5
+    _, rewards, _, _, infos = wrap.step({"a1": ag.action("right")})
+    assert rewards["a1"] == 1.0 and infos["a1"]["RQ"] == 0.5
