@@ -28,6 +28,8 @@ struct KP {
   int A, G, g_shift;  // agents, lane-group size (power of two >= A), log2(G)
   int nQ, nEv, rm_final, n_qrm, max_steps, ncell;
   int stochastic, slip_n;
+  int slip_cnt;              // thresholds below 2^32 (a threshold of 2^32 can never be reached by a 32-bit draw)
+  unsigned slip_thr32[3];
   unsigned long long slip_thr[3];
   unsigned char slip_outcome[16];
   int terminate_on_plants, terminate_hit_walls;
@@ -164,7 +166,7 @@ __device__ __forceinline__ int select_action(const float4& row, unsigned long lo
 __device__ __forceinline__ int slip_outcome(const KP& p, int intended, unsigned k) {
   int idx = 0;
 #pragma unroll
-  for (int j = 0; j < 3; j++) idx += (j + 1 < p.slip_n) && ((unsigned long long)k >= p.slip_thr[j]);
+  for (int j = 0; j < 3; j++) idx += (j < p.slip_cnt) && (k >= p.slip_thr32[j]);
   return p.slip_outcome[intended * 4 + idx];
 }
 
@@ -948,6 +950,12 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.max_steps = cfg->max_steps; kp.ncell = ncell;
   kp.stochastic = cfg->stochastic; kp.slip_n = cfg->slip_n;
   for (int j = 0; j < 3; j++) kp.slip_thr[j] = cfg->slip_thr[j];
+  kp.slip_cnt = 0;
+  for (int j = 0; j + 1 < cfg->slip_n && j < 3; j++) {
+    if (cfg->slip_thr[j] > 0xFFFFFFFFull) break;  // cumulative thresholds are non-decreasing
+    kp.slip_thr32[j] = (unsigned)cfg->slip_thr[j];
+    kp.slip_cnt = j + 1;
+  }
   for (int a = 0; a < 4; a++)
     for (int j = 0; j < 4; j++) kp.slip_outcome[a * 4 + j] = cfg->slip_outcome[a][j];
   kp.terminate_on_plants = cfg->terminate_on_plants; kp.terminate_hit_walls = cfg->terminate_hit_walls;

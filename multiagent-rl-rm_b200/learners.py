@@ -21,6 +21,48 @@ from . import _abi as abi
 from ._lib import check, load
 
 
+class DeviceTable:
+    """(S, A) view of a learner table living in GPU memory, with numpy-style indexing so reference-style code such as
+    ``learner.q_table[s] = np.array([...])`` or ``np.isclose(learner.q_table[s, a], x)`` keeps working.
+    ``.tensor`` is the underlying torch view (no copy); ``np.asarray(table)`` copies to the host."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    shape = property(lambda self: tuple(self.tensor.shape))
+    ndim = property(lambda self: self.tensor.dim())
+    dtype = property(lambda self: np.dtype(str(self.tensor.dtype).replace("torch.", "")))
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+    def __getitem__(self, idx):
+        r = self.tensor[idx]
+        return r.item() if r.dim() == 0 else DeviceTable(r)
+
+    def __setitem__(self, idx, value):
+        if isinstance(value, DeviceTable):
+            value = value.tensor
+        self.tensor[idx] = torch.as_tensor(np.asarray(value) if not torch.is_tensor(value) else value,
+                                           dtype=self.tensor.dtype, device=self.tensor.device)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.tensor.detach().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def copy(self):
+        return np.array(self)
+
+    def fill(self, value):
+        self.tensor.fill_(value)
+
+    def max(self):
+        return self.tensor.max().item()
+
+    def __repr__(self):
+        return f"DeviceTable({np.array(self)!r}, device={self.tensor.device})"
+
+
 def _factor_state_space(S):
     """(cells, nq) with cells * nq >= S, cells <= MAX_CELLS, nq <= MAX_RM_STATES."""
     nq = max(1, -(-S // abi.MAX_CELLS))
@@ -127,15 +169,15 @@ class _TabularBase(BaseLearningAlgorithm):
     # tables as views of exactly (S, A)
     @property
     def q_table(self):
-        return self._q[: self.state_space_size, : self.action_space_size]
+        return DeviceTable(self._q[: self.state_space_size, : self.action_space_size])
 
     @q_table.setter
     def q_table(self, value):
-        self._q[: self.state_space_size, : self.action_space_size].copy_(torch.as_tensor(value, dtype=torch.float32))
+        self.q_table[:] = value
 
     @property
     def visits(self):
-        return self._visits[: self.state_space_size, : self.action_space_size]
+        return DeviceTable(self._visits[: self.state_space_size, : self.action_space_size])
 
     def _state(self):
         return abi.State(1, self._slot.data_ptr(), self._eps.data_ptr(), self._q.data_ptr(),
@@ -262,7 +304,7 @@ class QLearningLambda(_TabularBase):
 
     @property
     def e_table(self):
-        return self._e[: self.state_space_size, : self.action_space_size]
+        return DeviceTable(self._e[: self.state_space_size, : self.action_space_size])
 
     def update(self, encoded_state, encoded_next_state, action, reward, terminated, next_action=None, **kwargs):
         self._device_update(encoded_state, encoded_next_state, action, reward, terminated)
@@ -271,7 +313,7 @@ class QLearningLambda(_TabularBase):
             # AgentRL.update_policy (next_action defaults to the argmax); honour it when a caller passes next_action.
             # The kernel applied the greedy-branch decay; an exploratory next action wipes the traces instead.
             row = self.q_table[int(encoded_next_state)]
-            if not bool((row[int(next_action)] == row.max()).item()):
+            if not (row[int(next_action)] == row.max()):
                 self._e.zero_()
 
     def learn_init_episode(self):

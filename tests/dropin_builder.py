@@ -45,7 +45,7 @@ def build_b200(sc, table_dtype=None):
                       epsilon_decay=sc["epsilon_decay"])
         if sc["algo"] == "qlambda":
             learner = P.QLearningLambda(lambd=sc["lambd"], **common)
-            learner.q_table = learner.q_table * 0 + sc["q_init"]
+            learner.q_table.fill(sc["q_init"])
         else:
             learner = P.QLearning(qtable_init=sc["q_init"], use_qrm=(sc["algo"] == "qrm"), **common)
         ag.set_learning_algorithm(learner)

@@ -41,8 +41,8 @@ def test_qlearning_update_greedy(cuda_device):
     ql = P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=1.0, state_space_size=2, action_space_size=2,
                      qtable_init=1.0)
     ql.update(encoded_state=0, encoded_next_state=1, action=0, reward=1.0, terminated=False, info={})
-    assert np.isclose(float(ql.q_table[0, 0]), 1.0 + 0.9 * 1.0)
-    assert float(ql.visits[0, 0]) == 1
+    assert np.isclose(ql.q_table[0, 0], 1.0 + 0.9 * 1.0)
+    assert ql.visits[0, 0] == 1
 
 
 def test_qlearning_epsilon_decay_and_choice(cuda_device):
@@ -73,8 +73,8 @@ def test_qlearning_lambda_update_and_traces_decay(cuda_device):
     ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=1.0, state_space_size=2,
                            action_space_size=1)
     ql.update(encoded_state=0, encoded_next_state=1, action=0, reward=1.0, terminated=False, next_action=0)
-    assert np.isclose(float(ql.q_table[0, 0]), 1.0)
-    assert np.isclose(float(ql.e_table[0, 0]), 0.9 * 0.5)
+    assert np.isclose(ql.q_table[0, 0], 1.0)
+    assert np.isclose(ql.e_table[0, 0], 0.9 * 0.5)
 
 
 def test_qlearning_lambda_reset_traces(cuda_device):
@@ -85,7 +85,7 @@ def test_qlearning_lambda_reset_traces(cuda_device):
                            action_space_size=1)
     ql.e_table[0, 0] = 0.7
     ql.learn_init_episode()
-    assert float(ql.e_table[0, 0]) == 0.0
+    assert ql.e_table[0, 0] == 0.0
 
 
 class _StubAgent:
