@@ -144,6 +144,11 @@ typedef struct rlrm_state {
   uint32_t* visits;     /* optional [same shape as q]: learner.visits; required when learning_rate < 0 */
   double* ep_return;    /* [N*A] running (undiscounted) return of the current episode */
   rlrm_stats_t* stats;  /* [N*A] or NULL */
+  /* shared_q only (one table per agent index, every instance on this GPU learns into it): per-iteration proposal
+   * accumulators, each [A*S*4], zero-initialised by the caller. See "shared learner" below. */
+  int64_t* acc_sum;     /* sum of round(new_value * 2^20) over the instances that updated the entry this iteration */
+  int32_t* acc_cnt;     /* number of such instances */
+  float* acc_last;      /* the new value itself (used verbatim when acc_cnt == 1) */
 } rlrm_state_t;
 
 /* device pointers, caller-owned, each [N*A]; any may be NULL (not written) */
@@ -205,6 +210,15 @@ int rlrm_rm_step(rlrm_handle_t* h, int64_t n_slots, uint8_t* q, const uint16_t* 
  * term_arg: device uint8 [N*A], the `terminated` argument the driver passes. `out` is the record rlrm_step wrote. */
 int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_cell, const uint8_t* actions,
                 const uint8_t* term_arg, const rlrm_step_out_t* out, void* stream);
+
+/* Shared learner (cfg.shared_q = 1; BASELINE config 5). The reference has no shared learner, so the merge rule is
+ * specified here: iterations are synchronous. Within one lockstep iteration every instance selects and computes its
+ * update_q result ("proposal") against the SAME table snapshot; afterwards each touched entry becomes the mean of its
+ * proposals: Q[s,a] = proposal if one instance proposed, else (float)((double)acc_sum / acc_cnt * 2^-20). Sums are
+ * integers, so the result does not depend on thread order or on how instances are spread over blocks/GPUs.
+ * With a single instance this is exactly the per-instance learner (for reward machines whose counterfactual updates
+ * do not read each other's writes, e.g. chains). rlrm_train runs two kernels per iteration in this mode.
+ * Inter-GPU merging (every K iterations) is the caller's step: all-reduce `q` (see dist.py). */
 
 /* One launch = n_iters lockstep iterations of the driver loop (select for all agents -> wrapper step -> update for
  * all agents -> per-instance auto reset when the episode ends), state in registers, Philox draws for iterations

@@ -96,6 +96,9 @@ class State(C.Structure):
         ("visits", C.c_void_p),
         ("ep_return", C.c_void_p),
         ("stats", C.c_void_p),
+        ("acc_sum", C.c_void_p),
+        ("acc_cnt", C.c_void_p),
+        ("acc_last", C.c_void_p),
     ]
 
 

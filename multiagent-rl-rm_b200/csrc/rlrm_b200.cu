@@ -65,6 +65,15 @@ struct DState {  // rlrm_state_t by value
   unsigned* visits;
   double* ep_return;
   rlrm_stats_t* stats;
+  long long* acc_sum;  // shared learner accumulators (include/rlrm_b200.h "Shared learner"), null otherwise
+  int* acc_cnt;
+  float* acc_last;
+};
+
+struct Acc {  // accumulators of one agent's shared table, or nulls
+  long long* sum;
+  int* cnt;
+  float* last;
 };
 
 struct DOut {  // rlrm_step_out_t by value
@@ -266,7 +275,8 @@ __device__ __forceinline__ float row_max(const float4& v) { return fmaxf(fmaxf(v
 
 // update_q (qlearning.py:70-79) in the float32 arithmetic numpy performs on a float32 table: weak Python scalars are
 // rounded to float32 first, every operation rounds separately (no FMA contraction).
-__device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, unsigned s, int a, double r, unsigned sn, bool terminated) {
+__device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, unsigned s, int a, double r, unsigned sn, bool terminated,
+                                         const Acc& acc) {
   const float cur = Q[s * 4 + a];
   const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
   const float mf = __fmul_rn(terminated ? 0.0f : 1.0f, row_max(nrow));
@@ -281,13 +291,19 @@ __device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, uns
     if (V) V[s * 4 + a] += 1;
     out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
   }
-  Q[s * 4 + a] = out;
+  if (acc.sum) {  // shared learner: propose; apply_shared_kernel turns the proposals of this iteration into their mean
+    atomicAdd(reinterpret_cast<unsigned long long*>(acc.sum + s * 4 + a), (unsigned long long)__float2ll_rn(__fmul_rn(out, 1048576.0f)));
+    atomicAdd(acc.cnt + s * 4 + a, 1);
+    acc.last[s * 4 + a] = out;
+  } else {
+    Q[s * 4 + a] = out;
+  }
 }
 
 // QL / QRM update of one agent (agent_rl.py:117-192 -> qlearning.py:41-110; QRM experiences rm_environment_wrapper.py:122-183)
 template <int ALGO>
 __device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, float* Q, unsigned* V, unsigned obs_cell, int action,
-                                             bool term_arg, const Rec& r) {
+                                             bool term_arg, const Rec& r, const Acc& acc) {
   if (ALGO == RLRM_ALGO_QRM) {
     const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
     for (int j = 0; j < p.n_qrm; j++) {
@@ -296,10 +312,10 @@ __device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, float* 
       const unsigned un = d == RLRM_NO_TRANSITION ? u : d;
       const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
       const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
-      update_q(p, Q, V, r.prev_cell * p.nQ + u, action, __dadd_rn(r.renv, ru), r.cell * p.nQ + un, done);
+      update_q(p, Q, V, r.prev_cell * p.nQ + u, action, __dadd_rn(r.renv, ru), r.cell * p.nQ + un, done, acc);
     }
   } else {
-    update_q(p, Q, V, obs_cell * p.nQ + r.prev_q, action, r.reward, r.cell * p.nQ + r.q, term_arg);
+    update_q(p, Q, V, obs_cell * p.nQ + r.prev_q, action, r.reward, r.cell * p.nQ + r.q, term_arg, acc);
   }
 }
 
@@ -314,6 +330,15 @@ __device__ __forceinline__ void reset_slot(const KP& p, const Tab& tb, int a, Sl
 
 __device__ __forceinline__ size_t table_base(const KP& p, long long i, int a) {
   return (size_t)(p.shared_q ? (long long)a : i * p.A + a) * (size_t)p.S4;
+}
+__device__ __forceinline__ Acc make_acc(const KP& p, const DState& st, size_t base) {
+  Acc acc = {nullptr, nullptr, nullptr};
+  if (p.shared_q && st.acc_sum) {
+    acc.sum = st.acc_sum + base;
+    acc.cnt = st.acc_cnt + base;
+    acc.last = st.acc_last + base;
+  }
+  return acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,7 +460,8 @@ __global__ void __launch_bounds__(256) update_kernel(KP p, DState st, const unsi
   r.prev_cell = o.prev_cell[k]; r.cell = o.cell[k]; r.prev_q = o.prev_q[k]; r.q = o.q[k]; r.event = o.event[k];
   r.env_term = o.env_term[k] != 0; r.renv = o.renv[k]; r.reward = o.reward[k];
   const size_t base = table_base(p, i, a);
-  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, obs_cell[k], actions[k], term_arg[k] != 0, r);
+  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, obs_cell[k], actions[k], term_arg[k] != 0, r,
+                     make_acc(p, st, base));
 }
 
 // QLearningLambda.update (qlearning_lambda.py:33-84), dense sweep exactly as written: one block per (instance, agent).
@@ -504,6 +530,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
   double eps = 0.0, ep_ret = 0.0;
   float* Q = nullptr;
   unsigned* V = nullptr;
+  Acc acc = {nullptr, nullptr, nullptr};
   unsigned long long active_steps = 0;
   unsigned episodes = 0, successes = 0, last_length = 0;
   double return_sum = 0.0;
@@ -516,6 +543,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
     const size_t base = table_base(p, i, a);
     Q = st.q + base;
     V = st.visits ? st.visits + base : nullptr;
+    acc = make_acc(p, st, base);
   }
   unsigned long long explore_thr = explore_threshold(eps);
   bool had_episode = false;
@@ -539,7 +567,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
         // receives the NEW position as `state` (frozen_lake_main.py:337,359 ; office_main.py:1700 deep-copies)
         const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
         const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
-        agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r);
+        agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r, acc);
       }
       term = r.term;
       trunc = r.trunc;
@@ -868,6 +896,18 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
   }
 }
 
+// shared learner: every touched entry becomes the mean of this iteration's proposals; accumulators are cleared
+__global__ void __launch_bounds__(256) apply_shared_kernel(KP p, DState st) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (long long)p.A * p.S4) return;
+  const int c = st.acc_cnt[j];
+  if (c == 0) return;
+  if (c == 1) st.q[j] = st.acc_last[j];
+  else st.q[j] = __double2float_rn(__dmul_rn(__ddiv_rn((double)st.acc_sum[j], (double)c), 9.5367431640625e-07));
+  st.acc_cnt[j] = 0;
+  st.acc_sum[j] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: handle + C ABI
 // ------------------------------------------------------------------------------------------------
@@ -1027,6 +1067,7 @@ static DState dstate(const rlrm_state_t* st) {
   DState d;
   d.N = st->n_instances; d.slot = (unsigned long long*)st->slot; d.epsilon = st->epsilon; d.q = st->q; d.e = st->e;
   d.visits = st->visits; d.ep_return = st->ep_return; d.stats = st->stats;
+  d.acc_sum = (long long*)st->acc_sum; d.acc_cnt = st->acc_cnt; d.acc_last = st->acc_last;
   return d;
 }
 static DOut dout(const rlrm_step_out_t* o) {
@@ -1047,6 +1088,9 @@ static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need
   if (need_q && !st->q) return fail(RLRM_ERR_ARG, "state.q is required");
   if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e");
   if (need_q && h->cfg.learning_rate < 0 && !st->visits) return fail(RLRM_ERR_ARG, "learning_rate=None needs state.visits");
+  if (need_q && h->cfg.shared_q && h->cfg.learning_rate < 0) return fail(RLRM_ERR_UNSUPPORTED, "shared table with learning_rate=None");
+  if (need_q && h->cfg.shared_q && (!st->acc_sum || !st->acc_cnt || !st->acc_last))
+    return fail(RLRM_ERR_ARG, "shared_q needs state.acc_sum / acc_cnt / acc_last");
   return RLRM_OK;
 }
 
@@ -1129,6 +1173,10 @@ extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint1
   else
     update_kernel<RLRM_ALGO_QL><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
   LAUNCH_CHECK(h);
+  if (h->kp.shared_q) {
+    apply_shared_kernel<<<blocks_for((long long)h->kp.A * h->kp.S4, 256), 256, 0, s>>>(h->kp, dstate(st));
+    LAUNCH_CHECK(h);
+  }
   return RLRM_OK;
 }
 
@@ -1157,6 +1205,21 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
   if (n_iters == 0) return RLRM_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.shared_q) {
+    // synchronous iterations: one propose launch over all instances + one apply launch per lockstep iteration
+    const size_t stride = (size_t)st->n_instances * h->kp.A;
+    for (int it = 0; it < n_iters; it++) {
+      uint32_t* tr = trace ? trace + (size_t)it * stride : nullptr;
+      if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t0 + it, 1, learn, tr, s);
+      else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t0 + it, 1, learn, tr, s);
+      LAUNCH_CHECK(h);
+      if (learn) {
+        apply_shared_kernel<<<blocks_for((long long)h->kp.A * h->kp.S4, 256), 256, 0, s>>>(h->kp, dstate(st));
+        LAUNCH_CHECK(h);
+      }
+    }
+    return RLRM_OK;
+  }
   if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t0, n_iters, learn, trace, s);
   else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t0, n_iters, learn, trace, s);
   LAUNCH_CHECK(h);

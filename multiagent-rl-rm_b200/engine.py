@@ -53,8 +53,12 @@ class Engine:
         self.visits = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if need_visits else None
         self.ep_return = torch.zeros(n_slots, dtype=torch.float64, device=d)
         self.stats = torch.zeros((n_slots, 32), dtype=torch.uint8, device=d) if with_stats else None
+        shared = bool(self.cfg.shared_q)
+        self.acc_sum = torch.zeros((n_tab, self.S, 4), dtype=torch.int64, device=d) if shared else None
+        self.acc_cnt = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if shared else None
+        self.acc_last = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if shared else None
         self.state = abi.State(self.N, _ptr(self.slot), _ptr(self.epsilon), _ptr(self.q), _ptr(self.e), _ptr(self.visits),
-                               _ptr(self.ep_return), _ptr(self.stats))
+                               _ptr(self.ep_return), _ptr(self.stats), _ptr(self.acc_sum), _ptr(self.acc_cnt), _ptr(self.acc_last))
         self.t = 0  # lockstep iteration counter (Philox counter word)
 
     def __del__(self):

@@ -181,7 +181,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     def _state(self):
         return abi.State(1, self._slot.data_ptr(), self._eps.data_ptr(), self._q.data_ptr(),
-                         None if self._e is None else self._e.data_ptr(), self._visits.data_ptr(), None, None)
+                         None if self._e is None else self._e.data_ptr(), self._visits.data_ptr(), None, None, None, None, None)
 
     def _sync_hyper(self):
         hp = (self.learning_rate, self.gamma, getattr(self, "lambd", 0.0))

@@ -73,8 +73,12 @@ class Oracle:
         self.visits = np.zeros((n_tab, self.S, 4), dtype=np.uint32) if need_visits else None
         self.ep_return = np.zeros(self.N * self.A, dtype=np.float64)
         self.stats = np.zeros(self.N * self.A, dtype=STATS_DTYPE)
+        shared = bool(self.cfg.shared_q)
+        self.acc_sum = np.zeros((n_tab, self.S, 4), dtype=np.int64) if shared else None
+        self.acc_cnt = np.zeros((n_tab, self.S, 4), dtype=np.int32) if shared else None
+        self.acc_last = np.zeros((n_tab, self.S, 4), dtype=np.float32) if shared else None
         self.state = abi.State(self.N, _p(self.slot), _p(self.epsilon), _p(self.q), _p(self.e), _p(self.visits),
-                               _p(self.ep_return), _p(self.stats))
+                               _p(self.ep_return), _p(self.stats), _p(self.acc_sum), _p(self.acc_cnt), _p(self.acc_last))
 
     # -- C calls -------------------------------------------------------------------------------
     def reset(self, mask=None):

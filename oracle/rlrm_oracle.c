@@ -280,7 +280,10 @@ static real row_max(const real* row) { /* np.max */
   return m;
 }
 
-static void update_q(const rlrm_config_t* cfg, real* Q, uint32_t* visits, size_t s, int a, double r, size_t sn, int terminated) {
+typedef struct { int64_t* sum; int32_t* cnt; float* last; } acc_t; /* shared learner: per-agent-table accumulators */
+
+static void update_q(const rlrm_config_t* cfg, real* Q, uint32_t* visits, size_t s, int a, double r, size_t sn, int terminated,
+                     const acc_t* acc) {
   real cur = Q[s * 4 + a];
   if (visits) visits[s * 4 + a] += 1;
   real mf = (real)(terminated ? 0 : 1) * row_max(Q + sn * 4); /* (not terminated) * np.max(q_table[sn]) */
@@ -290,7 +293,14 @@ static void update_q(const rlrm_config_t* cfg, real* Q, uint32_t* visits, size_t
     Q[s * 4 + a] = (real)((1.0 - lr) * (double)cur + lr * (double)inner);
   } else {
     double lr = cfg->learning_rate;
-    Q[s * 4 + a] = (real)(1.0 - lr) * cur + (real)lr * inner;
+    real nv = (real)(1.0 - lr) * cur + (real)lr * inner;
+    if (acc) { /* shared learner: propose instead of writing (include/rlrm_b200.h, "Shared learner") */
+      acc->sum[s * 4 + a] += llrintf((float)nv * 1048576.0f);
+      acc->cnt[s * 4 + a] += 1;
+      acc->last[s * 4 + a] = (float)nv;
+    } else {
+      Q[s * 4 + a] = nv;
+    }
   }
 }
 
@@ -318,6 +328,12 @@ static void update_slot(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const
   size_t base = table_base(cfg, i, a);
   real* Q = (real*)st->q + base;
   uint32_t* V = st->visits ? st->visits + base : NULL;
+  acc_t acc = {NULL, NULL, NULL};
+  const acc_t* accp = NULL;
+  if (cfg->shared_q && st->acc_sum) {
+    acc.sum = st->acc_sum + base; acc.cnt = st->acc_cnt + base; acc.last = st->acc_last + base;
+    accp = &acc;
+  }
   if (cfg->algo == RLRM_ALGO_QRM) { /* rm_environment_wrapper.py:122-183 -> qlearning.py:82-106 */
     int col = r->event == RLRM_EVENT_NONE ? nEv : (int)r->event;
     for (int j = 0; j < cfg->n_qrm_states; j++) {
@@ -326,11 +342,11 @@ static void update_slot(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const
       int un = d == RLRM_NO_TRANSITION ? u : d;
       double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb->rcf[u * (nEv + 1) + col];
       int done = r->env_term || (cfg->rm_final >= 0 && un == cfg->rm_final);
-      update_q(cfg, Q, V, (size_t)r->prev_cell * nQ + u, action, r->renv + ru, (size_t)r->cell * nQ + un, done);
+      update_q(cfg, Q, V, (size_t)r->prev_cell * nQ + u, action, r->renv + ru, (size_t)r->cell * nQ + un, done, accp);
     }
   } else {
     size_t s = (size_t)obs_cell * nQ + r->prev_q, sn = (size_t)r->cell * nQ + r->q; /* agent_rl.py:154-155 */
-    if (cfg->algo == RLRM_ALGO_QL) update_q(cfg, Q, V, s, action, r->reward, sn, term_arg);
+    if (cfg->algo == RLRM_ALGO_QL) update_q(cfg, Q, V, s, action, r->reward, sn, term_arg, accp);
     else update_qlambda(cfg, Q, (real*)st->e + base, V, S, s, action, r->reward, sn, term_arg);
   }
 }
@@ -350,60 +366,81 @@ int oracle_update(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_
 }
 
 /* ---- driver loop: frozen_lake_main.py:345-376 ; office_main.py:1709-1749 --------------------------- */
-int oracle_train(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, uint64_t t0, int32_t n_iters,
-                 int32_t learn, uint32_t* trace) {
+static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i, uint64_t t,
+                            int32_t it, int32_t learn, uint32_t* trace) {
   int A = cfg->n_agents;
   rec_t rec[RLRM_MAX_AGENTS];
   uint8_t act[RLRM_MAX_AGENTS];
-  for (int64_t i = 0; i < st->n_instances; i++) {
-    for (int32_t it = 0; it < n_iters; it++) {
-      uint64_t t = t0 + (uint64_t)it;
-      uint32_t before[RLRM_MAX_AGENTS];
-      int first = 0;
-      for (int a = 0; a < A; a++) { /* every agent selects, finished ones included (:350-352) */
-        size_t k = (size_t)i * A + a;
+  uint32_t before[RLRM_MAX_AGENTS];
+  int first = 0;
+  for (int a = 0; a < A; a++) { /* every agent selects, finished ones included (:350-352) */
+    size_t k = (size_t)i * A + a;
+    slot_t s = unpack(st->slot[k]);
+    before[a] = s.cell;
+    first = (s.flags & RLRM_FLAG_FIRST) != 0;
+    const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * cfg->n_rm_states + s.rm) * 4;
+    uint32_t w[4];
+    get_draws(cfg, NULL, t, i, a, w);
+    act[a] = (uint8_t)select_one(cfg, row, st->epsilon[k], w, !learn); /* learn == 0: greedy evaluation, best=True */
+  }
+  step_instance(cfg, tb, st, i, act, NULL, t, 1, rec);
+  int all_term = 1, all_trunc = 1;
+  for (int a = 0; a < A; a++) {
+    size_t k = (size_t)i * A + a;
+    /* FrozenLake driver: on the first iteration `states` still aliases agent.state (frozen_lake_main.py:337 vs
+     * office_main.py:1700 which deep-copies) so update_policy sees the NEW position as `state`. */
+    uint32_t obs = (cfg->driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? rec[a].cell : before[a];
+    int term_arg = cfg->driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (rec[a].term || rec[a].trunc) : rec[a].term;
+    if (learn) update_slot(cfg, tb, st, i, a, obs, act[a], term_arg, &rec[a]);
+    all_term &= (int)rec[a].term; all_trunc &= (int)rec[a].trunc;
+    if (st->ep_return) st->ep_return[k] += rec[a].reward;
+    if (st->stats) st->stats[k].active_steps += rec[a].stepped;
+    if (trace)
+      trace[(size_t)it * st->n_instances * A + k] = (uint32_t)act[a] | (rec[a].executed << 3) | (rec[a].cell << 6) |
+          (rec[a].q << 16) | (rec[a].term << 21) | (rec[a].trunc << 22) | (rec[a].stepped << 23);
+  }
+  clear_first(cfg, st, i);
+  if (all_term || all_trunc) { /* episode over -> next episode starts with rm_env.reset (:337 / :1699) */
+    for (int a = 0; a < A; a++) {
+      size_t k = (size_t)i * A + a;
+      if (st->stats) {
         slot_t s = unpack(st->slot[k]);
-        before[a] = s.cell;
-        first = (s.flags & RLRM_FLAG_FIRST) != 0;
-        const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * cfg->n_rm_states + s.rm) * 4;
-        uint32_t w[4];
-        get_draws(cfg, NULL, t, i, a, w);
-        act[a] = (uint8_t)select_one(cfg, row, st->epsilon[k], w, !learn); /* learn == 0: greedy evaluation, best=True */
-      }
-      step_instance(cfg, tb, st, i, act, NULL, t, 1, rec);
-      int all_term = 1, all_trunc = 1;
-      for (int a = 0; a < A; a++) {
-        size_t k = (size_t)i * A + a;
-        /* FrozenLake driver: on the first iteration `states` still aliases agent.state (frozen_lake_main.py:337 vs
-         * office_main.py:1700 which deep-copies) so update_policy sees the NEW position as `state`. */
-        uint32_t obs = (cfg->driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? rec[a].cell : before[a];
-        int term_arg = cfg->driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (rec[a].term || rec[a].trunc) : rec[a].term;
-        if (learn) update_slot(cfg, tb, st, i, a, obs, act[a], term_arg, &rec[a]);
-        all_term &= (int)rec[a].term; all_trunc &= (int)rec[a].trunc;
-        if (st->ep_return) st->ep_return[k] += rec[a].reward;
-        if (st->stats) st->stats[k].active_steps += rec[a].stepped;
-        if (trace)
-          trace[(size_t)it * st->n_instances * A + k] = (uint32_t)act[a] | (rec[a].executed << 3) | (rec[a].cell << 6) |
-              (rec[a].q << 16) | (rec[a].term << 21) | (rec[a].trunc << 22) | (rec[a].stepped << 23);
-      }
-      clear_first(cfg, st, i);
-      if (all_term || all_trunc) { /* episode over -> next episode starts with rm_env.reset (:337 / :1699) */
-        for (int a = 0; a < A; a++) {
-          size_t k = (size_t)i * A + a;
-          if (st->stats) {
-            slot_t s = unpack(st->slot[k]);
-            rlrm_stats_t* z = &st->stats[k];
-            z->episodes++;
-            z->successes += (cfg->rm_final >= 0 && (int)s.rm == cfg->rm_final);
-            double ret = st->ep_return ? st->ep_return[k] : 0.0;
-            z->last_return = (float)ret;
-            z->return_sum += ret;
-            z->last_length = s.time;
-          }
-        }
-        reset_instance(cfg, tb, st, i);
+        rlrm_stats_t* z = &st->stats[k];
+        z->episodes++;
+        z->successes += (cfg->rm_final >= 0 && (int)s.rm == cfg->rm_final);
+        double ret = st->ep_return ? st->ep_return[k] : 0.0;
+        z->last_return = (float)ret;
+        z->return_sum += ret;
+        z->last_length = s.time;
       }
     }
+    reset_instance(cfg, tb, st, i);
+  }
+}
+
+/* shared learner: every touched entry becomes the mean of this iteration's proposals (include/rlrm_b200.h) */
+static void apply_shared(const rlrm_config_t* cfg, const rlrm_state_t* st) {
+  size_t n = (size_t)cfg->n_agents * cfg->width * cfg->height * cfg->n_rm_states * 4;
+  real* Q = (real*)st->q;
+  for (size_t j = 0; j < n; j++) {
+    int32_t c = st->acc_cnt[j];
+    if (c == 1) Q[j] = (real)st->acc_last[j];
+    else if (c > 1) Q[j] = (real)(float)((double)st->acc_sum[j] / (double)c * 9.5367431640625e-07);
+    st->acc_cnt[j] = 0; st->acc_sum[j] = 0;
+  }
+}
+
+/* ---- driver loop: frozen_lake_main.py:345-376 ; office_main.py:1709-1749 --------------------------- */
+int oracle_train(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, uint64_t t0, int32_t n_iters,
+                 int32_t learn, uint32_t* trace) {
+  if (cfg->shared_q) { /* synchronous iterations over all instances */
+    for (int32_t it = 0; it < n_iters; it++) {
+      for (int64_t i = 0; i < st->n_instances; i++) train_iteration(cfg, tb, st, i, t0 + (uint64_t)it, it, learn, trace);
+      if (learn && st->acc_sum) apply_shared(cfg, st);
+    }
+  } else { /* instances are independent */
+    for (int64_t i = 0; i < st->n_instances; i++)
+      for (int32_t it = 0; it < n_iters; it++) train_iteration(cfg, tb, st, i, t0 + (uint64_t)it, it, learn, trace);
   }
   return 0;
 }

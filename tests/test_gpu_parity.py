@@ -189,3 +189,35 @@ def test_full_size_config3_windows_match_oracle(cuda_device):
     assert (s["timestep"] <= 1001).all() and (s["agent_steps"] <= s["timestep"]).all()
     assert int(stats["active_steps"].sum()) <= n * 2 * iters
     assert np.isfinite(q).all()
+
+
+def test_shared_learner_matches_oracle(cuda_device):
+    """BASELINE config 5 shared-learner mode (one table per agent index, synchronous proposal averaging):
+    the integer accumulation makes the CUDA result independent of thread order, so it equals the oracle bit for bit."""
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    sc = P.scenario_config5(shared=True)
+    c = P.compile_scenario(sc)
+    n, iters = 3000, 160
+    eng = _engine(c, n)
+    o = O.Oracle(c, n, "f32")
+    eng.reset(); o.reset()
+    tr_g = eng.train(iters, trace=True)
+    tr_o = o.train(0, iters, trace=True)
+    assert np.array_equal(tr_g.cpu().numpy().view(np.uint32), tr_o)
+    _compare_with_oracle(eng, o, "shared learner")
+    assert int(eng.acc_cnt.abs().sum()) == 0 and int(eng.acc_sum.abs().sum()) == 0  # accumulators are left clean
+
+
+def test_shared_learner_with_one_instance_is_the_reference_learner(cuda_device):
+    """Degenerate tie to the reference: N = 1 shared == per-instance tables (which equal the reference trace)."""
+    import multiagent_rlrm_b200 as P
+
+    a = _engine(P.compile_scenario(P.scenario_config5(shared=True)), 1)
+    b = _engine(P.compile_scenario(P.scenario_config5(shared=False)), 1)
+    a.reset(); b.reset()
+    ta, tb = a.train(900, trace=True), b.train(900, trace=True)
+    assert np.array_equal(ta.cpu().numpy(), tb.cpu().numpy())
+    assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy())
+    assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
