@@ -26,8 +26,8 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 
 METRIC = "agent-steps/sec (env+RM+Q update)"
 UNIT = "agent-steps/s"
-QRM_BYTES_PER_STEP = 140  # read cell block s (64) + read cell block s' (64) + 3 writes x 4 B, nQ = 4
-QL_BYTES_PER_STEP = 36    # read Q[s,:] 16 + read Q[s',:] 16 + write 4
+# algorithmic bytes per active agent-step: QRM nQ=4: cell block s 64 + cell block s' 64 + 3 writes x 4 B
+# = 140; plain QL: Q[s,:] 16 + Q[s',:] 16 + 4 = 36; dense Q(lambda): (q + e) read + write = 4 * S*A * 4 B
 
 
 def parse_args():
@@ -35,34 +35,76 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--iters", type=int, default=2048, help="lockstep iterations per launch (= per bench step)")
-    ap.add_argument("--instances", type=int, default=65536, help="environment instances per GPU")
-    ap.add_argument("--algo", default="qrm", choices=["qrm", "ql"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
+                    help="cfg3 = the headline (BASELINE configs[2]); the others are extra measured lines")
+    ap.add_argument("--iters", type=int, default=None, help="lockstep iterations per launch (= per bench step)")
+    ap.add_argument("--instances", type=int, default=None, help="environment instances per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def scenario(algo):
+# name -> (description, BASELINE config, default instances/GPU, default iters/launch, algorithmic bytes per active
+#          agent-step, dominant kernel)
+WORKLOADS = {
+    "cfg3": ("FrozenLake map1 (10x10), 2 agents, slippery 80/10/10, RM A->B->C (10/15/20), QLearning lr=1 gamma=.99 eps=.01 "
+             "init=2 use_qrm=True, per-instance Q tables, auto-reset",
+             "configs[2]: 65,536 batched FrozenLake map1 instances x 2 agents, slippery, per-instance Q-tables",
+             65536, 2048, 140, "train_qrm4_kernel<FrozenLake>"),
+    "cfg3_ql": ("FrozenLake map1, 2 agents, slippery, RM A->B->C, QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False, "
+                "per-instance Q tables, auto-reset",
+                "configs[2] companion (plain Q-learning variant, SURVEY.md §8d)", 65536, 2048, 36, "train_kernel<FrozenLake,QL>"),
+    "cfg4": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, plants -100, synthetic 12-state completed chain RM (108 "
+             "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, dense-faithful trace sweep",
+             "configs[3]: OfficeWorld 12-state RM, 262,144 instances x 4 agents, Q(lambda) traces",
+             262144, 4, 4 * 1296 * 4 * 4, "train_qlambda_kernel<OfficeWorld>"),
+    "cfg5_tables": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, per-instance Q tables",
+                    "configs[4] HBM-bound companion: 1M FrozenLake instances x 4 agents, per-instance tables",
+                    1048576, 256, 140, "train_qrm4_kernel<FrozenLake>"),
+    "cfg5_shared": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, ONE table per agent index per GPU "
+                    "(shared learner, synchronous proposal averaging), all-reduced every 64 iterations",
+                    "configs[4]: 1M FrozenLake instances x 4 agents, shared-learner Q-table allreduce over NVLink every K steps",
+                    1048576, 64, 140, "train_kernel<FrozenLake,QRM> + apply_shared_kernel (L2/atomic bound, not HBM)"),
+}
+
+
+def scenario(workload):
     import multiagent_rlrm_b200 as P
 
-    return P.scenario_config3(use_qrm=(algo == "qrm"))
+    return {"cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
+            "cfg4": P.scenario_config4, "cfg5_tables": lambda: P.scenario_config5(False),
+            "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
+
+
+def resolve_defaults(args):
+    w = WORKLOADS[args.workload]
+    if args.instances is None:
+        args.instances = w[2]
+    if args.iters is None:
+        args.iters = w[3]
+    return args
 
 
 def workload_config(args, world):
+    desc, base, _n, _t, _b, _k = WORKLOADS[args.workload]
+    sc = scenario(args.workload)
+    agents = len(sc.starts)
+    g = sc.grid()
+    n_rm = sc.reward_machine().numbers_state()
+    table_bytes = g.width * g.height * n_rm * 4 * 4 * (2 if sc.algo == "qlambda" else 1)
+    per_gpu = table_bytes * agents * (1 if sc.shared_q else args.instances)
     return {
-        "workload": "FrozenLake map1 (10x10), 2 agents, slippery 80/10/10, RM A->B->C (10/15/20), "
-                    + ("QLearning lr=1 gamma=.99 eps=.01 init=2 use_qrm=True" if args.algo == "qrm"
-                       else "QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False")
-                    + ", per-instance Q tables, auto-reset",
-        "baseline_config": "configs[2]: 65,536 batched FrozenLake map1 instances x 2 agents, slippery, per-instance Q-tables",
+        "workload": desc,
+        "baseline_config": base,
         "instances_per_gpu": args.instances,
-        "agents": 2,
+        "agents": agents,
         "iters_per_step": args.iters,
-        "q_table_bytes_per_gpu": args.instances * 2 * 400 * 4 * 4,
-        "l2_policy": "inputs larger than L2 (Q tables 839 MB per GPU vs 126 MB L2); no explicit flush",
-        "sharding": f"independent instances, {world} rank(s), no data-path collective",
+        "table_bytes_per_gpu": per_gpu,
+        "l2_policy": ("inputs larger than L2 (%.1f GB of tables per GPU vs 126 MB L2); no explicit flush" % (per_gpu / 1e9))
+                     if per_gpu > 126e6 else "tables are L2-resident by design (shared learner); state arrays are streamed",
+        "sharding": f"independent instances, {world} rank(s), "
+                    + ("shared tables all-reduced every 64 iterations (NCCL)" if sc.shared_q else "no data-path collective"),
     }
 
 
@@ -71,7 +113,7 @@ def workload_config(args, world):
 # its plain-C restatement, pinned bit-exactly to the live reference by tests/golden)
 # --------------------------------------------------------------------------------------------------------------------
 def _cpu_worker(job):
-    algo, n_inst, iters, offset = job
+    algo, n_inst, iters, offset = job  # `algo` is the workload name
     import multiagent_rlrm_b200 as P
     import oracle as O
 
@@ -93,10 +135,14 @@ def cpu_port_throughput(algo, seconds, procs):
 
     O.build()
     # calibrate one core
-    a, s, dt = _cpu_worker((algo, 256, 256, 0))
+    import multiagent_rlrm_b200 as P
+
+    agents = len(scenario(algo).starts)
+    heavy = scenario(algo).algo == "qlambda"  # dense trace sweep: ~1e4x more work per step
+    a, s, dt = _cpu_worker((algo, 8 if heavy else 256, 16 if heavy else 256, 0))
     rate = s / max(dt, 1e-6)  # slot-steps/s/core
-    iters = 512
-    n_inst = max(64, int(rate * seconds / (iters * 2)))
+    iters = 32 if heavy else 512
+    n_inst = max(4, int(rate * seconds / (iters * agents)))
     jobs = [(algo, n_inst, iters, k * n_inst) for k in range(procs)]
     t0 = time.perf_counter()
     if procs > 1:
@@ -113,7 +159,7 @@ def cpu_port_throughput(algo, seconds, procs):
         "unit": UNIT,
         "cores": procs,
         "kind": "port",
-        "sample": f"{procs} process(es) x {n_inst} instances x 2 agents x {iters} iterations of the same workload through "
+        "sample": f"{procs} process(es) x {n_inst} instances x {agents} agents x {iters} iterations of the same workload through "
                   f"oracle/rlrm_oracle.c (float32 tables); {slots / busy:.3e} slot-steps/s; wall {wall:.1f}s",
     }
 
@@ -126,7 +172,7 @@ def run_reference_arm(args):
     per_step = max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
     vals, last = [], None
     for k in range(args.warmup + args.steps):
-        last = cpu_port_throughput(args.algo, per_step, procs)
+        last = cpu_port_throughput(args.workload, per_step, procs)
         if k >= args.warmup:
             vals.append(last["value"])
     value = sum(vals) / len(vals)
@@ -223,11 +269,26 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
-    sc = scenario(args.algo)
+    sc = scenario(args.workload)
     c = P.compile_scenario(sc, instance_offset=rank * args.instances)  # Philox keyed on the GLOBAL instance id
     eng = Engine(c, args.instances, device=dev)
     eng.reset()
     n_slots = args.instances * c.n_agents
+    sync_every = 64 if (sc.shared_q and world > 1) else 0
+    real_train = eng.train
+
+    def train_with_merge(n_iters, **kw):  # shared learner: parameter averaging every 64 iterations (dist.ShardedTrainer rule)
+        done = 0
+        while done < n_iters:
+            chunk = min(sync_every, n_iters - done) if sync_every else n_iters
+            real_train(chunk, **kw)
+            done += chunk
+            if sync_every:
+                dist.all_reduce(eng.q, op=dist.ReduceOp.SUM)
+                eng.q.div_(world)
+
+    if sync_every:
+        eng.train = train_with_merge
 
     def barrier():
         if world > 1:
@@ -280,14 +341,14 @@ def run_gpu_arm(args):
 
     if rank == 0:
         value = active / (elapsed_ms * 1e-3)
-        bytes_per = QRM_BYTES_PER_STEP if args.algo == "qrm" else QL_BYTES_PER_STEP
+        bytes_per = WORKLOADS[args.workload][4]
         peak, peak_src = measured_peak()
         kernel_ms = sum(per_launch_ms) / len(per_launch_ms)          # this rank's average launch duration (CUDA events)
         active_per_launch_rank = (active / world) / args.steps
         achieved = bytes_per * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_port_throughput(args.algo, args.cpu_seconds, os.cpu_count() or 1)
+            cpu = cpu_port_throughput(args.workload, args.cpu_seconds, os.cpu_count() or 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -299,8 +360,8 @@ def run_gpu_arm(args):
                     "api": "Engine.train_host -> rlrm_train_host (pinned host slot/epsilon in+out, stats out)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.algo), "peak_source": peak_src,
-                         "kernel": "train_qrm4_kernel<FrozenLake>" if args.algo == "qrm" else "train_kernel<FrozenLake,QL>",
+                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "kernel": WORKLOADS[args.workload][5],
                          "algorithmic_bytes_per_active_agent_step": bytes_per,
                          "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms},
             "cpu_baseline": cpu,
@@ -311,7 +372,7 @@ def run_gpu_arm(args):
 
 
 def main():
-    args = parse_args()
+    args = resolve_defaults(parse_args())
     if args.impl == "reference":
         run_reference_arm(args)
     else:
