@@ -107,6 +107,7 @@ typedef struct rlrm_config {
   /* randomness: Philox4x32-10, key = (seed_lo, seed_hi), counter = (t_lo, t_hi, instance_offset + i, a) */
   uint32_t seed_lo, seed_hi;
   uint32_t instance_offset;    /* global id of local instance 0 (multi-GPU sharding keeps draws independent of G) */
+  int32_t use_rsh;             /* QLearning.use_rsh: potential-based shaping R' = R + gamma*Phi(q') - Phi(q) (qlearning.py:51-66, 93-105) */
   int32_t n_actions;           /* 1..4 usable actions (exploration draws (w1*n_actions)>>32); tables are always 4 wide */
   int32_t reserved;            /* bit 0: force the generic kernels (testing: generic vs specialised must agree) */
 } rlrm_config_t;
@@ -122,6 +123,12 @@ typedef struct rlrm_tables {
   const double* rcf;          /* [nQ][nEv+1] transition reward for QRM counterfactuals (unscaled, :150-153) */
   const uint8_t* qrm_states;  /* [n_qrm_states] RM state indices, in get_all_states()[:-1] order */
   const uint16_t* start_cell; /* [A] agent.initial_position */
+  const double* phi;          /* [2][nQ] RewardMachine.potentials (reward_machine.py:197-237); NULL = no shaping.
+                                 row 0: Phi of the state with index i — used by the QRM counterfactual loop, which maps
+                                        indices back to labels (qlearning.py:100-104);
+                                 row 1: potentials.get(i, 0) with the INTEGER i as dict key — what the plain-QL branch
+                                        evaluates, because AgentRL.update_policy hands it indices (agent_rl.py:158-172,
+                                        qlearning.py:60-65): all zeros unless the RM's state labels are integers */
 } rlrm_tables_t;
 
 /* per-(instance, agent) episode statistics, 32 bytes */
@@ -133,6 +140,21 @@ typedef struct rlrm_stats {
   float last_return;      /* return of the last finished episode */
   uint32_t last_length;   /* env.timestep at the end of the last finished episode */
 } rlrm_stats_t;
+
+/* per-(instance, agent) greedy-evaluation bookkeeping, 72 bytes (rlrm_evaluate) */
+typedef struct rlrm_eval {
+  double cum_gamma;      /* running gamma^t of the current episode (starts at 1) */
+  double disc_return;    /* running sum of cum_gamma * reward until the agent succeeds */
+  double return_sum;     /* over finished episodes: sum of disc_return, its squares, and of (disc_return/steps)/optimal_steps */
+  double return_sqsum;
+  double arps_sum;
+  uint64_t len_sum;      /* over SUCCESSFUL episodes: sum of episode lengths and of their squares */
+  uint64_t len_sqsum;
+  uint32_t episodes;     /* evaluation episodes finished */
+  uint32_t successes;    /* episodes in which this agent reached the final RM state */
+  uint32_t in_success;   /* the agent already succeeded in the current episode */
+  uint32_t reserved;
+} rlrm_eval_t;
 
 /* device pointers, caller-owned */
 typedef struct rlrm_state {
@@ -234,6 +256,15 @@ int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_
  * before returning. All copies are inside this call and therefore inside any end-to-end timing of it. */
 int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
                     uint64_t* host_slot, double* host_epsilon, rlrm_stats_t* host_stats, void* stream);
+
+/* Greedy policy evaluation = test_policy_optima (R/environments/utils_envs/evaluation_metrics.py:23-190): the driver
+ * loop with select_action(best=True), no update, no epsilon decay; per agent and episode the discounted return
+ * sum(gamma^t * reward) until the agent succeeds, success = terminated with the RM in its final state, episode length.
+ * Runs n_iters lockstep iterations; an instance stops starting new episodes once it finished n_episodes.
+ * `ev` is a device array [N*A], zero-initialised with cum_gamma = 1 by the caller. The caller passes a COPY of the
+ * environment state (slot) — the reference evaluates on copy.deepcopy(env) — while q is read-only here. */
+int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval_t* ev, uint64_t t0, int32_t n_iters, int32_t n_episodes,
+                  double gamma, double optimal_steps, void* stream);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t rlrm_launch_count(const rlrm_handle_t* h);

@@ -57,6 +57,7 @@ class Config(C.Structure):
         ("seed_lo", C.c_uint32),
         ("seed_hi", C.c_uint32),
         ("instance_offset", C.c_uint32),
+        ("use_rsh", C.c_int32),
         ("n_actions", C.c_int32),
         ("reserved", C.c_int32),
     ]
@@ -72,6 +73,7 @@ class Tables(C.Structure):
         ("rcf", C.c_void_p),
         ("qrm_states", C.c_void_p),
         ("start_cell", C.c_void_p),
+        ("phi", C.c_void_p),
     ]
 
 
@@ -83,6 +85,22 @@ class Stats(C.Structure):
         ("return_sum", C.c_double),
         ("last_return", C.c_float),
         ("last_length", C.c_uint32),
+    ]
+
+
+class Eval(C.Structure):
+    _fields_ = [
+        ("cum_gamma", C.c_double),
+        ("disc_return", C.c_double),
+        ("return_sum", C.c_double),
+        ("return_sqsum", C.c_double),
+        ("arps_sum", C.c_double),
+        ("len_sum", C.c_uint64),
+        ("len_sqsum", C.c_uint64),
+        ("episodes", C.c_uint32),
+        ("successes", C.c_uint32),
+        ("in_success", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -151,5 +169,6 @@ EXPORTED_SYMBOLS = (
     "rlrm_update",
     "rlrm_train",
     "rlrm_train_host",
+    "rlrm_evaluate",
     "rlrm_launch_count",
 )

@@ -36,13 +36,13 @@ struct KP {
   double hole_penalty, wall_penalty;
   double lr, gamma, eps_end, eps_decay;
   float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
-  int decay_on_reset, shared_q;
+  int decay_on_reset, shared_q, use_rsh;
   unsigned seed_lo, seed_hi, instance_offset, n_actions;
   long long S4;  // W*H*nQ*4 floats per table
   // table blob in global memory and section offsets (bytes) inside it / inside the shared-memory copy
   const unsigned char* blob;
   int blob_bytes;
-  int off_next, off_flags, off_label, off_delta, off_rq, off_rcf, off_qrm, off_start;
+  int off_next, off_flags, off_label, off_delta, off_rq, off_rcf, off_qrm, off_start, off_phi;
 };
 
 struct Tab {
@@ -54,6 +54,7 @@ struct Tab {
   const double* rcf;
   const unsigned char* qrm_states;
   const unsigned short* start_cell;
+  const double* phi;
 };
 
 struct DState {  // rlrm_state_t by value
@@ -100,6 +101,7 @@ __device__ __forceinline__ Tab stage_tables(const KP& p) {
   t.rcf = reinterpret_cast<const double*>(smem_raw + p.off_rcf);
   t.qrm_states = smem_raw + p.off_qrm;
   t.start_cell = reinterpret_cast<const unsigned short*>(smem_raw + p.off_start);
+  t.phi = reinterpret_cast<const double*>(smem_raw + p.off_phi);
   return t;
 }
 
@@ -312,10 +314,14 @@ __device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, float* 
       const unsigned un = d == RLRM_NO_TRANSITION ? u : d;
       const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
       const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
-      update_q(p, Q, V, r.prev_cell * p.nQ + u, action, __dadd_rn(r.renv, ru), r.cell * p.nQ + un, done, acc);
+      double rew = __dadd_rn(r.renv, ru);
+      if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[un]), tb.phi[u]));  // qlearning.py:93-105
+      update_q(p, Q, V, r.prev_cell * p.nQ + u, action, rew, r.cell * p.nQ + un, done, acc);
     }
   } else {
-    update_q(p, Q, V, obs_cell * p.nQ + r.prev_q, action, r.reward, r.cell * p.nQ + r.q, term_arg, acc);
+    double rew = r.reward;
+    if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.nQ + r.q]), tb.phi[p.nQ + r.prev_q]));  // qlearning.py:51-66
+    update_q(p, Q, V, obs_cell * p.nQ + r.prev_q, action, rew, r.cell * p.nQ + r.q, term_arg, acc);
   }
 }
 
@@ -896,6 +902,83 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// greedy evaluation (test_policy_optima, evaluation_metrics.py:23-190): the driver loop with best=True and no update
+// ------------------------------------------------------------------------------------------------
+template <int ENV>
+__global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p, DState st, rlrm_eval_t* evs, unsigned long long t0, int n_iters,
+                                                          int n_episodes, double gamma, double optimal_steps) {
+  Tab tb = stage_tables(p);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+  Slot s = {0, 0, 0, 0, 0};
+  rlrm_eval_t e;
+  memset(&e, 0, sizeof(e));
+  const float* Q = st.q;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    e = evs[k];
+    Q = st.q + table_base(p, i, a);
+  }
+  const unsigned w0[4] = {0, 0, 0, 0};
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    const bool running = valid && (int)e.episodes < n_episodes;  // all agents of an instance finish episodes together
+    if (running) {
+      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      const int action = select_action(row, 0ull, w0, true, p.n_actions);
+      unsigned w3 = 0;
+      if (p.stochastic) {
+        unsigned w[4];
+        philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+        w3 = w[3];
+      }
+      Rec r;
+      agent_step<ENV>(p, tb, s, action, w3, true, r);
+      if (!e.in_success) {
+        e.disc_return = __dadd_rn(e.disc_return, __dmul_rn(e.cum_gamma, r.reward));
+        if (r.term && p.rm_final >= 0 && (int)r.q == p.rm_final) {
+          e.successes++;
+          e.in_success = 1;
+        }
+      }
+      e.cum_gamma = __dmul_rn(e.cum_gamma, gamma);
+      term = r.term;
+      trunc = r.trunc;
+    }
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (running && over) {
+      const unsigned long long len = s.time;
+      e.episodes++;
+      e.return_sum = __dadd_rn(e.return_sum, e.disc_return);
+      e.return_sqsum = __dadd_rn(e.return_sqsum, __dmul_rn(e.disc_return, e.disc_return));
+      if (e.in_success) {
+        e.len_sum += len;
+        e.len_sqsum += len * len;
+      }
+      if (len > 0) e.arps_sum = __dadd_rn(e.arps_sum, __ddiv_rn(__ddiv_rn(e.disc_return, (double)len), optimal_steps));
+      e.cum_gamma = 1.0;
+      e.disc_return = 0.0;
+      e.in_success = 0;
+      double eps_unused = 0.0;
+      KP q = p;
+      q.decay_on_reset = 0;  // evaluation runs on a copy of the env: the training epsilon is not touched
+      reset_slot(q, tb, a, s, eps_unused);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    evs[k] = e;
+  }
+}
+
 // shared learner: every touched entry becomes the mean of this iteration's proposals; accumulators are cleared
 __global__ void __launch_bounds__(256) apply_shared_kernel(KP p, DState st) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1003,6 +1086,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.eps_end = cfg->epsilon_end; kp.eps_decay = cfg->epsilon_decay;
   fill_learner(kp, cfg->learning_rate, cfg->gamma, cfg->lambd);
   kp.decay_on_reset = cfg->decay_on_reset; kp.shared_q = cfg->shared_q;
+  kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
   kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;
   kp.n_actions = (unsigned)cfg->n_actions;
   kp.S4 = (long long)ncell * kp.nQ * 4;
@@ -1010,6 +1094,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   // pack the tables into one 16-byte aligned blob
   const int nd = kp.nQ * (kp.nEv + 1);
   int off = 0;
+  kp.off_phi = off; off = align16(off + 2 * RLRM_MAX_RM_STATES * 8);
   kp.off_rq = off; off = align16(off + nd * 8);
   kp.off_rcf = off; off = align16(off + nd * 8);
   kp.off_next = off; off = align16(off + ncell * 4 * 2);
@@ -1022,6 +1107,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   unsigned char* host = new (std::nothrow) unsigned char[off];
   if (!host) { delete h; return fail(RLRM_ERR_ARG, "out of host memory"); }
   memset(host, 0, off);
+  if (tb->phi) memcpy(host + kp.off_phi, tb->phi, (size_t)kp.nQ * 2 * 8);
   memcpy(host + kp.off_rq, tb->rq, (size_t)nd * 8);
   memcpy(host + kp.off_rcf, tb->rcf, (size_t)nd * 8);
   memcpy(host + kp.off_next, tb->next_cell, (size_t)ncell * 8);
@@ -1036,7 +1122,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   kp.blob = h->d_blob;
   h->smem_bytes = off;
-  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm <= 3 && !kp.shared_q && cfg->learning_rate >= 0.0 &&
+  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm <= 3 && !kp.shared_q && !kp.use_rsh && cfg->learning_rate >= 0.0 &&
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
@@ -1222,6 +1308,23 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
   }
   if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t0, n_iters, learn, trace, s);
   else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t0, n_iters, learn, trace, s);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval_t* ev, uint64_t t0, int32_t n_iters,
+                             int32_t n_episodes, double gamma, double optimal_steps, void* stream) {
+  int rc = check_state(h, st, false);
+  if (rc) return rc;
+  if (!st->q || !ev) return fail(RLRM_ERR_ARG, "state.q and ev are required");
+  if (n_iters <= 0 || n_episodes <= 0) return RLRM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = blocks_for(st->n_instances * h->kp.G, TRAIN_BLOCK);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE)
+    eval_kernel<RLRM_ENV_FROZEN_LAKE><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps);
+  else
+    eval_kernel<RLRM_ENV_OFFICE_WORLD><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps);
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }

@@ -19,6 +19,10 @@ from .tables import Compiled
 
 _TORCH_DT = {"uint16": torch.int16, "uint8": torch.uint8, "float64": torch.float64}
 
+EVAL_DTYPE = np.dtype([("cum_gamma", "<f8"), ("disc_return", "<f8"), ("return_sum", "<f8"), ("return_sqsum", "<f8"),
+                       ("arps_sum", "<f8"), ("len_sum", "<u8"), ("len_sqsum", "<u8"), ("episodes", "<u4"), ("successes", "<u4"),
+                       ("in_success", "<u4"), ("reserved", "<u4")])
+
 STATS_DTYPE = np.dtype([("active_steps", "<u8"), ("episodes", "<u4"), ("successes", "<u4"), ("return_sum", "<f8"),
                         ("last_return", "<f4"), ("last_length", "<u4")])
 
@@ -139,6 +143,24 @@ class Engine:
         check(self.L.rlrm_train_host(self.h, C.byref(self.state), t0, n_iters, int(learn), _ptr(host_slot),
                                      _ptr(host_epsilon), _ptr(host_stats), self._stream()))
         self.t = t0 + n_iters
+
+    def evaluate(self, n_episodes: int, gamma: float, optimal_steps: float = 1.0, t0: Optional[int] = None,
+                 max_iters: Optional[int] = None):
+        """Batched greedy evaluation (rlrm_evaluate): every instance plays `n_episodes` episodes with its own tables,
+        select_action(best=True), no update. Works on a copy of the environment state, like the reference's
+        copy.deepcopy(env) (evaluation_metrics.py:45). Returns a numpy record array [N*A] of rlrm_eval_t."""
+        ev = np.zeros(self.N * self.A, dtype=EVAL_DTYPE)
+        ev["cum_gamma"] = 1.0
+        ev_dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, EVAL_DTYPE.itemsize).copy()).to(self.device)
+        slot = self.slot.clone()
+        eps = self.epsilon.clone()
+        # e = NULL: the copy's traces are never read by a greedy rollout, and the training traces must not be wiped
+        st = abi.State(self.N, _ptr(slot), _ptr(eps), _ptr(self.q), None, None, None, None, None, None, None)
+        check(self.L.rlrm_reset(self.h, C.byref(st), None, self._stream()))  # env_test.reset(...)
+        n_iters = max_iters or n_episodes * (int(self.cfg.max_steps) + 1)
+        check(self.L.rlrm_evaluate(self.h, C.byref(st), _ptr(ev_dev), self.t if t0 is None else t0, n_iters, n_episodes,
+                                   float(gamma), float(optimal_steps), self._stream()))
+        return ev_dev.cpu().numpy().view(EVAL_DTYPE).reshape(-1)
 
     # -- views ---------------------------------------------------------------------------------
     def slots_numpy(self):

@@ -1,0 +1,70 @@
+"""Batched greedy policy evaluation and Q-table export.
+
+``test_policy_optima_batched`` is the batched counterpart of test_policy_optima / test_policy_opt_multi
+(/root/reference/multiagent_rlrm/environments/utils_envs/evaluation_metrics.py:23-190, 505-697): every environment
+instance plays ``episodi_test`` greedy episodes with its own tables on the device (rlrm_evaluate); the statistics the
+reference returns per agent are returned per (instance, agent).
+
+``save_q_tables`` / ``load_q_tables`` use the reference's ``data/q_tables.npz`` format (evaluation_metrics.py:193-214):
+one array per agent under the key ``q_table_<agent name>``; for a batch the arrays gain a leading instance axis.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def test_policy_optima_batched(engine, episodi_test: int = 100, optimal_steps: float = 30, gamma: float = 0.9) -> Dict[str, np.ndarray]:
+    ev = engine.evaluate(episodi_test, gamma, optimal_steps).reshape(engine.N, engine.A)
+    episodes = np.maximum(ev["episodes"], 1).astype(np.float64)
+    succ = ev["successes"].astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean_len = np.where(succ > 0, ev["len_sum"] / np.maximum(succ, 1), 0.0)
+        var_len = np.where(succ > 0, ev["len_sqsum"] / np.maximum(succ, 1) - mean_len ** 2, 0.0)
+        mean_ret = ev["return_sum"] / episodes
+        var_ret = ev["return_sqsum"] / episodes - mean_ret ** 2
+    return {
+        "success_rate": 100.0 * succ / episodes,            # success_rate_per_agente
+        "avg_timesteps": mean_len,                           # over successful episodes, 0 if none
+        "std_timesteps": np.sqrt(np.maximum(var_len, 0.0)),
+        "avg_reward": mean_ret,                              # discounted, until success
+        "std_reward": np.sqrt(np.maximum(var_ret, 0.0)),
+        "avg_arps": ev["arps_sum"] / episodes,
+        "episodes": ev["episodes"],
+    }
+
+
+test_policy_optima_batched.__test__ = False  # not a pytest test despite the reference-derived name
+
+
+def extract_policy_from_qtable(q_table) -> np.ndarray:
+    """Greedy action per encoded state (first maximum), evaluation_metrics.py:455-502."""
+    q = q_table.detach().cpu().numpy() if torch.is_tensor(q_table) else np.asarray(q_table)
+    return np.argmax(q, axis=-1)
+
+
+def save_q_tables(engine_or_agents, agent_names: Optional[Sequence[str]] = None, path: str = "data/q_tables.npz") -> str:
+    """np.savez(path, q_table_<agent>=...) — the reference's format (evaluation_metrics.py:193-214)."""
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    arrays = {}
+    if hasattr(engine_or_agents, "q") and hasattr(engine_or_agents, "N"):  # engine.Engine
+        eng = engine_or_agents
+        names = list(agent_names) if agent_names else [f"a{k + 1}" for k in range(eng.A)]
+        q = eng.q.detach().cpu().numpy()
+        q = q.reshape(eng.A, eng.S, 4) if eng.cfg.shared_q else q.reshape(eng.N, eng.A, eng.S, 4)
+        for k, name in enumerate(names):
+            table = q[k] if eng.cfg.shared_q else q[:, k]
+            arrays[f"q_table_{name}"] = table[0] if (table.ndim == 3 and table.shape[0] == 1) else table
+    else:  # iterable of AgentRL-like objects
+        for ag in engine_or_agents:
+            arrays[f"q_table_{ag.name}"] = np.asarray(ag.get_learning_algorithm().q_table)
+    np.savez(path, **arrays)
+    return path
+
+
+def load_q_tables(path: str) -> Dict[str, np.ndarray]:
+    z = np.load(path)
+    return {k[len("q_table_"):]: z[k] for k in z.files if k.startswith("q_table_")}

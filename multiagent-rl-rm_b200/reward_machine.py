@@ -192,16 +192,22 @@ class RewardMachine:
             "events": events,
         }
 
-    # ------------------------------------------------------------------ reward shaping (host side)
-    def add_reward_shaping(self, gamma, rs_gamma):  # filled in by shaping.py when that row is built
-        from .shaping import add_reward_shaping
+    # ------------------------------------------------------------------ reward shaping (reward_machine.py:197-345)
+    def add_reward_shaping(self, gamma, rs_gamma):
+        from .shaping import value_iteration_potentials
 
-        return add_reward_shaping(self, gamma, rs_gamma)
+        self.gamma = gamma
+        self.potentials = value_iteration_potentials(self, rs_gamma)
 
-    def add_distance_reward_shaping(self, gamma, alpha=1.0):
-        from .shaping import add_distance_reward_shaping
+    def add_distance_reward_shaping(self, gamma, rs_gamma, alpha=100):
+        from .shaping import distance_potentials
 
-        return add_distance_reward_shaping(self, gamma, alpha)
+        self.potentials = distance_potentials(self, alpha)
+
+    def get_distance(self, start_state):
+        from .shaping import rm_distance
+
+        return rm_distance(self, start_state)
 
 
 def builtin_frozen_lake_rm(goals: Dict[str, Tuple[int, int]], detector: Optional[EventDetector] = None) -> RewardMachine:

@@ -60,6 +60,11 @@ class Scenario:
     driver: str = "frozen_lake_main"  # "frozen_lake_main" | "office_main"
     shared_q: bool = False
     seed: int = 1234
+    # reward shaping on the RM (QL_RS / QRM_RS, office_main.py:543-573): "vi" = add_reward_shaping, "distance" = add_distance_reward_shaping
+    use_rsh: bool = False
+    rs_kind: str = "vi"
+    rs_gamma: float = 0.9
+    rs_alpha: float = 100
 
     def to_dict(self):
         import dataclasses
@@ -174,6 +179,7 @@ class Compiled:
     start_cell: np.ndarray
     events: List[Tuple[int, int]]
     config: abi.Config
+    phi: Optional[np.ndarray] = None
 
     @property
     def n_agents(self):
@@ -193,6 +199,9 @@ class Compiled:
             arr = np.ascontiguousarray(getattr(self, name))
             setattr(self, name, arr)  # keep alive
             setattr(t, name, arr.ctypes.data if arr.size else None)
+        if self.phi is not None:
+            self.phi = np.ascontiguousarray(self.phi, dtype=np.float64)
+            t.phi = self.phi.ctypes.data
         return t
 
 
@@ -249,12 +258,26 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
     cfg.seed_hi = (sc.seed >> 32) & 0xFFFFFFFF
     cfg.instance_offset = instance_offset
     cfg.n_actions = 4
+    phi = None
+    if sc.use_rsh or getattr(rm, "potentials", None) is not None:
+        if getattr(rm, "potentials", None) is None:
+            if sc.rs_kind == "distance":
+                rm.add_distance_reward_shaping(sc.gamma, sc.rs_gamma, sc.rs_alpha)
+            else:
+                rm.add_reward_shaping(sc.gamma, sc.rs_gamma)
+        # row 0: by label (QRM counterfactuals); row 1: potentials.get(<integer index>, 0), the lookup the plain-QL
+        # branch of the reference performs (see include/rlrm_b200.h, rlrm_tables_t.phi)
+        phi = np.zeros((2, t["n_states"]), dtype=np.float64)
+        for state, idx in rm.state_indices.items():
+            phi[0, idx] = rm.potentials.get(state, 0)
+            phi[1, idx] = rm.potentials.get(idx, 0)
+    cfg.use_rsh = int(bool(sc.use_rsh) and sc.algo in ("ql", "qrm"))
     start_cell = np.array([y * W + x for (x, y) in sc.starts], dtype=np.uint16)
     return Compiled(
         scenario=sc, grid=grid, rm=rm,
         next_cell=build_next_cell(grid), cell_flags=build_cell_flags(grid),
         label=t["label"], delta=t["delta"], rq=t["rq"], rcf=t["rcf"], qrm_states=t["qrm_states"],
-        start_cell=start_cell, events=t["events"], config=cfg,
+        start_cell=start_cell, events=t["events"], config=cfg, phi=phi,
     )
 
 

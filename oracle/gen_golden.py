@@ -85,6 +85,19 @@ def scenarios():
                   seed=23)
     S["ow_delay_completed_acbd_qrm"] = (sc, 2, 1300, "f32", 1)
 
+    sc = P.scenario_config3(False)
+    sc.use_rsh, sc.rs_kind, sc.rs_gamma, sc.seed, sc.learning_rate = True, "vi", 0.9, 31, 0.5
+    S["fl_shaping_vi_ql"] = (sc, 2, 500, "f32", 1)
+
+    sc = P.scenario_config3(True)
+    sc.use_rsh, sc.rs_kind, sc.rs_alpha, sc.seed, sc.learning_rate = True, "distance", 5, 32, 0.5
+    S["fl_shaping_distance_qrm"] = (sc, 2, 500, "f32", 1)
+
+    sc = Scenario(env="office_world", starts=[(2, 7)], rm_transitions=exp3, detector_positions=det, stochastic=True,
+                  high_prob=0.8, algo="qrm", learning_rate=0.1, gamma=0.9, epsilon_start=0.1, epsilon_end=0.1,
+                  epsilon_decay=1.0, q_init=2.0, driver="office_main", seed=33, use_rsh=True, rs_kind="vi", rs_gamma=0.9)
+    S["ow_shaping_vi_exp3_qrm"] = (sc, 2, 1200, "f32", 1)
+
     S["cfg4_office_chain12_qlambda"] = (P.scenario_config4(), 1, 1300, "f32", 1)
     S["cfg4_office_chain12_qlambda_f64"] = (P.scenario_config4(), 1, 300, "f64", 1)
 
@@ -109,5 +122,45 @@ def main(only=None):
               f"size={os.path.getsize(os.path.join(out_dir, name + '.npz')) // 1024} KiB")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--eval" not in sys.argv:
     main(set(sys.argv[1:]) or None)
+
+
+def gen_eval():
+    """Greedy-evaluation fixtures: trained tables come from the training fixtures' q_final."""
+    import ref_eval
+
+    import oracle as O
+
+    out_dir = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+    # (training fixture, extra oracle training iterations so that some evaluation episodes succeed, episodes, gamma, optimal)
+    for name, extra, n_ep, gamma, opt in (("cfg1_det_qrm", 30000, 3, 0.99, 21.0), ("cfg3_slip_qrm", 60000, 4, 0.99, 21.0),
+                                          ("cfg2_office_det_ql", 0, 2, 0.9, 30.0), ("ow_allslip_wallpen_exp3_qrm", 40000, 2, 0.9, 29.0)):
+        z = np.load(os.path.join(out_dir, name + ".npz"))
+        meta = json.loads(str(z["meta"]))
+        q_tables = z["q_final"]
+        if extra:  # tables are only INPUT data for the evaluation: train them further with the (reference-pinned) oracle
+            sc = P.Scenario.from_dict(meta["scenario"])
+            o = O.Oracle(P.compile_scenario(sc), meta["n_instances"], "f32")
+            for _ in range(meta["pre_resets"] + 1):
+                o.reset()
+            o.train(0, meta["n_iters"] + extra)
+            q_tables = o.q.reshape(z["q_final"].shape).copy()
+        res = ref_eval.reference_eval(meta["scenario"], q_tables, n_ep, gamma, opt)
+        own = res.pop("reference_function_outputs")
+        if own:  # deterministic: restated loop == the reference's own test_policy_optima
+            for i, o in enumerate(own):
+                succ_rate, _mov, avg_t, _std_t, avg_r, _std_r, avg_arps = o
+                for k, ag in enumerate(sorted(succ_rate)):
+                    assert abs(succ_rate[ag] - 100.0 * res["successes"][i, k] / n_ep) < 1e-9
+                    assert abs(avg_r[ag] - res["return_sum"][i, k] / n_ep) < 1e-9
+                    assert abs(avg_arps[ag] - res["arps_sum"][i, k] / n_ep) < 1e-9
+            print(f"eval_{name}: restated loop == reference test_policy_optima on {len(own)} instance(s)")
+        np.savez_compressed(os.path.join(out_dir, "eval_" + name + ".npz"),
+                            meta=json.dumps({"train_fixture": name, "n_episodes": n_ep, "gamma": gamma, "optimal_steps": opt,
+                                             "generator": "oracle/gen_golden.py gen_eval"}), q_tables=q_tables, **res)
+        print(f"eval_{name}: successes={res['successes'].sum()} of {res['episodes'].sum()}")
+
+
+if __name__ == "__main__" and "--eval" in sys.argv:
+    gen_eval()

@@ -23,6 +23,10 @@ from multiagent_rlrm_b200 import _abi as abi  # noqa: E402
 STATS_DTYPE = np.dtype([("active_steps", "<u8"), ("episodes", "<u4"), ("successes", "<u4"), ("return_sum", "<f8"),
                         ("last_return", "<f4"), ("last_length", "<u4")])
 assert STATS_DTYPE.itemsize == 32
+EVAL_DTYPE = np.dtype([("cum_gamma", "<f8"), ("disc_return", "<f8"), ("return_sum", "<f8"), ("return_sqsum", "<f8"),
+                       ("arps_sum", "<f8"), ("len_sum", "<u8"), ("len_sqsum", "<u8"), ("episodes", "<u4"), ("successes", "<u4"),
+                       ("in_success", "<u4"), ("reserved", "<u4")])
+assert EVAL_DTYPE.itemsize == 72
 
 _libs = {}
 
@@ -123,6 +127,19 @@ class Oracle:
         self.L.oracle_train(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_uint64(t0),
                             C.c_int32(n_iters), C.c_int32(int(learn)), C.c_void_p(_p(tr)))
         return tr
+
+    def evaluate(self, n_episodes, gamma, optimal_steps, t0=0, max_iters=None):
+        """Greedy evaluation on a COPY of the environment state (like copy.deepcopy(env) in the reference)."""
+        ev = np.zeros(self.N * self.A, dtype=EVAL_DTYPE)
+        ev["cum_gamma"] = 1.0
+        slot, eps = self.slot.copy(), self.epsilon.copy()
+        st = abi.State(self.N, _p(slot), _p(eps), _p(self.q), None, None, None, None, None, None, None)
+        self.L.oracle_reset(C.byref(self.cfg), C.byref(self.tables), C.byref(st), None)
+        eps[:] = self.epsilon
+        n_iters = max_iters or n_episodes * (self.cfg.max_steps + 1)
+        self.L.oracle_evaluate(C.byref(self.cfg), C.byref(self.tables), C.byref(st), C.c_void_p(ev.ctypes.data), C.c_uint64(t0),
+                               C.c_int32(n_iters), C.c_int32(n_episodes), C.c_double(gamma), C.c_double(optimal_steps))
+        return ev
 
     # -- views ---------------------------------------------------------------------------------
     def unpack(self):

@@ -41,9 +41,6 @@ class DrawSource:
     """Philox words per (t, instance, agent); t is set by the loop before each lockstep iteration."""
 
     def __init__(self, seed, n_instances, n_agents, instance_offset=0):
-        import philox
-
-        self._philox = philox
         self.seed, self.n, self.a, self.off = seed, n_instances, n_agents, instance_offset
         self.t = 0
         self._cache = {}
@@ -53,7 +50,9 @@ class DrawSource:
         if w is None:
             if len(self._cache) > 4096:
                 self._cache.clear()
-            w = self._cache[self.t] = self._philox.draws(self.seed, self.t, self.n, self.a, self.off)
+            import philox
+
+            w = self._cache[self.t] = philox.draws(self.seed, self.t, self.n, self.a, self.off)
         return w[i, a]
 
 
@@ -172,6 +171,16 @@ def build_reference(sc: dict, table_dtype=np.float32):
             learner = QLearning(qtable_init=sc["q_init"], use_qrm=(sc["algo"] == "qrm"), **common)
             learner.learning_rate = sc["learning_rate"]
         learner.q_table = np.full(learner.q_table.shape, sc["q_init"], dtype=table_dtype)
+        if sc.get("use_rsh") and sc["algo"] != "qlambda":  # QL_RS / QRM_RS (office_main.py:543-573)
+            import contextlib
+            import io
+
+            learner.use_rsh = True
+            with contextlib.redirect_stdout(io.StringIO()):  # value_iteration prints debug lines
+                if sc.get("rs_kind", "vi") == "distance":
+                    rm.add_distance_reward_shaping(sc["gamma"], sc["rs_gamma"], sc["rs_alpha"])
+                else:
+                    rm.add_reward_shaping(sc["gamma"], sc["rs_gamma"])
         ag.set_learning_algorithm(learner)
         agents.append(ag)
     rm_env = RMEnvironmentWrapper(env, agents)

@@ -342,11 +342,17 @@ static void update_slot(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const
       int un = d == RLRM_NO_TRANSITION ? u : d;
       double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb->rcf[u * (nEv + 1) + col];
       int done = r->env_term || (cfg->rm_final >= 0 && un == cfg->rm_final);
-      update_q(cfg, Q, V, (size_t)r->prev_cell * nQ + u, action, r->renv + ru, (size_t)r->cell * nQ + un, done, accp);
+      double rew = r->renv + ru;
+      if (cfg->use_rsh && tb->phi) rew += cfg->gamma * tb->phi[un] - tb->phi[u]; /* qlearning.py:93-105 */
+      update_q(cfg, Q, V, (size_t)r->prev_cell * nQ + u, action, rew, (size_t)r->cell * nQ + un, done, accp);
     }
   } else {
     size_t s = (size_t)obs_cell * nQ + r->prev_q, sn = (size_t)r->cell * nQ + r->q; /* agent_rl.py:154-155 */
-    if (cfg->algo == RLRM_ALGO_QL) update_q(cfg, Q, V, s, action, r->reward, sn, term_arg, accp);
+    if (cfg->algo == RLRM_ALGO_QL) {
+      double rew = r->reward;
+      if (cfg->use_rsh && tb->phi) rew += cfg->gamma * tb->phi[nQ + r->q] - tb->phi[nQ + r->prev_q]; /* qlearning.py:51-66 */
+      update_q(cfg, Q, V, s, action, rew, sn, term_arg, accp);
+    }
     else update_qlambda(cfg, Q, (real*)st->e + base, V, S, s, action, r->reward, sn, term_arg);
   }
 }
@@ -441,6 +447,57 @@ int oracle_train(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_s
   } else { /* instances are independent */
     for (int64_t i = 0; i < st->n_instances; i++)
       for (int32_t it = 0; it < n_iters; it++) train_iteration(cfg, tb, st, i, t0 + (uint64_t)it, it, learn, trace);
+  }
+  return 0;
+}
+
+/* ---- greedy evaluation: evaluation_metrics.py:23-190 (test_policy_optima) --------------------------- */
+int oracle_evaluate(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, rlrm_eval_t* ev, uint64_t t0,
+                    int32_t n_iters, int32_t n_episodes, double gamma, double optimal_steps) {
+  int A = cfg->n_agents;
+  rlrm_config_t c2 = *cfg;
+  c2.decay_on_reset = 0; /* evaluation runs on a deep copy of the env: the training epsilon is untouched */
+  rec_t rec[RLRM_MAX_AGENTS];
+  uint8_t act[RLRM_MAX_AGENTS];
+  for (int64_t i = 0; i < st->n_instances; i++) {
+    for (int32_t it = 0; it < n_iters; it++) {
+      if ((int32_t)ev[(size_t)i * A].episodes >= n_episodes) break;
+      uint64_t t = t0 + (uint64_t)it;
+      for (int a = 0; a < A; a++) {
+        size_t k = (size_t)i * A + a;
+        slot_t s = unpack(st->slot[k]);
+        const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * cfg->n_rm_states + s.rm) * 4;
+        uint32_t w[4] = {0, 0, 0, 0};
+        act[a] = (uint8_t)select_one(cfg, row, 0.0, w, 1); /* best=True: np.argmax, no randomness (:84-87) */
+      }
+      step_instance(&c2, tb, st, i, act, NULL, t, 1, rec);
+      clear_first(cfg, st, i);
+      int all_term = 1, all_trunc = 1;
+      for (int a = 0; a < A; a++) {
+        size_t k = (size_t)i * A + a;
+        rlrm_eval_t* e = &ev[k];
+        if (!e->in_success) { /* :96-110 */
+          e->disc_return += e->cum_gamma * rec[a].reward;
+          if (rec[a].term && cfg->rm_final >= 0 && (int)rec[a].q == cfg->rm_final) { e->successes++; e->in_success = 1; }
+        }
+        e->cum_gamma *= gamma;
+        all_term &= (int)rec[a].term; all_trunc &= (int)rec[a].trunc;
+      }
+      if (all_term || all_trunc) { /* the `timestep > 1000` exit (:117) coincides with truncation */
+        for (int a = 0; a < A; a++) {
+          size_t k = (size_t)i * A + a;
+          rlrm_eval_t* e = &ev[k];
+          uint64_t len = unpack(st->slot[k]).time;
+          e->episodes++;
+          e->return_sum += e->disc_return;
+          e->return_sqsum += e->disc_return * e->disc_return;
+          if (e->in_success) { e->len_sum += len; e->len_sqsum += len * len; }
+          if (len > 0) e->arps_sum += (e->disc_return / (double)len) / optimal_steps; /* :131-139 */
+          e->cum_gamma = 1.0; e->disc_return = 0.0; e->in_success = 0;
+        }
+        reset_instance(&c2, tb, st, i);
+      }
+    }
   }
   return 0;
 }

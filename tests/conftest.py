@@ -17,7 +17,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    """Training-trace fixtures (eval_*.npz are evaluation fixtures, see tests/test_eval.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("eval_"))
 
 
 def load_golden(name):

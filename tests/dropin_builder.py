@@ -48,6 +48,12 @@ def build_b200(sc, table_dtype=None):
             learner.q_table.fill(sc["q_init"])
         else:
             learner = P.QLearning(qtable_init=sc["q_init"], use_qrm=(sc["algo"] == "qrm"), **common)
+        if sc.get("use_rsh") and sc["algo"] != "qlambda":
+            learner.use_rsh = True
+            if sc.get("rs_kind", "vi") == "distance":
+                rm.add_distance_reward_shaping(sc["gamma"], sc["rs_gamma"], sc["rs_alpha"])
+            else:
+                rm.add_reward_shaping(sc["gamma"], sc["rs_gamma"])
         ag.set_learning_algorithm(learner)
         agents.append(ag)
     rm_env = P.RMEnvironmentWrapper(env, agents)

@@ -325,3 +325,44 @@ def test_slip_tables_equal_reference_probability_mappings():
             assert [names[c.config.slip_outcome[a][j]] for j in range(len(outs))] == list(outs)
             assert list(c.config.slip_thr)[: len(probs) - 1] == tables.slip_thresholds(probs)
             assert c.config.slip_n == len(probs)
+
+
+# ---------------------------------------------------------------------------------------------- reward shaping (f3)
+def test_distance_reward_shaping_known_answers():
+    """/root/reference/tests/test_reward_machine_shaping.py: qf -> 0, one step away -> -alpha, two steps -> -2 alpha"""
+    rm = P.RewardMachine({("q0", "a"): ("q1", 0), ("q1", "b"): ("qf", 1)}, _StubDetector())
+    rm.add_distance_reward_shaping(gamma=0.9, rs_gamma=0.9, alpha=5)
+    assert rm.potentials == {"q0": -10, "q1": -5, "qf": 0}
+    assert rm.get_distance("q0") == 2 and rm.get_distance("qf") == 0
+    lonely = P.RewardMachine({("q0", "a"): ("q0", 0), ("q1", "b"): ("qf", 1)}, _StubDetector())
+    assert lonely.get_distance("q0") == 999999
+
+
+def test_value_iteration_shaping_known_answers():
+    rm = P.builtin_frozen_lake_rm({"A": (4, 4), "B": (0, 0), "C": (4, 8)}) if hasattr(P, "builtin_frozen_lake_rm") else None
+    from multiagent_rlrm_b200.reward_machine import builtin_frozen_lake_rm
+
+    rm = builtin_frozen_lake_rm({"A": (4, 4), "B": (0, 0), "C": (4, 8)})
+    rm.add_reward_shaping(0.99, 0.9)
+    # V(state2) = 20, V(state1) = 15 + .9*20 = 33, V(state0) = 10 + .9*33 = 39.7 ; potentials are -V
+    assert rm.potentials == {"state0": -(10 + 0.9 * (15 + 0.9 * 20)), "state1": -(15 + 0.9 * 20), "state2": -20, "state3": 0}
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+def test_potentials_equal_live_reference():
+    import contextlib
+    import io
+
+    import ref_harness as H
+
+    for sc in (P.scenario_config1(), P.scenario_config2(), P.scenario_config4()):
+        _, _, agents = H.build_reference(sc.to_dict())
+        ref_rm = agents[0].get_reward_machine()
+        mine = sc.reward_machine()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_rm.add_reward_shaping(sc.gamma, 0.9)
+        mine.add_reward_shaping(sc.gamma, 0.9)
+        assert mine.potentials == ref_rm.potentials
+        ref_rm.add_distance_reward_shaping(sc.gamma, 0.9, alpha=7)
+        mine.add_distance_reward_shaping(sc.gamma, 0.9, alpha=7)
+        assert mine.potentials == ref_rm.potentials
