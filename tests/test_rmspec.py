@@ -1,0 +1,180 @@
+"""CPU: the RM-spec compile path: spec file + map name -> RewardMachine -> device tables.
+Known answers restated from the reference's tests, and a differential test against the live reference pipeline."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+import multiagent_rlrm_b200 as P
+from multiagent_rlrm_b200 import rmspec as R
+
+FIX = os.path.join(ROOT, "tests", "fixtures")
+HAVE_REF = os.path.isdir("/root/reference/multiagent_rlrm")
+
+
+def _partial():
+    return R.RMSpec.from_dict({"name": "partial", "env_id": "env", "version": "1.0", "states": ["q0", "q1"], "initial_state": "q0",
+                               "terminal_states": ["q1"], "event_vocabulary": ["e1", "e2"],
+                               "transitions": [{"from_state": "q0", "event": "e1", "to_state": "q1", "reward": 1}]})
+
+
+def test_completion_full_cartesian_and_defaults():
+    """/root/reference/tests/test_rmgen_completion.py:22-55"""
+    spec, report = R.complete_missing_transitions(_partial(), default_reward=0.0)
+    assert report["added"] == 3 and len(spec.transitions) == 4
+    assert any((t.from_state, t.event, t.to_state, t.reward) == ("q0", "e1", "q1", 1) for t in spec.transitions)
+    spec, _ = R.complete_missing_transitions(_partial(), default_reward=0.5)
+    assert next(t for t in spec.transitions if (t.from_state, t.event) == ("q1", "e2")).reward == 0.5
+    spec, _ = R.complete_missing_transitions(_partial(), terminal_self_loop=True)
+    assert any((t.from_state, t.event, t.to_state) == ("q1", "e1", "q1") for t in spec.transitions)
+    spec, rep = R.complete_missing_transitions(_partial(), terminal_self_loop=False)
+    assert rep["added"] == 1 and not any(t.from_state == "q1" for t in spec.transitions)
+
+
+def test_load_and_compile_with_passthrough_detector(tmp_path):
+    """/root/reference/tests/test_rmspec_io.py:10-18 (fixture rewritten: two-step machine ending on at(G))"""
+    p = tmp_path / "simple.json"
+    p.write_text(json.dumps({"name": "s", "env_id": "OfficeWorld ", "version": "1.0", "states": ["q0", "q1", "q2"],
+                             "initial_state": "q0", "terminal_states": ["q2"], "event_vocabulary": ["at(K)", "at(G)"],
+                             "transitions": [{"from_state": "q0", "event": "at(K)", "to_state": "q1", "reward": 0},
+                                             {"from_state": "q1", "event": "at(G)", "to_state": "q2", "reward": "r1"}]}))
+    spec = R.load_rmspec(p)
+    assert spec.env_id == "officeworld"
+    rm = R.compile_reward_machine(spec)
+    assert isinstance(rm, P.RewardMachine)
+    assert rm.get_reward_for_non_current_state("q1", "at(G)") == ("q2", 1.0)
+    assert rm.step({"event": "at(K)"}) == 0 and rm.get_current_state() == "q1"
+    with pytest.raises(FileNotFoundError):
+        R.load_rmspec(tmp_path / "nope.json")
+    bad = tmp_path / "bad.json"
+    bad.write_text("{not json")
+    with pytest.raises(ValueError):
+        R.load_rmspec(bad)
+
+
+def test_validation_errors():
+    d = _partial().to_dict()
+    for mutate, msg in ((lambda x: x.update(initial_state="zz"), "initial_state"),
+                        (lambda x: x["transitions"].append({"from_state": "q0", "event": "e1", "to_state": "q0", "reward": 0}), "Non-deterministic"),
+                        (lambda x: x["transitions"].append({"from_state": "q1", "event": "e2", "to_state": "q1", "reward": 2}), "Terminal transitions"),
+                        (lambda x: x.update(event_vocabulary=["e1", "e1"]), "Duplicate event")):
+        dd = json.loads(json.dumps(d))
+        mutate(dd)
+        with pytest.raises(R.ValidationError, match=msg):
+            R.compile_reward_machine(R.RMSpec.from_dict(dd))
+
+
+def test_officeworld_event_normalisation():
+    """/root/reference/tests/test_officeworld_event_context.py:15-64 ; tests/test_frozenlake_event_context.py"""
+    ctx = R.build_officeworld_context("map1")
+    spec = {"name": "b", "env_id": "officeworld", "version": "1.0", "states": ["q0", "q1", "q2", "q3", "q4"], "initial_state": "q0",
+            "terminal_states": ["q4"], "event_vocabulary": ["A", "B", "C", "D"],
+            "transitions": [{"from_state": f"q{i}", "event": e, "to_state": f"q{i + 1}", "reward": int(i == 3)} for i, e in enumerate("ABCD")]}
+    out = R.normalize_rmspec_events(spec, ctx)
+    assert out["event_vocabulary"] == ["at(A)", "at(B)", "at(C)", "at(D)"]
+    assert [t["event"] for t in out["transitions"]] == ["at(A)", "at(B)", "at(C)", "at(D)"]
+    syn = R.normalize_rmspec_events({"event_vocabulary": [" At( Office )"], "transitions": [{"event": "office"}]}, ctx)
+    assert syn["event_vocabulary"] == ["at(O)"] and syn["transitions"][0]["event"] == "at(O)"
+    with pytest.raises(R.UnknownEventError, match="Unknown event 'at\\(G\\)'"):
+        R.normalize_rmspec_events({"event_vocabulary": ["at(G)"], "transitions": []}, ctx)
+    fl = R.normalize_rmspec_events({"event_vocabulary": ["A", "B"], "transitions": [{"event": "A"}]}, R.build_frozenlake_context("map1"))
+    assert fl["event_vocabulary"] == ["at(A)", "at(B)"] and fl["transitions"][0]["event"] == "at(A)"
+
+
+def test_env_id_enforcement_and_autofix(capsys):
+    """/root/reference/tests/test_officeworld_env_id_enforcement.py"""
+    spec = R.RMSpec.from_dict({"name": "t", "env_id": "officework", "version": "1.0", "states": ["q0", "q1"], "initial_state": "q0",
+                               "terminal_states": [], "event_vocabulary": ["A"],
+                               "transitions": [{"from_state": "q0", "event": "A", "to_state": "q4", "reward": 1.0}]})
+    spec = R.enforce_env_id(spec, "officeworld", reason="--rm-spec is set")
+    assert spec.env_id == "officeworld" and "overriding env_id" in capsys.readouterr().out
+    spec = R.autofix_rmspec_states_for_officeworld(spec)
+    assert spec.states == ["q0", "q1", "q4"] and spec.terminal_states == ["q4"]
+    R.validate_spec(R.normalize_rmspec_events(spec, R.build_officeworld_context("map1")))
+    loop = R.RMSpec.from_dict({"name": "t", "env_id": "officeworld", "version": "1.0", "states": ["q0", "q1"], "initial_state": "q0",
+                               "terminal_states": ["q1"], "event_vocabulary": ["A", "B"],
+                               "transitions": [{"from_state": "q0", "event": "A", "to_state": "q1", "reward": 0},
+                                               {"from_state": "q1", "event": "B", "to_state": "q1", "reward": 1}]})
+    fixed = R.autofix_terminal_reward_violations_for_officeworld(loop)
+    assert fixed.states == ["q0", "q1", "q2"] and fixed.terminal_states == ["q2"]
+    assert (fixed.transitions[1].from_state, fixed.transitions[1].to_state, fixed.transitions[1].reward) == ("q1", "q2", 1.0)
+
+
+def test_spec_files_compile_to_the_baseline_scenarios():
+    """The authored spec fixtures reproduce the BASELINE config machines and their device tables."""
+    rm, _ = R.load_reward_machine(os.path.join(FIX, "officeworld_acbd.json"), "office_world", "map1")
+    want = P.scenario_config2().reward_machine()
+    assert list(rm.transitions.items()) == list(want.transitions.items())
+    sc, rm12 = R.scenario_from_rmspec(os.path.join(FIX, "officeworld_chain12.json"), P.scenario_config4(), complete_missing_transitions=True)
+    c_spec, c_ref = P.compile_scenario(sc), P.compile_scenario(P.scenario_config4())
+    assert len(rm12.transitions) == 108 and rm12.get_final_state() == "q11"
+    assert rm12.state_indices == c_ref.rm.state_indices
+    for name in ("label", "delta", "rq", "rcf", "qrm_states"):
+        assert np.array_equal(getattr(c_spec, name), getattr(c_ref, name)), name
+    rm3, _ = R.load_reward_machine(os.path.join(FIX, "frozenlake_abc.json"), "frozen_lake", "map1")
+    c3, c1 = P.compile_scenario(P.scenario_config1(), rm=rm3), P.compile_scenario(P.scenario_config1())
+    for name in ("label", "delta", "rq", "rcf", "qrm_states"):
+        assert np.array_equal(getattr(c3, name), getattr(c1, name)), name
+    assert c3.config.rm_final == c1.config.rm_final == 3
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+@pytest.mark.parametrize("fixture,env,complete", [("officeworld_acbd.json", "office_world", False), ("officeworld_acbd.json", "office_world", True),
+                                                  ("officeworld_chain12.json", "office_world", True), ("frozenlake_abc.json", "frozen_lake", False),
+                                                  ("frozenlake_abc.json", "frozen_lake", True), ("REF:frozenlake_linear.json", "frozen_lake", True)])
+def test_pipeline_equals_live_reference(fixture, env, complete, capsys):
+    """Same spec file through the reference's runner pipeline (office_main.py:487-515 / frozen_lake_main.py:133-183)."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "ref_shim"), "/root/reference"]
+    from multiagent_rlrm.environments.frozen_lake.config_frozen_lake import config as fc
+    from multiagent_rlrm.environments.frozen_lake.detect_event import PositionEventDetector
+    from multiagent_rlrm.environments.frozen_lake.event_context import build_frozenlake_context
+    from multiagent_rlrm.environments.office_world.config_office import config as oc
+    from multiagent_rlrm.environments.office_world.event_context import build_officeworld_context
+    from multiagent_rlrm.rmgen import io as rio
+    from multiagent_rlrm.rmgen import normalize as rnorm
+    from multiagent_rlrm.utils.utils import parse_map_emoji, parse_office_world
+
+    path = os.path.join("/root/reference/tests/fixtures", fixture[4:]) if fixture.startswith("REF:") else os.path.join(FIX, fixture)
+    spec = rio.load_rmspec(path)
+    if env == "office_world":
+        spec = rnorm.enforce_env_id(spec, "officeworld", reason="t")
+        ctx = build_officeworld_context("map1")
+        assert ctx == R.build_officeworld_context("map1")
+        spec = rnorm.normalize_rmspec_events(spec, ctx)
+        spec = rnorm.autofix_rmspec_states_for_officeworld(spec)
+        spec = rnorm.autofix_terminal_reward_violations_for_officeworld(spec)
+        coords, goals, _ = parse_office_world(oc["maps"]["map1"]["layout"])
+        mapping = {}
+        for label, pos in goals.items():
+            mapping[f"at({label})"] = pos
+            mapping[label] = pos
+        mapping["office"] = mapping["at(office)"] = goals["O"]
+        mapping["coffee"] = mapping["at(coffee)"] = list(coords["coffee"])
+        for k in ("letter", "email", "at(letter)", "at(email)"):
+            mapping[k] = list(coords["letter"])
+        assert mapping == R.officeworld_event_mapping("map1")
+        positions = set(oc["maps"]["map1"]["position_map"](coords, goals))
+    else:
+        spec = rnorm.enforce_env_id(spec, "frozenlake", reason="t")
+        ctx = build_frozenlake_context("map1")
+        assert ctx == R.build_frozenlake_context("map1")
+        spec = rnorm.normalize_rmspec_events(spec, ctx)
+        _, goals, _ = parse_map_emoji(fc["maps"]["map1"]["layout"])
+        mapping = {}
+        for label, pos in goals.items():
+            mapping[f"at({label})"] = pos
+            mapping[label] = pos
+        positions = set(goals.values())
+    for m in mapping.values():
+        positions.update(m if isinstance(m, list) else [m])
+    ref_rm = rio.compile_reward_machine(spec, event_detector=PositionEventDetector(positions), event_mapping=mapping,
+                                        complete_missing_transitions=complete)
+    rm, _ = R.load_reward_machine(path, env, "map1", complete_missing_transitions=complete)
+    assert list(rm.transitions.items()) == list(ref_rm.transitions.items())
+    assert rm.state_indices == ref_rm.state_indices and rm.initial_state == ref_rm.initial_state
+    assert rm.get_final_state() == ref_rm.get_final_state() and rm.get_all_states() == ref_rm.get_all_states()
+    assert set(rm.event_detector.positions) == set(ref_rm.event_detector.positions)
