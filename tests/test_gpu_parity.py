@@ -221,3 +221,65 @@ def test_shared_learner_with_one_instance_is_the_reference_learner(cuda_device):
     assert np.array_equal(ta.cpu().numpy(), tb.cpu().numpy())
     assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy())
     assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
+
+
+def test_full_size_config4_qlambda_windows_match_oracle(cuda_device):
+    """BASELINE config 4 at full size (262,144 OfficeWorld instances x 4 agents, Q(lambda), 43.5 GB of tables):
+    windows of the batch equal the oracle run with the matching instance_offset; traces obey their invariants."""
+    import torch
+
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    sc = P.scenario_config4()
+    c = P.compile_scenario(sc)
+    n, iters = 262144, 24
+    free, _total = torch.cuda.mem_get_info()
+    if free < 50e9:
+        pytest.skip("needs ~45 GB of free device memory")
+    eng = _engine(c, n)
+    eng.reset()
+    eng.train(iters)
+    for start in (0, 200001):
+        cw = P.compile_scenario(sc, instance_offset=start)
+        o = O.Oracle(cw, 3, "f32")
+        o.reset()
+        o.train(0, iters)
+        sl = slice(start * 4, (start + 3) * 4)
+        assert np.array_equal(eng.slot[sl].cpu().numpy().view(np.uint64), o.slot)
+        assert np.array_equal(eng.q[sl].cpu().numpy(), o.q)
+        assert np.array_equal(eng.e[sl].cpu().numpy(), o.e)
+    e = eng.e[: 4096 * 4]
+    assert float(e.min()) >= 0.0 and float(e.max()) <= 1.0           # replacing traces live in [0, 1]
+    assert int((e != 0).sum(dim=(1, 2)).max()) <= iters                # at most one new trace per step
+    del eng
+    torch.cuda.empty_cache()
+
+
+def test_full_size_config5_windows_match_oracle(cuda_device):
+    """BASELINE config 5 companion at full size (1,048,576 FrozenLake instances x 4 agents, per-instance tables, 26.8 GB)."""
+    import torch
+
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    sc = P.scenario_config5(shared=False)
+    c = P.compile_scenario(sc)
+    n, iters = 1048576, 300
+    free, _total = torch.cuda.mem_get_info()
+    if free < 32e9:
+        pytest.skip("needs ~28 GB of free device memory")
+    eng = _engine(c, n)
+    eng.reset()
+    eng.train(iters)
+    for start in (0, 777777, n - 16):
+        cw = P.compile_scenario(sc, instance_offset=start)
+        o = O.Oracle(cw, 16, "f32")
+        o.reset()
+        o.train(0, iters)
+        sl = slice(start * 4, (start + 16) * 4)
+        assert np.array_equal(eng.slot[sl].cpu().numpy().view(np.uint64), o.slot)
+        assert np.array_equal(eng.q[sl].cpu().numpy(), o.q)
+    assert eng.total_active_steps() <= n * 4 * iters
+    del eng
+    torch.cuda.empty_cache()
