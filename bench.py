@@ -123,7 +123,7 @@ def _cpu_worker(job):
     t0 = time.perf_counter()
     o.train(0, iters)
     dt = time.perf_counter() - t0
-    return int(o.stats["active_steps"].sum()), n_inst * c.n_agents * iters, dt
+    return o.total_active_steps(), n_inst * c.n_agents * iters, dt
 
 
 def cpu_port_throughput(algo, seconds, procs):
@@ -321,13 +321,16 @@ def run_gpu_arm(args):
     e2e_steps = max(3, args.steps // 2)
     eng.train_host(args.iters, host_stats, host_slot, host_eps)  # warm
     barrier()
-    a0 = int(host_stats.view(torch.int64)[:, 0].sum())
+    def host_active():  # finished episodes' agent_steps (stats) + running episodes' agent_steps (slot words), all on the host
+        return int(host_stats.view(torch.int64)[:, 0].sum()) + int(((host_slot >> 16) & 0xFFFF).sum())
+
+    a0 = host_active()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         eng.train_host(args.iters, host_stats, host_slot, host_eps)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    e2e_active = int(host_stats.view(torch.int64)[:, 0].sum()) - a0
+    e2e_active = host_active() - a0
     h2d = host_slot.numel() * 8 + host_eps.numel() * 8
     d2h = host_stats.numel() + host_slot.numel() * 8 + host_eps.numel() * 8
 

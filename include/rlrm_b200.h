@@ -133,7 +133,8 @@ typedef struct rlrm_tables {
 
 /* per-(instance, agent) episode statistics, 32 bytes */
 typedef struct rlrm_stats {
-  uint64_t active_steps;  /* sum of env.agent_steps increments = the headline "agent-steps" */
+  uint64_t active_steps;  /* sum of env.agent_steps over FINISHED episodes; add the slot's current agent_steps for the
+                             running total of active agent-steps (the headline unit) */
   uint32_t episodes;      /* episodes finished */
   uint32_t successes;     /* episodes that ended with the RM in its final state */
   double return_sum;      /* sum over finished episodes of the undiscounted episode return */

@@ -578,7 +578,6 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
       term = r.term;
       trunc = r.trunc;
       ep_ret = __dadd_rn(ep_ret, r.reward);
-      active_steps += r.stepped ? 1u : 0u;
       if (trace)
         trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                              ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
@@ -589,6 +588,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
     const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
     if (valid && over) {
       episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
       successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
       last_return = __double2float_rn(ep_ret);
       return_sum = __dadd_rn(return_sum, ep_ret);
@@ -741,7 +741,6 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       term = r.term;
       trunc = r.trunc;
       ep_ret = __dadd_rn(ep_ret, r.reward);
-      active_steps += r.stepped ? 1u : 0u;
       if (trace)
         trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                              ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
@@ -751,6 +750,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
     const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
     if (valid && over) {
       episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
       successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
       last_return = __double2float_rn(ep_ret);
       return_sum = __dadd_rn(return_sum, ep_ret);
@@ -852,7 +852,6 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
       __syncwarp();
     }
     ep_ret = __dadd_rn(ep_ret, r.reward);
-    active_steps += r.stepped ? 1u : 0u;
     if (trace && lane == 0)
       trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                            ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
@@ -870,6 +869,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
     __syncthreads();
     if (all_term || all_trunc) {
       episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
       successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
       last_return = __double2float_rn(ep_ret);
       return_sum_add = __dadd_rn(return_sum_add, ep_ret);
@@ -979,6 +979,106 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p, DState st, rlrm
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// shared learner, fast path: ONE lockstep iteration over all instances by persistent blocks. The per-agent shared
+// tables (A*S*4 floats, 25.6 KB for config 5) and the proposal accumulators live in SHARED memory: Q reads are LDS,
+// proposals are shared-memory atomics, and each block flushes its non-empty accumulators to the global ones once.
+// Integer sums make the result independent of the block/thread order (include/rlrm_b200.h "Shared learner").
+// Slot state is streamed from HBM (8 B in + 8 B out per slot); statistics are only touched when an episode ends.
+// ------------------------------------------------------------------------------------------------
+#define SHARED_BLOCK 1024
+
+template <int ENV, int ALGO>
+__global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, DState st, unsigned long long t, int learn,
+                                                                        unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const int n_ent = p.A * (int)p.S4;
+  float* Qs = reinterpret_cast<float*>(smem_raw + p.blob_bytes);
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(Qs + n_ent);
+  int* s_cnt = reinterpret_cast<int*>(s_sum + n_ent);
+  float* s_last = reinterpret_cast<float*>(s_cnt + n_ent);
+  for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x)
+    reinterpret_cast<float4*>(Qs)[j] = __ldg(reinterpret_cast<const float4*>(st.q) + j);
+  for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+    s_sum[j] = 0ull;
+    s_cnt[j] = 0;
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+  const long long total = st.N << p.g_shift;
+  for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += (long long)gridDim.x * blockDim.x) {
+    const long long tid = b0 + threadIdx.x;
+    const long long i = tid >> p.g_shift;
+    const int a = (int)(tid & (p.G - 1));
+    const bool valid = (i < st.N) && (a < p.A);
+    const long long k = i * p.A + a;
+    bool term = true, trunc = true;
+    Slot s = {0, 0, 0, 0, 0};
+    double eps = 0.0;
+    Rec r;
+    r.reward = 0.0;
+    if (valid) {
+      s = unpack_slot(st.slot[k]);
+      eps = st.epsilon[k];
+      unsigned w[4];
+      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      float* Q = Qs + (size_t)a * (size_t)p.S4;
+      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      const int action = select_action(row, explore_threshold(eps), w, learn == 0, p.n_actions);
+      const unsigned before = s.cell;
+      const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      if (learn) {
+        const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+        const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+        Acc acc = {reinterpret_cast<long long*>(s_sum) + (size_t)a * (size_t)p.S4, s_cnt + (size_t)a * (size_t)p.S4,
+                   s_last + (size_t)a * (size_t)p.S4};
+        agent_update<ALGO>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
+      }
+      term = r.term;
+      trunc = r.trunc;
+      if (r.reward != 0.0 && st.ep_return) st.ep_return[k] = __dadd_rn(st.ep_return[k], r.reward);
+      if (trace)
+        trace[k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) | ((unsigned)r.term << 21) |
+                   ((unsigned)r.trunc << 22) | ((unsigned)r.stepped << 23);
+    }
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (valid) {
+      if (over) {
+        const double ret = st.ep_return ? st.ep_return[k] : 0.0;
+        if (st.stats) {
+          rlrm_stats_t z = st.stats[k];
+          z.episodes++;
+          z.active_steps += s.steps;
+          z.successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+          z.last_return = __double2float_rn(ret);
+          z.return_sum = __dadd_rn(z.return_sum, ret);
+          z.last_length = s.time;
+          st.stats[k] = z;
+        }
+        if (st.ep_return) st.ep_return[k] = 0.0;
+        reset_slot(p, tb, a, s, eps);
+        st.epsilon[k] = eps;
+      }
+      st.slot[k] = pack_slot(s);
+    }
+  }
+  __syncthreads();
+  if (learn) {
+    for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+      const int c = s_cnt[j];
+      if (c) {
+        atomicAdd(st.acc_cnt + j, c);
+        atomicAdd(reinterpret_cast<unsigned long long*>(st.acc_sum) + j, s_sum[j]);
+        st.acc_last[j] = s_last[j];  // only read back when the GLOBAL count is 1, i.e. exactly one block wrote it
+      }
+    }
+  }
+}
+
 // shared learner: every touched entry becomes the mean of this iteration's proposals; accumulators are cleared
 __global__ void __launch_bounds__(256) apply_shared_kernel(KP p, DState st) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1002,7 +1102,9 @@ struct rlrm_handle {
   int smem_bytes;
   long long launches;
   int qrm4_fast;  // train_qrm4_kernel is applicable (see its header comment)
-  int force_generic;
+  int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
+  int shared_smem_bytes;
+  int num_sms;
 };
 
 static thread_local char g_err[512] = "";
@@ -1126,6 +1228,25 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  {
+    const long long n_ent = (long long)kp.A * kp.S4;
+    const long long need = (long long)off + n_ent * 20;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry
+    h->shared_smem_bytes = (int)need;
+    h->shared_fast = (kp.shared_q && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
+                      !(cfg->reserved & 1));
+    if (h->shared_fast) {
+      cudaError_t e1 = cudaSuccess;
+      if (kp.env_kind == RLRM_ENV_FROZEN_LAKE) {
+        if (kp.algo == RLRM_ALGO_QRM) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        else e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+      } else {
+        if (kp.algo == RLRM_ALGO_QRM) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        else e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+      }
+      if (e1 != cudaSuccess) h->shared_fast = 0;
+    }
+  }
   *out = h;
   return RLRM_OK;
 }
@@ -1296,7 +1417,19 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
     const size_t stride = (size_t)st->n_instances * h->kp.A;
     for (int it = 0; it < n_iters; it++) {
       uint32_t* tr = trace ? trace + (size_t)it * stride : nullptr;
-      if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t0 + it, 1, learn, tr, s);
+      if (h->shared_fast && !st->visits) {
+        const long long threads = st->n_instances * h->kp.G;
+        long long want = (threads + SHARED_BLOCK - 1) / SHARED_BLOCK;
+        const unsigned grid = (unsigned)(want < h->num_sms ? want : h->num_sms);
+        const DState d = dstate(st);
+        if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) {
+          if (h->kp.algo == RLRM_ALGO_QRM) shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM><<<grid, SHARED_BLOCK, h->shared_smem_bytes, s>>>(h->kp, d, t0 + it, learn, tr);
+          else shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL><<<grid, SHARED_BLOCK, h->shared_smem_bytes, s>>>(h->kp, d, t0 + it, learn, tr);
+        } else {
+          if (h->kp.algo == RLRM_ALGO_QRM) shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM><<<grid, SHARED_BLOCK, h->shared_smem_bytes, s>>>(h->kp, d, t0 + it, learn, tr);
+          else shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL><<<grid, SHARED_BLOCK, h->shared_smem_bytes, s>>>(h->kp, d, t0 + it, learn, tr);
+        }
+      } else if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t0 + it, 1, learn, tr, s);
       else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t0 + it, 1, learn, tr, s);
       LAUNCH_CHECK(h);
       if (learn) {

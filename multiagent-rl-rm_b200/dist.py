@@ -84,7 +84,7 @@ class ShardedTrainer:
     def global_counters(self):
         """(active agent-steps, episodes, successes) summed over all ranks — a counter reduction, not a data-path step."""
         s = self.engine.stats_numpy()
-        vals = torch.tensor([int(s["active_steps"].sum()), int(s["episodes"].sum()), int(s["successes"].sum())], dtype=torch.int64)
+        vals = torch.tensor([int(self.engine.total_active_steps()), int(s["episodes"].sum()), int(s["successes"].sum())], dtype=torch.int64)
         if self.world > 1:
             dev = self.engine.q.device
             vals = vals.to(dev)

@@ -174,8 +174,11 @@ class Engine:
         return self.stats.cpu().numpy().view(STATS_DTYPE).reshape(-1)
 
     def total_active_steps(self) -> int:
-        """Sum of env.agent_steps increments over all slots, reduced on the device."""
-        return int(self.stats.view(torch.int64)[:, 0].sum().item())
+        """Active agent-steps so far = env.agent_steps of every finished episode (stats.active_steps) + the running
+        episodes' agent_steps (slot words), reduced on the device."""
+        finished = self.stats.view(torch.int64)[:, 0].sum()
+        running = ((self.slot >> abi.SLOT_STEPS_SHIFT) & 0xFFFF).sum()
+        return int((finished + running).item())
 
     # -- the driver loop, call by call (reference API granularity) ----------------------------------
     def iterate_unfused(self, learn: bool = True, draws: Optional[torch.Tensor] = None, auto_reset: bool = True):

@@ -141,6 +141,11 @@ class Oracle:
                                C.c_int32(n_iters), C.c_int32(n_episodes), C.c_double(gamma), C.c_double(optimal_steps))
         return ev
 
+    def total_active_steps(self):
+        """finished episodes' env.agent_steps (stats) + the running episodes' agent_steps (slot words)"""
+        running = (self.slot >> np.uint64(abi.SLOT_STEPS_SHIFT)) & np.uint64(0xFFFF)
+        return int(self.stats["active_steps"].sum()) + int(running.sum())
+
     # -- views ---------------------------------------------------------------------------------
     def unpack(self):
         return unpack_slots(self.slot, self.N, self.A)

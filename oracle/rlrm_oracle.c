@@ -400,7 +400,6 @@ static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, c
     if (learn) update_slot(cfg, tb, st, i, a, obs, act[a], term_arg, &rec[a]);
     all_term &= (int)rec[a].term; all_trunc &= (int)rec[a].trunc;
     if (st->ep_return) st->ep_return[k] += rec[a].reward;
-    if (st->stats) st->stats[k].active_steps += rec[a].stepped;
     if (trace)
       trace[(size_t)it * st->n_instances * A + k] = (uint32_t)act[a] | (rec[a].executed << 3) | (rec[a].cell << 6) |
           (rec[a].q << 16) | (rec[a].term << 21) | (rec[a].trunc << 22) | (rec[a].stepped << 23);
@@ -413,6 +412,7 @@ static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, c
         slot_t s = unpack(st->slot[k]);
         rlrm_stats_t* z = &st->stats[k];
         z->episodes++;
+        z->active_steps += s.steps; /* env.agent_steps[agent] of the finished episode */
         z->successes += (cfg->rm_final >= 0 && (int)s.rm == cfg->rm_final);
         double ret = st->ep_return ? st->ep_return[k] : 0.0;
         z->last_return = (float)ret;

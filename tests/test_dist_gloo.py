@@ -30,6 +30,9 @@ class OracleEngine:
     def stats_numpy(self):
         return self.o.stats
 
+    def total_active_steps(self):
+        return self.o.total_active_steps()
+
 
 def _worker(rank, world, port, shared, out_dir):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
@@ -80,7 +83,7 @@ def test_sharded_per_instance_tables_equal_single_process(tmp_path):
     assert [int(p["offset"]) for p in parts] == [0, 19] and [int(p["n"]) for p in parts] == [19, 18]
     assert np.array_equal(np.concatenate([p["slot"] for p in parts]), o.slot)
     assert np.array_equal(np.concatenate([p["q"] for p in parts]), o.q)
-    total = (int(o.stats["active_steps"].sum()), int(o.stats["episodes"].sum()), int(o.stats["successes"].sum()))
+    total = (o.total_active_steps(), int(o.stats["episodes"].sum()), int(o.stats["successes"].sum()))
     assert tuple(parts[0]["counters"]) == total == tuple(parts[1]["counters"])
 
 

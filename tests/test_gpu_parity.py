@@ -283,3 +283,20 @@ def test_full_size_config5_windows_match_oracle(cuda_device):
     assert eng.total_active_steps() <= n * 4 * iters
     del eng
     torch.cuda.empty_cache()
+
+
+def test_shared_learner_generic_path_equals_fast_path(cuda_device):
+    """config.reserved bit 0 forces the global-atomic propose path; it must agree with shared_propose_kernel."""
+    import multiagent_rlrm_b200 as P
+
+    sc = P.scenario_config5(shared=True)
+    c_fast, c_gen = P.compile_scenario(sc), P.compile_scenario(sc)
+    c_gen.config.reserved = 1
+    a, b = _engine(c_fast, 5000), _engine(c_gen, 5000)
+    a.reset(); b.reset()
+    ta, tb = a.train(120, trace=True), b.train(120, trace=True)
+    assert np.array_equal(ta.cpu().numpy(), tb.cpu().numpy())
+    assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy())
+    assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
+    assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+    assert np.array_equal(a.ep_return.cpu().numpy(), b.ep_return.cpu().numpy())
