@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
             const float mf = __fmul_rn(done ? 0.0f : 1.0f, mx);
             const float inner = __fadd_rn(__double2float_rn(__dadd_rn(r.renv, ru)), __fmul_rn(p.gamma_f, mf));
             const float nv = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
-            dst[4 * u] = nv;
+            if (__float_as_uint(nv) != __float_as_uint(cur)) dst[4 * u] = nv;  // a bit-identical value needs no store
             if (!moved) {  // same cell: the carried block is the one just written
 #pragma unroll
               for (int c = 0; c < 4; c++) B[4 * u + c] = (c == action) ? nv : B[4 * u + c];
