@@ -189,8 +189,9 @@ struct Rec {
 
 // env.step + check_terminations + RewardMachine.step + wrapper merge for ONE agent. Every quantity an agent needs is
 // its own (the shared env.timestep is replicated per agent), so lanes never exchange data here.
-template <int ENV>
+template <int ENV, int STOCH = -1>  // STOCH: -1 = read p.stochastic at run time, 0/1 = compile-time
 __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, int action, unsigned w3, bool with_rm, Rec& r) {
+  const bool stochastic = STOCH < 0 ? (p.stochastic != 0) : (STOCH != 0);
   r.prev_cell = s.cell;
   r.executed = 5;
   r.stepped = false;
@@ -201,7 +202,7 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
     const bool rm_done = p.rm_final >= 0 && (int)s.rm == p.rm_final;  // ma_frozen_lake.py:107-115
     if (active && !rm_done) {
       int ex = action;
-      if (p.stochastic) ex = slip_outcome(p, action, w3);
+      if (stochastic) ex = slip_outcome(p, action, w3);
       if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
       if (tb.cell_flags[s.cell] & 1) {  // holes_in_the_ice
         s.flags |= RLRM_FLAG_FAIL;
@@ -220,7 +221,7 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
         wall_pen = p.wall_penalty;
         ex = RLRM_ACTION_WAIT;
       }
-      if (p.stochastic && ex != RLRM_ACTION_WAIT) ex = slip_outcome(p, ex, w3);
+      if (stochastic && ex != RLRM_ACTION_WAIT) ex = slip_outcome(p, ex, w3);
       if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
       double plant = 0.0;
       if (tb.cell_flags[s.cell] & 1) {  // plants_in_the_office
@@ -621,8 +622,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
 // ------------------------------------------------------------------------------------------------
 // fast path: QRM with nQ == 4 (BASELINE configs 1/3/5). The 64-byte cell block Q[cell, 0..3, 0..3] lives in registers
 // between iterations: it is fetched with two 256-bit loads only when the agent changes cell, the counterfactual
-// updates run on registers, and the dirty rows go back with one 256-bit + one 128-bit store. Requires
-// qrm_states == [0, 1, .., n_qrm-1] (so a static unroll over rows is the reference's update order), per-instance
+// updates run on registers, and the new values go back as scalar stores. Requires
+// qrm_states == [0, 1, 2] (so a static unroll over rows is the reference's update order), per-instance
 // tables, fixed learning rate, no visit counts; anything else takes train_kernel.
 // ------------------------------------------------------------------------------------------------
 struct __align__(32) F8 {
@@ -656,8 +657,10 @@ __device__ __forceinline__ void load_block4(const float* Q, unsigned cell, float
   for (int r = 0; r < 4; r++) bmax[r] = fmaxf(fmaxf(B[4 * r], B[4 * r + 1]), fmaxf(B[4 * r + 2], B[4 * r + 3]));
 }
 
-template <int ENV>
-__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+// STOCH / LEARN / TRACE are compile-time copies of p.stochastic / learn / (trace != nullptr): the loop body is issue-bound,
+// so runtime flag tests and their constant-bank loads are specialised away. n_qrm is 3 on this path.
+template <int ENV, bool STOCH, bool LEARN, bool TRACE>
+__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState st, unsigned long long t0, int n_iters,
                                                                 unsigned* trace) {
   Tab tb = stage_tables(p);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,17 +704,17 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       row.y = sel4(B[1], B[5], B[9], B[13], s.rm);
       row.z = sel4(B[2], B[6], B[10], B[14], s.rm);
       row.w = sel4(B[3], B[7], B[11], B[15], s.rm);
-      const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
+      const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);
       const unsigned before = s.cell;
       Rec r;
-      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
       const bool moved = r.cell != before;
       // values the updates overwrite, read before the carried block is replaced
       const float cur0 = sel4(B[0], B[1], B[2], B[3], (unsigned)action);
       const float cur1 = sel4(B[4], B[5], B[6], B[7], (unsigned)action);
       const float cur2 = sel4(B[8], B[9], B[10], B[11], (unsigned)action);
       if (moved) load_block4(Q, r.cell, B, bmax);  // the carried block becomes the NEXT cell's block
-      if (learn) {
+      if (LEARN) {
         // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106),
         // in get_all_states()[:-1] order == row order 0..n_qrm-1 on this path. The next state's row maximum comes from
         // the carried block: a different block when the agent moved, else the live one including earlier updates.
@@ -719,7 +722,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
         float* dst = Q + (size_t)before * 16 + action;  // infos["prev_s"] is the position before the move
 #pragma unroll
         for (int u = 0; u < 3; u++) {
-          if (u < p.n_qrm) {
+          {
             const unsigned d = tb.delta[u * (p.nEv + 1) + col];
             const unsigned un = d == RLRM_NO_TRANSITION ? (unsigned)u : d;
             const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       term = r.term;
       trunc = r.trunc;
       ep_ret = __dadd_rn(ep_ret, r.reward);
-      if (trace)
+      if (TRACE)
         trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                              ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
                                                              ((unsigned)r.stepped << 23);
@@ -1224,7 +1227,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   kp.blob = h->d_blob;
   h->smem_bytes = off;
-  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm <= 3 && !kp.shared_q && !kp.use_rsh && cfg->learning_rate >= 0.0 &&
+  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && cfg->learning_rate >= 0.0 &&
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
@@ -1395,8 +1398,22 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
   } else {
     const long long threads = st->n_instances * kp.G;
     const unsigned grid = blocks_for(threads, TRAIN_BLOCK);
-    if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits)
-      train_qrm4_kernel<ENV><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits) {
+      const DState d = dstate(st);
+#define RLRM_QRM4(ST, LE, TR) train_qrm4_kernel<ENV, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace)
+      const int key = (kp.stochastic ? 4 : 0) | (learn ? 2 : 0) | (trace ? 1 : 0);
+      switch (key) {
+        case 0: RLRM_QRM4(false, false, false); break;
+        case 1: RLRM_QRM4(false, false, true); break;
+        case 2: RLRM_QRM4(false, true, false); break;
+        case 3: RLRM_QRM4(false, true, true); break;
+        case 4: RLRM_QRM4(true, false, false); break;
+        case 5: RLRM_QRM4(true, false, true); break;
+        case 6: RLRM_QRM4(true, true, false); break;
+        default: RLRM_QRM4(true, true, true); break;
+      }
+#undef RLRM_QRM4
+    }
     else if (kp.algo == RLRM_ALGO_QRM)
       train_kernel<ENV, RLRM_ALGO_QRM><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
     else
