@@ -56,9 +56,14 @@ WORKLOADS = {
                 "per-instance Q tables, auto-reset",
                 "configs[2] companion (plain Q-learning variant, SURVEY.md §8d)", 65536, 2048, 36, "train_kernel<FrozenLake,QL>"),
     "cfg4": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, plants -100, synthetic 12-state completed chain RM (108 "
-             "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, dense-faithful trace sweep",
+             "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, SPARSE-EXACT traces (live entries only; "
+             "bit-identical to the dense sweep)",
              "configs[3]: OfficeWorld 12-state RM, 262,144 instances x 4 agents, Q(lambda) traces",
-             262144, 4, 4 * 1296 * 4 * 4, "train_qlambda_kernel<OfficeWorld>"),
+             262144, 64, None, "train_qlambda_sparse_kernel<OfficeWorld>"),
+    "cfg4_dense": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, plants -100, synthetic 12-state completed chain RM (108 "
+                   "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, dense-faithful trace sweep",
+                   "configs[3]: OfficeWorld 12-state RM, 262,144 instances x 4 agents, Q(lambda) traces",
+                   262144, 4, 4 * 1296 * 4 * 4, "train_qlambda_kernel<OfficeWorld>"),
     "cfg5_tables": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, per-instance Q tables",
                     "configs[4] HBM-bound companion: 1M FrozenLake instances x 4 agents, per-instance tables",
                     1048576, 256, 140, "train_qrm4_kernel<FrozenLake>"),
@@ -73,7 +78,7 @@ def scenario(workload):
     import multiagent_rlrm_b200 as P
 
     return {"cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
-            "cfg4": P.scenario_config4, "cfg5_tables": lambda: P.scenario_config5(False),
+            "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg5_tables": lambda: P.scenario_config5(False),
             "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
 
 
@@ -271,7 +276,7 @@ def run_gpu_arm(args):
 
     sc = scenario(args.workload)
     c = P.compile_scenario(sc, instance_offset=rank * args.instances)  # Philox keyed on the GLOBAL instance id
-    eng = Engine(c, args.instances, device=dev)
+    eng = Engine(c, args.instances, device=dev, qlambda_sparse=(args.workload == "cfg4"))
     eng.reset()
     n_slots = args.instances * c.n_agents
     sync_every = 64 if (sc.shared_q and world > 1) else 0
@@ -299,6 +304,7 @@ def run_gpu_arm(args):
         eng.train(args.iters)
     barrier()
     launches0, steps0 = eng.launches, eng.total_active_steps()
+    work0 = int(eng.tr_work.sum()) if eng.sparse else 0
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -312,6 +318,7 @@ def run_gpu_arm(args):
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     active = eng.total_active_steps() - steps0
     launches = eng.launches - launches0
+    mean_live = ((int(eng.tr_work.sum()) - work0) / max(1, n_slots * args.iters * args.steps)) if eng.sparse else None
 
     # ---- end to end: the public API call on HOST (pinned) buffers, copies inside the timed region --------------------
     host_slot = torch.empty(n_slots, dtype=torch.int64).pin_memory()
@@ -345,6 +352,8 @@ def run_gpu_arm(args):
     if rank == 0:
         value = active / (elapsed_ms * 1e-3)
         bytes_per = WORKLOADS[args.workload][4]
+        if bytes_per is None:  # sparse-exact Q(lambda): 32 + 16 * (mean live traces), SURVEY.md §8(d), measured in this run
+            bytes_per = 32 + 16 * mean_live
         peak, peak_src = measured_peak()
         kernel_ms = sum(per_launch_ms) / len(per_launch_ms)          # this rank's average launch duration (CUDA events)
         active_per_launch_rank = (active / world) / args.steps
@@ -366,7 +375,12 @@ def run_gpu_arm(args):
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
                          "kernel": WORKLOADS[args.workload][5],
                          "algorithmic_bytes_per_active_agent_step": bytes_per,
-                         "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms},
+                         "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms,
+                         **({"mean_live_traces": mean_live,
+                             "dense_equivalent_GBps": (4 * 1296 * 4 * 4) * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9,
+                             "note": "achieved uses the sparse algorithm's own bytes (32 + 16*L); dense_equivalent is what the "
+                                     "reference's dense sweep would have moved for the same steps, NOT achieved bandwidth"}
+                            if mean_live is not None else {})},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

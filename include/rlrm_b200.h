@@ -172,6 +172,20 @@ typedef struct rlrm_state {
   int64_t* acc_sum;     /* sum of round(new_value * 2^20) over the instances that updated the entry this iteration */
   int32_t* acc_cnt;     /* number of such instances */
   float* acc_last;      /* the new value itself (used verbatim when acc_cnt == 1) */
+  /* Q(lambda) sparse-exact traces (optional; give these INSTEAD of `e`). The reference sweeps the whole table every step
+   * (q += lr*td*e ; e *= gamma*lambda, qlearning_lambda.py:63,81); entries whose trace is 0 receive +0, so only the
+   * entries with a live trace need touching. Each (instance, agent) keeps a list of its live entries holding the trace
+   * AND the current q value (the table copy of a listed entry is stale until the list is flushed, which happens when
+   * the traces are wiped: terminated update or reset). Results equal the dense sweep bit for bit (up to the sign of
+   * zero). rlrm_qlambda_materialize writes the listed values back so `q` can be read. Needs S*4 <= 65535. */
+  uint16_t* tr_pos;     /* [N*A][S*4] 0 = entry not listed, else list position + 1 */
+  uint16_t* tr_idx;     /* [N*A][tr_cap] listed entry index = enc*4 + action */
+  float* tr_e;          /* [N*A][tr_cap] its trace */
+  float* tr_q;          /* [N*A][tr_cap] its current q value */
+  uint32_t* tr_len;     /* [N*A] list length */
+  uint64_t* tr_work;    /* [N*A] or NULL: sum over update steps of the list length swept (bench: mean live traces) */
+  int32_t tr_cap;       /* list capacity; must be >= max_steps + 1 (one new entry per step, wiped every episode) */
+  int32_t tr_reserved;
 } rlrm_state_t;
 
 /* device pointers, caller-owned, each [N*A]; any may be NULL (not written) */
@@ -266,6 +280,10 @@ int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32
  * environment state (slot) — the reference evaluates on copy.deepcopy(env) — while q is read-only here. */
 int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval_t* ev, uint64_t t0, int32_t n_iters, int32_t n_episodes,
                   double gamma, double optimal_steps, void* stream);
+
+/* Sparse Q(lambda) only: write every listed q value back into `q` (lists stay live) and, when e_dense is non-NULL
+ * (device, [N*A*S*4], zeroed by the caller), scatter the traces into it — the dense view of learner.q_table / e_table. */
+int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, float* e_dense, void* stream);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t rlrm_launch_count(const rlrm_handle_t* h);

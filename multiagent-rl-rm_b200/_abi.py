@@ -117,6 +117,14 @@ class State(C.Structure):
         ("acc_sum", C.c_void_p),
         ("acc_cnt", C.c_void_p),
         ("acc_last", C.c_void_p),
+        ("tr_pos", C.c_void_p),
+        ("tr_idx", C.c_void_p),
+        ("tr_e", C.c_void_p),
+        ("tr_q", C.c_void_p),
+        ("tr_len", C.c_void_p),
+        ("tr_work", C.c_void_p),
+        ("tr_cap", C.c_int32),
+        ("tr_reserved", C.c_int32),
     ]
 
 
@@ -170,5 +178,6 @@ EXPORTED_SYMBOLS = (
     "rlrm_train",
     "rlrm_train_host",
     "rlrm_evaluate",
+    "rlrm_qlambda_materialize",
     "rlrm_launch_count",
 )

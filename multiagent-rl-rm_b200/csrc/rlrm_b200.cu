@@ -69,6 +69,13 @@ struct DState {  // rlrm_state_t by value
   long long* acc_sum;  // shared learner accumulators (include/rlrm_b200.h "Shared learner"), null otherwise
   int* acc_cnt;
   float* acc_last;
+  unsigned short* tr_pos;  // Q(lambda) sparse-exact traces (include/rlrm_b200.h), null otherwise
+  unsigned short* tr_idx;
+  float* tr_e;
+  float* tr_q;
+  unsigned* tr_len;
+  unsigned long long* tr_work;
+  int tr_cap;
 };
 
 struct Acc {  // accumulators of one agent's shared table, or nulls
@@ -906,6 +913,205 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
 }
 
 // ------------------------------------------------------------------------------------------------
+// Q(lambda), sparse-exact traces: one block per instance, one warp per agent. Only entries with a live trace are
+// touched; each agent's live entries sit in a list that carries the trace AND the current q value (a write-back
+// cache over the table), so one update step reads/writes the list once, coalesced. Bit-identical to the dense sweep of
+// QLearningLambda.update (qlearning_lambda.py:33-84) up to the sign of zero: unlisted entries have e == 0 and receive +0.
+// ------------------------------------------------------------------------------------------------
+struct TraceList {
+  unsigned short* pos;  // [S*4]
+  unsigned short* idx;  // [cap]
+  float* e;
+  float* q;
+};
+
+// current value of table entry j: the listed copy when the entry has a live trace, else the table
+__device__ __forceinline__ float trace_lookup(const float* Q, const TraceList& L, unsigned j) {
+  const unsigned pz = L.pos[j];
+  return pz ? L.q[pz - 1] : Q[j];
+}
+
+// write the listed values back and forget the list (traces wiped: reset_e_table / e_table.fill(0))
+__device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsigned len, int lane) {
+  for (unsigned j = lane; j < len; j += 32) {
+    const unsigned id = L.idx[j];
+    Q[id] = L.q[j];
+    L.pos[id] = 0;
+  }
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                                  unsigned* trace) {
+  Tab tb = stage_tables(p);
+  __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
+  const long long i = blockIdx.x;
+  const int a = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long k = i * p.A + a;
+  Slot s = unpack_slot(st.slot[k]);
+  double eps = st.epsilon[k];
+  double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
+  float* Q = st.q + table_base(p, i, a);
+  TraceList L;
+  L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
+  L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
+  L.e = st.tr_e + (size_t)k * (size_t)st.tr_cap;
+  L.q = st.tr_q + (size_t)k * (size_t)st.tr_cap;
+  unsigned len = st.tr_len[k];
+  unsigned long long work = 0, active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  bool had_episode = false;
+  rlrm_stats_t z;
+  if (st.stats) z = st.stats[k];
+  double return_sum = st.stats ? z.return_sum : 0.0;
+  unsigned long long explore_thr = explore_threshold(eps);
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    unsigned w[4];
+    philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+    __syncwarp();
+    // Q row of the current state: lanes 0..3 fetch one action value each
+    const unsigned rbase = (s.cell * p.nQ + s.rm) * 4;
+    const float mine = lane < 4 ? trace_lookup(Q, L, rbase + lane) : 0.f;
+    float4 row;
+    row.x = __shfl_sync(0xFFFFFFFFu, mine, 0);
+    row.y = __shfl_sync(0xFFFFFFFFu, mine, 1);
+    row.z = __shfl_sync(0xFFFFFFFFu, mine, 2);
+    row.w = __shfl_sync(0xFFFFFFFFu, mine, 3);
+    const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
+    const unsigned before = s.cell;
+    const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+    Rec r;
+    agent_step<ENV>(p, tb, s, action, w[3], true, r);  // all lanes compute the same scalars
+    if (learn) {
+      const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+      const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+      const unsigned hot = (obs * p.nQ + r.prev_q) * 4 + action, nbase = (r.cell * p.nQ + r.q) * 4;
+      // lanes 0..3: next-state row, lane 4: Q[s,a] — five independent lookups in flight
+      const float got = lane < 4 ? trace_lookup(Q, L, nbase + lane) : (lane == 4 ? trace_lookup(Q, L, hot) : 0.f);
+      const float n0 = __shfl_sync(0xFFFFFFFFu, got, 0), n1 = __shfl_sync(0xFFFFFFFFu, got, 1);
+      const float n2 = __shfl_sync(0xFFFFFFFFu, got, 2), n3 = __shfl_sync(0xFFFFFFFFu, got, 3);
+      const float qsa = __shfl_sync(0xFFFFFFFFu, got, 4);
+      const double best = term_arg ? 0.0 : (double)fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
+      const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
+      const float c = __fmul_rn(p.lr_f, td);
+      bool found = false;
+      for (unsigned j = lane; j < len; j += 32) {  // one coalesced pass over the live entries
+        float e = L.e[j], q = L.q[j];
+        if (L.idx[j] == hot) {
+          e = 1.0f;  // replacing trace
+          found = true;
+        }
+        q = __fadd_rn(q, __fmul_rn(c, e));
+        e = term_arg ? 0.0f : __fmul_rn(e, p.trace_decay_f);
+        L.q[j] = q;
+        L.e[j] = e;
+      }
+      work += len;
+      if (!__any_sync(0xFFFFFFFFu, found)) {  // first visit since the last wipe: the table value is current
+        if (lane == 0) {
+          L.idx[len] = (unsigned short)hot;
+          L.q[len] = __fadd_rn(Q[hot], __fmul_rn(c, 1.0f));
+          L.e[len] = term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f);
+          L.pos[hot] = (unsigned short)(len + 1);
+        }
+        len++;
+      }
+      __syncwarp();
+      if (term_arg) {  // e_table.fill(0): nothing is live any more
+        trace_flush(Q, L, len, lane);
+        len = 0;
+        __syncwarp();
+      }
+    }
+    ep_ret = __dadd_rn(ep_ret, r.reward);
+    if (trace && lane == 0)
+      trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                           ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                           ((unsigned)r.stepped << 23);
+    if (lane == 0) {
+      sh_term[a] = r.term;
+      sh_trunc[a] = r.trunc;
+    }
+    __syncthreads();
+    bool all_term = true, all_trunc = true;
+    for (int b = 0; b < p.A; b++) {
+      all_term = all_term && sh_term[b];
+      all_trunc = all_trunc && sh_trunc[b];
+    }
+    __syncthreads();
+    if (all_term || all_trunc) {
+      episodes++;
+      active_steps += s.steps;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, a, s, eps);
+      explore_thr = explore_threshold(eps);
+      trace_flush(Q, L, len, lane);  // reset_e_table (ma_office.py:101-102)
+      len = 0;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    st.tr_len[k] = len;
+    if (st.tr_work) st.tr_work[k] += work;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// sparse Q(lambda): listed values -> table (lists stay live); optionally scatter the traces into a dense buffer
+__global__ void __launch_bounds__(256) qlambda_materialize_kernel(KP p, DState st, float* e_dense) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= st.N * p.A) return;
+  float* Q = st.q + (size_t)warp * (size_t)p.S4;
+  const unsigned short* idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
+  const float* lq = st.tr_q + (size_t)warp * (size_t)st.tr_cap;
+  const float* le = st.tr_e + (size_t)warp * (size_t)st.tr_cap;
+  const unsigned len = st.tr_len[warp];
+  for (unsigned j = lane; j < len; j += 32) {
+    Q[idx[j]] = lq[j];
+    if (e_dense) e_dense[(size_t)warp * (size_t)p.S4 + idx[j]] = le[j];
+  }
+}
+
+// sparse Q(lambda): reset_e_table for the masked instances = flush + forget the lists
+__global__ void __launch_bounds__(256) qlambda_sparse_reset_kernel(KP p, DState st, const unsigned char* mask) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= st.N * p.A) return;
+  if (mask && !mask[warp / p.A]) return;
+  TraceList L;
+  L.pos = st.tr_pos + (size_t)warp * (size_t)p.S4;
+  L.idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
+  L.e = st.tr_e + (size_t)warp * (size_t)st.tr_cap;
+  L.q = st.tr_q + (size_t)warp * (size_t)st.tr_cap;
+  trace_flush(st.q + (size_t)warp * (size_t)p.S4, L, st.tr_len[warp], lane);
+  __syncwarp();
+  if (lane == 0) st.tr_len[warp] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // greedy evaluation (test_policy_optima, evaluation_metrics.py:23-190): the driver loop with best=True and no update
 // ------------------------------------------------------------------------------------------------
 template <int ENV>
@@ -1278,6 +1484,8 @@ static DState dstate(const rlrm_state_t* st) {
   d.N = st->n_instances; d.slot = (unsigned long long*)st->slot; d.epsilon = st->epsilon; d.q = st->q; d.e = st->e;
   d.visits = st->visits; d.ep_return = st->ep_return; d.stats = st->stats;
   d.acc_sum = (long long*)st->acc_sum; d.acc_cnt = st->acc_cnt; d.acc_last = st->acc_last;
+  d.tr_pos = st->tr_pos; d.tr_idx = st->tr_idx; d.tr_e = st->tr_e; d.tr_q = st->tr_q; d.tr_len = st->tr_len;
+  d.tr_work = (unsigned long long*)st->tr_work; d.tr_cap = st->tr_cap;
   return d;
 }
 static DOut dout(const rlrm_step_out_t* o) {
@@ -1296,7 +1504,12 @@ static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need
   if (st->n_instances <= 0) return fail(RLRM_ERR_ARG, "n_instances must be positive");
   if (!st->slot || !st->epsilon) return fail(RLRM_ERR_ARG, "state.slot / state.epsilon are required");
   if (need_q && !st->q) return fail(RLRM_ERR_ARG, "state.q is required");
-  if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e");
+  if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) {
+    if (!st->tr_pos || !st->tr_idx || !st->tr_e || !st->tr_q || !st->tr_len)
+      return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e (dense traces) or state.tr_* (sparse traces)");
+    if (st->tr_cap < h->cfg.max_steps + 1) return fail(RLRM_ERR_ARG, "tr_cap must be >= max_steps + 1");
+    if (h->kp.S4 > 65535) return fail(RLRM_ERR_UNSUPPORTED, "sparse traces need S*4 <= 65535");
+  }
   if (need_q && h->cfg.learning_rate < 0 && !st->visits) return fail(RLRM_ERR_ARG, "learning_rate=None needs state.visits");
   if (need_q && h->cfg.shared_q && h->cfg.learning_rate < 0) return fail(RLRM_ERR_UNSUPPORTED, "shared table with learning_rate=None");
   if (need_q && h->cfg.shared_q && (!st->acc_sum || !st->acc_cnt || !st->acc_last))
@@ -1323,6 +1536,9 @@ extern "C" int rlrm_reset(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_
   LAUNCH_CHECK(h);
   if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->e) {
     clear_traces_kernel<<<blocks_for(n * (h->kp.S4 / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask);
+    LAUNCH_CHECK(h);
+  } else if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->tr_pos && st->q) {
+    qlambda_sparse_reset_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(h->kp, dstate(st), mask);
     LAUNCH_CHECK(h);
   }
   return RLRM_OK;
@@ -1376,6 +1592,8 @@ extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint1
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = st->n_instances * h->kp.A;
   cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.algo == RLRM_ALGO_QLAMBDA && !st->e)
+    return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update on Q(lambda) needs dense traces (state.e); sparse traces are for rlrm_train");
   if (h->kp.algo == RLRM_ALGO_QLAMBDA)
     update_qlambda_kernel<<<(unsigned)n, 256, 0, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
   else if (h->kp.algo == RLRM_ALGO_QRM)
@@ -1393,7 +1611,9 @@ extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint1
 template <int ENV>
 static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int n_iters, int learn, uint32_t* trace, cudaStream_t s) {
   const KP& kp = h->kp;
-  if (kp.algo == RLRM_ALGO_QLAMBDA) {
+  if (kp.algo == RLRM_ALGO_QLAMBDA && !st->e) {
+    train_qlambda_sparse_kernel<ENV><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+  } else if (kp.algo == RLRM_ALGO_QLAMBDA) {
     train_qlambda_kernel<ENV><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
   } else {
     const long long threads = st->n_instances * kp.G;
@@ -1475,6 +1695,16 @@ extern "C" int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval
     eval_kernel<RLRM_ENV_FROZEN_LAKE><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps);
   else
     eval_kernel<RLRM_ENV_OFFICE_WORLD><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, float* e_dense, void* stream) {
+  if (!h || !st) return fail(RLRM_ERR_ARG, "null handle/state");
+  if (!st->q || !st->tr_idx || !st->tr_q || !st->tr_e || !st->tr_len) return fail(RLRM_ERR_ARG, "no sparse trace state");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = st->n_instances * h->kp.A;
+  qlambda_materialize_kernel<<<blocks_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), e_dense);
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }

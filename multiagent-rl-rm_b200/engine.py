@@ -33,7 +33,10 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, compiled: Compiled, n_instances: int, device="cuda:0", track_visits: bool = False,
-                 with_stats: bool = True):
+                 with_stats: bool = True, qlambda_sparse: bool = False):
+        """qlambda_sparse: Q(lambda) only — keep the traces as per-agent lists of live entries (sparse-exact, see
+        include/rlrm_b200.h) instead of the dense e table. Same results bit for bit, far less memory traffic; the fused
+        `train` path only (the call-by-call `update` needs the dense table). Call `sync_tables()` before reading `q`."""
         self.L = load()
         if not torch.cuda.is_available():
             raise RuntimeError("multiagent-rl-rm_b200 needs a CUDA device (no CPU fallback)")
@@ -52,7 +55,20 @@ class Engine:
         self.slot = torch.zeros(n_slots, dtype=torch.int64, device=d)
         self.epsilon = torch.full((n_slots,), float(self.cfg.epsilon_start), dtype=torch.float64, device=d)
         self.q = torch.full((n_tab, self.S, 4), float(compiled.scenario.q_init), dtype=torch.float32, device=d)
-        self.e = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if self.cfg.algo == abi.ALGO_QLAMBDA else None
+        self.sparse = bool(qlambda_sparse) and self.cfg.algo == abi.ALGO_QLAMBDA
+        self.e = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
+        self.tr_cap = 0
+        self.tr_pos = self.tr_idx = self.tr_e = self.tr_q = self.tr_len = self.tr_work = None
+        if self.sparse:
+            if self.S * 4 > 65535:
+                raise ValueError("sparse Q(lambda) traces need S*4 <= 65535")
+            self.tr_cap = ((int(self.cfg.max_steps) + 1 + 31) // 32) * 32
+            self.tr_pos = torch.zeros((n_slots, self.S * 4), dtype=torch.int16, device=d)
+            self.tr_idx = torch.zeros((n_slots, self.tr_cap), dtype=torch.int16, device=d)
+            self.tr_e = torch.zeros((n_slots, self.tr_cap), dtype=torch.float32, device=d)
+            self.tr_q = torch.zeros((n_slots, self.tr_cap), dtype=torch.float32, device=d)
+            self.tr_len = torch.zeros(n_slots, dtype=torch.int32, device=d)
+            self.tr_work = torch.zeros(n_slots, dtype=torch.int64, device=d)
         need_visits = track_visits or self.cfg.learning_rate < 0
         self.visits = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if need_visits else None
         self.ep_return = torch.zeros(n_slots, dtype=torch.float64, device=d)
@@ -62,7 +78,9 @@ class Engine:
         self.acc_cnt = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if shared else None
         self.acc_last = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if shared else None
         self.state = abi.State(self.N, _ptr(self.slot), _ptr(self.epsilon), _ptr(self.q), _ptr(self.e), _ptr(self.visits),
-                               _ptr(self.ep_return), _ptr(self.stats), _ptr(self.acc_sum), _ptr(self.acc_cnt), _ptr(self.acc_last))
+                               _ptr(self.ep_return), _ptr(self.stats), _ptr(self.acc_sum), _ptr(self.acc_cnt), _ptr(self.acc_last),
+                               _ptr(self.tr_pos), _ptr(self.tr_idx), _ptr(self.tr_e), _ptr(self.tr_q), _ptr(self.tr_len),
+                               _ptr(self.tr_work), self.tr_cap, 0)
         self.t = 0  # lockstep iteration counter (Philox counter word)
 
     def __del__(self):
@@ -144,11 +162,21 @@ class Engine:
                                      _ptr(host_epsilon), _ptr(host_stats), self._stream()))
         self.t = t0 + n_iters
 
+    def sync_tables(self, with_traces: bool = False):
+        """Sparse Q(lambda): write the listed (live-trace) q values back into `q` so it can be read; returns the dense
+        e table when `with_traces`. No-op for every other configuration."""
+        if not self.sparse:
+            return self.e if with_traces else None
+        e_dense = torch.zeros_like(self.q) if with_traces else None
+        check(self.L.rlrm_qlambda_materialize(self.h, C.byref(self.state), _ptr(e_dense), self._stream()))
+        return e_dense
+
     def evaluate(self, n_episodes: int, gamma: float, optimal_steps: float = 1.0, t0: Optional[int] = None,
                  max_iters: Optional[int] = None):
         """Batched greedy evaluation (rlrm_evaluate): every instance plays `n_episodes` episodes with its own tables,
         select_action(best=True), no update. Works on a copy of the environment state, like the reference's
         copy.deepcopy(env) (evaluation_metrics.py:45). Returns a numpy record array [N*A] of rlrm_eval_t."""
+        self.sync_tables()
         ev = np.zeros(self.N * self.A, dtype=EVAL_DTYPE)
         ev["cum_gamma"] = 1.0
         ev_dev = torch.from_numpy(ev.view(np.uint8).reshape(-1, EVAL_DTYPE.itemsize).copy()).to(self.device)
@@ -185,6 +213,8 @@ class Engine:
         """One lockstep iteration through the separate entry points, in the reference drivers' order
         (frozen_lake_main.py:345-376 / office_main.py:1709-1749): select for every agent -> wrapper step -> update for
         every agent -> reset of the instances whose episode ended. Bit-identical to one iteration of :meth:`train`."""
+        if self.sparse:
+            raise RuntimeError("the call-by-call path needs dense Q(lambda) traces: build the Engine with qlambda_sparse=False")
         fl_driver = self.cfg.driver == abi.DRIVER_FROZEN_LAKE_MAIN
         cell_before = (self.slot & 0xFFFF).to(torch.int16)
         first = ((self.slot >> abi.SLOT_FLAGS_SHIFT) & abi.FLAG_FIRST) != 0

@@ -300,3 +300,42 @@ def test_shared_learner_generic_path_equals_fast_path(cuda_device):
     assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
     assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
     assert np.array_equal(a.ep_return.cpu().numpy(), b.ep_return.cpu().numpy())
+
+
+@pytest.mark.parametrize("name,n,iters", [("cfg4_office_chain12_qlambda", 48, 1300), ("fl_qlambda", 64, 1500)])
+def test_sparse_exact_qlambda_equals_dense_and_oracle(name, n, iters, cuda_device):
+    """The sparse-exact trace lists (live entries only, q values cached in the list) reproduce the dense sweep of
+    QLearningLambda.update bit for bit: vs the dense CUDA kernel and vs the oracle, across several launches, with
+    terminated updates and episode resets wiping the lists in between."""
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    meta, _ref = load_golden(name)
+    sc = P.Scenario.from_dict(meta["scenario"])
+    c = P.compile_scenario(sc)
+    sp, de = _engine(c, n, qlambda_sparse=True), _engine(c, n)
+    o = O.Oracle(c, n, "f32")
+    sp.reset(); de.reset(); o.reset()
+    t0 = 0
+    for chunk in (3, 250, iters - 253):
+        ts, td = sp.train(chunk, trace=True), de.train(chunk, trace=True)
+        to = o.train(t0, chunk, trace=True)
+        assert np.array_equal(ts.cpu().numpy().view(np.uint32), to) and np.array_equal(td.cpu().numpy().view(np.uint32), to)
+        t0 += chunk
+        e_dense = sp.sync_tables(with_traces=True)
+        assert np.array_equal(sp.q.cpu().numpy(), o.q), f"q after {t0}"
+        assert np.array_equal(e_dense.cpu().numpy(), o.e), f"traces after {t0}"
+        assert np.array_equal(de.q.cpu().numpy(), o.q) and np.array_equal(de.e.cpu().numpy(), o.e)
+    assert np.array_equal(sp.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert np.array_equal(sp.stats_numpy()["episodes"], o.stats["episodes"])
+    live = (o.e != 0).sum(axis=(1, 2))
+    assert int(sp.tr_len.max()) <= sp.tr_cap and (sp.tr_len.cpu().numpy() >= live).all()
+    # a masked reset flushes and forgets the lists of the selected instances only
+    import torch
+
+    mask = torch.zeros(n, dtype=torch.uint8)
+    mask[::2] = 1
+    sp.reset(mask); o.reset(mask.numpy())
+    e_dense = sp.sync_tables(with_traces=True)
+    assert np.array_equal(sp.q.cpu().numpy(), o.q) and np.array_equal(e_dense.cpu().numpy(), o.e)
+    assert int(sp.tr_len.view(n, -1)[::2].sum()) == 0
