@@ -339,3 +339,31 @@ def test_sparse_exact_qlambda_equals_dense_and_oracle(name, n, iters, cuda_devic
     e_dense = sp.sync_tables(with_traces=True)
     assert np.array_equal(sp.q.cpu().numpy(), o.q) and np.array_equal(e_dense.cpu().numpy(), o.e)
     assert int(sp.tr_len.view(n, -1)[::2].sum()) == 0
+
+
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip"])
+def test_batched_reference_style_driver_loop_equals_fused(name, cuda_device):
+    """The reference driver loop written with the batched API (vec.BatchedRMEnvironment: reset / select_action / step /
+    update_policy with [N, A] tensors) gives the same tables and states as the fused kernel."""
+    import multiagent_rlrm_b200 as P
+
+    sc, n, _ = _scenarios_medium()[name]
+    n, iters = 192, 220
+    env = P.BatchedRMEnvironment(sc, n)
+    fused = _engine(P.compile_scenario(sc), n)
+    fused.reset()
+    fused.train(iters)
+    fl = sc.driver == "frozen_lake_main"
+    states, _ = env.reset()
+    for _ in range(iters):
+        actions = env.select_action(states)
+        new_states, rewards, terminated, truncated, infos = env.step(actions)
+        env.update_policy(env.driver_states(states, new_states), actions, rewards, new_states,
+                          (terminated | truncated) if fl else terminated, infos)
+        states = new_states
+        over = env.episode_over(terminated, truncated)
+        if bool(over.any()):
+            states, _ = env.reset(mask=over)
+    assert np.array_equal(env.engine.slot.cpu().numpy(), fused.slot.cpu().numpy())
+    assert np.array_equal(env.q_table.cpu().numpy().reshape(-1), fused.q.cpu().numpy().reshape(-1))
+    assert np.array_equal(env.engine.epsilon.cpu().numpy(), fused.epsilon.cpu().numpy())
