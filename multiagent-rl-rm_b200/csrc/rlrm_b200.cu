@@ -281,6 +281,10 @@ __device__ __forceinline__ void set_component(float4& v, unsigned c, float x) {
   else v.w = x;
 }
 
+__device__ __forceinline__ float get_component(const float4& v, unsigned c) {
+  return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
+}
+
 __device__ __forceinline__ float row_max(const float4& v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
 
 // update_q (qlearning.py:70-79) in the float32 arithmetic numpy performs on a float32 table: weak Python scalars are
@@ -561,6 +565,10 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
   }
   unsigned long long explore_thr = explore_threshold(eps);
   bool had_episode = false;
+  // plain QL with a private table, fixed learning rate and no visit counts: carry the current row across iterations
+  const bool carry = (ALGO == RLRM_ALGO_QL) && !V && !acc.sum && p.lr >= 0.0;
+  float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned row_idx = 0xFFFFFFFFu;
 
   for (int it = 0; it < n_iters; it++) {
     const unsigned long long t = t0 + (unsigned long long)it;
@@ -571,7 +579,11 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
       unsigned w[4];
       philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
       // every agent selects on every iteration, finished ones included (frozen_lake_main.py:350-352)
-      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      const unsigned cur_idx = s.cell * p.nQ + s.rm;
+      if (cur_idx != row_idx) {  // plain QL carries the row of its current state in registers (1-entry cache of Q)
+        row = *reinterpret_cast<const float4*>(Q + (size_t)cur_idx * 4);
+        row_idx = carry ? cur_idx : 0xFFFFFFFFu;
+      }
       action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
       const unsigned before = s.cell;
       const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
@@ -581,7 +593,27 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
         // receives the NEW position as `state` (frozen_lake_main.py:337,359 ; office_main.py:1700 deep-copies)
         const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
         const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
-        agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r, acc);
+        if (ALGO == RLRM_ALGO_QL && carry) {
+          // update_q (qlearning.py:70-79) against the carried row: normally Q[s] is the carried row and only Q[s'] is loaded
+          const unsigned sidx = obs * p.nQ + r.prev_q, snidx = r.cell * p.nQ + r.q;
+          float4 nrow = (snidx == row_idx) ? row : *reinterpret_cast<const float4*>(Q + (size_t)snidx * 4);
+          const float cur = (sidx == row_idx) ? get_component(row, action)
+                                               : ((sidx == snidx) ? get_component(nrow, action) : Q[(size_t)sidx * 4 + action]);
+          double rew = r.reward;
+          if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.nQ + r.q]), tb.phi[p.nQ + r.prev_q]));
+          const float mf = __fmul_rn(term_arg ? 0.0f : 1.0f, row_max(nrow));
+          const float inner = __fadd_rn(__double2float_rn(rew), __fmul_rn(p.gamma_f, mf));
+          const float out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+          if (__float_as_uint(out) != __float_as_uint(cur)) Q[(size_t)sidx * 4 + action] = out;
+          if (sidx == row_idx) set_component(row, action, out);
+          if (snidx != row_idx) {  // the next state's row becomes the carried one
+            if (sidx == snidx) set_component(nrow, action, out);
+            row = nrow;
+            row_idx = snidx;
+          }
+        } else {
+          agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r, acc);
+        }
       }
       term = r.term;
       trunc = r.trunc;
