@@ -263,6 +263,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     import multiagent_rlrm_b200 as P
+    from multiagent_rlrm_b200.dist import merge_replicas
     from multiagent_rlrm_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -289,8 +290,7 @@ def run_gpu_arm(args):
             real_train(chunk, **kw)
             done += chunk
             if sync_every:
-                dist.all_reduce(eng.q, op=dist.ReduceOp.SUM)
-                eng.q.div_(world)
+                merge_replicas(eng.q, world)
 
     if sync_every:
         eng.train = train_with_merge

@@ -6,8 +6,8 @@ keyed on the GLOBAL instance id — the union of the shards is bit-identical to 
 
 Shared learner (BASELINE config 5, ``scenario.shared_q``): each rank learns into its own replica of the per-agent
 tables (include/rlrm_b200.h, "Shared learner") and every ``sync_every`` lockstep iterations the replicas are merged by
-parameter averaging: ``all_reduce(q, SUM) / world`` (NCCL over NVLink on GPUs; 25.6 KB for 4 x 400 x 4 floats, i.e.
-latency-bound). The reference has no shared learner; this rule is this repo's specification.
+parameter averaging: an NCCL all-gather of the 25.6 KB replicas (4 x 400 x 4 floats; latency-bound over NVLink) summed in
+rank order, so the merged table does not depend on the collective's reduction order (``merge_replicas``). The reference has no shared learner; this rule is this repo's specification.
 
 The compute backend is injected (``engine_factory``) so the host logic here is testable on CPU with gloo
 (tests/test_dist_gloo.py plugs the oracle in); the product default is engine.Engine (CUDA only).
@@ -28,6 +28,19 @@ def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     count = base + (1 if rank < rem else 0)
     offset = rank * base + min(rank, rem)
     return offset, count
+
+
+def merge_replicas(q: torch.Tensor, world: int, group=None) -> None:
+    """q <- (q_0 + q_1 + ... + q_{world-1}) / world, summed in RANK ORDER on every rank. A plain all_reduce(SUM) leaves
+    the association order to NCCL's ring/tree, which for more than two ranks changes the last bit; greedy tie-breaks then
+    diverge. The tables are tiny (25.6 KB for config 5), so gathering them costs the same latency as reducing them and
+    makes the merged table independent of the collective algorithm."""
+    parts = [torch.empty_like(q) for _ in range(world)]
+    dist.all_gather(parts, q.contiguous(), group=group)
+    acc = parts[0].clone()
+    for part in parts[1:]:
+        acc.add_(part)
+    q.copy_(acc.div_(world))
 
 
 def _default_engine_factory(compiled, n_local, device):
@@ -60,9 +73,7 @@ class ShardedTrainer:
     def _merge_tables(self):
         """Parameter averaging of the shared-table replicas (the only collective on the learning path)."""
         if self.world > 1:
-            q = self.engine.q
-            dist.all_reduce(q, op=dist.ReduceOp.SUM, group=self.group)
-            q.div_(self.world)
+            merge_replicas(self.engine.q, self.world, self.group)
         self.syncs += 1
 
     def train(self, n_iters: int, learn: bool = True):
