@@ -1,0 +1,148 @@
+"""Edge cases: lane groups with idle lanes (3 agents), the maximum agent count (8), the maximum grid (32x32 = 1024
+cells), a 32-state reward machine with 63 event cells, instance counts that do not fill a warp/block, and the C ABI's
+argument validation. GPU tests compare with the (reference-pinned) oracle; validation tests run on CPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import multiagent_rlrm_b200 as P
+from multiagent_rlrm_b200 import _abi as abi
+from multiagent_rlrm_b200.maps import GridSpec
+from multiagent_rlrm_b200.tables import Scenario, frozen_lake_abc_transitions
+
+
+def _big_grid(env):
+    rng = np.random.default_rng(5)
+    W = H = 32
+    cells = [(x, y) for y in range(H) for x in range(W)]
+    hazards = [cells[i] for i in rng.choice(len(cells), 60, replace=False) if cells[i] not in ((0, 0), (31, 31), (5, 5), (9, 20))]
+    walls = []
+    if env == "office_world":
+        for _ in range(120):
+            x, y = int(rng.integers(0, W - 1)), int(rng.integers(0, H - 1))
+            a, b = ((x, y), (x + 1, y)) if rng.random() < 0.5 else ((x, y), (x, y + 1))
+            walls += [(a, b), (b, a)]
+    return GridSpec(env, W, H, hazards=hazards, walls=walls)
+
+
+def _rm32(grid, n_states=32, n_events=63):
+    rng = np.random.default_rng(9)
+    free = [(x, y) for y in range(grid.height) for x in range(grid.width) if (x, y) not in set(grid.hazards)]
+    events = [free[i] for i in rng.choice(len(free), n_events, replace=False)]
+    tr = []
+    for i in range(n_states - 1):
+        tr.append((f"s{i:02d}", events[i], f"s{i + 1:02d}", float(i % 3)))
+    for i in range(n_states):  # extra branches, loops back, event-less states
+        for ev in events[40 + (i % 5): 63: 7]:
+            if (f"s{i:02d}", ev) not in {(s, e) for s, e, _t, _r in tr}:
+                tr.append((f"s{i:02d}", ev, f"s{(i * 7 + 3) % n_states:02d}", -0.5))
+    tr.append((f"s{n_states - 2:02d}", events[39], f"s{n_states - 1:02d}", 10.0))
+    return tr, events
+
+
+def edge_scenarios():
+    out = {}
+    sc = P.scenario_config3(True)
+    sc.starts = [(5, 0), (0, 0), (9, 9)]
+    out["fl_3_agents_qrm"] = (sc, None, 333, 700)
+    sc = P.scenario_config3(False)
+    sc.starts = [(5, 0), (0, 0), (9, 9), (7, 3), (9, 0), (0, 9), (5, 5), (2, 3)]
+    out["fl_8_agents_ql"] = (sc, None, 77, 700)
+    g = _big_grid("frozen_lake")
+    tr, ev = _rm32(g)
+    sc = Scenario(env="frozen_lake", starts=[(0, 0), (31, 31), (5, 5)], rm_transitions=tr, detector_positions=ev, stochastic=True,
+                  delay_action=True, penalty_amount=-3, algo="qrm", learning_rate=0.5, gamma=0.95, epsilon_start=0.3,
+                  epsilon_end=0.05, epsilon_decay=0.9, q_init=1.0, driver="frozen_lake_main", seed=3)
+    out["fl_32x32_rm32_qrm"] = (sc, g, 130, 1300)
+    g = _big_grid("office_world")
+    tr, ev = _rm32(g, 12, 40)
+    sc = Scenario(env="office_world", starts=[(0, 0), (9, 20)], rm_transitions=tr, detector_positions=ev, stochastic=True, all_slip=True,
+                  high_prob=0.6, wall_penalty=-0.25, plants_penalty=-7, algo="ql", learning_rate=None, gamma=0.9, epsilon_start=0.5,
+                  epsilon_end=0.1, epsilon_decay=0.99, q_init=0.5, driver="office_main", seed=4)
+    out["ow_32x32_lr_none_ql"] = (sc, g, 130, 1300)
+    sc = P.scenario_config1()
+    sc.starts = [(5, 0)]
+    out["one_instance_one_agent"] = (sc, None, 1, 2500)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(edge_scenarios()))
+def test_edge_case_matches_oracle(name, cuda_device):
+    import oracle as O
+    from multiagent_rlrm_b200.engine import Engine
+
+    sc, grid, n, iters = edge_scenarios()[name]
+    c = P.compile_scenario(sc, grid=grid)
+    eng, o = Engine(c, n), O.Oracle(c, n, "f32")
+    eng.reset(); o.reset()
+    tr_g = eng.train(iters, trace=True)
+    tr_o = o.train(0, iters, trace=True)
+    assert np.array_equal(tr_g.cpu().numpy().view(np.uint32), tr_o), name
+    assert np.array_equal(eng.q.cpu().numpy(), o.q) and np.array_equal(eng.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert np.array_equal(eng.epsilon.cpu().numpy(), o.epsilon)
+    if o.visits is not None:
+        assert np.array_equal(eng.visits.cpu().numpy().view(np.uint32), o.visits)
+    # and the same through the call-by-call entry points
+    eng2 = Engine(c, n)
+    eng2.reset()
+    for _ in range(40):
+        eng2.iterate_unfused()
+    o2 = O.Oracle(c, n, "f32")
+    o2.reset(); o2.train(0, 40)
+    assert np.array_equal(eng2.q.cpu().numpy(), o2.q) and np.array_equal(eng2.slot.cpu().numpy().view(np.uint64), o2.slot)
+
+
+def test_three_agent_oracle_matches_live_reference():
+    """CPU: the oracle on a 3-agent instance equals the live reference (skipped without /root/reference)."""
+    import os
+
+    if not os.path.isdir("/root/reference/multiagent_rlrm"):
+        pytest.skip("needs /root/reference")
+    import oracle as O
+    import ref_harness as H
+
+    sc, _g, _n, _t = edge_scenarios()["fl_3_agents_qrm"]
+    ref = H.run_reference(sc.to_dict(), 2, 400)
+    o = O.Oracle(P.compile_scenario(sc), 2, "f32")
+    o.reset(); o.reset()
+    tr = O.unpack_trace(o.train(0, 400, trace=True), 2, 3)
+    for k in ("action", "cell", "q", "term", "trunc"):
+        assert np.array_equal(tr[k], ref[k].astype(np.int32)), k
+    assert np.array_equal(o.q.reshape(ref["q_final"].shape), ref["q_final"])
+
+
+def test_create_rejects_bad_arguments():
+    """rlrm_create validates its arguments before touching the device (error codes, never exceptions)."""
+    from multiagent_rlrm_b200 import _lib
+
+    _lib.build()
+    L = _lib.load()
+
+    def create(mutate):
+        c = P.compile_scenario(P.scenario_config1())
+        t = c.tables_struct()
+        mutate(c.config, t)
+        h = C.c_void_p()
+        rc = L.rlrm_create(C.byref(c.config), C.byref(t), 0, C.byref(h))
+        if rc == 0:
+            L.rlrm_destroy(h)
+        return rc, L.rlrm_last_error().decode()
+
+    for mutate, text in ((lambda cfg, t: setattr(cfg, "abi_version", 99), "abi_version"),
+                         (lambda cfg, t: setattr(cfg, "n_agents", 9), "n_agents"),
+                         (lambda cfg, t: setattr(cfg, "width", 200), "width*height"),
+                         (lambda cfg, t: setattr(cfg, "n_rm_states", 33), "n_rm_states"),
+                         (lambda cfg, t: setattr(cfg, "n_actions", 5), "n_actions"),
+                         (lambda cfg, t: setattr(cfg, "algo", 7), "algo"),
+                         (lambda cfg, t: setattr(t, "delta", None), "null table")):
+        rc, msg = create(mutate)
+        assert rc == -1 and text in msg, (rc, msg)
+    assert L.rlrm_create(None, None, 0, None) == -1
+    with pytest.raises(ValueError):
+        P.compile_scenario(P.scenario_config1(), grid=GridSpec("frozen_lake", 40, 40))
+    sc = P.scenario_config1()
+    sc.starts = [(0, 0)] * 9
+    with pytest.raises(ValueError):
+        P.compile_scenario(sc)
