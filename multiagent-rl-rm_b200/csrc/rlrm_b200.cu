@@ -38,6 +38,7 @@ struct KP {
   float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
   int decay_on_reset, shared_q, use_rsh;
   unsigned seed_lo, seed_hi, instance_offset, n_actions;
+  unsigned rk[20];  // Philox round keys: rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85
   long long S4;  // W*H*nQ*4 floats per table
   // table blob in global memory and section offsets (bytes) inside it / inside the shared-memory copy
   const unsigned char* blob;
@@ -115,15 +116,19 @@ __device__ __forceinline__ Tab stage_tables(const KP& p) {
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Random123): counter (t_lo, t_hi, instance, agent), key (seed_lo, seed_hi)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
-                                              unsigned w[4]) {
+// The 10 round keys (k0 + r*W0, k1 + r*W1) depend only on the seed: they are precomputed on the host into KP::rk so every
+// round is two wide multiplies and two three-input XORs whose key operand comes straight from the constant bank.
+#define RLRM_PHILOX(c0, c1, c2, c3, p, w) philox4x32_10_rk(c0, c1, c2, c3, (p).rk, w)
+__device__ __forceinline__ void philox4x32_10_rk(unsigned c0, unsigned c1, unsigned c2, unsigned c3, const unsigned (&rk)[20],
+                                                 unsigned w[4]) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
-    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ rk[2 * r], n2 = (unsigned)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+    c1 = (unsigned)p1;
+    c3 = (unsigned)p0;
+    c0 = n0;
+    c2 = n2;
   }
   w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(256) select_kernel(KP p, DState st, const unsi
     const uint4 d = reinterpret_cast<const uint4*>(draws)[k];
     w[0] = d.x; w[1] = d.y; w[2] = d.z; w[3] = d.w;
   } else {
-    philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+    RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
   }
   actions_out[k] = (unsigned char)select_action(row, explore_threshold(st.epsilon[k]), w, best != 0, p.n_actions);
 }
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(256) step_kernel(KP p, DState st, const unsign
       w3 = draws[k * 4 + 3];
     } else {
       unsigned w[4];
-      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
       w3 = w[3];
     }
   }
@@ -577,7 +582,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
     int action = 0;
     if (valid) {
       unsigned w[4];
-      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
       // every agent selects on every iteration, finished ones included (frozen_lake_main.py:350-352)
       const unsigned cur_idx = s.cell * p.nQ + s.rm;
       if (cur_idx != row_idx) {  // plain QL carries the row of its current state in registers (1-entry cache of Q)
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
     bool term = true, trunc = true;
     if (valid) {
       unsigned w[4];
-      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
       float4 row;
       row.x = sel4(B[0], B[4], B[8], B[12], s.rm);
       row.y = sel4(B[1], B[5], B[9], B[13], s.rm);
@@ -851,7 +856,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
   for (int it = 0; it < n_iters; it++) {
     const unsigned long long t = t0 + (unsigned long long)it;
     unsigned w[4];
-    philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+    RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
     __syncwarp();
     const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
     const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
@@ -1003,7 +1008,7 @@ __global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState 
   for (int it = 0; it < n_iters; it++) {
     const unsigned long long t = t0 + (unsigned long long)it;
     unsigned w[4];
-    philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+    RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
     __syncwarp();
     // Q row of the current state: lanes 0..3 fetch one action value each
     const unsigned rbase = (s.cell * p.nQ + s.rm) * 4;
@@ -1177,7 +1182,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p, DState st, rlrm
       unsigned w3 = 0;
       if (p.stochastic) {
         unsigned w[4];
-        philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+        RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
         w3 = w[3];
       }
       Rec r;
@@ -1264,7 +1269,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
       s = unpack_slot(st.slot[k]);
       eps = st.epsilon[k];
       unsigned w[4];
-      philox4x32_10((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p.seed_lo, p.seed_hi, w);
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
       float* Q = Qs + (size_t)a * (size_t)p.S4;
       const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
       const int action = select_action(row, explore_threshold(eps), w, learn == 0, p.n_actions);
@@ -1432,6 +1437,10 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
   kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;
   kp.n_actions = (unsigned)cfg->n_actions;
+  for (int r = 0; r < 10; r++) {
+    kp.rk[2 * r] = cfg->seed_lo + (unsigned)r * 0x9E3779B9u;
+    kp.rk[2 * r + 1] = cfg->seed_hi + (unsigned)r * 0xBB67AE85u;
+  }
   kp.S4 = (long long)ncell * kp.nQ * 4;
 
   // pack the tables into one 16-byte aligned blob
