@@ -68,3 +68,17 @@ def save_q_tables(engine_or_agents, agent_names: Optional[Sequence[str]] = None,
 def load_q_tables(path: str) -> Dict[str, np.ndarray]:
     z = np.load(path)
     return {k[len("q_table_"):]: z[k] for k in z.files if k.startswith("q_table_")}
+
+
+def load_q_tables_into(engine, path_or_tables, agent_names: Optional[Sequence[str]] = None) -> None:
+    """Load `q_table_<agent>` arrays (reference format) into an engine: an (S, 4) array is broadcast to every instance,
+    an (N, S, 4) array is taken per instance."""
+    tables = load_q_tables(path_or_tables) if isinstance(path_or_tables, (str, os.PathLike)) else dict(path_or_tables)
+    names = list(agent_names) if agent_names else [f"a{k + 1}" for k in range(engine.A)]
+    q = engine.q.view(engine.A, engine.S, 4) if engine.cfg.shared_q else engine.q.view(engine.N, engine.A, engine.S, 4)
+    for k, name in enumerate(names):
+        t = torch.as_tensor(np.asarray(tables[name]), dtype=torch.float32, device=engine.q.device)
+        if engine.cfg.shared_q:
+            q[k].copy_(t.reshape(engine.S, 4))
+        else:
+            q[:, k].copy_(t if t.dim() == 3 else t.reshape(1, engine.S, 4).expand(engine.N, -1, -1))

@@ -237,6 +237,24 @@ class _TabularBase(BaseLearningAlgorithm):
                                             out.data_ptr(), self._th.stream()))
         return int(out.item())
 
+    # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
+    def __getstate__(self):
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_slot", "_eps")}
+        d["device"] = str(self.device)
+        d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
+                        "visits": self._visits.cpu().numpy()}
+        return d
+
+    def __setstate__(self, d):
+        tables = d.pop("_tables")
+        self.__dict__.update(d)
+        self.device = torch.device(self.device)
+        self._setup(0.0, getattr(self, "lambd", 0.0))
+        self._q.copy_(torch.from_numpy(tables["q"]))
+        self._visits.copy_(torch.from_numpy(tables["visits"]))
+        if self._e is not None and tables["e"] is not None:
+            self._e.copy_(torch.from_numpy(tables["e"]))
+
     def learn_done_episode(self):
         """Decay epsilon after each episode (qlearning.py:153-155)."""
         self.epsilon = max(self.epsilon_end, self.epsilon * self.epsilon_decay)

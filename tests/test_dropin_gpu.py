@@ -201,3 +201,35 @@ def test_wrapper_merges_env_and_rm_reward(cuda_device):
     wrap.reward_modifier = 0.5
     _, rewards, _, _, infos = wrap.step({"a1": ag.action("right")})
     assert rewards["a1"] == 1.0 and infos["a1"]["RQ"] == 0.5
+
+
+def test_learner_pickle_round_trip_and_table_export(cuda_device, tmp_path):
+    """office_main.py --save/--load pickles the learner; evaluation_metrics.save_q_tables writes q_table_<agent>.npz."""
+    import pickle
+
+    import multiagent_rlrm_b200 as P
+    from multiagent_rlrm_b200.engine import Engine
+
+    ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=0.5, state_space_size=6, action_space_size=4)
+    ql.update(0, 1, 2, 1.0, False)
+    ql.update(1, 2, 0, -1.0, False)
+    ql.epsilon = 0.123
+    clone = pickle.loads(pickle.dumps(ql))
+    assert np.array_equal(np.asarray(clone.q_table), np.asarray(ql.q_table)) and np.array_equal(np.asarray(clone.e_table), np.asarray(ql.e_table))
+    assert clone.epsilon == 0.123 and clone.lambd == 0.5
+    clone.update(2, 3, 1, 0.5, True)
+    ql.update(2, 3, 1, 0.5, True)
+    assert np.array_equal(np.asarray(clone.q_table), np.asarray(ql.q_table))
+
+    c = P.compile_scenario(P.scenario_config3())
+    eng = Engine(c, 8)
+    eng.reset(); eng.train(300)
+    path = P.save_q_tables(eng, path=str(tmp_path / "data" / "q_tables.npz"))
+    tables = P.load_q_tables(path)
+    assert set(tables) == {"a1", "a2"} and tables["a1"].shape == (8, 400, 4)
+    other = Engine(c, 8)
+    P.load_q_tables_into(other, path)
+    assert np.array_equal(other.q.cpu().numpy(), eng.q.cpu().numpy())
+    single = Engine(c, 3)
+    P.load_q_tables_into(single, {"a1": tables["a1"][0], "a2": tables["a2"][0]})
+    assert np.array_equal(single.q.cpu().numpy().reshape(3, 2, 400, 4)[2], eng.q.cpu().numpy().reshape(8, 2, 400, 4)[0])
