@@ -712,8 +712,6 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
   const int a = (int)(tid & (p.G - 1));
   const bool valid = (i < st.N) && (a < p.A);
   const long long k = i * p.A + a;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
 
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
@@ -793,8 +791,11 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
                                                              ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
                                                              ((unsigned)r.stepped << 23);
     }
-    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
-    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    // episode over <=> every agent of the instance terminated, or every agent truncated: AND-reduce the two flags
+    // (packed in one word) over the instance's lane group with xor shuffles
+    unsigned flags2 = (term ? 1u : 0u) | (trunc ? 2u : 0u);
+    for (int o = 1; o < p.G; o <<= 1) flags2 &= __shfl_xor_sync(0xFFFFFFFFu, flags2, o);
+    const bool over = flags2 != 0u;
     if (valid && over) {
       episodes++;
       active_steps += s.steps;  // env.agent_steps[agent] of the finished episode

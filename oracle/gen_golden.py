@@ -98,6 +98,19 @@ def scenarios():
                   epsilon_decay=1.0, q_init=2.0, driver="office_main", seed=33, use_rsh=True, rs_kind="vi", rs_gamma=0.9)
     S["ow_shaping_vi_exp3_qrm"] = (sc, 2, 1200, "f32", 1)
 
+    for mp, starts, seed in (("map0", [(0, 0), (5, 5)], 41), ("map2", [(2, 7), (6, 3)], 42), ("map3", [(2, 7), (10, 10), (0, 0)], 43),
+                             ("map4", [(2, 7), (14, 14)], 44)):
+        gm = office_world_grid(mp)
+        tr = [("u0", gm.coffee[0], "u1", 0.5), ("u0", gm.coffee[1], "u1", 0.5), ("u1", gm.letters[0], "u2", 0), ("u1", gm.goals["A"], "u0", -1),
+              ("u2", gm.goals["O"], "u3", 2)]
+        if mp == "map4":  # degenerate on purpose: the LAST inserted transition leads back to u0, so final == initial state and
+            tr = tr[:3] + [tr[4], tr[3]]  # every wrapper step reports termination (episode of length 1, reset every iteration)
+        detm = sorted(set(gm.goals.values()) | set(gm.coffee) | set(gm.letters))
+        sc = Scenario(env="office_world", map_name=mp, starts=starts, rm_transitions=tr, detector_positions=detm, stochastic=True,
+                      high_prob=0.75, wall_penalty=-0.5, plants_penalty=-10, algo="qrm", learning_rate=0.5, gamma=0.9,
+                      epsilon_start=0.5, epsilon_end=0.5, epsilon_decay=1.0, q_init=1.0, driver="office_main", seed=seed)
+        S[f"ow_{mp}_walls_qrm"] = (sc, 2, 700, "f32", 1)
+
     S["cfg4_office_chain12_qlambda"] = (P.scenario_config4(), 1, 1300, "f32", 1)
     S["cfg4_office_chain12_qlambda_f64"] = (P.scenario_config4(), 1, 300, "f64", 1)
 

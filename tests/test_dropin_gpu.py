@@ -14,7 +14,8 @@ DROPIN_CASES = [
     ("fl_delay_penalty_epsdecay_ql", 200), ("fl_lr_none_ql", 160), ("fl_reward_modifier_qrm", 120),
     ("fl_none_event_step_cost_ql", 120), ("cfg2_office_slip_ql", 200), ("ow_allslip_wallpen_exp3_qrm", 150),
     ("ow_terminate_plants_walls_ql", 250), ("cfg4_office_chain12_qlambda", 60), ("fl_shaping_vi_ql", 150),
-    ("fl_shaping_distance_qrm", 150), ("ow_shaping_vi_exp3_qrm", 150),
+    ("fl_shaping_distance_qrm", 150), ("ow_shaping_vi_exp3_qrm", 150), ("ow_map2_walls_qrm", 120), ("ow_map3_walls_qrm", 100),
+    ("ow_map4_walls_qrm", 60),
 ]
 
 
