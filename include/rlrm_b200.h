@@ -107,6 +107,12 @@ typedef struct rlrm_config {
   /* randomness: Philox4x32-10, key = (seed_lo, seed_hi), counter = (t_lo, t_hi, instance_offset + i, a) */
   uint32_t seed_lo, seed_hi;
   uint32_t instance_offset;    /* global id of local instance 0 (multi-GPU sharding keeps draws independent of G) */
+  int32_t random_starts;       /* env.random_start_positions (ma_frozen_lake.py:63-64, 156-172): on every reset the agents are
+                                  placed on distinct free cells. Sampling (this repo's injection-consistent scheme): partial
+                                  Fisher-Yates over tables.free_cells, pick k uses word (k & 3) of
+                                  philox(counter = (T_lo, ~T_hi, instance, 0x80000000 | k >> 2)), j = k + ((w * (F - k)) >> 32),
+                                  T = iteration index of the new episode's first step */
+  int32_t n_free_cells;        /* F */
   int32_t use_rsh;             /* QLearning.use_rsh: potential-based shaping R' = R + gamma*Phi(q') - Phi(q) (qlearning.py:51-66, 93-105) */
   int32_t n_actions;           /* 1..4 usable actions (exploration draws (w1*n_actions)>>32); tables are always 4 wide */
   int32_t reserved;            /* bit 0: force the generic kernels (testing: generic vs specialised must agree) */
@@ -123,6 +129,8 @@ typedef struct rlrm_tables {
   const double* rcf;          /* [nQ][nEv+1] transition reward for QRM counterfactuals (unscaled, :150-153) */
   const uint8_t* qrm_states;  /* [n_qrm_states] RM state indices, in get_all_states()[:-1] order */
   const uint16_t* start_cell; /* [A] agent.initial_position */
+  const uint16_t* free_cells; /* [F] cells that are not holes, enumerated x-major (for x: for y) as ma_frozen_lake.py:163-168; may be NULL
+                                 when random_starts == 0 */
   const double* phi;          /* [2][nQ] RewardMachine.potentials (reward_machine.py:197-237); NULL = no shaping.
                                  row 0: Phi of the state with index i — used by the QRM counterfactual loop, which maps
                                         indices back to labels (qlearning.py:100-104);
@@ -223,6 +231,9 @@ int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double gamma, doubl
  * ma_office.py:77-120): positions, RM state, counters, epsilon decay, Q(lambda) trace wipe.
  * mask: device uint8 [N] selecting instances, or NULL for all. */
 int rlrm_reset(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, void* stream);
+/* Same with the iteration index `t` of the next step, which keys the random start positions (cfg.random_starts);
+ * rlrm_reset is rlrm_reset_at with t = 0. The fused kernels use t + 1 of the iteration that ended the episode. */
+int rlrm_reset_at(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, uint64_t t, void* stream);
 
 /* AgentRL.select_action (agent_rl.py:80-106) -> QLearning.choose_action (qlearning.py:112-143).
  * draws: device uint32 [N*A*4] injected Philox words (w0 explore, w1 random action, w2 tie-break, w3 slip)

@@ -57,6 +57,8 @@ class Config(C.Structure):
         ("seed_lo", C.c_uint32),
         ("seed_hi", C.c_uint32),
         ("instance_offset", C.c_uint32),
+        ("random_starts", C.c_int32),
+        ("n_free_cells", C.c_int32),
         ("use_rsh", C.c_int32),
         ("n_actions", C.c_int32),
         ("reserved", C.c_int32),
@@ -73,6 +75,7 @@ class Tables(C.Structure):
         ("rcf", C.c_void_p),
         ("qrm_states", C.c_void_p),
         ("start_cell", C.c_void_p),
+        ("free_cells", C.c_void_p),
         ("phi", C.c_void_p),
     ]
 
@@ -171,6 +174,7 @@ EXPORTED_SYMBOLS = (
     "rlrm_destroy",
     "rlrm_set_learner",
     "rlrm_reset",
+    "rlrm_reset_at",
     "rlrm_select_action",
     "rlrm_step",
     "rlrm_rm_step",

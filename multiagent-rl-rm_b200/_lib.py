@@ -70,6 +70,7 @@ def load():
     L.rlrm_destroy.argtypes = [vp]
     L.rlrm_set_learner.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.rlrm_reset.argtypes = [vp, C.POINTER(abi.State), vp, vp]
+    L.rlrm_reset_at.argtypes = [vp, C.POINTER(abi.State), vp, u64, vp]
     L.rlrm_select_action.argtypes = [vp, C.POINTER(abi.State), vp, u64, C.c_int, vp, vp]
     L.rlrm_step.argtypes = [vp, C.POINTER(abi.State), vp, vp, u64, C.c_int, C.POINTER(abi.StepOut), vp]
     L.rlrm_rm_step.argtypes = [vp, i64, vp, vp, vp, vp, vp]
@@ -80,7 +81,7 @@ def load():
     L.rlrm_qlambda_materialize.argtypes = [vp, C.POINTER(abi.State), vp, vp]
     L.rlrm_launch_count.argtypes = [vp]
     L.rlrm_launch_count.restype = i64
-    for name in ("rlrm_create", "rlrm_destroy", "rlrm_set_learner", "rlrm_reset", "rlrm_select_action", "rlrm_step",
+    for name in ("rlrm_create", "rlrm_destroy", "rlrm_set_learner", "rlrm_reset", "rlrm_reset_at", "rlrm_select_action", "rlrm_step",
                  "rlrm_rm_step", "rlrm_update", "rlrm_train", "rlrm_train_host", "rlrm_evaluate", "rlrm_qlambda_materialize"):
         getattr(L, name).restype = C.c_int
     if L.rlrm_abi_version() != abi.ABI_VERSION:

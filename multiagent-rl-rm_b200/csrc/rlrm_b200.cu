@@ -36,14 +36,14 @@ struct KP {
   double hole_penalty, wall_penalty;
   double lr, gamma, eps_end, eps_decay;
   float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
-  int decay_on_reset, shared_q, use_rsh;
+  int decay_on_reset, shared_q, use_rsh, random_starts, n_free;
   unsigned seed_lo, seed_hi, instance_offset, n_actions;
   unsigned rk[20];  // Philox round keys: rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85
   long long S4;  // W*H*nQ*4 floats per table
   // table blob in global memory and section offsets (bytes) inside it / inside the shared-memory copy
   const unsigned char* blob;
   int blob_bytes;
-  int off_next, off_flags, off_label, off_delta, off_rq, off_rcf, off_qrm, off_start, off_phi;
+  int off_next, off_flags, off_label, off_delta, off_rq, off_rcf, off_qrm, off_start, off_phi, off_free;
 };
 
 struct Tab {
@@ -55,6 +55,7 @@ struct Tab {
   const double* rcf;
   const unsigned char* qrm_states;
   const unsigned short* start_cell;
+  const unsigned short* free_cells;
   const double* phi;
 };
 
@@ -110,6 +111,7 @@ __device__ __forceinline__ Tab stage_tables(const KP& p) {
   t.qrm_states = smem_raw + p.off_qrm;
   t.start_cell = reinterpret_cast<const unsigned short*>(smem_raw + p.off_start);
   t.phi = reinterpret_cast<const double*>(smem_raw + p.off_phi);
+  t.free_cells = reinterpret_cast<const unsigned short*>(smem_raw + p.off_free);
   return t;
 }
 
@@ -342,8 +344,31 @@ __device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, float* 
   }
 }
 
-__device__ __forceinline__ void reset_slot(const KP& p, const Tab& tb, int a, Slot& s, double& eps) {
-  s.cell = tb.start_cell[a];
+// _sample_start_positions (ma_frozen_lake.py:156-172): agent a's start cell = entry a of a Fisher-Yates shuffle of the free
+// cells driven by Philox words keyed on (T, instance) — see rlrm_config_t.random_starts. Every agent replays steps 0..a.
+__device__ __forceinline__ unsigned sample_start(const KP& p, const Tab& tb, long long i, int a, unsigned long long T) {
+  unsigned pos[RLRM_MAX_AGENTS], val[RLRM_MAX_AGENTS];
+  unsigned w[4] = {0, 0, 0, 0}, out = 0;
+  for (int k = 0; k <= a; k++) {
+    if ((k & 3) == 0)
+      RLRM_PHILOX((unsigned)T, ~(unsigned)(T >> 32), p.instance_offset + (unsigned)i, 0x80000000u | (unsigned)(k >> 2), p, w);
+    const unsigned wk = (k & 3) == 0 ? w[0] : ((k & 3) == 1 ? w[1] : ((k & 3) == 2 ? w[2] : w[3]));
+    const unsigned j = (unsigned)k + __umulhi(wk, (unsigned)(p.n_free - k));
+    unsigned vk = tb.free_cells[k], vj = tb.free_cells[j];
+    for (int m = 0; m < k; m++) {
+      if (pos[m] == (unsigned)k) vk = val[m];
+      if (pos[m] == j) vj = val[m];
+    }
+    out = vj;
+    pos[k] = j;
+    val[k] = vk;
+  }
+  return out;
+}
+
+// env.reset for one agent; T = iteration index of the new episode's first step (keys the random start positions)
+__device__ __forceinline__ void reset_slot(const KP& p, const Tab& tb, long long i, int a, unsigned long long T, Slot& s, double& eps) {
+  s.cell = p.random_starts ? sample_start(p, tb, i, a, T) : tb.start_cell[a];
   s.steps = 0;
   s.time = 0;
   s.rm = 0;  // the initial RM state has index 0 (reward_machine.py:32-36)
@@ -367,7 +392,7 @@ __device__ __forceinline__ Acc make_acc(const KP& p, const DState& st, size_t ba
 // ------------------------------------------------------------------------------------------------
 // unfused kernels (the reference's call-by-call API; also the parity path with injected draws)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsigned char* mask) {
+__global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsigned char* mask, unsigned long long t) {
   Tab tb = stage_tables(p);
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= st.N * p.A) return;
@@ -376,7 +401,7 @@ __global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsig
   if (mask && !mask[i]) return;
   Slot s;
   double eps = st.epsilon[k];
-  reset_slot(p, tb, a, s, eps);
+  reset_slot(p, tb, i, a, t, s, eps);
   st.slot[k] = pack_slot(s);
   st.epsilon[k] = eps;
   if (st.ep_return) st.ep_return[k] = 0.0;
@@ -640,7 +665,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
       last_length = s.time;
       had_episode = true;
       ep_ret = 0.0;
-      reset_slot(p, tb, a, s, eps);  // next episode starts with rm_env.reset (frozen_lake_main.py:337)
+      reset_slot(p, tb, i, a, t + 1, s, eps);  // next episode starts with rm_env.reset (frozen_lake_main.py:337)
       explore_thr = explore_threshold(eps);
     }
   }
@@ -805,7 +830,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       last_length = s.time;
       had_episode = true;
       ep_ret = 0.0;
-      reset_slot(p, tb, a, s, eps);
+      reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
       load_block4(Q, s.cell, B, bmax);
     }
@@ -924,7 +949,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
       last_length = s.time;
       had_episode = true;
       ep_ret = 0.0;
-      reset_slot(p, tb, a, s, eps);
+      reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
       // reset_e_table (ma_office.py:101-102)
       float4* E4 = reinterpret_cast<float4*>(E);
@@ -1090,7 +1115,7 @@ __global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState 
       last_length = s.time;
       had_episode = true;
       ep_ret = 0.0;
-      reset_slot(p, tb, a, s, eps);
+      reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
       trace_flush(Q, L, len, lane);  // reset_e_table (ma_office.py:101-102)
       len = 0;
@@ -1217,7 +1242,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p, DState st, rlrm
       double eps_unused = 0.0;
       KP q = p;
       q.decay_on_reset = 0;  // evaluation runs on a copy of the env: the training epsilon is not touched
-      reset_slot(q, tb, a, s, eps_unused);
+      reset_slot(q, tb, i, a, t + 1, s, eps_unused);
     }
   }
   if (valid) {
@@ -1307,7 +1332,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
           st.stats[k] = z;
         }
         if (st.ep_return) st.ep_return[k] = 0.0;
-        reset_slot(p, tb, a, s, eps);
+        reset_slot(p, tb, i, a, t + 1, s, eps);
         st.epsilon[k] = eps;
       }
       st.slot[k] = pack_slot(s);
@@ -1395,6 +1420,8 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (cfg->n_qrm_states < 0 || cfg->n_qrm_states > RLRM_MAX_RM_STATES) return fail(RLRM_ERR_ARG, "n_qrm_states out of range");
   if (cfg->slip_n < 1 || cfg->slip_n > 4) return fail(RLRM_ERR_ARG, "slip_n out of range");
   if (cfg->n_actions < 1 || cfg->n_actions > RLRM_N_ACTIONS) return fail(RLRM_ERR_ARG, "n_actions out of range");
+  if (cfg->random_starts && (!tb || !tb->free_cells || cfg->n_free_cells < cfg->n_agents || cfg->n_free_cells > ncell))
+    return fail(RLRM_ERR_ARG, "random_starts needs tables.free_cells with n_agents <= n_free_cells <= width*height");
   if (cfg->algo < 0 || cfg->algo > RLRM_ALGO_QLAMBDA) return fail(RLRM_ERR_ARG, "unknown algo");
   if (cfg->env_kind != RLRM_ENV_FROZEN_LAKE && cfg->env_kind != RLRM_ENV_OFFICE_WORLD) return fail(RLRM_ERR_ARG, "unknown env_kind");
   if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->learning_rate < 0)
@@ -1436,6 +1463,8 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   fill_learner(kp, cfg->learning_rate, cfg->gamma, cfg->lambd);
   kp.decay_on_reset = cfg->decay_on_reset; kp.shared_q = cfg->shared_q;
   kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
+  kp.random_starts = cfg->random_starts ? 1 : 0;
+  kp.n_free = cfg->n_free_cells;
   kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;
   kp.n_actions = (unsigned)cfg->n_actions;
   for (int r = 0; r < 10; r++) {
@@ -1456,6 +1485,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.off_label = off; off = align16(off + ncell);
   kp.off_delta = off; off = align16(off + nd);
   kp.off_qrm = off; off = align16(off + RLRM_MAX_RM_STATES);
+  kp.off_free = off; off = align16(off + (kp.random_starts ? kp.n_free : 0) * 2);
   kp.blob_bytes = off;
   unsigned char* host = new (std::nothrow) unsigned char[off];
   if (!host) { delete h; return fail(RLRM_ERR_ARG, "out of host memory"); }
@@ -1469,6 +1499,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   memcpy(host + kp.off_label, tb->label, ncell);
   memcpy(host + kp.off_delta, tb->delta, nd);
   if (kp.n_qrm > 0 && tb->qrm_states) memcpy(host + kp.off_qrm, tb->qrm_states, kp.n_qrm);
+  if (kp.random_starts) memcpy(host + kp.off_free, tb->free_cells, (size_t)kp.n_free * 2);
   cudaError_t e = cudaMalloc(&h->d_blob, off);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, host, off, cudaMemcpyHostToDevice);
   delete[] host;
@@ -1568,13 +1599,18 @@ static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need
 
 static unsigned blocks_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
+extern "C" int rlrm_reset_at(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, uint64_t t, void* stream);
 extern "C" int rlrm_reset(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, void* stream) {
+  return rlrm_reset_at(h, st, mask, 0, stream);
+}
+
+extern "C" int rlrm_reset_at(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* mask, uint64_t t, void* stream) {
   int rc = check_state(h, st, false);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = st->n_instances * h->kp.A;
-  reset_kernel<<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), mask);
+  reset_kernel<<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), mask, t);
   LAUNCH_CHECK(h);
   if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->e) {
     clear_traces_kernel<<<blocks_for(n * (h->kp.S4 / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask);

@@ -106,7 +106,7 @@ class Engine:
     def reset(self, mask: Optional[torch.Tensor] = None):
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        check(self.L.rlrm_reset(self.h, C.byref(self.state), _ptr(mask), self._stream()))
+        check(self.L.rlrm_reset_at(self.h, C.byref(self.state), _ptr(mask), self.t, self._stream()))
 
     def select_action(self, t: Optional[int] = None, draws: Optional[torch.Tensor] = None, best: bool = False) -> torch.Tensor:
         out = torch.empty(self.N * self.A, dtype=torch.uint8, device=self.device)
@@ -184,7 +184,7 @@ class Engine:
         eps = self.epsilon.clone()
         # e = NULL: the copy's traces are never read by a greedy rollout, and the training traces must not be wiped
         st = abi.State(self.N, _ptr(slot), _ptr(eps), _ptr(self.q), None, None, None, None, None, None, None)
-        check(self.L.rlrm_reset(self.h, C.byref(st), None, self._stream()))  # env_test.reset(...)
+        check(self.L.rlrm_reset_at(self.h, C.byref(st), None, self.t if t0 is None else t0, self._stream()))  # env_test.reset(...)
         n_iters = max_iters or n_episodes * (int(self.cfg.max_steps) + 1)
         check(self.L.rlrm_evaluate(self.h, C.byref(st), _ptr(ev_dev), self.t if t0 is None else t0, n_iters, n_episodes,
                                    float(gamma), float(optimal_steps), self._stream()))

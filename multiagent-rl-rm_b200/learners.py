@@ -101,7 +101,7 @@ class _TableHandle:
             delta=np.full((self.nq, 1), abi.NO_TRANSITION, np.uint8), rq=np.zeros((self.nq, 1)), rcf=np.zeros((self.nq, 1)),
             qrm_states=np.zeros(1, np.uint8), start_cell=np.zeros(1, np.uint16))
         t = abi.Tables(*[self._arrs[k].ctypes.data for k in ("next_cell", "cell_flags", "label", "delta", "rq", "rcf",
-                                                            "qrm_states", "start_cell")], None)
+                                                            "qrm_states", "start_cell")], None, None)
         h = C.c_void_p()
         dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
         check(self.L.rlrm_create(C.byref(cfg), C.byref(t), dev, C.byref(h)))

@@ -48,6 +48,7 @@ class Scenario:
     terminate_on_plants: bool = False
     terminate_hit_walls: bool = False
     max_steps: int = 1000
+    random_start_positions: bool = False  # FrozenLake only (ma_frozen_lake.py:63-64)
     # learner
     algo: str = "qrm"  # "ql" | "qrm" | "qlambda"
     learning_rate: Optional[float] = 1.0
@@ -180,6 +181,7 @@ class Compiled:
     events: List[Tuple[int, int]]
     config: abi.Config
     phi: Optional[np.ndarray] = None
+    free_cells: Optional[np.ndarray] = None
 
     @property
     def n_agents(self):
@@ -202,6 +204,9 @@ class Compiled:
         if self.phi is not None:
             self.phi = np.ascontiguousarray(self.phi, dtype=np.float64)
             t.phi = self.phi.ctypes.data
+        if self.free_cells is not None:
+            self.free_cells = np.ascontiguousarray(self.free_cells, dtype=np.uint16)
+            t.free_cells = self.free_cells.ctypes.data
         return t
 
 
@@ -273,11 +278,21 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
             phi[1, idx] = rm.potentials.get(idx, 0)
     cfg.use_rsh = int(bool(sc.use_rsh) and sc.algo in ("ql", "qrm"))
     start_cell = np.array([y * W + x for (x, y) in sc.starts], dtype=np.uint16)
+    free_cells = None
+    if sc.random_start_positions:
+        if grid.env != "frozen_lake":
+            raise ValueError("random_start_positions exists only in MultiAgentFrozenLake (ma_frozen_lake.py:63)")
+        holes = set(grid.hazards)
+        free = [(x, y) for x in range(W) for y in range(H) if (x, y) not in holes]  # x-major, as ma_frozen_lake.py:163-168
+        if len(free) < len(sc.starts):
+            raise ValueError("Not enough free cells to place all agents.")
+        free_cells = np.array([y * W + x for (x, y) in free], dtype=np.uint16)
+        cfg.random_starts, cfg.n_free_cells = 1, len(free)
     return Compiled(
         scenario=sc, grid=grid, rm=rm,
         next_cell=build_next_cell(grid), cell_flags=build_cell_flags(grid),
         label=t["label"], delta=t["delta"], rq=t["rq"], rcf=t["rcf"], qrm_states=t["qrm_states"],
-        start_cell=start_cell, events=t["events"], config=cfg, phi=phi,
+        start_cell=start_cell, events=t["events"], config=cfg, phi=phi, free_cells=free_cells,
     )
 
 

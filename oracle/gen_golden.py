@@ -56,6 +56,14 @@ def scenarios():
     sc.seed = 11
     S["fl_none_event_step_cost_ql"] = (sc, 2, 500, "f32", 1)
 
+    sc = P.scenario_config5(False)
+    sc.random_start_positions, sc.seed, sc.starts = True, 51, sc.starts[:3]
+    S["fl_random_starts_3agents_qrm"] = (sc, 3, 700, "f32", 1)
+
+    sc = P.scenario_config3(False)
+    sc.random_start_positions, sc.seed, sc.starts = True, 52, sc.starts + [(9, 9), (7, 3), (9, 0), (0, 9)]
+    S["fl_random_starts_6agents_ql"] = (sc, 2, 500, "f32", 1)
+
     S["cfg5_fl_4agents_qrm"] = (P.scenario_config5(False), 2, 500, "f32", 1)
 
     S["cfg2_office_det_ql"] = (P.scenario_config2(False), 2, 1500, "f32", 1)

@@ -85,9 +85,9 @@ class Oracle:
                                _p(self.ep_return), _p(self.stats), _p(self.acc_sum), _p(self.acc_cnt), _p(self.acc_last))
 
     # -- C calls -------------------------------------------------------------------------------
-    def reset(self, mask=None):
+    def reset(self, mask=None, t=0):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-        self.L.oracle_reset(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(m)))
+        self.L.oracle_reset_at(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(m)), C.c_uint64(t))
 
     def select_action(self, t=0, draws=None, best=False):
         out = np.zeros(self.N * self.A, dtype=np.uint8)
@@ -134,7 +134,7 @@ class Oracle:
         ev["cum_gamma"] = 1.0
         slot, eps = self.slot.copy(), self.epsilon.copy()
         st = abi.State(self.N, _p(slot), _p(eps), _p(self.q), None, None, None, None, None, None, None)
-        self.L.oracle_reset(C.byref(self.cfg), C.byref(self.tables), C.byref(st), None)
+        self.L.oracle_reset_at(C.byref(self.cfg), C.byref(self.tables), C.byref(st), None, C.c_uint64(t0))
         eps[:] = self.epsilon
         n_iters = max_iters or n_episodes * (self.cfg.max_steps + 1)
         self.L.oracle_evaluate(C.byref(self.cfg), C.byref(self.tables), C.byref(st), C.c_void_p(ev.ctypes.data), C.c_uint64(t0),

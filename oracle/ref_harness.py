@@ -45,6 +45,15 @@ class DrawSource:
         self.t = 0
         self._cache = {}
 
+    def start_words(self, i, block):
+        """Words that key the random start positions of instance i for the episode whose first step is iteration t."""
+        import philox
+
+        T = self.t
+        w = philox.philox4x32_10(T & 0xFFFFFFFF, (~(T >> 32)) & 0xFFFFFFFF, (self.off + i) & 0xFFFFFFFF, 0x80000000 | block,
+                                 self.seed & 0xFFFFFFFF, (self.seed >> 32) & 0xFFFFFFFF)
+        return [int(x) for x in w]
+
     def words(self, i, a):
         w = self._cache.get(self.t)
         if w is None:
@@ -89,6 +98,16 @@ class EnvRNG:
         """Hook used by this repo's environments (envs.py)."""
         return self.src.words(self.i, agent_index)
 
+    def shuffle(self, cells):
+        """Stands in for rng.shuffle(free_cells) in _sample_start_positions (ma_frozen_lake.py:171): an in-place Fisher-Yates
+        shuffle whose k-th swap partner is j = k + ((w_k * (F - k)) >> 32); only the first A entries are ever read."""
+        F, w = len(cells), None
+        for k in range(min(F - 1, 8)):
+            if k % 4 == 0:
+                w = self.src.start_words(self.i, k // 4)
+            j = k + ((w[k % 4] * (F - k)) >> 32)
+            cells[k], cells[j] = cells[j], cells[k]
+
     def choice(self, actions, p=None):
         u = int(self.src.words(self.i, self.agent_index)[3]) / 4294967296.0
         cdf = np.cumsum(np.array(p, dtype=np.float64))
@@ -118,6 +137,7 @@ def build_reference(sc: dict, table_dtype=np.float32):
         env.frozen_lake_stochastic = bool(sc["stochastic"])
         env.penalty_amount = sc["penalty_amount"]
         env.delay_action = bool(sc["delay_action"])
+        env.random_start_positions = bool(sc.get("random_start_positions", False))
     else:
         from multiagent_rlrm.environments.office_world.action_encoder_office_world import ActionEncoderOfficeWorld as AEnc
         from multiagent_rlrm.environments.office_world.config_office import config as ow_config
@@ -223,11 +243,23 @@ def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float
             return _orig(agent, intended)
 
         env.get_stochastic_action = gsa
+        def do_reset():
+            # env.reset() builds its own np.random.default_rng(seed) and (random_start_positions) shuffles with it before
+            # returning (ma_frozen_lake.py:59-64): hand it the stand-in for the duration of the call
+            real = np.random.default_rng
+            np.random.default_rng = lambda *a, **k: EnvRNG(src, i)
+            try:
+                return rm_env.reset(sc["seed"])
+            finally:
+                np.random.default_rng = real
+
+        src.t = 0
         for _ in range(pre_resets):
-            rm_env.reset(sc["seed"])
+            do_reset()
         t = 0
         while t < n_iters:
-            states, infos = rm_env.reset(sc["seed"])
+            src.t = t  # the new episode's first step is iteration t
+            states, infos = do_reset()
             env.rng = EnvRNG(src, i)  # reset() re-created env.rng (ma_frozen_lake.py:59 ; ma_office.py:96)
             if not fl_driver:
                 states = copy.deepcopy(states)  # office_main.py:1700

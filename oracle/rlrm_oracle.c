@@ -79,11 +79,33 @@ static size_t table_base(const rlrm_config_t* cfg, int64_t i, int a) {
 }
 
 /* ---- reset: ma_frozen_lake.py:43-94 ; ma_office.py:77-120 ; agent_rl.py:372-384 ------------------- */
-static void reset_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i) {
+/* _sample_start_positions (ma_frozen_lake.py:156-172): distinct free cells; the reference shuffles the whole free-cell list
+ * and keeps the first A entries, here the first A steps of a Fisher-Yates shuffle with injected Philox words (see
+ * rlrm_config_t.random_starts) */
+static void sample_starts(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int64_t i, uint64_t T, uint32_t* out) {
+  int F = cfg->n_free_cells, A = cfg->n_agents;
+  uint32_t pos[RLRM_MAX_AGENTS], val[RLRM_MAX_AGENTS];
+  int n_over = 0;
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int k = 0; k < A; k++) {
+    if ((k & 3) == 0)
+      oracle_philox((uint32_t)T, ~(uint32_t)(T >> 32), cfg->instance_offset + (uint32_t)i, 0x80000000u | (uint32_t)(k >> 2),
+                    cfg->seed_lo, cfg->seed_hi, w);
+    uint32_t j = (uint32_t)k + (uint32_t)(((uint64_t)w[k & 3] * (uint32_t)(F - k)) >> 32);
+    uint32_t vk = tb->free_cells[k], vj = tb->free_cells[j];
+    for (int m = 0; m < n_over; m++) { if (pos[m] == (uint32_t)k) vk = val[m]; if (pos[m] == j) vj = val[m]; }
+    out[k] = vj;          /* list[k] <- list[j] */
+    pos[n_over] = j; val[n_over] = vk; n_over++; /* list[j] <- list[k] (later entries override earlier ones) */
+  }
+}
+
+static void reset_instance_at(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i, uint64_t T) {
   size_t S4 = (size_t)cfg->width * cfg->height * cfg->n_rm_states * 4;
+  uint32_t starts[RLRM_MAX_AGENTS];
+  if (cfg->random_starts) sample_starts(cfg, tb, i, T, starts);
   for (int a = 0; a < cfg->n_agents; a++) {
     size_t k = (size_t)i * cfg->n_agents + a;
-    slot_t s = {tb->start_cell[a], 0, 0, 0 /* RM initial state has index 0: reward_machine.py:32-36 */,
+    slot_t s = {cfg->random_starts ? starts[a] : tb->start_cell[a], 0, 0, 0 /* RM initial state has index 0: reward_machine.py:32-36 */,
                 RLRM_FLAG_ACTIVE | RLRM_FLAG_FIRST};
     st->slot[k] = pack(s);
     if (cfg->algo == RLRM_ALGO_QLAMBDA && st->e && !cfg->shared_q) /* reset_e_table: ma_frozen_lake.py:80-81 */
@@ -96,10 +118,18 @@ static void reset_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, co
   }
 }
 
-int oracle_reset(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, const uint8_t* mask) {
+static void reset_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i) {
+  reset_instance_at(cfg, tb, st, i, 0);
+}
+
+int oracle_reset_at(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, const uint8_t* mask, uint64_t t) {
   for (int64_t i = 0; i < st->n_instances; i++)
-    if (!mask || mask[i]) reset_instance(cfg, tb, st, i);
+    if (!mask || mask[i]) reset_instance_at(cfg, tb, st, i, t);
   return 0;
+}
+
+int oracle_reset(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, const uint8_t* mask) {
+  return oracle_reset_at(cfg, tb, st, mask, 0);
 }
 
 /* ---- select: agent_rl.py:80-106 ; qlearning.py:112-143 -------------------------------------------- */
@@ -420,7 +450,7 @@ static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, c
         z->last_length = s.time;
       }
     }
-    reset_instance(cfg, tb, st, i);
+    reset_instance_at(cfg, tb, st, i, t + 1);
   }
 }
 
@@ -495,7 +525,7 @@ int oracle_evaluate(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlr
           if (len > 0) e->arps_sum += (e->disc_return / (double)len) / optimal_steps; /* :131-139 */
           e->cum_gamma = 1.0; e->disc_return = 0.0; e->in_success = 0;
         }
-        reset_instance(&c2, tb, st, i);
+        reset_instance_at(&c2, tb, st, i, t + 1);
       }
     }
   }

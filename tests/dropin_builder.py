@@ -11,6 +11,7 @@ def build_b200(sc, table_dtype=None):
         env.frozen_lake_stochastic = bool(sc["stochastic"])
         env.penalty_amount = sc["penalty_amount"]
         env.delay_action = bool(sc["delay_action"])
+        env.random_start_positions = bool(sc.get("random_start_positions", False))
         SEnc, AEnc = P.StateEncoderFrozenLake, P.ActionEncoderFrozenLake
     else:
         g = office_world_grid(sc["map_name"])

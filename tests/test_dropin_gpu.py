@@ -15,7 +15,7 @@ DROPIN_CASES = [
     ("fl_none_event_step_cost_ql", 120), ("cfg2_office_slip_ql", 200), ("ow_allslip_wallpen_exp3_qrm", 150),
     ("ow_terminate_plants_walls_ql", 250), ("cfg4_office_chain12_qlambda", 60), ("fl_shaping_vi_ql", 150),
     ("fl_shaping_distance_qrm", 150), ("ow_shaping_vi_exp3_qrm", 150), ("ow_map2_walls_qrm", 120), ("ow_map3_walls_qrm", 100),
-    ("ow_map4_walls_qrm", 60),
+    ("ow_map4_walls_qrm", 60), ("fl_random_starts_3agents_qrm", 200), ("fl_random_starts_6agents_ql", 120),
 ]
 
 

@@ -77,6 +77,9 @@ def _scenarios_medium():
     sc = P.scenario_config3(False)
     sc.learning_rate, sc.epsilon_start, sc.epsilon_end, sc.epsilon_decay = None, 0.6, 0.05, 0.97
     out["fl_lr_none_epsdecay"] = (sc, 512, 1500)
+    sc = P.scenario_config5(False)
+    sc.random_start_positions = True
+    out["fl_random_starts_qrm"] = (sc, 1500, 1200)
     return out
 
 
