@@ -367,8 +367,9 @@ __device__ __forceinline__ unsigned sample_start(const KP& p, const Tab& tb, lon
 }
 
 // env.reset for one agent; T = iteration index of the new episode's first step (keys the random start positions)
+template <bool RANDOM_STARTS = true>  // false: the caller guarantees cfg.random_starts == 0 (keeps the sampler out of hot kernels)
 __device__ __forceinline__ void reset_slot(const KP& p, const Tab& tb, long long i, int a, unsigned long long T, Slot& s, double& eps) {
-  s.cell = p.random_starts ? sample_start(p, tb, i, a, T) : tb.start_cell[a];
+  s.cell = (RANDOM_STARTS && p.random_starts) ? sample_start(p, tb, i, a, T) : tb.start_cell[a];
   s.steps = 0;
   s.time = 0;
   s.rm = 0;  // the initial RM state has index 0 (reward_machine.py:32-36)
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       last_length = s.time;
       had_episode = true;
       ep_ret = 0.0;
-      reset_slot(p, tb, i, a, t + 1, s, eps);
+      reset_slot<false>(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
       load_block4(Q, s.cell, B, bmax);
     }
@@ -1506,7 +1507,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   kp.blob = h->d_blob;
   h->smem_bytes = off;
-  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && cfg->learning_rate >= 0.0 &&
+  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && !kp.random_starts && cfg->learning_rate >= 0.0 &&
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
