@@ -107,6 +107,16 @@ typedef struct rlrm_config {
   /* randomness: Philox4x32-10, key = (seed_lo, seed_hi), counter = (t_lo, t_hi, instance_offset + i, a) */
   uint32_t seed_lo, seed_hi;
   uint32_t instance_offset;    /* global id of local instance 0 (multi-GPU sharding keeps draws independent of G) */
+  /* Agents with different reward machines (frozen_lake_main.py --rm-spec-a1 / --rm-spec-a2). per_agent_rm = 1: n_rm_states
+   * and n_qrm_states are the MAXIMA over the agents (= the row strides of the tables below), every table of rlrm_tables_t
+   * that depends on the machine has one section per agent, label included:
+   *   label [A][W*H], delta / rq / rcf [A][nQmax][nEv+1], qrm_states [A][nQmax], phi [A][2][nQmax]
+   * and agent a uses its own nQ_a for the state encoding, so its table holds W*H*agent_n_rm_states[a] rows; the tables of one
+   * instance are concatenated in agent order: Q offset of (i, a) = (i * sum_b S_b + sum_{b<a} S_b) * 4. */
+  int32_t per_agent_rm;
+  int32_t agent_n_rm_states[RLRM_MAX_AGENTS];
+  int32_t agent_rm_final[RLRM_MAX_AGENTS];
+  int32_t agent_n_qrm[RLRM_MAX_AGENTS];
   int32_t random_starts;       /* env.random_start_positions (ma_frozen_lake.py:63-64, 156-172): on every reset the agents are
                                   placed on distinct free cells. Sampling (this repo's injection-consistent scheme): partial
                                   Fisher-Yates over tables.free_cells, pick k uses word (k & 3) of
@@ -251,6 +261,9 @@ int rlrm_step(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* actions, 
 /* RewardMachine.step (reward_machine.py:45-59) on explicit positions: q[N*A] in/out, cell[N*A] in, reward[N*A] out */
 int rlrm_rm_step(rlrm_handle_t* h, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
                  double* reward_out, void* stream);
+/* Same on the reward machine of agent `agent` (per_agent_rm configurations; rlrm_rm_step uses agent 0's machine). */
+int rlrm_rm_step_agent(rlrm_handle_t* h, int agent, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
+                       double* reward_out, void* stream);
 
 /* AgentRL.update_policy (agent_rl.py:117-192) -> QLearning.update (qlearning.py:41-110, incl. the QRM
  * counterfactual loop fed by rm_environment_wrapper.py:122-183) or QLearningLambda.update (qlearning_lambda.py:33-84).

@@ -57,6 +57,10 @@ class Config(C.Structure):
         ("seed_lo", C.c_uint32),
         ("seed_hi", C.c_uint32),
         ("instance_offset", C.c_uint32),
+        ("per_agent_rm", C.c_int32),
+        ("agent_n_rm_states", C.c_int32 * 8),
+        ("agent_rm_final", C.c_int32 * 8),
+        ("agent_n_qrm", C.c_int32 * 8),
         ("random_starts", C.c_int32),
         ("n_free_cells", C.c_int32),
         ("use_rsh", C.c_int32),
@@ -178,6 +182,7 @@ EXPORTED_SYMBOLS = (
     "rlrm_select_action",
     "rlrm_step",
     "rlrm_rm_step",
+    "rlrm_rm_step_agent",
     "rlrm_update",
     "rlrm_train",
     "rlrm_train_host",

@@ -37,6 +37,10 @@ struct KP {
   double lr, gamma, eps_end, eps_decay;
   float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
   int decay_on_reset, shared_q, use_rsh, random_starts, n_free;
+  // agents with different reward machines (rlrm_config_t.per_agent_rm): per-agent scalars and table strides
+  int per_agent, a_nQ[RLRM_MAX_AGENTS], a_final[RLRM_MAX_AGENTS], a_nqrm[RLRM_MAX_AGENTS];
+  long long a_prefix4[RLRM_MAX_AGENTS], sum4;  // float offset of agent a's table inside one instance, floats per instance
+  int nd;                                       // nQmax * (nEv + 1): one agent's delta / rq / rcf section
   unsigned seed_lo, seed_hi, instance_offset, n_actions;
   unsigned rk[20];  // Philox round keys: rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85
   long long S4;  // W*H*nQ*4 floats per table
@@ -378,7 +382,23 @@ __device__ __forceinline__ void reset_slot(const KP& p, const Tab& tb, long long
 }
 
 __device__ __forceinline__ size_t table_base(const KP& p, long long i, int a) {
+  if (p.per_agent) return (size_t)((p.shared_q ? 0ll : i * p.sum4) + p.a_prefix4[a]);
   return (size_t)(p.shared_q ? (long long)a : i * p.A + a) * (size_t)p.S4;
+}
+
+// Per-agent reward machines: turn the uniform parameter block / table pointers into agent a's own (nQ, final state, number
+// of counterfactual states, table sections). Called only from kernels instantiated with PA = true; `p` must be the kernel's
+// private copy of the parameter block, so with PA = false nothing here exists and the parameters stay in the constant bank.
+__device__ __forceinline__ void agent_view(const KP& p_in, KP& p, Tab& tb, int a) {
+  p.nQ = p_in.a_nQ[a];
+  p.rm_final = p_in.a_final[a];
+  p.n_qrm = p_in.a_nqrm[a];
+  p.S4 = (long long)p_in.ncell * p.nQ * 4;
+  tb.label += (size_t)a * p_in.ncell;
+  tb.delta += (size_t)a * p_in.nd;
+  tb.rq += (size_t)a * p_in.nd;
+  tb.rcf += (size_t)a * p_in.nd;
+  tb.qrm_states += (size_t)a * p_in.nQ;
 }
 __device__ __forceinline__ Acc make_acc(const KP& p, const DState& st, size_t base) {
   Acc acc = {nullptr, nullptr, nullptr};
@@ -418,14 +438,17 @@ __global__ void __launch_bounds__(256) clear_traces_kernel(KP p, DState st, cons
   reinterpret_cast<float4*>(st.e)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__global__ void __launch_bounds__(256) select_kernel(KP p, DState st, const unsigned* draws, unsigned long long t, int best,
+template <bool PA>
+__global__ void __launch_bounds__(256) select_kernel(KP p_in, DState st, const unsigned* draws, unsigned long long t, int best,
                                                     unsigned char* actions_out) {
+  KP p = p_in;
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= st.N * p.A) return;
   const long long i = k / p.A;
   const int a = (int)(k - i * p.A);
+  if (PA) p.nQ = p_in.a_nQ[a];
   const Slot s = unpack_slot(st.slot[k]);
-  const float* Q = st.q + table_base(p, i, a);
+  const float* Q = st.q + table_base(p_in, i, a);
   const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
   unsigned w[4];
   if (draws) {
@@ -453,14 +476,16 @@ __device__ __forceinline__ void store_rec(const DOut& o, long long k, const Rec&
   if (o.trunc) o.trunc[k] = r.trunc;
 }
 
-template <int ENV>
-__global__ void __launch_bounds__(256) step_kernel(KP p, DState st, const unsigned char* actions, const unsigned* draws,
+template <int ENV, bool PA>
+__global__ void __launch_bounds__(256) step_kernel(KP p_in, DState st, const unsigned char* actions, const unsigned* draws,
                                                   unsigned long long t, int with_rm, DOut out) {
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= st.N * p.A) return;
   const long long i = k / p.A;
   const int a = (int)(k - i * p.A);
+  if (PA) agent_view(p_in, p, tb, a);
   Slot s = unpack_slot(st.slot[k]);
   unsigned w3 = 0;
   if (p.stochastic) {
@@ -479,9 +504,11 @@ __global__ void __launch_bounds__(256) step_kernel(KP p, DState st, const unsign
 }
 
 // RewardMachine.step on explicit (state, position) pairs (reward_machine.py:45-59)
-__global__ void __launch_bounds__(256) rm_step_kernel(KP p, long long n, unsigned char* q, const unsigned short* cell,
+__global__ void __launch_bounds__(256) rm_step_kernel(KP p_in, int agent, long long n, unsigned char* q, const unsigned short* cell,
                                                      unsigned char* event_out, double* reward_out) {
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  if (p_in.per_agent) agent_view(p_in, p, tb, agent);  // the reward machine of agent `agent`
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const unsigned ev = tb.label[cell[k]];
@@ -497,18 +524,20 @@ __global__ void __launch_bounds__(256) rm_step_kernel(KP p, long long n, unsigne
   if (reward_out) reward_out[k] = r;
 }
 
-template <int ALGO>
-__global__ void __launch_bounds__(256) update_kernel(KP p, DState st, const unsigned short* obs_cell, const unsigned char* actions,
+template <int ALGO, bool PA>
+__global__ void __launch_bounds__(256) update_kernel(KP p_in, DState st, const unsigned short* obs_cell, const unsigned char* actions,
                                                     const unsigned char* term_arg, DOut o) {
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= st.N * p.A) return;
   const long long i = k / p.A;
   const int a = (int)(k - i * p.A);
+  if (PA) agent_view(p_in, p, tb, a);
   Rec r;
   r.prev_cell = o.prev_cell[k]; r.cell = o.cell[k]; r.prev_q = o.prev_q[k]; r.q = o.q[k]; r.event = o.event[k];
   r.env_term = o.env_term[k] != 0; r.renv = o.renv[k]; r.reward = o.reward[k];
-  const size_t base = table_base(p, i, a);
+  const size_t base = table_base(p_in, i, a);
   agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, obs_cell[k], actions[k], term_arg[k] != 0, r,
                      make_acc(p, st, base));
 }
@@ -563,10 +592,11 @@ __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, co
 // ------------------------------------------------------------------------------------------------
 #define TRAIN_BLOCK 128
 
-template <int ENV, int ALGO>
-__global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+template <int ENV, int ALGO, bool PA>
+__global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                            unsigned* trace) {
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = tid >> p.g_shift;
   const int a = (int)(tid & (p.G - 1));
@@ -589,7 +619,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p, DState st, uns
     eps = st.epsilon[k];
     if (st.ep_return) ep_ret = st.ep_return[k];
     if (st.stats) return_sum = st.stats[k].return_sum;
-    const size_t base = table_base(p, i, a);
+    if (PA) agent_view(p_in, p, tb, a);
+    const size_t base = table_base(p_in, i, a);
     Q = st.q + base;
     V = st.visits ? st.visits + base : nullptr;
     acc = make_acc(p, st, base);
@@ -1178,10 +1209,11 @@ __global__ void __launch_bounds__(256) qlambda_sparse_reset_kernel(KP p, DState 
 // ------------------------------------------------------------------------------------------------
 // greedy evaluation (test_policy_optima, evaluation_metrics.py:23-190): the driver loop with best=True and no update
 // ------------------------------------------------------------------------------------------------
-template <int ENV>
-__global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p, DState st, rlrm_eval_t* evs, unsigned long long t0, int n_iters,
+template <int ENV, bool PA>
+__global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p_in, DState st, rlrm_eval_t* evs, unsigned long long t0, int n_iters,
                                                           int n_episodes, double gamma, double optimal_steps) {
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = tid >> p.g_shift;
   const int a = (int)(tid & (p.G - 1));
@@ -1196,7 +1228,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p, DState st, rlrm
   if (valid) {
     s = unpack_slot(st.slot[k]);
     e = evs[k];
-    Q = st.q + table_base(p, i, a);
+    if (PA) agent_view(p_in, p, tb, a);
+    Q = st.q + table_base(p_in, i, a);
   }
   const unsigned w0[4] = {0, 0, 0, 0};
   for (int it = 0; it < n_iters; it++) {
@@ -1355,7 +1388,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
 // shared learner: every touched entry becomes the mean of this iteration's proposals; accumulators are cleared
 __global__ void __launch_bounds__(256) apply_shared_kernel(KP p, DState st) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= (long long)p.A * p.S4) return;
+  if (j >= (p.per_agent ? p.sum4 : (long long)p.A * p.S4)) return;
   const int c = st.acc_cnt[j];
   if (c == 0) return;
   if (c == 1) st.q[j] = st.acc_last[j];
@@ -1464,6 +1497,20 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   fill_learner(kp, cfg->learning_rate, cfg->gamma, cfg->lambd);
   kp.decay_on_reset = cfg->decay_on_reset; kp.shared_q = cfg->shared_q;
   kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
+  kp.per_agent = cfg->per_agent_rm ? 1 : 0;
+  kp.nd = kp.nQ * (kp.nEv + 1);
+  kp.sum4 = 0;
+  for (int a = 0; a < kp.A; a++) {
+    kp.a_nQ[a] = kp.per_agent ? cfg->agent_n_rm_states[a] : kp.nQ;
+    kp.a_final[a] = kp.per_agent ? cfg->agent_rm_final[a] : kp.rm_final;
+    kp.a_nqrm[a] = kp.per_agent ? cfg->agent_n_qrm[a] : kp.n_qrm;
+    kp.a_prefix4[a] = kp.sum4;
+    kp.sum4 += (long long)ncell * kp.a_nQ[a] * 4;
+    if (kp.a_nQ[a] < 1 || kp.a_nQ[a] > kp.nQ || kp.a_nqrm[a] < 0 || kp.a_nqrm[a] > kp.nQ)
+      return fail(RLRM_ERR_ARG, "per-agent reward machine sizes out of range");
+  }
+  if (kp.per_agent && (cfg->algo == RLRM_ALGO_QLAMBDA || kp.use_rsh))
+    return fail(RLRM_ERR_UNSUPPORTED, "per-agent reward machines are supported for QL / QRM without shaping");
   kp.random_starts = cfg->random_starts ? 1 : 0;
   kp.n_free = cfg->n_free_cells;
   kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;
@@ -1475,7 +1522,8 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.S4 = (long long)ncell * kp.nQ * 4;
 
   // pack the tables into one 16-byte aligned blob
-  const int nd = kp.nQ * (kp.nEv + 1);
+  const int sec = kp.per_agent ? kp.A : 1;  // machine-dependent tables have one section per agent
+  const int nd = kp.nQ * (kp.nEv + 1) * sec;
   int off = 0;
   kp.off_phi = off; off = align16(off + 2 * RLRM_MAX_RM_STATES * 8);
   kp.off_rq = off; off = align16(off + nd * 8);
@@ -1483,9 +1531,9 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.off_next = off; off = align16(off + ncell * 4 * 2);
   kp.off_start = off; off = align16(off + RLRM_MAX_AGENTS * 2);
   kp.off_flags = off; off = align16(off + ncell);
-  kp.off_label = off; off = align16(off + ncell);
+  kp.off_label = off; off = align16(off + ncell * sec);
   kp.off_delta = off; off = align16(off + nd);
-  kp.off_qrm = off; off = align16(off + RLRM_MAX_RM_STATES);
+  kp.off_qrm = off; off = align16(off + RLRM_MAX_RM_STATES * sec);
   kp.off_free = off; off = align16(off + (kp.random_starts ? kp.n_free : 0) * 2);
   kp.blob_bytes = off;
   unsigned char* host = new (std::nothrow) unsigned char[off];
@@ -1497,9 +1545,9 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   memcpy(host + kp.off_next, tb->next_cell, (size_t)ncell * 8);
   memcpy(host + kp.off_start, tb->start_cell, (size_t)kp.A * 2);
   memcpy(host + kp.off_flags, tb->cell_flags, ncell);
-  memcpy(host + kp.off_label, tb->label, ncell);
+  memcpy(host + kp.off_label, tb->label, (size_t)ncell * sec);
   memcpy(host + kp.off_delta, tb->delta, nd);
-  if (kp.n_qrm > 0 && tb->qrm_states) memcpy(host + kp.off_qrm, tb->qrm_states, kp.n_qrm);
+  if (kp.n_qrm > 0 && tb->qrm_states) memcpy(host + kp.off_qrm, tb->qrm_states, kp.per_agent ? (size_t)kp.nQ * sec : (size_t)kp.n_qrm);
   if (kp.random_starts) memcpy(host + kp.off_free, tb->free_cells, (size_t)kp.n_free * 2);
   cudaError_t e = cudaMalloc(&h->d_blob, off);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_blob, host, off, cudaMemcpyHostToDevice);
@@ -1507,7 +1555,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   kp.blob = h->d_blob;
   h->smem_bytes = off;
-  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && !kp.random_starts && cfg->learning_rate >= 0.0 &&
+  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
@@ -1516,7 +1564,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     const long long n_ent = (long long)kp.A * kp.S4;
     const long long need = (long long)off + n_ent * 20;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry
     h->shared_smem_bytes = (int)need;
-    h->shared_fast = (kp.shared_q && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
+    h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
                       !(cfg->reserved & 1));
     if (h->shared_fast) {
       cudaError_t e1 = cudaSuccess;
@@ -1630,7 +1678,8 @@ extern "C" int rlrm_select_action(rlrm_handle_t* h, const rlrm_state_t* st, cons
   if (!actions_out) return fail(RLRM_ERR_ARG, "actions_out is null");
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = st->n_instances * h->kp.A;
-  select_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out);
+  if (h->kp.per_agent) select_kernel<true><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out);
+  else select_kernel<false><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out);
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }
@@ -1643,20 +1692,31 @@ extern "C" int rlrm_step(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = st->n_instances * h->kp.A;
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE)
-    step_kernel<RLRM_ENV_FROZEN_LAKE><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), actions, draws, t, with_rm, dout(out));
-  else
-    step_kernel<RLRM_ENV_OFFICE_WORLD><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), actions, draws, t, with_rm, dout(out));
+#define RLRM_STEP(ENV, PA) step_kernel<ENV, PA><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), actions, draws, t, with_rm, dout(out))
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) {
+    if (h->kp.per_agent) RLRM_STEP(RLRM_ENV_FROZEN_LAKE, true); else RLRM_STEP(RLRM_ENV_FROZEN_LAKE, false);
+  } else {
+    if (h->kp.per_agent) RLRM_STEP(RLRM_ENV_OFFICE_WORLD, true); else RLRM_STEP(RLRM_ENV_OFFICE_WORLD, false);
+  }
+#undef RLRM_STEP
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }
 
+extern "C" int rlrm_rm_step_agent(rlrm_handle_t* h, int agent, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
+                                  double* reward_out, void* stream);
 extern "C" int rlrm_rm_step(rlrm_handle_t* h, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
                             double* reward_out, void* stream) {
+  return rlrm_rm_step_agent(h, 0, n_slots, q, cell, event_out, reward_out, stream);
+}
+
+extern "C" int rlrm_rm_step_agent(rlrm_handle_t* h, int agent, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
+                                  double* reward_out, void* stream) {
   if (!h || !q || !cell) return fail(RLRM_ERR_ARG, "null argument");
+  if (agent < 0 || agent >= h->kp.A) return fail(RLRM_ERR_ARG, "agent out of range");
   if (n_slots <= 0) return RLRM_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  rm_step_kernel<<<blocks_for(n_slots, 256), 256, h->smem_bytes, (cudaStream_t)stream>>>(h->kp, n_slots, q, cell, event_out, reward_out);
+  rm_step_kernel<<<blocks_for(n_slots, 256), 256, h->smem_bytes, (cudaStream_t)stream>>>(h->kp, agent, n_slots, q, cell, event_out, reward_out);
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }
@@ -1675,13 +1735,16 @@ extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint1
     return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update on Q(lambda) needs dense traces (state.e); sparse traces are for rlrm_train");
   if (h->kp.algo == RLRM_ALGO_QLAMBDA)
     update_qlambda_kernel<<<(unsigned)n, 256, 0, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
-  else if (h->kp.algo == RLRM_ALGO_QRM)
-    update_kernel<RLRM_ALGO_QRM><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
-  else
-    update_kernel<RLRM_ALGO_QL><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
+#define RLRM_UPD(ALGO, PA) update_kernel<ALGO, PA><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out))
+  else if (h->kp.algo == RLRM_ALGO_QRM) {
+    if (h->kp.per_agent) RLRM_UPD(RLRM_ALGO_QRM, true); else RLRM_UPD(RLRM_ALGO_QRM, false);
+  } else {
+    if (h->kp.per_agent) RLRM_UPD(RLRM_ALGO_QL, true); else RLRM_UPD(RLRM_ALGO_QL, false);
+  }
+#undef RLRM_UPD
   LAUNCH_CHECK(h);
   if (h->kp.shared_q) {
-    apply_shared_kernel<<<blocks_for((long long)h->kp.A * h->kp.S4, 256), 256, 0, s>>>(h->kp, dstate(st));
+    apply_shared_kernel<<<blocks_for(h->kp.per_agent ? h->kp.sum4 : (long long)h->kp.A * h->kp.S4, 256), 256, 0, s>>>(h->kp, dstate(st));
     LAUNCH_CHECK(h);
   }
   return RLRM_OK;
@@ -1697,6 +1760,7 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
   } else {
     const long long threads = st->n_instances * kp.G;
     const unsigned grid = blocks_for(threads, TRAIN_BLOCK);
+#define RLRM_TRAIN(ALGO, PA) train_kernel<ENV, ALGO, PA><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace)
     if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits) {
       const DState d = dstate(st);
 #define RLRM_QRM4(ST, LE, TR) train_qrm4_kernel<ENV, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace)
@@ -1713,10 +1777,12 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
       }
 #undef RLRM_QRM4
     }
-    else if (kp.algo == RLRM_ALGO_QRM)
-      train_kernel<ENV, RLRM_ALGO_QRM><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
-    else
-      train_kernel<ENV, RLRM_ALGO_QL><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    else if (kp.algo == RLRM_ALGO_QRM) {
+      if (kp.per_agent) RLRM_TRAIN(RLRM_ALGO_QRM, true); else RLRM_TRAIN(RLRM_ALGO_QRM, false);
+    } else {
+      if (kp.per_agent) RLRM_TRAIN(RLRM_ALGO_QL, true); else RLRM_TRAIN(RLRM_ALGO_QL, false);
+    }
+#undef RLRM_TRAIN
   }
 }
 
@@ -1749,7 +1815,7 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
       else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t0 + it, 1, learn, tr, s);
       LAUNCH_CHECK(h);
       if (learn) {
-        apply_shared_kernel<<<blocks_for((long long)h->kp.A * h->kp.S4, 256), 256, 0, s>>>(h->kp, dstate(st));
+        apply_shared_kernel<<<blocks_for(h->kp.per_agent ? h->kp.sum4 : (long long)h->kp.A * h->kp.S4, 256), 256, 0, s>>>(h->kp, dstate(st));
         LAUNCH_CHECK(h);
       }
     }
@@ -1770,10 +1836,13 @@ extern "C" int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = blocks_for(st->n_instances * h->kp.G, TRAIN_BLOCK);
   cudaStream_t s = (cudaStream_t)stream;
-  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE)
-    eval_kernel<RLRM_ENV_FROZEN_LAKE><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps);
-  else
-    eval_kernel<RLRM_ENV_OFFICE_WORLD><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps);
+#define RLRM_EVAL(ENV, PA) eval_kernel<ENV, PA><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps)
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) {
+    if (h->kp.per_agent) RLRM_EVAL(RLRM_ENV_FROZEN_LAKE, true); else RLRM_EVAL(RLRM_ENV_FROZEN_LAKE, false);
+  } else {
+    if (h->kp.per_agent) RLRM_EVAL(RLRM_ENV_OFFICE_WORLD, true); else RLRM_EVAL(RLRM_ENV_OFFICE_WORLD, false);
+  }
+#undef RLRM_EVAL
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }

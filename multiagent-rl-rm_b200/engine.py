@@ -51,12 +51,16 @@ class Engine:
         self.h = h
         n_slots = self.N * self.A
         n_tab = self.A if self.cfg.shared_q else n_slots
+        tab_shape = (n_tab, self.S, 4)
+        if self.cfg.per_agent_rm:  # the tables of one instance are concatenated in agent order, S_a = W*H*nQ_a rows each
+            self.agent_rows = list(compiled.agent_rows)
+            tab_shape = (1 if self.cfg.shared_q else self.N, sum(self.agent_rows), 4)
         d = self.device
         self.slot = torch.zeros(n_slots, dtype=torch.int64, device=d)
         self.epsilon = torch.full((n_slots,), float(self.cfg.epsilon_start), dtype=torch.float64, device=d)
-        self.q = torch.full((n_tab, self.S, 4), float(compiled.scenario.q_init), dtype=torch.float32, device=d)
+        self.q = torch.full(tab_shape, float(compiled.scenario.q_init), dtype=torch.float32, device=d)
         self.sparse = bool(qlambda_sparse) and self.cfg.algo == abi.ALGO_QLAMBDA
-        self.e = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
+        self.e = torch.zeros(tab_shape, dtype=torch.float32, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
         self.tr_cap = 0
         self.tr_pos = self.tr_idx = self.tr_e = self.tr_q = self.tr_len = self.tr_work = None
         if self.sparse:
@@ -70,13 +74,13 @@ class Engine:
             self.tr_len = torch.zeros(n_slots, dtype=torch.int32, device=d)
             self.tr_work = torch.zeros(n_slots, dtype=torch.int64, device=d)
         need_visits = track_visits or self.cfg.learning_rate < 0
-        self.visits = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if need_visits else None
+        self.visits = torch.zeros(tab_shape, dtype=torch.int32, device=d) if need_visits else None
         self.ep_return = torch.zeros(n_slots, dtype=torch.float64, device=d)
         self.stats = torch.zeros((n_slots, 32), dtype=torch.uint8, device=d) if with_stats else None
         shared = bool(self.cfg.shared_q)
-        self.acc_sum = torch.zeros((n_tab, self.S, 4), dtype=torch.int64, device=d) if shared else None
-        self.acc_cnt = torch.zeros((n_tab, self.S, 4), dtype=torch.int32, device=d) if shared else None
-        self.acc_last = torch.zeros((n_tab, self.S, 4), dtype=torch.float32, device=d) if shared else None
+        self.acc_sum = torch.zeros(tab_shape, dtype=torch.int64, device=d) if shared else None
+        self.acc_cnt = torch.zeros(tab_shape, dtype=torch.int32, device=d) if shared else None
+        self.acc_last = torch.zeros(tab_shape, dtype=torch.float32, device=d) if shared else None
         self.state = abi.State(self.N, _ptr(self.slot), _ptr(self.epsilon), _ptr(self.q), _ptr(self.e), _ptr(self.visits),
                                _ptr(self.ep_return), _ptr(self.stats), _ptr(self.acc_sum), _ptr(self.acc_cnt), _ptr(self.acc_last),
                                _ptr(self.tr_pos), _ptr(self.tr_idx), _ptr(self.tr_e), _ptr(self.tr_q), _ptr(self.tr_len),
@@ -130,13 +134,23 @@ class Engine:
                                int(with_rm), C.byref(so), self._stream()))
         return rec
 
-    def rm_step(self, q: torch.Tensor, cell: torch.Tensor):
+    def rm_step(self, q: torch.Tensor, cell: torch.Tensor, agent: int = 0):
+        """RewardMachine.step on explicit (state index, cell) pairs, on agent `agent`'s machine."""
         q = q.to(device=self.device, dtype=torch.uint8).contiguous().clone()
         cell = cell.to(device=self.device, dtype=torch.int16).contiguous()
         ev = torch.empty_like(q)
         r = torch.empty(q.numel(), dtype=torch.float64, device=self.device)
-        check(self.L.rlrm_rm_step(self.h, q.numel(), _ptr(q), _ptr(cell), _ptr(ev), _ptr(r), self._stream()))
+        check(self.L.rlrm_rm_step_agent(self.h, int(agent), q.numel(), _ptr(q), _ptr(cell), _ptr(ev), _ptr(r), self._stream()))
         return q, ev, r
+
+    def agent_table(self, a: int) -> torch.Tensor:
+        """learner.q_table of agent a for every instance: [N, S_a, 4] (shared learner: [S_a, 4])."""
+        self.sync_tables()
+        if self.cfg.per_agent_rm:
+            lo = sum(self.agent_rows[:a])
+            t = self.q[:, lo:lo + self.agent_rows[a], :]
+            return t[0] if self.cfg.shared_q else t
+        return self.q.view(self.A, self.S, 4)[a] if self.cfg.shared_q else self.q.view(self.N, self.A, self.S, 4)[:, a]
 
     def update(self, obs_cell: torch.Tensor, actions: torch.Tensor, term_arg: torch.Tensor, rec: Dict[str, torch.Tensor]):
         obs_cell = obs_cell.to(device=self.device, dtype=torch.int16).contiguous()

@@ -62,11 +62,11 @@ class BaseEnvironment:
         rms = [r for r in rms if r is not None]
         if not rms:
             return None
+        if len(rms) != len(self.agents):
+            raise NotImplementedError("either every agent has a reward machine or none has")
         first = list(rms[0].transitions.items())
-        for r in rms[1:]:
-            if list(r.transitions.items()) != first:
-                raise NotImplementedError("agents with different reward machines in one environment are not supported by the "
-                                          "batched tables (one RM table set per environment)")
+        if any(list(r.transitions.items()) != first or r.initial_state != rms[0].initial_state for r in rms[1:]):
+            return rms  # different machines (frozen_lake_main.py --rm-spec-a1/--rm-spec-a2): per-agent table sections
         return rms[0]
 
     def _get_engine(self, reward_modifier=1):
@@ -76,7 +76,8 @@ class BaseEnvironment:
         grid = self._grid()
         fields = self._scenario_fields()
         starts = [tuple(getattr(a, "initial_position", None) or a.position) for a in self.agents]
-        rm_key = None if rm is None else (tuple(rm.transitions.items()), tuple(sorted(rm.detector_positions())))
+        rm_list = rm if isinstance(rm, list) else ([] if rm is None else [rm])
+        rm_key = tuple((tuple(m.transitions.items()), tuple(sorted(m.detector_positions())), m.initial_state) for m in rm_list) or None
         key = (tuple(sorted(fields.items())), tuple(starts), rm_key, reward_modifier,
                grid.width, grid.height, tuple(grid.hazards), tuple(grid.walls))
         if self._engine is None or key != self._engine_key:

@@ -36,6 +36,8 @@ class Scenario:
     # reward machine as an ordered transition list [(src, event_pos | None, dst, reward)] (dict order matters)
     rm_transitions: List[Tuple[str, Optional[Tuple[int, int]], str, float]] = field(default_factory=list)
     detector_positions: Optional[List[Tuple[int, int]]] = None  # default: the positions used by transitions
+    # agents with different reward machines (frozen_lake_main.py --rm-spec-a1/--rm-spec-a2): one transition list per agent
+    rm_transitions_per_agent: Optional[List[List[Tuple[str, Optional[Tuple[int, int]], str, float]]]] = None
     reward_modifier: float = 1
     # dynamics
     stochastic: bool = False
@@ -75,6 +77,9 @@ class Scenario:
         d["rm_transitions"] = [[s, None if e is None else list(e), t, r] for (s, e, t, r) in self.rm_transitions]
         if self.detector_positions is not None:
             d["detector_positions"] = [list(p) for p in self.detector_positions]
+        if self.rm_transitions_per_agent is not None:
+            d["rm_transitions_per_agent"] = [[[s, None if e is None else list(e), t, r] for (s, e, t, r) in tr]
+                                             for tr in self.rm_transitions_per_agent]
         return d
 
     @staticmethod
@@ -84,18 +89,22 @@ class Scenario:
         d["rm_transitions"] = [(s, None if e is None else tuple(e), t, r) for (s, e, t, r) in d["rm_transitions"]]
         if d.get("detector_positions") is not None:
             d["detector_positions"] = [tuple(p) for p in d["detector_positions"]]
+        if d.get("rm_transitions_per_agent") is not None:
+            d["rm_transitions_per_agent"] = [[(s, None if e is None else tuple(e), t, r) for (s, e, t, r) in tr]
+                                             for tr in d["rm_transitions_per_agent"]]
         return Scenario(**d)
 
     # -- helpers ---------------------------------------------------------------------------------
     def grid(self) -> GridSpec:
         return frozen_lake_grid(self.map_name) if self.env == "frozen_lake" else office_world_grid(self.map_name)
 
-    def reward_machine(self) -> RewardMachine:
-        transitions = {(s, e): (t, r) for (s, e, t, r) in self.rm_transitions}
+    def reward_machine(self, agent: Optional[int] = None) -> RewardMachine:
+        trs = self.rm_transitions if (agent is None or self.rm_transitions_per_agent is None) else self.rm_transitions_per_agent[agent]
+        transitions = {(s, e): (t, r) for (s, e, t, r) in trs}
         if self.detector_positions is not None:
             positions = set(self.detector_positions)
         else:
-            positions = {e for (_s, e, _t, _r) in self.rm_transitions if e is not None}
+            positions = {e for (_s, e, _t, _r) in trs if e is not None}
         return RewardMachine(transitions, PositionEventDetector(positions))
 
 
@@ -193,7 +202,17 @@ class Compiled:
 
     @property
     def state_space(self):
+        """S = W*H*nQ of the (uniform) per-agent table; with per-agent reward machines use `agent_rows`."""
         return self.config.width * self.config.height * self.config.n_rm_states
+
+    @property
+    def agent_rows(self):
+        """[S_a] rows of each agent's table (S_a = W*H*nQ_a)."""
+        c = self.config
+        cells = c.width * c.height
+        if c.per_agent_rm:
+            return [cells * c.agent_n_rm_states[a] for a in range(c.n_agents)]
+        return [cells * c.n_rm_states] * c.n_agents
 
     def tables_struct(self) -> abi.Tables:
         t = abi.Tables()
@@ -217,12 +236,21 @@ _DRIVER = {"frozen_lake_main": abi.DRIVER_FROZEN_LAKE_MAIN, "office_main": abi.D
 def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional[RewardMachine] = None,
                      instance_offset: int = 0) -> Compiled:
     grid = grid or sc.grid()
-    rm = rm or sc.reward_machine()
     W, H = grid.width, grid.height
     if W * H > abi.MAX_CELLS:
         raise ValueError(f"grid {W}x{H} exceeds {abi.MAX_CELLS} cells")
     if not (1 <= len(sc.starts) <= abi.MAX_AGENTS):
         raise ValueError("1..8 agents per instance")
+    per_agent = rm is None and sc.rm_transitions_per_agent is not None
+    rms = None
+    if isinstance(rm, (list, tuple)):  # explicit list of per-agent RewardMachine objects
+        rms, rm, per_agent = list(rm), rm[0], True
+    elif per_agent:
+        rms = [sc.reward_machine(a) for a in range(len(sc.starts))]
+        rm = rms[0]
+    if per_agent and len(rms) != len(sc.starts):
+        raise ValueError("one reward machine per agent is required")
+    rm = rm or sc.reward_machine()
     t = rm.compile_tables(W, H, sc.reward_modifier)
 
     cfg = abi.Config()
@@ -277,6 +305,32 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
             phi[0, idx] = rm.potentials.get(state, 0)
             phi[1, idx] = rm.potentials.get(idx, 0)
     cfg.use_rsh = int(bool(sc.use_rsh) and sc.algo in ("ql", "qrm"))
+    if per_agent:
+        # one table section per agent, rows padded to the largest machine; every agent keeps its own event ids
+        parts = [m.compile_tables(W, H, sc.reward_modifier) for m in rms]
+        if len({tuple(p["events"]) for p in parts}) != 1:
+            # different detectors: give every agent the union as event vocabulary (an event outside its own detector set is
+            # simply labelled EVENT_NONE in that agent's label section)
+            union = sorted({e for p in parts for e in p["events"]})
+            for m in rms:
+                m._event_vocabulary = union
+            parts = [_compile_with_vocabulary(m, W, H, sc.reward_modifier, union) for m in rms]
+        n_ev, nq_max = parts[0]["n_events"], max(p["n_states"] for p in parts)
+        A = len(rms)
+        label = np.stack([p["label"] for p in parts])
+        delta = np.full((A, nq_max, n_ev + 1), abi.NO_TRANSITION, dtype=np.uint8)
+        rqa, rcfa = np.zeros((A, nq_max, n_ev + 1)), np.zeros((A, nq_max, n_ev + 1))
+        qrm = np.zeros((A, nq_max), dtype=np.uint8)
+        for a, p in enumerate(parts):
+            n = p["n_states"]
+            delta[a, :n], rqa[a, :n], rcfa[a, :n] = p["delta"], p["rq"], p["rcf"]
+            qrm[a, : len(p["qrm_states"])] = p["qrm_states"]
+            cfg.agent_n_rm_states[a], cfg.agent_rm_final[a], cfg.agent_n_qrm[a] = n, p["final"], len(p["qrm_states"])
+        cfg.per_agent_rm, cfg.n_rm_states, cfg.n_events = 1, nq_max, n_ev
+        cfg.n_qrm_states, cfg.rm_final = max(len(p["qrm_states"]) for p in parts), parts[0]["final"]
+        t = dict(t, label=label, delta=delta, rq=rqa, rcf=rcfa, qrm_states=qrm, events=parts[0]["events"])
+        if phi is not None:
+            raise NotImplementedError("reward shaping with per-agent reward machines")
     start_cell = np.array([y * W + x for (x, y) in sc.starts], dtype=np.uint16)
     free_cells = None
     if sc.random_start_positions:
@@ -294,6 +348,25 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
         label=t["label"], delta=t["delta"], rq=t["rq"], rcf=t["rcf"], qrm_states=t["qrm_states"],
         start_cell=start_cell, events=t["events"], config=cfg, phi=phi, free_cells=free_cells,
     )
+
+
+def _compile_with_vocabulary(rm, width, height, reward_modifier, vocabulary):
+    """compile_tables with a fixed event vocabulary (ids = positions in `vocabulary`); positions outside the machine's own
+    detector set stay EVENT_NONE in its label."""
+    own = set(rm.detector_positions())
+    t = rm.compile_tables(width, height, reward_modifier)
+    remap = {k: vocabulary.index(p) for k, p in enumerate(t["events"])}
+    n_ev = len(vocabulary)
+    label = np.full(width * height, abi.EVENT_NONE, dtype=np.uint8)
+    for k, (x, y) in enumerate(vocabulary):
+        if (x, y) in own:
+            label[y * width + x] = k
+    n = t["n_states"]
+    delta = np.full((n, n_ev + 1), abi.NO_TRANSITION, dtype=np.uint8)
+    rq, rcf = np.zeros((n, n_ev + 1)), np.zeros((n, n_ev + 1))
+    for old, new in list(remap.items()) + [(t["n_events"], n_ev)]:
+        delta[:, new], rq[:, new], rcf[:, new] = t["delta"][:, old], t["rq"][:, old], t["rcf"][:, old]
+    return dict(t, label=label, delta=delta, rq=rq, rcf=rcf, n_events=n_ev, events=list(vocabulary))
 
 
 # --------------------------------------------------------------------------------------------------

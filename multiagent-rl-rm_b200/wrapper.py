@@ -61,7 +61,7 @@ class RMEnvironmentWrapper:
         W = self.env.grid_width
         cell = next_state["pos_y"] * W + next_state["pos_x"]
         q_in = torch.tensor([rm.get_state_index(s) for s in states], dtype=torch.uint8)
-        q_out, _ev, r = eng.rm_step(q_in, torch.full((len(states),), cell, dtype=torch.int16))
+        q_out, _ev, r = eng.rm_step(q_in, torch.full((len(states),), cell, dtype=torch.int16), agent=self.agents.index(agent))
         q_out, r = q_out.cpu().numpy(), r.cpu().numpy()
         final = rm.get_final_state()
         a_idx = agent.actions_idx(action)

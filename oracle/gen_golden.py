@@ -64,6 +64,17 @@ def scenarios():
     sc.random_start_positions, sc.seed, sc.starts = True, 52, sc.starts + [(9, 9), (7, 3), (9, 0), (0, 9)]
     S["fl_random_starts_6agents_ql"] = (sc, 2, 500, "f32", 1)
 
+    gl = P.frozen_lake_grid("map1").goals
+    other = [("p0", gl["C"], "p1", 3.0), ("p1", gl["A"], "p2", 7.0)]
+    third = [("w0", gl["B"], "w1", 1.0), ("w1", gl["A"], "w2", 1.0), ("w2", gl["C"], "w3", 1.0), ("w3", gl["B"], "w4", 5.0), ("w1", gl["C"], "w0", -1.0)]
+    for algo, lr, seed in (("qrm", 1.0, 61), ("ql", 0.3, 62)):
+        sc = P.scenario_config3(algo == "qrm")
+        sc.algo, sc.learning_rate, sc.seed = algo, lr, seed
+        sc.starts = [(5, 0), (0, 0), (9, 9)]
+        sc.detector_positions = sorted(gl.values())
+        sc.rm_transitions_per_agent = [frozen_lake_abc_transitions(), other, third]
+        S[f"fl_per_agent_rms_{algo}"] = (sc, 2, 700, "f32", 1)
+
     S["cfg5_fl_4agents_qrm"] = (P.scenario_config5(False), 2, 500, "f32", 1)
 
     S["cfg2_office_det_ql"] = (P.scenario_config2(False), 2, 1500, "f32", 1)

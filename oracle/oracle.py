@@ -69,18 +69,21 @@ class Oracle:
         self.L = lib(real)
         dt = np.float32 if real == "f32" else np.float64
         n_tab = self.A if self.cfg.shared_q else self.N * self.A
+        tab_shape = (n_tab, self.S, 4)
+        if self.cfg.per_agent_rm:  # tables of one instance concatenated in agent order, S_a rows each
+            tab_shape = (1 if self.cfg.shared_q else self.N, sum(compiled.agent_rows), 4)
         self.slot = np.zeros(self.N * self.A, dtype=np.uint64)
         self.epsilon = np.full(self.N * self.A, self.cfg.epsilon_start, dtype=np.float64)
-        self.q = np.full((n_tab, self.S, 4), compiled.scenario.q_init, dtype=dt)
-        self.e = np.zeros((n_tab, self.S, 4), dtype=dt) if self.cfg.algo == abi.ALGO_QLAMBDA else None
+        self.q = np.full(tab_shape, compiled.scenario.q_init, dtype=dt)
+        self.e = np.zeros(tab_shape, dtype=dt) if self.cfg.algo == abi.ALGO_QLAMBDA else None
         need_visits = track_visits or self.cfg.learning_rate < 0
-        self.visits = np.zeros((n_tab, self.S, 4), dtype=np.uint32) if need_visits else None
+        self.visits = np.zeros(tab_shape, dtype=np.uint32) if need_visits else None
         self.ep_return = np.zeros(self.N * self.A, dtype=np.float64)
         self.stats = np.zeros(self.N * self.A, dtype=STATS_DTYPE)
         shared = bool(self.cfg.shared_q)
-        self.acc_sum = np.zeros((n_tab, self.S, 4), dtype=np.int64) if shared else None
-        self.acc_cnt = np.zeros((n_tab, self.S, 4), dtype=np.int32) if shared else None
-        self.acc_last = np.zeros((n_tab, self.S, 4), dtype=np.float32) if shared else None
+        self.acc_sum = np.zeros(tab_shape, dtype=np.int64) if shared else None
+        self.acc_cnt = np.zeros(tab_shape, dtype=np.int32) if shared else None
+        self.acc_last = np.zeros(tab_shape, dtype=np.float32) if shared else None
         self.state = abi.State(self.N, _p(self.slot), _p(self.epsilon), _p(self.q), _p(self.e), _p(self.visits),
                                _p(self.ep_return), _p(self.stats), _p(self.acc_sum), _p(self.acc_cnt), _p(self.acc_last))
 

@@ -160,16 +160,20 @@ def build_reference(sc: dict, table_dtype=np.float32):
     env.max_steps_unused = sc["max_steps"]
     assert sc["max_steps"] == 1000, "the reference hard-codes the 1000-step cap"
 
-    transitions = {}
-    for (s, e, t, r) in sc["rm_transitions"]:
-        transitions[(s, None if e is None else tuple(e))] = (t, r)
-    if sc.get("detector_positions") is not None:
-        positions = {tuple(p) for p in sc["detector_positions"]}
-    else:
-        positions = {ev for (_s, ev) in transitions if ev is not None}
+    def machine(k):
+        trs = sc["rm_transitions"] if not sc.get("rm_transitions_per_agent") else sc["rm_transitions_per_agent"][k]
+        tmap = {}
+        for (s, e, t, r) in trs:
+            tmap[(s, None if e is None else tuple(e))] = (t, r)
+        if sc.get("detector_positions") is not None:
+            pos = {tuple(p) for p in sc["detector_positions"]}
+        else:
+            pos = {ev for (_s, ev) in tmap if ev is not None}
+        return tmap, pos
 
     agents = []
     for k, (x, y) in enumerate(sc["starts"]):
+        transitions, positions = machine(k)
         ag = AgentRL(f"a{k + 1}", env)
         ag.set_initial_position(x, y)
         ag.add_state_encoder(SEnc(ag))
@@ -312,9 +316,10 @@ def run_reference(sc: dict, n_instances: int, n_iters: int, table_dtype=np.float
                 if over:
                     out["episode_end"][t - 1, i] = 1
                     break
-        q_final.append(np.stack([_np(ag.get_learning_algorithm().q_table) for ag in agents]))
+        join = np.concatenate if sc.get("rm_transitions_per_agent") else np.stack  # per-agent machines: tables of S_a rows
+        q_final.append(join([_np(ag.get_learning_algorithm().q_table) for ag in agents]))
         if sc["algo"] == "qlambda":
-            e_final.append(np.stack([_np(ag.get_learning_algorithm().e_table) for ag in agents]))
+            e_final.append(join([_np(ag.get_learning_algorithm().e_table) for ag in agents]))
     out["q_final"] = np.stack(q_final)
     if e_final:
         out["e_final"] = np.stack(e_final)

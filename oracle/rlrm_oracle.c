@@ -73,7 +73,38 @@ static void get_draws(const rlrm_config_t* cfg, const uint32_t* draws, uint64_t 
   }
 }
 
+/* ---- per-agent reward machines (rlrm_config_t.per_agent_rm): agent a's scalars and table sections ---------- */
+typedef struct {
+  int nQ, final, n_qrm;
+  const uint8_t *label, *delta, *qrm_states;
+  const double *rq, *rcf, *phi;
+} arm_t;
+
+static arm_t agent_rm(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int a) {
+  arm_t v;
+  int nd = cfg->n_rm_states * (cfg->n_events + 1), nc = cfg->width * cfg->height;
+  if (cfg->per_agent_rm) {
+    v.nQ = cfg->agent_n_rm_states[a]; v.final = cfg->agent_rm_final[a]; v.n_qrm = cfg->agent_n_qrm[a];
+    v.label = tb->label + (size_t)a * nc; v.delta = tb->delta + (size_t)a * nd; v.rq = tb->rq + (size_t)a * nd;
+    v.rcf = tb->rcf + (size_t)a * nd; v.qrm_states = tb->qrm_states ? tb->qrm_states + (size_t)a * cfg->n_rm_states : NULL;
+    v.phi = tb->phi ? tb->phi + (size_t)a * 2 * cfg->n_rm_states : NULL;
+  } else {
+    v.nQ = cfg->n_rm_states; v.final = cfg->rm_final; v.n_qrm = cfg->n_qrm_states;
+    v.label = tb->label; v.delta = tb->delta; v.rq = tb->rq; v.rcf = tb->rcf; v.qrm_states = tb->qrm_states; v.phi = tb->phi;
+  }
+  return v;
+}
+
+static size_t table_rows(const rlrm_config_t* cfg, int a) { /* S_a = W*H*nQ_a */
+  return (size_t)cfg->width * cfg->height * (cfg->per_agent_rm ? cfg->agent_n_rm_states[a] : cfg->n_rm_states);
+}
+
 static size_t table_base(const rlrm_config_t* cfg, int64_t i, int a) {
+  if (cfg->per_agent_rm) {
+    size_t sum = 0, pre = 0;
+    for (int b = 0; b < cfg->n_agents; b++) { if (b < a) pre += table_rows(cfg, b); sum += table_rows(cfg, b); }
+    return (cfg->shared_q ? pre : (size_t)i * sum + pre) * 4;
+  }
   size_t S = (size_t)cfg->width * cfg->height * cfg->n_rm_states;
   return (cfg->shared_q ? (size_t)a : (size_t)i * cfg->n_agents + a) * S * 4;
 }
@@ -100,7 +131,6 @@ static void sample_starts(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int
 }
 
 static void reset_instance_at(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i, uint64_t T) {
-  size_t S4 = (size_t)cfg->width * cfg->height * cfg->n_rm_states * 4;
   uint32_t starts[RLRM_MAX_AGENTS];
   if (cfg->random_starts) sample_starts(cfg, tb, i, T, starts);
   for (int a = 0; a < cfg->n_agents; a++) {
@@ -109,17 +139,13 @@ static void reset_instance_at(const rlrm_config_t* cfg, const rlrm_tables_t* tb,
                 RLRM_FLAG_ACTIVE | RLRM_FLAG_FIRST};
     st->slot[k] = pack(s);
     if (cfg->algo == RLRM_ALGO_QLAMBDA && st->e && !cfg->shared_q) /* reset_e_table: ma_frozen_lake.py:80-81 */
-      memset((real*)st->e + table_base(cfg, i, a), 0, S4 * sizeof(real));
+      memset((real*)st->e + table_base(cfg, i, a), 0, table_rows(cfg, a) * 4 * sizeof(real));
     if (cfg->decay_on_reset) { /* learn_done_episode: qlearning.py:153-155 */
       double e = st->epsilon[k] * cfg->epsilon_decay;
       st->epsilon[k] = cfg->epsilon_end > e ? cfg->epsilon_end : e;
     }
     if (st->ep_return) st->ep_return[k] = 0.0;
   }
-}
-
-static void reset_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i) {
-  reset_instance_at(cfg, tb, st, i, 0);
 }
 
 int oracle_reset_at(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, const uint8_t* mask, uint64_t t) {
@@ -146,12 +172,11 @@ static int select_one(const rlrm_config_t* cfg, const real* row, double eps, con
 
 int oracle_select_action(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, const uint32_t* draws,
                          uint64_t t, int best, uint8_t* actions_out) {
-  (void)tb;
   for (int64_t i = 0; i < st->n_instances; i++)
     for (int a = 0; a < cfg->n_agents; a++) {
       size_t k = (size_t)i * cfg->n_agents + a;
       slot_t s = unpack(st->slot[k]);
-      const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * cfg->n_rm_states + s.rm) * 4;
+      const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * agent_rm(cfg, tb, a).nQ + s.rm) * 4;
       uint32_t w[4];
       get_draws(cfg, draws, t, i, a, w);
       actions_out[k] = (uint8_t)select_one(cfg, row, st->epsilon[k], w, best);
@@ -188,7 +213,8 @@ static void step_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, con
     int active = (s[a].flags & RLRM_FLAG_ACTIVE) != 0;
     uint32_t w[4];
     if (cfg->env_kind == RLRM_ENV_FROZEN_LAKE) {
-      int rm_done = cfg->rm_final >= 0 && (int)s[a].rm == cfg->rm_final; /* ma_frozen_lake.py:107-115 */
+      int fin = agent_rm(cfg, tb, a).final;
+      int rm_done = fin >= 0 && (int)s[a].rm == fin; /* ma_frozen_lake.py:107-115 */
       if (active && !rm_done) {
         int act = act_i[a], ex = act;
         if (cfg->stochastic) { get_draws(cfg, draws, t, i, a, w); ex = slip(cfg, act, w[3]); }
@@ -225,7 +251,8 @@ static void step_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, con
     int fail = (s[a].flags & RLRM_FLAG_FAIL) != 0;
     if (cfg->env_kind == RLRM_ENV_FROZEN_LAKE) {
       r->trunc = ((int)s[a].steps > cfg->max_steps) || ((int)time > cfg->max_steps);
-      r->env_term = r->trunc || (cfg->rm_final >= 0 && (int)s[a].rm == cfg->rm_final) || fail;
+      int fin = agent_rm(cfg, tb, a).final;
+      r->env_term = r->trunc || (fin >= 0 && (int)s[a].rm == fin) || fail;
       if (r->env_term) s[a].flags &= ~RLRM_FLAG_ACTIVE;
     } else {
       r->trunc = (int)time > cfg->max_steps;
@@ -237,14 +264,15 @@ static void step_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, con
   for (int a = 0; a < A; a++) { /* rm_environment_wrapper.py:57-107 */
     rec_t* r = &rec[a];
     r->prev_q = s[a].rm;
-    r->event = tb->label[s[a].cell];
+    arm_t v = agent_rm(cfg, tb, a);
+    r->event = v.label[s[a].cell];
     r->q = s[a].rm;
     if (with_rm) {
       int col = r->event == RLRM_EVENT_NONE ? nEv : (int)r->event;
-      uint8_t d = tb->delta[s[a].rm * (nEv + 1) + col]; /* reward_machine.py:45-59 */
-      if (d != RLRM_NO_TRANSITION) { r->rq = tb->rq[s[a].rm * (nEv + 1) + col]; s[a].rm = d; }
+      uint8_t d = v.delta[s[a].rm * (nEv + 1) + col]; /* reward_machine.py:45-59 */
+      if (d != RLRM_NO_TRANSITION) { r->rq = v.rq[s[a].rm * (nEv + 1) + col]; s[a].rm = d; }
       r->q = s[a].rm;
-      r->rm_term = cfg->rm_final >= 0 && (int)s[a].rm == cfg->rm_final;
+      r->rm_term = v.final >= 0 && (int)s[a].rm == v.final;
     }
     r->reward = r->renv + r->rq;
     r->term = r->env_term || r->rm_term;
@@ -353,7 +381,8 @@ static void update_qlambda(const rlrm_config_t* cfg, real* Q, real* E, uint32_t*
 
 static void update_slot(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_state_t* st, int64_t i, int a,
                         uint32_t obs_cell, int action, int term_arg, const rec_t* r) {
-  int nQ = cfg->n_rm_states, nEv = cfg->n_events;
+  arm_t v = agent_rm(cfg, tb, a);
+  int nQ = v.nQ, nEv = cfg->n_events, pstride = cfg->n_rm_states; /* phi rows are nQmax apart */
   size_t S = (size_t)cfg->width * cfg->height * nQ;
   size_t base = table_base(cfg, i, a);
   real* Q = (real*)st->q + base;
@@ -366,21 +395,21 @@ static void update_slot(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const
   }
   if (cfg->algo == RLRM_ALGO_QRM) { /* rm_environment_wrapper.py:122-183 -> qlearning.py:82-106 */
     int col = r->event == RLRM_EVENT_NONE ? nEv : (int)r->event;
-    for (int j = 0; j < cfg->n_qrm_states; j++) {
-      int u = tb->qrm_states[j];
-      uint8_t d = tb->delta[u * (nEv + 1) + col];
+    for (int j = 0; j < v.n_qrm; j++) {
+      int u = v.qrm_states[j];
+      uint8_t d = v.delta[u * (nEv + 1) + col];
       int un = d == RLRM_NO_TRANSITION ? u : d;
-      double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb->rcf[u * (nEv + 1) + col];
-      int done = r->env_term || (cfg->rm_final >= 0 && un == cfg->rm_final);
+      double ru = d == RLRM_NO_TRANSITION ? 0.0 : v.rcf[u * (nEv + 1) + col];
+      int done = r->env_term || (v.final >= 0 && un == v.final);
       double rew = r->renv + ru;
-      if (cfg->use_rsh && tb->phi) rew += cfg->gamma * tb->phi[un] - tb->phi[u]; /* qlearning.py:93-105 */
+      if (cfg->use_rsh && v.phi) rew += cfg->gamma * v.phi[un] - v.phi[u]; /* qlearning.py:93-105 */
       update_q(cfg, Q, V, (size_t)r->prev_cell * nQ + u, action, rew, (size_t)r->cell * nQ + un, done, accp);
     }
   } else {
     size_t s = (size_t)obs_cell * nQ + r->prev_q, sn = (size_t)r->cell * nQ + r->q; /* agent_rl.py:154-155 */
     if (cfg->algo == RLRM_ALGO_QL) {
       double rew = r->reward;
-      if (cfg->use_rsh && tb->phi) rew += cfg->gamma * tb->phi[nQ + r->q] - tb->phi[nQ + r->prev_q]; /* qlearning.py:51-66 */
+      if (cfg->use_rsh && v.phi) rew += cfg->gamma * v.phi[pstride + r->q] - v.phi[pstride + r->prev_q]; /* qlearning.py:51-66 */
       update_q(cfg, Q, V, s, action, rew, sn, term_arg, accp);
     }
     else update_qlambda(cfg, Q, (real*)st->e + base, V, S, s, action, r->reward, sn, term_arg);
@@ -414,7 +443,7 @@ static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, c
     slot_t s = unpack(st->slot[k]);
     before[a] = s.cell;
     first = (s.flags & RLRM_FLAG_FIRST) != 0;
-    const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * cfg->n_rm_states + s.rm) * 4;
+    const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * agent_rm(cfg, tb, a).nQ + s.rm) * 4;
     uint32_t w[4];
     get_draws(cfg, NULL, t, i, a, w);
     act[a] = (uint8_t)select_one(cfg, row, st->epsilon[k], w, !learn); /* learn == 0: greedy evaluation, best=True */
@@ -443,7 +472,7 @@ static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, c
         rlrm_stats_t* z = &st->stats[k];
         z->episodes++;
         z->active_steps += s.steps; /* env.agent_steps[agent] of the finished episode */
-        z->successes += (cfg->rm_final >= 0 && (int)s.rm == cfg->rm_final);
+        { int fin = agent_rm(cfg, tb, a).final; z->successes += (fin >= 0 && (int)s.rm == fin); }
         double ret = st->ep_return ? st->ep_return[k] : 0.0;
         z->last_return = (float)ret;
         z->return_sum += ret;
@@ -456,7 +485,8 @@ static void train_iteration(const rlrm_config_t* cfg, const rlrm_tables_t* tb, c
 
 /* shared learner: every touched entry becomes the mean of this iteration's proposals (include/rlrm_b200.h) */
 static void apply_shared(const rlrm_config_t* cfg, const rlrm_state_t* st) {
-  size_t n = (size_t)cfg->n_agents * cfg->width * cfg->height * cfg->n_rm_states * 4;
+  size_t n = 0;
+  for (int a = 0; a < cfg->n_agents; a++) n += table_rows(cfg, a) * 4;
   real* Q = (real*)st->q;
   for (size_t j = 0; j < n; j++) {
     int32_t c = st->acc_cnt[j];
@@ -496,7 +526,7 @@ int oracle_evaluate(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlr
       for (int a = 0; a < A; a++) {
         size_t k = (size_t)i * A + a;
         slot_t s = unpack(st->slot[k]);
-        const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * cfg->n_rm_states + s.rm) * 4;
+        const real* row = (const real*)st->q + table_base(cfg, i, a) + ((size_t)s.cell * agent_rm(cfg, tb, a).nQ + s.rm) * 4;
         uint32_t w[4] = {0, 0, 0, 0};
         act[a] = (uint8_t)select_one(cfg, row, 0.0, w, 1); /* best=True: np.argmax, no randomness (:84-87) */
       }
@@ -508,7 +538,7 @@ int oracle_evaluate(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlr
         rlrm_eval_t* e = &ev[k];
         if (!e->in_success) { /* :96-110 */
           e->disc_return += e->cum_gamma * rec[a].reward;
-          if (rec[a].term && cfg->rm_final >= 0 && (int)rec[a].q == cfg->rm_final) { e->successes++; e->in_success = 1; }
+          { int fin = agent_rm(cfg, tb, a).final; if (rec[a].term && fin >= 0 && (int)rec[a].q == fin) { e->successes++; e->in_success = 1; } }
         }
         e->cum_gamma *= gamma;
         all_term &= (int)rec[a].term; all_trunc &= (int)rec[a].trunc;

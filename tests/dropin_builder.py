@@ -24,15 +24,20 @@ def build_b200(sc, table_dtype=None):
         env.high_prob = sc["high_prob"]
         env.delay_action = bool(sc["delay_action"])
         SEnc, AEnc = P.StateEncoderOfficeWorld, P.ActionEncoderOfficeWorld
-    transitions = {}
-    for (s, e, t, r) in sc["rm_transitions"]:
-        transitions[(s, None if e is None else tuple(e))] = (t, r)
-    if sc.get("detector_positions") is not None:
-        positions = {tuple(p) for p in sc["detector_positions"]}
-    else:
-        positions = {ev for (_s, ev) in transitions if ev is not None}
+    def machine(k):
+        trs = sc["rm_transitions"] if not sc.get("rm_transitions_per_agent") else sc["rm_transitions_per_agent"][k]
+        tmap = {}
+        for (s, e, t, r) in trs:
+            tmap[(s, None if e is None else tuple(e))] = (t, r)
+        if sc.get("detector_positions") is not None:
+            pos = {tuple(p) for p in sc["detector_positions"]}
+        else:
+            pos = {ev for (_s, ev) in tmap if ev is not None}
+        return tmap, pos
+
     agents = []
     for k, (x, y) in enumerate(sc["starts"]):
+        transitions, positions = machine(k)
         ag = P.AgentRL(f"a{k + 1}", env)
         ag.set_initial_position(x, y)
         ag.add_state_encoder(SEnc(ag))

@@ -16,6 +16,7 @@ DROPIN_CASES = [
     ("ow_terminate_plants_walls_ql", 250), ("cfg4_office_chain12_qlambda", 60), ("fl_shaping_vi_ql", 150),
     ("fl_shaping_distance_qrm", 150), ("ow_shaping_vi_exp3_qrm", 150), ("ow_map2_walls_qrm", 120), ("ow_map3_walls_qrm", 100),
     ("ow_map4_walls_qrm", 60), ("fl_random_starts_3agents_qrm", 200), ("fl_random_starts_6agents_ql", 120),
+    ("fl_per_agent_rms_qrm", 200), ("fl_per_agent_rms_ql", 200),
 ]
 
 

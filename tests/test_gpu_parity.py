@@ -80,6 +80,14 @@ def _scenarios_medium():
     sc = P.scenario_config5(False)
     sc.random_start_positions = True
     out["fl_random_starts_qrm"] = (sc, 1500, 1200)
+    g = P.frozen_lake_grid("map1").goals
+    for algo, lr in (("qrm", 1.0), ("ql", 0.2)):
+        sc = P.scenario_config3(algo == "qrm")
+        sc.algo, sc.learning_rate, sc.starts, sc.detector_positions = algo, lr, [(5, 0), (0, 0), (9, 9)], sorted(g.values())
+        sc.rm_transitions_per_agent = [P.tables.frozen_lake_abc_transitions(), [("p0", g["C"], "p1", 3.0), ("p1", g["A"], "p2", 7.0)],
+                                       [("w0", g["B"], "w1", 1.0), ("w1", g["A"], "w2", 1.0), ("w2", g["C"], "w3", 1.0),
+                                        ("w3", g["B"], "w4", 5.0), ("w1", g["C"], "w0", -1.0)]]
+        out[f"fl_per_agent_rms_{algo}"] = (sc, 700, 1300)
     return out
 
 
@@ -120,7 +128,8 @@ def test_generic_kernel_equals_specialised(name, cuda_device):
     assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
 
 
-@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda"])
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda", "fl_per_agent_rms_qrm",
+                                  "fl_per_agent_rms_ql", "fl_random_starts_qrm"])
 def test_unfused_entry_points_equal_fused(name, cuda_device):
     """select -> step -> update -> reset through the separate C-ABI calls == the fused persistent kernel."""
     import multiagent_rlrm_b200 as P
