@@ -241,7 +241,7 @@ class Engine:
         term = rec["term"].view(self.N, self.A).bool()
         trunc = rec["trunc"].view(self.N, self.A).bool()
         over = term.all(dim=1) | trunc.all(dim=1)
+        self.t += 1  # the reset below starts episodes whose first step is iteration t + 1 (keys the random start positions)
         if auto_reset:
             self.reset(over)
-        self.t += 1
         return actions, rec, over
