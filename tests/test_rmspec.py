@@ -178,3 +178,24 @@ def test_pipeline_equals_live_reference(fixture, env, complete, capsys):
     assert rm.state_indices == ref_rm.state_indices and rm.initial_state == ref_rm.initial_state
     assert rm.get_final_state() == ref_rm.get_final_state() and rm.get_all_states() == ref_rm.get_all_states()
     assert set(rm.event_detector.positions) == set(ref_rm.event_detector.positions)
+
+
+def test_per_agent_spec_files_compile_to_per_agent_tables(tmp_path):
+    """frozen_lake_main.py --rm-spec-a1 / --rm-spec-a2: one spec per agent -> per-agent table sections."""
+    a2 = tmp_path / "a2.json"
+    a2.write_text(json.dumps({"name": "a2", "env_id": "frozenlake", "version": "1.0", "states": ["p0", "p1", "p2"], "initial_state": "p0",
+                              "terminal_states": ["p2"], "event_vocabulary": ["C", "A"],
+                              "transitions": [{"from_state": "p0", "event": "C", "to_state": "p1", "reward": 3},
+                                              {"from_state": "p1", "event": "A", "to_state": "p2", "reward": 7}]}))
+    rm1, _ = R.load_reward_machine(os.path.join(FIX, "frozenlake_abc.json"), "frozen_lake", "map1")
+    rm2, _ = R.load_reward_machine(a2, "frozen_lake", "map1")
+    c = P.compile_scenario(P.scenario_config3(True), rm=[rm1, rm2])
+    cfg = c.config
+    assert cfg.per_agent_rm == 1 and list(cfg.agent_n_rm_states)[:2] == [4, 3] and list(cfg.agent_rm_final)[:2] == [3, 2]
+    assert list(cfg.agent_n_qrm)[:2] == [3, 2] and cfg.n_rm_states == 4 and c.agent_rows == [400, 300]
+    assert c.delta.shape == (2, 4, cfg.n_events + 1) and c.label.shape == (2, 100)
+    uniform = P.compile_scenario(P.scenario_config3(True))
+    assert np.array_equal(c.delta[0], uniform.delta) and np.array_equal(c.rq[0], uniform.rq)
+    g = P.frozen_lake_grid("map1").goals
+    col = {ev: k for k, ev in enumerate(c.events)}
+    assert c.delta[1, 0, col[g["C"]]] == 1 and c.rq[1, 1, col[g["A"]]] == 7.0 and c.delta[1, 0, col[g["A"]]] == 255
