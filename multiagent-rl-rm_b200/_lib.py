@@ -16,7 +16,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "librlrm_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "rlrm_b200.cu")]
-HEADERS = [os.path.join(_ROOT, "include", "rlrm_b200.h")]
+HEADERS = [os.path.join(_ROOT, "include", "rlrm_b200.h")] + sorted(
+    os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc")) if f.endswith(".cuh"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

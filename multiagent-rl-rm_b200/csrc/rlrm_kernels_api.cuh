@@ -1,0 +1,181 @@
+// rlrm_kernels_api.cuh: call-by-call kernels (reset / select / step / rm_step / update), also the trace-injection parity path — part of the single translation unit csrc/rlrm_b200.cu (see its header comment).
+#pragma once
+#include "rlrm_device.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// unfused kernels (the reference's call-by-call API; also the parity path with injected draws)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsigned char* mask, unsigned long long t) {
+  Tab tb = stage_tables(p);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  if (mask && !mask[i]) return;
+  Slot s;
+  double eps = st.epsilon[k];
+  reset_slot(p, tb, i, a, t, s, eps);
+  st.slot[k] = pack_slot(s);
+  st.epsilon[k] = eps;
+  if (st.ep_return) st.ep_return[k] = 0.0;
+}
+
+// Q(lambda): reset_e_table for the masked instances (ma_frozen_lake.py:80-81 ; ma_office.py:101-102)
+__global__ void __launch_bounds__(256) clear_traces_kernel(KP p, DState st, const unsigned char* mask) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of one slot's table
+  const long long per = p.S4 / 4;
+  if (g >= st.N * p.A * per) return;
+  const long long slot = g / per;
+  if (mask && !mask[slot / p.A]) return;
+  reinterpret_cast<float4*>(st.e)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <bool PA>
+__global__ void __launch_bounds__(256) select_kernel(KP p_in, DState st, const unsigned* draws, unsigned long long t, int best,
+                                                    unsigned char* actions_out) {
+  KP p = p_in;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  if (PA) p.nQ = p_in.a_nQ[a];
+  const Slot s = unpack_slot(st.slot[k]);
+  const float* Q = st.q + table_base(p_in, i, a);
+  const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+  unsigned w[4];
+  if (draws) {
+    const uint4 d = reinterpret_cast<const uint4*>(draws)[k];
+    w[0] = d.x; w[1] = d.y; w[2] = d.z; w[3] = d.w;
+  } else {
+    RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+  }
+  actions_out[k] = (unsigned char)select_action(row, explore_threshold(st.epsilon[k]), w, best != 0, p.n_actions);
+}
+
+__device__ __forceinline__ void store_rec(const DOut& o, long long k, const Rec& r) {
+  if (o.prev_cell) o.prev_cell[k] = (unsigned short)r.prev_cell;
+  if (o.cell) o.cell[k] = (unsigned short)r.cell;
+  if (o.prev_q) o.prev_q[k] = (unsigned char)r.prev_q;
+  if (o.q) o.q[k] = (unsigned char)r.q;
+  if (o.event) o.event[k] = (unsigned char)r.event;
+  if (o.executed) o.executed[k] = (unsigned char)r.executed;
+  if (o.renv) o.renv[k] = r.renv;
+  if (o.rq) o.rq[k] = r.rq;
+  if (o.reward) o.reward[k] = r.reward;
+  if (o.env_term) o.env_term[k] = r.env_term;
+  if (o.rm_term) o.rm_term[k] = r.rm_term;
+  if (o.term) o.term[k] = r.term;
+  if (o.trunc) o.trunc[k] = r.trunc;
+}
+
+template <int ENV, bool PA>
+__global__ void __launch_bounds__(256) step_kernel(KP p_in, DState st, const unsigned char* actions, const unsigned* draws,
+                                                  unsigned long long t, int with_rm, DOut out) {
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  if (PA) agent_view(p_in, p, tb, a);
+  Slot s = unpack_slot(st.slot[k]);
+  unsigned w3 = 0;
+  if (p.stochastic) {
+    if (draws) {
+      w3 = draws[k * 4 + 3];
+    } else {
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      w3 = w[3];
+    }
+  }
+  Rec r;
+  agent_step<ENV>(p, tb, s, actions[k], w3, with_rm != 0, r);
+  st.slot[k] = pack_slot(s);
+  store_rec(out, k, r);
+}
+
+// RewardMachine.step on explicit (state, position) pairs (reward_machine.py:45-59)
+__global__ void __launch_bounds__(256) rm_step_kernel(KP p_in, int agent, long long n, unsigned char* q, const unsigned short* cell,
+                                                     unsigned char* event_out, double* reward_out) {
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  if (p_in.per_agent) agent_view(p_in, p, tb, agent);  // the reward machine of agent `agent`
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const unsigned ev = tb.label[cell[k]];
+  const int col = ev == RLRM_EVENT_NONE ? p.nEv : (int)ev;
+  const unsigned cur = q[k];
+  const unsigned d = tb.delta[cur * (p.nEv + 1) + col];
+  double r = 0.0;
+  if (d != RLRM_NO_TRANSITION) {
+    r = tb.rq[cur * (p.nEv + 1) + col];
+    q[k] = (unsigned char)d;
+  }
+  if (event_out) event_out[k] = (unsigned char)ev;
+  if (reward_out) reward_out[k] = r;
+}
+
+template <int ALGO, bool PA>
+__global__ void __launch_bounds__(256) update_kernel(KP p_in, DState st, const unsigned short* obs_cell, const unsigned char* actions,
+                                                    const unsigned char* term_arg, DOut o) {
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= st.N * p.A) return;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  if (PA) agent_view(p_in, p, tb, a);
+  Rec r;
+  r.prev_cell = o.prev_cell[k]; r.cell = o.cell[k]; r.prev_q = o.prev_q[k]; r.q = o.q[k]; r.event = o.event[k];
+  r.env_term = o.env_term[k] != 0; r.renv = o.renv[k]; r.reward = o.reward[k];
+  const size_t base = table_base(p_in, i, a);
+  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, obs_cell[k], actions[k], term_arg[k] != 0, r,
+                     make_acc(p, st, base));
+}
+
+// QLearningLambda.update (qlearning_lambda.py:33-84), dense sweep exactly as written: one block per (instance, agent).
+// q += (lr*td) * e ; e = terminated ? 0 : e * (gamma*lambda), with e[s,a] replaced by 1 first.
+__device__ __forceinline__ void qlambda_sweep(const KP& p, float* Q, float* E, unsigned s, int a, double reward, unsigned sn,
+                                              bool terminated, int tid, int nthreads) {
+  // every thread reads the two scalars before anyone writes
+  const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
+  const float qsa = Q[s * 4 + a];
+  __syncthreads();
+  const double best = terminated ? 0.0 : (double)row_max(nrow);
+  const float td = __fsub_rn(__double2float_rn(__dadd_rn(reward, __dmul_rn(p.gamma, best))), qsa);
+  const float c = __fmul_rn(p.lr_f, td);
+  const unsigned hot = s * 4 + a;
+  float4* Q4 = reinterpret_cast<float4*>(Q);
+  float4* E4 = reinterpret_cast<float4*>(E);
+  for (long long j = tid; j < p.S4 / 4; j += nthreads) {
+    float4 e = E4[j], q = Q4[j];
+    if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);  // replacing trace
+    q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
+    q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
+    q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
+    q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+    if (terminated) {
+      e = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {  // next_action defaults to argmax Q[s'] => greedy => decay (qlearning_lambda.py:71-81)
+      e.x = __fmul_rn(e.x, p.trace_decay_f);
+      e.y = __fmul_rn(e.y, p.trace_decay_f);
+      e.z = __fmul_rn(e.z, p.trace_decay_f);
+      e.w = __fmul_rn(e.w, p.trace_decay_f);
+    }
+    Q4[j] = q;
+    E4[j] = e;
+  }
+}
+
+__global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, const unsigned short* obs_cell,
+                                                            const unsigned char* actions, const unsigned char* term_arg, DOut o) {
+  const long long k = blockIdx.x;
+  const long long i = k / p.A;
+  const int a = (int)(k - i * p.A);
+  const size_t base = table_base(p, i, a);
+  if (st.visits && threadIdx.x == 0) st.visits[base + (size_t)(obs_cell[k] * p.nQ + o.prev_q[k]) * 4 + actions[k]] += 1;
+  qlambda_sweep(p, st.q + base, st.e + base, obs_cell[k] * p.nQ + o.prev_q[k], actions[k], o.reward[k],
+                o.cell[k] * p.nQ + o.q[k], term_arg[k] != 0, threadIdx.x, blockDim.x);
+}
+

@@ -1,0 +1,195 @@
+// rlrm_kernels_eval_shared.cuh: greedy evaluation and the shared-learner kernels — part of the single translation unit csrc/rlrm_b200.cu (see its header comment).
+#pragma once
+#include "rlrm_kernels_train.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// greedy evaluation (test_policy_optima, evaluation_metrics.py:23-190): the driver loop with best=True and no update
+// ------------------------------------------------------------------------------------------------
+template <int ENV, bool PA>
+__global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p_in, DState st, rlrm_eval_t* evs, unsigned long long t0, int n_iters,
+                                                          int n_episodes, double gamma, double optimal_steps) {
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+  Slot s = {0, 0, 0, 0, 0};
+  rlrm_eval_t e;
+  memset(&e, 0, sizeof(e));
+  const float* Q = st.q;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    e = evs[k];
+    if (PA) agent_view(p_in, p, tb, a);
+    Q = st.q + table_base(p_in, i, a);
+  }
+  const unsigned w0[4] = {0, 0, 0, 0};
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    const bool running = valid && (int)e.episodes < n_episodes;  // all agents of an instance finish episodes together
+    if (running) {
+      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      const int action = select_action(row, 0ull, w0, true, p.n_actions);
+      unsigned w3 = 0;
+      if (p.stochastic) {
+        unsigned w[4];
+        RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+        w3 = w[3];
+      }
+      Rec r;
+      agent_step<ENV>(p, tb, s, action, w3, true, r);
+      if (!e.in_success) {
+        e.disc_return = __dadd_rn(e.disc_return, __dmul_rn(e.cum_gamma, r.reward));
+        if (r.term && p.rm_final >= 0 && (int)r.q == p.rm_final) {
+          e.successes++;
+          e.in_success = 1;
+        }
+      }
+      e.cum_gamma = __dmul_rn(e.cum_gamma, gamma);
+      term = r.term;
+      trunc = r.trunc;
+    }
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (running && over) {
+      const unsigned long long len = s.time;
+      e.episodes++;
+      e.return_sum = __dadd_rn(e.return_sum, e.disc_return);
+      e.return_sqsum = __dadd_rn(e.return_sqsum, __dmul_rn(e.disc_return, e.disc_return));
+      if (e.in_success) {
+        e.len_sum += len;
+        e.len_sqsum += len * len;
+      }
+      if (len > 0) e.arps_sum = __dadd_rn(e.arps_sum, __ddiv_rn(__ddiv_rn(e.disc_return, (double)len), optimal_steps));
+      e.cum_gamma = 1.0;
+      e.disc_return = 0.0;
+      e.in_success = 0;
+      double eps_unused = 0.0;
+      KP q = p;
+      q.decay_on_reset = 0;  // evaluation runs on a copy of the env: the training epsilon is not touched
+      reset_slot(q, tb, i, a, t + 1, s, eps_unused);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    evs[k] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared learner, fast path: ONE lockstep iteration over all instances by persistent blocks. The per-agent shared
+// tables (A*S*4 floats, 25.6 KB for config 5) and the proposal accumulators live in SHARED memory: Q reads are LDS,
+// proposals are shared-memory atomics, and each block flushes its non-empty accumulators to the global ones once.
+// Integer sums make the result independent of the block/thread order (include/rlrm_b200.h "Shared learner").
+// Slot state is streamed from HBM (8 B in + 8 B out per slot); statistics are only touched when an episode ends.
+// ------------------------------------------------------------------------------------------------
+#define SHARED_BLOCK 1024
+
+template <int ENV, int ALGO>
+__global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, DState st, unsigned long long t, int learn,
+                                                                        unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const int n_ent = p.A * (int)p.S4;
+  float* Qs = reinterpret_cast<float*>(smem_raw + p.blob_bytes);
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(Qs + n_ent);
+  int* s_cnt = reinterpret_cast<int*>(s_sum + n_ent);
+  float* s_last = reinterpret_cast<float*>(s_cnt + n_ent);
+  for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x)
+    reinterpret_cast<float4*>(Qs)[j] = __ldg(reinterpret_cast<const float4*>(st.q) + j);
+  for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+    s_sum[j] = 0ull;
+    s_cnt[j] = 0;
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+  const long long total = st.N << p.g_shift;
+  for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += (long long)gridDim.x * blockDim.x) {
+    const long long tid = b0 + threadIdx.x;
+    const long long i = tid >> p.g_shift;
+    const int a = (int)(tid & (p.G - 1));
+    const bool valid = (i < st.N) && (a < p.A);
+    const long long k = i * p.A + a;
+    bool term = true, trunc = true;
+    Slot s = {0, 0, 0, 0, 0};
+    double eps = 0.0;
+    Rec r;
+    r.reward = 0.0;
+    if (valid) {
+      s = unpack_slot(st.slot[k]);
+      eps = st.epsilon[k];
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      float* Q = Qs + (size_t)a * (size_t)p.S4;
+      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      const int action = select_action(row, explore_threshold(eps), w, learn == 0, p.n_actions);
+      const unsigned before = s.cell;
+      const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      if (learn) {
+        const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+        const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+        Acc acc = {reinterpret_cast<long long*>(s_sum) + (size_t)a * (size_t)p.S4, s_cnt + (size_t)a * (size_t)p.S4,
+                   s_last + (size_t)a * (size_t)p.S4};
+        agent_update<ALGO>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
+      }
+      term = r.term;
+      trunc = r.trunc;
+      if (r.reward != 0.0 && st.ep_return) st.ep_return[k] = __dadd_rn(st.ep_return[k], r.reward);
+      if (trace)
+        trace[k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) | ((unsigned)r.term << 21) |
+                   ((unsigned)r.trunc << 22) | ((unsigned)r.stepped << 23);
+    }
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (valid) {
+      if (over) {
+        const double ret = st.ep_return ? st.ep_return[k] : 0.0;
+        if (st.stats) {
+          rlrm_stats_t z = st.stats[k];
+          z.episodes++;
+          z.active_steps += s.steps;
+          z.successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+          z.last_return = __double2float_rn(ret);
+          z.return_sum = __dadd_rn(z.return_sum, ret);
+          z.last_length = s.time;
+          st.stats[k] = z;
+        }
+        if (st.ep_return) st.ep_return[k] = 0.0;
+        reset_slot(p, tb, i, a, t + 1, s, eps);
+        st.epsilon[k] = eps;
+      }
+      st.slot[k] = pack_slot(s);
+    }
+  }
+  __syncthreads();
+  if (learn) {
+    for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+      const int c = s_cnt[j];
+      if (c) {
+        atomicAdd(st.acc_cnt + j, c);
+        atomicAdd(reinterpret_cast<unsigned long long*>(st.acc_sum) + j, s_sum[j]);
+        st.acc_last[j] = s_last[j];  // only read back when the GLOBAL count is 1, i.e. exactly one block wrote it
+      }
+    }
+  }
+}
+
+// shared learner: every touched entry becomes the mean of this iteration's proposals; accumulators are cleared
+__global__ void __launch_bounds__(256) apply_shared_kernel(KP p, DState st) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (p.per_agent ? p.sum4 : (long long)p.A * p.S4)) return;
+  const int c = st.acc_cnt[j];
+  if (c == 0) return;
+  if (c == 1) st.q[j] = st.acc_last[j];
+  else st.q[j] = __double2float_rn(__dmul_rn(__ddiv_rn((double)st.acc_sum[j], (double)c), 9.5367431640625e-07));
+  st.acc_cnt[j] = 0;
+  st.acc_sum[j] = 0;
+}
+

@@ -1,0 +1,323 @@
+// rlrm_kernels_qlambda.cuh: Q(lambda) fused kernels, dense-faithful and sparse-exact — part of the single translation unit csrc/rlrm_b200.cu (see its header comment).
+#pragma once
+#include "rlrm_kernels_train.cuh"
+
+template <int ENV>
+__global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                           unsigned* trace) {
+  Tab tb = stage_tables(p);
+  __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
+  const long long i = blockIdx.x;
+  const int a = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long k = i * p.A + a;
+  Slot s = unpack_slot(st.slot[k]);
+  double eps = st.epsilon[k];
+  double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
+  const size_t base = table_base(p, i, a);
+  float* Q = st.q + base;
+  float* E = st.e + base;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  bool had_episode = false;
+  rlrm_stats_t z;
+  if (st.stats) z = st.stats[k];
+  double return_sum_add = st.stats ? z.return_sum : 0.0;
+  unsigned long long explore_thr = explore_threshold(eps);
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    unsigned w[4];
+    RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+    __syncwarp();
+    const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+    const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
+    const unsigned before = s.cell;
+    const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+    Rec r;
+    agent_step<ENV>(p, tb, s, action, w[3], true, r);  // all 32 lanes compute the same scalars
+    if (learn) {
+      const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+      const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+      // warp-cooperative dense sweep (the __syncthreads inside qlambda_sweep is replaced by __syncwarp here)
+      const unsigned sidx = obs * p.nQ + r.prev_q, snidx = r.cell * p.nQ + r.q;
+      const float4 nrow = *reinterpret_cast<const float4*>(Q + snidx * 4);
+      const float qsa = Q[sidx * 4 + action];
+      __syncwarp();
+      const double best = term_arg ? 0.0 : (double)row_max(nrow);
+      const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
+      const float c = __fmul_rn(p.lr_f, td);
+      const unsigned hot = sidx * 4 + action;
+      float4* Q4 = reinterpret_cast<float4*>(Q);
+      float4* E4 = reinterpret_cast<float4*>(E);
+      for (long long j = lane; j < p.S4 / 4; j += 32) {
+        float4 e = E4[j], q = Q4[j];
+        if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);
+        q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
+        q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
+        q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
+        q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+        if (term_arg) {
+          e = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          e.x = __fmul_rn(e.x, p.trace_decay_f);
+          e.y = __fmul_rn(e.y, p.trace_decay_f);
+          e.z = __fmul_rn(e.z, p.trace_decay_f);
+          e.w = __fmul_rn(e.w, p.trace_decay_f);
+        }
+        Q4[j] = q;
+        E4[j] = e;
+      }
+      __syncwarp();
+    }
+    ep_ret = __dadd_rn(ep_ret, r.reward);
+    if (trace && lane == 0)
+      trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                           ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                           ((unsigned)r.stepped << 23);
+    if (lane == 0) {
+      sh_term[a] = r.term;
+      sh_trunc[a] = r.trunc;
+    }
+    __syncthreads();
+    bool all_term = true, all_trunc = true;
+    for (int b = 0; b < p.A; b++) {
+      all_term = all_term && sh_term[b];
+      all_trunc = all_trunc && sh_trunc[b];
+    }
+    __syncthreads();
+    if (all_term || all_trunc) {
+      episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum_add = __dadd_rn(return_sum_add, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, i, a, t + 1, s, eps);
+      explore_thr = explore_threshold(eps);
+      // reset_e_table (ma_office.py:101-102)
+      float4* E4 = reinterpret_cast<float4*>(E);
+      for (long long j = lane; j < p.S4 / 4; j += 32) E4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum_add;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q(lambda), sparse-exact traces: one block per instance, one warp per agent. Only entries with a live trace are
+// touched; each agent's live entries sit in a list that carries the trace AND the current q value (a write-back
+// cache over the table), so one update step reads/writes the list once, coalesced. Bit-identical to the dense sweep of
+// QLearningLambda.update (qlearning_lambda.py:33-84) up to the sign of zero: unlisted entries have e == 0 and receive +0.
+// ------------------------------------------------------------------------------------------------
+struct TraceList {
+  unsigned short* pos;  // [S*4]
+  unsigned short* idx;  // [cap]
+  float* e;
+  float* q;
+};
+
+// current value of table entry j: the listed copy when the entry has a live trace, else the table
+__device__ __forceinline__ float trace_lookup(const float* Q, const TraceList& L, unsigned j) {
+  const unsigned pz = L.pos[j];
+  return pz ? L.q[pz - 1] : Q[j];
+}
+
+// write the listed values back and forget the list (traces wiped: reset_e_table / e_table.fill(0))
+__device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsigned len, int lane) {
+  for (unsigned j = lane; j < len; j += 32) {
+    const unsigned id = L.idx[j];
+    Q[id] = L.q[j];
+    L.pos[id] = 0;
+  }
+}
+
+template <int ENV>
+__global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                                  unsigned* trace) {
+  Tab tb = stage_tables(p);
+  __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
+  const long long i = blockIdx.x;
+  const int a = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long k = i * p.A + a;
+  Slot s = unpack_slot(st.slot[k]);
+  double eps = st.epsilon[k];
+  double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
+  float* Q = st.q + table_base(p, i, a);
+  TraceList L;
+  L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
+  L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
+  L.e = st.tr_e + (size_t)k * (size_t)st.tr_cap;
+  L.q = st.tr_q + (size_t)k * (size_t)st.tr_cap;
+  unsigned len = st.tr_len[k];
+  unsigned long long work = 0, active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  bool had_episode = false;
+  rlrm_stats_t z;
+  if (st.stats) z = st.stats[k];
+  double return_sum = st.stats ? z.return_sum : 0.0;
+  unsigned long long explore_thr = explore_threshold(eps);
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    unsigned w[4];
+    RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+    __syncwarp();
+    // Q row of the current state: lanes 0..3 fetch one action value each
+    const unsigned rbase = (s.cell * p.nQ + s.rm) * 4;
+    const float mine = lane < 4 ? trace_lookup(Q, L, rbase + lane) : 0.f;
+    float4 row;
+    row.x = __shfl_sync(0xFFFFFFFFu, mine, 0);
+    row.y = __shfl_sync(0xFFFFFFFFu, mine, 1);
+    row.z = __shfl_sync(0xFFFFFFFFu, mine, 2);
+    row.w = __shfl_sync(0xFFFFFFFFu, mine, 3);
+    const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
+    const unsigned before = s.cell;
+    const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+    Rec r;
+    agent_step<ENV>(p, tb, s, action, w[3], true, r);  // all lanes compute the same scalars
+    if (learn) {
+      const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+      const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+      const unsigned hot = (obs * p.nQ + r.prev_q) * 4 + action, nbase = (r.cell * p.nQ + r.q) * 4;
+      // lanes 0..3: next-state row, lane 4: Q[s,a] — five independent lookups in flight
+      const float got = lane < 4 ? trace_lookup(Q, L, nbase + lane) : (lane == 4 ? trace_lookup(Q, L, hot) : 0.f);
+      const float n0 = __shfl_sync(0xFFFFFFFFu, got, 0), n1 = __shfl_sync(0xFFFFFFFFu, got, 1);
+      const float n2 = __shfl_sync(0xFFFFFFFFu, got, 2), n3 = __shfl_sync(0xFFFFFFFFu, got, 3);
+      const float qsa = __shfl_sync(0xFFFFFFFFu, got, 4);
+      const double best = term_arg ? 0.0 : (double)fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
+      const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
+      const float c = __fmul_rn(p.lr_f, td);
+      bool found = false;
+      for (unsigned j = lane; j < len; j += 32) {  // one coalesced pass over the live entries
+        float e = L.e[j], q = L.q[j];
+        if (L.idx[j] == hot) {
+          e = 1.0f;  // replacing trace
+          found = true;
+        }
+        q = __fadd_rn(q, __fmul_rn(c, e));
+        e = term_arg ? 0.0f : __fmul_rn(e, p.trace_decay_f);
+        L.q[j] = q;
+        L.e[j] = e;
+      }
+      work += len;
+      if (!__any_sync(0xFFFFFFFFu, found)) {  // first visit since the last wipe: the table value is current
+        if (lane == 0) {
+          L.idx[len] = (unsigned short)hot;
+          L.q[len] = __fadd_rn(Q[hot], __fmul_rn(c, 1.0f));
+          L.e[len] = term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f);
+          L.pos[hot] = (unsigned short)(len + 1);
+        }
+        len++;
+      }
+      __syncwarp();
+      if (term_arg) {  // e_table.fill(0): nothing is live any more
+        trace_flush(Q, L, len, lane);
+        len = 0;
+        __syncwarp();
+      }
+    }
+    ep_ret = __dadd_rn(ep_ret, r.reward);
+    if (trace && lane == 0)
+      trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                           ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                           ((unsigned)r.stepped << 23);
+    if (lane == 0) {
+      sh_term[a] = r.term;
+      sh_trunc[a] = r.trunc;
+    }
+    __syncthreads();
+    bool all_term = true, all_trunc = true;
+    for (int b = 0; b < p.A; b++) {
+      all_term = all_term && sh_term[b];
+      all_trunc = all_trunc && sh_trunc[b];
+    }
+    __syncthreads();
+    if (all_term || all_trunc) {
+      episodes++;
+      active_steps += s.steps;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, i, a, t + 1, s, eps);
+      explore_thr = explore_threshold(eps);
+      trace_flush(Q, L, len, lane);  // reset_e_table (ma_office.py:101-102)
+      len = 0;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    st.tr_len[k] = len;
+    if (st.tr_work) st.tr_work[k] += work;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// sparse Q(lambda): listed values -> table (lists stay live); optionally scatter the traces into a dense buffer
+__global__ void __launch_bounds__(256) qlambda_materialize_kernel(KP p, DState st, float* e_dense) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= st.N * p.A) return;
+  float* Q = st.q + (size_t)warp * (size_t)p.S4;
+  const unsigned short* idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
+  const float* lq = st.tr_q + (size_t)warp * (size_t)st.tr_cap;
+  const float* le = st.tr_e + (size_t)warp * (size_t)st.tr_cap;
+  const unsigned len = st.tr_len[warp];
+  for (unsigned j = lane; j < len; j += 32) {
+    Q[idx[j]] = lq[j];
+    if (e_dense) e_dense[(size_t)warp * (size_t)p.S4 + idx[j]] = le[j];
+  }
+}
+
+// sparse Q(lambda): reset_e_table for the masked instances = flush + forget the lists
+__global__ void __launch_bounds__(256) qlambda_sparse_reset_kernel(KP p, DState st, const unsigned char* mask) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= st.N * p.A) return;
+  if (mask && !mask[warp / p.A]) return;
+  TraceList L;
+  L.pos = st.tr_pos + (size_t)warp * (size_t)p.S4;
+  L.idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
+  L.e = st.tr_e + (size_t)warp * (size_t)st.tr_cap;
+  L.q = st.tr_q + (size_t)warp * (size_t)st.tr_cap;
+  trace_flush(st.q + (size_t)warp * (size_t)p.S4, L, st.tr_len[warp], lane);
+  __syncwarp();
+  if (lane == 0) st.tr_len[warp] = 0;
+}
+

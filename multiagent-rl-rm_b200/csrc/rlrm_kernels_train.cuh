@@ -1,0 +1,304 @@
+// rlrm_kernels_train.cuh: fused persistent training kernels (generic train_kernel and the QRM nQ=4 fast path) — part of the single translation unit csrc/rlrm_b200.cu (see its header comment).
+#pragma once
+#include "rlrm_device.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// fused persistent kernel: n_iters lockstep iterations, state in registers
+// ------------------------------------------------------------------------------------------------
+#define TRAIN_BLOCK 128
+
+template <int ENV, int ALGO, bool PA>
+__global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
+                                                           unsigned* trace) {
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0;
+  float* Q = nullptr;
+  unsigned* V = nullptr;
+  Acc acc = {nullptr, nullptr, nullptr};
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  double return_sum = 0.0;
+  float last_return = 0.f;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    if (PA) agent_view(p_in, p, tb, a);
+    const size_t base = table_base(p_in, i, a);
+    Q = st.q + base;
+    V = st.visits ? st.visits + base : nullptr;
+    acc = make_acc(p, st, base);
+  }
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+  // plain QL with a private table, fixed learning rate and no visit counts: carry the current row across iterations
+  const bool carry = (ALGO == RLRM_ALGO_QL) && !V && !acc.sum && p.lr >= 0.0;
+  float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned row_idx = 0xFFFFFFFFu;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    Rec r;
+    int action = 0;
+    if (valid) {
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      // every agent selects on every iteration, finished ones included (frozen_lake_main.py:350-352)
+      const unsigned cur_idx = s.cell * p.nQ + s.rm;
+      if (cur_idx != row_idx) {  // plain QL carries the row of its current state in registers (1-entry cache of Q)
+        row = *reinterpret_cast<const float4*>(Q + (size_t)cur_idx * 4);
+        row_idx = carry ? cur_idx : 0xFFFFFFFFu;
+      }
+      action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
+      const unsigned before = s.cell;
+      const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      if (learn) {
+        // FrozenLake driver: on an episode's first iteration `states` still aliases agent.state, so update_policy
+        // receives the NEW position as `state` (frozen_lake_main.py:337,359 ; office_main.py:1700 deep-copies)
+        const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+        const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+        if (ALGO == RLRM_ALGO_QL && carry) {
+          // update_q (qlearning.py:70-79) against the carried row: normally Q[s] is the carried row and only Q[s'] is loaded
+          const unsigned sidx = obs * p.nQ + r.prev_q, snidx = r.cell * p.nQ + r.q;
+          float4 nrow = (snidx == row_idx) ? row : *reinterpret_cast<const float4*>(Q + (size_t)snidx * 4);
+          const float cur = (sidx == row_idx) ? get_component(row, action)
+                                               : ((sidx == snidx) ? get_component(nrow, action) : Q[(size_t)sidx * 4 + action]);
+          double rew = r.reward;
+          if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.nQ + r.q]), tb.phi[p.nQ + r.prev_q]));
+          const float mf = __fmul_rn(term_arg ? 0.0f : 1.0f, row_max(nrow));
+          const float inner = __fadd_rn(__double2float_rn(rew), __fmul_rn(p.gamma_f, mf));
+          const float out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+          if (__float_as_uint(out) != __float_as_uint(cur)) Q[(size_t)sidx * 4 + action] = out;
+          if (sidx == row_idx) set_component(row, action, out);
+          if (snidx != row_idx) {  // the next state's row becomes the carried one
+            if (sidx == snidx) set_component(nrow, action, out);
+            row = nrow;
+            row_idx = snidx;
+          }
+        } else {
+          agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r, acc);
+        }
+      }
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      if (trace)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    // episode over when all agents terminated, or all truncated (frozen_lake_main.py:345,375 ; office_main.py:1748)
+    const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+    const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+    if (valid && over) {
+      episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot(p, tb, i, a, t + 1, s, eps);  // next episode starts with rm_env.reset (frozen_lake_main.py:337)
+      explore_thr = explore_threshold(eps);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: QRM with nQ == 4 (BASELINE configs 1/3/5). The 64-byte cell block Q[cell, 0..3, 0..3] lives in registers
+// between iterations: it is fetched with two 256-bit loads only when the agent changes cell, the counterfactual
+// updates run on registers, and the new values go back as scalar stores. Requires
+// qrm_states == [0, 1, 2] (so a static unroll over rows is the reference's update order), per-instance
+// tables, fixed learning rate, no visit counts; anything else takes train_kernel.
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ float sel4(float a, float b, float c, float d, unsigned k) {
+  const float lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
+  return (k & 2u) ? hi : lo;
+}
+__device__ __forceinline__ void load_block4(const float* Q, unsigned cell, float B[16], float bmax[4]) {
+  const F8 lo = ldg256(Q + (size_t)cell * 16), hi = ldg256(Q + (size_t)cell * 16 + 8);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    B[j] = lo.v[j];
+    B[8 + j] = hi.v[j];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) bmax[r] = fmaxf(fmaxf(B[4 * r], B[4 * r + 1]), fmaxf(B[4 * r + 2], B[4 * r + 3]));
+}
+
+// STOCH / LEARN / TRACE are compile-time copies of p.stochastic / learn / (trace != nullptr): the loop body is issue-bound,
+// so runtime flag tests and their constant-bank loads are specialised away. n_qrm is 3 on this path.
+template <int ENV, bool STOCH, bool LEARN, bool TRACE>
+__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState st, unsigned long long t0, int n_iters,
+                                                                unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
+  float* Q = st.q;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  float B[16], bmax[4];  // carried cell block Q[cell, rm state, action] and its row maxima
+#pragma unroll
+  for (int j = 0; j < 16; j++) B[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; j++) bmax[j] = 0.f;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    Q = st.q + table_base(p, i, a);
+    load_block4(Q, s.cell, B, bmax);
+  }
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    if (valid) {
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      float4 row;
+      row.x = sel4(B[0], B[4], B[8], B[12], s.rm);
+      row.y = sel4(B[1], B[5], B[9], B[13], s.rm);
+      row.z = sel4(B[2], B[6], B[10], B[14], s.rm);
+      row.w = sel4(B[3], B[7], B[11], B[15], s.rm);
+      const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);
+      const unsigned before = s.cell;
+      Rec r;
+      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
+      const bool moved = r.cell != before;
+      // values the updates overwrite, read before the carried block is replaced
+      const float cur0 = sel4(B[0], B[1], B[2], B[3], (unsigned)action);
+      const float cur1 = sel4(B[4], B[5], B[6], B[7], (unsigned)action);
+      const float cur2 = sel4(B[8], B[9], B[10], B[11], (unsigned)action);
+      if (moved) load_block4(Q, r.cell, B, bmax);  // the carried block becomes the NEXT cell's block
+      if (LEARN) {
+        // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106),
+        // in get_all_states()[:-1] order == row order 0..n_qrm-1 on this path. The next state's row maximum comes from
+        // the carried block: a different block when the agent moved, else the live one including earlier updates.
+        const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+        float* dst = Q + (size_t)before * 16 + action;  // infos["prev_s"] is the position before the move
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          {
+            const unsigned d = tb.delta[u * (p.nEv + 1) + col];
+            const unsigned un = d == RLRM_NO_TRANSITION ? (unsigned)u : d;
+            const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
+            const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
+            const float mx = sel4(bmax[0], bmax[1], bmax[2], bmax[3], un);
+            const float cur = u == 0 ? cur0 : (u == 1 ? cur1 : cur2);
+            const float mf = __fmul_rn(done ? 0.0f : 1.0f, mx);
+            const float inner = __fadd_rn(__double2float_rn(__dadd_rn(r.renv, ru)), __fmul_rn(p.gamma_f, mf));
+            const float nv = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+            if (__float_as_uint(nv) != __float_as_uint(cur)) dst[4 * u] = nv;  // a bit-identical value needs no store
+            if (!moved) {  // same cell: the carried block is the one just written
+#pragma unroll
+              for (int c = 0; c < 4; c++) B[4 * u + c] = (c == action) ? nv : B[4 * u + c];
+              bmax[u] = fmaxf(fmaxf(B[4 * u], B[4 * u + 1]), fmaxf(B[4 * u + 2], B[4 * u + 3]));
+            }
+          }
+        }
+      }
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      if (TRACE)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    // episode over <=> every agent of the instance terminated, or every agent truncated: AND-reduce the two flags
+    // (packed in one word) over the instance's lane group with xor shuffles
+    unsigned flags2 = (term ? 1u : 0u) | (trunc ? 2u : 0u);
+    for (int o = 1; o < p.G; o <<= 1) flags2 &= __shfl_xor_sync(0xFFFFFFFFu, flags2, o);
+    const bool over = flags2 != 0u;
+    if (valid && over) {
+      episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot<false>(p, tb, i, a, t + 1, s, eps);
+      explore_thr = explore_threshold(eps);
+      load_block4(Q, s.cell, B, bmax);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// Q(lambda) fused: one block per instance, one warp per agent; the dense trace sweep is cooperative over the warp.
