@@ -36,16 +36,26 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc cross-compiles for sm_100a; works without a GPU."""
-    if force or is_stale():
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-        if verbose:
-            print(res.stderr)
+    """nvcc cross-compiles for sm_100a; works without a GPU. Serialised with a file lock so that several ranks of one
+    job (torchrun) never compile into the same file at once; the library is written to a temporary name and renamed."""
+    import fcntl
+
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or is_stale():
+                tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+                cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *SOURCES]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp, LIB_PATH)
+                if verbose:
+                    print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -54,6 +64,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if is_stale() and os.path.exists(_nvcc()):
+        build()  # missing or older than its sources: rebuild in-tree (there is still no CPU fallback)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "

@@ -4,7 +4,6 @@ the learner, whose arithmetic runs on the device."""
 from __future__ import annotations
 
 import random
-from typing import Optional
 
 
 class UPValueError(Exception):

@@ -13,10 +13,9 @@ harness (oracle/ref_harness.py), the C oracle and the CUDA library.
 """
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass, field
 from fractions import Fraction
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -25,7 +24,6 @@ from .maps import GridSpec, frozen_lake_grid, office_world_grid
 from .reward_machine import PositionEventDetector, RewardMachine
 
 UP, DOWN, LEFT, RIGHT, WAIT = 0, 1, 2, 3, 4
-_NAME_TO_ACTION = {"up": UP, "down": DOWN, "left": LEFT, "right": RIGHT, "wait": WAIT}
 
 
 @dataclass

@@ -23,7 +23,7 @@ import torch
 
 from . import _abi as abi
 from .engine import Engine
-from .tables import Compiled, Scenario, compile_scenario
+from .tables import Compiled, compile_scenario
 
 
 class BatchedRMEnvironment:

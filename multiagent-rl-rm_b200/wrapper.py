@@ -4,7 +4,6 @@ transitions reported in infos["qrm_experience"] come from rlrm_rm_step on the sa
 out of scope."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from .envs import _num

@@ -39,15 +39,21 @@ def build(force=False):
     stale = force or any((not os.path.exists(t)) or os.path.getmtime(t) < max(os.path.getmtime(src), os.path.getmtime(hdr))
                          for t in targets)
     if stale:
-        subprocess.run(["make", "-C", _HERE, "-B", "all"], check=True, capture_output=True)
+        import fcntl
+
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:  # several ranks / pytest workers may get here together
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                subprocess.run(["make", "-C", _HERE, "-B", "all"], check=True, capture_output=True)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return targets
 
 
 def lib(real="f32"):
     if real not in _libs:
         path = os.path.join(_HERE, f"liboracle_{real}.so")
-        if not os.path.exists(path):
-            build()
+        build()  # no-op unless missing or older than rlrm_oracle.c / the header
         L = C.CDLL(path)
         assert L.oracle_real_size() == (4 if real == "f32" else 8)
         _libs[real] = L

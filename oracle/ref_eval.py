@@ -3,8 +3,6 @@
 self-check against the reference's OWN function on deterministic dynamics (where no randomness is consumed)."""
 from __future__ import annotations
 
-import copy
-
 import numpy as np
 
 import ref_harness as H
