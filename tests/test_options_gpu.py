@@ -1,0 +1,108 @@
+"""GPU: less-travelled options of the C ABI against the oracle (bit-exact): greedy rollouts (learn = 0), visit counting
+with a fixed learning rate, hyper-parameter changes between launches (rlrm_set_learner), a state without statistics, the
+shared learner on OfficeWorld / plain QL (generic accumulation path), evaluation with per-agent reward machines."""
+import numpy as np
+import pytest
+
+import multiagent_rlrm_b200 as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(sc, n, **kw):
+    import oracle as O
+    from multiagent_rlrm_b200.engine import Engine
+
+    c = P.compile_scenario(sc)
+    eng = Engine(c, n, **kw)
+    o = O.Oracle(c, n, "f32", track_visits=kw.get("track_visits", False))
+    eng.reset(); o.reset()
+    return eng, o
+
+
+def _same(eng, o):
+    assert np.array_equal(eng.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert np.array_equal(eng.q.cpu().numpy().reshape(-1), o.q.reshape(-1))
+    assert np.array_equal(eng.epsilon.cpu().numpy(), o.epsilon)
+
+
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2", "chain12_qrm"])
+def test_greedy_rollout_without_learning(name, cuda_device):
+    sc = {"cfg3_qrm": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
+          "cfg2": lambda: P.scenario_config2(True)}.get(name)
+    if sc is None:
+        sc = P.scenario_config4()
+        sc.algo, sc.learning_rate, sc.q_init = "qrm", 0.1, 2.0
+    else:
+        sc = sc()
+    eng, o = _pair(sc, 300)
+    eng.train(400); o.train(0, 400)
+    q_before = eng.q.clone()
+    tr_g = eng.train(500, learn=False, trace=True)
+    tr_o = o.train(400, 500, learn=False, trace=True)
+    assert np.array_equal(tr_g.cpu().numpy().view(np.uint32), tr_o)
+    assert bool((eng.q == q_before).all())  # nothing learns
+    _same(eng, o)
+
+
+def test_visit_counts_with_fixed_learning_rate(cuda_device):
+    eng, o = _pair(P.scenario_config3(True), 200, track_visits=True)
+    eng.train(600); o.train(0, 600)
+    _same(eng, o)
+    assert np.array_equal(eng.visits.cpu().numpy().view(np.uint32).reshape(-1), o.visits.reshape(-1))
+    assert int(o.visits.sum()) > 0
+
+
+def test_hyper_parameters_can_change_between_launches(cuda_device):
+    sc = P.scenario_config3(False)
+    eng, o = _pair(sc, 256)
+    eng.train(300); o.train(0, 300)
+    eng.set_learner(0.5, 0.8)
+    o.cfg.learning_rate, o.cfg.gamma = 0.5, 0.8
+    eng.train(300); o.train(300, 300)
+    _same(eng, o)
+
+
+def test_state_without_statistics(cuda_device):
+    import oracle as O
+    from multiagent_rlrm_b200.engine import Engine
+
+    c = P.compile_scenario(P.scenario_config3(True))
+    eng = Engine(c, 128, with_stats=False)
+    o = O.Oracle(c, 128, "f32")
+    eng.reset(); o.reset()
+    eng.train(700); o.train(0, 700)
+    _same(eng, o)
+
+
+@pytest.mark.parametrize("name", ["office_qrm", "frozen_ql"])
+def test_shared_learner_generic_accumulation(name, cuda_device):
+    if name == "office_qrm":  # 12-state machine: tables too large for the shared-memory fast path
+        sc = P.scenario_config4()
+        sc.algo, sc.learning_rate, sc.q_init, sc.shared_q = "qrm", 0.1, 2.0, True
+    else:
+        sc = P.scenario_config5(True)
+        sc.algo, sc.learning_rate = "ql", 0.1
+    eng, o = _pair(sc, 700)
+    tr_g = eng.train(90, trace=True)
+    tr_o = o.train(0, 90, trace=True)
+    assert np.array_equal(tr_g.cpu().numpy().view(np.uint32), tr_o)
+    _same(eng, o)
+    s = eng.stats_numpy()
+    for f in ("episodes", "successes", "active_steps", "return_sum"):
+        assert np.array_equal(s[f], o.stats[f]), f
+
+
+def test_evaluation_with_per_agent_reward_machines(cuda_device):
+    g = P.frozen_lake_grid("map1").goals
+    sc = P.scenario_config1()
+    sc.starts = [(5, 0), (0, 0)]
+    sc.detector_positions = sorted(g.values())
+    sc.rm_transitions_per_agent = [P.tables.frozen_lake_abc_transitions(), [("p0", g["B"], "p1", 3.0), ("p1", g["A"], "p2", 7.0)]]
+    eng, o = _pair(sc, 128)
+    eng.train(5000); o.train(0, 5000)
+    _same(eng, o)
+    ev_g, ev_o = eng.evaluate(2, 0.99, 21.0, t0=0), o.evaluate(2, 0.99, 21.0, t0=0)
+    for f in ("episodes", "successes", "len_sum", "return_sum", "arps_sum"):
+        assert np.array_equal(ev_g[f], ev_o[f]), f
+    assert np.array_equal(eng.agent_table(1).cpu().numpy().reshape(-1), o.q.reshape(128, -1, 4)[:, 400:, :].reshape(-1))
