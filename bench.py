@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=None, help="lockstep iterations per launch (= per bench step)")
     ap.add_argument("--instances", type=int, default=None, help="environment instances per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="target CPU time of one CPU sample (default: 12 s for cpu_baseline, 60 s / steps for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -174,7 +175,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     procs = os.cpu_count() or 1
-    per_step = max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step = args.cpu_seconds if args.cpu_seconds else max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
     vals, last = [], None
     for k in range(args.warmup + args.steps):
         last = cpu_port_throughput(args.workload, per_step, procs)
@@ -360,7 +361,7 @@ def run_gpu_arm(args):
         achieved = bytes_per * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_port_throughput(args.workload, args.cpu_seconds, os.cpu_count() or 1)
+            cpu = cpu_port_throughput(args.workload, args.cpu_seconds or 12.0, os.cpu_count() or 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
