@@ -64,10 +64,8 @@ class RewardMachine:
         return order
 
     def _generate_state_indices(self):
-        rest = set(self._states_in_order())
-        rest.add(self.current_state)
-        rest.discard(self.current_state)
-        ordered = [self.current_state] + sorted(rest)
+        rest = set(self._states_in_order()) - {self.current_state}
+        ordered = [self.current_state] + sorted(rest)  # initial state first, the others in sorted order
         return {s: i for i, s in enumerate(ordered)}
 
     def _get_start_state(self):
