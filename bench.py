@@ -342,6 +342,52 @@ def run_gpu_arm(args):
     h2d = host_slot.numel() * 8 + host_eps.numel() * 8
     d2h = host_stats.numel() + host_slot.numel() * 8 + host_eps.numel() * 8
 
+    # ---- secondary: the call-by-call API (the reference's granularity) end to end on host buffers --------------------------
+    # per iteration: select_action -> actions to the host and back (a user hands env.step host actions) -> step ->
+    # observations / rewards / done flags to the host -> update_policy -> reset of finished instances
+    stepwise = None
+    if world == 1 and args.workload in ("cfg3", "cfg3_ql"):
+        from multiagent_rlrm_b200.vec import BatchedRMEnvironment
+
+        env = BatchedRMEnvironment(c, args.instances, device=dev)
+        h_act = torch.empty((args.instances, c.n_agents), dtype=torch.uint8).pin_memory()
+        h_cell = torch.empty((args.instances, c.n_agents), dtype=torch.int64).pin_memory()
+        h_rew = torch.empty((args.instances, c.n_agents), dtype=torch.float64).pin_memory()
+        h_done = torch.empty((args.instances, c.n_agents), dtype=torch.bool).pin_memory()
+        fl = sc.driver == "frozen_lake_main"
+
+        def loop(n):
+            states, _ = env.reset()
+            for _ in range(n):
+                actions = env.select_action(states)
+                h_act.copy_(actions, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                actions = h_act.to(dev, non_blocking=True)
+                new_states, rewards, term, trunc, infos = env.step(actions)
+                h_cell.copy_(new_states["cell"], non_blocking=True)
+                h_rew.copy_(rewards, non_blocking=True)
+                h_done.copy_(term | trunc, non_blocking=True)
+                env.update_policy(env.driver_states(states, new_states), actions, rewards, new_states,
+                                  (term | trunc) if fl else term, infos)
+                states = new_states
+                over = env.episode_over(term, trunc)
+                env.reset(mask=over)
+                states = env._obs(env._cells())
+                torch.cuda.current_stream(dev).synchronize()
+
+        loop(20)
+        a0 = env.engine.total_active_steps()
+        n_loop = 200
+        torch.cuda.synchronize(dev)
+        ts = time.perf_counter()
+        loop(n_loop)
+        dt = time.perf_counter() - ts
+        stepwise = {"value": (env.engine.total_active_steps() - a0) / dt, "unit": UNIT, "iterations": n_loop,
+                    "us_per_iteration": dt / n_loop * 1e6,
+                    "h2d_bytes_per_iteration": h_act.numel(), "d2h_bytes_per_iteration": h_act.numel() + h_cell.numel() * 8 + h_rew.numel() * 8 + h_done.numel(),
+                    "api": "vec.BatchedRMEnvironment select_action / step / update_policy / reset (one C-ABI call each), host round trip every iteration"}
+        del env
+
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -371,6 +417,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_active / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "Engine.train_host -> rlrm_train_host (pinned host slot/epsilon in+out, stats out)"},
+            "e2e_call_by_call": stepwise,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args.workload), "peak_source": peak_src,

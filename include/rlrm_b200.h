@@ -279,7 +279,8 @@ int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_ce
  * integers, so the result does not depend on thread order or on how instances are spread over blocks/GPUs.
  * With a single instance this is exactly the per-instance learner (for reward machines whose counterfactual updates
  * do not read each other's writes, e.g. chains). rlrm_train runs two kernels per iteration in this mode.
- * Inter-GPU merging (every K iterations) is the caller's step: all-reduce `q` (see dist.py). */
+ * Inter-GPU merging (every K iterations) is the caller's step: average the replicas of `q` (dist.merge_replicas gathers
+ * them over NCCL and sums in rank order, so the result does not depend on the collective's reduction order). */
 
 /* One launch = n_iters lockstep iterations of the driver loop (select for all agents -> wrapper step -> update for
  * all agents -> per-instance auto reset when the episode ends), state in registers, Philox draws for iterations
