@@ -265,6 +265,20 @@ int rlrm_rm_step(rlrm_handle_t* h, int64_t n_slots, uint8_t* q, const uint16_t* 
 int rlrm_rm_step_agent(rlrm_handle_t* h, int agent, int64_t n_slots, uint8_t* q, const uint16_t* cell, uint8_t* event_out,
                        double* reward_out, void* stream);
 
+/* RMEnvironmentWrapper.get_mdp (rm_environment_wrapper.py:185-283): the product MDP of agent `agent` (grid cell x RM
+ * state), every (encoded state s, nominal action a, sub-action j) in one launch. The reference builds it with
+ * reset(seed) + env.set_state + one step per triple with env.stochastic forced to False, so each sub-action is executed
+ * as is (a blocked OfficeWorld move still becomes "wait" + wall penalty, ma_office.py:311-325).
+ * sub_actions: HOST uint8 [4][n_sub], the sub-action lists of get_action_distribution (ma_frozen_lake.py:337-351,
+ * ma_office.py:434-453) as action indices, RLRM_ACTION_WAIT allowed; n_sub in 1..4.
+ * rm_terminal: treat "RM state == final state" as terminal (is_terminal_state_mdp, ma_office.py:424-428).
+ * Outputs, device, index (s*4 + a)*n_sub + j with S = width*height*n_rm_states(agent):
+ *   next_state int32 (encoded), reward f64 (env + RM reward * reward_modifier), done u8 (terminated or truncated);
+ *   terminal u8 [S]: 0 = not terminal, 1 = hazard cell (hole / terminating plant), 2 = RM final state. Terminal states
+ *   self-loop with the terminal reward (hole / plant penalty, or 0) in every (a, j) entry. */
+int rlrm_mdp(rlrm_handle_t* h, int agent, int n_sub, const uint8_t* sub_actions, int rm_terminal, int32_t* next_state,
+             double* reward, uint8_t* done, uint8_t* terminal, void* stream);
+
 /* AgentRL.update_policy (agent_rl.py:117-192) -> QLearning.update (qlearning.py:41-110, incl. the QRM
  * counterfactual loop fed by rm_environment_wrapper.py:122-183) or QLearningLambda.update (qlearning_lambda.py:33-84).
  * obs_cell: device uint16 [N*A], the `state` argument the driver passes (previous observation);

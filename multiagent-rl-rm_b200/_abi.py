@@ -183,6 +183,7 @@ EXPORTED_SYMBOLS = (
     "rlrm_step",
     "rlrm_rm_step",
     "rlrm_rm_step_agent",
+    "rlrm_mdp",
     "rlrm_update",
     "rlrm_train",
     "rlrm_train_host",

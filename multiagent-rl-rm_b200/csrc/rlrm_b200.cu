@@ -351,6 +351,30 @@ extern "C" int rlrm_rm_step_agent(rlrm_handle_t* h, int agent, int64_t n_slots, 
   return RLRM_OK;
 }
 
+extern "C" int rlrm_mdp(rlrm_handle_t* h, int agent, int n_sub, const uint8_t* sub_actions, int rm_terminal, int32_t* next_state,
+                        double* reward, uint8_t* done, uint8_t* terminal, void* stream) {
+  if (!h || !sub_actions || !next_state || !reward || !done || !terminal) return fail(RLRM_ERR_ARG, "null argument");
+  if (agent < 0 || agent >= h->kp.A) return fail(RLRM_ERR_ARG, "agent out of range");
+  if (n_sub < 1 || n_sub > 4) return fail(RLRM_ERR_ARG, "n_sub must be 1..4");
+  MdpSub sub;
+  for (int a = 0; a < 4; a++)
+    for (int j = 0; j < 4; j++) {
+      const int v = j < n_sub ? sub_actions[a * n_sub + j] : RLRM_ACTION_WAIT;
+      if (v > RLRM_ACTION_WAIT) return fail(RLRM_ERR_ARG, "sub-action out of range");
+      sub.a[a * 4 + j] = (unsigned char)v;
+    }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int nQ = h->kp.per_agent ? h->kp.a_nQ[agent] : h->kp.nQ;
+  const long long n = (long long)h->kp.ncell * nQ * 4 * n_sub;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE)
+    mdp_kernel<RLRM_ENV_FROZEN_LAKE><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, agent, n_sub, sub, rm_terminal, next_state, reward, done, terminal);
+  else
+    mdp_kernel<RLRM_ENV_OFFICE_WORLD><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, agent, n_sub, sub, rm_terminal, next_state, reward, done, terminal);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
 extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_cell, const uint8_t* actions,
                            const uint8_t* term_arg, const rlrm_step_out_t* out, void* stream) {
   int rc = check_state(h, st, true);

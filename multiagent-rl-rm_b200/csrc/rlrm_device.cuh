@@ -193,7 +193,9 @@ struct Rec {
 
 // env.step + check_terminations + RewardMachine.step + wrapper merge for ONE agent. Every quantity an agent needs is
 // its own (the shared env.timestep is replicated per agent), so lanes never exchange data here.
-template <int ENV, int STOCH = -1>  // STOCH: -1 = read p.stochastic at run time, 0/1 = compile-time
+// WAIT_OK: the caller may pass RLRM_ACTION_WAIT itself (env.wait_action through the call-by-call API and the "wait"
+// sub-action of get_mdp); the fused kernels only ever select 0..3 and skip the test.
+template <int ENV, int STOCH = -1, bool WAIT_OK = false>  // STOCH: -1 = read p.stochastic at run time, 0/1 = compile-time
 __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, int action, unsigned w3, bool with_rm, Rec& r) {
   const bool stochastic = STOCH < 0 ? (p.stochastic != 0) : (STOCH != 0);
   r.prev_cell = s.cell;
@@ -206,7 +208,7 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
     const bool rm_done = p.rm_final >= 0 && (int)s.rm == p.rm_final;  // ma_frozen_lake.py:107-115
     if (active && !rm_done) {
       int ex = action;
-      if (stochastic) ex = slip_outcome(p, action, w3);
+      if (stochastic && (!WAIT_OK || action != RLRM_ACTION_WAIT)) ex = slip_outcome(p, action, w3);
       if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
       if (tb.cell_flags[s.cell] & 1) {  // holes_in_the_ice
         s.flags |= RLRM_FLAG_FAIL;
@@ -220,7 +222,8 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
     if (active) {  // ma_office.py:143-186
       int ex = action;
       double wall_pen = 0.0;
-      if (tb.next_cell[s.cell * 4 + action] == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
+      // is_wall_collision("wait") is False (ma_office.py:299-300)
+      if ((!WAIT_OK || action != RLRM_ACTION_WAIT) && tb.next_cell[s.cell * 4 + action] == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
         if (p.terminate_hit_walls) s.flags |= RLRM_FLAG_FAIL;
         wall_pen = p.wall_penalty;
         ex = RLRM_ACTION_WAIT;

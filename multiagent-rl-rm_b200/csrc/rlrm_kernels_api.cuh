@@ -90,9 +90,58 @@ __global__ void __launch_bounds__(256) step_kernel(KP p_in, DState st, const uns
     }
   }
   Rec r;
-  agent_step<ENV>(p, tb, s, actions[k], w3, with_rm != 0, r);
+  agent_step<ENV, -1, true>(p, tb, s, min((int)actions[k], RLRM_ACTION_WAIT), w3, with_rm != 0, r);
   st.slot[k] = pack_slot(s);
   store_rec(out, k, r);
+}
+
+// RMEnvironmentWrapper.get_mdp (rm_environment_wrapper.py:185-283): every (encoded state, nominal action, sub-action) of one
+// agent's product MDP in one launch. The reference does reset(seed) + set_state + one step with env.stochastic = False per
+// triple; here each thread builds the freshly-reset slot (active, no failure, agent_steps = timestep = 0) at its (cell, RM
+// state) and runs the same agent_step the training kernels use, executing the sub-action as is.
+struct MdpSub {
+  unsigned char a[16];  // [nominal action][sub-action index]
+};
+template <int ENV>
+__global__ void __launch_bounds__(256) mdp_kernel(KP p_in, int agent, int n_sub, MdpSub sub, int rm_terminal, int* next_state,
+                                                 double* reward, unsigned char* done, unsigned char* terminal) {
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
+  if (p_in.per_agent) agent_view(p_in, p, tb, agent);
+  const long long n = (long long)p.ncell * p.nQ * 4 * n_sub;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int j = (int)(k % n_sub);
+  const int a = (int)((k / n_sub) & 3);
+  const int enc = (int)(k / (4 * n_sub));
+  const unsigned cell = enc / p.nQ, q = enc - cell * p.nQ;
+  // is_terminal_state_mdp (ma_frozen_lake.py:321-335, ma_office.py:411-432): hazard first, then the RM's final state
+  int kind = 0;
+  double term_reward = 0.0;
+  if ((tb.cell_flags[cell] & 1) && (ENV == RLRM_ENV_FROZEN_LAKE || p.terminate_on_plants)) {
+    kind = 1;
+    term_reward = p.hole_penalty;
+  } else if (rm_terminal && p.rm_final >= 0 && (int)q == p.rm_final) {
+    kind = 2;
+  }
+  if (a == 0 && j == 0) terminal[enc] = (unsigned char)kind;
+  if (kind) {  // self-loop (rm_environment_wrapper.py:232-236)
+    next_state[k] = enc;
+    reward[k] = term_reward;
+    done[k] = 1;
+    return;
+  }
+  Slot s;
+  s.cell = cell;
+  s.steps = 0;
+  s.time = 0;
+  s.rm = q;
+  s.flags = RLRM_FLAG_ACTIVE;
+  Rec r;
+  agent_step<ENV, 0, true>(p, tb, s, min((int)sub.a[a * 4 + j], RLRM_ACTION_WAIT), 0u, true, r);
+  next_state[k] = (int)(r.cell * p.nQ + r.q);
+  reward[k] = r.reward;
+  done[k] = (r.term || r.trunc) ? 1 : 0;
 }
 
 // RewardMachine.step on explicit (state, position) pairs (reward_machine.py:45-59)

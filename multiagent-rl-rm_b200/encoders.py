@@ -43,7 +43,15 @@ class StateEncoderFrozenLake(_GridStateEncoder):
 
 
 class StateEncoderOfficeWorld(_GridStateEncoder):
-    pass
+    def decode(self, encoded_state):
+        """(position dict, RM state LABEL) — state_encoder_office.py:37-66; FrozenLake's decode returns an info dict instead
+        (state_encoder_frozen_lake.py:50-86), which is what makes get_mdp degenerate there (see wrapper.get_mdp)."""
+        width, height, n_rm = self._dims()
+        total = width * height * n_rm
+        if encoded_state < 0 or encoded_state >= total:
+            raise ValueError(f"Encoded state {encoded_state} out of range [0..{total - 1}].")
+        pos, info = super().decode(encoded_state)
+        return pos, info["q"]
 
 
 def encode_state(agent, state, state_reward_machine):

@@ -143,6 +143,25 @@ class Engine:
         check(self.L.rlrm_rm_step_agent(self.h, int(agent), q.numel(), _ptr(q), _ptr(cell), _ptr(ev), _ptr(r), self._stream()))
         return q, ev, r
 
+    def mdp(self, agent: int, sub_actions, rm_terminal: bool = True):
+        """Product MDP of agent `agent` in one launch (rlrm_mdp; RMEnvironmentWrapper.get_mdp, rm_environment_wrapper.py:185-283).
+        sub_actions: [4][n_sub] action indices (4 = wait). Returns numpy (next_state [S,4,n_sub] i32, reward f64, done u8,
+        terminal [S] u8)."""
+        import numpy as np
+
+        sub = np.ascontiguousarray(sub_actions, dtype=np.uint8)
+        if sub.ndim != 2 or sub.shape[0] != 4:
+            raise ValueError("sub_actions must be [4][n_sub]")
+        n_sub = sub.shape[1]
+        S = self.agent_rows[agent] if self.cfg.per_agent_rm else self.S
+        nxt = torch.empty((S, 4, n_sub), dtype=torch.int32, device=self.device)
+        rew = torch.empty((S, 4, n_sub), dtype=torch.float64, device=self.device)
+        done = torch.empty((S, 4, n_sub), dtype=torch.uint8, device=self.device)
+        term = torch.empty(S, dtype=torch.uint8, device=self.device)
+        check(self.L.rlrm_mdp(self.h, int(agent), n_sub, sub.ctypes.data, int(rm_terminal), _ptr(nxt), _ptr(rew), _ptr(done),
+                              _ptr(term), self._stream()))
+        return nxt.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), term.cpu().numpy()
+
     def agent_table(self, a: int) -> torch.Tensor:
         """learner.q_table of agent a for every instance: [N, S_a, 4] (shared learner: [S_a, 4])."""
         self.sync_tables()

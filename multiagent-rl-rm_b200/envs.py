@@ -125,8 +125,10 @@ class BaseEnvironment:
         for a in self.agents:
             act = actions[a.name]
             name = act if isinstance(act, str) else act.name
-            if name not in _A2I or name == "wait":
+            if name not in _A2I:
                 raise ValueError(f"Invalid action: {name}")
+            if name == "wait" and getattr(self, "frozen_lake_stochastic", False):
+                raise KeyError(name)  # the slippery FrozenLake action map has no "wait" entry (ma_frozen_lake.py:283-296)
             acts.append(_A2I[name])
         eng.slot.copy_(self._pack_slots())
         rec = eng.step(torch.tensor(acts, dtype=torch.uint8), t=0, draws=self._slip_words().to(eng.device), with_rm=with_rm)

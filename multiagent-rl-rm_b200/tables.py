@@ -157,6 +157,15 @@ def slip_table(env: str, stochastic: bool, delay_action: bool, all_slip: bool, h
     return [[a, perp[a][0], perp[a][1]] for a in range(4)], [hp, lp, lp]
 
 
+def mdp_action_distribution(sc: "Scenario"):
+    """(sub-actions[4][n], probabilities[n]) RMEnvironmentWrapper.get_mdp works with (rm_environment_wrapper.py:196-197, 244):
+    OfficeWorld's ``stochastic`` flag is forced off first, so only ``delay_action`` keeps a real distribution there
+    (ma_office.py:333-347); FrozenLake's map follows ``frozen_lake_stochastic`` (ma_frozen_lake.py:264-296)."""
+    if sc.env == "frozen_lake":
+        return slip_table(sc.env, bool(sc.stochastic), bool(sc.delay_action), False, 0.8)
+    return slip_table(sc.env, bool(sc.delay_action), bool(sc.delay_action), False, sc.high_prob)
+
+
 def slip_thresholds(probabilities: Sequence[float]) -> List[int]:
     """Integer thresholds T_j = ceil(cdf_j * 2^32): for a 32-bit draw k, u = k / 2^32,
     numpy's ``cdf.searchsorted(u, side='right')`` equals ``#{j : k >= T_j}`` exactly."""

@@ -1,12 +1,30 @@
 """RMEnvironmentWrapper — mirrors multi_agent/wrappers/rm_environment_wrapper.py:4-183 (reset, step, QRM experiences).
 `step` is ONE device call (env.step + RewardMachine.step + merge, rlrm_step with_rm=1); the QRM counterfactual
-transitions reported in infos["qrm_experience"] come from rlrm_rm_step on the same tables. get_mdp (VI tooling) is
-out of scope."""
+transitions reported in infos["qrm_experience"] come from rlrm_rm_step on the same tables. get_mdp
+(rm_environment_wrapper.py:185-283) is ONE rlrm_mdp launch per agent instead of reset + set_state + step per
+(state, action, sub-action)."""
 from __future__ import annotations
 
 import torch
 
-from .envs import _num
+from .envs import _A2I, _num
+
+
+def assemble_mdp(next_state, reward, done, terminal, probabilities, empty_nonterminal=False):
+    """Arrays of rlrm_mdp ([S,4,n_sub] + terminal [S]) -> the reference's P[s][a] = [(prob, s', reward, done), ...]
+    (rm_environment_wrapper.py:218-276): terminal states carry one self-loop entry with probability 1.0.
+    probabilities: per nominal action, the list matching that action's sub-actions."""
+    S = next_state.shape[0]
+    P = {}
+    for s in range(S):
+        if terminal[s]:
+            P[s] = {a: [(1.0, s, _num(reward[s, a, 0]), True)] for a in range(4)}
+        elif empty_nonterminal:
+            P[s] = {a: [] for a in range(4)}
+        else:
+            P[s] = {a: [(probabilities[a][j], int(next_state[s, a, j]), _num(reward[s, a, j]), bool(done[s, a, j]))
+                        for j in range(len(probabilities[a]))] for a in range(4)}
+    return P
 
 
 class RMEnvironmentWrapper:
@@ -48,6 +66,41 @@ class RMEnvironmentWrapper:
             info["rm_terminated"] = bool(rec["rm_term"][i])
             terminations[agent.name] = bool(rec["term"][i])
         return observations, rewards, terminations, env_trunc, infos
+
+    def get_mdp(self, seed, repaired=False):
+        """Transition model of every agent's product MDP: (all_P, all_num_states, all_num_actions), same structure and
+        values as the reference (rm_environment_wrapper.py:185-283), including its side effects: env.stochastic is
+        switched off and stays off (:196-197), and the wrapper ends freshly reset (:282).
+
+        FrozenLake: the reference's StateEncoderFrozenLake.decode hands back an info DICT where get_mdp expects the RM
+        state (state_encoder_frozen_lake.py:80-86), so every step raises inside its try/except (:259-264) and P keeps
+        EMPTY outcome lists for all non-hole states, with the RM's final state never terminal. That is reproduced as is;
+        ``repaired=True`` (an extension, not reference behaviour) builds the MDP the way OfficeWorld's is built."""
+        if hasattr(self.env, "stochastic"):
+            self.env.stochastic = False
+        width = getattr(self.env, "map_width", None) or self.env.grid_width
+        height = getattr(self.env, "map_height", None) or self.env.grid_height
+        all_P, all_num_states, all_num_actions = {}, {}, {}
+        for idx, agent in enumerate(self.env.agents):
+            rm = agent.get_reward_machine()
+            num_states = width * height * rm.numbers_state()
+            actions_list = agent.get_actions()
+            if len(actions_list) != 4:
+                raise NotImplementedError("get_mdp supports the 4-action grid agents")
+            _pos, rm_state0 = agent.encoder.decode(0)
+            degenerate = isinstance(rm_state0, dict) and not repaired
+            dists = [self.env.get_action_distribution(a) for a in actions_list]
+            n_sub = max(len(d[0]) for d in dists)
+            sub = [[_A2I[getattr(x, "name", x)] for x in d[0]] + [_A2I["wait"]] * (n_sub - len(d[0])) for d in dists]
+            eng = self.env._get_engine(self.reward_modifier)
+            nxt, rew, done, term = eng.mdp(idx, sub, rm_terminal=not degenerate)
+            if nxt.shape[0] != num_states:
+                raise RuntimeError("state-space size mismatch between the encoder and the compiled tables")
+            all_P[agent.name] = assemble_mdp(nxt, rew, done, term, [list(d[1]) for d in dists], empty_nonterminal=degenerate)
+            all_num_states[agent.name] = num_states
+            all_num_actions[agent.name] = len(actions_list)
+        self.reset(seed)
+        return all_P, all_num_states, all_num_actions
 
     def _get_qrm_experiences(self, agent, current_state, next_state, action, env_reward, next_rm_state, env_termination):
         """Counterfactual transitions for every RM state in get_all_states()[:-1] (rm_environment_wrapper.py:122-183);

@@ -150,6 +150,19 @@ class Oracle:
                                C.c_int32(n_iters), C.c_int32(n_episodes), C.c_double(gamma), C.c_double(optimal_steps))
         return ev
 
+    def mdp(self, agent, sub_actions, rm_terminal=True):
+        """RMEnvironmentWrapper.get_mdp restated (oracle_mdp): arrays indexed [s, a, j] + terminal kind per state."""
+        sub = np.ascontiguousarray(sub_actions, dtype=np.uint8)
+        n_sub = sub.shape[1]
+        S = self.c.agent_rows[agent] if self.cfg.per_agent_rm else self.S
+        nxt = np.zeros((S, 4, n_sub), dtype=np.int32)
+        rew = np.zeros((S, 4, n_sub), dtype=np.float64)
+        done = np.zeros((S, 4, n_sub), dtype=np.uint8)
+        term = np.zeros(S, dtype=np.uint8)
+        self.L.oracle_mdp(C.byref(self.cfg), C.byref(self.tables), C.c_int(agent), C.c_int(n_sub), C.c_void_p(_p(sub)),
+                          C.c_int(int(rm_terminal)), C.c_void_p(_p(nxt)), C.c_void_p(_p(rew)), C.c_void_p(_p(done)), C.c_void_p(_p(term)))
+        return nxt, rew, done, term
+
     def total_active_steps(self):
         """finished episodes' env.agent_steps (stats) + the running episodes' agent_steps (slot words)"""
         running = (self.slot >> np.uint64(abi.SLOT_STEPS_SHIFT)) & np.uint64(0xFFFF)

@@ -217,7 +217,7 @@ static void step_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, con
       int rm_done = fin >= 0 && (int)s[a].rm == fin; /* ma_frozen_lake.py:107-115 */
       if (active && !rm_done) {
         int act = act_i[a], ex = act;
-        if (cfg->stochastic) { get_draws(cfg, draws, t, i, a, w); ex = slip(cfg, act, w[3]); }
+        if (cfg->stochastic && act != RLRM_ACTION_WAIT) { get_draws(cfg, draws, t, i, a, w); ex = slip(cfg, act, w[3]); }
         if (ex != RLRM_ACTION_WAIT) s[a].cell = tb->next_cell[s[a].cell * 4 + ex]; /* :121-126, 224-242 */
         if (tb->cell_flags[s[a].cell] & 1) { s[a].flags |= RLRM_FLAG_FAIL; r->renv = cfg->hole_penalty; } /* :174-187 */
         s[a].steps++;
@@ -227,7 +227,8 @@ static void step_instance(const rlrm_config_t* cfg, const rlrm_tables_t* tb, con
       if (active) { /* ma_office.py:143-186 (no RM-final test: a finished agent keeps moving) */
         int act = act_i[a], ex = act;
         double wall_pen = 0.0;
-        if (tb->next_cell[s[a].cell * 4 + act] == s[a].cell) { /* is_wall_collision -> "wait", no slip draw (:311-325) */
+        /* is_wall_collision -> "wait", no slip draw (:311-325); a "wait" action itself never collides (:299-300) */
+        if (act != RLRM_ACTION_WAIT && tb->next_cell[s[a].cell * 4 + act] == s[a].cell) {
           if (cfg->terminate_hit_walls) s[a].flags |= RLRM_FLAG_FAIL;
           wall_pen = cfg->wall_penalty; ex = RLRM_ACTION_WAIT;
         }
@@ -312,6 +313,53 @@ int oracle_step(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_st
     step_instance(cfg, tb, st, i, actions + (size_t)i * cfg->n_agents, draws, t, with_rm, rec);
     clear_first(cfg, st, i);
     for (int a = 0; a < cfg->n_agents; a++) store_rec(out, (size_t)i * cfg->n_agents + a, &rec[a]);
+  }
+  return 0;
+}
+
+/* ---- RMEnvironmentWrapper.get_mdp (rm_environment_wrapper.py:185-283) ----------------------------------------------
+ * Follows the reference's procedure literally: for every encoded state of `agent`, skip terminal states
+ * (is_terminal_state_mdp: ma_frozen_lake.py:321-335, ma_office.py:411-432); otherwise for every nominal action and
+ * every sub-action: reset the instance (wrapper.reset), overwrite the agent's position / RM state (env.set_state),
+ * step once with env.stochastic = False, the other agents doing anything (their moves cannot touch this agent), and
+ * record (next encoded state, reward, terminated or truncated). */
+int oracle_mdp(const rlrm_config_t* cfg_in, const rlrm_tables_t* tb, int agent, int n_sub, const uint8_t* sub_actions,
+               int rm_terminal, int32_t* next_state, double* reward, uint8_t* done, uint8_t* terminal) {
+  rlrm_config_t cfg = *cfg_in;
+  cfg.stochastic = 0;   /* rm_environment_wrapper.py:196-197 */
+  cfg.random_starts = 0; /* set_state overrides this agent's start; the others' positions are irrelevant */
+  int A = cfg.n_agents;
+  arm_t v = agent_rm(&cfg, tb, agent);
+  int nQ = v.nQ, ncell = cfg.width * cfg.height;
+  uint64_t slot[RLRM_MAX_AGENTS];
+  double eps[RLRM_MAX_AGENTS], ret[RLRM_MAX_AGENTS];
+  rlrm_state_t st;
+  memset(&st, 0, sizeof(st));
+  st.n_instances = 1; st.slot = slot; st.epsilon = eps; st.ep_return = ret;
+  rec_t rec[RLRM_MAX_AGENTS];
+  uint8_t acts[RLRM_MAX_AGENTS];
+  for (int enc = 0; enc < ncell * nQ; enc++) {
+    int cell = enc / nQ, q = enc % nQ;
+    int kind = 0; double tr = 0.0;
+    if ((tb->cell_flags[cell] & 1) && (cfg.env_kind == RLRM_ENV_FROZEN_LAKE || cfg.terminate_on_plants)) { kind = 1; tr = cfg.hole_penalty; }
+    else if (rm_terminal && v.final >= 0 && q == v.final) kind = 2;
+    terminal[enc] = (uint8_t)kind;
+    for (int a = 0; a < 4; a++)
+      for (int j = 0; j < n_sub; j++) {
+        size_t k = ((size_t)enc * 4 + a) * n_sub + j;
+        if (kind) { next_state[k] = enc; reward[k] = tr; done[k] = 1; continue; }
+        for (int b = 0; b < A; b++) { eps[b] = cfg.epsilon_start; slot[b] = 0; }
+        reset_instance_at(&cfg, tb, &st, 0, 0);
+        slot_t s = unpack(slot[agent]);
+        s.cell = (uint32_t)cell; s.rm = (uint32_t)q;
+        slot[agent] = pack(s);
+        memset(acts, 0, sizeof(acts));
+        acts[agent] = sub_actions[a * n_sub + j];
+        step_instance(&cfg, tb, &st, 0, acts, NULL, 0, 1, rec);
+        next_state[k] = (int32_t)(rec[agent].cell * nQ + rec[agent].q);
+        reward[k] = rec[agent].reward;
+        done[k] = (uint8_t)(rec[agent].term || rec[agent].trunc);
+      }
   }
   return 0;
 }

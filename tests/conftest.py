@@ -17,8 +17,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    """Training-trace fixtures (eval_*.npz are evaluation fixtures, see tests/test_eval.py)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("eval_"))
+    """Training-trace fixtures (eval_*.npz: tests/test_eval.py, mdp_*.npz: tests/test_mdp.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith(("eval_", "mdp_")))
 
 
 def load_golden(name):
