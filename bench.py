@@ -55,7 +55,7 @@ WORKLOADS = {
              65536, 2048, 140, "train_qrm4_kernel<FrozenLake>"),
     "cfg3_ql": ("FrozenLake map1, 2 agents, slippery, RM A->B->C, QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False, "
                 "per-instance Q tables, auto-reset",
-                "configs[2] companion (plain Q-learning variant, SURVEY.md §8d)", 65536, 2048, 36, "train_kernel<FrozenLake,QL>"),
+                "configs[2] companion (plain Q-learning variant, SURVEY.md §8d)", 65536, 2048, 36, "train_ql_fast_kernel<FrozenLake>"),
     "cfg4": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, plants -100, synthetic 12-state completed chain RM (108 "
              "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, SPARSE-EXACT traces (live entries only; "
              "bit-identical to the dense sweep)",

@@ -38,6 +38,7 @@ struct rlrm_handle {
   int smem_bytes;
   long long launches;
   int qrm4_fast;  // train_qrm4_kernel is applicable (see its header comment)
+  int ql_fast;    // train_ql_fast_kernel is applicable (see its header comment)
   int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
   int shared_smem_bytes;
   int num_sms;
@@ -189,6 +190,8 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
+  h->ql_fast = (kp.algo == RLRM_ALGO_QL && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
+                !(cfg->reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   {
     const long long n_ent = (long long)kp.A * kp.S4;
@@ -225,7 +228,7 @@ extern "C" int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double g
   if (h->cfg.algo == RLRM_ALGO_QLAMBDA && learning_rate < 0) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) needs a fixed learning rate");
   h->cfg.learning_rate = learning_rate; h->cfg.gamma = gamma; h->cfg.lambd = lambd;
   fill_learner(h->kp, learning_rate, gamma, lambd);
-  if (learning_rate < 0.0) h->qrm4_fast = 0;
+  if (learning_rate < 0.0) h->qrm4_fast = h->ql_fast = 0;
   return RLRM_OK;
 }
 
@@ -430,6 +433,22 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
         default: RLRM_QRM4(true, true, true); break;
       }
 #undef RLRM_QRM4
+    }
+    else if (kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
+      const DState d = dstate(st);
+#define RLRM_QLF(ST, LE, TR) train_ql_fast_kernel<ENV, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace)
+      const int key = (kp.stochastic ? 4 : 0) | (learn ? 2 : 0) | (trace ? 1 : 0);
+      switch (key) {
+        case 0: RLRM_QLF(false, false, false); break;
+        case 1: RLRM_QLF(false, false, true); break;
+        case 2: RLRM_QLF(false, true, false); break;
+        case 3: RLRM_QLF(false, true, true); break;
+        case 4: RLRM_QLF(true, false, false); break;
+        case 5: RLRM_QLF(true, false, true); break;
+        case 6: RLRM_QLF(true, true, false); break;
+        default: RLRM_QLF(true, true, true); break;
+      }
+#undef RLRM_QLF
     }
     else if (kp.algo == RLRM_ALGO_QRM) {
       if (kp.per_agent) RLRM_TRAIN(RLRM_ALGO_QRM, true); else RLRM_TRAIN(RLRM_ALGO_QRM, false);

@@ -6,6 +6,9 @@
 // fused persistent kernel: n_iters lockstep iterations, state in registers
 // ------------------------------------------------------------------------------------------------
 #define TRAIN_BLOCK 128
+#ifndef QLF_MINB
+#define QLF_MINB 8
+#endif
 
 template <int ENV, int ALGO, bool PA>
 __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
@@ -280,6 +283,117 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState
       reset_slot<false>(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
       load_block4(Q, s.cell, B, bmax);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: plain Q-learning with a private table per (instance, agent), fixed learning rate, no visit counts, no shaping
+// (BASELINE config 3's `use_qrm=0, lr=0.1` variant). Same algorithm as train_kernel's row-carry branch — the row of the
+// agent's current state stays in registers, one 16-byte load of Q[s'] and at most one 4-byte store per step — with the
+// run-time switches (stochastic / learn / trace / per-agent views / random starts / shared accumulators) compiled out.
+// ------------------------------------------------------------------------------------------------
+template <int ENV, bool STOCH, bool LEARN, bool TRACE>
+__global__ void __launch_bounds__(TRAIN_BLOCK, QLF_MINB) train_ql_fast_kernel(KP p, DState st, unsigned long long t0, int n_iters,
+                                                                   unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
+  float* Q = st.q;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  float4 row = make_float4(0.f, 0.f, 0.f, 0.f);  // Q[row_idx, :], the 1-entry register cache of the table
+  unsigned row_idx = 0;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    Q = st.q + table_base(p, i, a);
+    row_idx = s.cell * p.nQ + s.rm;
+    row = *reinterpret_cast<const float4*>(Q + (size_t)row_idx * 4);
+  }
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    if (valid) {
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);  // row_idx == enc(current state) here
+      const unsigned before = s.cell;
+      const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+      Rec r;
+      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
+      const unsigned snidx = r.cell * p.nQ + r.q;
+      float4 nrow = row;
+      if (snidx != row_idx) nrow = *reinterpret_cast<const float4*>(Q + (size_t)snidx * 4);
+      if (LEARN) {
+        // update_q (qlearning.py:70-79). `state` is the previous observation, except on an episode's first iteration under
+        // the FrozenLake driver where it aliases the new position (frozen_lake_main.py:337,359)
+        const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+        const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+        const unsigned sidx = obs * p.nQ + r.prev_q;
+        const float cur = (sidx == row_idx) ? get_component(row, action)
+                                             : ((sidx == snidx) ? get_component(nrow, action) : Q[(size_t)sidx * 4 + action]);
+        const float mf = __fmul_rn(term_arg ? 0.0f : 1.0f, row_max(nrow));
+        const float inner = __fadd_rn(__double2float_rn(r.reward), __fmul_rn(p.gamma_f, mf));
+        const float out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+        if (__float_as_uint(out) != __float_as_uint(cur)) Q[(size_t)sidx * 4 + action] = out;
+        if (sidx == snidx) set_component(nrow, action, out);
+      }
+      row = nrow;  // the next state's row is the one the next selection reads
+      row_idx = snidx;
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      if (TRACE)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    unsigned flags2 = (term ? 1u : 0u) | (trunc ? 2u : 0u);
+    for (int o = 1; o < p.G; o <<= 1) flags2 &= __shfl_xor_sync(0xFFFFFFFFu, flags2, o);
+    const bool over = flags2 != 0u;
+    if (valid && over) {
+      episodes++;
+      active_steps += s.steps;  // env.agent_steps[agent] of the finished episode
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot<false>(p, tb, i, a, t + 1, s, eps);
+      explore_thr = explore_threshold(eps);
+      row_idx = s.cell * p.nQ + s.rm;
+      row = *reinterpret_cast<const float4*>(Q + (size_t)row_idx * 4);
     }
   }
   if (valid) {
