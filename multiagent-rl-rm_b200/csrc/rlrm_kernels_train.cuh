@@ -360,13 +360,20 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QLF_MINB) train_ql_fast_kernel(KP
         const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
         const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
         const unsigned sidx = obs * p.nQ + r.prev_q;
-        const float cur = (sidx == row_idx) ? get_component(row, action)
-                                             : ((sidx == snidx) ? get_component(nrow, action) : Q[(size_t)sidx * 4 + action]);
+        // branch-free component picks: lanes of a warp hold different actions, a switch would serialise them
+        const float row_a = sel4(row.x, row.y, row.z, row.w, (unsigned)action);
+        const float nrow_a = sel4(nrow.x, nrow.y, nrow.z, nrow.w, (unsigned)action);
+        float cur = (sidx == row_idx) ? row_a : nrow_a;
+        if (sidx != row_idx && sidx != snidx) cur = Q[(size_t)sidx * 4 + action];  // only the aliased first iteration gets here
         const float mf = __fmul_rn(term_arg ? 0.0f : 1.0f, row_max(nrow));
         const float inner = __fadd_rn(__double2float_rn(r.reward), __fmul_rn(p.gamma_f, mf));
         const float out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
         if (__float_as_uint(out) != __float_as_uint(cur)) Q[(size_t)sidx * 4 + action] = out;
-        if (sidx == snidx) set_component(nrow, action, out);
+        const bool same = sidx == snidx;  // the updated entry belongs to the row carried into the next iteration
+        nrow.x = (same && action == 0) ? out : nrow.x;
+        nrow.y = (same && action == 1) ? out : nrow.y;
+        nrow.z = (same && action == 2) ? out : nrow.z;
+        nrow.w = (same && action == 3) ? out : nrow.w;
       }
       row = nrow;  // the next state's row is the one the next selection reads
       row_idx = snidx;
