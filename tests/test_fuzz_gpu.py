@@ -141,3 +141,28 @@ def test_random_scenario_call_by_call_equals_fused(seed, cuda_device):
     assert bool((fused.q.view(torch.int32) == unfused.q.view(torch.int32)).all()), info
     if sc.algo == "qlambda":
         assert bool((fused.e.view(torch.int32) == unfused.e.view(torch.int32)).all()), info
+
+
+@pytest.mark.parametrize("seed", range(2, N_CASES, 4))
+def test_random_scenario_greedy_evaluation_equals_oracle(seed, cuda_device):
+    """rlrm_evaluate (test_policy_optima batched) after some training, on the same random scenarios."""
+    import oracle as O
+    from multiagent_rlrm_b200.engine import Engine
+
+    sc, opts = random_scenario(seed)
+    sc.shared_q = False
+    c = P.compile_scenario(sc)
+    eng = Engine(c, opts["n"])
+    eng.reset()
+    eng.train(opts["iters"])
+    o = O.Oracle(c, opts["n"], "f32")
+    o.reset()
+    o.q[...] = eng.q.cpu().numpy().reshape(o.q.shape)
+    o.slot[...] = eng.slot.cpu().numpy().view(np.uint64)
+    o.epsilon[...] = eng.epsilon.cpu().numpy()
+    ev_g = eng.evaluate(2, sc.gamma, 10.0, t0=5000)
+    ev_o = o.evaluate(2, sc.gamma, 10.0, t0=5000)
+    info = f"seed {seed}: {sc.env}/{sc.map_name} A={len(sc.starts)} {sc.algo}"
+    for f in ev_o.dtype.names:
+        if f != "reserved":
+            assert np.array_equal(ev_g[f], ev_o[f]), (info, f)
