@@ -121,7 +121,17 @@ class Engine:
         return out.view(self.N, self.A)
 
     def new_record(self) -> Dict[str, torch.Tensor]:
-        return {k: torch.zeros(self.N * self.A, dtype=_TORCH_DT[v], device=self.device) for k, v in abi.STEP_OUT_FIELDS.items()}
+        """Step-record arrays (rlrm_step_out_t) carved out of ONE allocation; rlrm_step writes every element of every field."""
+        n = self.N * self.A
+        fields = sorted(abi.STEP_OUT_FIELDS.items(), key=lambda kv: -_TORCH_DT[kv[1]].itemsize)  # widest first keeps alignment
+        pad = (-n) % 8
+        buf = torch.empty(sum((n + pad) * _TORCH_DT[v].itemsize for _k, v in fields), dtype=torch.uint8, device=self.device)
+        rec, off = {}, 0
+        for k, v in fields:
+            size = n * _TORCH_DT[v].itemsize
+            rec[k] = buf[off:off + size].view(_TORCH_DT[v])
+            off += (n + pad) * _TORCH_DT[v].itemsize
+        return {k: rec[k] for k in abi.STEP_OUT_FIELDS}
 
     def step(self, actions: torch.Tensor, t: Optional[int] = None, draws: Optional[torch.Tensor] = None, with_rm: bool = True,
              rec: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:

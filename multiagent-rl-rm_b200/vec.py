@@ -17,13 +17,34 @@ Mirrors RMEnvironmentWrapper (rm_environment_wrapper.py:28-107), AgentRL.select_
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from collections.abc import Mapping
+from typing import Callable, Dict, Optional, Tuple
 
 import torch
 
 from . import _abi as abi
 from .engine import Engine
 from .tables import Compiled, compile_scenario
+
+
+class LazyTensors(Mapping):
+    """Read-only dict of tensors whose entries are computed on first access. A driver that only needs the step's rewards
+    and done flags does not pay a kernel launch for every derived view (pos_x, pos_y, boolean casts, ...)."""
+
+    def __init__(self, makers: Dict[str, Callable[[], object]]):
+        self._makers = makers
+        self._cache: Dict[str, object] = {}
+
+    def __getitem__(self, key):
+        if key not in self._cache:
+            self._cache[key] = self._makers[key]()
+        return self._cache[key]
+
+    def __iter__(self):
+        return iter(self._makers)
+
+    def __len__(self):
+        return len(self._makers)
 
 
 class BatchedRMEnvironment:
@@ -40,9 +61,15 @@ class BatchedRMEnvironment:
     def _cells(self) -> torch.Tensor:
         return (self.engine.slot & 0xFFFF).view(self.n_envs, self.n_agents)
 
-    def _obs(self, cells: torch.Tensor) -> Dict[str, torch.Tensor]:
-        cells = cells.to(torch.int64) & 0xFFFF
-        return {"pos_x": cells % self.width, "pos_y": cells // self.width, "cell": cells}
+    def _obs(self, cells) -> Mapping:
+        """Observation dict {"pos_x", "pos_y", "cell"} ([N, A] int64) over a cell-index tensor (or a thunk producing one)."""
+        def cell():
+            c = cells() if callable(cells) else cells
+            return c.to(torch.int64) & 0xFFFF
+
+        obs = LazyTensors({})
+        obs._makers.update({"pos_x": lambda: obs["cell"] % self.width, "pos_y": lambda: obs["cell"] // self.width, "cell": cell})
+        return obs
 
     @property
     def rm_state(self) -> torch.Tensor:
@@ -83,15 +110,19 @@ class BatchedRMEnvironment:
 
     def step(self, actions: torch.Tensor):
         e = self.engine
-        self._first = ((e.slot >> abi.SLOT_FLAGS_SHIFT) & abi.FLAG_FIRST) != 0
+        fl_driver = self.compiled.config.driver == abi.DRIVER_FROZEN_LAKE_MAIN
+        slot_before = e.slot.clone() if fl_driver else None  # RLRM_FLAG_FIRST as of before the step (driver_states)
+        self._first = None if slot_before is None else (lambda: ((slot_before >> abi.SLOT_FLAGS_SHIFT) & abi.FLAG_FIRST) != 0)
         rec = e.step(actions.reshape(-1))
         e.t += 1
         self._rec = rec
         v = lambda x: x.view(self.n_envs, self.n_agents)  # noqa: E731
-        infos = {"prev_s": self._obs(v(rec["prev_cell"])), "s": self._obs(v(rec["cell"])), "Renv": v(rec["renv"]), "RQ": v(rec["rq"]),
-                 "prev_q": v(rec["prev_q"]), "q": v(rec["q"]), "event": v(rec["event"]), "env_terminated": v(rec["env_term"]).bool(),
-                 "rm_terminated": v(rec["rm_term"]).bool()}
-        return self._obs(v(rec["cell"])), v(rec["reward"]), v(rec["term"]).bool(), v(rec["trunc"]).bool(), infos
+        new_states = self._obs(v(rec["cell"]))
+        infos = LazyTensors({"prev_s": lambda: self._obs(v(rec["prev_cell"])), "s": lambda: new_states,
+                             "Renv": lambda: v(rec["renv"]), "RQ": lambda: v(rec["rq"]), "prev_q": lambda: v(rec["prev_q"]),
+                             "q": lambda: v(rec["q"]), "event": lambda: v(rec["event"]),
+                             "env_terminated": lambda: v(rec["env_term"]).bool(), "rm_terminated": lambda: v(rec["rm_term"]).bool()})
+        return new_states, v(rec["reward"]), v(rec["term"]).view(torch.bool), v(rec["trunc"]).view(torch.bool), infos
 
     def update_policy(self, states, actions, rewards, next_states, terminated, infos=None):
         """ag.update_policy(state, action, reward, next_state, terminated, infos=...) for every agent. `states` are the
@@ -112,8 +143,8 @@ class BatchedRMEnvironment:
         therefore already shows the NEW position (frozen_lake_main.py:337,359)."""
         if self.compiled.config.driver != abi.DRIVER_FROZEN_LAKE_MAIN or self._first is None:
             return states
-        first = self._first.view(self.n_envs, self.n_agents)
-        return {k: torch.where(first, new_states[k], states[k]) for k in states}
+        first = self._first().view(self.n_envs, self.n_agents)
+        return self._obs(lambda: torch.where(first, new_states["cell"], states["cell"]))
 
     # -- fused ---------------------------------------------------------------------------------------
     def train(self, n_iters: int, learn: bool = True):
