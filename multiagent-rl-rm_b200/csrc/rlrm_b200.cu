@@ -411,7 +411,7 @@ template <int ENV>
 static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int n_iters, int learn, uint32_t* trace, cudaStream_t s) {
   const KP& kp = h->kp;
   if (kp.algo == RLRM_ALGO_QLAMBDA && !st->e) {
-    train_qlambda_sparse_kernel<ENV><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    train_qlambda_sparse_kernel<ENV><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
   } else if (kp.algo == RLRM_ALGO_QLAMBDA) {
     train_qlambda_kernel<ENV><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
   } else {

@@ -142,40 +142,59 @@ __device__ __forceinline__ float trace_lookup(const float* Q, const TraceList& L
 }
 
 // write the listed values back and forget the list (traces wiped: reset_e_table / e_table.fill(0))
-__device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsigned len, int lane) {
-  for (unsigned j = lane; j < len; j += 32) {
+__device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsigned len, int lane, int stride = 32) {
+  for (unsigned j = lane; j < len; j += stride) {
     const unsigned id = L.idx[j];
     Q[id] = L.q[j];
     L.pos[id] = 0;
   }
 }
 
+// One WARP per instance, one lane GROUP per agent (LG = 32 / next_pow2(A) lanes: 32, 16, 8 or 4). The scalar part of a step
+// (Philox, epsilon-greedy, env / RM step, TD error) is computed per lane for the lane's own agent — redundantly inside a
+// group, but once per warp-instruction for all agents of the instance — and each group sweeps its own agent's list. The
+// previous one-warp-per-agent layout spent ~550 warp-instructions per agent-step at 79 % issue utilisation (ncu,
+// profiles/r01_sparse_qlambda_ncu.csv): the lists stay L1-resident for the n_iters of a launch, so the kernel is bound by
+// instruction issue, not by HBM. Episode-over detection is two warp ballots; no shared memory, no block barrier.
+#define QLS_BLOCK 128
 template <int ENV>
-__global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
-                                                                  unsigned* trace) {
+__global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                                        unsigned* trace) {
   Tab tb = stage_tables(p);
-  __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
-  const long long i = blockIdx.x;
-  const int a = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * (QLS_BLOCK / 32) + (threadIdx.x >> 5);
+  if (i >= st.N) return;  // whole warps leave; nothing below synchronises across warps
+  const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  const long long k = i * p.A + a;
-  Slot s = unpack_slot(st.slot[k]);
-  double eps = st.epsilon[k];
-  double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
-  float* Q = st.q + table_base(p, i, a);
+  const int LG = 32 >> p.g_shift;  // lanes per agent
+  const int a = lane / LG;         // this lane's agent (slot a >= A idles when A is not a power of two)
+  const int gl = lane - a * LG;    // lane within the agent's group
+  const bool valid = a < p.A;
+  const unsigned gmask = (LG == 32 ? FULL : ((1u << LG) - 1u)) << (a * LG);
+  const long long k = i * p.A + (valid ? a : 0);
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
+  float* Q = st.q + table_base(p, i, valid ? a : 0);
   TraceList L;
   L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
   L.e = st.tr_e + (size_t)k * (size_t)st.tr_cap;
   L.q = st.tr_q + (size_t)k * (size_t)st.tr_cap;
-  unsigned len = st.tr_len[k];
+  unsigned len = 0;
+  rlrm_stats_t z;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    len = st.tr_len[k];
+    if (st.stats) {
+      z = st.stats[k];
+      return_sum = z.return_sum;
+    }
+  }
   unsigned long long work = 0, active_steps = 0;
   unsigned episodes = 0, successes = 0, last_length = 0;
   float last_return = 0.f;
   bool had_episode = false;
-  rlrm_stats_t z;
-  if (st.stats) z = st.stats[k];
-  double return_sum = st.stats ? z.return_sum : 0.0;
   unsigned long long explore_thr = explore_threshold(eps);
 
   for (int it = 0; it < n_iters; it++) {
@@ -183,33 +202,42 @@ __global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState 
     unsigned w[4];
     RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
     __syncwarp();
-    // Q row of the current state: lanes 0..3 fetch one action value each
+    // Q row of the current state: group lanes 0..3 fetch one action value each
     const unsigned rbase = (s.cell * p.nQ + s.rm) * 4;
-    const float mine = lane < 4 ? trace_lookup(Q, L, rbase + lane) : 0.f;
+    const float mine = (valid && gl < 4) ? trace_lookup(Q, L, rbase + gl) : 0.f;
     float4 row;
-    row.x = __shfl_sync(0xFFFFFFFFu, mine, 0);
-    row.y = __shfl_sync(0xFFFFFFFFu, mine, 1);
-    row.z = __shfl_sync(0xFFFFFFFFu, mine, 2);
-    row.w = __shfl_sync(0xFFFFFFFFu, mine, 3);
+    row.x = __shfl_sync(FULL, mine, 0, LG);
+    row.y = __shfl_sync(FULL, mine, 1, LG);
+    row.z = __shfl_sync(FULL, mine, 2, LG);
+    row.w = __shfl_sync(FULL, mine, 3, LG);
     const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
     const unsigned before = s.cell;
     const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
     Rec r;
-    agent_step<ENV>(p, tb, s, action, w[3], true, r);  // all lanes compute the same scalars
+    agent_step<ENV>(p, tb, s, action, w[3], true, r);  // every lane of a group computes its agent's scalars
+    bool wipe = false;
     if (learn) {
       const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
       const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
       const unsigned hot = (obs * p.nQ + r.prev_q) * 4 + action, nbase = (r.cell * p.nQ + r.q) * 4;
-      // lanes 0..3: next-state row, lane 4: Q[s,a] — five independent lookups in flight
-      const float got = lane < 4 ? trace_lookup(Q, L, nbase + lane) : (lane == 4 ? trace_lookup(Q, L, hot) : 0.f);
-      const float n0 = __shfl_sync(0xFFFFFFFFu, got, 0), n1 = __shfl_sync(0xFFFFFFFFu, got, 1);
-      const float n2 = __shfl_sync(0xFFFFFFFFu, got, 2), n3 = __shfl_sync(0xFFFFFFFFu, got, 3);
-      const float qsa = __shfl_sync(0xFFFFFFFFu, got, 4);
+      // group lanes 0..3: next-state row; lane 4 (groups of 8+) or lane 0 in a second round (groups of 4): Q[s,a]
+      float got = 0.f;
+      if (valid && gl < 4) got = trace_lookup(Q, L, nbase + gl);
+      else if (valid && gl == 4) got = trace_lookup(Q, L, hot);
+      const float n0 = __shfl_sync(FULL, got, 0, LG), n1 = __shfl_sync(FULL, got, 1, LG);
+      const float n2 = __shfl_sync(FULL, got, 2, LG), n3 = __shfl_sync(FULL, got, 3, LG);
+      float qsa;
+      if (LG > 4) {
+        qsa = __shfl_sync(FULL, got, 4, LG);
+      } else {
+        const float h = (valid && gl == 0) ? trace_lookup(Q, L, hot) : 0.f;
+        qsa = __shfl_sync(FULL, h, 0, LG);
+      }
       const double best = term_arg ? 0.0 : (double)fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
       const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
       const float c = __fmul_rn(p.lr_f, td);
       bool found = false;
-      for (unsigned j = lane; j < len; j += 32) {  // one coalesced pass over the live entries
+      for (unsigned j = gl; j < len; j += LG) {  // one pass over the agent's live entries (len = 0 on idle lanes)
         float e = L.e[j], q = L.q[j];
         if (L.idx[j] == hot) {
           e = 1.0f;  // replacing trace
@@ -221,8 +249,10 @@ __global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState 
         L.e[j] = e;
       }
       work += len;
-      if (!__any_sync(0xFFFFFFFFu, found)) {  // first visit since the last wipe: the table value is current
-        if (lane == 0) {
+      __syncwarp();
+      const bool any_found = (__ballot_sync(FULL, found) & gmask) != 0u;
+      if (valid && !any_found) {  // first visit since the last wipe: the table value is current
+        if (gl == 0) {
           L.idx[len] = (unsigned short)hot;
           L.q[len] = __fadd_rn(Q[hot], __fmul_rn(c, 1.0f));
           L.e[len] = term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f);
@@ -230,30 +260,16 @@ __global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState 
         }
         len++;
       }
-      __syncwarp();
-      if (term_arg) {  // e_table.fill(0): nothing is live any more
-        trace_flush(Q, L, len, lane);
-        len = 0;
-        __syncwarp();
-      }
+      wipe = valid && term_arg;  // e_table.fill(0): nothing is live any more
     }
     ep_ret = __dadd_rn(ep_ret, r.reward);
-    if (trace && lane == 0)
+    if (trace && valid && gl == 0)
       trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                            ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
                                                            ((unsigned)r.stepped << 23);
-    if (lane == 0) {
-      sh_term[a] = r.term;
-      sh_trunc[a] = r.trunc;
-    }
-    __syncthreads();
-    bool all_term = true, all_trunc = true;
-    for (int b = 0; b < p.A; b++) {
-      all_term = all_term && sh_term[b];
-      all_trunc = all_trunc && sh_trunc[b];
-    }
-    __syncthreads();
-    if (all_term || all_trunc) {
+    // episode over <=> every agent of the instance terminated, or every agent truncated (idle lanes vote yes)
+    const bool over = __all_sync(FULL, !valid || r.term) || __all_sync(FULL, !valid || r.trunc);
+    if (valid && over) {
       episodes++;
       active_steps += s.steps;
       successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
@@ -264,12 +280,14 @@ __global__ void __launch_bounds__(256) train_qlambda_sparse_kernel(KP p, DState 
       ep_ret = 0.0;
       reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
-      trace_flush(Q, L, len, lane);  // reset_e_table (ma_office.py:101-102)
-      len = 0;
-      __syncwarp();
+      wipe = true;  // reset_e_table (ma_office.py:101-102)
     }
+    __syncwarp();
+    trace_flush(Q, L, wipe ? len : 0u, gl, LG);
+    if (wipe) len = 0;
+    __syncwarp();
   }
-  if (lane == 0) {
+  if (valid && gl == 0) {
     st.slot[k] = pack_slot(s);
     st.epsilon[k] = eps;
     st.tr_len[k] = len;
