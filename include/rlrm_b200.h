@@ -198,8 +198,7 @@ typedef struct rlrm_state {
    * zero). rlrm_qlambda_materialize writes the listed values back so `q` can be read. Needs S*4 <= 65535. */
   uint16_t* tr_pos;     /* [N*A][S*4] 0 = entry not listed, else list position + 1 */
   uint16_t* tr_idx;     /* [N*A][tr_cap] listed entry index = enc*4 + action */
-  float* tr_e;          /* [N*A][tr_cap] its trace */
-  float* tr_q;          /* [N*A][tr_cap] its current q value */
+  float* tr_eq;         /* [N*A][tr_cap][2] its (trace, current q value), interleaved: one 8-byte access per entry */
   uint32_t* tr_len;     /* [N*A] list length */
   uint64_t* tr_work;    /* [N*A] or NULL: sum over update steps of the list length swept (bench: mean live traces) */
   int32_t tr_cap;       /* list capacity; must be >= max_steps + 1 (one new entry per step, wiped every episode) */

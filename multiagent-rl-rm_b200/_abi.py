@@ -126,8 +126,7 @@ class State(C.Structure):
         ("acc_last", C.c_void_p),
         ("tr_pos", C.c_void_p),
         ("tr_idx", C.c_void_p),
-        ("tr_e", C.c_void_p),
-        ("tr_q", C.c_void_p),
+        ("tr_eq", C.c_void_p),
         ("tr_len", C.c_void_p),
         ("tr_work", C.c_void_p),
         ("tr_cap", C.c_int32),

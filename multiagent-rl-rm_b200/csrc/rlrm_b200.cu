@@ -239,7 +239,7 @@ static DState dstate(const rlrm_state_t* st) {
   d.N = st->n_instances; d.slot = (unsigned long long*)st->slot; d.epsilon = st->epsilon; d.q = st->q; d.e = st->e;
   d.visits = st->visits; d.ep_return = st->ep_return; d.stats = st->stats;
   d.acc_sum = (long long*)st->acc_sum; d.acc_cnt = st->acc_cnt; d.acc_last = st->acc_last;
-  d.tr_pos = st->tr_pos; d.tr_idx = st->tr_idx; d.tr_e = st->tr_e; d.tr_q = st->tr_q; d.tr_len = st->tr_len;
+  d.tr_pos = st->tr_pos; d.tr_idx = st->tr_idx; d.tr_eq = (float2*)st->tr_eq; d.tr_len = st->tr_len;
   d.tr_work = (unsigned long long*)st->tr_work; d.tr_cap = st->tr_cap;
   return d;
 }
@@ -260,7 +260,7 @@ static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need
   if (!st->slot || !st->epsilon) return fail(RLRM_ERR_ARG, "state.slot / state.epsilon are required");
   if (need_q && !st->q) return fail(RLRM_ERR_ARG, "state.q is required");
   if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) {
-    if (!st->tr_pos || !st->tr_idx || !st->tr_e || !st->tr_q || !st->tr_len)
+    if (!st->tr_pos || !st->tr_idx || !st->tr_eq || !st->tr_len)
       return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e (dense traces) or state.tr_* (sparse traces)");
     if (st->tr_cap < h->cfg.max_steps + 1) return fail(RLRM_ERR_ARG, "tr_cap must be >= max_steps + 1");
     if (h->kp.S4 > 65535) return fail(RLRM_ERR_UNSUPPORTED, "sparse traces need S*4 <= 65535");
@@ -522,7 +522,7 @@ extern "C" int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval
 
 extern "C" int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, float* e_dense, void* stream) {
   if (!h || !st) return fail(RLRM_ERR_ARG, "null handle/state");
-  if (!st->q || !st->tr_idx || !st->tr_q || !st->tr_e || !st->tr_len) return fail(RLRM_ERR_ARG, "no sparse trace state");
+  if (!st->q || !st->tr_idx || !st->tr_eq || !st->tr_len) return fail(RLRM_ERR_ARG, "no sparse trace state");
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = st->n_instances * h->kp.A;
   qlambda_materialize_kernel<<<blocks_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), e_dense);

@@ -63,8 +63,7 @@ struct DState {  // rlrm_state_t by value
   float* acc_last;
   unsigned short* tr_pos;  // Q(lambda) sparse-exact traces (include/rlrm_b200.h), null otherwise
   unsigned short* tr_idx;
-  float* tr_e;
-  float* tr_q;
+  float2* tr_eq;  // (trace, current q value) of each listed entry
   unsigned* tr_len;
   unsigned long long* tr_work;
   int tr_cap;

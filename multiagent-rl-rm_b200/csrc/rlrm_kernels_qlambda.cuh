@@ -131,21 +131,20 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
 struct TraceList {
   unsigned short* pos;  // [S*4]
   unsigned short* idx;  // [cap]
-  float* e;
-  float* q;
+  float2* eq;           // [cap] (trace, current q value)
 };
 
 // current value of table entry j: the listed copy when the entry has a live trace, else the table
 __device__ __forceinline__ float trace_lookup(const float* Q, const TraceList& L, unsigned j) {
   const unsigned pz = L.pos[j];
-  return pz ? L.q[pz - 1] : Q[j];
+  return pz ? L.eq[pz - 1].y : Q[j];
 }
 
 // write the listed values back and forget the list (traces wiped: reset_e_table / e_table.fill(0))
 __device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsigned len, int lane, int stride = 32) {
   for (unsigned j = lane; j < len; j += stride) {
     const unsigned id = L.idx[j];
-    Q[id] = L.q[j];
+    Q[id] = L.eq[j].y;
     L.pos[id] = 0;
   }
 }
@@ -177,8 +176,7 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
   TraceList L;
   L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
-  L.e = st.tr_e + (size_t)k * (size_t)st.tr_cap;
-  L.q = st.tr_q + (size_t)k * (size_t)st.tr_cap;
+  L.eq = st.tr_eq + (size_t)k * (size_t)st.tr_cap;
   unsigned len = 0;
   rlrm_stats_t z;
   if (valid) {
@@ -220,42 +218,47 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
       const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
       const unsigned hot = (obs * p.nQ + r.prev_q) * 4 + action, nbase = (r.cell * p.nQ + r.q) * 4;
-      // group lanes 0..3: next-state row; lane 4 (groups of 8+) or lane 0 in a second round (groups of 4): Q[s,a]
+      // group lanes 0..3: next-state row; lane 4 (groups of 8+) or lane 0 in a second round (groups of 4): Q[s,a] together
+      // with its list position (0 = no live trace yet), which also tells the sweep which entry is the visited one
       float got = 0.f;
-      if (valid && gl < 4) got = trace_lookup(Q, L, nbase + gl);
-      else if (valid && gl == 4) got = trace_lookup(Q, L, hot);
+      unsigned pz = 0;
+      if (valid && gl < 4) {
+        got = trace_lookup(Q, L, nbase + gl);
+      } else if (valid && gl == 4) {
+        pz = L.pos[hot];
+        got = pz ? L.eq[pz - 1].y : Q[hot];
+      }
       const float n0 = __shfl_sync(FULL, got, 0, LG), n1 = __shfl_sync(FULL, got, 1, LG);
       const float n2 = __shfl_sync(FULL, got, 2, LG), n3 = __shfl_sync(FULL, got, 3, LG);
       float qsa;
+      unsigned hotpos;
       if (LG > 4) {
         qsa = __shfl_sync(FULL, got, 4, LG);
+        hotpos = __shfl_sync(FULL, pz, 4, LG);
       } else {
-        const float h = (valid && gl == 0) ? trace_lookup(Q, L, hot) : 0.f;
+        float h = 0.f;
+        if (valid && gl == 0) {
+          pz = L.pos[hot];
+          h = pz ? L.eq[pz - 1].y : Q[hot];
+        }
         qsa = __shfl_sync(FULL, h, 0, LG);
+        hotpos = __shfl_sync(FULL, gl == 0 ? pz : 0u, 0, LG);
       }
       const double best = term_arg ? 0.0 : (double)fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
       const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
       const float c = __fmul_rn(p.lr_f, td);
-      bool found = false;
       for (unsigned j = gl; j < len; j += LG) {  // one pass over the agent's live entries (len = 0 on idle lanes)
-        float e = L.e[j], q = L.q[j];
-        if (L.idx[j] == hot) {
-          e = 1.0f;  // replacing trace
-          found = true;
-        }
-        q = __fadd_rn(q, __fmul_rn(c, e));
-        e = term_arg ? 0.0f : __fmul_rn(e, p.trace_decay_f);
-        L.q[j] = q;
-        L.e[j] = e;
+        float2 eq = L.eq[j];
+        if (j + 1 == hotpos) eq.x = 1.0f;  // replacing trace on the visited entry
+        eq.y = __fadd_rn(eq.y, __fmul_rn(c, eq.x));
+        eq.x = term_arg ? 0.0f : __fmul_rn(eq.x, p.trace_decay_f);
+        L.eq[j] = eq;
       }
       work += len;
-      __syncwarp();
-      const bool any_found = (__ballot_sync(FULL, found) & gmask) != 0u;
-      if (valid && !any_found) {  // first visit since the last wipe: the table value is current
+      if (valid && hotpos == 0u) {  // first visit since the last wipe: the table value (qsa) is current
         if (gl == 0) {
           L.idx[len] = (unsigned short)hot;
-          L.q[len] = __fadd_rn(Q[hot], __fmul_rn(c, 1.0f));
-          L.e[len] = term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f);
+          L.eq[len] = make_float2(term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f), __fadd_rn(qsa, __fmul_rn(c, 1.0f)));
           L.pos[hot] = (unsigned short)(len + 1);
         }
         len++;
@@ -314,12 +317,12 @@ __global__ void __launch_bounds__(256) qlambda_materialize_kernel(KP p, DState s
   if (warp >= st.N * p.A) return;
   float* Q = st.q + (size_t)warp * (size_t)p.S4;
   const unsigned short* idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
-  const float* lq = st.tr_q + (size_t)warp * (size_t)st.tr_cap;
-  const float* le = st.tr_e + (size_t)warp * (size_t)st.tr_cap;
+  const float2* leq = st.tr_eq + (size_t)warp * (size_t)st.tr_cap;
   const unsigned len = st.tr_len[warp];
   for (unsigned j = lane; j < len; j += 32) {
-    Q[idx[j]] = lq[j];
-    if (e_dense) e_dense[(size_t)warp * (size_t)p.S4 + idx[j]] = le[j];
+    const float2 eq = leq[j];
+    Q[idx[j]] = eq.y;
+    if (e_dense) e_dense[(size_t)warp * (size_t)p.S4 + idx[j]] = eq.x;
   }
 }
 
@@ -332,8 +335,7 @@ __global__ void __launch_bounds__(256) qlambda_sparse_reset_kernel(KP p, DState 
   TraceList L;
   L.pos = st.tr_pos + (size_t)warp * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
-  L.e = st.tr_e + (size_t)warp * (size_t)st.tr_cap;
-  L.q = st.tr_q + (size_t)warp * (size_t)st.tr_cap;
+  L.eq = st.tr_eq + (size_t)warp * (size_t)st.tr_cap;
   trace_flush(st.q + (size_t)warp * (size_t)p.S4, L, st.tr_len[warp], lane);
   __syncwarp();
   if (lane == 0) st.tr_len[warp] = 0;

@@ -62,15 +62,14 @@ class Engine:
         self.sparse = bool(qlambda_sparse) and self.cfg.algo == abi.ALGO_QLAMBDA
         self.e = torch.zeros(tab_shape, dtype=torch.float32, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
         self.tr_cap = 0
-        self.tr_pos = self.tr_idx = self.tr_e = self.tr_q = self.tr_len = self.tr_work = None
+        self.tr_pos = self.tr_idx = self.tr_eq = self.tr_len = self.tr_work = None
         if self.sparse:
             if self.S * 4 > 65535:
                 raise ValueError("sparse Q(lambda) traces need S*4 <= 65535")
             self.tr_cap = ((int(self.cfg.max_steps) + 1 + 31) // 32) * 32
             self.tr_pos = torch.zeros((n_slots, self.S * 4), dtype=torch.int16, device=d)
             self.tr_idx = torch.zeros((n_slots, self.tr_cap), dtype=torch.int16, device=d)
-            self.tr_e = torch.zeros((n_slots, self.tr_cap), dtype=torch.float32, device=d)
-            self.tr_q = torch.zeros((n_slots, self.tr_cap), dtype=torch.float32, device=d)
+            self.tr_eq = torch.zeros((n_slots, self.tr_cap, 2), dtype=torch.float32, device=d)  # (trace, q value) pairs
             self.tr_len = torch.zeros(n_slots, dtype=torch.int32, device=d)
             self.tr_work = torch.zeros(n_slots, dtype=torch.int64, device=d)
         need_visits = track_visits or self.cfg.learning_rate < 0
@@ -83,7 +82,7 @@ class Engine:
         self.acc_last = torch.zeros(tab_shape, dtype=torch.float32, device=d) if shared else None
         self.state = abi.State(self.N, _ptr(self.slot), _ptr(self.epsilon), _ptr(self.q), _ptr(self.e), _ptr(self.visits),
                                _ptr(self.ep_return), _ptr(self.stats), _ptr(self.acc_sum), _ptr(self.acc_cnt), _ptr(self.acc_last),
-                               _ptr(self.tr_pos), _ptr(self.tr_idx), _ptr(self.tr_e), _ptr(self.tr_q), _ptr(self.tr_len),
+                               _ptr(self.tr_pos), _ptr(self.tr_idx), _ptr(self.tr_eq), _ptr(self.tr_len),
                                _ptr(self.tr_work), self.tr_cap, 0)
         self.t = 0  # lockstep iteration counter (Philox counter word)
 
