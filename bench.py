@@ -429,8 +429,11 @@ def run_gpu_arm(args):
                          "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms,
                          **({"mean_live_traces": mean_live,
                              "dense_equivalent_GBps": (4 * 1296 * 4 * 4) * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9,
-                             "note": "achieved uses the sparse algorithm's own bytes (32 + 16*L); dense_equivalent is what the "
-                                     "reference's dense sweep would have moved for the same steps, NOT achieved bandwidth"}
+                             "note": "achieved uses the sparse algorithm's own bytes (32 + 16*L, SURVEY 8d); dense_equivalent is "
+                                     "what the reference's dense sweep would have moved for the same steps, NOT achieved "
+                                     "bandwidth. The lists stay L1/L2-resident across the iterations of one launch (ncu: DRAM "
+                                     "at 3 % of peak, issue slots 74 %, L1 wavefronts 61 %), so frac can exceed 1: the kernel "
+                                     "is instruction-issue bound, see profiles/r01_sparse_qlambda_v3_ncu_full.csv"}
                             if mean_live is not None else {})},
             "cpu_baseline": cpu,
         }

@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
 }
 
 // ------------------------------------------------------------------------------------------------
-// Q(lambda), sparse-exact traces: one block per instance, one warp per agent. Only entries with a live trace are
-// touched; each agent's live entries sit in a list that carries the trace AND the current q value (a write-back
-// cache over the table), so one update step reads/writes the list once, coalesced. Bit-identical to the dense sweep of
+// Q(lambda), sparse-exact traces: one warp per instance, one lane group per agent. Only entries with a live trace are
+// touched; each agent's live entries sit in a list of (trace, current q value) pairs (a write-back cache over the
+// table), so one update step reads/writes the list once, 8 bytes per entry. Bit-identical to the dense sweep of
 // QLearningLambda.update (qlearning_lambda.py:33-84) up to the sign of zero: unlisted entries have e == 0 and receive +0.
 // ------------------------------------------------------------------------------------------------
 struct TraceList {
