@@ -74,6 +74,46 @@ static void fill_learner(KP& kp, double lr, double gamma, double lambd) {
   kp.trace_decay_f = (float)(gamma * lambd);
 }
 
+// Table CONTENTS are indices the kernels follow without bounds checks: reject anything out of range here, on the host.
+static int validate_tables(const rlrm_config_t* cfg, const rlrm_tables_t* tb) {
+  const int ncell = cfg->width * cfg->height, nQ = cfg->n_rm_states, nEv = cfg->n_events;
+  const int sec = cfg->per_agent_rm ? cfg->n_agents : 1;
+  for (int j = 0; j < ncell * 4; j++)
+    if (tb->next_cell[j] >= ncell) return fail(RLRM_ERR_ARG, "tables.next_cell holds a cell index >= width*height");
+  for (int a = 0; a < cfg->n_agents; a++)
+    if (tb->start_cell[a] >= ncell) return fail(RLRM_ERR_ARG, "tables.start_cell holds a cell index >= width*height");
+  for (int j = 0; j < ncell * sec; j++)
+    if (tb->label[j] != RLRM_EVENT_NONE && tb->label[j] >= nEv) return fail(RLRM_ERR_ARG, "tables.label holds an event id >= n_events");
+  for (int j = 0; j < nQ * (nEv + 1) * sec; j++)
+    if (tb->delta[j] != RLRM_NO_TRANSITION && tb->delta[j] >= nQ) return fail(RLRM_ERR_ARG, "tables.delta holds a state index >= n_rm_states");
+  if (cfg->rm_final >= nQ) return fail(RLRM_ERR_ARG, "rm_final >= n_rm_states");
+  if (cfg->n_qrm_states > 0) {
+    if (!tb->qrm_states) return fail(RLRM_ERR_ARG, "n_qrm_states > 0 needs tables.qrm_states");
+    for (int s = 0; s < sec; s++) {
+      const int n = cfg->per_agent_rm ? cfg->agent_n_qrm[s] : cfg->n_qrm_states;
+      const int lim = cfg->per_agent_rm ? cfg->agent_n_rm_states[s] : nQ;
+      for (int j = 0; j < n && j < nQ; j++)
+        if (tb->qrm_states[(cfg->per_agent_rm ? s * nQ : 0) + j] >= lim) return fail(RLRM_ERR_ARG, "tables.qrm_states holds a state index out of range");
+    }
+  }
+  if (cfg->random_starts)
+    for (int j = 0; j < cfg->n_free_cells; j++)
+      if (tb->free_cells[j] >= ncell) return fail(RLRM_ERR_ARG, "tables.free_cells holds a cell index >= width*height");
+  for (int a = 0; a < 4; a++)
+    for (int j = 0; j < 4; j++)
+      if (cfg->slip_outcome[a][j] > RLRM_ACTION_WAIT) return fail(RLRM_ERR_ARG, "slip_outcome holds an action > RLRM_ACTION_WAIT");
+  if (cfg->per_agent_rm)
+    for (int a = 0; a < cfg->n_agents; a++) {
+      if (cfg->agent_n_rm_states[a] < 1 || cfg->agent_n_rm_states[a] > nQ || cfg->agent_n_qrm[a] < 0 || cfg->agent_n_qrm[a] > nQ ||
+          cfg->agent_rm_final[a] >= cfg->agent_n_rm_states[a])
+        return fail(RLRM_ERR_ARG, "per-agent reward machine sizes out of range");
+    }
+  if (cfg->per_agent_rm && (cfg->algo == RLRM_ALGO_QLAMBDA || (cfg->use_rsh && tb->phi)))
+    return fail(RLRM_ERR_UNSUPPORTED, "per-agent reward machines are supported for QL / QRM without shaping");
+  if (cfg->max_steps < 0 || cfg->max_steps > 65534) return fail(RLRM_ERR_ARG, "max_steps must be in 0..65534 (16-bit step counters)");
+  return RLRM_OK;
+}
+
 extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int device, rlrm_handle_t** out) {
   if (!cfg || !tb || !out) return fail(RLRM_ERR_ARG, "null argument");
   if (cfg->abi_version != RLRM_ABI_VERSION) return fail(RLRM_ERR_ARG, "abi_version mismatch");
@@ -94,6 +134,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->shared_q) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) with a shared table is not supported");
   if (!tb->next_cell || !tb->cell_flags || !tb->label || !tb->delta || !tb->rq || !tb->rcf || !tb->start_cell)
     return fail(RLRM_ERR_ARG, "null table");
+  if (int rc = validate_tables(cfg, tb)) return rc;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(RLRM_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -137,11 +178,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     kp.a_nqrm[a] = kp.per_agent ? cfg->agent_n_qrm[a] : kp.n_qrm;
     kp.a_prefix4[a] = kp.sum4;
     kp.sum4 += (long long)ncell * kp.a_nQ[a] * 4;
-    if (kp.a_nQ[a] < 1 || kp.a_nQ[a] > kp.nQ || kp.a_nqrm[a] < 0 || kp.a_nqrm[a] > kp.nQ)
-      return fail(RLRM_ERR_ARG, "per-agent reward machine sizes out of range");
   }
-  if (kp.per_agent && (cfg->algo == RLRM_ALGO_QLAMBDA || kp.use_rsh))
-    return fail(RLRM_ERR_UNSUPPORTED, "per-agent reward machines are supported for QL / QRM without shaping");
   kp.random_starts = cfg->random_starts ? 1 : 0;
   kp.n_free = cfg->n_free_cells;
   kp.seed_lo = cfg->seed_lo; kp.seed_hi = cfg->seed_hi; kp.instance_offset = cfg->instance_offset;

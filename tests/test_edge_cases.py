@@ -136,9 +136,33 @@ def test_create_rejects_bad_arguments():
                          (lambda cfg, t: setattr(cfg, "n_rm_states", 33), "n_rm_states"),
                          (lambda cfg, t: setattr(cfg, "n_actions", 5), "n_actions"),
                          (lambda cfg, t: setattr(cfg, "algo", 7), "algo"),
-                         (lambda cfg, t: setattr(t, "delta", None), "null table")):
+                         (lambda cfg, t: setattr(t, "delta", None), "null table"),
+                         (lambda cfg, t: setattr(cfg, "rm_final", 4), "rm_final"),
+                         (lambda cfg, t: setattr(cfg, "max_steps", 70000), "max_steps")):
         rc, msg = create(mutate)
         assert rc == -1 and text in msg, (rc, msg)
+
+    # table CONTENTS are validated too: the kernels follow these indices without bounds checks
+    def create_with(field, index, value):
+        c = P.compile_scenario(P.scenario_config1())
+        arr = getattr(c, field)
+        arr.reshape(-1)[index] = value
+        t = c.tables_struct()
+        h = C.c_void_p()
+        rc = L.rlrm_create(C.byref(c.config), C.byref(t), 0, C.byref(h))
+        if rc == 0:
+            L.rlrm_destroy(h)
+        return rc, L.rlrm_last_error().decode()
+
+    for field, index, value, text in (("next_cell", 17, 100, "next_cell"), ("start_cell", 1, 400, "start_cell"),
+                                      ("label", 5, 3, "label"), ("delta", 2, 4, "delta"), ("qrm_states", 1, 9, "qrm_states")):
+        rc, msg = create_with(field, index, value)
+        assert rc == -1 and text in msg, (field, rc, msg)
+    c = P.compile_scenario(P.scenario_config3(True))
+    c.config.slip_outcome[2][1] = 7
+    t = c.tables_struct()
+    h = C.c_void_p()
+    assert L.rlrm_create(C.byref(c.config), C.byref(t), 0, C.byref(h)) == -1 and "slip_outcome" in L.rlrm_last_error().decode()
     assert L.rlrm_create(None, None, 0, None) == -1
     with pytest.raises(ValueError):
         P.compile_scenario(P.scenario_config1(), grid=GridSpec("frozen_lake", 40, 40))
