@@ -252,8 +252,11 @@ int rlrm_select_action(rlrm_handle_t* h, const rlrm_state_t* st, const uint32_t*
 
 /* RMEnvironmentWrapper.step (rm_environment_wrapper.py:43-107): env.step (ma_frozen_lake.py:96-154 /
  * ma_office.py:122-202) + RewardMachine.step (reward_machine.py:45-59) per agent + reward / termination merge.
- * actions: device uint8 [N*A]. with_rm == 0 runs the bare env.step (RM state is read for FrozenLake's rm_done
- * test but not advanced). */
+ * actions: device uint8 [N*A], 0..3 or RLRM_ACTION_WAIT (env.wait_action; larger values are treated as wait).
+ * with_rm == 0 runs the bare env.step (RM state is read for FrozenLake's rm_done test but not advanced).
+ * Robustness contract of the call-by-call entry points: indices read from caller memory (actions, cells, RM states,
+ * step records) are clamped to the table they address, so garbage in gives garbage out but never an out-of-bounds
+ * access; slot words are only ever produced by rlrm_reset / rlrm_step / rlrm_train and are trusted. */
 int rlrm_step(rlrm_handle_t* h, const rlrm_state_t* st, const uint8_t* actions, const uint32_t* draws, uint64_t t,
               int with_rm, const rlrm_step_out_t* out, void* stream);
 

@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) rm_step_kernel(KP p_in, int agent, long l
   if (p_in.per_agent) agent_view(p_in, p, tb, agent);  // the reward machine of agent `agent`
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const unsigned ev = tb.label[cell[k]];
+  const unsigned ev = tb.label[min((unsigned)cell[k], (unsigned)p.ncell - 1u)];  // caller memory: clamp what indexes a table
   const int col = ev == RLRM_EVENT_NONE ? p.nEv : (int)ev;
-  const unsigned cur = q[k];
+  const unsigned cur = min((unsigned)q[k], (unsigned)p.nQ - 1u);
   const unsigned d = tb.delta[cur * (p.nEv + 1) + col];
   double r = 0.0;
   if (d != RLRM_NO_TRANSITION) {
@@ -175,12 +175,16 @@ __global__ void __launch_bounds__(256) update_kernel(KP p_in, DState st, const u
   const long long i = k / p.A;
   const int a = (int)(k - i * p.A);
   if (PA) agent_view(p_in, p, tb, a);
+  // the record and the arguments are caller memory: clamp every index that addresses a table
+  const unsigned cmax = (unsigned)p.ncell - 1u, qmax = (unsigned)p.nQ - 1u;
   Rec r;
-  r.prev_cell = o.prev_cell[k]; r.cell = o.cell[k]; r.prev_q = o.prev_q[k]; r.q = o.q[k]; r.event = o.event[k];
+  r.prev_cell = min((unsigned)o.prev_cell[k], cmax); r.cell = min((unsigned)o.cell[k], cmax);
+  r.prev_q = min((unsigned)o.prev_q[k], qmax); r.q = min((unsigned)o.q[k], qmax);
+  r.event = o.event[k] == RLRM_EVENT_NONE ? (unsigned)RLRM_EVENT_NONE : min((unsigned)o.event[k], (unsigned)max(p.nEv, 1) - 1u);
   r.env_term = o.env_term[k] != 0; r.renv = o.renv[k]; r.reward = o.reward[k];
   const size_t base = table_base(p_in, i, a);
-  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, obs_cell[k], actions[k], term_arg[k] != 0, r,
-                     make_acc(p, st, base));
+  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, min((unsigned)obs_cell[k], cmax),
+                     min((int)actions[k], RLRM_N_ACTIONS - 1), term_arg[k] != 0, r, make_acc(p, st, base));
 }
 
 // QLearningLambda.update (qlearning_lambda.py:33-84), dense sweep exactly as written: one block per (instance, agent).
@@ -223,8 +227,12 @@ __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, co
   const long long i = k / p.A;
   const int a = (int)(k - i * p.A);
   const size_t base = table_base(p, i, a);
-  if (st.visits && threadIdx.x == 0) st.visits[base + (size_t)(obs_cell[k] * p.nQ + o.prev_q[k]) * 4 + actions[k]] += 1;
-  qlambda_sweep(p, st.q + base, st.e + base, obs_cell[k] * p.nQ + o.prev_q[k], actions[k], o.reward[k],
-                o.cell[k] * p.nQ + o.q[k], term_arg[k] != 0, threadIdx.x, blockDim.x);
+  // caller memory: clamp what indexes a table
+  const unsigned cmax = (unsigned)p.ncell - 1u, qmax = (unsigned)p.nQ - 1u;
+  const unsigned s_idx = min((unsigned)obs_cell[k], cmax) * p.nQ + min((unsigned)o.prev_q[k], qmax);
+  const unsigned sn_idx = min((unsigned)o.cell[k], cmax) * p.nQ + min((unsigned)o.q[k], qmax);
+  const int action = min((int)actions[k], RLRM_N_ACTIONS - 1);
+  if (st.visits && threadIdx.x == 0) st.visits[base + (size_t)s_idx * 4 + action] += 1;
+  qlambda_sweep(p, st.q + base, st.e + base, s_idx, action, o.reward[k], sn_idx, term_arg[k] != 0, threadIdx.x, blockDim.x);
 }
 
