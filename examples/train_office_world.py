@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""The reference's OfficeWorld run (`office_main --map map1 --experiment <name> --rm-spec FILE --algorithm QL|QRM|QL-lambda`)
+on a batch of instances: authored reward-machine spec -> device tables -> fused training -> batched greedy evaluation, and the
+product MDP of the first agent through RMEnvironmentWrapper.get_mdp (what the reference feeds its value iteration).
+
+    python examples/train_office_world.py --rm-spec tests/fixtures/officeworld_acbd.json --algorithm QRM --instances 8192
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import multiagent_rlrm_b200 as P  # noqa: E402
+from multiagent_rlrm_b200.engine import Engine  # noqa: E402
+from multiagent_rlrm_b200.maps import office_world_grid  # noqa: E402
+from multiagent_rlrm_b200.rmspec import scenario_from_rmspec  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rm-spec", default=os.path.join(os.path.dirname(__file__), "..", "tests", "fixtures", "officeworld_acbd.json"))
+    ap.add_argument("--map", default="map1")
+    ap.add_argument("--algorithm", default="QRM", choices=["QL", "QRM", "QL-lambda"])
+    ap.add_argument("--stochastic", action="store_true")
+    ap.add_argument("--instances", type=int, default=8192)
+    ap.add_argument("--iterations", type=int, default=20000)
+    ap.add_argument("--seed", type=int, default=100)
+    ap.add_argument("--mdp", action="store_true", help="also build the product MDP with get_mdp")
+    args = ap.parse_args()
+
+    sc = P.scenario_config2(args.stochastic)
+    sc.map_name, sc.seed = args.map, args.seed
+    sc.algo = {"QL": "ql", "QRM": "qrm", "QL-lambda": "qlambda"}[args.algorithm]
+    if sc.algo == "qlambda":
+        sc.lambd, sc.learning_rate, sc.q_init = 0.9, 0.1, 0.0
+    sc, rm = scenario_from_rmspec(args.rm_spec, sc)
+    print(f"reward machine: {rm.numbers_state()} states, {len(rm.transitions)} transitions, final {rm.get_final_state()}")
+    eng = Engine(P.compile_scenario(sc), args.instances, qlambda_sparse=(sc.algo == "qlambda"))
+    eng.reset()
+    done = 0
+    while done < args.iterations:
+        chunk = min(4000, args.iterations - done)
+        eng.train(chunk)
+        done += chunk
+        st = eng.stats_numpy()
+        print(f"iter {done:7d}: episodes {int(st['episodes'].sum()):9d}  successes {int(st['successes'].sum()):9d}  "
+              f"active agent-steps {eng.total_active_steps():12d}")
+    res = P.test_policy_optima_batched(eng, episodi_test=3, optimal_steps=30, gamma=sc.gamma)
+    print(f"greedy evaluation: success rate {res['success_rate'].mean():.1f} %")
+
+    if args.mdp:
+        g = office_world_grid(args.map)
+        env = P.MultiAgentOfficeWorld(width=g.width, height=g.height, plants=g.hazards, coffee=g.coffee, letters=g.letters,
+                                      walls=g.walls, plants_penalty_value=sc.plants_penalty, wall_penalty_value=sc.wall_penalty,
+                                      terminate_on_plants=sc.terminate_on_plants, terminate_hit_walls=sc.terminate_hit_walls)
+        env.stochastic, env.all_slip, env.high_prob, env.delay_action = sc.stochastic, sc.all_slip, sc.high_prob, sc.delay_action
+        ag = P.AgentRL("a1", env)
+        ag.set_initial_position(*sc.starts[0])
+        ag.add_state_encoder(P.StateEncoderOfficeWorld(ag))
+        ag.add_action_encoder(P.ActionEncoderOfficeWorld(ag))
+        ag.set_reward_machine(rm)
+        env.add_agent(ag)
+        all_P, n_states, n_actions = P.RMEnvironmentWrapper(env, [ag]).get_mdp(args.seed)
+        n_term = sum(1 for s in all_P["a1"] if all_P["a1"][s][0][0][3] and all_P["a1"][s][0][0][1] == s)
+        print(f"product MDP of a1: {n_states['a1']} states x {n_actions['a1']} actions, {n_term} terminal states")
+
+
+if __name__ == "__main__":
+    main()
