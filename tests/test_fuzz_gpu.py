@@ -166,3 +166,22 @@ def test_random_scenario_greedy_evaluation_equals_oracle(seed, cuda_device):
     for f in ev_o.dtype.names:
         if f != "reserved":
             assert np.array_equal(ev_g[f], ev_o[f]), (info, f)
+
+
+@pytest.mark.parametrize("seed", range(1, N_CASES, 8))
+def test_random_scenario_product_mdp_equals_oracle(seed, cuda_device):
+    """rlrm_mdp on the random scenarios: every (state, action, sub-action) outcome equals the oracle's reset + set_state + step."""
+    import oracle as O
+    from multiagent_rlrm_b200.engine import Engine
+    from multiagent_rlrm_b200.tables import mdp_action_distribution
+
+    sc, _opts = random_scenario(seed)
+    sc.shared_q = False
+    c = P.compile_scenario(sc)
+    eng, o = Engine(c, 1), O.Oracle(c, 1, "f32")
+    sub, _probs = mdp_action_distribution(sc)
+    for k in range(len(sc.starts)):
+        for rm_terminal in (True, False):
+            got, exp = eng.mdp(k, sub, rm_terminal=rm_terminal), o.mdp(k, sub, rm_terminal=rm_terminal)
+            for g, e, name in zip(got, exp, ("next_state", "reward", "done", "terminal")):
+                assert np.array_equal(g, e), (seed, k, rm_terminal, name)
