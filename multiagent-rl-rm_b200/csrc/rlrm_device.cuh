@@ -73,6 +73,7 @@ struct Acc {  // accumulators of one agent's shared table, or nulls
   long long* sum;
   int* cnt;
   float* last;
+  bool smem;  // the accumulators live in shared memory (shared_propose_kernel)
 };
 
 struct DOut {  // rlrm_step_out_t by value
@@ -305,7 +306,19 @@ __device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, uns
     out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
   }
   if (acc.sum) {  // shared learner: propose; apply_shared_kernel turns the proposals of this iteration into their mean
-    atomicAdd(reinterpret_cast<unsigned long long*>(acc.sum + s * 4 + a), (unsigned long long)__float2ll_rn(__fmul_rn(out, 1048576.0f)));
+    const unsigned long long v = (unsigned long long)__float2ll_rn(__fmul_rn(out, 1048576.0f));
+    if (acc.smem) {
+      // shared memory has no native 64-bit add (the compiler emits a CAS spin loop, which collapses when many lanes propose
+      // to the same entry): add the low word, derive the carry from the value the atomic returns, add the high word. Each
+      // 32-bit add is atomic and addition commutes, so the 64-bit sum is exact in any order.
+      unsigned* w = reinterpret_cast<unsigned*>(acc.sum + s * 4 + a);
+      const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+      const unsigned old = atomicAdd(w, lo);
+      const unsigned up = hi + ((old + lo) < old ? 1u : 0u);
+      if (up) atomicAdd(w + 1, up);
+    } else {
+      atomicAdd(reinterpret_cast<unsigned long long*>(acc.sum + s * 4 + a), v);
+    }
     atomicAdd(acc.cnt + s * 4 + a, 1);
     acc.last[s * 4 + a] = out;
   } else {

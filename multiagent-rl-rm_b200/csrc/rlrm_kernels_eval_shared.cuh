@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
         const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
         const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
         Acc acc = {reinterpret_cast<long long*>(s_sum) + (size_t)a * (size_t)p.S4, s_cnt + (size_t)a * (size_t)p.S4,
-                   s_last + (size_t)a * (size_t)p.S4};
+                   s_last + (size_t)a * (size_t)p.S4, true};
         agent_update<ALGO>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
       }
       term = r.term;

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
   const int a = lane / LG;         // this lane's agent (slot a >= A idles when A is not a power of two)
   const int gl = lane - a * LG;    // lane within the agent's group
   const bool valid = a < p.A;
-  const unsigned gmask = (LG == 32 ? FULL : ((1u << LG) - 1u)) << (a * LG);
   const long long k = i * p.A + (valid ? a : 0);
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
