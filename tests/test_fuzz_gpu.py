@@ -185,3 +185,38 @@ def test_random_scenario_product_mdp_equals_oracle(seed, cuda_device):
             got, exp = eng.mdp(k, sub, rm_terminal=rm_terminal), o.mdp(k, sub, rm_terminal=rm_terminal)
             for g, e, name in zip(got, exp, ("next_state", "reward", "done", "terminal")):
                 assert np.array_equal(g, e), (seed, k, rm_terminal, name)
+
+
+@pytest.mark.parametrize("n_agents", [1, 2, 3, 5, 6, 8])
+@pytest.mark.parametrize("env", ["frozen_lake", "office_world"])
+def test_sparse_qlambda_lane_groups(env, n_agents, cuda_device):
+    """The sparse Q(lambda) kernel maps agents to lane groups of 32 / 16 / 8 / 4 lanes (1 / 2 / 3-4 / 5-8 agents, idle group
+    slots when the agent count is not a power of two): every width against the oracle AND the dense kernel."""
+    import oracle as O
+    from multiagent_rlrm_b200.engine import Engine
+
+    rng = np.random.default_rng(77 + n_agents)
+    grid = frozen_lake_grid("map1") if env == "frozen_lake" else office_world_grid("map1")
+    hazards = set(grid.hazards)
+    free = [(x, y) for y in range(grid.height) for x in range(grid.width) if (x, y) not in hazards]
+    rm, ev = random_machine(rng, free, "s")
+    sc = P.Scenario(env=env, map_name="map1", starts=[free[i] for i in rng.choice(len(free), size=n_agents, replace=False)],
+                    rm_transitions=rm, detector_positions=sorted(set(ev)), algo="qlambda", learning_rate=0.2, lambd=0.8, gamma=0.9,
+                    q_init=0.0, epsilon_start=0.3, epsilon_end=0.3, epsilon_decay=1.0, stochastic=True, max_steps=60,
+                    driver="frozen_lake_main" if env == "frozen_lake" else "office_main", seed=4242 + n_agents)
+    c = P.compile_scenario(sc)
+    n = 37
+    sparse, dense, o = Engine(c, n, qlambda_sparse=True), Engine(c, n), O.Oracle(c, n, "f32")
+    for x in (sparse, dense, o):
+        x.reset()
+    for chunk in (130, 1, 269):
+        sparse.train(chunk); dense.train(chunk)
+    o.train(0, 400)
+    e_sparse = sparse.sync_tables(with_traces=True)
+    for eng in (sparse, dense):
+        assert np.array_equal(eng.slot.cpu().numpy().view(np.uint64), o.slot)
+        assert np.array_equal(eng.q.cpu().numpy().reshape(-1), o.q.reshape(-1))
+        assert np.array_equal(eng.stats_numpy()["episodes"].reshape(-1), o.stats["episodes"].reshape(-1))
+    assert np.array_equal(e_sparse.cpu().numpy().reshape(-1), o.e.reshape(-1))
+    assert np.array_equal(dense.e.cpu().numpy().reshape(-1), o.e.reshape(-1))
+    assert int(o.stats["episodes"].sum()) > 0
