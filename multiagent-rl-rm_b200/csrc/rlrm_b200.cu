@@ -457,7 +457,13 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
 #define RLRM_TRAIN(ALGO, PA) train_kernel<ENV, ALGO, PA><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace)
     if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits) {
       const DState d = dstate(st);
-#define RLRM_QRM4(ST, LE, TR) train_qrm4_kernel<ENV, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace)
+#define RLRM_QRM4(ST, LE, TR)                                                                                          \
+  do {                                                                                                                \
+    if (dense_batch) train_qrm4_kernel<ENV, ST, LE, TR, 8><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace); \
+    else train_qrm4_kernel<ENV, ST, LE, TR, 7><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace);   \
+  } while (0)
+      // more threads than 7 resident blocks per SM hold: take the 64-register instantiation (8 blocks per SM)
+      const bool dense_batch = threads > (long long)h->num_sms * 7 * TRAIN_BLOCK;
       const int key = (kp.stochastic ? 4 : 0) | (learn ? 2 : 0) | (trace ? 1 : 0);
       switch (key) {
         case 0: RLRM_QRM4(false, false, false); break;

@@ -178,8 +178,11 @@ __device__ __forceinline__ void load_block4(const float* Q, unsigned cell, float
 
 // STOCH / LEARN / TRACE are compile-time copies of p.stochastic / learn / (trace != nullptr): the loop body is issue-bound,
 // so runtime flag tests and their constant-bank loads are specialised away. n_qrm is 3 on this path.
-template <int ENV, bool STOCH, bool LEARN, bool TRACE>
-__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm4_kernel(KP p, DState st, unsigned long long t0, int n_iters,
+// MINB = resident blocks per SM the register allocation is sized for: 7 (72 registers, no spills) when the whole batch
+// fits in 28 warps per SM anyway (BASELINE config 3: 131,072 threads on 148 SMs), 8 (64 registers, 64 B of spills) when
+// there are more threads than that and the extra resident warps pay (config 5: +21 %, config 3 would lose 8 %).
+template <int ENV, bool STOCH, bool LEARN, bool TRACE, int MINB>
+__global__ void __launch_bounds__(TRAIN_BLOCK, MINB) train_qrm4_kernel(KP p, DState st, unsigned long long t0, int n_iters,
                                                                 unsigned* trace) {
   Tab tb = stage_tables(p);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
