@@ -250,6 +250,29 @@ class Engine:
         running = ((self.slot >> abi.SLOT_STEPS_SHIFT) & 0xFFFF).sum()
         return int((finished + running).item())
 
+    # -- checkpoint / resume -----------------------------------------------------------------------
+    _STATE_TENSORS = ("slot", "epsilon", "q", "e", "visits", "ep_return", "stats", "acc_sum", "acc_cnt", "acc_last",
+                      "tr_pos", "tr_idx", "tr_eq", "tr_len", "tr_work")
+
+    def state_dict(self) -> Dict[str, object]:
+        """Everything a run needs to continue bit-identically: the device arrays of rlrm_state_t (CPU copies) and the lockstep
+        iteration counter (the Philox counter word). The reference only pickles learner objects (office_main.py:1611-1613,
+        1922-1925; see learners.QLearning.__getstate__ for that format); a batch of instances resumes from this instead."""
+        out = {k: getattr(self, k).cpu() for k in self._STATE_TENSORS if getattr(self, k) is not None}
+        out.update({"t": int(self.t), "n_instances": self.N, "n_agents": self.A, "state_space": self.S, "sparse": self.sparse})
+        return out
+
+    def load_state_dict(self, state: Dict[str, object]) -> None:
+        if (state["n_instances"], state["n_agents"], state["state_space"], state["sparse"]) != (self.N, self.A, self.S, self.sparse):
+            raise ValueError("checkpoint was taken from a differently shaped engine")
+        for k in self._STATE_TENSORS:
+            mine = getattr(self, k)
+            if (mine is None) != (k not in state):
+                raise ValueError(f"checkpoint and engine disagree on state array {k!r}")
+            if mine is not None:
+                mine.copy_(state[k])  # in place: the C-ABI state struct keeps pointing at the same device memory
+        self.t = int(state["t"])
+
     # -- the driver loop, call by call (reference API granularity) ----------------------------------
     def iterate_unfused(self, learn: bool = True, draws: Optional[torch.Tensor] = None, auto_reset: bool = True):
         """One lockstep iteration through the separate entry points, in the reference drivers' order
