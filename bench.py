@@ -71,7 +71,7 @@ WORKLOADS = {
     "cfg5_shared": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, ONE table per agent index per GPU "
                     "(shared learner, synchronous proposal averaging), all-reduced every 64 iterations",
                     "configs[4]: 1M FrozenLake instances x 4 agents, shared-learner Q-table allreduce over NVLink every K steps",
-                    1048576, 64, 140, "train_kernel<FrozenLake,QRM> + apply_shared_kernel (L2/atomic bound, not HBM)"),
+                    1048576, 64, 140, "shared_propose_kernel<FrozenLake,QRM> + apply_shared_kernel (shared-memory wavefront bound, not HBM)"),
 }
 
 
