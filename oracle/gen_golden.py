@@ -137,6 +137,13 @@ def scenarios():
     sc.algo, sc.learning_rate, sc.q_init, sc.map_name = "qrm", 0.1, 2.0, "map1"
     sc.starts = sc.starts[:2]
     S["ow_chain12_qrm"] = (sc, 1, 1100, "f32", 1)
+
+    # long runs: the short fixtures above end before any agent completes its machine. These reach the learned regime
+    # (all RM states, goal rewards propagating, successful episodes); long_cfg1 is BASELINE configs[0] end to end
+    # (deterministic FrozenLake map1, 2 agents, QRM, 2000+ back-to-back episodes of the reference driver loop).
+    S["long_cfg1_det_qrm"] = (P.scenario_config1(), 1, 75000, "f32", 1)
+    S["long_cfg3_slip_qrm"] = (P.scenario_config3(True), 1, 40000, "f32", 1)
+    S["long_cfg2_office_det_ql"] = (P.scenario_config2(False), 1, 30000, "f32", 1)
     return S
 
 
