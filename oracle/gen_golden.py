@@ -144,6 +144,12 @@ def scenarios():
     S["long_cfg1_det_qrm"] = (P.scenario_config1(), 1, 75000, "f32", 1)
     S["long_cfg3_slip_qrm"] = (P.scenario_config3(True), 1, 40000, "f32", 1)
     S["long_cfg2_office_det_ql"] = (P.scenario_config2(False), 1, 30000, "f32", 1)
+    g1 = office_world_grid("map1")  # Q(lambda) with successful episodes: coffee (either machine) then the office, 2 agents
+    tr = [("u0", g1.coffee[0], "u1", 1.0), ("u0", g1.coffee[1], "u1", 1.0), ("u1", g1.goals["O"], "u2", 5.0)]
+    sc = Scenario(env="office_world", starts=[(2, 7), (6, 3)], rm_transitions=tr, detector_positions=sorted(set(g1.coffee) | {g1.goals["O"]}),
+                  stochastic=True, high_prob=0.8, algo="qlambda", learning_rate=0.1, lambd=0.9, gamma=0.9, epsilon_start=0.3,
+                  epsilon_end=0.3, epsilon_decay=1.0, q_init=0.0, driver="office_main", seed=71)
+    S["long_office_coffee_qlambda"] = (sc, 1, 20000, "f32", 1)
     return S
 
 

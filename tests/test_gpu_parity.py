@@ -314,7 +314,8 @@ def test_shared_learner_generic_path_equals_fast_path(cuda_device):
     assert np.array_equal(a.ep_return.cpu().numpy(), b.ep_return.cpu().numpy())
 
 
-@pytest.mark.parametrize("name,n,iters", [("cfg4_office_chain12_qlambda", 48, 1300), ("fl_qlambda", 64, 1500)])
+@pytest.mark.parametrize("name,n,iters", [("cfg4_office_chain12_qlambda", 48, 1300), ("fl_qlambda", 64, 1500),
+                                            ("long_office_coffee_qlambda", 8, 12000)])
 def test_sparse_exact_qlambda_equals_dense_and_oracle(name, n, iters, cuda_device):
     """The sparse-exact trace lists (live entries only, q values cached in the list) reproduce the dense sweep of
     QLearningLambda.update bit for bit: vs the dense CUDA kernel and vs the oracle, across several launches, with
