@@ -19,13 +19,12 @@ pytestmark = [pytest.mark.reference,
 SEEDS = list(range(0, 128, 4))
 
 
-@pytest.mark.parametrize("seed", SEEDS)
-def test_random_scenario_oracle_equals_live_reference(seed):
+@pytest.mark.parametrize("seed,n,T", [(s, 2, 220) for s in SEEDS] + [(s, 1, 3000) for s in range(1, 128, 16)])
+def test_random_scenario_oracle_equals_live_reference(seed, n, T):
     import ref_harness as H
 
     sc, _opts = random_scenario(seed)
     sc.max_steps, sc.shared_q = 1000, False
-    n, T = 2, 220
     ref = H.run_reference(sc.to_dict(), n, T, np.float32, pre_resets=1)
     c = P.compile_scenario(sc)
     o = O.Oracle(c, n, "f32")
