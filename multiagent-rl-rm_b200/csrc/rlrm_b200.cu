@@ -232,7 +232,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   {
     const long long n_ent = (long long)kp.A * kp.S4;
-    const long long need = (long long)off + n_ent * 20;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry
+    const long long need = (long long)off + n_ent * 21;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry + row max 4 B per 4 entries
     h->shared_smem_bytes = (int)need;
     h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
                       !(cfg->reserved & 1));

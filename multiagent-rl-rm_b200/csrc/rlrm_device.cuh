@@ -74,6 +74,8 @@ struct Acc {  // accumulators of one agent's shared table, or nulls
   int* cnt;
   float* last;
   bool smem;  // the accumulators live in shared memory (shared_propose_kernel)
+  const float* rmax;  // optional: max over actions of every table row as of the start of the iteration (proposals do not
+                      // touch Q until apply_shared_kernel, so it stays valid for the whole launch); null = read the row
 };
 
 struct DOut {  // rlrm_step_out_t by value
@@ -292,8 +294,8 @@ __device__ __forceinline__ float row_max(const float4& v) { return fmaxf(fmaxf(v
 __device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, unsigned s, int a, double r, unsigned sn, bool terminated,
                                          const Acc& acc) {
   const float cur = Q[s * 4 + a];
-  const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
-  const float mf = __fmul_rn(terminated ? 0.0f : 1.0f, row_max(nrow));
+  const float mx = acc.rmax ? acc.rmax[sn] : row_max(*reinterpret_cast<const float4*>(Q + sn * 4));
+  const float mf = __fmul_rn(terminated ? 0.0f : 1.0f, mx);
   const float inner = __fadd_rn(__double2float_rn(r), __fmul_rn(p.gamma_f, mf));
   float out;
   if (p.lr < 0.0) {  // lr = 1/visits is an np.float64: the outer expression is evaluated in double
@@ -402,7 +404,7 @@ __device__ __forceinline__ void agent_view(const KP& p_in, KP& p, Tab& tb, int a
   tb.qrm_states += (size_t)a * p_in.nQ;
 }
 __device__ __forceinline__ Acc make_acc(const KP& p, const DState& st, size_t base) {
-  Acc acc = {nullptr, nullptr, nullptr};
+  Acc acc = {nullptr, nullptr, nullptr, false, nullptr};
   if (p.shared_q && st.acc_sum) {
     acc.sum = st.acc_sum + base;
     acc.cnt = st.acc_cnt + base;

@@ -99,8 +99,12 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
   unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(Qs + n_ent);
   int* s_cnt = reinterpret_cast<int*>(s_sum + n_ent);
   float* s_last = reinterpret_cast<float*>(s_cnt + n_ent);
-  for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x)
-    reinterpret_cast<float4*>(Qs)[j] = __ldg(reinterpret_cast<const float4*>(st.q) + j);
+  float* s_rmax = s_last + n_ent;  // [n_ent / 4] max over actions of every row: one 4-byte read per counterfactual instead of 16
+  for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(st.q) + j);
+    reinterpret_cast<float4*>(Qs)[j] = v;
+    s_rmax[j] = row_max(v);
+  }
   for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
     s_sum[j] = 0ull;
     s_cnt[j] = 0;
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
         const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
         const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
         Acc acc = {reinterpret_cast<long long*>(s_sum) + (size_t)a * (size_t)p.S4, s_cnt + (size_t)a * (size_t)p.S4,
-                   s_last + (size_t)a * (size_t)p.S4, true};
+                   s_last + (size_t)a * (size_t)p.S4, true, s_rmax + (size_t)a * (size_t)(p.S4 / 4)};
         agent_update<ALGO>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
       }
       term = r.term;

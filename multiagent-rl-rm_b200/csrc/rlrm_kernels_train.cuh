@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p_in, DState st, 
   double eps = 0.0, ep_ret = 0.0;
   float* Q = nullptr;
   unsigned* V = nullptr;
-  Acc acc = {nullptr, nullptr, nullptr};
+  Acc acc = {nullptr, nullptr, nullptr, false, nullptr};
   unsigned long long active_steps = 0;
   unsigned episodes = 0, successes = 0, last_length = 0;
   double return_sum = 0.0;
