@@ -29,6 +29,7 @@ from .envs import MultiAgentFrozenLake, MultiAgentOfficeWorld  # noqa: E402,F401
 from .learners import QLearning, QLearningLambda  # noqa: E402,F401
 from .wrapper import RMEnvironmentWrapper  # noqa: E402,F401
 from . import rmspec  # noqa: E402,F401
-from .evaluation import load_q_tables, load_q_tables_into, save_q_tables, test_policy_optima_batched  # noqa: E402,F401
+from .evaluation import (extract_policy_from_qtable, load_q_tables, load_q_tables_into, save_q_tables,  # noqa: E402,F401
+                         test_policy_opt_multi_batched, test_policy_optima_batched)
 from .rmspec import compile_reward_machine, load_reward_machine, load_rmspec  # noqa: E402,F401
 from .vec import BatchedRMEnvironment  # noqa: E402,F401

@@ -82,3 +82,48 @@ def load_q_tables_into(engine, path_or_tables, agent_names: Optional[Sequence[st
             q[k].copy_(t.reshape(engine.S, 4))
         else:
             q[:, k].copy_(t if t.dim() == 3 else t.reshape(1, engine.S, 4).expand(engine.N, -1, -1))
+
+
+def test_policy_opt_multi_batched(engine, policies, episodes_test: int = 100, optimal_steps: float = 30, gamma: float = 0.9,
+                                  test_deterministic: Optional[bool] = None) -> Dict[str, np.ndarray]:
+    """Batched test_policy_opt_multi (evaluation_metrics.py:505-697): evaluate explicit per-agent policies
+    (``policy[s] = action index``, e.g. from extract_policy_from_qtable or a value-iteration solution) instead of the
+    learners' argmax. ``policies`` is [A, S] (one policy per agent for every instance) or [N, A, S].
+
+    The policy is played by the same device rollout as test_policy_optima_batched: it is turned into one-hot tables, whose
+    greedy action is unique, on a scratch engine compiled from the same scenario. Two details of the reference function are
+    kept: its loop stops at ``timestep < 1000`` — one step before the environment's own truncation — so the scratch
+    scenario's step cap is max_steps - 1; and ``test_deterministic`` sets ``env.stochastic = not test_deterministic``
+    (an attribute only OfficeWorld reads) and plays a single episode when true. Returns the per-(instance, agent)
+    statistics of test_policy_optima_batched (the reference's per-episode reward lists are not kept on the device)."""
+    import copy
+
+    from .engine import Engine
+    from .tables import compile_scenario
+
+    pol = policies.detach().cpu().numpy() if torch.is_tensor(policies) else np.asarray(policies)
+    if pol.ndim == 2:
+        pol = np.broadcast_to(pol[None], (engine.N,) + pol.shape)
+    if pol.shape != (engine.N, engine.A, engine.S):
+        raise ValueError(f"policies must be [A, S] or [N, A, S] with A={engine.A}, S={engine.S}; got {pol.shape}")
+    if pol.min() < 0 or pol.max() >= 4:
+        raise ValueError("policy holds an action index outside 0..3")
+    if engine.cfg.per_agent_rm or engine.cfg.shared_q:
+        raise NotImplementedError("explicit-policy evaluation is implemented for per-instance tables with one reward machine")
+    sc = copy.deepcopy(engine.c.scenario)
+    sc.max_steps = max(int(sc.max_steps) - 1, 0)
+    sc.algo, sc.learning_rate, sc.use_rsh, sc.random_start_positions = "ql", 1.0, False, sc.random_start_positions
+    if test_deterministic is not None:
+        if sc.env == "office_world":
+            sc.stochastic = not test_deterministic
+        if test_deterministic:
+            episodes_test = 1
+    scratch = Engine(compile_scenario(sc, instance_offset=int(engine.cfg.instance_offset)), engine.N, device=engine.device, with_stats=False)
+    onehot = torch.zeros_like(scratch.q).view(engine.N, engine.A, engine.S, 4)
+    onehot.scatter_(3, torch.from_numpy(np.ascontiguousarray(pol)).to(engine.device, torch.int64).unsqueeze(-1), 1.0)
+    scratch.q.copy_(onehot.view_as(scratch.q))
+    scratch.t = engine.t
+    return test_policy_optima_batched(scratch, episodes_test, optimal_steps, gamma)
+
+
+test_policy_opt_multi_batched.__test__ = False

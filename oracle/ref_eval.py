@@ -65,5 +65,12 @@ def reference_eval(sc: dict, q_tables, n_episodes: int, gamma: float, optimal_st
             from multiagent_rlrm.environments.utils_envs.evaluation_metrics import test_policy_optima
 
             own.append(test_policy_optima(rm_env, episodi_test=n_episodes, window_size=1, optimal_steps=optimal_steps, gamma=gamma))
+            # explicit-policy evaluation (test_policy_opt_multi, evaluation_metrics.py:505-697) of the greedy policy of the same tables
+            from multiagent_rlrm.environments.utils_envs.evaluation_metrics import test_policy_opt_multi
+
+            policy = {ag.name: np.argmax(ag.get_learning_algorithm().q_table, axis=1) for ag in agents}
+            res = test_policy_opt_multi(rm_env, policy, episodes_test=n_episodes, window_size=1, optimal_steps=optimal_steps, gamma=gamma)
+            for key, val in zip(("success_rate", "avg_timesteps", "avg_reward", "avg_arps"), (res[0], res[2], res[4], res[6])):
+                out.setdefault("optmulti_" + key, np.zeros((n, A)))[i] = [float(val[ag.name]) for ag in agents]
     out["reference_function_outputs"] = own
     return out
