@@ -237,6 +237,15 @@ class _TabularBase(BaseLearningAlgorithm):
                                             out.data_ptr(), self._th.stream()))
         return int(out.item())
 
+    def choose_action_greedy(self, encoded_state, rng):
+        """Uniform choice among the greedy actions (qlearning.py:136-143): the device selection with exploration switched off
+        for this one call, tie-break word taken from `rng`."""
+        eps, self.epsilon = self.epsilon, 0.0
+        try:
+            return self.choose_action(encoded_state, best=False, rng=rng)
+        finally:
+            self.epsilon = eps
+
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
         d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_slot", "_eps")}

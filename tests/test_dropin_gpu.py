@@ -67,6 +67,10 @@ def test_qlearning_epsilon_decay_and_choice(cuda_device):
     assert all(ql.choose_action(0) == 1 for _ in range(20))
     ql.epsilon = 1.0
     assert {ql.choose_action(0) for _ in range(64)} == {0, 1}
+    # choose_action_greedy (qlearning.py:136-143): never explores, whatever epsilon is; ties are split uniformly
+    assert all(ql.choose_action_greedy(0, ql.rng) == 1 for _ in range(20)) and ql.epsilon == 1.0
+    ql.q_table[0] = np.array([0.8, 0.8])
+    assert {ql.choose_action_greedy(0, ql.rng) for _ in range(64)} == {0, 1}
 
 
 def test_qlearning_lambda_update_and_traces_decay(cuda_device):

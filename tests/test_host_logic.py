@@ -262,6 +262,27 @@ def test_agent_select_and_update_plumbing():
         P.AgentRL("x", _Problem()).select_action({"pos_x": 0, "pos_y": 0})
 
 
+def test_agent_host_side_bookkeeping():
+    """agent_rl.py:237-335: add_rl_action, execute_action (preconditions / effects), message bookkeeping."""
+    from multiagent_rlrm_b200.actions import ActionRL
+    from multiagent_rlrm_b200.agent import Message
+
+    ag = P.AgentRL("a", _Problem())
+    ag.set_initial_position(1, 1)
+    hop = ActionRL("hop", [lambda agent: agent.get_position()[0] < 2], [lambda agent: agent.set_position(agent.get_position()[0] + 1, 1)])
+    ag.add_rl_action(hop)
+    assert ag.get_actions()[-1] is hop and ag.action("hop") is hop
+    assert ag.execute_action(hop) is True and ag.get_position() == (2, 1)
+    assert ag.execute_action(hop) is False and ag.get_position() == (2, 1)  # precondition no longer holds
+    with pytest.raises(ValueError):
+        ag.execute_action(None)
+    ag._receive_message(Message("b", [("door_open", True)]))
+    ag._receive_message("not a message")
+    assert ag.return_messages() == {("b", "door_open"): True}
+    ag.reset_messages()
+    assert ag.return_messages() == {} and ag.take_specific_action() is None
+
+
 # ---------------------------------------------------------------------------------------------- table compiler
 def test_slip_thresholds_equal_numpy_searchsorted():
     rng = np.random.default_rng(0)
