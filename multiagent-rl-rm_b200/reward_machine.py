@@ -207,6 +207,64 @@ class RewardMachine:
 
         return rm_distance(self, start_state)
 
+    def get_delta_u(self):
+        """delta_u[u1][u2] = event; every state is a key, also pure targets (reward_machine.py:280-292)."""
+        out = {}
+        for (u1, event), (u2, _r) in self.transitions.items():
+            out.setdefault(u1, {})
+            out.setdefault(u2, {})
+            out[u1][u2] = event
+        return out
+
+    def get_delta_r(self):
+        """delta_r[u1][u2] = ConstantRewardFunction(reward) (reward_machine.py:294-306)."""
+        out = {}
+        for (u1, _event), (u2, reward) in self.transitions.items():
+            out.setdefault(u1, {})
+            out.setdefault(u2, {})
+            out[u1][u2] = ConstantRewardFunction(reward)
+        return out
+
+    def value_iteration(self, U, delta_u, delta_r, terminal_u, gamma):
+        """In-place value iteration over the RM graph (reward_machine.py:308-345); non-constant rewards count as 0."""
+        V = {u: 0 for u in U}
+        V[terminal_u] = 0
+        err = 1
+        while err > 0.0000001:
+            err = 0
+            for u1 in U:
+                if not delta_u[u1]:
+                    continue
+                best = max((delta_r[u1][u2].get_reward(None) if delta_r[u1][u2].get_type() == "constant" else 0) + gamma * V[u2]
+                           for u2 in delta_u[u1])
+                err = max(err, abs(best - V[u1]))
+                V[u1] = best
+        return V
+
+
+class RewardFunction:
+    """reward_machine.py:348-357"""
+
+    def get_reward(self, s_info):
+        raise NotImplementedError("To be implemented")
+
+    def get_type(self):
+        raise NotImplementedError("To be implemented")
+
+
+class ConstantRewardFunction(RewardFunction):
+    """reward_machine.py:360-373"""
+
+    def __init__(self, c):
+        super().__init__()
+        self.c = c
+
+    def get_type(self):
+        return "constant"
+
+    def get_reward(self, s_info):
+        return self.c
+
 
 def builtin_frozen_lake_rm(goals: Dict[str, Tuple[int, int]], detector: Optional[EventDetector] = None) -> RewardMachine:
     """The A -> B -> C machine of frozen_lake_main.py:254-260 (rewards 10 / 15 / 20)."""

@@ -387,3 +387,11 @@ def test_potentials_equal_live_reference():
         ref_rm.add_distance_reward_shaping(sc.gamma, 0.9, alpha=7)
         mine.add_distance_reward_shaping(sc.gamma, 0.9, alpha=7)
         assert mine.potentials == ref_rm.potentials
+        # the public pieces add_reward_shaping is made of (reward_machine.py:280-345)
+        assert mine.get_delta_u() == ref_rm.get_delta_u()
+        dr_mine, dr_ref = mine.get_delta_r(), ref_rm.get_delta_r()
+        assert {u: {v: (f.get_type(), f.get_reward(None)) for v, f in d.items()} for u, d in dr_mine.items()} == \
+               {u: {v: (f.get_type(), f.get_reward(None)) for v, f in d.items()} for u, d in dr_ref.items()}
+        with contextlib.redirect_stdout(io.StringIO()):
+            v_ref = ref_rm.value_iteration(list(ref_rm.state_indices), ref_rm.get_delta_u(), dr_ref, ref_rm.get_final_state(), 0.8)
+        assert mine.value_iteration(list(mine.state_indices), mine.get_delta_u(), dr_mine, mine.get_final_state(), 0.8) == v_ref
