@@ -378,6 +378,10 @@ class MultiAgentOfficeWorld(BaseEnvironment):
             return self.plants_penalty_value
         return 0
 
+    def calculate_environment_rewards(self, agent, state, wall_penalty):
+        """wall penalty + plant penalty (ma_office.py:222-238); single-agent helper, the batched step computes the same sum"""
+        return wall_penalty + self.plants_in_the_office(state, agent.name)
+
     def check_terminations(self):
         terms = {a.name: bool(self.agent_fail[a.name]) for a in self.agents}
         truncs = {a.name: self.timestep > 1000 for a in self.agents}
