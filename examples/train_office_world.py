@@ -3,7 +3,8 @@
 on a batch of instances: authored reward-machine spec -> device tables -> fused training -> batched greedy evaluation, and the
 product MDP of the first agent through RMEnvironmentWrapper.get_mdp (what the reference feeds its value iteration).
 
-    python examples/train_office_world.py --rm-spec tests/fixtures/officeworld_acbd.json --algorithm QRM --instances 8192
+    python examples/train_office_world.py --experiment exp3 --algorithm QRM --instances 8192
+    python examples/train_office_world.py --rm-spec tests/fixtures/officeworld_acbd.json --algorithm QL --mdp
 """
 import argparse
 import os
@@ -19,7 +20,8 @@ from multiagent_rlrm_b200.rmspec import scenario_from_rmspec  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rm-spec", default=os.path.join(os.path.dirname(__file__), "..", "tests", "fixtures", "officeworld_acbd.json"))
+    ap.add_argument("--rm-spec", default=None, help="authored reward-machine spec (.json / .yaml); default: the built-in --experiment")
+    ap.add_argument("--experiment", default="exp4", help="built-in task of config_office.get_experiment_for_map (exp0 .. exp7)")
     ap.add_argument("--map", default="map1")
     ap.add_argument("--algorithm", default="QRM", choices=["QL", "QRM", "QL-lambda"])
     ap.add_argument("--stochastic", action="store_true")
@@ -34,7 +36,14 @@ def main():
     sc.algo = {"QL": "ql", "QRM": "qrm", "QL-lambda": "qlambda"}[args.algorithm]
     if sc.algo == "qlambda":
         sc.lambd, sc.learning_rate, sc.q_init = 0.9, 0.1, 0.0
-    sc, rm = scenario_from_rmspec(args.rm_spec, sc)
+    if args.rm_spec:
+        sc, rm = scenario_from_rmspec(args.rm_spec, sc)
+    else:
+        exp = P.get_experiment_for_map(args.map, args.experiment)
+        sc.rm_transitions = [(s, ev, t, r) for (s, ev), (t, r) in exp["transitions"].items()]
+        sc.detector_positions = sorted(exp["positions"])
+        rm = sc.reward_machine()
+        print(f"built-in task {args.experiment}: {exp['description']}")
     print(f"reward machine: {rm.numbers_state()} states, {len(rm.transitions)} transitions, final {rm.get_final_state()}")
     eng = Engine(P.compile_scenario(sc), args.instances, qlambda_sparse=(sc.algo == "qlambda"))
     eng.reset()
@@ -46,7 +55,8 @@ def main():
         st = eng.stats_numpy()
         print(f"iter {done:7d}: episodes {int(st['episodes'].sum()):9d}  successes {int(st['successes'].sum()):9d}  "
               f"active agent-steps {eng.total_active_steps():12d}")
-    res = P.test_policy_optima_batched(eng, episodi_test=3, optimal_steps=30, gamma=sc.gamma)
+    optimal = P.OPTIMAL.get(f"{args.map};{args.experiment}", 30)
+    res = P.test_policy_optima_batched(eng, episodi_test=3, optimal_steps=optimal, gamma=sc.gamma)
     print(f"greedy evaluation: success rate {res['success_rate'].mean():.1f} %")
 
     if args.mdp:

@@ -33,3 +33,4 @@ from .evaluation import (extract_policy_from_qtable, load_q_tables, load_q_table
                          test_policy_opt_multi_batched, test_policy_optima_batched)
 from .rmspec import compile_reward_machine, load_reward_machine, load_rmspec  # noqa: E402,F401
 from .vec import BatchedRMEnvironment  # noqa: E402,F401
+from .experiments import OPTIMAL, get_experiment_for_map, scenario_for_experiment  # noqa: E402,F401

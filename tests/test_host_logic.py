@@ -348,6 +348,48 @@ def test_slip_tables_equal_reference_probability_mappings():
             assert c.config.slip_n == len(probs)
 
 
+# ---------------------------------------------------------------------------------------------- built-in OfficeWorld tasks
+def test_builtin_office_experiments_known_answers():
+    """config_office.py:292-470: exp4 on map1 is A -> B -> C -> D with the reward on the last link (SURVEY.md §8 constants)."""
+    from multiagent_rlrm_b200.experiments import OPTIMAL, get_experiment_for_map, scenario_for_experiment
+
+    exp = get_experiment_for_map("map1", "exp4")
+    assert list(exp["transitions"].items()) == [(("state0", (1, 7)), ("state1", 0)), (("state1", (1, 1)), ("state2", 0)),
+                                                (("state2", (10, 1)), ("state3", 0)), (("state3", (10, 7)), ("state4", 1))]
+    assert exp["positions"] == {(1, 7), (1, 1), (10, 1), (10, 7)}
+    assert get_experiment_for_map("map1", "exp1")["transitions"][("state0", (8, 6))] == ("state1", 0)  # second coffee machine
+    assert get_experiment_for_map("map1", "no such experiment") is None
+    assert get_experiment_for_map("map4", "exp6")["transitions"] == get_experiment_for_map("map4", "exp7")["transitions"]
+    assert OPTIMAL["map1;exp4"] == 30 and OPTIMAL["map1;exp1"] == 15
+    sc = scenario_for_experiment("map1", "exp3", starts=[(2, 7)], algo="qrm")
+    c = P.compile_scenario(sc)
+    assert c.config.n_rm_states == 5 and c.config.rm_final == 4 and c.config.n_events == 4
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+def test_builtin_office_experiments_equal_live_reference():
+    import ast
+
+    import ref_harness as H
+
+    H._import_reference()  # puts the stub packages and /root/reference on sys.path
+    from multiagent_rlrm.environments.office_world.config_office import config, get_experiment_for_map as ref_get
+
+    from multiagent_rlrm_b200.experiments import OPTIMAL, get_experiment_for_map
+
+    for mp in config["maps"]:
+        for exp in ("exp0", "exp0_simply", "exp1", "exp2", "exp3", "exp4", "exp5", "exp6", "exp7", "unknown"):
+            r, m = ref_get(mp, exp), get_experiment_for_map(mp, exp)
+            if r is None:
+                assert m is None
+                continue
+            assert list(r["transitions"].items()) == list(m["transitions"].items()), (mp, exp)  # insertion order matters
+            assert r["positions"] == m["positions"] and r["description"] == m["description"], (mp, exp)
+    src = open("/root/reference/multiagent_rlrm/environments/office_world/office_main.py").read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "OPTIMAL")
+    assert ast.literal_eval(node.value) == OPTIMAL
+
+
 # ---------------------------------------------------------------------------------------------- reward shaping (f3)
 def test_distance_reward_shaping_known_answers():
     """/root/reference/tests/test_reward_machine_shaping.py: qf -> 0, one step away -> -alpha, two steps -> -2 alpha"""
