@@ -5,6 +5,8 @@ COMBINATIONS no fixture has (environment x map x number of agents x machine shap
 shaping x per-agent machines x random starts x shared learner x visit counts x short step caps that force frequent
 truncation and auto-reset). Scenarios are drawn from numpy Generators with fixed seeds, so a failure is reproducible
 from its test id."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,7 +16,7 @@ from multiagent_rlrm_b200.maps import frozen_lake_grid, office_world_grid
 
 pytestmark = pytest.mark.gpu
 
-N_CASES = 128
+N_CASES = int(os.environ.get("RLRM_FUZZ_CASES", "128"))  # raise for a one-off soak run (1024 cases take about a minute on a B200)
 
 
 def random_machine(rng, cells, tag):
