@@ -281,6 +281,20 @@ int rlrm_rm_step_agent(rlrm_handle_t* h, int agent, int64_t n_slots, uint8_t* q,
 int rlrm_mdp(rlrm_handle_t* h, int agent, int n_sub, const uint8_t* sub_actions, int rm_terminal, int32_t* next_state,
              double* reward, uint8_t* done, uint8_t* terminal, void* stream);
 
+/* mdp_vi.value_iteration (environments/utils_envs/mdp_vi.py:9-60) on the transition model get_mdp / rlrm_mdp produce, as padded
+ * outcome arrays (device): prob / next_state / reward / done are [n_states][4][n_outcomes], outcome order = list order of
+ * P[s][a], unused slots have prob 0. V starts at 0; a sweep sets Q[s][a] = sum prob * (reward + gamma * V[s'] * !done) and
+ * V[s] = max_a Q[s][a]; sweeps repeat until max_s |V_new[s] - V_old[s]| (divided by max(|V_new[s]|, 1e-12 -> 1) when
+ * delta_rel) < theta. The reference updates V in place while sweeping (Gauss-Seidel), this kernel sweeps all states in
+ * parallel from the previous V (Jacobi): same fixed point and stopping rule, so V agrees within 2*theta*gamma/(1-gamma), not
+ * bit for bit; policy[s] = first argmax of the final Q[s]. Outputs (device): V f64 [n_states], Q f64 [n_states][4], policy
+ * int32 [n_states]. work: device scratch of n_states + 1 doubles. sweeps_out (host, may be NULL) = sweeps performed.
+ * Needs no handle (the model is self-contained): `device` is the CUDA device the arrays live on. Synchronous (one 8-byte
+ * read-back per sweep). RLRM_ERR_UNSUPPORTED when max_sweeps is reached. */
+int rlrm_value_iteration(int device, int64_t n_states, int n_outcomes, const double* prob, const int32_t* next_state,
+                         const double* reward, const uint8_t* done, double gamma, double theta, int delta_rel, int max_sweeps,
+                         double* V, double* Q, int32_t* policy, double* work, int32_t* sweeps_out, void* stream);
+
 /* AgentRL.update_policy (agent_rl.py:117-192) -> QLearning.update (qlearning.py:41-110, incl. the QRM
  * counterfactual loop fed by rm_environment_wrapper.py:122-183) or QLearningLambda.update (qlearning_lambda.py:33-84).
  * obs_cell: device uint16 [N*A], the `state` argument the driver passes (previous observation);

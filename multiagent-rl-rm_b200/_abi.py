@@ -183,6 +183,7 @@ EXPORTED_SYMBOLS = (
     "rlrm_rm_step",
     "rlrm_rm_step_agent",
     "rlrm_mdp",
+    "rlrm_value_iteration",
     "rlrm_update",
     "rlrm_train",
     "rlrm_train_host",

@@ -89,6 +89,8 @@ def load():
     L.rlrm_rm_step.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.rlrm_rm_step_agent.argtypes = [vp, C.c_int, i64, vp, vp, vp, vp, vp]
     L.rlrm_mdp.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp]
+    L.rlrm_value_iteration.argtypes = [C.c_int, i64, C.c_int, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp,
+                                       C.POINTER(C.c_int32), vp]
     L.rlrm_update.argtypes = [vp, C.POINTER(abi.State), vp, vp, vp, C.POINTER(abi.StepOut), vp]
     L.rlrm_train.argtypes = [vp, C.POINTER(abi.State), u64, i32, i32, vp, vp]
     L.rlrm_train_host.argtypes = [vp, C.POINTER(abi.State), u64, i32, i32, vp, vp, vp, vp]
@@ -97,7 +99,7 @@ def load():
     L.rlrm_launch_count.argtypes = [vp]
     L.rlrm_launch_count.restype = i64
     for name in ("rlrm_create", "rlrm_destroy", "rlrm_set_learner", "rlrm_reset", "rlrm_reset_at", "rlrm_select_action", "rlrm_step",
-                 "rlrm_rm_step", "rlrm_rm_step_agent", "rlrm_mdp", "rlrm_update", "rlrm_train", "rlrm_train_host", "rlrm_evaluate", "rlrm_qlambda_materialize"):
+                 "rlrm_rm_step", "rlrm_rm_step_agent", "rlrm_mdp", "rlrm_value_iteration", "rlrm_update", "rlrm_train", "rlrm_train_host", "rlrm_evaluate", "rlrm_qlambda_materialize"):
         getattr(L, name).restype = C.c_int
     if L.rlrm_abi_version() != abi.ABI_VERSION:
         raise RuntimeError("librlrm_b200.so ABI version mismatch: rebuild")

@@ -415,6 +415,44 @@ extern "C" int rlrm_mdp(rlrm_handle_t* h, int agent, int n_sub, const uint8_t* s
   return RLRM_OK;
 }
 
+extern "C" int rlrm_value_iteration(int device, int64_t n_states, int n_outcomes, const double* prob, const int32_t* next_state,
+                                    const double* reward, const uint8_t* done, double gamma, double theta, int delta_rel, int max_sweeps,
+                                    double* V, double* Q, int32_t* policy, double* work, int32_t* sweeps_out, void* stream) {
+  if (!prob || !next_state || !reward || !done || !V || !Q || !policy || !work) return fail(RLRM_ERR_ARG, "null argument");
+  if (n_states <= 0 || n_outcomes < 1) return fail(RLRM_ERR_ARG, "n_states / n_outcomes out of range");
+  if (!(theta > 0.0) || max_sweeps < 1) return fail(RLRM_ERR_ARG, "theta must be positive and max_sweeps >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RLRM_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(RLRM_ERR_ARG, "device out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  double* v[2] = {V, work};  // ping-pong; the result is copied back into V at the end if it landed in work
+  unsigned long long* d_delta = reinterpret_cast<unsigned long long*>(work + n_states);
+  CUDA_TRY(cudaMemsetAsync(V, 0, (size_t)n_states * sizeof(double), s));  // V = 0 (mdp_vi.py:28)
+  int cur = 0, sweeps = 0;
+  for (;;) {
+    CUDA_TRY(cudaMemsetAsync(d_delta, 0, sizeof(unsigned long long), s));
+    vi_sweep_kernel<<<blocks_for(n_states, 256), 256, 0, s>>>(n_states, n_outcomes, prob, next_state, reward, done, gamma, delta_rel,
+                                                           v[cur], v[cur ^ 1], Q, policy, d_delta);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long bits = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bits, d_delta, sizeof(bits), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cur ^= 1;
+    sweeps++;
+    double delta;
+    memcpy(&delta, &bits, sizeof(delta));
+    if (delta < theta) break;  // mdp_vi.py:56-57
+    if (sweeps >= max_sweeps) {
+      if (sweeps_out) *sweeps_out = sweeps;
+      return fail(RLRM_ERR_UNSUPPORTED, "value iteration did not converge within max_sweeps");
+    }
+  }
+  if (cur == 1) CUDA_TRY(cudaMemcpyAsync(V, work, (size_t)n_states * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (sweeps_out) *sweeps_out = sweeps;
+  return RLRM_OK;
+}
+
 extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_cell, const uint8_t* actions,
                            const uint8_t* term_arg, const rlrm_step_out_t* out, void* stream) {
   int rc = check_state(h, st, true);

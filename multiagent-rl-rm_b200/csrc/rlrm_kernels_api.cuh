@@ -144,6 +144,52 @@ __global__ void __launch_bounds__(256) mdp_kernel(KP p_in, int agent, int n_sub,
   done[k] = (r.term || r.trunc) ? 1 : 0;
 }
 
+// Value iteration over a product MDP held as padded outcome arrays (mdp_vi.value_iteration, environments/utils_envs/mdp_vi.py:9-60,
+// consumes RMEnvironmentWrapper.get_mdp's P[s][a] = [(prob, s', reward, done), ...]). One thread per state and sweep:
+// Q[s][a] = sum_j prob * (reward + gamma * V[s'] * !done) in outcome order, V'[s] = max_a Q[s][a]. The reference sweeps the
+// states in place (Gauss-Seidel); a parallel sweep reads the previous V (Jacobi): same fixed point and same stopping rule,
+// different iterates — results agree to the tolerance the stopping rule implies, not bit for bit (tests/test_mdp.py).
+__global__ void __launch_bounds__(256) vi_sweep_kernel(long long S, int n_out, const double* prob, const int* next_state,
+                                                      const double* reward, const unsigned char* done, double gamma, int delta_rel,
+                                                      const double* v_in, double* v_out, double* Q, int* policy,
+                                                      unsigned long long* delta_bits) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double cdelta = 0.0;
+  if (s < S) {
+    double best = 0.0;
+    int arg = 0;
+    for (int a = 0; a < 4; a++) {
+      double q = 0.0;
+      const size_t base = ((size_t)s * 4 + a) * (size_t)n_out;
+      for (int j = 0; j < n_out; j++) {
+        const double pr = prob[base + j];
+        if (pr == 0.0) continue;  // padding
+        const double future = done[base + j] ? 0.0 : __dmul_rn(gamma, v_in[next_state[base + j]]);
+        q = __dadd_rn(q, __dmul_rn(pr, __dadd_rn(reward[base + j], future)));
+      }
+      Q[s * 4 + a] = q;
+      if (a == 0 || q > best) {
+        best = q;
+        arg = a;
+      }
+    }
+    v_out[s] = best;
+    policy[s] = arg;
+    const double diff = fabs(best - v_in[s]);
+    cdelta = delta_rel ? diff / (fabs(best) > 1e-12 ? fabs(best) : 1.0) : diff;
+  }
+  // block maximum, then one atomic per block; non-negative doubles order like their bit patterns
+  for (int o = 16; o > 0; o >>= 1) cdelta = fmax(cdelta, __shfl_xor_sync(0xFFFFFFFFu, cdelta, o));
+  __shared__ double wmax[8];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = cdelta;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = wmax[0];
+    for (int w = 1; w < 8; w++) m = fmax(m, wmax[w]);
+    atomicMax(delta_bits, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
 // RewardMachine.step on explicit (state, position) pairs (reward_machine.py:45-59)
 __global__ void __launch_bounds__(256) rm_step_kernel(KP p_in, int agent, long long n, unsigned char* q, const unsigned short* cell,
                                                      unsigned char* event_out, double* reward_out) {

@@ -79,7 +79,20 @@ def main():
             assert n_actions[ag.name] == 4
             c, p, n, r, dn = flatten(all_P[ag.name], n_states[ag.name])
             arrays.update({f"count_{k}": c, f"prob_{k}": p, f"next_{k}": n, f"reward_{k}": r, f"done_{k}": dn})
-        meta = {"scenario": d, "seed": 123, "n_states": [int(n_states[a.name]) for a in agents],
+        if sc.env == "office_world":
+            # the reference's own value iteration on this model (mdp_vi.py:9-60), both stopping rules: travels to the GPU box
+            # as the tolerance anchor for the device sweeps
+            import contextlib
+            import io
+
+            from multiagent_rlrm.environments.utils_envs.mdp_vi import value_iteration
+
+            for k, ag in enumerate(agents):
+                for tag, rel in (("abs", False), ("rel", True)):
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        V, pol, Q = value_iteration(all_P[ag.name], n_states[ag.name], 4, gamma=0.9, theta=1e-4, delta_rel=rel)
+                    arrays.update({f"vi_{tag}_V_{k}": V, f"vi_{tag}_policy_{k}": np.asarray(pol, dtype=np.int32), f"vi_{tag}_Q_{k}": Q})
+        meta = {"scenario": d, "seed": 123, "vi": {"gamma": 0.9, "theta": 1e-4}, "n_states": [int(n_states[a.name]) for a in agents],
                 "stochastic_after": getattr(env, "stochastic", None), "generator": "oracle/gen_mdp_golden.py"}
         np.savez_compressed(os.path.join(out_dir, "mdp_" + name + ".npz"), meta=json.dumps(meta), **arrays)
         tot = sum(int(arrays[f"count_{k}"].sum()) for k in range(len(agents)))

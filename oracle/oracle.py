@@ -173,6 +173,22 @@ class Oracle:
         return unpack_slots(self.slot, self.N, self.A)
 
 
+def value_iteration(prob, next_state, reward, done, gamma=0.9, theta=1e-3, delta_rel=False):
+    """mdp_vi.value_iteration restated (oracle_value_iteration, in-place Gauss-Seidel sweeps) on padded [S, 4, n_out] arrays."""
+    prob = np.ascontiguousarray(prob, dtype=np.float64)
+    S, _four, n_out = prob.shape
+    nxt = np.ascontiguousarray(next_state, dtype=np.int32)
+    rew = np.ascontiguousarray(reward, dtype=np.float64)
+    dn = np.ascontiguousarray(done, dtype=np.uint8)
+    V, Q, pol, old = np.zeros(S), np.zeros((S, 4)), np.zeros(S, dtype=np.int32), np.zeros(S)
+    L = lib("f64")
+    L.oracle_value_iteration.restype = C.c_int
+    sweeps = L.oracle_value_iteration(C.c_int64(S), C.c_int(n_out), C.c_void_p(_p(prob)), C.c_void_p(_p(nxt)), C.c_void_p(_p(rew)),
+                                      C.c_void_p(_p(dn)), C.c_double(gamma), C.c_double(theta), C.c_int(int(delta_rel)),
+                                      C.c_void_p(_p(V)), C.c_void_p(_p(Q)), C.c_void_p(_p(pol)), C.c_void_p(_p(old)))
+    return V, pol, Q, sweeps
+
+
 def unpack_slots(slot, N, A):
     s = np.asarray(slot, dtype=np.uint64).reshape(N, A)
     return {

@@ -364,6 +364,49 @@ int oracle_mdp(const rlrm_config_t* cfg_in, const rlrm_tables_t* tb, int agent, 
   return 0;
 }
 
+/* ---- mdp_vi.value_iteration (environments/utils_envs/mdp_vi.py:9-60), literally: V = 0; repeat { old_V = V.copy(); for s in
+ * order: q[a] = sum over P[s][a] of prob * (reward + gamma * V[s_next] * (not done)) -- V is updated IN PLACE while sweeping;
+ * delta = max |max_q - old_V[s]| (relative variant: / |max_q| when > 1e-12) } until delta < theta; policy = argmax(Q, axis=1).
+ * P is given as padded arrays [S][4][n_out], prob 0 = unused slot. Returns the number of sweeps. */
+int oracle_value_iteration(int64_t S, int n_out, const double* prob, const int32_t* next_state, const double* reward,
+                           const uint8_t* done, double gamma, double theta, int delta_rel, double* V, double* Q, int32_t* policy,
+                           double* old_v) {
+  for (int64_t s = 0; s < S; s++) V[s] = 0.0;
+  for (int64_t k = 0; k < S * 4; k++) Q[k] = 0.0;
+  int sweeps = 0;
+  for (;;) {
+    double delta = 0.0;
+    memcpy(old_v, V, (size_t)S * sizeof(double));
+    for (int64_t s = 0; s < S; s++) {
+      double max_q = 0.0;
+      for (int a = 0; a < 4; a++) {
+        double q = 0.0;
+        size_t base = ((size_t)s * 4 + a) * (size_t)n_out;
+        for (int j = 0; j < n_out; j++) {
+          if (prob[base + j] == 0.0) continue;
+          double fut = gamma * V[next_state[base + j]];
+          fut = done[base + j] ? fut * 0.0 : fut * 1.0; /* gamma * V[s_next] * (not done) */
+          q += prob[base + j] * (reward[base + j] + fut);
+        }
+        Q[s * 4 + a] = q;
+        if (a == 0 || q > max_q) max_q = q;
+      }
+      double diff = fabs(max_q - old_v[s]);
+      double cdelta = delta_rel ? diff / (fabs(max_q) > 1e-12 ? fabs(max_q) : 1.0) : diff;
+      if (cdelta > delta) delta = cdelta;
+      V[s] = max_q;
+    }
+    sweeps++;
+    if (delta < theta) break;
+  }
+  for (int64_t s = 0; s < S; s++) {
+    int arg = 0;
+    for (int a = 1; a < 4; a++) if (Q[s * 4 + a] > Q[s * 4 + arg]) arg = a;
+    policy[s] = arg;
+  }
+  return sweeps;
+}
+
 int oracle_rm_step(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int64_t n_slots, uint8_t* q, const uint16_t* cell,
                    uint8_t* event_out, double* reward_out) {
   int nEv = cfg->n_events;

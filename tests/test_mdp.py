@@ -141,3 +141,87 @@ def test_wait_action_through_the_env_api():
     _obs, rewards, term, trunc, _infos = rm_env.step({agents[0].name: env.wait_action})
     assert tuple(agents[0].get_position()) == before and rewards[agents[0].name] == 0
     assert not term[agents[0].name] and not trunc[agents[0].name] and env.timestep == 1
+
+
+# ---------------------------------------------------------------------------------------------- value iteration on the model
+OFFICE = [n for n in NAMES if n.startswith("office")]
+VI_TOL = 2 * 1e-4 * 0.9 / (1 - 0.9)  # both solvers stop within theta*gamma/(1-gamma) of the fixed point (theta 1e-4, gamma 0.9)
+
+
+def golden_arrays(z, k):
+    count, prob = z[f"count_{k}"], z[f"prob_{k}"].copy()
+    prob[np.arange(4)[None, None, :] >= count[:, :, None]] = 0.0  # slots past the list length carry no probability
+    return prob, z[f"next_{k}"], z[f"reward_{k}"], z[f"done_{k}"]
+
+
+@pytest.mark.parametrize("name", OFFICE)
+def test_oracle_value_iteration_equals_reference(name):
+    """The oracle's in-place (Gauss-Seidel) sweeps == the reference's mdp_vi.value_iteration output stored in the fixture,
+    bit for bit, for the absolute and the relative stopping rule."""
+    import oracle as O
+
+    z, meta = load(name)
+    for k in range(len(meta["n_states"])):
+        for tag, rel in (("abs", False), ("rel", True)):
+            V, pol, Q, sweeps = O.value_iteration(*golden_arrays(z, k), gamma=meta["vi"]["gamma"], theta=meta["vi"]["theta"], delta_rel=rel)
+            assert np.array_equal(V, z[f"vi_{tag}_V_{k}"]) and np.array_equal(Q, z[f"vi_{tag}_Q_{k}"]), (name, k, tag)
+            assert np.array_equal(pol, z[f"vi_{tag}_policy_{k}"]) and sweeps > 1
+
+
+def test_mdp_to_arrays_round_trip():
+    from multiagent_rlrm_b200.mdp_vi import mdp_to_arrays
+
+    z, meta = load("office_chain12_delay_wallterm_plantterm")
+    prob, nxt, rew, done = mdp_to_arrays(golden_P(z, 0), meta["n_states"][0], 4)
+    g = golden_arrays(z, 0)
+    assert np.array_equal(prob, g[0]) and np.array_equal(nxt * (prob > 0), g[1] * (g[0] > 0))
+    assert np.array_equal(rew * (prob > 0), g[2] * (g[0] > 0)) and np.array_equal(done * (prob > 0), g[3] * (g[0] > 0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", OFFICE)
+def test_cuda_value_iteration_within_tolerance_of_reference(name):
+    """Device sweeps are Jacobi, the reference's are Gauss-Seidel: same fixed point, same stopping rule. Tolerance (stated):
+    |V - V_ref| <= 2*theta*gamma/(1-gamma) = 1.8e-3 for theta = 1e-4, gamma = 0.9; the chosen actions must be optimal for the
+    reference's Q up to the same tolerance."""
+    from multiagent_rlrm_b200.mdp_vi import value_iteration, value_iteration_arrays
+
+    z, meta = load(name)
+    for k in range(len(meta["n_states"])):
+        arrays = golden_arrays(z, k)
+        for tag, rel in (("abs", False), ("rel", True)):
+            V, pol, Q, sweeps = value_iteration_arrays(*arrays, gamma=0.9, theta=1e-4, delta_rel=rel)
+            V, pol, Q = V.cpu().numpy(), pol.cpu().numpy(), Q.cpu().numpy()
+            V_ref, Q_ref = z[f"vi_{tag}_V_{k}"], z[f"vi_{tag}_Q_{k}"]
+            scale = np.maximum(np.abs(V_ref), 1.0) if rel else 1.0
+            assert np.max(np.abs(V - V_ref) / scale) <= VI_TOL, (name, k, tag, float(np.max(np.abs(V - V_ref))))
+            assert np.max(np.abs(Q - Q_ref) / (np.maximum(np.abs(Q_ref), 1.0) if rel else 1.0)) <= VI_TOL
+            chosen = Q_ref[np.arange(len(pol)), pol]
+            assert np.all(chosen >= Q_ref.max(axis=1) - 2 * VI_TOL * (np.maximum(np.abs(Q_ref.max(axis=1)), 1.0) if rel else 1.0))
+            assert 1 < sweeps < 10000
+    # drop-in signature on the reference's dictionary
+    V2, pol2, Q2 = value_iteration(golden_P(z, 0), meta["n_states"][0], 4, gamma=0.9, theta=1e-4)
+    assert V2.shape == (meta["n_states"][0],) and Q2.shape == (meta["n_states"][0], 4) and pol2.dtype == np.int64
+    assert np.max(np.abs(V2 - z["vi_abs_V_0"])) <= VI_TOL
+
+
+@pytest.mark.gpu
+def test_vi_comparison_pipeline_on_device(cuda_device):
+    """The reference's VI comparison end to end (office_main.py:1117-1140, 1408-1431): get_mdp -> value_iteration -> play the VI
+    policy with test_policy_opt_multi. On the deterministic A -> C -> B -> D task the VI policy must solve every episode in
+    the optimal number of steps its own value function implies."""
+    import multiagent_rlrm_b200 as P
+    from multiagent_rlrm_b200.engine import Engine
+    from multiagent_rlrm_b200.evaluation import test_policy_opt_multi_batched
+    from multiagent_rlrm_b200.mdp_vi import value_iteration
+
+    _z, meta = load("office_acbd_det")
+    rm_env, env, agents = build_b200(meta["scenario"])
+    all_P, n_states, n_actions = rm_env.get_mdp(1)
+    V, policy, Q = value_iteration(all_P["a1"], n_states["a1"], n_actions["a1"], gamma=0.9, theta=1e-6)
+    c = P.compile_scenario(P.Scenario.from_dict(meta["scenario"]))
+    res = test_policy_opt_multi_batched(Engine(c, 3), policy[None, :], episodes_test=2, optimal_steps=30, gamma=0.9)
+    assert (res["success_rate"] == 100.0).all()
+    steps = float(res["avg_timesteps"][0, 0])
+    start = (7 * env.grid_width + 2) * agents[0].get_reward_machine().numbers_state()  # (2, 7), initial RM state
+    assert abs(V[start] - 0.9 ** (steps - 1) * 1.0) < 1e-4  # one reward of 1 on the last of `steps` moves, discounted
