@@ -34,3 +34,4 @@ from .evaluation import (extract_policy_from_qtable, load_q_tables, load_q_table
 from .rmspec import compile_reward_machine, load_reward_machine, load_rmspec  # noqa: E402,F401
 from .vec import BatchedRMEnvironment  # noqa: E402,F401
 from .experiments import OPTIMAL, get_experiment_for_map, scenario_for_experiment  # noqa: E402,F401
+from .mdp_vi import mdp_to_arrays, value_iteration, value_iteration_arrays  # noqa: E402,F401
