@@ -74,6 +74,13 @@ def main():
         all_P, n_states, n_actions = P.RMEnvironmentWrapper(env, [ag]).get_mdp(args.seed)
         n_term = sum(1 for s in all_P["a1"] if all_P["a1"][s][0][0][3] and all_P["a1"][s][0][0][1] == s)
         print(f"product MDP of a1: {n_states['a1']} states x {n_actions['a1']} actions, {n_term} terminal states")
+        # the reference's VI comparison (office_main.py:1117-1140, 1408-1431): solve the model, play the VI policy
+        V, policy_vi, _Q = P.value_iteration(all_P["a1"], n_states["a1"], n_actions["a1"], gamma=sc.gamma, theta=1e-4)
+        if eng.A == 1 and not sc.stochastic:
+            res_vi = P.test_policy_opt_multi_batched(eng, policy_vi[None, :], episodes_test=1, optimal_steps=optimal, gamma=sc.gamma)
+            print(f"value iteration: V(start) = {V[(sc.starts[0][1] * g.width + sc.starts[0][0]) * rm.numbers_state()]:.4f}; "
+                  f"VI policy success rate {res_vi['success_rate'].mean():.1f} %, {res_vi['avg_timesteps'].mean():.0f} steps "
+                  f"(learned policy: {res['success_rate'].mean():.1f} %, {res['avg_timesteps'][res['avg_timesteps'] > 0].mean() if (res['avg_timesteps'] > 0).any() else 0:.0f} steps; optimal {optimal})")
 
 
 if __name__ == "__main__":

@@ -120,7 +120,7 @@ def test_policy_opt_multi_batched(engine, policies, episodes_test: int = 100, op
             episodes_test = 1
     scratch = Engine(compile_scenario(sc, instance_offset=int(engine.cfg.instance_offset)), engine.N, device=engine.device, with_stats=False)
     onehot = torch.zeros_like(scratch.q).view(engine.N, engine.A, engine.S, 4)
-    onehot.scatter_(3, torch.from_numpy(np.ascontiguousarray(pol)).to(engine.device, torch.int64).unsqueeze(-1), 1.0)
+    onehot.scatter_(3, torch.from_numpy(np.array(pol, dtype=np.int64)).to(engine.device).unsqueeze(-1), 1.0)
     scratch.q.copy_(onehot.view_as(scratch.q))
     scratch.t = engine.t
     return test_policy_optima_batched(scratch, episodes_test, optimal_steps, gamma)

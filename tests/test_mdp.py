@@ -225,3 +225,29 @@ def test_vi_comparison_pipeline_on_device(cuda_device):
     steps = float(res["avg_timesteps"][0, 0])
     start = (7 * env.grid_width + 2) * agents[0].get_reward_machine().numbers_state()  # (2, 7), initial RM state
     assert abs(V[start] - 0.9 ** (steps - 1) * 1.0) < 1e-4  # one reward of 1 on the last of `steps` moves, discounted
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,steps", [("map1;exp1", 15), ("map1;exp2", 29), ("map1;exp3", 29), ("map1;exp4", 30), ("map1;exp5", 55),
+                                       ("map1;exp6", 75), ("map0;exp0_simply", 18), ("map0;exp0", 45), ("map2;exp1", 38)])
+def test_vi_policy_length_equals_reference_optimal_steps(key, steps, cuda_device):
+    """The only task constants the reference ships are the optimal path lengths OPTIMAL (office_main.py:111-135). Solving the
+    product MDP of the built-in task (rlrm_mdp -> rlrm_value_iteration) and playing the VI policy on the device must take exactly
+    that many steps: all six map1 tasks and map0's exp0_simply reproduce the reference's constants. For (map0, exp0) and
+    (map2, exp1) the reference's constants (28, 48) do not match its own code: its get_mdp + value_iteration + environment give
+    45 and 38 (checked live in the build container), which is what is asserted here."""
+    import multiagent_rlrm_b200 as P
+    from multiagent_rlrm_b200.engine import Engine
+    from multiagent_rlrm_b200.maps import office_world_grid
+    from multiagent_rlrm_b200.mdp_vi import value_iteration_arrays
+
+    mp, exp = key.split(";")
+    if mp == "map1" or exp == "exp0_simply":
+        assert P.OPTIMAL[key] == steps
+    g = office_world_grid(mp)
+    sc = P.scenario_for_experiment(mp, exp, starts=[g.start], algo="ql", learning_rate=1.0, gamma=0.9, stochastic=False)
+    eng = Engine(P.compile_scenario(sc), 1)
+    nxt, rew, done, _term = eng.mdp(0, [[0], [1], [2], [3]])
+    _V, pol, _Q, _sweeps = value_iteration_arrays(np.ones_like(rew), nxt, rew, done, gamma=0.99, theta=1e-12)
+    res = P.test_policy_opt_multi_batched(eng, pol.cpu().numpy()[None, :], episodes_test=1, optimal_steps=steps, gamma=0.9)
+    assert float(res["success_rate"][0, 0]) == 100.0 and float(res["avg_timesteps"][0, 0]) == steps
