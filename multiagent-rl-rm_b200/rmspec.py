@@ -144,7 +144,8 @@ def _no_duplicates(items, label):
         seen.add(it)
 
 
-def validate_spec(spec: RMSpec) -> None:
+def validate_schema(spec: RMSpec) -> None:
+    """Structural checks (rmgen/validator.py:18-57)."""
     if not spec.states:
         raise ValidationError("states must be non-empty")
     _no_duplicates(spec.states, "state")
@@ -169,11 +170,21 @@ def validate_spec(spec: RMSpec) -> None:
             raise ValidationError(f"transition event {t.event} not in vocabulary")
     if not any(spec.initial_state in (t.from_state, t.to_state) for t in spec.transitions):
         raise ValidationError(f"initial_state {spec.initial_state} has no incident transitions")
+
+
+def ensure_deterministic(spec: RMSpec) -> None:
+    """One target per (state, event) (rmgen/validator.py:60-69)."""
     target = {}
-    for t in spec.transitions:  # determinism
+    for t in spec.transitions:
         key = (t.from_state, t.event)
         if target.setdefault(key, t.to_state) != t.to_state:
             raise ValidationError(f"Non-deterministic transitions for {key}: {target[key]} vs {t.to_state}")
+
+
+def validate_spec(spec: RMSpec) -> None:
+    """All validations; raises ValidationError on the first failure (rmgen/validator.py:72-77)."""
+    validate_schema(spec)
+    ensure_deterministic(spec)
 
 
 def validate_semantics(spec: RMSpec, *, max_positive_reward_transitions=None, terminal_reward_must_be_zero=True) -> None:
