@@ -498,6 +498,51 @@ def load_reward_machine(path, env: str, map_name: str = "map1", *, complete_miss
     return rm, spec
 
 
+def export_spec_to_file(spec: RMSpec, output_path) -> None:
+    """Write the spec back in the on-disk JSON format load_rmspec reads (rmgen/exporter.py:28-31): the output side of f1."""
+    out = Path(output_path)
+    out.parent.mkdir(parents=True, exist_ok=True)
+    with out.open("w", encoding="utf-8") as f:
+        json.dump(spec.to_dict(), f, indent=2, ensure_ascii=True)
+
+
+def build_reward_machine(spec: RMSpec, event_detector=None):
+    """RewardMachine over the spec's own event names (rmgen/exporter.py:34-50): no position mapping, the default detector
+    passes the ``event`` field of the state dict through. Initial state and index map follow the spec's initial_state."""
+    from .reward_machine import RewardMachine
+
+    rm = RewardMachine(spec.as_transition_map(), event_detector or PassthroughEventDetector(spec.event_vocabulary))
+    rm.initial_state = spec.initial_state
+    rm.current_state = spec.initial_state
+    rm.state_indices = rm._generate_state_indices()
+    return rm
+
+
+def format_rmspec_summary(spec: RMSpec, *, agent_names=None, source=None, max_core_transition_lines=200) -> str:
+    """The readable summary the drivers log after loading a spec (rmgen/summary.py:8-67; office_main.py:525,
+    frozen_lake_main.py:170): header, agents, sizes, the non-self-loop transitions in sorted order, the rewarded ones."""
+    out = ["Reward Machine summary" + (f" (from {source})" if source else "")]
+    names = list(agent_names) if agent_names else []
+    if len(names) == 1:
+        out.append(f"Agent: {names[0]}")
+    elif names:
+        out.append("Shared by agents: [" + ", ".join(names) + "]")
+    out += [f"name: {spec.name}", f"env_id: {spec.env_id}",
+            f"states: {len(spec.states)} (initial: {spec.initial_state}, terminal: {spec.terminal_states})",
+            f"event_vocabulary ({len(spec.event_vocabulary)}): " + ", ".join(spec.event_vocabulary),
+            f"transitions_total: {len(spec.transitions)}"]
+    core = sorted((t for t in spec.transitions if t.from_state != t.to_state), key=lambda t: (t.from_state, t.event, t.to_state))
+    out += [f"core_transitions_count: {len(core)}", "core_transitions (excluding self-loops):"]
+    shown = core if max_core_transition_lines is None else core[:max_core_transition_lines]
+    out += [f"- {t.from_state} --{t.event}--> {t.to_state}" for t in shown]
+    if max_core_transition_lines is not None and len(core) > max_core_transition_lines:
+        out.append("... truncated")
+    rewarded = [t for t in spec.transitions if t.reward > 0]
+    out.append(f"transitions_with_reward>0: {len(rewarded)}")
+    out += [f"- {t.from_state} --{t.event}--> {t.to_state} (reward={t.reward})" for t in rewarded]
+    return "\n".join(out)
+
+
 def scenario_from_rmspec(path, scenario, **kwargs):
     """Fill `scenario.rm_transitions` / `detector_positions` from a spec file, so `compile_scenario(scenario)` emits the
     device tables directly from (spec file, map name). Note: a Scenario's machine starts in the source of its first

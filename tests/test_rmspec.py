@@ -199,3 +199,38 @@ def test_per_agent_spec_files_compile_to_per_agent_tables(tmp_path):
     g = P.frozen_lake_grid("map1").goals
     col = {ev: k for k, ev in enumerate(c.events)}
     assert c.delta[1, 0, col[g["C"]]] == 1 and c.rq[1, 1, col[g["A"]]] == 7.0 and c.delta[1, 0, col[g["A"]]] == 255
+
+
+def test_export_round_trip_and_passthrough_machine(tmp_path):
+    """rmgen/exporter.py: export_spec_to_file writes what load_rmspec reads; build_reward_machine runs on the spec's own events."""
+    spec = R.load_rmspec(os.path.join(FIX, "officeworld_acbd.json"))
+    out = tmp_path / "nested" / "dir" / "spec.json"
+    R.export_spec_to_file(spec, out)
+    assert R.load_rmspec(out).to_dict() == spec.to_dict()
+    rm = R.build_reward_machine(spec)
+    assert rm.initial_state == spec.initial_state and rm.get_state_index(spec.initial_state) == 0
+    first = spec.transitions[0]
+    assert rm.step({"event": first.event}) == first.reward and rm.get_current_state() == first.to_state
+    assert rm.step({"event": "not in the vocabulary"}) == 0 and rm.get_current_state() == first.to_state
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs /root/reference")
+@pytest.mark.parametrize("fixture", ["officeworld_acbd.json", "officeworld_chain12.json", "frozenlake_abc.json"])
+def test_exporter_equals_live_reference(fixture, tmp_path):
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "ref_shim"), "/root/reference"]
+    from multiagent_rlrm.rmgen import exporter as rexp
+    from multiagent_rlrm.rmgen import io as rio
+
+    path = os.path.join(FIX, fixture)
+    mine, theirs = tmp_path / "mine.json", tmp_path / "theirs.json"
+    R.export_spec_to_file(R.load_rmspec(path), mine)
+    rexp.export_spec_to_file(rio.load_rmspec(path), theirs)
+    assert mine.read_bytes() == theirs.read_bytes()  # the on-disk format, byte for byte
+    from multiagent_rlrm.rmgen.summary import format_rmspec_summary as ref_summary
+
+    for kw in ({}, {"agent_names": ["a1"], "source": "x.json"}, {"agent_names": ["a1", "a2"], "max_core_transition_lines": 2},
+               {"max_core_transition_lines": None}):
+        assert R.format_rmspec_summary(R.load_rmspec(path), **kw) == ref_summary(rio.load_rmspec(path), **kw)
+    a, b = R.build_reward_machine(R.load_rmspec(path)), rexp.build_reward_machine(rio.load_rmspec(path))
+    assert list(a.transitions.items()) == list(b.transitions.items()) and a.state_indices == b.state_indices
+    assert a.initial_state == b.initial_state and a.get_final_state() == b.get_final_state()
