@@ -234,3 +234,61 @@ def test_exporter_equals_live_reference(fixture, tmp_path):
     a, b = R.build_reward_machine(R.load_rmspec(path)), rexp.build_reward_machine(rio.load_rmspec(path))
     assert list(a.transitions.items()) == list(b.transitions.items()) and a.state_indices == b.state_indices
     assert a.initial_state == b.initial_state and a.get_final_state() == b.get_final_state()
+
+
+# ---- known answers of the reference's remaining spec tests --------------------------------------------------------------
+_BASE = {"name": "reward_test", "env_id": "env", "version": "1.0", "states": ["q0", "q1"], "initial_state": "q0",
+         "terminal_states": ["q1"], "event_vocabulary": ["e"]}
+
+
+@pytest.mark.parametrize("raw,expected", [("r0", 0.0), ("r1", 1.0), ("r0.5", 0.5), ("1", 1.0), (2, 2.0)])
+def test_reward_strings_and_env_id_normalisation(raw, expected):
+    """/root/reference/tests/test_rmgen_rewards.py:28-49"""
+    spec = R.RMSpec.from_dict({**_BASE, "transitions": [{"from_state": "q0", "event": "e", "to_state": "q1", "reward": raw}]})
+    assert spec.transitions[0].reward == expected
+    with pytest.raises(ValueError):
+        R.RMSpec.from_dict({**_BASE, "transitions": [{"from_state": "q0", "event": "e", "to_state": "q1", "reward": "not_a_number"}]})
+    upper = R.RMSpec.from_dict({**_BASE, "env_id": "OfficeWorld ", "transitions": [{"from_state": "q0", "event": "e", "to_state": "q1", "reward": 0}]})
+    assert upper.env_id == "officeworld"
+
+
+def test_semantic_limits_known_answers():
+    """/root/reference/tests/test_rmgen_semantics.py:14-62 (the checks the generation pipeline applies to a spec)"""
+    two_rewards = R.RMSpec.from_dict({"name": "pos_limit", "env_id": "env", "version": "1.0", "states": ["q0"], "initial_state": "q0",
+                                      "terminal_states": [], "event_vocabulary": ["e1", "e2"],
+                                      "transitions": [{"from_state": "q0", "event": "e1", "to_state": "q0", "reward": 1},
+                                                      {"from_state": "q0", "event": "e2", "to_state": "q0", "reward": 1}]})
+    R.validate_spec(two_rewards)
+    with pytest.raises(R.ValidationError):
+        R.validate_semantics(two_rewards, max_positive_reward_transitions=1)
+    terminal_reward = R.RMSpec.from_dict({"name": "terminal_reward", "env_id": "env", "version": "1.0", "states": ["q0"],
+                                          "initial_state": "q0", "terminal_states": ["q0"], "event_vocabulary": ["e1"],
+                                          "transitions": [{"from_state": "q0", "event": "e1", "to_state": "q0", "reward": 1}]})
+    with pytest.raises(R.ValidationError):
+        R.validate_semantics(terminal_reward, terminal_reward_must_be_zero=True)
+    R.validate_semantics(terminal_reward, terminal_reward_must_be_zero=False)
+
+
+def test_summary_known_answers():
+    """/root/reference/tests/test_rmspec_summary.py:8-34"""
+    spec = R.RMSpec(name="core_only", env_id="officeworld", version="1.0", states=["q0", "q1"], initial_state="q0", terminal_states=["q1"],
+                    event_vocabulary=["at(C)", "at(E)"],
+                    transitions=[R.TransitionSpec("q0", "at(C)", "q1", 0.0), R.TransitionSpec("q0", "at(E)", "q0", 0.0)])
+    text = R.format_rmspec_summary(spec)
+    assert "core_transitions_count: 1" in text and "q0 --at(C)--> q1" in text and "q0 --at(E)--> q0" not in text
+    acbd = R.format_rmspec_summary(R.load_rmspec(os.path.join(FIX, "officeworld_acbd.json")), agent_names=["agent0"], source="f.json")
+    assert "env_id: officeworld" in acbd and "reward=1.0" in acbd and acbd.splitlines()[0] == "Reward Machine summary (from f.json)"
+
+
+def test_reward_machine_extras_known_answers():
+    """/root/reference/tests/test_reward_machine_extras.py:12-25"""
+    import multiagent_rlrm_b200 as P
+
+    class Detector:
+        def detect_event(self, _state):
+            return None
+
+    rm = P.RewardMachine({("q0", "a"): ("q1", 0)}, Detector())
+    assert rm.get_distance("q_missing") == 999999
+    V = rm.value_iteration(list(rm.state_indices.keys()), rm.get_delta_u(), rm.get_delta_r(), rm.get_final_state(), gamma=0.9)
+    assert V[rm.get_final_state()] == 0
