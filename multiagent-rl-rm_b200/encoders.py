@@ -62,3 +62,28 @@ def encode_state(agent, state, state_reward_machine):
     if enc >= width * height * n_rm:
         raise ValueError("Encoded state index exceeds total state space size", enc, ">=", width * height * n_rm)
     return enc
+
+
+def _time_dims(agent, state_reward_machine):
+    rm = agent.get_reward_machine()
+    p = agent.ma_problem
+    return p.grid_width, p.grid_height, p.max_time, rm.numbers_state(), rm.get_state_index(state_reward_machine)
+
+
+def encode_state_with_time(agent, state, state_reward_machine):
+    """(position, state["timestamp"], RM state) -> ((y*W + x) * max_time + timestamp) * nQ + q (utils/utils.py:38-75). Time-augmented
+    encodings are not used by the reference drivers (nor by the kernels); kept for API parity with the reference's utilities."""
+    width, height, max_time, n_rm, q = _time_dims(agent, state_reward_machine)
+    enc = ((state["pos_y"] * width + state["pos_x"]) * max_time + state["timestamp"]) * n_rm + q
+    if enc >= width * height * max_time * n_rm:
+        raise ValueError("Encoded state index exceeds total state space size.")
+    return enc
+
+
+def encode_state_time(agent, state, state_reward_machine):
+    """(position, RM state, state["timestep"]) -> ((y*W + x) * nQ + q) * max_time + timestep (utils/utils.py:78-115)."""
+    width, height, max_time, n_rm, q = _time_dims(agent, state_reward_machine)
+    enc = ((state["pos_y"] * width + state["pos_x"]) * n_rm + q) * max_time + state["timestep"]
+    if enc >= width * height * n_rm * max_time:
+        raise ValueError("Encoded state index exceeds total state space size.")
+    return enc

@@ -225,6 +225,27 @@ def test_state_encoder_known_answers():
     ag2 = P.AgentRL("b", P2())
     ag2.set_reward_machine(P.RewardMachine({("q0", "e"): ("q0", 0)}, _StubDetector()))
     assert P.encode_state(ag2, {"pos_x": 1, "pos_y": 1}, "q0") == 3
+    # time-augmented variants (/root/reference/tests/test_utils_encoding.py:24-47)
+    from multiagent_rlrm_b200.encoders import encode_state_time, encode_state_with_time
+
+    class P3:
+        grid_width, grid_height, max_time = 2, 2, 3
+
+    ag3 = P.AgentRL("c", P3())
+    ag3.set_reward_machine(P.RewardMachine({("q0", None): ("q0", 0)}, _StubDetector()))
+    state = {"pos_x": 1, "pos_y": 1, "timestamp": 1, "timestep": 2}
+    assert encode_state_with_time(ag3, state, "q0") == 3 * 3 + 1 and encode_state_time(ag3, state, "q0") == 3 * 3 + 2
+
+    class P4:
+        grid_width, grid_height, max_time = 1, 1, 1
+
+    ag4 = P.AgentRL("d", P4())
+    ag4.set_reward_machine(P.RewardMachine({("q0", None): ("q0", 0)}, _StubDetector()))
+    zero = {"pos_x": 0, "pos_y": 0, "timestamp": 0, "timestep": 0}
+    with pytest.raises(ValueError):
+        encode_state_with_time(ag4, zero | {"timestamp": 2}, "q0")
+    with pytest.raises(ValueError):
+        encode_state_time(ag4, zero | {"timestep": 2}, "q0")
 
 
 class _DummyAlgo:
