@@ -129,8 +129,6 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     return fail(RLRM_ERR_ARG, "random_starts needs tables.free_cells with n_agents <= n_free_cells <= width*height");
   if (cfg->algo < 0 || cfg->algo > RLRM_ALGO_QLAMBDA) return fail(RLRM_ERR_ARG, "unknown algo");
   if (cfg->env_kind != RLRM_ENV_FROZEN_LAKE && cfg->env_kind != RLRM_ENV_OFFICE_WORLD) return fail(RLRM_ERR_ARG, "unknown env_kind");
-  if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->learning_rate < 0)
-    return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) with learning_rate=None is not supported");
   if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->shared_q) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) with a shared table is not supported");
   if (!tb->next_cell || !tb->cell_flags || !tb->label || !tb->delta || !tb->rq || !tb->rcf || !tb->start_cell)
     return fail(RLRM_ERR_ARG, "null table");
@@ -262,7 +260,6 @@ extern "C" int rlrm_destroy(rlrm_handle_t* h) {
 
 extern "C" int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double gamma, double lambd) {
   if (!h) return fail(RLRM_ERR_ARG, "null handle");
-  if (h->cfg.algo == RLRM_ALGO_QLAMBDA && learning_rate < 0) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) needs a fixed learning rate");
   h->cfg.learning_rate = learning_rate; h->cfg.gamma = gamma; h->cfg.lambd = lambd;
   fill_learner(h->kp, learning_rate, gamma, lambd);
   if (learning_rate < 0.0) h->qrm4_fast = h->ql_fast = 0;

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) update_kernel(KP p_in, DState st, const u
 // QLearningLambda.update (qlearning_lambda.py:33-84), dense sweep exactly as written: one block per (instance, agent).
 // q += (lr*td) * e ; e = terminated ? 0 : e * (gamma*lambda), with e[s,a] replaced by 1 first.
 __device__ __forceinline__ void qlambda_sweep(const KP& p, float* Q, float* E, unsigned s, int a, double reward, unsigned sn,
-                                              bool terminated, int tid, int nthreads) {
+                                              bool terminated, int tid, int nthreads, unsigned visits_now) {
   // every thread reads the two scalars before anyone writes
   const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
   const float qsa = Q[s * 4 + a];
@@ -244,16 +244,25 @@ __device__ __forceinline__ void qlambda_sweep(const KP& p, float* Q, float* E, u
   const double best = terminated ? 0.0 : (double)row_max(nrow);
   const float td = __fsub_rn(__double2float_rn(__dadd_rn(reward, __dmul_rn(p.gamma, best))), qsa);
   const float c = __fmul_rn(p.lr_f, td);
+  const bool lr_none = p.lr < 0.0;  // lr = 1 / visits[s, a] (np.float64): the add happens in float64 (qlearning_lambda.py:44-49, 63)
+  const double c64 = lr_none ? __dmul_rn(__ddiv_rn(1.0, (double)(visits_now ? visits_now : 1u)), (double)td) : 0.0;
   const unsigned hot = s * 4 + a;
   float4* Q4 = reinterpret_cast<float4*>(Q);
   float4* E4 = reinterpret_cast<float4*>(E);
   for (long long j = tid; j < p.S4 / 4; j += nthreads) {
     float4 e = E4[j], q = Q4[j];
     if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);  // replacing trace
-    q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
-    q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
-    q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
-    q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+    if (lr_none) {
+      q.x = __double2float_rn(__dadd_rn((double)q.x, __dmul_rn(c64, (double)e.x)));
+      q.y = __double2float_rn(__dadd_rn((double)q.y, __dmul_rn(c64, (double)e.y)));
+      q.z = __double2float_rn(__dadd_rn((double)q.z, __dmul_rn(c64, (double)e.z)));
+      q.w = __double2float_rn(__dadd_rn((double)q.w, __dmul_rn(c64, (double)e.w)));
+    } else {
+      q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
+      q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
+      q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
+      q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+    }
     if (terminated) {
       e = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {  // next_action defaults to argmax Q[s'] => greedy => decay (qlearning_lambda.py:71-81)
@@ -278,7 +287,12 @@ __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, co
   const unsigned s_idx = min((unsigned)obs_cell[k], cmax) * p.nQ + min((unsigned)o.prev_q[k], qmax);
   const unsigned sn_idx = min((unsigned)o.cell[k], cmax) * p.nQ + min((unsigned)o.q[k], qmax);
   const int action = min((int)actions[k], RLRM_N_ACTIONS - 1);
-  if (st.visits && threadIdx.x == 0) st.visits[base + (size_t)s_idx * 4 + action] += 1;
-  qlambda_sweep(p, st.q + base, st.e + base, s_idx, action, o.reward[k], sn_idx, term_arg[k] != 0, threadIdx.x, blockDim.x);
+  unsigned vis = 0;
+  if (st.visits) {  // every thread reads the old count, then one writes the new one
+    vis = st.visits[base + (size_t)s_idx * 4 + action] + 1;
+    __syncthreads();
+    if (threadIdx.x == 0) st.visits[base + (size_t)s_idx * 4 + action] = vis;
+  }
+  qlambda_sweep(p, st.q + base, st.e + base, s_idx, action, o.reward[k], sn_idx, term_arg[k] != 0, threadIdx.x, blockDim.x, vis);
 }
 

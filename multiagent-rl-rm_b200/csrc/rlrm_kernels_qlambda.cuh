@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
   const size_t base = table_base(p, i, a);
   float* Q = st.q + base;
   float* E = st.e + base;
+  unsigned* V = st.visits ? st.visits + base : nullptr;  // QLearningLambda counts visits on every update (qlearning_lambda.py:44)
   unsigned long long active_steps = 0;
   unsigned episodes = 0, successes = 0, last_length = 0;
   float last_return = 0.f;
@@ -49,15 +50,32 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
       const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
       const float c = __fmul_rn(p.lr_f, td);
       const unsigned hot = sidx * 4 + action;
+      // learning_rate=None: lr = 1 / visits[s, a] is an np.float64, so lr * td and (lr * td) * e_table are float64 and the
+      // in-place add happens in float64 before the cast back to float32 (qlearning_lambda.py:44-49, 63)
+      const bool lr_none = p.lr < 0.0;
+      unsigned vis = 0;
+      if (V) {
+        vis = V[hot] + 1;
+        __syncwarp();
+        if (lane == 0) V[hot] = vis;
+      }
+      const double c64 = lr_none ? __dmul_rn(__ddiv_rn(1.0, (double)vis), (double)td) : 0.0;
       float4* Q4 = reinterpret_cast<float4*>(Q);
       float4* E4 = reinterpret_cast<float4*>(E);
       for (long long j = lane; j < p.S4 / 4; j += 32) {
         float4 e = E4[j], q = Q4[j];
         if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);
-        q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
-        q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
-        q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
-        q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+        if (lr_none) {
+          q.x = __double2float_rn(__dadd_rn((double)q.x, __dmul_rn(c64, (double)e.x)));
+          q.y = __double2float_rn(__dadd_rn((double)q.y, __dmul_rn(c64, (double)e.y)));
+          q.z = __double2float_rn(__dadd_rn((double)q.z, __dmul_rn(c64, (double)e.z)));
+          q.w = __double2float_rn(__dadd_rn((double)q.w, __dmul_rn(c64, (double)e.w)));
+        } else {
+          q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
+          q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
+          q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
+          q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
+        }
         if (term_arg) {
           e = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
@@ -172,6 +190,7 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
   float* Q = st.q + table_base(p, i, valid ? a : 0);
+  unsigned* V = st.visits ? st.visits + table_base(p, i, valid ? a : 0) : nullptr;
   TraceList L;
   L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
@@ -246,10 +265,18 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       const double best = term_arg ? 0.0 : (double)fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
       const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
       const float c = __fmul_rn(p.lr_f, td);
+      const bool lr_none = p.lr < 0.0;  // lr = 1 / visits: float64 arithmetic, see train_qlambda_kernel
+      unsigned vis = 0;
+      if (V && valid) {
+        vis = V[hot] + 1;
+      }
+      __syncwarp();
+      if (V && valid && gl == 0) V[hot] = vis;
+      const double c64 = lr_none ? __dmul_rn(__ddiv_rn(1.0, (double)(vis ? vis : 1u)), (double)td) : 0.0;
       for (unsigned j = gl; j < len; j += LG) {  // one pass over the agent's live entries (len = 0 on idle lanes)
         float2 eq = L.eq[j];
         if (j + 1 == hotpos) eq.x = 1.0f;  // replacing trace on the visited entry
-        eq.y = __fadd_rn(eq.y, __fmul_rn(c, eq.x));
+        eq.y = lr_none ? __double2float_rn(__dadd_rn((double)eq.y, __dmul_rn(c64, (double)eq.x))) : __fadd_rn(eq.y, __fmul_rn(c, eq.x));
         eq.x = term_arg ? 0.0f : __fmul_rn(eq.x, p.trace_decay_f);
         L.eq[j] = eq;
       }
@@ -257,7 +284,8 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       if (valid && hotpos == 0u) {  // first visit since the last wipe: the table value (qsa) is current
         if (gl == 0) {
           L.idx[len] = (unsigned short)hot;
-          L.eq[len] = make_float2(term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f), __fadd_rn(qsa, __fmul_rn(c, 1.0f)));
+          const float q_new = lr_none ? __double2float_rn(__dadd_rn((double)qsa, __dmul_rn(c64, 1.0))) : __fadd_rn(qsa, __fmul_rn(c, 1.0f));
+          L.eq[len] = make_float2(term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f), q_new);
           L.pos[hot] = (unsigned short)(len + 1);
         }
         len++;

@@ -319,9 +319,7 @@ class QLearningLambda(_TabularBase):
     def __init__(self, gamma, lambd, action_selection, learning_rate=None, epsilon_start=1.0, epsilon_end=0.2,
                  epsilon_decay=0.99, **kwargs):
         super().__init__(gamma=gamma, **kwargs)
-        if learning_rate is None:
-            raise NotImplementedError("Q(lambda) with learning_rate=None (1/visits) is not supported on the CUDA path")
-        self.learning_rate = learning_rate
+        self.learning_rate = learning_rate  # None -> 1 / visits[s, a], evaluated in float64 (qlearning_lambda.py:44-49)
         self.lambd = lambd
         self.action_selection = action_selection
         self.epsilon_start, self.epsilon_end, self.epsilon_decay = epsilon_start, epsilon_end, epsilon_decay

@@ -150,6 +150,13 @@ def scenarios():
                   stochastic=True, high_prob=0.8, algo="qlambda", learning_rate=0.1, lambd=0.9, gamma=0.9, epsilon_start=0.3,
                   epsilon_end=0.3, epsilon_decay=1.0, q_init=0.0, driver="office_main", seed=71)
     S["long_office_coffee_qlambda"] = (sc, 1, 20000, "f32", 1)
+
+    # QLearningLambda(learning_rate=None): lr = 1 / visits, float64 arithmetic on float32 tables (qlearning_lambda.py:44-49, 63)
+    sc = P.scenario_config3(False)
+    sc.algo, sc.lambd, sc.learning_rate, sc.q_init, sc.epsilon_start, sc.epsilon_end, sc.seed = "qlambda", 0.7, None, 0.5, 0.2, 0.2, 12
+    sc.penalty_amount = -2.0
+    S["fl_qlambda_lr_none"] = (sc, 2, 900, "f32", 1)
+    S["fl_qlambda_lr_none_f64"] = (sc, 1, 500, "f64", 1)
     return S
 
 

@@ -460,8 +460,15 @@ static void update_qlambda(const rlrm_config_t* cfg, real* Q, real* E, uint32_t*
   double best = terminated ? 0.0 : (double)row_max(Q + sn * 4);
   real td = (real)(reward + cfg->gamma * best) - Q[s * 4 + a]; /* double sum, rounded at the subtraction */
   E[s * 4 + a] = (real)1;
-  real c = (real)cfg->learning_rate * td;
-  for (size_t j = 0; j < S * 4; j++) Q[j] = Q[j] + c * E[j];
+  if (cfg->learning_rate < 0) {
+    /* lr = 1 / visits[s, a] is an np.float64 (qlearning_lambda.py:44-49): lr * td_error and (lr * td_error) * e_table are
+     * float64, and `q_table +=` adds in float64 before casting back to the table's dtype */
+    double c = (1.0 / (double)visits[s * 4 + a]) * (double)td;
+    for (size_t j = 0; j < S * 4; j++) Q[j] = (real)((double)Q[j] + c * (double)E[j]);
+  } else {
+    real c = (real)cfg->learning_rate * td;
+    for (size_t j = 0; j < S * 4; j++) Q[j] = Q[j] + c * E[j];
+  }
   if (terminated) {
     memset(E, 0, S * 4 * sizeof(real));
   } else { /* next_action defaults to argmax Q[s'] => greedy => decay (:71-81) */

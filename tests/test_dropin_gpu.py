@@ -84,6 +84,29 @@ def test_qlearning_lambda_update_and_traces_decay(cuda_device):
     assert np.isclose(ql.e_table[0, 0], 0.9 * 0.5)
 
 
+def test_qlearning_lambda_adaptive_step_size(cuda_device):
+    """learning_rate=None -> lr = 1 / visits[s, a] (qlearning_lambda.py:44-49): against the same updates done by hand in the
+    reference's float64-then-cast arithmetic."""
+    import multiagent_rlrm_b200 as P
+
+    ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=None, state_space_size=3,
+                           action_space_size=2)
+    q = np.zeros((3, 2), dtype=np.float32)
+    e = np.zeros((3, 2), dtype=np.float32)
+    visits = np.zeros((3, 2))
+    for (s, sn, a, r, term) in [(0, 1, 0, 1.0, False), (1, 2, 1, 0.3, False), (0, 1, 0, -0.7, False), (1, 0, 1, 2.0, True), (0, 1, 0, 0.1, False)]:
+        ql.update(encoded_state=s, encoded_next_state=sn, action=a, reward=r, terminated=term)
+        visits[s, a] += 1
+        lr = 1 / visits[s, a]                                        # np.float64
+        best = 0.0 if term else float(np.max(q[sn]))
+        td = np.float32(r + 0.9 * best) - q[s, a]                      # python float is weak: rounded to float32 first
+        e[s, a] = 1.0
+        q = (q.astype(np.float64) + (lr * np.float64(td)) * e.astype(np.float64)).astype(np.float32)
+        e = np.zeros_like(e) if term else e * np.float32(0.9 * 0.5)
+        assert np.array_equal(np.asarray(ql.q_table), q) and np.array_equal(np.asarray(ql.e_table), e), (s, a)
+    assert np.array_equal(np.asarray(ql.visits), visits)
+
+
 def test_qlearning_lambda_reset_traces(cuda_device):
     """/root/reference/tests/test_qlearning_lambda.py:30-41"""
     import multiagent_rlrm_b200 as P

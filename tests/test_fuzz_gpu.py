@@ -78,6 +78,8 @@ def random_scenario(seed):
     sc.epsilon_decay = float(rng.choice([1.0, 0.9, 0.999]))
     if algo == "qlambda":
         sc.learning_rate, sc.lambd = float(rng.choice([0.1, 0.5])), float(rng.choice([0.0, 0.5, 0.9]))
+        if rng.random() < 0.25:
+            sc.learning_rate = None  # 1 / visits, float64 arithmetic (qlearning_lambda.py:44-49)
     else:
         sc.learning_rate = None if rng.random() < 0.2 else float(rng.choice([1.0, 0.1, 0.37]))
         if not per_agent and rng.random() < 0.25:
@@ -86,7 +88,7 @@ def random_scenario(seed):
     sc.random_start_positions = bool(env == "frozen_lake" and rng.random() < 0.25)
     sc.shared_q = bool(algo != "qlambda" and sc.learning_rate is not None and not sc.use_rsh and rng.random() < 0.2)
     opts = {"n": int(rng.choice([1, 3, 17, 64, 129])), "iters": int(rng.choice([150, 400, 700])),
-            "track_visits": bool(algo != "qlambda" and not sc.shared_q and rng.random() < 0.25),
+            "track_visits": bool(not sc.shared_q and rng.random() < 0.25),
             "sparse": bool(algo == "qlambda" and rng.random() < 0.5), "chunks": int(rng.choice([1, 1, 3]))}
     return sc, opts
 
