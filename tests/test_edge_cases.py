@@ -170,3 +170,40 @@ def test_create_rejects_bad_arguments():
     sc.starts = [(0, 0)] * 9
     with pytest.raises(ValueError):
         P.compile_scenario(sc)
+
+
+def test_value_iteration_rejects_bad_arguments():
+    """rlrm_value_iteration needs no handle: its argument checks run before any device work."""
+    from multiagent_rlrm_b200 import _lib
+
+    L = _lib.load()
+    buf = (C.c_double * 64)()
+    p = C.addressof(buf)
+    ok = dict(device=0, n=4, n_out=1, prob=p, nxt=p, rew=p, done=p, gamma=0.9, theta=1e-3, rel=0, sweeps=10, V=p, Q=p, pol=p, work=p)
+
+    def call(**kw):
+        a = {**ok, **kw}
+        return L.rlrm_value_iteration(a["device"], a["n"], a["n_out"], a["prob"], a["nxt"], a["rew"], a["done"], a["gamma"], a["theta"],
+                                      a["rel"], a["sweeps"], a["V"], a["Q"], a["pol"], a["work"], None, None)
+
+    for kw, text in (({"prob": None}, "null"), ({"work": None}, "null"), ({"n": 0}, "n_states"), ({"n_out": 0}, "n_states"),
+                     ({"theta": 0.0}, "theta"), ({"sweeps": 0}, "theta")):
+        assert call(**kw) == -1 and text in L.rlrm_last_error().decode(), kw
+
+
+@pytest.mark.gpu
+def test_value_iteration_reports_non_convergence(cuda_device):
+    """gamma = 1 with a rewarded self-loop never converges: RLRM_ERR_UNSUPPORTED after max_sweeps, as an exception in Python."""
+    from multiagent_rlrm_b200._lib import RlrmError
+    from multiagent_rlrm_b200.mdp_vi import value_iteration_arrays
+
+    prob = np.ones((2, 4, 1))
+    nxt = np.zeros((2, 4, 1), dtype=np.int32)
+    rew = np.ones((2, 4, 1))
+    done = np.zeros((2, 4, 1), dtype=np.uint8)
+    with pytest.raises(RlrmError, match="did not converge"):
+        value_iteration_arrays(prob, nxt, rew, done, gamma=1.0, theta=1e-3, max_sweeps=50)
+    V, pol, Q, sweeps = value_iteration_arrays(prob, nxt, rew, done, gamma=0.5, theta=1e-9)
+    assert np.allclose(V.cpu().numpy(), 2.0, atol=1e-8) and sweeps > 10  # 1 / (1 - 0.5)
+    with pytest.raises(ValueError):
+        value_iteration_arrays(prob, nxt + 5, rew, done)
