@@ -236,6 +236,23 @@ class Compiled:
         return t
 
 
+def dump_blob(compiled: "Compiled", path) -> None:
+    """Write the compiled scenario for a non-Python host of the C ABI (examples/c_abi_demo.c): the rlrm_config_t bytes, the
+    initial Q value (f64), then every table of rlrm_tables_t in field order as <u64 byte count><bytes> (count 0 = NULL)."""
+    import ctypes as C
+    import struct
+
+    t = compiled.tables_struct()  # makes every array contiguous and keeps it alive on `compiled`
+    with open(path, "wb") as f:
+        f.write(bytes(memoryview((C.c_char * C.sizeof(compiled.config)).from_address(C.addressof(compiled.config)))))
+        f.write(struct.pack("<d", float(compiled.scenario.q_init)))
+        for name in ("next_cell", "cell_flags", "label", "delta", "rq", "rcf", "qrm_states", "start_cell", "free_cells", "phi"):
+            arr = getattr(compiled, name, None)
+            data = b"" if arr is None or getattr(t, name) is None else np.ascontiguousarray(arr).tobytes()
+            f.write(struct.pack("<Q", len(data)))
+            f.write(data)
+
+
 _ALGO = {"ql": abi.ALGO_QL, "qrm": abi.ALGO_QRM, "qlambda": abi.ALGO_QLAMBDA}
 _DRIVER = {"frozen_lake_main": abi.DRIVER_FROZEN_LAKE_MAIN, "office_main": abi.DRIVER_OFFICE_MAIN}
 
