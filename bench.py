@@ -259,6 +259,14 @@ def ncu_traffic(algo):
         return None
 
 
+def ncu_summary(workload):
+    """Cache hit rates and pipe utilisation of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload + "_ncu")
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -433,7 +441,7 @@ def run_gpu_arm(args):
             "e2e_call_by_call": stepwise,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "traffic": ncu_traffic(args.workload), "ncu": ncu_summary(args.workload), "peak_source": peak_src,
                          "kernel": WORKLOADS[args.workload][5],
                          "algorithmic_bytes_per_active_agent_step": bytes_per,
                          "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms,
