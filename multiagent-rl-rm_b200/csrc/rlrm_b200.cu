@@ -39,6 +39,7 @@ struct rlrm_handle {
   long long launches;
   int qrm4_fast;  // train_qrm4_kernel is applicable (see its header comment)
   int ql_fast;    // train_ql_fast_kernel is applicable (see its header comment)
+  int qrmn_fast;  // train_qrmn_kernel<NQ = 3 or 5> is applicable (see its header comment)
   int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
   int shared_smem_bytes;
   int num_sms;
@@ -225,6 +226,10 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
+  h->qrmn_fast = (kp.algo == RLRM_ALGO_QRM && (kp.nQ == 3 || kp.nQ == 5) && kp.n_qrm == kp.nQ - 1 && !kp.shared_q && !kp.use_rsh &&
+                  !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 && !(cfg->reserved & 1));
+  for (int j = 0; j < kp.n_qrm; j++)
+    if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrmn_fast = 0;
   h->ql_fast = (kp.algo == RLRM_ALGO_QL && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
                 !(cfg->reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -262,7 +267,7 @@ extern "C" int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double g
   if (!h) return fail(RLRM_ERR_ARG, "null handle");
   h->cfg.learning_rate = learning_rate; h->cfg.gamma = gamma; h->cfg.lambd = lambd;
   fill_learner(h->kp, learning_rate, gamma, lambd);
-  if (learning_rate < 0.0) h->qrm4_fast = h->ql_fast = 0;
+  if (learning_rate < 0.0) h->qrm4_fast = h->ql_fast = h->qrmn_fast = 0;
   return RLRM_OK;
 }
 
@@ -511,6 +516,26 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
         default: RLRM_QRM4(true, true, true); break;
       }
 #undef RLRM_QRM4
+    }
+    else if (kp.algo == RLRM_ALGO_QRM && h->qrmn_fast && !st->visits) {
+      const DState d = dstate(st);
+#define RLRM_QRMN(ST, LE, TR)                                                                                             \
+  do {                                                                                                                   \
+    if (kp.nQ == 3) train_qrmn_kernel<ENV, 3, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace); \
+    else train_qrmn_kernel<ENV, 5, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace);       \
+  } while (0)
+      const int key = (kp.stochastic ? 4 : 0) | (learn ? 2 : 0) | (trace ? 1 : 0);
+      switch (key) {
+        case 0: RLRM_QRMN(false, false, false); break;
+        case 1: RLRM_QRMN(false, false, true); break;
+        case 2: RLRM_QRMN(false, true, false); break;
+        case 3: RLRM_QRMN(false, true, true); break;
+        case 4: RLRM_QRMN(true, false, false); break;
+        case 5: RLRM_QRMN(true, false, true); break;
+        case 6: RLRM_QRMN(true, true, false); break;
+        default: RLRM_QRMN(true, true, true); break;
+      }
+#undef RLRM_QRMN
     }
     else if (kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
       const DState d = dstate(st);

@@ -308,6 +308,149 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, MINB) train_qrm4_kernel(KP p, DSt
 }
 
 // ------------------------------------------------------------------------------------------------
+// fast path: QRM with NQ = 3 or 5 reward-machine states (OfficeWorld's built-in tasks exp0-exp4). Same scheme as
+// train_qrm4_kernel — the cell block Q[cell, 0..NQ-1, 0..3] lives in registers between iterations, it is re-fetched (NQ 16-byte
+// loads) only when the agent changes cell, the NQ-1 counterfactual updates run on registers in get_all_states()[:-1] order and
+// go back as scalar stores — with the state count as a template parameter. Requires qrm_states == [0 .. NQ-2].
+// ------------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ float sel_state(const float* v, int stride, unsigned k) {  // v[k * stride], k < NQ, without indexing
+  float r = v[0];
+#pragma unroll
+  for (int j = 1; j < NQ; j++) r = (k == (unsigned)j) ? v[j * stride] : r;
+  return r;
+}
+template <int NQ>
+__device__ __forceinline__ void load_block_n(const float* Q, unsigned cell, float* B, float* bmax) {
+  const float4* src = reinterpret_cast<const float4*>(Q + (size_t)cell * (NQ * 4));
+#pragma unroll
+  for (int r = 0; r < NQ; r++) {
+    const float4 v = src[r];
+    B[4 * r] = v.x;
+    B[4 * r + 1] = v.y;
+    B[4 * r + 2] = v.z;
+    B[4 * r + 3] = v.w;
+    bmax[r] = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+  }
+}
+
+template <int ENV, int NQ, bool STOCH, bool LEARN, bool TRACE>
+__global__ void __launch_bounds__(TRAIN_BLOCK) train_qrmn_kernel(KP p, DState st, unsigned long long t0, int n_iters, unsigned* trace) {
+  Tab tb = stage_tables(p);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
+  float* Q = st.q;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  float B[NQ * 4], bmax[NQ];  // carried cell block Q[cell, rm state, action] and its row maxima
+#pragma unroll
+  for (int j = 0; j < NQ * 4; j++) B[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NQ; j++) bmax[j] = 0.f;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    Q = st.q + table_base(p, i, a);
+    load_block_n<NQ>(Q, s.cell, B, bmax);
+  }
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    if (valid) {
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      float4 row;
+      row.x = sel_state<NQ>(B + 0, 4, s.rm);
+      row.y = sel_state<NQ>(B + 1, 4, s.rm);
+      row.z = sel_state<NQ>(B + 2, 4, s.rm);
+      row.w = sel_state<NQ>(B + 3, 4, s.rm);
+      const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);
+      const unsigned before = s.cell;
+      Rec r;
+      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
+      const bool moved = r.cell != before;
+      float cur[NQ - 1];  // values the updates overwrite, read before the carried block is replaced
+#pragma unroll
+      for (int u = 0; u < NQ - 1; u++) cur[u] = sel4(B[4 * u], B[4 * u + 1], B[4 * u + 2], B[4 * u + 3], (unsigned)action);
+      if (moved) load_block_n<NQ>(Q, r.cell, B, bmax);  // the carried block becomes the NEXT cell's block
+      if (LEARN) {
+        const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+        float* dst = Q + (size_t)before * (NQ * 4) + action;  // infos["prev_s"] is the position before the move
+#pragma unroll
+        for (int u = 0; u < NQ - 1; u++) {
+          const unsigned d = tb.delta[u * (p.nEv + 1) + col];
+          const unsigned un = d == RLRM_NO_TRANSITION ? (unsigned)u : d;
+          const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
+          const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
+          const float mx = sel_state<NQ>(bmax, 1, un);
+          const float mf = __fmul_rn(done ? 0.0f : 1.0f, mx);
+          const float inner = __fadd_rn(__double2float_rn(__dadd_rn(r.renv, ru)), __fmul_rn(p.gamma_f, mf));
+          const float nv = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur[u]), __fmul_rn(p.lr_f, inner));
+          if (__float_as_uint(nv) != __float_as_uint(cur[u])) dst[4 * u] = nv;  // a bit-identical value needs no store
+          if (!moved) {  // same cell: the carried block is the one just written
+#pragma unroll
+            for (int c = 0; c < 4; c++) B[4 * u + c] = (c == action) ? nv : B[4 * u + c];
+            bmax[u] = fmaxf(fmaxf(B[4 * u], B[4 * u + 1]), fmaxf(B[4 * u + 2], B[4 * u + 3]));
+          }
+        }
+      }
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      if (TRACE)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    unsigned flags2 = (term ? 1u : 0u) | (trunc ? 2u : 0u);
+    for (int o = 1; o < p.G; o <<= 1) flags2 &= __shfl_xor_sync(0xFFFFFFFFu, flags2, o);
+    const bool over = flags2 != 0u;
+    if (valid && over) {
+      episodes++;
+      active_steps += s.steps;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      reset_slot<false>(p, tb, i, a, t + 1, s, eps);
+      explore_thr = explore_threshold(eps);
+      load_block_n<NQ>(Q, s.cell, B, bmax);
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fast path: plain Q-learning with a private table per (instance, agent), fixed learning rate, no visit counts, no shaping
 // (BASELINE config 3's `use_qrm=0, lr=0.1` variant). Same algorithm as train_kernel's row-carry branch — the row of the
 // agent's current state stays in registers, one 16-byte load of Q[s'] and at most one 4-byte store per step — with the

@@ -111,12 +111,28 @@ def test_fused_kernel_matches_oracle(name, cuda_device):
     _compare_with_oracle(eng, o, name)
 
 
-@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg5_qrm_4agents"])
-def test_generic_kernel_equals_specialised(name, cuda_device):
-    """config.reserved bit 0 forces train_kernel<.., QRM>; it must agree bit-for-bit with train_qrm4_kernel."""
+def _office_task(exp, algo, stochastic=True):
     import multiagent_rlrm_b200 as P
 
-    sc, n, t = _scenarios_medium()[name]
+    return P.scenario_for_experiment("map1", exp, starts=[(2, 7), (6, 3), (0, 0)], algo=algo, learning_rate=0.1 if stochastic else 1.0,
+                                     gamma=0.9, stochastic=stochastic, epsilon_start=0.1, epsilon_end=0.1, epsilon_decay=1.0, q_init=2.0,
+                                     wall_penalty=-0.5, max_steps=200, seed=97)
+
+
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg5_qrm_4agents", "cfg3_ql", "office_exp1_qrm", "office_exp3_qrm", "office_exp4_qrm_det",
+                                  "office_exp2_ql"])
+def test_generic_kernel_equals_specialised(name, cuda_device):
+    """config.reserved bit 0 forces the generic train_kernel; it must agree bit-for-bit with the specialised kernels
+    (train_qrm4_kernel, train_qrmn_kernel<3 / 5 RM states>, train_ql_fast_kernel) — and both with the oracle."""
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    if name.startswith("office"):
+        sc = {"office_exp1_qrm": lambda: _office_task("exp1", "qrm"), "office_exp3_qrm": lambda: _office_task("exp3", "qrm"),
+              "office_exp4_qrm_det": lambda: _office_task("exp4", "qrm", False), "office_exp2_ql": lambda: _office_task("exp2", "ql")}[name]()
+        n, t = 300, 1500
+    else:
+        sc, n, t = _scenarios_medium()[name]
     c_fast, c_gen = P.compile_scenario(sc), P.compile_scenario(sc)
     c_gen.config.reserved = 1
     a, b = _engine(c_fast, n), _engine(c_gen, n)
@@ -126,6 +142,11 @@ def test_generic_kernel_equals_specialised(name, cuda_device):
     assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy())
     assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
     assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+    o = O.Oracle(c_fast, n, "f32")
+    o.reset()
+    o.train(0, t)
+    assert np.array_equal(a.q.cpu().numpy().reshape(-1), o.q.reshape(-1)) and np.array_equal(a.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert int(o.stats["episodes"].sum()) > 0
 
 
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda", "fl_per_agent_rms_qrm",
