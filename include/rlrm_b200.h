@@ -180,7 +180,8 @@ typedef struct rlrm_state {
   int64_t n_instances;  /* N (local to this GPU) */
   uint64_t* slot;       /* [N*A] packed env + RM state, see RLRM_SLOT_* */
   double* epsilon;      /* [N*A] learner.epsilon */
-  float* q;             /* [N*A*S*4] (shared_q: [A*S*4]) learner.q_table, S = W*H*nQ */
+  float* q;             /* [N*A*S*4] (shared_q: [A*S*4]) learner.q_table, S = W*H*nQ. Must be 32-byte aligned (cudaMalloc and
+                           torch allocations are): rows are read with 16- and 32-byte vector loads. e / visits: 16-byte aligned. */
   float* e;             /* Q(lambda) only: learner.e_table, same shape as q; else NULL */
   uint32_t* visits;     /* optional [same shape as q]: learner.visits; required when learning_rate < 0 */
   double* ep_return;    /* [N*A] running (undiscounted) return of the current episode */

@@ -298,6 +298,8 @@ static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need
   if (st->n_instances <= 0) return fail(RLRM_ERR_ARG, "n_instances must be positive");
   if (!st->slot || !st->epsilon) return fail(RLRM_ERR_ARG, "state.slot / state.epsilon are required");
   if (need_q && !st->q) return fail(RLRM_ERR_ARG, "state.q is required");
+  if (need_q && ((uintptr_t)st->q & 31u)) return fail(RLRM_ERR_ARG, "state.q must be 32-byte aligned");
+  if (st->e && ((uintptr_t)st->e & 15u)) return fail(RLRM_ERR_ARG, "state.e must be 16-byte aligned");
   if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) {
     if (!st->tr_pos || !st->tr_idx || !st->tr_eq || !st->tr_len)
       return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e (dense traces) or state.tr_* (sparse traces)");
