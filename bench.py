@@ -56,6 +56,13 @@ WORKLOADS = {
     "cfg3_ql": ("FrozenLake map1, 2 agents, slippery, RM A->B->C, QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False, "
                 "per-instance Q tables, auto-reset",
                 "configs[2] companion (plain Q-learning variant, SURVEY.md §8d)", 65536, 2048, 36, "train_ql_fast_kernel<FrozenLake>"),
+    "cfg2_batch": ("OfficeWorld map1 (12x9), 1 agent at (2,7), slip hp=.8, RM 'A -> C -> B -> D, reward on D' (5 states, the --rm-spec "
+                   "fixture of configs[1]), QLearning lr=.1 gamma=.9 eps=.1 init=2 use_qrm=False, per-instance Q tables, auto-reset",
+                   "configs[1] batched (the reference case itself is N=1 and is a parity test, not a bench line)",
+                   131072, 2048, 36, "train_ql_fast_kernel<OfficeWorld>"),
+    "cfg2_batch_qrm": ("OfficeWorld map1 (12x9), 1 agent at (2,7), slip hp=.8, RM 'A -> C -> B -> D, reward on D' (5 states), QLearning "
+                       "lr=.1 gamma=.9 eps=.1 init=2 use_qrm=True, per-instance Q tables, auto-reset",
+                       "configs[1] batched, QRM variant", 131072, 2048, 2 * 5 * 16 + 4 * 4, "train_qrmn_kernel<OfficeWorld,5>"),
     "cfg4": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, plants -100, synthetic 12-state completed chain RM (108 "
              "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, SPARSE-EXACT traces (live entries only; "
              "bit-identical to the dense sweep)",
@@ -78,7 +85,13 @@ WORKLOADS = {
 def scenario(workload):
     import multiagent_rlrm_b200 as P
 
+    def cfg2(qrm):
+        sc = P.scenario_config2(True)
+        sc.algo = "qrm" if qrm else "ql"
+        return sc
+
     return {"cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
+            "cfg2_batch": lambda: cfg2(False), "cfg2_batch_qrm": lambda: cfg2(True),
             "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg5_tables": lambda: P.scenario_config5(False),
             "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
 
