@@ -151,3 +151,42 @@ def test_checkpoint_resume_is_bit_identical(name, cuda_device, tmp_path):
         assert torch.equal(ea, eb)
     with pytest.raises(ValueError):
         Engine(c, 95, **kw).load_state_dict(first.state_dict())
+
+
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg2_ql", "cfg4_sparse"])
+def test_train_host_equals_train(name, cuda_device):
+    """rlrm_train_host (the end-to-end entry point bench.py's `e2e` times: host slot / epsilon in, fused iterations, host slot /
+    epsilon / statistics out) == rlrm_train on resident state, and the host buffers hold exactly what the device holds."""
+    import torch
+
+    from multiagent_rlrm_b200.engine import Engine
+
+    kw = {}
+    if name == "cfg3_qrm":
+        sc = P.scenario_config3(True)
+    elif name == "cfg2_ql":
+        sc = P.scenario_config2(True)
+    else:
+        sc, kw = P.scenario_config4(), {"qlambda_sparse": True}
+    c = P.compile_scenario(sc)
+    resident, hosted = Engine(c, 200, **kw), Engine(c, 200, **kw)
+    resident.reset(); hosted.reset()
+    n_slots = 200 * c.n_agents
+    host_slot = torch.empty(n_slots, dtype=torch.int64).pin_memory()
+    host_eps = torch.empty(n_slots, dtype=torch.float64).pin_memory()
+    host_stats = torch.empty((n_slots, 32), dtype=torch.uint8).pin_memory()
+    host_slot.copy_(hosted.slot); host_eps.copy_(hosted.epsilon)
+    for chunk in (37, 300, 163):
+        resident.train(chunk)
+        hosted.train_host(chunk, host_stats, host_slot, host_eps)
+    assert hosted.t == resident.t == 500
+    assert torch.equal(hosted.slot, resident.slot) and torch.equal(hosted.epsilon, resident.epsilon)
+    resident.sync_tables(); hosted.sync_tables()
+    assert torch.equal(hosted.q, resident.q) and torch.equal(hosted.stats, resident.stats)
+    assert torch.equal(host_slot, resident.slot.cpu()) and torch.equal(host_eps, resident.epsilon.cpu())
+    assert torch.equal(host_stats, resident.stats.cpu())
+    # the host copies are INPUTS too: editing them before the call changes what the device runs on
+    host_eps.fill_(1.0)
+    hosted.train_host(5, host_stats, host_slot, host_eps)
+    assert float(hosted.epsilon.max()) <= 1.0 and float(hosted.epsilon.min()) >= float(sc.epsilon_end)
+    assert not torch.equal(hosted.slot, resident.slot)
