@@ -207,3 +207,48 @@ def test_value_iteration_reports_non_convergence(cuda_device):
     assert np.allclose(V.cpu().numpy(), 2.0, atol=1e-8) and sweeps > 10  # 1 / (1 - 0.5)
     with pytest.raises(ValueError):
         value_iteration_arrays(prob, nxt + 5, rew, done)
+
+
+@pytest.mark.gpu
+def test_state_validation_errors(cuda_device):
+    """check_state: every entry point refuses an incomplete or misaligned rlrm_state_t with an error code and a message."""
+    import torch
+
+    from multiagent_rlrm_b200 import _lib
+    from multiagent_rlrm_b200.engine import Engine
+
+    L = _lib.load()
+
+    def rc_msg(eng, **override):
+        st = abi.State.from_buffer_copy(bytes(eng.state))
+        for k, v in override.items():
+            setattr(st, k, v)
+        rc = L.rlrm_train(eng.h, C.byref(st), 0, 1, 1, None, None)
+        return rc, L.rlrm_last_error().decode()
+
+    eng = Engine(P.compile_scenario(P.scenario_config3(True)), 8)
+    eng.reset()
+    assert rc_msg(eng)[0] == 0
+    for override, text in (({"slot": None}, "slot"), ({"q": None}, "state.q is required"), ({"n_instances": 0}, "n_instances"),
+                           ({"q": eng.q.data_ptr() + 4}, "32-byte aligned")):
+        rc, msg = rc_msg(eng, **override)
+        assert rc == -1 and text in msg, (override, rc, msg)
+    assert L.rlrm_train(eng.h, C.byref(eng.state), 0, -1, 1, None, None) == -1
+
+    sc = P.scenario_config3(False)
+    sc.learning_rate = None
+    lr_none = Engine(P.compile_scenario(sc), 8)
+    rc, msg = rc_msg(lr_none, visits=None)
+    assert rc == -1 and "visits" in msg
+
+    qlam = Engine(P.compile_scenario(P.scenario_config4()), 4)
+    rc, msg = rc_msg(qlam, e=None)
+    assert rc == -1 and "Q(lambda) needs" in msg
+    sparse = Engine(P.compile_scenario(P.scenario_config4()), 4, qlambda_sparse=True)
+    rc, msg = rc_msg(sparse, tr_cap=10)
+    assert rc == -1 and "tr_cap" in msg
+
+    shared = Engine(P.compile_scenario(P.scenario_config5(True)), 8)
+    rc, msg = rc_msg(shared, acc_sum=None)
+    assert rc == -1 and "acc_sum" in msg
+    torch.cuda.synchronize()
