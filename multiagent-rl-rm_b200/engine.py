@@ -130,6 +130,7 @@ class Engine:
             size = n * _TORCH_DT[v].itemsize
             rec[k] = buf[off:off + size].view(_TORCH_DT[v])
             off += (n + pad) * _TORCH_DT[v].itemsize
+        self._record_buffer = buf  # lets a caller that wants every field on the host fetch them with one copy
         return {k: rec[k] for k in abi.STEP_OUT_FIELDS}
 
     def step(self, actions: torch.Tensor, t: Optional[int] = None, draws: Optional[torch.Tensor] = None, with_rm: bool = True,

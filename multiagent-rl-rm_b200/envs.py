@@ -132,7 +132,13 @@ class BaseEnvironment:
             acts.append(_A2I[name])
         eng.slot.copy_(self._pack_slots())
         rec = eng.step(torch.tensor(acts, dtype=torch.uint8), t=0, draws=self._slip_words().to(eng.device), with_rm=with_rm)
-        out = {k: v.cpu().numpy() for k, v in rec.items()}
+        # the record fields are views of ONE device allocation (Engine.new_record): bring it to the host with one copy
+        buf = eng._record_buffer
+        host, origin = buf.cpu(), buf.data_ptr()
+        out = {}
+        for k, v in rec.items():
+            off = v.data_ptr() - origin
+            out[k] = host[off:off + v.numel() * v.element_size()].view(v.dtype).numpy()
         out["prev_cell"] = out["prev_cell"].view(np.uint16)
         out["cell"] = out["cell"].view(np.uint16)
         s = eng.slots_numpy()

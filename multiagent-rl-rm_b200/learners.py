@@ -162,8 +162,11 @@ class _TabularBase(BaseLearningAlgorithm):
             self._q[:, self.action_space_size:] = float("-inf")
         self._e = torch.zeros((Sp, 4), dtype=torch.float32, device=d) if self._ALGO == abi.ALGO_QLAMBDA else None
         self._visits = torch.zeros((Sp, 4), dtype=torch.int32, device=d)
-        self._slot = torch.zeros(1, dtype=torch.int64, device=d)
-        self._eps = torch.zeros(1, dtype=torch.float64, device=d)
+        # One 64-byte device staging block per learner holds everything a single call needs (slot word, epsilon, Philox
+        # words, the synthesised step record); each call packs it on the host and uploads it with ONE copy.
+        self._stage = torch.zeros(64, dtype=torch.uint8, device=d)
+        self._slot = self._stage[0:8].view(torch.int64)
+        self._eps = self._stage[8:16].view(torch.float64)
         self._hp = (self.learning_rate, self.gamma, lambd)
 
     # tables as views of exactly (S, A)
@@ -195,29 +198,35 @@ class _TabularBase(BaseLearningAlgorithm):
             raise IndexError(f"encoded state {enc} out of range for state_space_size {self.state_space_size}")
         return enc // self._th.nq, enc % self._th.nq
 
+    # staging block layout (bytes): 0 slot u64 | 8 epsilon f64 | 16 draws 4 x u32 | 32 prev_cell u16 | 34 cell u16 | 36 prev_q u8 |
+    # 37 q u8 | 38 event u8 | 39 executed u8 | 40 reward f64 | 48 zero f64 (renv, rq) | 56 term u8 | 57 zero u8 (env_term,
+    # rm_term, trunc) | 58 action u8 | 59 selected action (output) u8
+    _REC_OFFSETS = {"prev_cell": 32, "cell": 34, "prev_q": 36, "q": 37, "event": 38, "executed": 39, "renv": 48, "rq": 48, "reward": 40,
+                    "env_term": 57, "rm_term": 57, "term": 56, "trunc": 57}
+
+    def _upload(self, payload: bytes, offset: int):
+        host = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+        self._stage[offset:offset + len(payload)].copy_(host)  # pageable source: returns once the bytes are staged
+
     def _device_update(self, s, sn, action, reward, terminated):
         """One update_q / Q(lambda) update on the device (rlrm_update on a synthesised one-slot step record)."""
+        import struct
+
         self._sync_hyper()
         (c0, q0), (c1, q1) = self._split(s), self._split(sn)
-        d = self.device
-        u16 = lambda v: torch.tensor([v], dtype=torch.int16, device=d)  # noqa: E731
-        u8 = lambda v: torch.tensor([v], dtype=torch.uint8, device=d)  # noqa: E731
-        f64 = lambda v: torch.tensor([float(v)], dtype=torch.float64, device=d)  # noqa: E731
-        rec = dict(prev_cell=u16(c0), cell=u16(c1), prev_q=u8(q0), q=u8(q1), event=u8(abi.EVENT_NONE), executed=u8(5),
-                   renv=f64(0.0), rq=f64(0.0), reward=f64(reward), env_term=u8(0), rm_term=u8(0), term=u8(int(bool(terminated))),
-                   trunc=u8(0))
-        so = abi.StepOut(*[rec[k].data_ptr() for k in abi.STEP_OUT_FIELDS])
+        self._upload(struct.pack("<HHBBBBddBBB", c0, c1, q0, q1, abi.EVENT_NONE, 5, float(reward), 0.0, int(bool(terminated)), 0,
+                                 int(action)), 32)
+        base = self._stage.data_ptr()
+        so = abi.StepOut(*[base + self._REC_OFFSETS[k] for k in abi.STEP_OUT_FIELDS])
         st = self._state()
-        check(self._th.L.rlrm_update(self._th.h, C.byref(st), rec["prev_cell"].data_ptr(), u8(int(action)).data_ptr(),
-                                     rec["term"].data_ptr(), C.byref(so), self._th.stream()))
-        torch.cuda.current_stream(d).synchronize()  # the temporaries above must outlive the kernel
+        check(self._th.L.rlrm_update(self._th.h, C.byref(st), base + 32, base + 58, base + 56, C.byref(so), self._th.stream()))
 
-    def _words(self, rng):
+    @staticmethod
+    def _raw_words(rng):
+        """Four 32-bit words for one selection: the injected Philox words when the rng exposes them, else from the generator."""
         if hasattr(rng, "words"):
-            w = rng.words()
-        else:
-            w = rng.integers(0, 1 << 32, size=4, dtype=np.uint64)
-        return torch.tensor([int(x) & 0xFFFFFFFF for x in w], dtype=torch.int64).to(torch.int32)
+            return rng.words()
+        return rng.integers(0, 1 << 32, size=4, dtype=np.uint64)
 
     def choose_action(self, encoded_state, best=False, rng=None, **kwargs):
         """epsilon-greedy with uniform tie-break (qlearning.py:112-143); best=True -> first argmax."""
@@ -225,17 +234,16 @@ class _TabularBase(BaseLearningAlgorithm):
             if self.action_selection == "softmax":
                 raise NotImplementedError("softmax selection is out of scope (no reference driver uses it; DESIGN.md §8)")
             raise ValueError("Unsupported action selection method")
+        import struct
+
         cell, q = self._split(encoded_state)
-        self._slot[0] = (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT)
-        self._eps[0] = float(self.epsilon)
-        draws = None
-        if not best:
-            draws = self._words(self.rng if rng is None else rng).to(self.device)
-        out = torch.zeros(1, dtype=torch.uint8, device=self.device)
+        words = [0, 0, 0, 0] if best else [int(x) & 0xFFFFFFFF for x in self._raw_words(self.rng if rng is None else rng)]
+        self._upload(struct.pack("<QdIIII", (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT), float(self.epsilon), *words), 0)
+        base = self._stage.data_ptr()
         st = self._state()
-        check(self._th.L.rlrm_select_action(self._th.h, C.byref(st), None if draws is None else draws.data_ptr(), 0, int(bool(best)),
-                                            out.data_ptr(), self._th.stream()))
-        return int(out.item())
+        check(self._th.L.rlrm_select_action(self._th.h, C.byref(st), None if best else base + 16, 0, int(bool(best)), base + 59,
+                                            self._th.stream()))
+        return int(self._stage[59].item())
 
     def choose_action_greedy(self, encoded_state, rng):
         """Uniform choice among the greedy actions (qlearning.py:136-143): the device selection with exploration switched off
@@ -248,7 +256,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_slot", "_eps")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_slot", "_eps", "_stage")}
         d["device"] = str(self.device)
         d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
                         "visits": self._visits.cpu().numpy()}

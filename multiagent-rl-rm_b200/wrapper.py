@@ -48,6 +48,7 @@ class RMEnvironmentWrapper:
         observations, rewards, env_term, env_trunc, infos, rec = self.env._step(actions, with_rm=True,
                                                                                 reward_modifier=self.reward_modifier)
         terminations = {}
+        self._cf_cache = self._counterfactual_lookups(observations)  # one rlrm_rm_step for every QRM agent of this step
         for i, agent in enumerate(self.agents):
             rm = agent.get_reward_machine()
             info = infos[agent.name]
@@ -102,6 +103,37 @@ class RMEnvironmentWrapper:
         self.reset(seed)
         return all_P, all_num_states, all_num_actions
 
+    def _counterfactual_lookups(self, observations):
+        """Hypothetical RM transitions (q_u, new position) -> (q', reward) for every agent whose learner uses QRM, evaluated with
+        ONE device call when all agents share a machine (per-agent machines: one call per agent, rlrm_rm_step_agent)."""
+        wanted = [(i, a) for i, a in enumerate(self.agents) if a.name in observations
+                  and getattr(a.get_learning_algorithm(), "use_qrm", False) and a.get_reward_machine().get_all_states()[:-1]]
+        if not wanted:
+            return {}
+        eng = self.env._get_engine(1)  # counterfactual rewards ignore reward_modifier (rm_environment_wrapper.py:150-153)
+        W = self.env.grid_width
+        per_agent = bool(eng.cfg.per_agent_rm)
+        out, q_all, cell_all, spans = {}, [], [], []
+        for i, a in wanted:
+            rm = a.get_reward_machine()
+            states = rm.get_all_states()[:-1]
+            obs = observations[a.name]
+            q_in = [rm.get_state_index(s) for s in states]
+            cells = [obs["pos_y"] * W + obs["pos_x"]] * len(states)
+            if per_agent:
+                q_out, _ev, r = eng.rm_step(torch.tensor(q_in, dtype=torch.uint8), torch.tensor(cells, dtype=torch.int16), agent=i)
+                out[a.name] = (q_out.cpu().numpy(), r.cpu().numpy())
+            else:
+                spans.append((a.name, len(q_all), len(states)))
+                q_all += q_in
+                cell_all += cells
+        if spans:
+            q_out, _ev, r = eng.rm_step(torch.tensor(q_all, dtype=torch.uint8), torch.tensor(cell_all, dtype=torch.int16), agent=0)
+            q_out, r = q_out.cpu().numpy(), r.cpu().numpy()
+            for name, lo, n in spans:
+                out[name] = (q_out[lo:lo + n], r[lo:lo + n])
+        return out
+
     def _get_qrm_experiences(self, agent, current_state, next_state, action, env_reward, next_rm_state, env_termination):
         """Counterfactual transitions for every RM state in get_all_states()[:-1] (rm_environment_wrapper.py:122-183);
         the hypothetical RM transitions are evaluated on the device (rlrm_rm_step)."""
@@ -109,12 +141,10 @@ class RMEnvironmentWrapper:
         states = rm.get_all_states()[:-1]
         if not states:
             return []
-        eng = self.env._get_engine(1)  # counterfactual rewards ignore reward_modifier (rm_environment_wrapper.py:150-153)
-        W = self.env.grid_width
-        cell = next_state["pos_y"] * W + next_state["pos_x"]
-        q_in = torch.tensor([rm.get_state_index(s) for s in states], dtype=torch.uint8)
-        q_out, _ev, r = eng.rm_step(q_in, torch.full((len(states),), cell, dtype=torch.int16), agent=self.agents.index(agent))
-        q_out, r = q_out.cpu().numpy(), r.cpu().numpy()
+        cached = getattr(self, "_cf_cache", {}).get(agent.name)
+        if cached is None:  # called outside step(): evaluate just this agent
+            cached = self._counterfactual_lookups({agent.name: next_state}).get(agent.name)
+        q_out, r = cached
         final = rm.get_final_state()
         a_idx = agent.actions_idx(action)
         out = []
