@@ -335,7 +335,7 @@ __device__ __forceinline__ void load_block_n(const float* Q, unsigned cell, floa
 }
 
 template <int ENV, int NQ, bool STOCH, bool LEARN, bool TRACE>
-__global__ void __launch_bounds__(TRAIN_BLOCK) train_qrmn_kernel(KP p, DState st, unsigned long long t0, int n_iters, unsigned* trace) {
+__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrmn_kernel(KP p, DState st, unsigned long long t0, int n_iters, unsigned* trace) {
   Tab tb = stage_tables(p);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = tid >> p.g_shift;
