@@ -11,7 +11,7 @@
 #endif
 
 template <int ENV, int ALGO, bool PA>
-__global__ void __launch_bounds__(TRAIN_BLOCK) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
+__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                            unsigned* trace) {
   KP p = p_in;
   Tab tb = stage_tables(p_in);
