@@ -72,6 +72,14 @@ WORKLOADS = {
                    "transitions), QLearningLambda gamma=.9 lambda=.9 lr=.1 eps=.1 init 0, dense-faithful trace sweep",
                    "configs[3]: OfficeWorld 12-state RM, 262,144 instances x 4 agents, Q(lambda) traces",
                    262144, 4, 4 * 1296 * 4 * 4, "train_qlambda_kernel<OfficeWorld>"),
+    "cfg4_qrm": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, plants -100, synthetic 12-state completed chain RM, QLearning "
+                 "lr=.1 gamma=.9 eps=.1 init=2 use_qrm=True (11 counterfactual updates per step), per-instance Q tables",
+                 "configs[3]'s environment and reward machine with the QRM learner (generic / lane-group QRM kernel for nQ > 5)",
+                 65536, 512, 2 * 12 * 16 + 4 * 11, "train_qrm_block_kernel<OfficeWorld,12>"),
+    "ow_exp6_qrm": ("OfficeWorld map1 built-in task exp6 (A-B-C-D-E then coffee + e-mail to office, 10 RM states), 2 agents at "
+                    "(2,7),(6,3), slip hp=.8, QLearning lr=.1 gamma=.9 eps=.1 init=2 use_qrm=True, per-instance Q tables",
+                    "office_main --experiment exp6 batched (not a BASELINE configuration; the largest built-in machine)",
+                    65536, 1024, 2 * 10 * 16 + 4 * 9, "train_qrm_block_kernel<OfficeWorld,10>"),
     "cfg5_tables": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, per-instance Q tables",
                     "configs[4] HBM-bound companion: 1M FrozenLake instances x 4 agents, per-instance tables",
                     1048576, 256, 140, "train_qrm4_kernel<FrozenLake>"),
@@ -90,9 +98,19 @@ def scenario(workload):
         sc.algo = "qrm" if qrm else "ql"
         return sc
 
+    def cfg4_qrm():
+        sc = P.scenario_config4()
+        sc.algo, sc.learning_rate, sc.q_init = "qrm", 0.1, 2.0
+        return sc
+
+    def exp6():
+        return P.scenario_for_experiment("map1", "exp6", starts=[(2, 7), (6, 3)], algo="qrm", learning_rate=0.1, gamma=0.9,
+                                         stochastic=True, high_prob=0.8, epsilon_start=0.1, epsilon_end=0.1, epsilon_decay=1.0,
+                                         q_init=2.0, seed=1234)
+
     return {"cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
             "cfg2_batch": lambda: cfg2(False), "cfg2_batch_qrm": lambda: cfg2(True),
-            "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg5_tables": lambda: P.scenario_config5(False),
+            "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg4_qrm": cfg4_qrm, "ow_exp6_qrm": exp6, "cfg5_tables": lambda: P.scenario_config5(False),
             "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
 
 
