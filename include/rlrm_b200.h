@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RLRM_ABI_VERSION 1
+#define RLRM_ABI_VERSION 2
 
 #define RLRM_MAX_AGENTS 8      /* agents per instance (lane group = next power of two) */
 #define RLRM_MAX_CELLS 1024    /* W*H */
@@ -57,6 +57,12 @@ extern "C" {
 #define RLRM_ALGO_QL 0
 #define RLRM_ALGO_QRM 1
 #define RLRM_ALGO_QLAMBDA 2
+
+/* table arithmetic type. The reference keeps q_table / e_table / visits in float64 (np.zeros default: qlearning.py:26-29,
+ * qlearning_lambda.py:26-30). RLRM_TABLE_F64 is that arithmetic, bit for bit; RLRM_TABLE_F32 is what NumPy computes once the
+ * tables are cast to float32 (half the HBM bytes; the specialised kernels exist for this type only). */
+#define RLRM_TABLE_F32 0
+#define RLRM_TABLE_F64 1
 
 /* episode-loop semantics: R/environments/frozen_lake/frozen_lake_main.py:336-376,
  * R/environments/office_world/office_main.py:1696-1749 */
@@ -126,6 +132,7 @@ typedef struct rlrm_config {
   int32_t use_rsh;             /* QLearning.use_rsh: potential-based shaping R' = R + gamma*Phi(q') - Phi(q) (qlearning.py:51-66, 93-105) */
   int32_t n_actions;           /* 1..4 usable actions (exploration draws (w1*n_actions)>>32); tables are always 4 wide */
   int32_t reserved;            /* bit 0: force the generic kernels (testing: generic vs specialised must agree) */
+  int32_t table_dtype;         /* RLRM_TABLE_F32 / RLRM_TABLE_F64: element type of rlrm_state_t.q / e / tr_eq */
 } rlrm_config_t;
 
 /* host pointers; copied at rlrm_create */
@@ -180,9 +187,10 @@ typedef struct rlrm_state {
   int64_t n_instances;  /* N (local to this GPU) */
   uint64_t* slot;       /* [N*A] packed env + RM state, see RLRM_SLOT_* */
   double* epsilon;      /* [N*A] learner.epsilon */
-  float* q;             /* [N*A*S*4] (shared_q: [A*S*4]) learner.q_table, S = W*H*nQ. Must be 32-byte aligned (cudaMalloc and
-                           torch allocations are): rows are read with 16- and 32-byte vector loads. e / visits: 16-byte aligned. */
-  float* e;             /* Q(lambda) only: learner.e_table, same shape as q; else NULL */
+  void* q;              /* [N*A*S*4] (shared_q: [A*S*4]) learner.q_table, S = W*H*nQ; float (RLRM_TABLE_F32) or double
+                           (RLRM_TABLE_F64). Must be 32-byte aligned (cudaMalloc and torch allocations are): rows are read with
+                           16- and 32-byte vector loads. e: same alignment; visits: 16-byte aligned. */
+  void* e;              /* Q(lambda) only: learner.e_table, same shape and element type as q; else NULL */
   uint32_t* visits;     /* optional [same shape as q]: learner.visits; required when learning_rate < 0 */
   double* ep_return;    /* [N*A] running (undiscounted) return of the current episode */
   rlrm_stats_t* stats;  /* [N*A] or NULL */
@@ -199,7 +207,8 @@ typedef struct rlrm_state {
    * zero). rlrm_qlambda_materialize writes the listed values back so `q` can be read. Needs S*4 <= 65535. */
   uint16_t* tr_pos;     /* [N*A][S*4] 0 = entry not listed, else list position + 1 */
   uint16_t* tr_idx;     /* [N*A][tr_cap] listed entry index = enc*4 + action */
-  float* tr_eq;         /* [N*A][tr_cap][2] its (trace, current q value), interleaved: one 8-byte access per entry */
+  void* tr_eq;          /* [N*A][tr_cap][2] its (trace, current q value), interleaved (element type of q): one 8-byte
+                           (float) or 16-byte (double) access per entry */
   uint32_t* tr_len;     /* [N*A] list length */
   uint64_t* tr_work;    /* [N*A] or NULL: sum over update steps of the list length swept (bench: mean live traces) */
   int32_t tr_cap;       /* list capacity; must be >= max_steps + 1 (one new entry per step, wiped every episode) */
@@ -339,7 +348,7 @@ int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval_t* ev, uin
 
 /* Sparse Q(lambda) only: write every listed q value back into `q` (lists stay live) and, when e_dense is non-NULL
  * (device, [N*A*S*4], zeroed by the caller), scatter the traces into it — the dense view of learner.q_table / e_table. */
-int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, float* e_dense, void* stream);
+int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, void* e_dense, void* stream);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t rlrm_launch_count(const rlrm_handle_t* h);

@@ -1,10 +1,10 @@
 """ctypes mirror of include/rlrm_b200.h (struct layouts and constants). Keep in lock-step with the header;
-tests/test_abi.py checks sizes/offsets against a C program compiled from the header."""
+tests/test_host_logic.py::test_struct_layouts_match_the_header checks sizes/offsets against a C program compiled from the header."""
 from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_AGENTS = 8
 MAX_CELLS = 1024
 MAX_RM_STATES = 32
@@ -17,6 +17,7 @@ NO_TRANSITION = 255
 ENV_FROZEN_LAKE, ENV_OFFICE_WORLD = 0, 1
 ALGO_QL, ALGO_QRM, ALGO_QLAMBDA = 0, 1, 2
 DRIVER_FROZEN_LAKE_MAIN, DRIVER_OFFICE_MAIN = 0, 1
+TABLE_F32, TABLE_F64 = 0, 1
 
 SLOT_CELL_SHIFT, SLOT_STEPS_SHIFT, SLOT_TIME_SHIFT, SLOT_RMSTATE_SHIFT, SLOT_FLAGS_SHIFT = 0, 16, 32, 48, 56
 FLAG_ACTIVE, FLAG_FAIL, FLAG_DONE, FLAG_TRUNC, FLAG_FIRST = 1, 2, 4, 8, 16
@@ -66,6 +67,7 @@ class Config(C.Structure):
         ("use_rsh", C.c_int32),
         ("n_actions", C.c_int32),
         ("reserved", C.c_int32),
+        ("table_dtype", C.c_int32),
     ]
 
 

@@ -3,19 +3,9 @@ it). The agent is a host-side record (name, position, state dict, RM, encoders, 
 the learner, whose arithmetic runs on the device."""
 from __future__ import annotations
 
-import random
-
 
 class UPValueError(Exception):
     """Raised for an undefined action name (unified_planning.exceptions.UPValueError in the reference, agent_rl.py:55)."""
-
-
-class Message:
-    """A message an agent sends together with the condition it communicates (utils/message.py:1-6)."""
-
-    def __init__(self, sender, condition):
-        self.sender = sender
-        self.condition = condition
 
 
 class AgentRL:
@@ -67,11 +57,6 @@ class AgentRL:
             if value == action:
                 return key
         return None
-
-    def get_random_action(self):
-        if not self.actions_:
-            raise ValueError("No actions available for this agent.")
-        return random.choice(self.actions_)
 
     # -- wiring ----------------------------------------------------------------------------------
     def add_state_encoder(self, encoder):
@@ -157,36 +142,6 @@ class AgentRL:
     def reset_messages(self):
         self.messages = {}
         self.message_conditions = None
-
-    def return_messages(self):
-        return self.messages
-
-    # -- host-only bookkeeping the reference keeps on the agent (agent_rl.py:237-335); none of it is on the hot path ----
-    def add_rl_action(self, action):
-        self.actions_.append(action)
-
-    def execute_action(self, action):
-        """Run the action's effects when all its preconditions hold (agent_rl.py:318-335)."""
-        if action is None:
-            raise ValueError(f"Action not found for agent {self.name}.")
-        if all(pre(self) for pre in action.preconditions):
-            for effect in action.effects:
-                effect(self)
-            return True
-        return False
-
-    def _send_message(self, agents, condition):
-        self.ma_problem.broadcast_message(agents, Message(self.name, condition))
-
-    def _receive_message(self, message):
-        if isinstance(message, Message):
-            self.process_message(message)
-
-    def process_message(self, message):
-        self.messages[(message.sender, message.condition[0][0])] = message.condition[0][1]
-
-    def take_specific_action(self):
-        pass
 
     def set_state(self, **kwargs):
         for key, value in kwargs.items():

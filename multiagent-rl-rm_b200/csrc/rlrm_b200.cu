@@ -43,7 +43,21 @@ struct rlrm_handle {
   int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
   int shared_smem_bytes;
   int num_sms;
+  int f64;        // float64 tables (cfg.table_dtype == RLRM_TABLE_F64): generic kernels instantiated on double
+  int max_smem;   // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
 };
+
+// run STMT with T = float or double, whichever table type the handle was created for
+#define RLRM_BY_T(h, ...)   \
+  do {                      \
+    if ((h)->f64) {         \
+      typedef double T;     \
+      __VA_ARGS__;          \
+    } else {                \
+      typedef float T;      \
+      __VA_ARGS__;          \
+    }                       \
+  } while (0)
 
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, const char* detail = "") {
@@ -73,6 +87,8 @@ static void fill_learner(KP& kp, double lr, double gamma, double lambd) {
   kp.one_minus_lr_f = (float)(1.0 - lr);
   kp.gamma_f = (float)gamma;
   kp.trace_decay_f = (float)(gamma * lambd);
+  kp.one_minus_lr = 1.0 - lr;
+  kp.trace_decay = gamma * lambd;
 }
 
 // Table CONTENTS are indices the kernels follow without bounds checks: reject anything out of range here, on the host.
@@ -131,6 +147,9 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (cfg->algo < 0 || cfg->algo > RLRM_ALGO_QLAMBDA) return fail(RLRM_ERR_ARG, "unknown algo");
   if (cfg->env_kind != RLRM_ENV_FROZEN_LAKE && cfg->env_kind != RLRM_ENV_OFFICE_WORLD) return fail(RLRM_ERR_ARG, "unknown env_kind");
   if (cfg->algo == RLRM_ALGO_QLAMBDA && cfg->shared_q) return fail(RLRM_ERR_UNSUPPORTED, "Q(lambda) with a shared table is not supported");
+  if (cfg->table_dtype != RLRM_TABLE_F32 && cfg->table_dtype != RLRM_TABLE_F64) return fail(RLRM_ERR_ARG, "unknown table_dtype");
+  if (cfg->table_dtype == RLRM_TABLE_F64 && cfg->shared_q)
+    return fail(RLRM_ERR_UNSUPPORTED, "the shared learner is specified on float32 tables (fixed-point proposal sums of float32 values)");
   if (!tb->next_cell || !tb->cell_flags || !tb->label || !tb->delta || !tb->rq || !tb->rcf || !tb->start_cell)
     return fail(RLRM_ERR_ARG, "null table");
   if (int rc = validate_tables(cfg, tb)) return rc;
@@ -145,6 +164,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
   h->device = device;
+  h->f64 = cfg->table_dtype == RLRM_TABLE_F64;
   KP& kp = h->kp;
   kp.env_kind = cfg->env_kind; kp.driver = cfg->driver; kp.algo = cfg->algo;
   kp.A = cfg->n_agents;
@@ -203,6 +223,10 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.off_qrm = off; off = align16(off + RLRM_MAX_RM_STATES * sec);
   kp.off_free = off; off = align16(off + (kp.random_starts ? kp.n_free : 0) * 2);
   kp.blob_bytes = off;
+  if (off > 48 * 1024) {  // every kernel stages the blob in (non-opt-in) dynamic shared memory
+    delete h;
+    return fail(RLRM_ERR_UNSUPPORTED, "the table blob exceeds 48 KB of shared memory (too many per-agent reward-machine sections x states x events)");
+  }
   unsigned char* host = new (std::nothrow) unsigned char[off];
   if (!host) { delete h; return fail(RLRM_ERR_ARG, "out of host memory"); }
   memset(host, 0, off);
@@ -222,15 +246,16 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (e != cudaSuccess) { delete h; return fail(RLRM_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
   kp.blob = h->d_blob;
   h->smem_bytes = off;
-  h->qrm4_fast = (kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
+  const bool f32 = !h->f64;  // the specialised kernels exist for float32 tables
+  h->qrm4_fast = (f32 && kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
                   !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
-  h->qrmn_fast = (kp.algo == RLRM_ALGO_QRM && (kp.nQ == 3 || kp.nQ == 5) && kp.n_qrm == kp.nQ - 1 && !kp.shared_q && !kp.use_rsh &&
+  h->qrmn_fast = (f32 && kp.algo == RLRM_ALGO_QRM && (kp.nQ == 3 || kp.nQ == 5) && kp.n_qrm == kp.nQ - 1 && !kp.shared_q && !kp.use_rsh &&
                   !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 && !(cfg->reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrmn_fast = 0;
-  h->ql_fast = (kp.algo == RLRM_ALGO_QL && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
+  h->ql_fast = (f32 && kp.algo == RLRM_ALGO_QL && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
                 !(cfg->reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   {
@@ -239,15 +264,15 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     h->shared_smem_bytes = (int)need;
     h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
                       !(cfg->reserved & 1));
+    cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (need > h->max_smem) h->shared_fast = 0;
     if (h->shared_fast) {
-      cudaError_t e1 = cudaSuccess;
-      if (kp.env_kind == RLRM_ENV_FROZEN_LAKE) {
-        if (kp.algo == RLRM_ALGO_QRM) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-        else e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-      } else {
-        if (kp.algo == RLRM_ALGO_QRM) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-        else e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-      }
+      // opt every instantiation in to the DEVICE maximum: the attribute is per function, not per handle, so a later handle
+      // with a smaller table must never lower it under an earlier, larger one
+      cudaError_t e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
       if (e1 != cudaSuccess) h->shared_fast = 0;
     }
   }
@@ -275,7 +300,7 @@ extern "C" int64_t rlrm_launch_count(const rlrm_handle_t* h) { return h ? (int64
 
 static DState dstate(const rlrm_state_t* st) {
   DState d;
-  d.N = st->n_instances; d.slot = (unsigned long long*)st->slot; d.epsilon = st->epsilon; d.q = st->q; d.e = st->e;
+  d.N = st->n_instances; d.slot = (unsigned long long*)st->slot; d.epsilon = st->epsilon; d.q = (float*)st->q; d.e = (float*)st->e;
   d.visits = st->visits; d.ep_return = st->ep_return; d.stats = st->stats;
   d.acc_sum = (long long*)st->acc_sum; d.acc_cnt = st->acc_cnt; d.acc_last = st->acc_last;
   d.tr_pos = st->tr_pos; d.tr_idx = st->tr_idx; d.tr_eq = (float2*)st->tr_eq; d.tr_len = st->tr_len;
@@ -299,7 +324,7 @@ static int check_state(const rlrm_handle_t* h, const rlrm_state_t* st, bool need
   if (!st->slot || !st->epsilon) return fail(RLRM_ERR_ARG, "state.slot / state.epsilon are required");
   if (need_q && !st->q) return fail(RLRM_ERR_ARG, "state.q is required");
   if (need_q && ((uintptr_t)st->q & 31u)) return fail(RLRM_ERR_ARG, "state.q must be 32-byte aligned");
-  if (st->e && ((uintptr_t)st->e & 15u)) return fail(RLRM_ERR_ARG, "state.e must be 16-byte aligned");
+  if (st->e && ((uintptr_t)st->e & (h->f64 ? 31u : 15u))) return fail(RLRM_ERR_ARG, "state.e must be 16-byte (float64 tables: 32-byte) aligned");
   if (need_q && h->cfg.algo == RLRM_ALGO_QLAMBDA && !st->e) {
     if (!st->tr_pos || !st->tr_idx || !st->tr_eq || !st->tr_len)
       return fail(RLRM_ERR_ARG, "Q(lambda) needs state.e (dense traces) or state.tr_* (sparse traces)");
@@ -336,10 +361,10 @@ extern "C" int rlrm_reset_at(rlrm_handle_t* h, const rlrm_state_t* st, const uin
   reset_kernel<<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), mask, t);
   LAUNCH_CHECK(h);
   if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->e) {
-    clear_traces_kernel<<<blocks_for(n * (h->kp.S4 / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask);
+    RLRM_BY_T(h, clear_traces_kernel<T><<<blocks_for(n * (h->kp.S4 / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask));
     LAUNCH_CHECK(h);
   } else if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->tr_pos && st->q) {
-    qlambda_sparse_reset_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(h->kp, dstate(st), mask);
+    RLRM_BY_T(h, qlambda_sparse_reset_kernel<T><<<blocks_for(n * 32, 256), 256, 0, s>>>(h->kp, dstate(st), mask));
     LAUNCH_CHECK(h);
   }
   return RLRM_OK;
@@ -352,8 +377,8 @@ extern "C" int rlrm_select_action(rlrm_handle_t* h, const rlrm_state_t* st, cons
   if (!actions_out) return fail(RLRM_ERR_ARG, "actions_out is null");
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = st->n_instances * h->kp.A;
-  if (h->kp.per_agent) select_kernel<true><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out);
-  else select_kernel<false><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out);
+  if (h->kp.per_agent) RLRM_BY_T(h, select_kernel<true, T><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out));
+  else RLRM_BY_T(h, select_kernel<false, T><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), draws, t, best, actions_out));
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }
@@ -470,8 +495,8 @@ extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint1
   if (h->kp.algo == RLRM_ALGO_QLAMBDA && !st->e)
     return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update on Q(lambda) needs dense traces (state.e); sparse traces are for rlrm_train");
   if (h->kp.algo == RLRM_ALGO_QLAMBDA)
-    update_qlambda_kernel<<<(unsigned)n, 256, 0, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out));
-#define RLRM_UPD(ALGO, PA) update_kernel<ALGO, PA><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out))
+    RLRM_BY_T(h, update_qlambda_kernel<T><<<(unsigned)n, 256, 0, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out)));
+#define RLRM_UPD(ALGO, PA) RLRM_BY_T(h, update_kernel<ALGO, PA, T><<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), obs_cell, actions, term_arg, dout(out)))
   else if (h->kp.algo == RLRM_ALGO_QRM) {
     if (h->kp.per_agent) RLRM_UPD(RLRM_ALGO_QRM, true); else RLRM_UPD(RLRM_ALGO_QRM, false);
   } else {
@@ -490,13 +515,13 @@ template <int ENV>
 static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int n_iters, int learn, uint32_t* trace, cudaStream_t s) {
   const KP& kp = h->kp;
   if (kp.algo == RLRM_ALGO_QLAMBDA && !st->e) {
-    train_qlambda_sparse_kernel<ENV><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace));
   } else if (kp.algo == RLRM_ALGO_QLAMBDA) {
-    train_qlambda_kernel<ENV><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace);
+    RLRM_BY_T(h, train_qlambda_kernel<ENV, T><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace));
   } else {
     const long long threads = st->n_instances * kp.G;
     const unsigned grid = blocks_for(threads, TRAIN_BLOCK);
-#define RLRM_TRAIN(ALGO, PA) train_kernel<ENV, ALGO, PA><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace)
+#define RLRM_TRAIN(ALGO, PA) RLRM_BY_T(h, train_kernel<ENV, ALGO, PA, T><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace))
     if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits) {
       const DState d = dstate(st);
 #define RLRM_QRM4(ST, LE, TR)                                                                                          \
@@ -614,7 +639,7 @@ extern "C" int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = blocks_for(st->n_instances * h->kp.G, TRAIN_BLOCK);
   cudaStream_t s = (cudaStream_t)stream;
-#define RLRM_EVAL(ENV, PA) eval_kernel<ENV, PA><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps)
+#define RLRM_EVAL(ENV, PA) RLRM_BY_T(h, eval_kernel<ENV, PA, T><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(h->kp, dstate(st), ev, t0, n_iters, n_episodes, gamma, optimal_steps))
   if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) {
     if (h->kp.per_agent) RLRM_EVAL(RLRM_ENV_FROZEN_LAKE, true); else RLRM_EVAL(RLRM_ENV_FROZEN_LAKE, false);
   } else {
@@ -625,12 +650,12 @@ extern "C" int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval
   return RLRM_OK;
 }
 
-extern "C" int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, float* e_dense, void* stream) {
+extern "C" int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, void* e_dense, void* stream) {
   if (!h || !st) return fail(RLRM_ERR_ARG, "null handle/state");
   if (!st->q || !st->tr_idx || !st->tr_eq || !st->tr_len) return fail(RLRM_ERR_ARG, "no sparse trace state");
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = st->n_instances * h->kp.A;
-  qlambda_materialize_kernel<<<blocks_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), e_dense);
+  RLRM_BY_T(h, qlambda_materialize_kernel<T><<<blocks_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), (T*)e_dense));
   LAUNCH_CHECK(h);
   return RLRM_OK;
 }

@@ -22,6 +22,7 @@ struct KP {
   double hole_penalty, wall_penalty;
   double lr, gamma, eps_end, eps_decay;
   float lr_f, one_minus_lr_f, gamma_f, trace_decay_f;  // (float)lr, (float)(1-lr), (float)gamma, (float)(gamma*lambda)
+  double one_minus_lr, trace_decay;                    // 1 - lr and gamma*lambda as doubles (float64 tables)
   int decay_on_reset, shared_q, use_rsh, random_starts, n_free;
   // agents with different reward machines (rlrm_config_t.per_agent_rm): per-agent scalars and table strides
   int per_agent, a_nQ[RLRM_MAX_AGENTS], a_final[RLRM_MAX_AGENTS], a_nqrm[RLRM_MAX_AGENTS];
@@ -53,7 +54,7 @@ struct DState {  // rlrm_state_t by value
   long long N;
   unsigned long long* slot;
   double* epsilon;
-  float* q;
+  float* q;  // learner.q_table; holds doubles when the handle was created with table_dtype = RLRM_TABLE_F64 (tab<T>() below)
   float* e;
   unsigned* visits;
   double* ep_return;
@@ -63,7 +64,7 @@ struct DState {  // rlrm_state_t by value
   float* acc_last;
   unsigned short* tr_pos;  // Q(lambda) sparse-exact traces (include/rlrm_b200.h), null otherwise
   unsigned short* tr_idx;
-  float2* tr_eq;  // (trace, current q value) of each listed entry
+  float2* tr_eq;  // (trace, current q value) of each listed entry (double2 for float64 tables)
   unsigned* tr_len;
   unsigned long long* tr_work;
   int tr_cap;
@@ -105,6 +106,56 @@ __device__ __forceinline__ Tab stage_tables(const KP& p) {
   t.phi = reinterpret_cast<const double*>(smem_raw + p.off_phi);
   t.free_cells = reinterpret_cast<const unsigned short*>(smem_raw + p.off_free);
   return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// table arithmetic type. The reference keeps q_table / e_table in float64 (np.zeros default, qlearning.py:26-29,
+// qlearning_lambda.py:26-30); RT<double> is that arithmetic. RT<float> is what NumPy computes when the tables are cast to
+// float32 (NEP 50: weak Python scalars are rounded to the table dtype first, every operation rounds separately — hence the
+// explicit _rn intrinsics, which also keep the compiler from contracting a*b+c into an FMA).
+// ------------------------------------------------------------------------------------------------
+struct __align__(32) double4r {
+  double x, y, z, w;
+};
+template <typename T>
+struct RT;
+template <>
+struct RT<float> {
+  typedef float4 row_t;
+  typedef float2 pair_t;
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float cvt(double x) { return __double2float_rn(x); }
+  static __device__ __forceinline__ bool same_bits(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+  static __device__ __forceinline__ float lr(const KP& p) { return p.lr_f; }
+  static __device__ __forceinline__ float one_minus_lr(const KP& p) { return p.one_minus_lr_f; }
+  static __device__ __forceinline__ float gamma(const KP& p) { return p.gamma_f; }
+  static __device__ __forceinline__ float decay(const KP& p) { return p.trace_decay_f; }
+  static __device__ __forceinline__ row_t zero_row() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ pair_t make_pair(float a, float b) { return make_float2(a, b); }
+};
+template <>
+struct RT<double> {
+  typedef double4r row_t;
+  typedef double2 pair_t;
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double cvt(double x) { return x; }
+  static __device__ __forceinline__ bool same_bits(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+  static __device__ __forceinline__ double lr(const KP& p) { return p.lr; }
+  static __device__ __forceinline__ double one_minus_lr(const KP& p) { return p.one_minus_lr; }
+  static __device__ __forceinline__ double gamma(const KP& p) { return p.gamma; }
+  static __device__ __forceinline__ double decay(const KP& p) { return p.trace_decay; }
+  static __device__ __forceinline__ row_t zero_row() { return double4r{0.0, 0.0, 0.0, 0.0}; }
+  static __device__ __forceinline__ pair_t make_pair(double a, double b) { return make_double2(a, b); }
+};
+template <typename T>
+__device__ __forceinline__ T* tab(float* p) { return reinterpret_cast<T*>(p); }  // typed view of a DState table pointer
+template <typename T>
+__device__ __forceinline__ typename RT<T>::row_t load_row(const T* Q, size_t row) {
+  return *reinterpret_cast<const typename RT<T>::row_t*>(Q + row * 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -156,11 +207,12 @@ __device__ __forceinline__ unsigned long long explore_threshold(double eps) {
 }
 
 // QLearning.choose_action / choose_action_greedy (qlearning.py:112-143)
-__device__ __forceinline__ int select_action(const float4& row, unsigned long long explore_thr, const unsigned w[4], bool best,
+template <typename R>
+__device__ __forceinline__ int select_action(const R& row, unsigned long long explore_thr, const unsigned w[4], bool best,
                                              unsigned n_actions) {
   // np.argmax: first maximum
   int va = 0;
-  float m = row.x;
+  auto m = row.x;
   if (row.y > m) { m = row.y; va = 1; }
   if (row.z > m) { m = row.z; va = 2; }
   if (row.w > m) { m = row.w; va = 3; }
@@ -276,39 +328,47 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
   if (r.trunc) s.flags |= RLRM_FLAG_TRUNC;
 }
 
-__device__ __forceinline__ void set_component(float4& v, unsigned c, float x) {
+template <typename R, typename T>
+__device__ __forceinline__ void set_component(R& v, unsigned c, T x) {
   if (c == 0) v.x = x;
   else if (c == 1) v.y = x;
   else if (c == 2) v.z = x;
   else v.w = x;
 }
 
-__device__ __forceinline__ float get_component(const float4& v, unsigned c) {
+template <typename R>
+__device__ __forceinline__ auto get_component(const R& v, unsigned c) -> decltype(v.x) {
   return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w));
 }
 
 __device__ __forceinline__ float row_max(const float4& v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
+__device__ __forceinline__ double row_max(const double4r& v) { return fmax(fmax(v.x, v.y), fmax(v.z, v.w)); }
 
 // update_q (qlearning.py:70-79) in the float32 arithmetic numpy performs on a float32 table: weak Python scalars are
 // rounded to float32 first, every operation rounds separately (no FMA contraction).
-__device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, unsigned s, int a, double r, unsigned sn, bool terminated,
+template <typename T>
+__device__ __forceinline__ void update_q(const KP& p, T* Q, unsigned* V, unsigned s, int a, double r, unsigned sn, bool terminated,
                                          const Acc& acc) {
-  const float cur = Q[s * 4 + a];
-  const float mx = acc.rmax ? acc.rmax[sn] : row_max(*reinterpret_cast<const float4*>(Q + sn * 4));
-  const float mf = __fmul_rn(terminated ? 0.0f : 1.0f, mx);
-  const float inner = __fadd_rn(__double2float_rn(r), __fmul_rn(p.gamma_f, mf));
-  float out;
+  typedef RT<T> R;
+  const T cur = Q[s * 4 + a];
+  T mx;
+  if (sizeof(T) == 4 && acc.rmax) mx = (T)acc.rmax[sn];
+  else mx = row_max(load_row<T>(Q, sn));
+  const T mf = R::mul(terminated ? (T)0 : (T)1, mx);
+  const T inner = R::add(R::cvt(r), R::mul(R::gamma(p), mf));
+  T out;
   if (p.lr < 0.0) {  // lr = 1/visits is an np.float64: the outer expression is evaluated in double
     const unsigned v = V[s * 4 + a] + 1;
     V[s * 4 + a] = v;
     const double lr = __ddiv_rn(1.0, (double)v);
-    out = __double2float_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, lr), (double)cur), __dmul_rn(lr, (double)inner)));
+    out = R::cvt(__dadd_rn(__dmul_rn(__dsub_rn(1.0, lr), (double)cur), __dmul_rn(lr, (double)inner)));
   } else {
     if (V) V[s * 4 + a] += 1;
-    out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+    out = R::add(R::mul(R::one_minus_lr(p), cur), R::mul(R::lr(p), inner));
   }
-  if (acc.sum) {  // shared learner: propose; apply_shared_kernel turns the proposals of this iteration into their mean
-    const unsigned long long v = (unsigned long long)__float2ll_rn(__fmul_rn(out, 1048576.0f));
+  if (sizeof(T) == 4 && acc.sum) {  // shared learner (float32 tables only): propose; apply_shared_kernel turns the proposals of this iteration into their mean
+    const float outf = (float)out;
+    const unsigned long long v = (unsigned long long)__float2ll_rn(__fmul_rn(outf, 1048576.0f));
     if (acc.smem) {
       // shared memory has no native 64-bit add (the compiler emits a CAS spin loop, which collapses when many lanes propose
       // to the same entry): add the low word, derive the carry from the value the atomic returns, add the high word. Each
@@ -322,15 +382,15 @@ __device__ __forceinline__ void update_q(const KP& p, float* Q, unsigned* V, uns
       atomicAdd(reinterpret_cast<unsigned long long*>(acc.sum + s * 4 + a), v);
     }
     atomicAdd(acc.cnt + s * 4 + a, 1);
-    acc.last[s * 4 + a] = out;
+    acc.last[s * 4 + a] = outf;
   } else {
     Q[s * 4 + a] = out;
   }
 }
 
 // QL / QRM update of one agent (agent_rl.py:117-192 -> qlearning.py:41-110; QRM experiences rm_environment_wrapper.py:122-183)
-template <int ALGO>
-__device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, float* Q, unsigned* V, unsigned obs_cell, int action,
+template <int ALGO, typename T>
+__device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, T* Q, unsigned* V, unsigned obs_cell, int action,
                                              bool term_arg, const Rec& r, const Acc& acc) {
   if (ALGO == RLRM_ALGO_QRM) {
     const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;

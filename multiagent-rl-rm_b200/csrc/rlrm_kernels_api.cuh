@@ -21,16 +21,17 @@ __global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsig
 }
 
 // Q(lambda): reset_e_table for the masked instances (ma_frozen_lake.py:80-81 ; ma_office.py:101-102)
+template <typename T>
 __global__ void __launch_bounds__(256) clear_traces_kernel(KP p, DState st, const unsigned char* mask) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of one slot's table
   const long long per = p.S4 / 4;
   if (g >= st.N * p.A * per) return;
   const long long slot = g / per;
   if (mask && !mask[slot / p.A]) return;
-  reinterpret_cast<float4*>(st.e)[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  reinterpret_cast<typename RT<T>::row_t*>(st.e)[g] = RT<T>::zero_row();
 }
 
-template <bool PA>
+template <bool PA, typename T>
 __global__ void __launch_bounds__(256) select_kernel(KP p_in, DState st, const unsigned* draws, unsigned long long t, int best,
                                                     unsigned char* actions_out) {
   KP p = p_in;
@@ -40,8 +41,8 @@ __global__ void __launch_bounds__(256) select_kernel(KP p_in, DState st, const u
   const int a = (int)(k - i * p.A);
   if (PA) p.nQ = p_in.a_nQ[a];
   const Slot s = unpack_slot(st.slot[k]);
-  const float* Q = st.q + table_base(p_in, i, a);
-  const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+  const T* Q = tab<T>(st.q) + table_base(p_in, i, a);
+  const typename RT<T>::row_t row = load_row<T>(Q, s.cell * p.nQ + s.rm);
   unsigned w[4];
   if (draws) {
     const uint4 d = reinterpret_cast<const uint4*>(draws)[k];
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(256) rm_step_kernel(KP p_in, int agent, long l
   if (reward_out) reward_out[k] = r;
 }
 
-template <int ALGO, bool PA>
+template <int ALGO, bool PA, typename T>
 __global__ void __launch_bounds__(256) update_kernel(KP p_in, DState st, const unsigned short* obs_cell, const unsigned char* actions,
                                                     const unsigned char* term_arg, DOut o) {
   KP p = p_in;
@@ -229,53 +230,64 @@ __global__ void __launch_bounds__(256) update_kernel(KP p_in, DState st, const u
   r.event = o.event[k] == RLRM_EVENT_NONE ? (unsigned)RLRM_EVENT_NONE : min((unsigned)o.event[k], (unsigned)max(p.nEv, 1) - 1u);
   r.env_term = o.env_term[k] != 0; r.renv = o.renv[k]; r.reward = o.reward[k];
   const size_t base = table_base(p_in, i, a);
-  agent_update<ALGO>(p, tb, st.q + base, st.visits ? st.visits + base : nullptr, min((unsigned)obs_cell[k], cmax),
+  agent_update<ALGO, T>(p, tb, tab<T>(st.q) + base, st.visits ? st.visits + base : nullptr, min((unsigned)obs_cell[k], cmax),
                      min((int)actions[k], RLRM_N_ACTIONS - 1), term_arg[k] != 0, r, make_acc(p, st, base));
 }
 
 // QLearningLambda.update (qlearning_lambda.py:33-84), dense sweep exactly as written: one block per (instance, agent).
 // q += (lr*td) * e ; e = terminated ? 0 : e * (gamma*lambda), with e[s,a] replaced by 1 first.
-__device__ __forceinline__ void qlambda_sweep(const KP& p, float* Q, float* E, unsigned s, int a, double reward, unsigned sn,
+// one row (4 entries) of the dense sweep: q += c * e (float64 when lr = 1/visits), then e = terminated ? 0 : e * (gamma*lambda)
+template <typename T>
+__device__ __forceinline__ void sweep_row(const KP& p, typename RT<T>::row_t* Q4, typename RT<T>::row_t* E4, long long j, unsigned hot, T c,
+                                          double c64, bool lr_none, bool terminated) {
+  typedef RT<T> R;
+  typename R::row_t e = E4[j], q = Q4[j];
+  if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, (T)1);  // replacing trace
+  if (lr_none) {
+    q.x = R::cvt(__dadd_rn((double)q.x, __dmul_rn(c64, (double)e.x)));
+    q.y = R::cvt(__dadd_rn((double)q.y, __dmul_rn(c64, (double)e.y)));
+    q.z = R::cvt(__dadd_rn((double)q.z, __dmul_rn(c64, (double)e.z)));
+    q.w = R::cvt(__dadd_rn((double)q.w, __dmul_rn(c64, (double)e.w)));
+  } else {
+    q.x = R::add(q.x, R::mul(c, e.x));
+    q.y = R::add(q.y, R::mul(c, e.y));
+    q.z = R::add(q.z, R::mul(c, e.z));
+    q.w = R::add(q.w, R::mul(c, e.w));
+  }
+  if (terminated) {
+    e = R::zero_row();
+  } else {  // next_action defaults to argmax Q[s'] => greedy => decay (qlearning_lambda.py:71-81)
+    const T d = R::decay(p);
+    e.x = R::mul(e.x, d);
+    e.y = R::mul(e.y, d);
+    e.z = R::mul(e.z, d);
+    e.w = R::mul(e.w, d);
+  }
+  Q4[j] = q;
+  E4[j] = e;
+}
+
+template <typename T>
+__device__ __forceinline__ void qlambda_sweep(const KP& p, T* Q, T* E, unsigned s, int a, double reward, unsigned sn,
                                               bool terminated, int tid, int nthreads, unsigned visits_now) {
+  typedef RT<T> R;
+  typedef typename R::row_t row_t;
   // every thread reads the two scalars before anyone writes
-  const float4 nrow = *reinterpret_cast<const float4*>(Q + sn * 4);
-  const float qsa = Q[s * 4 + a];
+  const row_t nrow = load_row<T>(Q, sn);
+  const T qsa = Q[s * 4 + a];
   __syncthreads();
   const double best = terminated ? 0.0 : (double)row_max(nrow);
-  const float td = __fsub_rn(__double2float_rn(__dadd_rn(reward, __dmul_rn(p.gamma, best))), qsa);
-  const float c = __fmul_rn(p.lr_f, td);
+  const T td = R::sub(R::cvt(__dadd_rn(reward, __dmul_rn(p.gamma, best))), qsa);
+  const T c = R::mul(R::lr(p), td);
   const bool lr_none = p.lr < 0.0;  // lr = 1 / visits[s, a] (np.float64): the add happens in float64 (qlearning_lambda.py:44-49, 63)
   const double c64 = lr_none ? __dmul_rn(__ddiv_rn(1.0, (double)(visits_now ? visits_now : 1u)), (double)td) : 0.0;
   const unsigned hot = s * 4 + a;
-  float4* Q4 = reinterpret_cast<float4*>(Q);
-  float4* E4 = reinterpret_cast<float4*>(E);
-  for (long long j = tid; j < p.S4 / 4; j += nthreads) {
-    float4 e = E4[j], q = Q4[j];
-    if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);  // replacing trace
-    if (lr_none) {
-      q.x = __double2float_rn(__dadd_rn((double)q.x, __dmul_rn(c64, (double)e.x)));
-      q.y = __double2float_rn(__dadd_rn((double)q.y, __dmul_rn(c64, (double)e.y)));
-      q.z = __double2float_rn(__dadd_rn((double)q.z, __dmul_rn(c64, (double)e.z)));
-      q.w = __double2float_rn(__dadd_rn((double)q.w, __dmul_rn(c64, (double)e.w)));
-    } else {
-      q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
-      q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
-      q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
-      q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
-    }
-    if (terminated) {
-      e = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {  // next_action defaults to argmax Q[s'] => greedy => decay (qlearning_lambda.py:71-81)
-      e.x = __fmul_rn(e.x, p.trace_decay_f);
-      e.y = __fmul_rn(e.y, p.trace_decay_f);
-      e.z = __fmul_rn(e.z, p.trace_decay_f);
-      e.w = __fmul_rn(e.w, p.trace_decay_f);
-    }
-    Q4[j] = q;
-    E4[j] = e;
-  }
+  row_t* Q4 = reinterpret_cast<row_t*>(Q);
+  row_t* E4 = reinterpret_cast<row_t*>(E);
+  for (long long j = tid; j < p.S4 / 4; j += nthreads) sweep_row<T>(p, Q4, E4, j, hot, c, c64, lr_none, terminated);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, const unsigned short* obs_cell,
                                                             const unsigned char* actions, const unsigned char* term_arg, DOut o) {
   const long long k = blockIdx.x;
@@ -293,6 +305,6 @@ __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, co
     __syncthreads();
     if (threadIdx.x == 0) st.visits[base + (size_t)s_idx * 4 + action] = vis;
   }
-  qlambda_sweep(p, st.q + base, st.e + base, s_idx, action, o.reward[k], sn_idx, term_arg[k] != 0, threadIdx.x, blockDim.x, vis);
+  qlambda_sweep<T>(p, tab<T>(st.q) + base, tab<T>(st.e) + base, s_idx, action, o.reward[k], sn_idx, term_arg[k] != 0, threadIdx.x, blockDim.x, vis);
 }
 

@@ -5,7 +5,7 @@
 // ------------------------------------------------------------------------------------------------
 // greedy evaluation (test_policy_optima, evaluation_metrics.py:23-190): the driver loop with best=True and no update
 // ------------------------------------------------------------------------------------------------
-template <int ENV, bool PA>
+template <int ENV, bool PA, typename T>
 __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p_in, DState st, rlrm_eval_t* evs, unsigned long long t0, int n_iters,
                                                           int n_episodes, double gamma, double optimal_steps) {
   KP p = p_in;
@@ -20,12 +20,12 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p_in, DState st, r
   Slot s = {0, 0, 0, 0, 0};
   rlrm_eval_t e;
   memset(&e, 0, sizeof(e));
-  const float* Q = st.q;
+  const T* Q = tab<T>(st.q);
   if (valid) {
     s = unpack_slot(st.slot[k]);
     e = evs[k];
     if (PA) agent_view(p_in, p, tb, a);
-    Q = st.q + table_base(p_in, i, a);
+    Q = tab<T>(st.q) + table_base(p_in, i, a);
   }
   const unsigned w0[4] = {0, 0, 0, 0};
   for (int it = 0; it < n_iters; it++) {
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK) eval_kernel(KP p_in, DState st, r
     bool term = true, trunc = true;
     const bool running = valid && (int)e.episodes < n_episodes;  // all agents of an instance finish episodes together
     if (running) {
-      const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+      const typename RT<T>::row_t row = load_row<T>(Q, s.cell * p.nQ + s.rm);
       const int action = select_action(row, 0ull, w0, true, p.n_actions);
       unsigned w3 = 0;
       if (p.stochastic) {
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
         const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
         Acc acc = {reinterpret_cast<long long*>(s_sum) + (size_t)a * (size_t)p.S4, s_cnt + (size_t)a * (size_t)p.S4,
                    s_last + (size_t)a * (size_t)p.S4, true, s_rmax + (size_t)a * (size_t)(p.S4 / 4)};
-        agent_update<ALGO>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
+        agent_update<ALGO, float>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
       }
       term = r.term;
       trunc = r.trunc;

@@ -1,10 +1,13 @@
 // rlrm_kernels_qlambda.cuh: Q(lambda) fused kernels, dense-faithful and sparse-exact — part of the single translation unit csrc/rlrm_b200.cu (see its header comment).
 #pragma once
+#include "rlrm_kernels_api.cuh"
 #include "rlrm_kernels_train.cuh"
 
-template <int ENV>
+template <int ENV, typename T>
 __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
                                                            unsigned* trace) {
+  typedef RT<T> R;
+  typedef typename R::row_t row_t;
   Tab tb = stage_tables(p);
   __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
   const long long i = blockIdx.x;
@@ -15,8 +18,8 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
   double eps = st.epsilon[k];
   double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
   const size_t base = table_base(p, i, a);
-  float* Q = st.q + base;
-  float* E = st.e + base;
+  T* Q = tab<T>(st.q) + base;
+  T* E = tab<T>(st.e) + base;
   unsigned* V = st.visits ? st.visits + base : nullptr;  // QLearningLambda counts visits on every update (qlearning_lambda.py:44)
   unsigned long long active_steps = 0;
   unsigned episodes = 0, successes = 0, last_length = 0;
@@ -32,7 +35,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
     unsigned w[4];
     RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
     __syncwarp();
-    const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+    const row_t row = load_row<T>(Q, s.cell * p.nQ + s.rm);
     const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
     const unsigned before = s.cell;
     const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
@@ -43,12 +46,12 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
       const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
       // warp-cooperative dense sweep (the __syncthreads inside qlambda_sweep is replaced by __syncwarp here)
       const unsigned sidx = obs * p.nQ + r.prev_q, snidx = r.cell * p.nQ + r.q;
-      const float4 nrow = *reinterpret_cast<const float4*>(Q + snidx * 4);
-      const float qsa = Q[sidx * 4 + action];
+      const row_t nrow = load_row<T>(Q, snidx);
+      const T qsa = Q[sidx * 4 + action];
       __syncwarp();
       const double best = term_arg ? 0.0 : (double)row_max(nrow);
-      const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
-      const float c = __fmul_rn(p.lr_f, td);
+      const T td = R::sub(R::cvt(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
+      const T c = R::mul(R::lr(p), td);
       const unsigned hot = sidx * 4 + action;
       // learning_rate=None: lr = 1 / visits[s, a] is an np.float64, so lr * td and (lr * td) * e_table are float64 and the
       // in-place add happens in float64 before the cast back to float32 (qlearning_lambda.py:44-49, 63)
@@ -60,33 +63,9 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
         if (lane == 0) V[hot] = vis;
       }
       const double c64 = lr_none ? __dmul_rn(__ddiv_rn(1.0, (double)vis), (double)td) : 0.0;
-      float4* Q4 = reinterpret_cast<float4*>(Q);
-      float4* E4 = reinterpret_cast<float4*>(E);
-      for (long long j = lane; j < p.S4 / 4; j += 32) {
-        float4 e = E4[j], q = Q4[j];
-        if ((unsigned)j == (hot >> 2)) set_component(e, hot & 3, 1.0f);
-        if (lr_none) {
-          q.x = __double2float_rn(__dadd_rn((double)q.x, __dmul_rn(c64, (double)e.x)));
-          q.y = __double2float_rn(__dadd_rn((double)q.y, __dmul_rn(c64, (double)e.y)));
-          q.z = __double2float_rn(__dadd_rn((double)q.z, __dmul_rn(c64, (double)e.z)));
-          q.w = __double2float_rn(__dadd_rn((double)q.w, __dmul_rn(c64, (double)e.w)));
-        } else {
-          q.x = __fadd_rn(q.x, __fmul_rn(c, e.x));
-          q.y = __fadd_rn(q.y, __fmul_rn(c, e.y));
-          q.z = __fadd_rn(q.z, __fmul_rn(c, e.z));
-          q.w = __fadd_rn(q.w, __fmul_rn(c, e.w));
-        }
-        if (term_arg) {
-          e = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          e.x = __fmul_rn(e.x, p.trace_decay_f);
-          e.y = __fmul_rn(e.y, p.trace_decay_f);
-          e.z = __fmul_rn(e.z, p.trace_decay_f);
-          e.w = __fmul_rn(e.w, p.trace_decay_f);
-        }
-        Q4[j] = q;
-        E4[j] = e;
-      }
+      row_t* Q4 = reinterpret_cast<row_t*>(Q);
+      row_t* E4 = reinterpret_cast<row_t*>(E);
+      for (long long j = lane; j < p.S4 / 4; j += 32) sweep_row<T>(p, Q4, E4, j, hot, c, c64, lr_none, term_arg);
       __syncwarp();
     }
     ep_ret = __dadd_rn(ep_ret, r.reward);
@@ -117,8 +96,8 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
       reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
       // reset_e_table (ma_office.py:101-102)
-      float4* E4 = reinterpret_cast<float4*>(E);
-      for (long long j = lane; j < p.S4 / 4; j += 32) E4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      row_t* E4 = reinterpret_cast<row_t*>(E);
+      for (long long j = lane; j < p.S4 / 4; j += 32) E4[j] = R::zero_row();
       __syncwarp();
     }
   }
@@ -146,20 +125,25 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
 // table), so one update step reads/writes the list once, 8 bytes per entry. Bit-identical to the dense sweep of
 // QLearningLambda.update (qlearning_lambda.py:33-84) up to the sign of zero: unlisted entries have e == 0 and receive +0.
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 struct TraceList {
-  unsigned short* pos;  // [S*4]
-  unsigned short* idx;  // [cap]
-  float2* eq;           // [cap] (trace, current q value)
+  unsigned short* pos;         // [S*4]
+  unsigned short* idx;         // [cap]
+  typename RT<T>::pair_t* eq;  // [cap] (trace, current q value)
 };
+template <typename T>
+__device__ __forceinline__ typename RT<T>::pair_t* pairs(float2* p) { return reinterpret_cast<typename RT<T>::pair_t*>(p); }
 
 // current value of table entry j: the listed copy when the entry has a live trace, else the table
-__device__ __forceinline__ float trace_lookup(const float* Q, const TraceList& L, unsigned j) {
+template <typename T>
+__device__ __forceinline__ T trace_lookup(const T* Q, const TraceList<T>& L, unsigned j) {
   const unsigned pz = L.pos[j];
   return pz ? L.eq[pz - 1].y : Q[j];
 }
 
 // write the listed values back and forget the list (traces wiped: reset_e_table / e_table.fill(0))
-__device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsigned len, int lane, int stride = 32) {
+template <typename T>
+__device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigned len, int lane, int stride = 32) {
   for (unsigned j = lane; j < len; j += stride) {
     const unsigned id = L.idx[j];
     Q[id] = L.eq[j].y;
@@ -174,9 +158,12 @@ __device__ __forceinline__ void trace_flush(float* Q, const TraceList& L, unsign
 // profiles/r01_sparse_qlambda_ncu.csv): the lists stay L1-resident for the n_iters of a launch, so the kernel is bound by
 // instruction issue, not by HBM. Episode-over detection is two warp ballots; no shared memory, no block barrier.
 #define QLS_BLOCK 128
-template <int ENV>
+template <int ENV, typename T>
 __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
                                                                         unsigned* trace) {
+  typedef RT<T> R;
+  typedef typename R::row_t row_t;
+  typedef typename R::pair_t pair_t;
   Tab tb = stage_tables(p);
   const long long i = (long long)blockIdx.x * (QLS_BLOCK / 32) + (threadIdx.x >> 5);
   if (i >= st.N) return;  // whole warps leave; nothing below synchronises across warps
@@ -189,12 +176,12 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
   const long long k = i * p.A + (valid ? a : 0);
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
-  float* Q = st.q + table_base(p, i, valid ? a : 0);
+  T* Q = tab<T>(st.q) + table_base(p, i, valid ? a : 0);
   unsigned* V = st.visits ? st.visits + table_base(p, i, valid ? a : 0) : nullptr;
-  TraceList L;
+  TraceList<T> L;
   L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
-  L.eq = st.tr_eq + (size_t)k * (size_t)st.tr_cap;
+  L.eq = pairs<T>(st.tr_eq) + (size_t)k * (size_t)st.tr_cap;
   unsigned len = 0;
   rlrm_stats_t z;
   if (valid) {
@@ -220,8 +207,8 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
     __syncwarp();
     // Q row of the current state: group lanes 0..3 fetch one action value each
     const unsigned rbase = (s.cell * p.nQ + s.rm) * 4;
-    const float mine = (valid && gl < 4) ? trace_lookup(Q, L, rbase + gl) : 0.f;
-    float4 row;
+    const T mine = (valid && gl < 4) ? trace_lookup<T>(Q, L, rbase + gl) : (T)0;
+    row_t row;
     row.x = __shfl_sync(FULL, mine, 0, LG);
     row.y = __shfl_sync(FULL, mine, 1, LG);
     row.z = __shfl_sync(FULL, mine, 2, LG);
@@ -238,23 +225,23 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       const unsigned hot = (obs * p.nQ + r.prev_q) * 4 + action, nbase = (r.cell * p.nQ + r.q) * 4;
       // group lanes 0..3: next-state row; lane 4 (groups of 8+) or lane 0 in a second round (groups of 4): Q[s,a] together
       // with its list position (0 = no live trace yet), which also tells the sweep which entry is the visited one
-      float got = 0.f;
+      T got = (T)0;
       unsigned pz = 0;
       if (valid && gl < 4) {
-        got = trace_lookup(Q, L, nbase + gl);
+        got = trace_lookup<T>(Q, L, nbase + gl);
       } else if (valid && gl == 4) {
         pz = L.pos[hot];
         got = pz ? L.eq[pz - 1].y : Q[hot];
       }
-      const float n0 = __shfl_sync(FULL, got, 0, LG), n1 = __shfl_sync(FULL, got, 1, LG);
-      const float n2 = __shfl_sync(FULL, got, 2, LG), n3 = __shfl_sync(FULL, got, 3, LG);
-      float qsa;
+      const T n0 = __shfl_sync(FULL, got, 0, LG), n1 = __shfl_sync(FULL, got, 1, LG);
+      const T n2 = __shfl_sync(FULL, got, 2, LG), n3 = __shfl_sync(FULL, got, 3, LG);
+      T qsa;
       unsigned hotpos;
       if (LG > 4) {
         qsa = __shfl_sync(FULL, got, 4, LG);
         hotpos = __shfl_sync(FULL, pz, 4, LG);
       } else {
-        float h = 0.f;
+        T h = (T)0;
         if (valid && gl == 0) {
           pz = L.pos[hot];
           h = pz ? L.eq[pz - 1].y : Q[hot];
@@ -262,9 +249,11 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
         qsa = __shfl_sync(FULL, h, 0, LG);
         hotpos = __shfl_sync(FULL, gl == 0 ? pz : 0u, 0, LG);
       }
-      const double best = term_arg ? 0.0 : (double)fmaxf(fmaxf(n0, n1), fmaxf(n2, n3));
-      const float td = __fsub_rn(__double2float_rn(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
-      const float c = __fmul_rn(p.lr_f, td);
+      row_t nrow;
+      nrow.x = n0; nrow.y = n1; nrow.z = n2; nrow.w = n3;
+      const double best = term_arg ? 0.0 : (double)row_max(nrow);
+      const T td = R::sub(R::cvt(__dadd_rn(r.reward, __dmul_rn(p.gamma, best))), qsa);
+      const T c = R::mul(R::lr(p), td);
       const bool lr_none = p.lr < 0.0;  // lr = 1 / visits: float64 arithmetic, see train_qlambda_kernel
       unsigned vis = 0;
       if (V && valid) {
@@ -274,18 +263,18 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       if (V && valid && gl == 0) V[hot] = vis;
       const double c64 = lr_none ? __dmul_rn(__ddiv_rn(1.0, (double)(vis ? vis : 1u)), (double)td) : 0.0;
       for (unsigned j = gl; j < len; j += LG) {  // one pass over the agent's live entries (len = 0 on idle lanes)
-        float2 eq = L.eq[j];
-        if (j + 1 == hotpos) eq.x = 1.0f;  // replacing trace on the visited entry
-        eq.y = lr_none ? __double2float_rn(__dadd_rn((double)eq.y, __dmul_rn(c64, (double)eq.x))) : __fadd_rn(eq.y, __fmul_rn(c, eq.x));
-        eq.x = term_arg ? 0.0f : __fmul_rn(eq.x, p.trace_decay_f);
+        pair_t eq = L.eq[j];
+        if (j + 1 == hotpos) eq.x = (T)1;  // replacing trace on the visited entry
+        eq.y = lr_none ? R::cvt(__dadd_rn((double)eq.y, __dmul_rn(c64, (double)eq.x))) : R::add(eq.y, R::mul(c, eq.x));
+        eq.x = term_arg ? (T)0 : R::mul(eq.x, R::decay(p));
         L.eq[j] = eq;
       }
       work += len;
       if (valid && hotpos == 0u) {  // first visit since the last wipe: the table value (qsa) is current
         if (gl == 0) {
           L.idx[len] = (unsigned short)hot;
-          const float q_new = lr_none ? __double2float_rn(__dadd_rn((double)qsa, __dmul_rn(c64, 1.0))) : __fadd_rn(qsa, __fmul_rn(c, 1.0f));
-          L.eq[len] = make_float2(term_arg ? 0.0f : __fmul_rn(1.0f, p.trace_decay_f), q_new);
+          const T q_new = lr_none ? R::cvt(__dadd_rn((double)qsa, __dmul_rn(c64, 1.0))) : R::add(qsa, R::mul(c, (T)1));
+          L.eq[len] = R::make_pair(term_arg ? (T)0 : R::mul((T)1, R::decay(p)), q_new);
           L.pos[hot] = (unsigned short)(len + 1);
         }
         len++;
@@ -313,7 +302,7 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       wipe = true;  // reset_e_table (ma_office.py:101-102)
     }
     __syncwarp();
-    trace_flush(Q, L, wipe ? len : 0u, gl, LG);
+    trace_flush<T>(Q, L, wipe ? len : 0u, gl, LG);
     if (wipe) len = 0;
     __syncwarp();
   }
@@ -338,32 +327,34 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
 }
 
 // sparse Q(lambda): listed values -> table (lists stay live); optionally scatter the traces into a dense buffer
-__global__ void __launch_bounds__(256) qlambda_materialize_kernel(KP p, DState st, float* e_dense) {
+template <typename T>
+__global__ void __launch_bounds__(256) qlambda_materialize_kernel(KP p, DState st, T* e_dense) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= st.N * p.A) return;
-  float* Q = st.q + (size_t)warp * (size_t)p.S4;
+  T* Q = tab<T>(st.q) + (size_t)warp * (size_t)p.S4;
   const unsigned short* idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
-  const float2* leq = st.tr_eq + (size_t)warp * (size_t)st.tr_cap;
+  const typename RT<T>::pair_t* leq = pairs<T>(st.tr_eq) + (size_t)warp * (size_t)st.tr_cap;
   const unsigned len = st.tr_len[warp];
   for (unsigned j = lane; j < len; j += 32) {
-    const float2 eq = leq[j];
+    const typename RT<T>::pair_t eq = leq[j];
     Q[idx[j]] = eq.y;
     if (e_dense) e_dense[(size_t)warp * (size_t)p.S4 + idx[j]] = eq.x;
   }
 }
 
 // sparse Q(lambda): reset_e_table for the masked instances = flush + forget the lists
+template <typename T>
 __global__ void __launch_bounds__(256) qlambda_sparse_reset_kernel(KP p, DState st, const unsigned char* mask) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= st.N * p.A) return;
   if (mask && !mask[warp / p.A]) return;
-  TraceList L;
+  TraceList<T> L;
   L.pos = st.tr_pos + (size_t)warp * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
-  L.eq = st.tr_eq + (size_t)warp * (size_t)st.tr_cap;
-  trace_flush(st.q + (size_t)warp * (size_t)p.S4, L, st.tr_len[warp], lane);
+  L.eq = pairs<T>(st.tr_eq) + (size_t)warp * (size_t)st.tr_cap;
+  trace_flush<T>(tab<T>(st.q) + (size_t)warp * (size_t)p.S4, L, st.tr_len[warp], lane);
   __syncwarp();
   if (lane == 0) st.tr_len[warp] = 0;
 }

@@ -10,9 +10,12 @@
 #define QLF_MINB 8
 #endif
 
-template <int ENV, int ALGO, bool PA>
-__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
+// T = table arithmetic type (float: float32 tables; double: the reference's native float64 tables, see RT<T>)
+template <int ENV, int ALGO, bool PA, typename T>
+__global__ void __launch_bounds__(TRAIN_BLOCK, sizeof(T) == 4 ? 7 : 5) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                            unsigned* trace) {
+  typedef RT<T> R;
+  typedef typename R::row_t row_t;
   KP p = p_in;
   Tab tb = stage_tables(p_in);
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -25,7 +28,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState s
 
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0;
-  float* Q = nullptr;
+  T* Q = nullptr;
   unsigned* V = nullptr;
   Acc acc = {nullptr, nullptr, nullptr, false, nullptr};
   unsigned long long active_steps = 0;
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState s
     if (st.stats) return_sum = st.stats[k].return_sum;
     if (PA) agent_view(p_in, p, tb, a);
     const size_t base = table_base(p_in, i, a);
-    Q = st.q + base;
+    Q = tab<T>(st.q) + base;
     V = st.visits ? st.visits + base : nullptr;
     acc = make_acc(p, st, base);
   }
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState s
   bool had_episode = false;
   // plain QL with a private table, fixed learning rate and no visit counts: carry the current row across iterations
   const bool carry = (ALGO == RLRM_ALGO_QL) && !V && !acc.sum && p.lr >= 0.0;
-  float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+  row_t row = R::zero_row();
   unsigned row_idx = 0xFFFFFFFFu;
 
   for (int it = 0; it < n_iters; it++) {
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState s
       // every agent selects on every iteration, finished ones included (frozen_lake_main.py:350-352)
       const unsigned cur_idx = s.cell * p.nQ + s.rm;
       if (cur_idx != row_idx) {  // plain QL carries the row of its current state in registers (1-entry cache of Q)
-        row = *reinterpret_cast<const float4*>(Q + (size_t)cur_idx * 4);
+        row = load_row<T>(Q, cur_idx);
         row_idx = carry ? cur_idx : 0xFFFFFFFFu;
       }
       action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
@@ -76,15 +79,15 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState s
         if (ALGO == RLRM_ALGO_QL && carry) {
           // update_q (qlearning.py:70-79) against the carried row: normally Q[s] is the carried row and only Q[s'] is loaded
           const unsigned sidx = obs * p.nQ + r.prev_q, snidx = r.cell * p.nQ + r.q;
-          float4 nrow = (snidx == row_idx) ? row : *reinterpret_cast<const float4*>(Q + (size_t)snidx * 4);
-          const float cur = (sidx == row_idx) ? get_component(row, action)
+          row_t nrow = (snidx == row_idx) ? row : load_row<T>(Q, snidx);
+          const T cur = (sidx == row_idx) ? get_component(row, action)
                                                : ((sidx == snidx) ? get_component(nrow, action) : Q[(size_t)sidx * 4 + action]);
           double rew = r.reward;
           if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.nQ + r.q]), tb.phi[p.nQ + r.prev_q]));
-          const float mf = __fmul_rn(term_arg ? 0.0f : 1.0f, row_max(nrow));
-          const float inner = __fadd_rn(__double2float_rn(rew), __fmul_rn(p.gamma_f, mf));
-          const float out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
-          if (__float_as_uint(out) != __float_as_uint(cur)) Q[(size_t)sidx * 4 + action] = out;
+          const T mf = R::mul(term_arg ? (T)0 : (T)1, row_max(nrow));
+          const T inner = R::add(R::cvt(rew), R::mul(R::gamma(p), mf));
+          const T out = R::add(R::mul(R::one_minus_lr(p), cur), R::mul(R::lr(p), inner));
+          if (!R::same_bits(out, cur)) Q[(size_t)sidx * 4 + action] = out;
           if (sidx == row_idx) set_component(row, action, out);
           if (snidx != row_idx) {  // the next state's row becomes the carried one
             if (sidx == snidx) set_component(nrow, action, out);
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_kernel(KP p_in, DState s
             row_idx = snidx;
           }
         } else {
-          agent_update<ALGO>(p, tb, Q, V, obs, action, term_arg, r, acc);
+          agent_update<ALGO, T>(p, tb, Q, V, obs, action, term_arg, r, acc);
         }
       }
       term = r.term;

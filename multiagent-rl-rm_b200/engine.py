@@ -56,11 +56,12 @@ class Engine:
             self.agent_rows = list(compiled.agent_rows)
             tab_shape = (1 if self.cfg.shared_q else self.N, sum(self.agent_rows), 4)
         d = self.device
+        self.table_dtype = torch.float64 if self.cfg.table_dtype == abi.TABLE_F64 else torch.float32
         self.slot = torch.zeros(n_slots, dtype=torch.int64, device=d)
         self.epsilon = torch.full((n_slots,), float(self.cfg.epsilon_start), dtype=torch.float64, device=d)
-        self.q = torch.full(tab_shape, float(compiled.scenario.q_init), dtype=torch.float32, device=d)
+        self.q = torch.full(tab_shape, float(compiled.scenario.q_init), dtype=self.table_dtype, device=d)
         self.sparse = bool(qlambda_sparse) and self.cfg.algo == abi.ALGO_QLAMBDA
-        self.e = torch.zeros(tab_shape, dtype=torch.float32, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
+        self.e = torch.zeros(tab_shape, dtype=self.table_dtype, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
         self.tr_cap = 0
         self.tr_pos = self.tr_idx = self.tr_eq = self.tr_len = self.tr_work = None
         if self.sparse:
@@ -69,7 +70,7 @@ class Engine:
             self.tr_cap = ((int(self.cfg.max_steps) + 1 + 31) // 32) * 32
             self.tr_pos = torch.zeros((n_slots, self.S * 4), dtype=torch.int16, device=d)
             self.tr_idx = torch.zeros((n_slots, self.tr_cap), dtype=torch.int16, device=d)
-            self.tr_eq = torch.zeros((n_slots, self.tr_cap, 2), dtype=torch.float32, device=d)  # (trace, q value) pairs
+            self.tr_eq = torch.zeros((n_slots, self.tr_cap, 2), dtype=self.table_dtype, device=d)  # (trace, q value) pairs
             self.tr_len = torch.zeros(n_slots, dtype=torch.int32, device=d)
             self.tr_work = torch.zeros(n_slots, dtype=torch.int64, device=d)
         need_visits = track_visits or self.cfg.learning_rate < 0

@@ -53,10 +53,8 @@ def save_q_tables(engine_or_agents, agent_names: Optional[Sequence[str]] = None,
     if hasattr(engine_or_agents, "q") and hasattr(engine_or_agents, "N"):  # engine.Engine
         eng = engine_or_agents
         names = list(agent_names) if agent_names else [f"a{k + 1}" for k in range(eng.A)]
-        q = eng.q.detach().cpu().numpy()
-        q = q.reshape(eng.A, eng.S, 4) if eng.cfg.shared_q else q.reshape(eng.N, eng.A, eng.S, 4)
-        for k, name in enumerate(names):
-            table = q[k] if eng.cfg.shared_q else q[:, k]
+        for k, name in enumerate(names):  # agent_table() flushes sparse Q(lambda) lists and handles per-agent table sections
+            table = eng.agent_table(k).detach().cpu().numpy()
             arrays[f"q_table_{name}"] = table[0] if (table.ndim == 3 and table.shape[0] == 1) else table
     else:  # iterable of AgentRL-like objects
         for ag in engine_or_agents:
@@ -77,7 +75,7 @@ def load_q_tables_into(engine, path_or_tables, agent_names: Optional[Sequence[st
     names = list(agent_names) if agent_names else [f"a{k + 1}" for k in range(engine.A)]
     q = engine.q.view(engine.A, engine.S, 4) if engine.cfg.shared_q else engine.q.view(engine.N, engine.A, engine.S, 4)
     for k, name in enumerate(names):
-        t = torch.as_tensor(np.asarray(tables[name]), dtype=torch.float32, device=engine.q.device)
+        t = torch.as_tensor(np.asarray(tables[name]), dtype=engine.q.dtype, device=engine.q.device)
         if engine.cfg.shared_q:
             q[k].copy_(t.reshape(engine.S, 4))
         else:
@@ -118,7 +116,7 @@ def test_policy_opt_multi_batched(engine, policies, episodes_test: int = 100, op
             sc.stochastic = not test_deterministic
         if test_deterministic:
             episodes_test = 1
-    scratch = Engine(compile_scenario(sc, instance_offset=int(engine.cfg.instance_offset)), engine.N, device=engine.device, with_stats=False)
+    scratch = Engine(compile_scenario(sc, grid=engine.c.grid, rm=engine.c.rm, instance_offset=int(engine.cfg.instance_offset)), engine.N, device=engine.device, with_stats=False)
     onehot = torch.zeros_like(scratch.q).view(engine.N, engine.A, engine.S, 4)
     onehot.scatter_(3, torch.from_numpy(np.array(pol, dtype=np.int64)).to(engine.device).unsqueeze(-1), 1.0)
     scratch.q.copy_(onehot.view_as(scratch.q))

@@ -60,6 +60,9 @@ class Scenario:
     q_init: float = 2.0
     driver: str = "frozen_lake_main"  # "frozen_lake_main" | "office_main"
     shared_q: bool = False
+    # element type of the learner tables on the device: "f32" (NumPy-on-float32 arithmetic, half the bytes, all specialised
+    # kernels) or "f64" (the reference's native float64 tables, qlearning.py:26-29 — bit-identical to the unmodified reference)
+    table_dtype: str = "f32"
     seed: int = 1234
     # reward shaping on the RM (QL_RS / QRM_RS, office_main.py:543-573): "vi" = add_reward_shaping, "distance" = add_distance_reward_shaping
     use_rsh: bool = False
@@ -315,6 +318,9 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
     cfg.seed_hi = (sc.seed >> 32) & 0xFFFFFFFF
     cfg.instance_offset = instance_offset
     cfg.n_actions = 4
+    if sc.table_dtype not in ("f32", "f64"):
+        raise ValueError("table_dtype must be 'f32' or 'f64'")
+    cfg.table_dtype = abi.TABLE_F64 if sc.table_dtype == "f64" else abi.TABLE_F32
     phi = None
     if sc.use_rsh or getattr(rm, "potentials", None) is not None:
         if getattr(rm, "potentials", None) is None:

@@ -90,9 +90,12 @@ class BatchedRMEnvironment:
 
     @property
     def q_table(self) -> torch.Tensor:
-        """learner.q_table of every agent: [N, A, S, 4] (shared learner: [A, S, 4])."""
+        """learner.q_table of every agent: [N, A, S, 4] (shared learner: [A, S, 4]); with per-agent reward machines the
+        tables differ in size, so a list of [N, S_a, 4] tensors (one per agent) is returned instead."""
         e = self.engine
         e.sync_tables()
+        if e.cfg.per_agent_rm:
+            return [e.agent_table(a) for a in range(e.A)]
         return e.q.view(e.A, e.S, 4) if e.cfg.shared_q else e.q.view(e.N, e.A, e.S, 4)
 
     # -- the reference's calls ---------------------------------------------------------------------

@@ -157,6 +157,14 @@ def scenarios():
     sc.penalty_amount = -2.0
     S["fl_qlambda_lr_none"] = (sc, 2, 900, "f32", 1)
     S["fl_qlambda_lr_none_f64"] = (sc, 1, 500, "f64", 1)
+    # float64 companions (the reference's NATIVE table type) of fixtures above: the device's float64 table mode
+    # (RLRM_TABLE_F64) must reproduce these bit for bit, 20,000-iteration runs included
+    for base, n, t in (("cfg3_slip_qrm", 2, 800), ("cfg2_office_slip_ql", 2, 1500), ("fl_lr_none_ql", 2, 600), ("fl_lr_none_qrm", 2, 600),
+                       ("fl_shaping_vi_ql", 2, 500), ("fl_shaping_distance_qrm", 2, 500), ("fl_per_agent_rms_qrm", 2, 700),
+                       ("ow_chain12_qrm", 1, 1100), ("fl_qlambda", 2, 500), ("ow_allslip_wallpen_exp3_qrm", 2, 1300),
+                       ("long_cfg3_slip_qrm", 1, 20000), ("long_cfg2_office_slip_ql", 1, 20000), ("long_office_coffee_qlambda", 1, 20000)):
+        src = base if base in S else base.replace("long_cfg2_office_slip_ql", "cfg2_office_slip_ql")
+        S[base + "_f64"] = (S[src][0], n, t, "f64", S[src][4])
     return S
 
 

@@ -65,9 +65,11 @@ def _p(arr):
 
 
 class Oracle:
-    def __init__(self, compiled, n_instances, real="f32", track_visits=False):
+    def __init__(self, compiled, n_instances, real=None, track_visits=False):
         self.c = compiled
         self.cfg = compiled.config
+        if real is None:  # follow the scenario's table type unless the caller asks for a flavour explicitly
+            real = "f64" if getattr(compiled.config, "table_dtype", 0) == abi.TABLE_F64 else "f32"
         self.tables = compiled.tables_struct()
         self.N, self.A = int(n_instances), compiled.n_agents
         self.S = compiled.state_space

@@ -21,15 +21,15 @@ def _trace(tr, n, a):
     return O.unpack_trace(tr.cpu().numpy().view(np.uint32), n, a)
 
 
-F32_GOLDEN = [n for n in golden_names() if not n.endswith("_f64")]
-
-
-@pytest.mark.parametrize("name", F32_GOLDEN)
+@pytest.mark.parametrize("name", golden_names())
 def test_fused_kernel_matches_reference_golden(name, cuda_device):
+    """Every fixture recorded from the live reference, float32-cast tables AND the reference's native float64 tables
+    (`*_f64`: the device runs its float64 table mode, RLRM_TABLE_F64) — traces and final tables bit for bit."""
     import multiagent_rlrm_b200 as P
 
     meta, ref = load_golden(name)
     sc = P.Scenario.from_dict(meta["scenario"])
+    sc.table_dtype = meta["real"]
     c = P.compile_scenario(sc)
     n, t = meta["n_instances"], meta["n_iters"]
     eng = _engine(c, n)
@@ -39,6 +39,7 @@ def test_fused_kernel_matches_reference_golden(name, cuda_device):
     for k in ("action", "cell", "q", "term", "trunc"):
         assert np.array_equal(tr[k], ref[k].astype(np.int32)), f"{name}: {k}"
     q = eng.q.cpu().numpy().reshape(ref["q_final"].shape)
+    assert q.dtype == ref["q_final"].dtype == (np.float64 if meta["real"] == "f64" else np.float32)
     assert np.array_equal(q, ref["q_final"]), f"{name}: Q"
     if "e_final" in ref:
         assert np.array_equal(eng.e.cpu().numpy().reshape(ref["e_final"].shape), ref["e_final"]), f"{name}: traces"
@@ -91,15 +92,17 @@ def _scenarios_medium():
     return out
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
 @pytest.mark.parametrize("name", list(_scenarios_medium().keys()))
-def test_fused_kernel_matches_oracle(name, cuda_device):
+def test_fused_kernel_matches_oracle(name, dtype, cuda_device):
     import multiagent_rlrm_b200 as P
     import oracle as O
 
     sc, n, t = _scenarios_medium()[name]
+    sc.table_dtype = dtype
     c = P.compile_scenario(sc)
     eng = _engine(c, n)
-    o = O.Oracle(c, n, "f32")
+    o = O.Oracle(c, n, dtype)
     eng.reset(); o.reset()
     # several launches with odd lengths: state must carry across launches exactly
     t0 = 0
@@ -149,13 +152,15 @@ def test_generic_kernel_equals_specialised(name, cuda_device):
     assert int(o.stats["episodes"].sum()) > 0
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda", "fl_per_agent_rms_qrm",
                                   "fl_per_agent_rms_ql", "fl_random_starts_qrm"])
-def test_unfused_entry_points_equal_fused(name, cuda_device):
+def test_unfused_entry_points_equal_fused(name, dtype, cuda_device):
     """select -> step -> update -> reset through the separate C-ABI calls == the fused persistent kernel."""
     import multiagent_rlrm_b200 as P
 
     sc, n, _ = _scenarios_medium()[name]
+    sc.table_dtype = dtype
     n = min(n, 256)
     iters = 260 if name != "cfg4_qlambda" else 60
     c = P.compile_scenario(sc)
@@ -336,7 +341,8 @@ def test_shared_learner_generic_path_equals_fast_path(cuda_device):
 
 
 @pytest.mark.parametrize("name,n,iters", [("cfg4_office_chain12_qlambda", 48, 1300), ("fl_qlambda", 64, 1500),
-                                            ("long_office_coffee_qlambda", 8, 12000)])
+                                            ("long_office_coffee_qlambda", 8, 12000), ("cfg4_office_chain12_qlambda_f64", 24, 1300),
+                                            ("fl_qlambda_lr_none_f64", 32, 1500), ("long_office_coffee_qlambda_f64", 4, 12000)])
 def test_sparse_exact_qlambda_equals_dense_and_oracle(name, n, iters, cuda_device):
     """The sparse-exact trace lists (live entries only, q values cached in the list) reproduce the dense sweep of
     QLearningLambda.update bit for bit: vs the dense CUDA kernel and vs the oracle, across several launches, with
@@ -346,9 +352,10 @@ def test_sparse_exact_qlambda_equals_dense_and_oracle(name, n, iters, cuda_devic
 
     meta, _ref = load_golden(name)
     sc = P.Scenario.from_dict(meta["scenario"])
+    sc.table_dtype = meta["real"]
     c = P.compile_scenario(sc)
     sp, de = _engine(c, n, qlambda_sparse=True), _engine(c, n)
-    o = O.Oracle(c, n, "f32")
+    o = O.Oracle(c, n, meta["real"])
     sp.reset(); de.reset(); o.reset()
     t0 = 0
     for chunk in (3, 250, iters - 253):

@@ -29,6 +29,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "rlrm_stats_t": [f for f, _ in abi.Stats._fields_],
         "rlrm_state_t": [f for f, _ in abi.State._fields_],
         "rlrm_step_out_t": [f for f, _ in abi.StepOut._fields_],
+        "rlrm_eval_t": [f for f, _ in abi.Eval._fields_],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for st, fs in fields.items():
@@ -42,7 +43,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
     out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     for st, cls in (("rlrm_config_t", abi.Config), ("rlrm_tables_t", abi.Tables), ("rlrm_stats_t", abi.Stats),
-                    ("rlrm_state_t", abi.State), ("rlrm_step_out_t", abi.StepOut)):
+                    ("rlrm_state_t", abi.State), ("rlrm_step_out_t", abi.StepOut), ("rlrm_eval_t", abi.Eval)):
         assert int(out[st]) == C.sizeof(cls), st
         for f, _ in cls._fields_:
             assert int(out[f"{st}.{f}"]) == getattr(cls, f).offset, f"{st}.{f}"
@@ -281,27 +282,6 @@ def test_agent_select_and_update_plumbing():
         ag.action("jump")
     with pytest.raises(Exception, match="Encoder not set"):
         P.AgentRL("x", _Problem()).select_action({"pos_x": 0, "pos_y": 0})
-
-
-def test_agent_host_side_bookkeeping():
-    """agent_rl.py:237-335: add_rl_action, execute_action (preconditions / effects), message bookkeeping."""
-    from multiagent_rlrm_b200.actions import ActionRL
-    from multiagent_rlrm_b200.agent import Message
-
-    ag = P.AgentRL("a", _Problem())
-    ag.set_initial_position(1, 1)
-    hop = ActionRL("hop", [lambda agent: agent.get_position()[0] < 2], [lambda agent: agent.set_position(agent.get_position()[0] + 1, 1)])
-    ag.add_rl_action(hop)
-    assert ag.get_actions()[-1] is hop and ag.action("hop") is hop
-    assert ag.execute_action(hop) is True and ag.get_position() == (2, 1)
-    assert ag.execute_action(hop) is False and ag.get_position() == (2, 1)  # precondition no longer holds
-    with pytest.raises(ValueError):
-        ag.execute_action(None)
-    ag._receive_message(Message("b", [("door_open", True)]))
-    ag._receive_message("not a message")
-    assert ag.return_messages() == {("b", "door_open"): True}
-    ag.reset_messages()
-    assert ag.return_messages() == {} and ag.take_specific_action() is None
 
 
 # ---------------------------------------------------------------------------------------------- table compiler
