@@ -230,6 +230,12 @@ typedef struct rlrm_step_out {
   uint8_t* rm_term;     /* infos["rm_terminated"] */
   uint8_t* term;        /* terminations[agent] */
   uint8_t* trunc;       /* truncations[agent] */
+  /* optional, rlrm_step only: the hypothetical Reward-Machine transitions _get_qrm_experiences evaluates on the NEW position
+   * (rm_environment_wrapper.py:144-153), for every state u of get_all_states()[:-1] in that order (tables.qrm_states):
+   * [N*A][n_qrm_states] next RM state index (u itself when (u, event) has no transition) and its reward (0 then; unscaled
+   * by reward_modifier, as the reference). Rows of agents with fewer states (per_agent_rm) are padded. */
+  uint8_t* cf_q;
+  double* cf_r;
 } rlrm_step_out_t;
 
 typedef struct rlrm_handle rlrm_handle_t;
@@ -329,6 +335,42 @@ int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_ce
  *   bits 0-2 action, 3-5 executed, 6-15 cell after, 16-20 rm state after, 21 term, 22 trunc, 23 active-step. */
 int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
                uint32_t* trace, void* stream);
+
+/* ONE lockstep iteration of the driver loop, at the reference's call granularity but in a single launch: select_action for
+ * every agent -> rm_env.step -> update_policy for every agent -> rm_env.reset of the instances whose episode ended (the
+ * while-loop body of frozen_lake_main.py:345-376 / office_main.py:1709-1749). It is rlrm_train with n_iters = 1 that also
+ * reports what rm_env.step returned for this iteration:
+ *   record [N*A] uint32, the packed step record described at rlrm_train (action, executed action, new cell, new RM state,
+ *          terminated, truncated, active-step);
+ *   reward [N*A] double, rewards[agent] = Renv + RQ (rm_environment_wrapper.py:85), or NULL.
+ * Both may point to page-locked HOST memory (cudaHostAlloc / torch pin_memory: device-accessible under unified addressing):
+ * the kernel then writes the record straight into the caller's buffer and a host loop costs one launch + one stream
+ * synchronisation per iteration. Results are bit-identical to the same iteration of rlrm_train. */
+int rlrm_iterate(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t, int32_t learn, uint32_t* record, double* reward,
+                 void* stream);
+
+/* One entry of QLearning.update's counterfactual list (qlearning.py:82-106; the tuples built by
+ * rm_environment_wrapper.py:155-173) or one plain update (qlearning.py:108 / qlearning_lambda.py:33-84). 24 bytes. */
+typedef struct rlrm_experience {
+  uint32_t s;          /* encoded state  (enc = cell*nQ + q) */
+  uint32_t sn;         /* encoded next state */
+  uint8_t action;      /* 0..3 */
+  uint8_t terminated;  /* the `terminated` / `_done` flag */
+  uint8_t pad[6];
+  double reward;
+} rlrm_experience_t;
+/* update_q (qlearning.py:70-79) / QLearningLambda.update applied to `n` experiences on the table of slot `slot` (= i*A + a),
+ * in list order, in one launch. `experiences` is device-accessible memory (device or page-locked host). */
+int rlrm_update_list(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
+                     void* stream);
+
+/* Shared learner, inter-GPU merge: q[j] = (gathered[0][j] + gathered[1][j] + ... + gathered[world-1][j]) / world for j < n,
+ * added in rank order (float32, round to nearest), so every rank gets the same bits whatever collective produced
+ * `gathered` ([world][n] floats, device; e.g. the output of one NCCL all-gather of the replicas). */
+int rlrm_merge_replicas(rlrm_handle_t* h, const float* gathered, int32_t world, int64_t n, float* q, void* stream);
+
+/* cudaStreamSynchronize for hosts without a CUDA runtime binding of their own (ctypes / cgo / JNI callers). */
+int rlrm_stream_sync(rlrm_handle_t* h, void* stream);
 
 /* Same call with HOST buffers (the end-to-end path). host_slot / host_epsilon ([N*A], in/out, may be NULL): the
  * environment / RM state and epsilon to resume from are uploaded before the launch and the updated values are

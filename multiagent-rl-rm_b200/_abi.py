@@ -1,5 +1,5 @@
 """ctypes mirror of include/rlrm_b200.h (struct layouts and constants). Keep in lock-step with the header;
-tests/test_host_logic.py::test_struct_layouts_match_the_header checks sizes/offsets against a C program compiled from the header."""
+tests/test_host_logic.py::test_ctypes_structs_match_the_header checks sizes/offsets against a C program compiled from the header."""
 from __future__ import annotations
 
 import ctypes as C
@@ -151,6 +151,8 @@ class StepOut(C.Structure):
         ("rm_term", C.c_void_p),
         ("term", C.c_void_p),
         ("trunc", C.c_void_p),
+        ("cf_q", C.c_void_p),
+        ("cf_r", C.c_void_p),
     ]
 
 
@@ -192,4 +194,13 @@ EXPORTED_SYMBOLS = (
     "rlrm_evaluate",
     "rlrm_qlambda_materialize",
     "rlrm_launch_count",
+    "rlrm_iterate",
+    "rlrm_update_list",
+    "rlrm_merge_replicas",
+    "rlrm_stream_sync",
 )
+
+
+class Experience(C.Structure):
+    _fields_ = [("s", C.c_uint32), ("sn", C.c_uint32), ("action", C.c_uint8), ("terminated", C.c_uint8), ("pad", C.c_uint8 * 6),
+                ("reward", C.c_double)]

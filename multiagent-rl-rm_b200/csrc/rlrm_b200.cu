@@ -313,7 +313,7 @@ static DOut dout(const rlrm_step_out_t* o) {
   if (o) {
     d.prev_cell = o->prev_cell; d.cell = o->cell; d.prev_q = o->prev_q; d.q = o->q; d.event = o->event; d.executed = o->executed;
     d.renv = o->renv; d.rq = o->rq; d.reward = o->reward; d.env_term = o->env_term; d.rm_term = o->rm_term; d.term = o->term;
-    d.trunc = o->trunc;
+    d.trunc = o->trunc; d.cf_q = o->cf_q; d.cf_r = o->cf_r;
   }
   return d;
 }
@@ -512,17 +512,19 @@ extern "C" int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint1
 }
 
 template <int ENV>
-static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int n_iters, int learn, uint32_t* trace, cudaStream_t s) {
+static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int n_iters, int learn, uint32_t* trace, cudaStream_t s,
+                         double* reward_out = nullptr) {
   const KP& kp = h->kp;
+  const bool fast_ok = reward_out == nullptr;  // the per-step reward output exists in the generic kernels only
   if (kp.algo == RLRM_ALGO_QLAMBDA && !st->e) {
-    RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace));
+    RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
   } else if (kp.algo == RLRM_ALGO_QLAMBDA) {
-    RLRM_BY_T(h, train_qlambda_kernel<ENV, T><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace));
+    RLRM_BY_T(h, train_qlambda_kernel<ENV, T><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
   } else {
     const long long threads = st->n_instances * kp.G;
     const unsigned grid = blocks_for(threads, TRAIN_BLOCK);
-#define RLRM_TRAIN(ALGO, PA) RLRM_BY_T(h, train_kernel<ENV, ALGO, PA, T><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace))
-    if (kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits) {
+#define RLRM_TRAIN(ALGO, PA) RLRM_BY_T(h, train_kernel<ENV, ALGO, PA, T><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out))
+    if (fast_ok && kp.algo == RLRM_ALGO_QRM && h->qrm4_fast && !st->visits) {
       const DState d = dstate(st);
 #define RLRM_QRM4(ST, LE, TR)                                                                                          \
   do {                                                                                                                \
@@ -544,7 +546,7 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
       }
 #undef RLRM_QRM4
     }
-    else if (kp.algo == RLRM_ALGO_QRM && h->qrmn_fast && !st->visits) {
+    else if (fast_ok && kp.algo == RLRM_ALGO_QRM && h->qrmn_fast && !st->visits) {
       const DState d = dstate(st);
 #define RLRM_QRMN(ST, LE, TR)                                                                                             \
   do {                                                                                                                   \
@@ -564,7 +566,7 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
       }
 #undef RLRM_QRMN
     }
-    else if (kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
+    else if (fast_ok && kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
       const DState d = dstate(st);
 #define RLRM_QLF(ST, LE, TR) train_ql_fast_kernel<ENV, ST, LE, TR><<<grid, TRAIN_BLOCK, h->smem_bytes, s>>>(kp, d, t0, n_iters, trace)
       const int key = (kp.stochastic ? 4 : 0) | (learn ? 2 : 0) | (trace ? 1 : 0);
@@ -681,3 +683,51 @@ extern "C" int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_
   return RLRM_OK;
 }
 
+
+extern "C" int rlrm_iterate(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t, int32_t learn, uint32_t* record, double* reward,
+                            void* stream) {
+  int rc = check_state(h, st, true);
+  if (rc) return rc;
+  if (h->kp.shared_q) {
+    if (reward) return fail(RLRM_ERR_UNSUPPORTED, "rlrm_iterate: the per-step reward output is not available with a shared table");
+    return rlrm_train(h, st, t, 1, learn, record, stream);
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE) launch_train<RLRM_ENV_FROZEN_LAKE>(h, st, t, 1, learn, record, s, reward);
+  else launch_train<RLRM_ENV_OFFICE_WORLD>(h, st, t, 1, learn, record, s, reward);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_update_list(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
+                                void* stream) {
+  int rc = check_state(h, st, true);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !experiences)) return fail(RLRM_ERR_ARG, "rlrm_update_list: bad experience list");
+  if (slot < 0 || slot >= st->n_instances * h->kp.A) return fail(RLRM_ERR_ARG, "rlrm_update_list: slot out of range");
+  if (h->kp.shared_q) return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update_list on a shared table (proposals need the synchronous iteration of rlrm_train)");
+  if (h->kp.algo == RLRM_ALGO_QLAMBDA && !st->e) return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update_list on Q(lambda) needs dense traces (state.e)");
+  if (n == 0) return RLRM_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  RLRM_BY_T(h, update_list_kernel<T><<<1, h->kp.algo == RLRM_ALGO_QLAMBDA ? 256 : 32, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), slot, n, experiences));
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_merge_replicas(rlrm_handle_t* h, const float* gathered, int32_t world, int64_t n, float* q, void* stream) {
+  if (!h || !gathered || !q) return fail(RLRM_ERR_ARG, "null argument");
+  if (world < 1 || n <= 0) return fail(RLRM_ERR_ARG, "rlrm_merge_replicas: world / n out of range");
+  if (h->f64) return fail(RLRM_ERR_UNSUPPORTED, "the shared learner is specified on float32 tables");
+  CUDA_TRY(cudaSetDevice(h->device));
+  merge_replicas_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(gathered, world, n, q);
+  LAUNCH_CHECK(h);
+  return RLRM_OK;
+}
+
+extern "C" int rlrm_stream_sync(rlrm_handle_t* h, void* stream) {
+  if (!h) return fail(RLRM_ERR_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return RLRM_OK;
+}

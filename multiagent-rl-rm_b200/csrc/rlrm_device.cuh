@@ -84,6 +84,8 @@ struct DOut {  // rlrm_step_out_t by value
   unsigned char *prev_q, *q, *event, *executed;
   double *renv, *rq, *reward;
   unsigned char *env_term, *rm_term, *term, *trunc;
+  unsigned char* cf_q;
+  double* cf_r;
 };
 
 extern __shared__ __align__(16) unsigned char smem_raw[];

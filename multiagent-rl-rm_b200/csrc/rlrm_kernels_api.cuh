@@ -94,6 +94,16 @@ __global__ void __launch_bounds__(256) step_kernel(KP p_in, DState st, const uns
   agent_step<ENV, -1, true>(p, tb, s, min((int)actions[k], RLRM_ACTION_WAIT), w3, with_rm != 0, r);
   st.slot[k] = pack_slot(s);
   store_rec(out, k, r);
+  if (out.cf_q || out.cf_r) {  // counterfactual RM lookups on the new position (rm_environment_wrapper.py:144-153)
+    const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+    const int stride = p_in.n_qrm;  // row stride = the maximum over agents
+    for (int j = 0; j < p.n_qrm; j++) {
+      const unsigned u = tb.qrm_states[j];
+      const unsigned d = tb.delta[u * (p.nEv + 1) + col];
+      if (out.cf_q) out.cf_q[k * stride + j] = (unsigned char)(d == RLRM_NO_TRANSITION ? u : d);
+      if (out.cf_r) out.cf_r[k * stride + j] = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
+    }
+  }
 }
 
 // RMEnvironmentWrapper.get_mdp (rm_environment_wrapper.py:185-283): every (encoded state, nominal action, sub-action) of one
@@ -308,3 +318,50 @@ __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, co
   qlambda_sweep<T>(p, tab<T>(st.q) + base, tab<T>(st.e) + base, s_idx, action, o.reward[k], sn_idx, term_arg[k] != 0, threadIdx.x, blockDim.x, vis);
 }
 
+
+// QLearning.update's inner update_q (qlearning.py:70-79) / QLearningLambda.update (qlearning_lambda.py:33-84) applied to a LIST
+// of experiences on one (instance, agent) table, in list order, in one launch: the QRM counterfactual loop of
+// QLearning.update (qlearning.py:82-106) hands its experiences over as one list instead of one launch per experience.
+// Q-learning / QRM: thread 0 applies them one after the other (each update may read what the previous one wrote);
+// Q(lambda): the whole block sweeps the table once per experience.
+template <typename T>
+__global__ void __launch_bounds__(256) update_list_kernel(KP p, DState st, long long slot, int n, const rlrm_experience_t* ex) {
+  const long long i = slot / p.A;
+  const int a = (int)(slot - i * p.A);
+  const size_t base = table_base(p, i, a);
+  const unsigned rows = (unsigned)p.ncell * (unsigned)(p.per_agent ? p.a_nQ[a] : p.nQ);
+  T* Q = tab<T>(st.q) + base;
+  unsigned* V = st.visits ? st.visits + base : nullptr;
+  if (p.algo == RLRM_ALGO_QLAMBDA) {
+    KP pa = p;
+    pa.S4 = (long long)rows * 4;
+    T* E = tab<T>(st.e) + base;
+    for (int j = 0; j < n; j++) {
+      const unsigned s = min(ex[j].s, rows - 1u), sn = min(ex[j].sn, rows - 1u);  // caller memory: clamp what indexes a table
+      const int act = min((int)ex[j].action, RLRM_N_ACTIONS - 1);
+      unsigned vis = 0;
+      if (V) {  // every thread reads the old count, then one writes the new one
+        vis = V[(size_t)s * 4 + act] + 1;
+        __syncthreads();
+        if (threadIdx.x == 0) V[(size_t)s * 4 + act] = vis;
+      }
+      qlambda_sweep<T>(pa, Q, E, s, act, ex[j].reward, sn, ex[j].terminated != 0, threadIdx.x, blockDim.x, vis);
+      __syncthreads();
+    }
+  } else if (threadIdx.x == 0) {
+    const Acc none = {nullptr, nullptr, nullptr, false, nullptr};
+    for (int j = 0; j < n; j++)
+      update_q<T>(p, Q, V, min(ex[j].s, rows - 1u), min((int)ex[j].action, RLRM_N_ACTIONS - 1), ex[j].reward, min(ex[j].sn, rows - 1u),
+                  ex[j].terminated != 0, none);
+  }
+}
+
+// Shared learner, inter-GPU merge (include/rlrm_b200.h "Shared learner"): q <- (g_0 + g_1 + ... + g_{world-1}) / world with the
+// replicas added in RANK ORDER, so every rank computes the same bits whatever the collective that gathered them did.
+__global__ void __launch_bounds__(256) merge_replicas_kernel(const float* gathered, int world, long long n, float* q) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float acc = gathered[j];
+  for (int r = 1; r < world; r++) acc = __fadd_rn(acc, gathered[(size_t)r * (size_t)n + j]);
+  q[j] = __fdiv_rn(acc, (float)world);
+}

@@ -5,7 +5,7 @@
 
 template <int ENV, typename T>
 __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
-                                                           unsigned* trace) {
+                                                           unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
   Tab tb = stage_tables(p);
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, uns
       trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                            ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
                                                            ((unsigned)r.stepped << 23);
+    if (reward_out && lane == 0) reward_out[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = r.reward;
     if (lane == 0) {
       sh_term[a] = r.term;
       sh_trunc[a] = r.trunc;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigne
 #define QLS_BLOCK 128
 template <int ENV, typename T>
 __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
-                                                                        unsigned* trace) {
+                                                                        unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
   typedef typename R::pair_t pair_t;
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
       trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                            ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
                                                            ((unsigned)r.stepped << 23);
+    if (reward_out && valid && gl == 0) reward_out[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = r.reward;
     // episode over <=> every agent of the instance terminated, or every agent truncated (idle lanes vote yes)
     const bool over = __all_sync(FULL, !valid || r.term) || __all_sync(FULL, !valid || r.trunc);
     if (valid && over) {

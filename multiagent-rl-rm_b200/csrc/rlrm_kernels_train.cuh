@@ -13,7 +13,7 @@
 // T = table arithmetic type (float: float32 tables; double: the reference's native float64 tables, see RT<T>)
 template <int ENV, int ALGO, bool PA, typename T>
 __global__ void __launch_bounds__(TRAIN_BLOCK, sizeof(T) == 4 ? 7 : 5) train_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
-                                                           unsigned* trace) {
+                                                           unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
   KP p = p_in;
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, sizeof(T) == 4 ? 7 : 5) train_ker
         trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
                                                              ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
                                                              ((unsigned)r.stepped << 23);
+      if (reward_out) reward_out[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = r.reward;  // rewards[agent] of rm_env.step
     }
     // episode over when all agents terminated, or all truncated (frozen_lake_main.py:345,375 ; office_main.py:1748)
     const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);

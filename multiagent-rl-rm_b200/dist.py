@@ -30,11 +30,32 @@ def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     return offset, count
 
 
-def merge_replicas(q: torch.Tensor, world: int, group=None) -> None:
+_gather_buffers = {}
+
+
+def merge_replicas(q: torch.Tensor, world: int, group=None, engine=None) -> None:
     """q <- (q_0 + q_1 + ... + q_{world-1}) / world, summed in RANK ORDER on every rank. A plain all_reduce(SUM) leaves
     the association order to NCCL's ring/tree, which for more than two ranks changes the last bit; greedy tie-breaks then
     diverge. The tables are tiny (25.6 KB for config 5), so gathering them costs the same latency as reducing them and
-    makes the merged table independent of the collective algorithm."""
+    makes the merged table independent of the collective algorithm.
+
+    On the GPU (``engine`` given, NCCL): ONE all-gather into a persistent [world, n] buffer + ONE hand-written rank-ordered
+    reduce kernel (rlrm_merge_replicas) — two launches per merge. Without an engine (CPU / gloo tests of the host logic) the
+    same sum is formed with torch ops."""
+    if engine is not None and q.is_cuda:
+        import ctypes as C
+
+        from ._lib import check
+
+        n = q.numel()
+        key = (q.device, world, n)
+        buf = _gather_buffers.get(key)
+        if buf is None:
+            buf = _gather_buffers[key] = torch.empty((world, n), dtype=torch.float32, device=q.device)
+        dist.all_gather_into_tensor(buf, q.view(-1), group=group)
+        check(engine.L.rlrm_merge_replicas(engine.h, buf.data_ptr(), world, n, q.data_ptr(),
+                                           C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)))
+        return
     parts = [torch.empty_like(q) for _ in range(world)]
     dist.all_gather(parts, q.contiguous(), group=group)
     acc = parts[0].clone()
@@ -73,7 +94,8 @@ class ShardedTrainer:
     def _merge_tables(self):
         """Parameter averaging of the shared-table replicas (the only collective on the learning path)."""
         if self.world > 1:
-            merge_replicas(self.engine.q, self.world, self.group)
+            eng = self.engine if hasattr(self.engine, "L") and getattr(self.engine.q, "is_cuda", False) else None
+            merge_replicas(self.engine.q, self.world, self.group, engine=eng)
         self.syncs += 1
 
     def train(self, n_iters: int, learn: bool = True):

@@ -33,8 +33,12 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class Engine:
     def __init__(self, compiled: Compiled, n_instances: int, device="cuda:0", track_visits: bool = False,
-                 with_stats: bool = True, qlambda_sparse: bool = False):
-        """qlambda_sparse: Q(lambda) only — keep the traces as per-agent lists of live entries (sparse-exact, see
+                 with_stats: bool = True, qlambda_sparse: bool = False, host_control: bool = False):
+        """host_control: keep the small per-slot control state (slot words, epsilon, running return) in page-locked HOST
+        memory instead of device memory. Page-locked memory is device-accessible under unified addressing, so the kernels
+        read / write it in place and a host driver (the one-instance reference-shaped classes in envs.py) touches it through
+        numpy views without any copy. Meant for small N; large batches keep it in HBM.
+        qlambda_sparse: Q(lambda) only — keep the traces as per-agent lists of live entries (sparse-exact, see
         include/rlrm_b200.h) instead of the dense e table. Same results bit for bit, far less memory traffic; the fused
         `train` path only (the call-by-call `update` needs the dense table). Call `sync_tables()` before reading `q`."""
         self.L = load()
@@ -57,8 +61,11 @@ class Engine:
             tab_shape = (1 if self.cfg.shared_q else self.N, sum(self.agent_rows), 4)
         d = self.device
         self.table_dtype = torch.float64 if self.cfg.table_dtype == abi.TABLE_F64 else torch.float32
-        self.slot = torch.zeros(n_slots, dtype=torch.int64, device=d)
-        self.epsilon = torch.full((n_slots,), float(self.cfg.epsilon_start), dtype=torch.float64, device=d)
+        self.host_control = bool(host_control)
+        cd = "cpu" if self.host_control else d  # where the control state lives
+        pin = (lambda t: t.pin_memory()) if self.host_control else (lambda t: t)
+        self.slot = pin(torch.zeros(n_slots, dtype=torch.int64, device=cd))
+        self.epsilon = pin(torch.full((n_slots,), float(self.cfg.epsilon_start), dtype=torch.float64, device=cd))
         self.q = torch.full(tab_shape, float(compiled.scenario.q_init), dtype=self.table_dtype, device=d)
         self.sparse = bool(qlambda_sparse) and self.cfg.algo == abi.ALGO_QLAMBDA
         self.e = torch.zeros(tab_shape, dtype=self.table_dtype, device=d) if (self.cfg.algo == abi.ALGO_QLAMBDA and not self.sparse) else None
@@ -75,7 +82,7 @@ class Engine:
             self.tr_work = torch.zeros(n_slots, dtype=torch.int64, device=d)
         need_visits = track_visits or self.cfg.learning_rate < 0
         self.visits = torch.zeros(tab_shape, dtype=torch.int32, device=d) if need_visits else None
-        self.ep_return = torch.zeros(n_slots, dtype=torch.float64, device=d)
+        self.ep_return = pin(torch.zeros(n_slots, dtype=torch.float64, device=cd))
         self.stats = torch.zeros((n_slots, 32), dtype=torch.uint8, device=d) if with_stats else None
         shared = bool(self.cfg.shared_q)
         self.acc_sum = torch.zeros(tab_shape, dtype=torch.int64, device=d) if shared else None
@@ -86,6 +93,8 @@ class Engine:
                                _ptr(self.tr_pos), _ptr(self.tr_idx), _ptr(self.tr_eq), _ptr(self.tr_len),
                                _ptr(self.tr_work), self.tr_cap, 0)
         self.t = 0  # lockstep iteration counter (Philox counter word)
+        self._it_record = self._it_reward = None
+        self._hio = None
 
     def __del__(self):
         try:
@@ -101,6 +110,10 @@ class Engine:
 
     def set_learner(self, learning_rate, gamma, lambd=0.0):
         check(self.L.rlrm_set_learner(self.h, -1.0 if learning_rate is None else float(learning_rate), float(gamma), float(lambd)))
+
+    def sync(self):
+        """Wait for the work queued on the current stream (rlrm_stream_sync)."""
+        check(self.L.rlrm_stream_sync(self.h, self._stream()))
 
     @property
     def launches(self) -> int:
@@ -197,6 +210,71 @@ class Engine:
         check(self.L.rlrm_train(self.h, C.byref(self.state), t0, n_iters, int(learn), _ptr(tr), self._stream()))
         self.t = t0 + n_iters
         return tr
+
+    def iterate(self, learn: bool = True, record: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
+                want_reward: bool = True, sync: bool = True):
+        """ONE lockstep iteration of the driver loop in one launch (rlrm_iterate): select -> rm_env.step -> update -> reset of
+        the finished instances, reporting what rm_env.step returned: `record` int32 [N*A] (packed: bits 0-2 action, 3-5
+        executed action, 6-15 new cell, 16-20 new RM state, 21 terminated, 22 truncated, 23 active step) and `reward`
+        float64 [N*A]. By default both are page-locked HOST tensors owned by the engine that the kernel writes in place:
+        after the stream synchronisation (`sync=True`) the host reads them without a copy. Bit-identical to train(1)."""
+        n = self.N * self.A
+        if record is None:
+            if self._it_record is None:
+                self._it_record = torch.zeros(n, dtype=torch.int32).pin_memory()
+                self._it_reward = torch.zeros(n, dtype=torch.float64).pin_memory()
+            record = self._it_record
+            if want_reward and reward is None:
+                reward = self._it_reward
+        check(self.L.rlrm_iterate(self.h, C.byref(self.state), self.t, int(learn), _ptr(record), _ptr(reward), self._stream()))
+        self.t += 1
+        if sync:
+            self.sync()
+        return record, reward
+
+    @staticmethod
+    def unpack_record(record: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Fields of the packed step record of :meth:`iterate` / the trace of :meth:`train`."""
+        r = record
+        return {"action": r & 7, "executed": (r >> 3) & 7, "cell": (r >> 6) & 0x3FF, "q": (r >> 16) & 0x1F,
+                "terminated": ((r >> 21) & 1).bool(), "truncated": ((r >> 22) & 1).bool(), "active": ((r >> 23) & 1).bool()}
+
+    # -- one-instance host bridge (envs.py): everything a step needs lives in ONE page-locked block --------------------
+    def _host_io(self):
+        if self._hio is None:
+            n, nq = self.N * self.A, max(1, int(self.cfg.n_qrm_states))
+            sizes = [("actions", "uint8", n), ("draws", "uint32", n * 4)] + [(k, v, n) for k, v in abi.STEP_OUT_FIELDS.items()] + \
+                    [("cf_q", "uint8", n * nq), ("cf_r", "float64", n * nq)]
+            sizes.sort(key=lambda kv: -np.dtype(kv[1]).itemsize)  # widest first keeps every field aligned
+            total = sum(-(-np.dtype(dt).itemsize * cnt // 16) * 16 for _k, dt, cnt in sizes)
+            buf = torch.zeros(total, dtype=torch.uint8).pin_memory()
+            host = buf.numpy()
+            views, ptrs, off = {}, {}, 0
+            for k, dt, cnt in sizes:
+                nbytes = np.dtype(dt).itemsize * cnt
+                views[k] = host[off:off + nbytes].view(dt)
+                ptrs[k] = buf.data_ptr() + off
+                off += -(-nbytes // 16) * 16
+            so = abi.StepOut(*[ptrs[k] for k in abi.STEP_OUT_FIELDS], None, None)
+            so_cf = abi.StepOut(*[ptrs[k] for k in abi.STEP_OUT_FIELDS], ptrs["cf_q"], ptrs["cf_r"])
+            self._hio = {"buf": buf, "v": views, "p": ptrs, "so": so, "so_cf": so_cf, "n_qrm": nq}
+        return self._hio
+
+    def step_host(self, actions, draws=None, with_rm: bool = True, counterfactuals: bool = False):
+        """rlrm_step driven from the host with no copies (needs host_control=True): `actions` (N*A ints) and `draws`
+        (N*A*4 32-bit words, or None) are written into the page-locked block, the kernel reads them and writes the step
+        record — plus, when `counterfactuals`, the QRM lookups on the new position (cf_q / cf_r, [N*A][n_qrm]) — in place;
+        one launch, one synchronisation. Returns numpy views of the record, valid until the next call."""
+        if not self.host_control:
+            raise RuntimeError("step_host needs an Engine built with host_control=True")
+        io = self._host_io()
+        io["v"]["actions"][:] = actions
+        if draws is not None:
+            io["v"]["draws"][:] = draws
+        check(self.L.rlrm_step(self.h, C.byref(self.state), io["p"]["actions"], io["p"]["draws"] if draws is not None else None, 0,
+                               int(with_rm), C.byref(io["so_cf"] if counterfactuals else io["so"]), self._stream()))
+        self.sync()
+        return io["v"]
 
     def train_host(self, n_iters: int, host_stats: torch.Tensor, host_slot: Optional[torch.Tensor] = None,
                    host_epsilon: Optional[torch.Tensor] = None, learn: bool = True, t0: Optional[int] = None):

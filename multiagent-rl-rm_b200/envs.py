@@ -37,6 +37,7 @@ class BaseEnvironment:
         self.device = device
         self._engine = None
         self._engine_key = None
+        self._engine_quick = None
         self._first = True
         self._last_rec = None
 
@@ -72,16 +73,24 @@ class BaseEnvironment:
     def _get_engine(self, reward_modifier=1):
         from .engine import Engine
 
+        # cheap fingerprint first: the behaviour flags are plain attributes the caller may change between calls (as the
+        # reference's drivers do), so they are looked at on every call; the reward machines are identified by object and size
+        fields = self._scenario_fields()
+        agents = self.agents
+        starts = tuple(tuple(getattr(a, "initial_position", None) or a.position) for a in agents)
+        quick = (tuple(fields.values()), starts, reward_modifier,
+                 tuple((id(getattr(a, "reward_machine", None)), len(getattr(getattr(a, "reward_machine", None), "transitions", ())))
+                       for a in agents))
+        if self._engine is not None and quick == self._engine_quick:
+            return self._engine
         rm = self._shared_rm()
         grid = self._grid()
-        fields = self._scenario_fields()
-        starts = [tuple(getattr(a, "initial_position", None) or a.position) for a in self.agents]
         rm_list = rm if isinstance(rm, list) else ([] if rm is None else [rm])
         rm_key = tuple((tuple(m.transitions.items()), tuple(sorted(m.detector_positions())), m.initial_state) for m in rm_list) or None
-        key = (tuple(sorted(fields.items())), tuple(starts), rm_key, reward_modifier,
+        key = (tuple(sorted(fields.items())), starts, rm_key, reward_modifier,
                grid.width, grid.height, tuple(grid.hazards), tuple(grid.walls))
         if self._engine is None or key != self._engine_key:
-            sc = Scenario(env=grid.env, starts=starts, algo="ql", learning_rate=1.0, reward_modifier=reward_modifier, **fields)
+            sc = Scenario(env=grid.env, starts=list(starts), algo="ql", learning_rate=1.0, reward_modifier=reward_modifier, **fields)
             if rm is None:  # an environment without reward machines: one-state machine, no transitions, no final state
                 rm_c = RewardMachine({}, PositionEventDetector(set()))
                 rm_c.current_state = rm_c.initial_state = "__none__"
@@ -90,70 +99,71 @@ class BaseEnvironment:
                 rm_c.get_all_states = lambda: ["__none__"]
             else:
                 rm_c = rm
-            self._engine = Engine(compile_scenario(sc, grid=grid, rm=rm_c), 1, device=self.device, with_stats=False)
+            # one instance: the control state lives in page-locked host memory the kernels access in place (no copies)
+            self._engine = Engine(compile_scenario(sc, grid=grid, rm=rm_c), 1, device=self.device, with_stats=False, host_control=True)
             self._engine_key = key
+            self._slot_np = self._engine.slot.numpy()
+        self._engine_quick = quick
         return self._engine
 
-    def _pack_slots(self):
-        words = []
-        for a in self.agents:
+    def _pack_slots(self, out):
+        W = self.grid_width
+        for i, a in enumerate(self.agents):
             x, y = a.get_position()
             rm = getattr(a, "reward_machine", None)
             q = rm.get_state_index(rm.get_current_state()) if rm is not None else 0
             flags = (abi.FLAG_ACTIVE if self.active_agents.get(a.name, True) else 0) | \
                     (abi.FLAG_FAIL if self.agent_fail.get(a.name, False) else 0) | (abi.FLAG_FIRST if self._first else 0)
-            words.append(((y * self.grid_width + x) << abi.SLOT_CELL_SHIFT) | (int(self.agent_steps.get(a.name, 0)) << abi.SLOT_STEPS_SHIFT)
-                         | (int(self.timestep) << abi.SLOT_TIME_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT) | (flags << abi.SLOT_FLAGS_SHIFT))
-        return torch.tensor(words, dtype=torch.int64)
+            out[i] = ((y * W + x) << abi.SLOT_CELL_SHIFT) | (int(self.agent_steps.get(a.name, 0)) << abi.SLOT_STEPS_SHIFT) \
+                | (int(self.timestep) << abi.SLOT_TIME_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT) | (flags << abi.SLOT_FLAGS_SHIFT)
 
     def _slip_words(self):
-        """One 32-bit slip word per agent from env.rng (`rng.words(i)` hook = trace injection)."""
+        """One 32-bit slip word per agent from env.rng (`rng.words(i)` hook = trace injection): uint32 [A*4]."""
         n = len(self.agents)
-        w = np.zeros((n, 4), dtype=np.int64)
+        w = np.zeros((n, 4), dtype=np.uint32)
         rng = self.rng if self.rng is not None else np.random.default_rng()
         if hasattr(rng, "words"):
             for i in range(n):
-                w[i] = [int(v) for v in rng.words(i)]
+                w[i] = [int(v) & 0xFFFFFFFF for v in rng.words(i)]
         else:
-            w[:, 3] = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.int64)
-        return torch.from_numpy(w.astype(np.uint32).view(np.int32).reshape(-1))
+            w[:, 3] = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+        return w.reshape(-1)
 
-    def _device_step(self, actions, with_rm: bool, reward_modifier=1):
-        """rlrm_step on the packed host state; returns the record as numpy arrays and syncs the host objects."""
+    def _device_step(self, actions, with_rm: bool, reward_modifier=1, counterfactuals=False):
+        """rlrm_step on the packed host state: ONE launch that reads the slot words / actions / slip words from page-locked
+        host memory and writes the new slot words and the step record back in place, one stream synchronisation; then the
+        host objects are brought up to date. Returns the record as numpy views (valid until the next step)."""
         eng = self._get_engine(reward_modifier)
         acts = []
+        stochastic_fl = getattr(self, "frozen_lake_stochastic", False)
         for a in self.agents:
             act = actions[a.name]
             name = act if isinstance(act, str) else act.name
             if name not in _A2I:
                 raise ValueError(f"Invalid action: {name}")
-            if name == "wait" and getattr(self, "frozen_lake_stochastic", False):
+            if name == "wait" and stochastic_fl:
                 raise KeyError(name)  # the slippery FrozenLake action map has no "wait" entry (ma_frozen_lake.py:283-296)
             acts.append(_A2I[name])
-        eng.slot.copy_(self._pack_slots())
-        rec = eng.step(torch.tensor(acts, dtype=torch.uint8), t=0, draws=self._slip_words().to(eng.device), with_rm=with_rm)
-        # the record fields are views of ONE device allocation (Engine.new_record): bring it to the host with one copy
-        buf = eng._record_buffer
-        host, origin = buf.cpu(), buf.data_ptr()
-        out = {}
-        for k, v in rec.items():
-            off = v.data_ptr() - origin
-            out[k] = host[off:off + v.numel() * v.element_size()].view(v.dtype).numpy()
-        out["prev_cell"] = out["prev_cell"].view(np.uint16)
-        out["cell"] = out["cell"].view(np.uint16)
-        s = eng.slots_numpy()
+        slot = self._slot_np
+        self._pack_slots(slot)
+        draws = self._slip_words() if eng.cfg.stochastic else None
+        out = eng.step_host(acts, draws, with_rm=with_rm, counterfactuals=counterfactuals)
         W = self.grid_width
+        timestep = self.timestep + 1
         for i, a in enumerate(self.agents):
-            cell = int(s["cell"][0, i])
+            w = int(slot[i])
+            cell = w & 0xFFFF
             if (cell % W, cell // W) != tuple(a.get_position()):
                 a.set_position(cell % W, cell // W)
-            fl = int(s["flags"][0, i])
+            fl = (w >> abi.SLOT_FLAGS_SHIFT) & 0xFF
             self.active_agents[a.name] = bool(fl & abi.FLAG_ACTIVE)
             self.agent_fail[a.name] = bool(fl & abi.FLAG_FAIL)
-            self.agent_steps[a.name] = int(s["agent_steps"][0, i])
+            self.agent_steps[a.name] = (w >> abi.SLOT_STEPS_SHIFT) & 0xFFFF
             if with_rm and getattr(a, "reward_machine", None) is not None:
-                a.reward_machine.current_state = a.reward_machine.get_state_from_index(int(s["q"][0, i]))
-        self.timestep = int(s["timestep"][0, 0]) if self.agents else self.timestep + 1
+                a.reward_machine.current_state = a.reward_machine.get_state_from_index((w >> abi.SLOT_RMSTATE_SHIFT) & 0xFF)
+            if i == 0:
+                timestep = (w >> abi.SLOT_TIME_SHIFT) & 0xFFFF
+        self.timestep = timestep
         self._first = False
         self._last_rec = out
         return out
@@ -248,8 +258,8 @@ class MultiAgentFrozenLake(BaseEnvironment):
     def step(self, actions):
         return self._step(actions, with_rm=False)[:5]
 
-    def _step(self, actions, with_rm, reward_modifier=1):
-        rec = self._device_step(actions, with_rm, reward_modifier)
+    def _step(self, actions, with_rm, reward_modifier=1, counterfactuals=False):
+        rec = self._device_step(actions, with_rm, reward_modifier, counterfactuals)
         self.rewards = {a.name: 0 for a in self.agents}
         infos, terms, truncs = {}, {}, {}
         for i, a in enumerate(self.agents):
@@ -361,9 +371,9 @@ class MultiAgentOfficeWorld(BaseEnvironment):
     def step(self, actions):
         return self._step(actions, with_rm=False)[:5]
 
-    def _step(self, actions, with_rm, reward_modifier=1):
+    def _step(self, actions, with_rm, reward_modifier=1, counterfactuals=False):
         was_active = dict(self.active_agents)
-        rec = self._device_step(actions, with_rm, reward_modifier)
+        rec = self._device_step(actions, with_rm, reward_modifier, counterfactuals)
         self.rewards = {a.name: 0 for a in self.agents}
         infos, terms, truncs = {}, {}, {}
         for i, a in enumerate(self.agents):

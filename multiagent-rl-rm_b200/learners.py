@@ -74,7 +74,7 @@ def _factor_state_space(S):
 class _TableHandle:
     """One-slot C-ABI handle over a learner's own tables: grid = (cells x 1), nQ = nq, enc = cell*nq + q."""
 
-    def __init__(self, S, algo, learning_rate, gamma, lambd, device, n_actions=4):
+    def __init__(self, S, algo, learning_rate, gamma, lambd, device, n_actions=4, table_dtype="f32"):
         if not torch.cuda.is_available():
             raise RuntimeError("multiagent-rl-rm_b200 learners need a CUDA device (no CPU fallback)")
         self.L = load()
@@ -93,6 +93,7 @@ class _TableHandle:
         cfg.gamma, cfg.lambd = float(gamma), float(lambd)
         cfg.epsilon_start = cfg.epsilon_end = cfg.epsilon_decay = 1.0
         cfg.n_actions = n_actions
+        cfg.table_dtype = abi.TABLE_F64 if table_dtype == "f64" else abi.TABLE_F32
         self.cfg = cfg
         n = self.cells
         self._arrs = dict(
@@ -120,7 +121,14 @@ class _TableHandle:
 
 
 class BaseLearningAlgorithm:
-    def __init__(self, state_space_size, action_space_size, gamma=0.99, seed=2020, max_steps=400, device="cuda:0"):
+    def __init__(self, state_space_size, action_space_size, gamma=0.99, seed=2020, max_steps=400, device="cuda:0",
+                 table_dtype="f32"):
+        """table_dtype (this package's extension): "f32" = float32 tables (what the batched kernels are tuned for; equals the
+        reference with its tables cast to float32, bit for bit) or "f64" = the reference's own float64 tables
+        (learning_algorithm.py / qlearning.py:26-29), bit-identical to the unmodified reference."""
+        if table_dtype not in ("f32", "f64"):
+            raise ValueError("table_dtype must be 'f32' or 'f64'")
+        self.table_dtype = table_dtype
         if not (1 <= action_space_size <= 4):
             raise ValueError("the CUDA path implements the reference's grid worlds: at most 4 actions (up, down, left, right)")
         self.state_space_size = state_space_size
@@ -152,21 +160,32 @@ class BaseLearningAlgorithm:
 
 class _TabularBase(BaseLearningAlgorithm):
     _ALGO = abi.ALGO_QL
+    # staging block layout (bytes): 0 slot u64 | 8 epsilon f64 | 16 draws 4 x u32 | 59 selected action (output) u8 |
+    # 1024.. a ring of _RING blocks of _BLOCK rlrm_experience_t (24 bytes each) for rlrm_update_list
+    _RING, _BLOCK, _EXP_OFF = 8, 16, 1024
+    _STAGE_BYTES = 1024 + 8 * 16 * 24
 
     def _setup(self, q_init, lambd=0.0):
         S = self.state_space_size
-        self._th = _TableHandle(S, self._ALGO, self.learning_rate, self.gamma, lambd, self.device, self.action_space_size)
+        self._th = _TableHandle(S, self._ALGO, self.learning_rate, self.gamma, lambd, self.device, self.action_space_size, self.table_dtype)
         d, Sp = self.device, self._th.S_pad
-        self._q = torch.full((Sp, 4), float(q_init), dtype=torch.float32, device=d)
+        dt = torch.float64 if self.table_dtype == "f64" else torch.float32
+        self._q = torch.full((Sp, 4), float(q_init), dtype=dt, device=d)
         if self.action_space_size < 4:  # tables are 4 wide on the device; unused actions can never be a maximum
             self._q[:, self.action_space_size:] = float("-inf")
-        self._e = torch.zeros((Sp, 4), dtype=torch.float32, device=d) if self._ALGO == abi.ALGO_QLAMBDA else None
+        self._e = torch.zeros((Sp, 4), dtype=dt, device=d) if self._ALGO == abi.ALGO_QLAMBDA else None
         self._visits = torch.zeros((Sp, 4), dtype=torch.int32, device=d)
-        # One 64-byte device staging block per learner holds everything a single call needs (slot word, epsilon, Philox
-        # words, the synthesised step record); each call packs it on the host and uploads it with ONE copy.
-        self._stage = torch.zeros(64, dtype=torch.uint8, device=d)
-        self._slot = self._stage[0:8].view(torch.int64)
-        self._eps = self._stage[8:16].view(torch.float64)
+        # One page-locked HOST staging block per learner holds everything a single call needs (slot word, epsilon, Philox
+        # words, the selected action, a ring of experience lists). Page-locked memory is device-accessible under unified
+        # addressing, so a call is: pack on the host -> ONE kernel launch that reads / writes the block in place -> (for a
+        # selection) one stream synchronisation. No staging copies, no torch ops on the call path.
+        self._stage = torch.zeros(self._STAGE_BYTES, dtype=torch.uint8).pin_memory()
+        self._stage_np = self._stage.numpy()
+        self._stage_mv = memoryview(self._stage_np)
+        self._base = self._stage.data_ptr()
+        self._ring = 0
+        self._st = abi.State(1, self._base, self._base + 8, self._q.data_ptr(), None if self._e is None else self._e.data_ptr(),
+                             self._visits.data_ptr(), None, None, None, None, None)
         self._hp = (self.learning_rate, self.gamma, lambd)
 
     # tables as views of exactly (S, A)
@@ -182,10 +201,6 @@ class _TabularBase(BaseLearningAlgorithm):
     def visits(self):
         return DeviceTable(self._visits[: self.state_space_size, : self.action_space_size])
 
-    def _state(self):
-        return abi.State(1, self._slot.data_ptr(), self._eps.data_ptr(), self._q.data_ptr(),
-                         None if self._e is None else self._e.data_ptr(), self._visits.data_ptr(), None, None, None, None, None)
-
     def _sync_hyper(self):
         hp = (self.learning_rate, self.gamma, getattr(self, "lambd", 0.0))
         if hp != self._hp:  # the reference lets callers mutate these attributes in place
@@ -198,28 +213,33 @@ class _TabularBase(BaseLearningAlgorithm):
             raise IndexError(f"encoded state {enc} out of range for state_space_size {self.state_space_size}")
         return enc // self._th.nq, enc % self._th.nq
 
-    # staging block layout (bytes): 0 slot u64 | 8 epsilon f64 | 16 draws 4 x u32 | 32 prev_cell u16 | 34 cell u16 | 36 prev_q u8 |
-    # 37 q u8 | 38 event u8 | 39 executed u8 | 40 reward f64 | 48 zero f64 (renv, rq) | 56 term u8 | 57 zero u8 (env_term,
-    # rm_term, trunc) | 58 action u8 | 59 selected action (output) u8
-    _REC_OFFSETS = {"prev_cell": 32, "cell": 34, "prev_q": 36, "q": 37, "event": 38, "executed": 39, "renv": 48, "rq": 48, "reward": 40,
-                    "env_term": 57, "rm_term": 57, "term": 56, "trunc": 57}
+    def _sync(self):
+        check(self._th.L.rlrm_stream_sync(self._th.h, self._th.stream()))
 
-    def _upload(self, payload: bytes, offset: int):
-        host = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
-        self._stage[offset:offset + len(payload)].copy_(host)  # pageable source: returns once the bytes are staged
-
-    def _device_update(self, s, sn, action, reward, terminated):
-        """One update_q / Q(lambda) update on the device (rlrm_update on a synthesised one-slot step record)."""
+    def _device_update_list(self, experiences):
+        """update_q / the Q(lambda) update for a list of (s, a, r, s', terminated) experiences, applied in order on the device
+        by ONE launch per _BLOCK experiences (rlrm_update_list). Asynchronous: the next selection (or any read of the
+        tables through torch, which runs on the same stream) is ordered after it."""
         import struct
 
         self._sync_hyper()
-        (c0, q0), (c1, q1) = self._split(s), self._split(sn)
-        self._upload(struct.pack("<HHBBBBddBBB", c0, c1, q0, q1, abi.EVENT_NONE, 5, float(reward), 0.0, int(bool(terminated)), 0,
-                                 int(action)), 32)
-        base = self._stage.data_ptr()
-        so = abi.StepOut(*[base + self._REC_OFFSETS[k] for k in abi.STEP_OUT_FIELDS])
-        st = self._state()
-        check(self._th.L.rlrm_update(self._th.h, C.byref(st), base + 32, base + 58, base + 56, C.byref(so), self._th.stream()))
+        S, L, th = self.state_space_size, self._th.L, self._th
+        for lo in range(0, len(experiences), self._BLOCK):
+            chunk = experiences[lo:lo + self._BLOCK]
+            blk = self._ring % self._RING
+            if blk == 0 and self._ring:
+                self._sync()  # the ring wrapped: make sure the launches that read these blocks have finished
+            off = self._EXP_OFF + blk * self._BLOCK * 24
+            for j, (s_, a_, r_, sn_, done_) in enumerate(chunk):
+                s_, sn_ = int(s_), int(sn_)
+                if not (0 <= s_ < S and 0 <= sn_ < S):
+                    raise IndexError(f"encoded state {s_ if not 0 <= s_ < S else sn_} out of range for state_space_size {S}")
+                struct.pack_into("<IIBB6xd", self._stage_mv, off + 24 * j, s_, sn_, int(a_), int(bool(done_)), float(r_))
+            check(L.rlrm_update_list(th.h, C.byref(self._st), 0, len(chunk), self._base + off, th.stream()))
+            self._ring += 1
+
+    def _device_update(self, s, sn, action, reward, terminated):
+        self._device_update_list([(s, action, reward, sn, terminated)])
 
     @staticmethod
     def _raw_words(rng):
@@ -238,12 +258,12 @@ class _TabularBase(BaseLearningAlgorithm):
 
         cell, q = self._split(encoded_state)
         words = [0, 0, 0, 0] if best else [int(x) & 0xFFFFFFFF for x in self._raw_words(self.rng if rng is None else rng)]
-        self._upload(struct.pack("<QdIIII", (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT), float(self.epsilon), *words), 0)
-        base = self._stage.data_ptr()
-        st = self._state()
-        check(self._th.L.rlrm_select_action(self._th.h, C.byref(st), None if best else base + 16, 0, int(bool(best)), base + 59,
-                                            self._th.stream()))
-        return int(self._stage[59].item())
+        struct.pack_into("<QdIIII", self._stage_mv, 0, (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT), float(self.epsilon), *words)
+        th = self._th
+        check(th.L.rlrm_select_action(th.h, C.byref(self._st), None if best else self._base + 16, 0, int(bool(best)), self._base + 59,
+                                      th.stream()))
+        self._sync()
+        return int(self._stage_np[59])
 
     def choose_action_greedy(self, encoded_state, rng):
         """Uniform choice among the greedy actions (qlearning.py:136-143): the device selection with exploration switched off
@@ -256,7 +276,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_slot", "_eps", "_stage")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_base", "_ring")}
         d["device"] = str(self.device)
         d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
                         "visits": self._visits.cpu().numpy()}
@@ -307,13 +327,16 @@ class QLearning(_TabularBase):
             pq, nq = info.get("prev_q", None), info.get("q", None)
             if pq is not None and nq is not None:
                 reward += self.gamma * rm.potentials.get(nq, 0) - rm.potentials.get(pq, 0)
-        if self.use_qrm:  # only the counterfactual list is applied (qlearning.py:82-106)
+        if self.use_qrm:  # only the counterfactual list is applied (qlearning.py:82-106): one launch for the whole list
+            todo = []
             for exp in info.get("qrm_experience", []):
                 _s, _a, _r, _sn, _done, _, cur_q, _, nxt_q, _ = exp
                 if shaping:
                     _r += self.gamma * rm.potentials.get(rm.get_state_from_index(nxt_q), 0) - rm.potentials.get(
                         rm.get_state_from_index(cur_q), 0)
-                self._device_update(_s, _sn, _a, _r, _done)
+                todo.append((_s, _a, _r, _sn, _done))
+            if todo:
+                self._device_update_list(todo)
         else:
             self._device_update(encoded_state, encoded_next_state, action, reward, terminated)
         return False

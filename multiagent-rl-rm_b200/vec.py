@@ -150,6 +150,16 @@ class BatchedRMEnvironment:
         return self._obs(lambda: torch.where(first, new_states["cell"], states["cell"]))
 
     # -- fused ---------------------------------------------------------------------------------------
+    def iterate(self, learn: bool = True, want_reward: bool = True):
+        """The whole loop body above — select_action, step, update_policy, reset of the finished instances — as ONE launch
+        (rlrm_iterate), for drivers that want the reference's per-iteration view of the run without five calls per
+        iteration. Returns (record, rewards): page-locked HOST tensors the kernel wrote in place, int32 / float64 of shape
+        [N, A]; `Engine.unpack_record(record)` gives action / executed action / new cell / new RM state / terminated /
+        truncated / active. Bit-identical to one iteration of the loop above and of `train(1)`."""
+        rec, rew = self.engine.iterate(learn=learn, want_reward=want_reward)
+        self._rec = None
+        return rec.view(self.n_envs, self.n_agents), None if rew is None else rew.view(self.n_envs, self.n_agents)
+
     def train(self, n_iters: int, learn: bool = True):
         return self.engine.train(n_iters, learn=learn)
 

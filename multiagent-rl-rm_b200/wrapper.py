@@ -45,10 +45,19 @@ class RMEnvironmentWrapper:
 
     def step(self, actions):
         prev_q = {a.name: a.get_reward_machine().get_current_state() for a in self.agents}
+        qrm_agents = [getattr(a.get_learning_algorithm(), "use_qrm", False) for a in self.agents]
+        # the same launch also evaluates the hypothetical RM transitions on the new position (cf_q / cf_r of rlrm_step)
         observations, rewards, env_term, env_trunc, infos, rec = self.env._step(actions, with_rm=True,
-                                                                                reward_modifier=self.reward_modifier)
+                                                                                reward_modifier=self.reward_modifier,
+                                                                                counterfactuals=any(qrm_agents))
         terminations = {}
-        self._cf_cache = self._counterfactual_lookups(observations)  # one rlrm_rm_step for every QRM agent of this step
+        self._cf_cache = {}
+        if any(qrm_agents):
+            stride = max(1, int(self.env._engine.cfg.n_qrm_states))
+            for i, agent in enumerate(self.agents):
+                n = len(agent.get_reward_machine().get_all_states()) - 1
+                if qrm_agents[i] and n > 0:
+                    self._cf_cache[agent.name] = (rec["cf_q"][i * stride:i * stride + n], rec["cf_r"][i * stride:i * stride + n])
         for i, agent in enumerate(self.agents):
             rm = agent.get_reward_machine()
             info = infos[agent.name]

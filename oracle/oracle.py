@@ -107,11 +107,17 @@ class Oracle:
                                     C.c_uint64(t), C.c_int(int(best)), C.c_void_p(_p(out)))
         return out.reshape(self.N, self.A)
 
-    def step(self, actions, t=0, draws=None, with_rm=True):
+    def step(self, actions, t=0, draws=None, with_rm=True, counterfactuals=False):
         acts = np.ascontiguousarray(actions, dtype=np.uint8).reshape(-1)
         d = None if draws is None else np.ascontiguousarray(draws, dtype=np.uint32)
         rec = {k: np.zeros(self.N * self.A, dtype=np.dtype(v)) for k, v in abi.STEP_OUT_FIELDS.items()}
-        so = abi.StepOut(*[_p(rec[k]) for k in abi.STEP_OUT_FIELDS])
+        cf = [None, None]
+        if counterfactuals:  # _get_qrm_experiences' RM lookups on the new position: [N*A][n_qrm_states]
+            nq = max(1, int(self.cfg.n_qrm_states))
+            rec["cf_q"] = np.zeros(self.N * self.A * nq, dtype=np.uint8)
+            rec["cf_r"] = np.zeros(self.N * self.A * nq, dtype=np.float64)
+            cf = [_p(rec["cf_q"]), _p(rec["cf_r"])]
+        so = abi.StepOut(*[_p(rec[k]) for k in abi.STEP_OUT_FIELDS], *cf)
         self.L.oracle_step(C.byref(self.cfg), C.byref(self.tables), C.byref(self.state), C.c_void_p(_p(acts)),
                            C.c_void_p(_p(d)), C.c_uint64(t), C.c_int(int(with_rm)), C.byref(so))
         return rec

@@ -19,7 +19,10 @@ import sys
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REFERENCE_ROOT = os.environ.get("RLRM_REFERENCE_ROOT", "/root/reference")
+# the live reference: the read-only tree in the build container, else the copy __graft_entry__.build() staged into the
+# git-ignored oracle/_ref/ (it travels to the GPU box with the snapshot so that bench.py can time the real reference there)
+REFERENCE_ROOT = os.environ.get("RLRM_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/multiagent_rlrm") else os.path.join(_HERE, "_ref"))
 
 
 def reference_available() -> bool:

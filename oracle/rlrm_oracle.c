@@ -312,7 +312,20 @@ int oracle_step(const rlrm_config_t* cfg, const rlrm_tables_t* tb, const rlrm_st
   for (int64_t i = 0; i < st->n_instances; i++) {
     step_instance(cfg, tb, st, i, actions + (size_t)i * cfg->n_agents, draws, t, with_rm, rec);
     clear_first(cfg, st, i);
-    for (int a = 0; a < cfg->n_agents; a++) store_rec(out, (size_t)i * cfg->n_agents + a, &rec[a]);
+    for (int a = 0; a < cfg->n_agents; a++) {
+      size_t k = (size_t)i * cfg->n_agents + a;
+      store_rec(out, k, &rec[a]);
+      if (out && (out->cf_q || out->cf_r)) { /* _get_qrm_experiences' RM lookups on the new position (rm_environment_wrapper.py:144-153) */
+        arm_t v = agent_rm(cfg, tb, a);
+        int col = rec[a].event == RLRM_EVENT_NONE ? cfg->n_events : (int)rec[a].event;
+        for (int j = 0; j < v.n_qrm; j++) {
+          int u = v.qrm_states[j];
+          int d = v.delta[u * (cfg->n_events + 1) + col];
+          if (out->cf_q) out->cf_q[k * cfg->n_qrm_states + j] = (uint8_t)(d == RLRM_NO_TRANSITION ? u : d);
+          if (out->cf_r) out->cf_r[k * cfg->n_qrm_states + j] = d == RLRM_NO_TRANSITION ? 0.0 : v.rcf[u * (cfg->n_events + 1) + col];
+        }
+      }
+    }
   }
   return 0;
 }
