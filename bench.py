@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=None,
                     help="target CPU time of one CPU sample (default: 12 s for cpu_baseline, 60 s / steps for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE configurations)")
+    ap.add_argument("--no-call-by-call", action="store_true", help="skip the per-iteration API measurements")
     return ap.parse_args()
 
 
@@ -141,7 +143,8 @@ def workload_config(args, world):
         "l2_policy": ("inputs larger than L2 (%.1f GB of tables per GPU vs 126 MB L2); no explicit flush" % (per_gpu / 1e9))
                      if per_gpu > 126e6 else "tables are L2-resident by design (shared learner); state arrays are streamed",
         "sharding": f"independent instances, {world} rank(s), "
-                    + ("shared tables all-reduced every 64 iterations (NCCL)" if sc.shared_q else "no data-path collective"),
+                    + ("shared tables merged every 64 iterations (NCCL all_gather_into_tensor + rank-ordered reduce kernel)"
+                       if sc.shared_q else "no data-path collective"),
     }
 
 
@@ -214,6 +217,7 @@ def run_reference_arm(args):
             vals.append(last["value"])
     value = sum(vals) / len(vals)
     last["value"] = value
+    last["reference_python"] = reference_python_throughput(args.workload, min(8.0, max(1.0, per_step)), procs)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -281,30 +285,307 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(algo):
-    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+def ncu_capture(workload):
+    """What the committed ncu --set full capture of this workload's dominant kernel measured (profiles/traffic.json, written by
+    profiles/scripts/make_traffic.py from profiles/<round>/*_raw.csv): DRAM bytes per active agent-step, cache hit rates,
+    pipe utilisation, the file and commit it came from. NOT measured in this run (ncu cannot run inside a timed bench)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return d.get(algo)
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
     except Exception:
         return None
 
 
-def ncu_summary(workload):
-    """Cache hit rates and pipe utilisation of the dominant kernel from the committed ncu capture, or None."""
+# what bounds the dominant kernel of each workload (ncu evidence under profiles/, DESIGN.md section 6); `frac` is always
+# computed against the HBM peak with SURVEY 8d's algorithmic bytes — it is an HBM-utilisation figure only where bound = hbm
+BOUND = {
+    "cfg3": "issue/latency (carried cell block: most algorithmic bytes never leave registers; DRAM ~30 % of peak)",
+    "cfg3_ql": "latency (one dependent 16-byte gather per step at 6.9 warps per scheduler)",
+    "cfg2_batch": "latency (one dependent 16-byte gather per step)",
+    "cfg2_batch_qrm": "latency on the row loads after a move, then L1 wavefronts",
+    "cfg4": "issue (trace lists stay L1/L2-resident)",
+    "cfg4_dense": "hbm",
+    "cfg4_qrm": "latency on the block fetch after a move, then shared-memory wavefronts",
+    "ow_exp6_qrm": "latency on the block fetch after a move, then shared-memory wavefronts",
+    "cfg5_tables": "issue/latency",
+    "cfg5_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
+}
+
+
+class Runner:
+    """One workload on this rank's GPU: engine, optional shared-learner merge schedule, device-timed steps, e2e on host buffers."""
+
+    def __init__(self, workload, instances, iters, rank, world, dev, offset=None, sync_every=0):
+        import multiagent_rlrm_b200 as P
+        from multiagent_rlrm_b200.engine import Engine
+
+        self.workload, self.instances, self.iters, self.world, self.dev = workload, instances, iters, world, dev
+        self.sc = scenario(workload)
+        self.c = P.compile_scenario(self.sc, instance_offset=rank * instances if offset is None else offset)  # Philox keyed on the GLOBAL instance id
+        self.eng = Engine(self.c, instances, device=dev, qlambda_sparse=(workload == "cfg4"))
+        self.eng.reset()
+        self.n_slots = instances * self.c.n_agents
+        self.sync_every = sync_every if (self.sc.shared_q and world > 1) else 0
+        self.merge_events = []
+
+    def train(self, n_iters, timed=False):
+        import torch
+
+        from multiagent_rlrm_b200.dist import merge_replicas
+
+        if not self.sync_every:
+            self.eng.train(n_iters)
+            return
+        done = 0
+        while done < n_iters:  # shared learner: parameter averaging every sync_every iterations (dist.ShardedTrainer's rule)
+            chunk = min(self.sync_every, n_iters - done)
+            self.eng.train(chunk)
+            done += chunk
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            merge_replicas(self.eng.q, self.world, engine=self.eng)
+            if timed:
+                e1.record()
+                self.merge_events.append((e0, e1))
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def run(self, steps, warmup, e2e_steps, rank0_sampler=None):
+        import torch
+        import torch.distributed as dist
+
+        eng = self.eng
+        for _ in range(warmup):
+            self.train(self.iters)
+        self.barrier()
+        launches0, steps0 = eng.launches, eng.total_active_steps()
+        work0 = int(eng.tr_work.sum()) if eng.sparse else 0
+        sampler = rank0_sampler() if rank0_sampler else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        self.barrier()
+        ev[0].record()
+        for k in range(steps):
+            self.train(self.iters, timed=True)
+            ev[k + 1].record()
+        self.barrier()
+        clocks = sampler.stop() if sampler else None
+        elapsed_ms = ev[0].elapsed_time(ev[-1])
+        per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        merge_ms = [a.elapsed_time(b) for a, b in self.merge_events]
+        active = eng.total_active_steps() - steps0
+        launches = eng.launches - launches0
+        mean_live = ((int(eng.tr_work.sum()) - work0) / max(1, self.n_slots * self.iters * steps)) if eng.sparse else None
+
+        # ---- end to end: the public API call on HOST (pinned) buffers, copies inside the timed region ----------------
+        e2e = None
+        if e2e_steps:
+            n = self.n_slots
+            host_slot = torch.empty(n, dtype=torch.int64).pin_memory()
+            host_eps = torch.empty(n, dtype=torch.float64).pin_memory()
+            host_stats = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+            host_slot.copy_(eng.slot); host_eps.copy_(eng.epsilon)
+
+            def host_active():  # finished episodes' agent_steps (stats) + running episodes' agent_steps (slot words), on the host
+                return int(host_stats.view(torch.int64)[:, 0].sum()) + int(((host_slot >> 16) & 0xFFFF).sum())
+
+            def one():
+                if not self.sync_every:
+                    eng.train_host(self.iters, host_stats, host_slot, host_eps)
+                    return
+                from multiagent_rlrm_b200.dist import merge_replicas
+
+                done = 0
+                while done < self.iters:
+                    chunk = min(self.sync_every, self.iters - done)
+                    eng.train_host(chunk, host_stats, host_slot, host_eps)
+                    done += chunk
+                    merge_replicas(eng.q, self.world, engine=eng)
+
+            one()  # warm
+            self.barrier()
+            a0 = host_active()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                one()
+            torch.cuda.synchronize(self.dev)
+            e2e_s = time.perf_counter() - t0
+            e2e = {"active": host_active() - a0, "seconds": e2e_s, "h2d": host_slot.numel() * 8 + host_eps.numel() * 8,
+                   "d2h": host_stats.numel() + host_slot.numel() * 8 + host_eps.numel() * 8}
+
+        merge_total = sum(merge_ms)
+        if self.world > 1:
+            t = torch.tensor([elapsed_ms, e2e["seconds"] if e2e else 0.0, merge_total], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed_ms, e2e_s_max, merge_total = float(t[0]), float(t[1]), float(t[2])
+            cnt = torch.tensor([active, e2e["active"] if e2e else 0, launches], dtype=torch.int64, device=self.dev)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            active, e2e_active, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
+            if e2e:
+                e2e["seconds"], e2e["active"] = e2e_s_max, e2e_active
+        return {"elapsed_ms": elapsed_ms, "per_launch_ms": per_launch_ms, "active": active, "launches": launches, "mean_live": mean_live,
+                "e2e": e2e, "clocks": clocks, "merge_ms_total": merge_total, "n_merges": len(merge_ms), "steps": steps}
+
+
+def summarise(workload, r, res, world, peak, peak_src):
+    """One measured entry (headline or `configs` block) from Runner.run's numbers."""
+    steps, iters = res["steps"], r.iters
+    value = res["active"] / (res["elapsed_ms"] * 1e-3)
+    bytes_per = WORKLOADS[workload][4]
+    if bytes_per is None:  # sparse-exact Q(lambda): 32 + 16 * (mean live traces), SURVEY.md 8(d), measured in this run
+        bytes_per = 32 + 16 * res["mean_live"]
+    kernel_ms = sum(res["per_launch_ms"]) / len(res["per_launch_ms"])  # this rank's average step duration (CUDA events)
+    active_per_launch_rank = (res["active"] / world) / steps
+    achieved = bytes_per * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9
+    cap = ncu_capture(workload) or {}
+    dram_b = cap.get("dram_bytes_per_active_step")
+    dram_gbs = dram_b * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9 if dram_b else None
+    roof = {"bound": BOUND.get(workload, "hbm"), "roofline": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "dram_GBps": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
+            "traffic": (dram_b * active_per_launch_rank) if dram_b else None,
+            "traffic_source": cap.get("source"), "ncu": cap.get("ncu"), "peak_source": peak_src, "kernel": WORKLOADS[workload][5],
+            "algorithmic_bytes_per_active_agent_step": bytes_per, "active_agent_steps_per_launch": active_per_launch_rank,
+            "launch_ms": kernel_ms,
+            "note": "frac = SURVEY 8d algorithmic bytes / step time / HBM peak; dram_frac = DRAM bytes the committed ncu capture "
+                    "measured per active agent-step (traffic_source) x this run's rate / HBM peak — the real HBM utilisation"}
+    if res["mean_live"] is not None:
+        roof.update({"mean_live_traces": res["mean_live"],
+                     "dense_equivalent_GBps": (4 * 1296 * 4 * 4) * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9,
+                     "sparse_note": "achieved uses the sparse algorithm's own bytes (32 + 16*L, SURVEY 8d); dense_equivalent is what the "
+                                    "reference's dense sweep would have moved for the same steps, NOT achieved bandwidth; the lists stay "
+                                    "cache-resident across the iterations of a launch, so frac can exceed 1"})
+    out = {"value": value, "unit": UNIT, "ms_per_step": res["elapsed_ms"] / steps, "steps": steps, "instances_per_gpu": r.instances,
+           "agents": r.c.n_agents, "iters_per_step": iters, "gpu_launches": res["launches"],
+           "slot_steps_per_s": world * r.n_slots * iters * steps / (res["elapsed_ms"] * 1e-3),
+           "active_fraction": res["active"] / (world * r.n_slots * iters * steps), "roofline": roof,
+           "baseline_config": WORKLOADS[workload][1]}
+    if res["e2e"]:
+        e = res["e2e"]
+        out["e2e"] = {"value": e["active"] / e["seconds"], "unit": UNIT, "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
+                      "api": "Engine.train_host -> rlrm_train_host (pinned host slot/epsilon in+out, stats out)"}
+        out["e2e_over_value"] = out["e2e"]["value"] / value
+    if r.sync_every:
+        out["collective"] = {"op": "NCCL all_gather_into_tensor of the replicas + rank-ordered reduce kernel (rlrm_merge_replicas)",
+                             "sync_every": r.sync_every, "merges": res["n_merges"],
+                             "merge_ms": res["merge_ms_total"] / max(1, res["n_merges"]),
+                             "collective_share": res["merge_ms_total"] / res["elapsed_ms"]}
+    return out
+
+
+def call_by_call(c, sc, instances, dev):
+    """The reference's per-iteration granularity, end to end on host buffers, two ways: (1) rlrm_iterate — ONE launch per
+    driver-loop iteration that writes the step record (4 B) and reward (8 B) per agent straight into page-locked host
+    memory, one stream synchronisation per iteration; (2) the five separate calls of the reference loop (select_action ->
+    step -> update_policy -> reset), each one C-ABI call, with the actions / observations / rewards / done flags copied to
+    the host every iteration."""
+    import torch
+
+    from multiagent_rlrm_b200.vec import BatchedRMEnvironment
+
+    env = BatchedRMEnvironment(c, instances, device=dev)
+    eng = env.engine
+    env.reset()
+    for _ in range(50):
+        env.iterate()
+    a0, n_loop = eng.total_active_steps(), 400
+    torch.cuda.synchronize(dev)
+    ts = time.perf_counter()
+    chk = 0
+    for _ in range(n_loop):
+        rec, rew = env.iterate()           # synchronised: the host owns the record now
+        chk ^= int(rec[0, 0])              # touch it
+    dt = time.perf_counter() - ts
+    fused = {"value": (eng.total_active_steps() - a0) / dt, "unit": UNIT, "iterations": n_loop, "us_per_iteration": dt / n_loop * 1e6,
+             "launches_per_iteration": 1, "d2h_bytes_per_iteration": rec.numel() * 4 + rew.numel() * 8, "h2d_bytes_per_iteration": 0,
+             "api": "vec.BatchedRMEnvironment.iterate -> rlrm_iterate (select + step + update + masked reset in one launch; record and "
+                    "reward written in place into page-locked host memory; one stream synchronisation per iteration)"}
+    del env
+
+    env = BatchedRMEnvironment(c, instances, device=dev)
+    h_act = torch.empty((instances, c.n_agents), dtype=torch.uint8).pin_memory()
+    h_cell = torch.empty((instances, c.n_agents), dtype=torch.int64).pin_memory()
+    h_rew = torch.empty((instances, c.n_agents), dtype=torch.float64).pin_memory()
+    h_done = torch.empty((instances, c.n_agents), dtype=torch.bool).pin_memory()
+    fl = sc.driver == "frozen_lake_main"
+    n_active = torch.zeros((), dtype=torch.int64, device=dev)  # agents that actually stepped (executed != 5), on the device
+
+    def loop(n):
+        states, _ = env.reset()
+        for _ in range(n):
+            actions = env.select_action(states)
+            h_act.copy_(actions, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            actions = h_act.to(dev, non_blocking=True)
+            new_states, rewards, term, trunc, infos = env.step(actions)
+            n_active.add_((env._rec["executed"] != 5).sum())
+            h_cell.copy_(new_states["cell"], non_blocking=True)
+            h_rew.copy_(rewards, non_blocking=True)
+            h_done.copy_(term | trunc, non_blocking=True)
+            env.update_policy(env.driver_states(states, new_states), actions, rewards, new_states, (term | trunc) if fl else term, infos)
+            states = new_states
+            over = env.episode_over(term, trunc)
+            env.reset(mask=over)
+            states = env._obs(env._cells())
+            torch.cuda.current_stream(dev).synchronize()
+
+    prev = None
+    for _ in range(8):  # warm up until the per-iteration time stops improving (lazy kernel loading on a fresh box)
+        tw = time.perf_counter()
+        loop(20)
+        torch.cuda.synchronize(dev)
+        tw = time.perf_counter() - tw
+        if prev is not None and tw > 0.8 * prev:
+            break
+        prev = tw
+    n_active.zero_()
+    n_loop = 100
+    torch.cuda.synchronize(dev)
+    ts = time.perf_counter()
+    loop(n_loop)
+    dt = time.perf_counter() - ts
+    unfused = {"value": int(n_active) / dt, "unit": UNIT, "iterations": n_loop, "us_per_iteration": dt / n_loop * 1e6,
+               "h2d_bytes_per_iteration": h_act.numel(),
+               "d2h_bytes_per_iteration": h_act.numel() + h_cell.numel() * 8 + h_rew.numel() * 8 + h_done.numel(),
+               "api": "vec.BatchedRMEnvironment select_action / step / update_policy / reset (one C-ABI call each), host round trip every iteration"}
+    del env
+    return fused, unfused
+
+
+def reference_python_throughput(workload, seconds, procs):
+    """The REAL reference (its Python sources staged into the git-ignored oracle/_ref by __graft_entry__.build) on `procs` host
+    processes, own PCG64 randomness, float64 tables: BASELINE.md section 3's baseline of record. None when it is not staged."""
+    import multiprocessing as mp
+
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload + "_ncu")
-    except Exception:
-        return None
+        import ref_harness as H
+
+        if not H.reference_available():
+            return None
+        import time_reference_python as T
+
+        sc = scenario(workload).to_dict()
+        mode = "fixed" if sc["driver"] == "frozen_lake_main" else "episode"
+        jobs = [(workload, dict(sc, seed=sc["seed"] + k), seconds, 10**9, mode) for k in range(procs)]
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(T.run_case, jobs)
+        return {"value": sum(r["active_agent_steps_per_s"] for r in res), "unit": UNIT, "cores": procs, "kind": "reference",
+                "per_core": sum(r["active_agent_steps_per_s"] for r in res) / procs,
+                "sample": f"{procs} independent processes x {seconds:.0f} s of the live Python reference classes (multiagent_rlrm, float64 "
+                          f"tables, its own driver loop restated) on the same workload"}
+    except Exception as exc:  # the staged reference is optional
+        return {"unavailable": repr(exc)[:200]}
 
 
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    import multiagent_rlrm_b200 as P
-    from multiagent_rlrm_b200.dist import merge_replicas
-    from multiagent_rlrm_b200.engine import Engine
+    from multiagent_rlrm_b200.dist import shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -314,178 +595,69 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    peak, peak_src = measured_peak()
 
-    sc = scenario(args.workload)
-    c = P.compile_scenario(sc, instance_offset=rank * args.instances)  # Philox keyed on the GLOBAL instance id
-    eng = Engine(c, args.instances, device=dev, qlambda_sparse=(args.workload == "cfg4"))
-    eng.reset()
-    n_slots = args.instances * c.n_agents
-    sync_every = 64 if (sc.shared_q and world > 1) else 0
-    real_train = eng.train
+    # ---- headline ------------------------------------------------------------------------------------------------------
+    shared = scenario(args.workload).shared_q
+    r = Runner(args.workload, args.instances, args.iters, rank, world, dev, sync_every=64 if shared else 0)
+    res = r.run(args.steps, args.warmup, max(3, args.steps // 2), (lambda: ClockSampler(local_rank)) if rank == 0 else None)
+    head = summarise(args.workload, r, res, world, peak, peak_src)
+    stepwise = unfused = None
+    if world == 1 and args.workload in ("cfg3", "cfg3_ql") and not args.no_call_by_call:
+        stepwise, unfused = call_by_call(r.c, r.sc, args.instances, dev)
+    del r
+    torch.cuda.empty_cache()
 
-    def train_with_merge(n_iters, **kw):  # shared learner: parameter averaging every 64 iterations (dist.ShardedTrainer rule)
-        done = 0
-        while done < n_iters:
-            chunk = min(sync_every, n_iters - done) if sync_every else n_iters
-            real_train(chunk, **kw)
-            done += chunk
-            if sync_every:
-                merge_replicas(eng.q, world)
-
-    if sync_every:
-        eng.train = train_with_merge
-
-    def barrier():
+    # ---- every other BASELINE configuration, short measured entries (same timing rules) -------------------------------------
+    configs = {}
+    if args.workload == "cfg3" and not args.no_configs:
+        n_total5 = 1048576
+        off5, n5 = shard_range(n_total5, rank, world)
+        plan = [  # name, workload, instances on this rank, global offset (None = rank * instances), iters, steps, sync_every, scaling
+            ("cfg2_batch", "cfg2_batch", 131072, None, 2048, 5, 0, "weak"),
+            ("cfg4_sparse", "cfg4", 262144, None, 64, 5, 0, "weak"),
+            ("cfg4_dense", "cfg4_dense", 262144, None, 4, 3, 0, "weak"),
+            ("cfg5_tables", "cfg5_tables", n5, off5, 256, 5, 0, "strong"),
+            ("cfg5_shared", "cfg5_shared", n5, off5, 256, 5, 64, "strong"),
+        ]
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(args.warmup):
-        eng.train(args.iters)
-    barrier()
-    launches0, steps0 = eng.launches, eng.total_active_steps()
-    work0 = int(eng.tr_work.sum()) if eng.sparse else 0
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record()
-    for k in range(args.steps):
-        eng.train(args.iters)
-        ev[k + 1].record()
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    elapsed_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    active = eng.total_active_steps() - steps0
-    launches = eng.launches - launches0
-    mean_live = ((int(eng.tr_work.sum()) - work0) / max(1, n_slots * args.iters * args.steps)) if eng.sparse else None
-
-    # ---- end to end: the public API call on HOST (pinned) buffers, copies inside the timed region --------------------
-    host_slot = torch.empty(n_slots, dtype=torch.int64).pin_memory()
-    host_eps = torch.empty(n_slots, dtype=torch.float64).pin_memory()
-    host_stats = torch.empty((n_slots, 32), dtype=torch.uint8).pin_memory()
-    host_slot.copy_(eng.slot); host_eps.copy_(eng.epsilon)
-    e2e_steps = max(3, args.steps // 2)
-    eng.train_host(args.iters, host_stats, host_slot, host_eps)  # warm
-    barrier()
-    def host_active():  # finished episodes' agent_steps (stats) + running episodes' agent_steps (slot words), all on the host
-        return int(host_stats.view(torch.int64)[:, 0].sum()) + int(((host_slot >> 16) & 0xFFFF).sum())
-
-    a0 = host_active()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.train_host(args.iters, host_stats, host_slot, host_eps)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    e2e_active = host_active() - a0
-    h2d = host_slot.numel() * 8 + host_eps.numel() * 8
-    d2h = host_stats.numel() + host_slot.numel() * 8 + host_eps.numel() * 8
-
-    # ---- secondary: the call-by-call API (the reference's granularity) end to end on host buffers --------------------------
-    # per iteration: select_action -> actions to the host and back (a user hands env.step host actions) -> step ->
-    # observations / rewards / done flags to the host -> update_policy -> reset of finished instances
-    stepwise = None
-    if world == 1 and args.workload in ("cfg3", "cfg3_ql"):
-        from multiagent_rlrm_b200.vec import BatchedRMEnvironment
-
-        env = BatchedRMEnvironment(c, args.instances, device=dev)
-        h_act = torch.empty((args.instances, c.n_agents), dtype=torch.uint8).pin_memory()
-        h_cell = torch.empty((args.instances, c.n_agents), dtype=torch.int64).pin_memory()
-        h_rew = torch.empty((args.instances, c.n_agents), dtype=torch.float64).pin_memory()
-        h_done = torch.empty((args.instances, c.n_agents), dtype=torch.bool).pin_memory()
-        fl = sc.driver == "frozen_lake_main"
-
-        n_active = torch.zeros((), dtype=torch.int64, device=dev)  # agents that actually stepped (executed != 5), on the device
-
-        def loop(n):
-            states, _ = env.reset()
-            for _ in range(n):
-                actions = env.select_action(states)
-                h_act.copy_(actions, non_blocking=True)
-                torch.cuda.current_stream(dev).synchronize()
-                actions = h_act.to(dev, non_blocking=True)
-                new_states, rewards, term, trunc, infos = env.step(actions)
-                n_active.add_((env._rec["executed"] != 5).sum())
-                h_cell.copy_(new_states["cell"], non_blocking=True)
-                h_rew.copy_(rewards, non_blocking=True)
-                h_done.copy_(term | trunc, non_blocking=True)
-                env.update_policy(env.driver_states(states, new_states), actions, rewards, new_states,
-                                  (term | trunc) if fl else term, infos)
-                states = new_states
-                over = env.episode_over(term, trunc)
-                env.reset(mask=over)
-                states = env._obs(env._cells())
-                torch.cuda.current_stream(dev).synchronize()
-
-        # warm up until the per-iteration time stops improving: the first process on a fresh box pages the image in and
-        # loads the call-by-call kernels lazily, which can cost milliseconds per iteration for the first few hundred
-        prev = None
-        for _ in range(12):
-            tw = time.perf_counter()
-            loop(20)
-            torch.cuda.synchronize(dev)
-            tw = time.perf_counter() - tw
-            if prev is not None and tw > 0.8 * prev:
-                break
-            prev = tw
-        n_active.zero_()
-        n_loop = 200
-        torch.cuda.synchronize(dev)
-        ts = time.perf_counter()
-        loop(n_loop)
-        dt = time.perf_counter() - ts
-        stepwise = {"value": int(n_active) / dt, "unit": UNIT, "iterations": n_loop,
-                    "us_per_iteration": dt / n_loop * 1e6,
-                    "h2d_bytes_per_iteration": h_act.numel(), "d2h_bytes_per_iteration": h_act.numel() + h_cell.numel() * 8 + h_rew.numel() * 8 + h_done.numel(),
-                    "api": "vec.BatchedRMEnvironment select_action / step / update_policy / reset (one C-ABI call each), host round trip every iteration"}
-        del env
-
-    if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s = float(t[0]), float(t[1])
-        cnt = torch.tensor([active, e2e_active, launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        active, e2e_active, launches = int(cnt[0]), int(cnt[1]), int(cnt[2])
+            plan += [("cfg5_shared_K16", "cfg5_shared", n5, off5, 256, 3, 16, "strong"),
+                     ("cfg5_shared_K256", "cfg5_shared", n5, off5, 256, 3, 256, "strong"),
+                     ("cfg5_shared_weak", "cfg5_shared", n_total5, None, 256, 3, 64, "weak")]
+        for name, wl, inst, off, iters, steps, k_sync, scaling in plan:
+            try:
+                rr = Runner(wl, inst, iters, rank, world, dev, offset=off, sync_every=k_sync)
+                rs = rr.run(steps, 3, 2)
+                entry = summarise(wl, rr, rs, world, peak, peak_src)
+                entry["scaling"] = scaling
+                entry["sharding"] = (f"{n_total5} instances in total over {world} rank(s) (dist.shard_range)" if scaling == "strong"
+                                     else f"{inst} instances per rank") + \
+                                    (f"; shared tables merged every {k_sync} iterations: NCCL all_gather_into_tensor + rank-ordered reduce kernel"
+                                     if (k_sync and world > 1) else ("; shared tables, single replica (no collective at 1 GPU)" if k_sync else
+                                                                     "; no data-path collective"))
+                configs[name] = entry
+                del rr
+            except Exception as exc:  # a config that does not fit must not take the headline down
+                configs[name] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
 
     if rank == 0:
-        value = active / (elapsed_ms * 1e-3)
-        bytes_per = WORKLOADS[args.workload][4]
-        if bytes_per is None:  # sparse-exact Q(lambda): 32 + 16 * (mean live traces), SURVEY.md §8(d), measured in this run
-            bytes_per = 32 + 16 * mean_live
-        peak, peak_src = measured_peak()
-        kernel_ms = sum(per_launch_ms) / len(per_launch_ms)          # this rank's average launch duration (CUDA events)
-        active_per_launch_rank = (active / world) / args.steps
-        achieved = bytes_per * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_port_throughput(args.workload, args.cpu_seconds or 12.0, os.cpu_count() or 1)
+            procs = os.cpu_count() or 1
+            cpu = cpu_port_throughput(args.workload, args.cpu_seconds or 12.0, procs)
+            cpu["reference_python"] = reference_python_throughput(args.workload, 8.0, procs)
+        cfgd = workload_config(args, world)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
-            "slot_steps_per_s": world * n_slots * args.iters * args.steps / (elapsed_ms * 1e-3),
-            "active_fraction": active / (world * n_slots * args.iters * args.steps),
-            "clocks": clocks,
-            "e2e": {"value": e2e_active / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "Engine.train_host -> rlrm_train_host (pinned host slot/epsilon in+out, stats out)"},
-            "e2e_call_by_call": stepwise,
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload), "ncu": ncu_summary(args.workload), "peak_source": peak_src,
-                         "kernel": WORKLOADS[args.workload][5],
-                         "algorithmic_bytes_per_active_agent_step": bytes_per,
-                         "active_agent_steps_per_launch": active_per_launch_rank, "launch_ms": kernel_ms,
-                         **({"mean_live_traces": mean_live,
-                             "dense_equivalent_GBps": (4 * 1296 * 4 * 4) * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9,
-                             "note": "achieved uses the sparse algorithm's own bytes (32 + 16*L, SURVEY 8d); dense_equivalent is "
-                                     "what the reference's dense sweep would have moved for the same steps, NOT achieved "
-                                     "bandwidth. The lists stay L1/L2-resident across the iterations of one launch (ncu: DRAM "
-                                     "at 3 % of peak, issue slots 74 %, L1 wavefronts 61 %), so frac can exceed 1: the kernel "
-                                     "is instruction-issue bound, see profiles/r01_sparse_qlambda_v3_ncu_full.csv"}
-                            if mean_live is not None else {})},
-            "cpu_baseline": cpu,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfgd,
+            "slot_steps_per_s": head["slot_steps_per_s"], "active_fraction": head["active_fraction"],
+            "clocks": res["clocks"], "e2e": head.get("e2e"), "e2e_call_by_call": stepwise, "e2e_call_by_call_unfused": unfused,
+            "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": cpu, "configs": configs,
         }
+        if "collective" in head:
+            line["collective"] = head["collective"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -40,6 +40,8 @@ struct rlrm_handle {
   int qrm4_fast;  // train_qrm4_kernel is applicable (see its header comment)
   int ql_fast;    // train_ql_fast_kernel is applicable (see its header comment)
   int qrmn_fast;  // train_qrmn_kernel<NQ = 3 or 5> is applicable (see its header comment)
+  int qrmb_fast;  // train_qrm_block_kernel is applicable (QRM, any state order, 6..16 RM states; see its header comment)
+  int qrmb_smem;  // its dynamic shared memory: table blob + 16*nQ bytes per thread
   int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
   int shared_smem_bytes;
   int num_sms;
@@ -258,13 +260,25 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   h->ql_fast = (f32 && kp.algo == RLRM_ALGO_QL && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
                 !(cfg->reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  h->qrmb_smem = align16(off) + kp.nQ * 16 * TRAIN_BLOCK;
+  h->qrmb_fast = (f32 && kp.algo == RLRM_ALGO_QRM && !h->qrm4_fast && !h->qrmn_fast && kp.nQ >= 2 && kp.nQ <= 16 && kp.n_qrm >= 1 && kp.n_qrm <= 15 &&
+                  !kp.shared_q && !kp.per_agent && cfg->learning_rate >= 0.0 && h->qrmb_smem <= h->max_smem && !(cfg->reserved & 1));
+  if (h->qrmb_fast) {  // opt in to the device maximum (per function, only ever raised)
+    cudaError_t e2 = cudaSuccess;
+#define RLRM_OPTIN(K) if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 7>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 11>));
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 15>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 7>));
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 11>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 15>));
+#undef RLRM_OPTIN
+    if (e2 != cudaSuccess) h->qrmb_fast = 0;
+  }
   {
     const long long n_ent = (long long)kp.A * kp.S4;
     const long long need = (long long)off + n_ent * 21;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry + row max 4 B per 4 entries
     h->shared_smem_bytes = (int)need;
     h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
                       !(cfg->reserved & 1));
-    cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (need > h->max_smem) h->shared_fast = 0;
     if (h->shared_fast) {
       // opt every instantiation in to the DEVICE maximum: the attribute is per function, not per handle, so a later handle
@@ -292,7 +306,7 @@ extern "C" int rlrm_set_learner(rlrm_handle_t* h, double learning_rate, double g
   if (!h) return fail(RLRM_ERR_ARG, "null handle");
   h->cfg.learning_rate = learning_rate; h->cfg.gamma = gamma; h->cfg.lambd = lambd;
   fill_learner(h->kp, learning_rate, gamma, lambd);
-  if (learning_rate < 0.0) h->qrm4_fast = h->ql_fast = h->qrmn_fast = 0;
+  if (learning_rate < 0.0) h->qrm4_fast = h->ql_fast = h->qrmn_fast = h->qrmb_fast = 0;
   return RLRM_OK;
 }
 
@@ -565,6 +579,12 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
         default: RLRM_QRMN(true, true, true); break;
       }
 #undef RLRM_QRMN
+    }
+    else if (fast_ok && kp.algo == RLRM_ALGO_QRM && h->qrmb_fast && !st->visits) {
+      const DState d = dstate(st);
+      if (kp.n_qrm <= 7) train_qrm_block_kernel<ENV, 7><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace);
+      else if (kp.n_qrm <= 11) train_qrm_block_kernel<ENV, 11><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace);
+      else train_qrm_block_kernel<ENV, 15><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace);
     }
     else if (fast_ok && kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
       const DState d = dstate(st);

@@ -455,6 +455,156 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrmn_kernel(KP p, DState
 }
 
 // ------------------------------------------------------------------------------------------------
+// fast path: QRM with MORE than five reward-machine states (OfficeWorld exp5 / exp6: 9 / 10 states, BASELINE config 4's
+// 12-state machine with the QRM learner). The generic kernel issues, per counterfactual state, a dependent load -> update ->
+// store chain on global memory (ncu: 81 % of the warp time on the long scoreboard, issue slots 22 % busy). Here the cell block
+// Q[cell, 0..nQ-1, 0..3] of the agent's current cell lives in SHARED memory (16*nQ bytes per thread, laid out [row][thread]
+// so that every access is a conflict-free 16-byte one): it is (re)fetched with one cp.async per row — all rows in flight at
+// once, no registers — only when the agent changes cell; selection and the row maxima of the counterfactual targets are LDS;
+// the new values go back to global memory as scalar stores and, when the agent stayed in its cell, into the shared block.
+// A register-carried block (train_qrmn_kernel) would need 4*nQ + nQ registers; shared memory also makes the dynamic row
+// index free, so qrm_states may be any permutation (the 12-state chain's index map is lexicographic: q10 < q2).
+// NU = compile-time bound on the number of counterfactual states (the values they overwrite are read into registers before
+// the block is replaced). Supports shaping and random starts; per-agent machines / lr=None / shared tables stay generic.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <int ENV, int NU>
+__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                                      unsigned* trace) {
+  Tab tb = stage_tables(p);
+  float4* blk = reinterpret_cast<float4*>(smem_raw + ((p.blob_bytes + 15) & ~15)) + threadIdx.x;  // row r of this thread: blk[r * TRAIN_BLOCK]
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = tid >> p.g_shift;
+  const int a = (int)(tid & (p.G - 1));
+  const bool valid = (i < st.N) && (a < p.A);
+  const long long k = i * p.A + a;
+  const int nQ = p.nQ, nE1 = p.nEv + 1;
+
+  Slot s = {0, 0, 0, 0, 0};
+  double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
+  float* Q = st.q;
+  unsigned long long active_steps = 0;
+  unsigned episodes = 0, successes = 0, last_length = 0;
+  float last_return = 0.f;
+  if (valid) {
+    s = unpack_slot(st.slot[k]);
+    eps = st.epsilon[k];
+    if (st.ep_return) ep_ret = st.ep_return[k];
+    if (st.stats) return_sum = st.stats[k].return_sum;
+    Q = st.q + table_base(p, i, a);
+    const float* src = Q + (size_t)s.cell * (size_t)(nQ * 4);
+    for (int r = 0; r < nQ; r++) cp_async16(blk + r * TRAIN_BLOCK, src + 4 * r);
+  }
+  cp_async_wait_all();
+  unsigned long long explore_thr = explore_threshold(eps);
+  bool had_episode = false;
+
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    bool term = true, trunc = true;
+    if (valid) {
+      unsigned w[4];
+      RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      const float4 row = blk[s.rm * TRAIN_BLOCK];
+      const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
+      const unsigned before = s.cell;
+      Rec r;
+      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      const bool moved = r.cell != before;
+      if (learn) {
+        float cur[NU];  // values the updates overwrite, read before the block is replaced
+#pragma unroll
+        for (int j = 0; j < NU; j++) {
+          const float4 v = blk[(j < p.n_qrm ? tb.qrm_states[j] : 0) * TRAIN_BLOCK];
+          cur[j] = sel4(v.x, v.y, v.z, v.w, (unsigned)action);
+        }
+        if (moved) {  // the shared block becomes the NEXT cell's block: one asynchronous 16-byte copy per row
+          const float* src = Q + (size_t)r.cell * (size_t)(nQ * 4);
+          for (int rr = 0; rr < nQ; rr++) cp_async16(blk + rr * TRAIN_BLOCK, src + 4 * rr);
+          cp_async_wait_all();
+        }
+        // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106) in
+        // get_all_states()[:-1] order. The next state's row maximum comes from the shared block: the new cell's block when
+        // the agent moved, else the live one including this step's earlier updates.
+        const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+        float* dst = Q + (size_t)before * (size_t)(nQ * 4) + action;  // infos["prev_s"] is the position before the move
+#pragma unroll
+        for (int j = 0; j < NU; j++) {
+          if (j < p.n_qrm) {
+            const unsigned u = tb.qrm_states[j];
+            const unsigned d = tb.delta[u * nE1 + col];
+            const unsigned un = d == RLRM_NO_TRANSITION ? u : d;
+            const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * nE1 + col];
+            const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
+            double rew = __dadd_rn(r.renv, ru);
+            if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[un]), tb.phi[u]));  // qlearning.py:93-105
+            const float mf = __fmul_rn(done ? 0.0f : 1.0f, row_max(blk[un * TRAIN_BLOCK]));
+            const float inner = __fadd_rn(__double2float_rn(rew), __fmul_rn(p.gamma_f, mf));
+            const float nv = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur[j]), __fmul_rn(p.lr_f, inner));
+            if (__float_as_uint(nv) != __float_as_uint(cur[j])) dst[4 * u] = nv;  // a bit-identical value needs no store
+            if (!moved) reinterpret_cast<float*>(blk + u * TRAIN_BLOCK)[action] = nv;  // same cell: the shared block is the one just written
+          }
+        }
+      } else if (moved) {
+        const float* src = Q + (size_t)r.cell * (size_t)(nQ * 4);
+        for (int rr = 0; rr < nQ; rr++) cp_async16(blk + rr * TRAIN_BLOCK, src + 4 * rr);
+        cp_async_wait_all();
+      }
+      term = r.term;
+      trunc = r.trunc;
+      ep_ret = __dadd_rn(ep_ret, r.reward);
+      if (trace)
+        trace[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = (unsigned)action | (r.executed << 3) | (r.cell << 6) | (r.q << 16) |
+                                                             ((unsigned)r.term << 21) | ((unsigned)r.trunc << 22) |
+                                                             ((unsigned)r.stepped << 23);
+    }
+    unsigned flags2 = (term ? 1u : 0u) | (trunc ? 2u : 0u);
+    for (int o = 1; o < p.G; o <<= 1) flags2 &= __shfl_xor_sync(0xFFFFFFFFu, flags2, o);
+    const bool over = flags2 != 0u;
+    if (valid && over) {
+      episodes++;
+      active_steps += s.steps;
+      successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+      last_return = __double2float_rn(ep_ret);
+      return_sum = __dadd_rn(return_sum, ep_ret);
+      last_length = s.time;
+      had_episode = true;
+      ep_ret = 0.0;
+      const unsigned old_cell = s.cell;
+      reset_slot(p, tb, i, a, t + 1, s, eps);
+      explore_thr = explore_threshold(eps);
+      if (s.cell != old_cell) {
+        const float* src = Q + (size_t)s.cell * (size_t)(nQ * 4);
+        for (int rr = 0; rr < nQ; rr++) cp_async16(blk + rr * TRAIN_BLOCK, src + 4 * rr);
+        cp_async_wait_all();
+      }
+    }
+  }
+  if (valid) {
+    st.slot[k] = pack_slot(s);
+    st.epsilon[k] = eps;
+    if (st.ep_return) st.ep_return[k] = ep_ret;
+    if (st.stats) {
+      rlrm_stats_t z = st.stats[k];
+      z.active_steps += active_steps;
+      z.episodes += episodes;
+      z.successes += successes;
+      z.return_sum = return_sum;
+      if (had_episode) {
+        z.last_return = last_return;
+        z.last_length = last_length;
+      }
+      st.stats[k] = z;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fast path: plain Q-learning with a private table per (instance, agent), fixed learning rate, no visit counts, no shaping
 // (BASELINE config 3's `use_qrm=0, lr=0.1` variant). Same algorithm as train_kernel's row-carry branch — the row of the
 // agent's current state stays in registers, one 16-byte load of Q[s'] and at most one 4-byte store per step — with the

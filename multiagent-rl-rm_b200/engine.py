@@ -49,6 +49,7 @@ class Engine:
         self.device = torch.device(device)
         self.N, self.A, self.S = int(n_instances), compiled.n_agents, compiled.state_space
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._dev_index = dev_index
         self._tables = compiled.tables_struct()
         h = C.c_void_p()
         check(self.L.rlrm_create(C.byref(self.cfg), C.byref(self._tables), dev_index, C.byref(h)))
@@ -106,7 +107,8 @@ class Engine:
 
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        """torch's current stream on this device as a raw cudaStream_t (one C call; the Stream object is not built)."""
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def set_learner(self, learning_rate, gamma, lambd=0.0):
         check(self.L.rlrm_set_learner(self.h, -1.0 if learning_rate is None else float(learning_rate), float(gamma), float(lambd)))

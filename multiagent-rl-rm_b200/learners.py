@@ -13,6 +13,7 @@ tie-break, unused) taken from ``rng`` — ``rng.words()`` if it has that hook (t
 from __future__ import annotations
 
 import ctypes as C
+import struct
 
 import numpy as np
 import torch
@@ -107,6 +108,7 @@ class _TableHandle:
         dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
         check(self.L.rlrm_create(C.byref(cfg), C.byref(t), dev, C.byref(h)))
         self.h = h
+        self._dev_index = dev
 
     def __del__(self):
         try:
@@ -117,7 +119,8 @@ class _TableHandle:
             pass
 
     def stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        """torch's current stream on this device as a raw cudaStream_t (one C call; the Stream object is not built)."""
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
 
 class BaseLearningAlgorithm:
@@ -220,8 +223,6 @@ class _TabularBase(BaseLearningAlgorithm):
         """update_q / the Q(lambda) update for a list of (s, a, r, s', terminated) experiences, applied in order on the device
         by ONE launch per _BLOCK experiences (rlrm_update_list). Asynchronous: the next selection (or any read of the
         tables through torch, which runs on the same stream) is ordered after it."""
-        import struct
-
         self._sync_hyper()
         S, L, th = self.state_space_size, self._th.L, self._th
         for lo in range(0, len(experiences), self._BLOCK):
@@ -254,8 +255,6 @@ class _TabularBase(BaseLearningAlgorithm):
             if self.action_selection == "softmax":
                 raise NotImplementedError("softmax selection is out of scope (no reference driver uses it; DESIGN.md §8)")
             raise ValueError("Unsupported action selection method")
-        import struct
-
         cell, q = self._split(encoded_state)
         words = [0, 0, 0, 0] if best else [int(x) & 0xFFFFFFFF for x in self._raw_words(self.rng if rng is None else rng)]
         struct.pack_into("<QdIIII", self._stage_mv, 0, (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT), float(self.epsilon), *words)

@@ -54,13 +54,21 @@ class RewardMachine:
 
     # ------------------------------------------------------------------ bookkeeping
     def _states_in_order(self) -> List[Hashable]:
+        """First-appearance order of the states (reward_machine.py:95-111). The reference re-derives it on every call — it is
+        the top line of its profile, reached from every encode(); here it is cached and re-derived only when the transition
+        dict was replaced or changed size (configuration code builds machines by inserting transitions)."""
+        tr = self.transitions
+        cached = self.__dict__.get("_order_cache")
+        if cached is not None and cached[0] is tr and cached[1] == len(tr):
+            return cached[2]
         order: List[Hashable] = []
         seen = set()
-        for (src, _ev), (dst, _r) in self.transitions.items():
+        for (src, _ev), (dst, _r) in tr.items():
             for s in (src, dst):
                 if s not in seen:
                     seen.add(s)
                     order.append(s)
+        self.__dict__["_order_cache"] = (tr, len(tr), order)
         return order
 
     def _generate_state_indices(self):
@@ -83,7 +91,7 @@ class RewardMachine:
         raise ValueError(f"Index {rm_state_index} not present in RewardMachine.state_indices")
 
     def get_all_states(self):
-        return self._states_in_order()
+        return list(self._states_in_order())
 
     def numbers_state(self):
         return len(self._states_in_order())

@@ -122,17 +122,31 @@ def _office_task(exp, algo, stochastic=True):
                                      wall_penalty=-0.5, max_steps=200, seed=97)
 
 
+def _shaped_qrm():
+    import multiagent_rlrm_b200 as P
+
+    sc = P.scenario_config3(True)
+    sc.use_rsh, sc.rs_kind, sc.rs_alpha, sc.learning_rate = True, "distance", 5, 0.5
+    return sc
+
+
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg5_qrm_4agents", "cfg3_ql", "office_exp1_qrm", "office_exp3_qrm", "office_exp4_qrm_det",
-                                  "office_exp2_ql"])
+                                  "office_exp2_ql", "office_exp5_qrm", "office_exp6_qrm", "office_exp6_qrm_det", "office_chain12_qrm",
+                                  "fl_random_starts_qrm", "fl_shaping_qrm"])
 def test_generic_kernel_equals_specialised(name, cuda_device):
     """config.reserved bit 0 forces the generic train_kernel; it must agree bit-for-bit with the specialised kernels
-    (train_qrm4_kernel, train_qrmn_kernel<3 / 5 RM states>, train_ql_fast_kernel) — and both with the oracle."""
+    (train_qrm4_kernel, train_qrmn_kernel<3 / 5 RM states>, train_ql_fast_kernel, and train_qrm_block_kernel for machines with
+    more states / permuted state order / shaping / random starts) — and both with the oracle."""
     import multiagent_rlrm_b200 as P
     import oracle as O
 
-    if name.startswith("office"):
+    if name == "fl_shaping_qrm":
+        sc, n, t = _shaped_qrm(), 400, 1500
+    elif name.startswith("office_exp"):
         sc = {"office_exp1_qrm": lambda: _office_task("exp1", "qrm"), "office_exp3_qrm": lambda: _office_task("exp3", "qrm"),
-              "office_exp4_qrm_det": lambda: _office_task("exp4", "qrm", False), "office_exp2_ql": lambda: _office_task("exp2", "ql")}[name]()
+              "office_exp4_qrm_det": lambda: _office_task("exp4", "qrm", False), "office_exp2_ql": lambda: _office_task("exp2", "ql"),
+              "office_exp5_qrm": lambda: _office_task("exp5", "qrm"), "office_exp6_qrm": lambda: _office_task("exp6", "qrm"),
+              "office_exp6_qrm_det": lambda: _office_task("exp6", "qrm", False)}[name]()
         n, t = 300, 1500
     else:
         sc, n, t = _scenarios_medium()[name]
