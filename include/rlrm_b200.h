@@ -131,7 +131,8 @@ typedef struct rlrm_config {
   int32_t n_free_cells;        /* F */
   int32_t use_rsh;             /* QLearning.use_rsh: potential-based shaping R' = R + gamma*Phi(q') - Phi(q) (qlearning.py:51-66, 93-105) */
   int32_t n_actions;           /* 1..4 usable actions (exploration draws (w1*n_actions)>>32); tables are always 4 wide */
-  int32_t reserved;            /* bit 0: force the generic kernels (testing: generic vs specialised must agree) */
+  int32_t reserved;            /* testing switches (paths that must agree bit for bit): bit 0 forces the generic kernels, bit 1 forces the
+                                  shared learner's two-launches-per-iteration path instead of the persistent cooperative kernel */
   int32_t table_dtype;         /* RLRM_TABLE_F32 / RLRM_TABLE_F64: element type of rlrm_state_t.q / e / tr_eq */
 } rlrm_config_t;
 
@@ -324,7 +325,9 @@ int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_ce
  * proposals: Q[s,a] = proposal if one instance proposed, else (float)((double)acc_sum / acc_cnt * 2^-20). Sums are
  * integers, so the result does not depend on thread order or on how instances are spread over blocks/GPUs.
  * With a single instance this is exactly the per-instance learner (for reward machines whose counterfactual updates
- * do not read each other's writes, e.g. chains). rlrm_train runs two kernels per iteration in this mode.
+ * do not read each other's writes, e.g. chains). rlrm_train runs all n_iters iterations of this mode in ONE persistent
+ * cooperative launch (tables and proposal accumulators in shared memory, one grid barrier per iteration); with a trace
+ * buffer, learn = 0 or tables that do not fit in shared memory it falls back to two launches per iteration.
  * Inter-GPU merging (every K iterations) is the caller's step: average the replicas of `q` (dist.merge_replicas gathers
  * them over NCCL and sums in rank order, so the result does not depend on the collective's reduction order). */
 

@@ -44,7 +44,12 @@ struct rlrm_handle {
   int qrmb_smem;  // its dynamic shared memory: table blob + 16*nQ bytes per thread
   int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
   int shared_smem_bytes;
+  unsigned char* d_coop;  // shared learner, persistent path: three global accumulator sets (sum i64 | count i32 | last f32), zeroed
+  int coop_ok;            // cooperative launch is supported and the kernel attributes were set
   int num_sms;
+  cudaStream_t pipe_stream[2];  // rlrm_train_host: copy-in / copy-out streams of the chunk pipeline (created on first use)
+  cudaEvent_t pipe_event[3 * 8];
+  int pipe_ready;
   int f64;        // float64 tables (cfg.table_dtype == RLRM_TABLE_F64): generic kernels instantiated on double
   int max_smem;   // cudaDevAttrMaxSharedMemoryPerBlockOptin of the device
 };
@@ -289,6 +294,19 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
       if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(shared_propose_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
       if (e1 != cudaSuccess) h->shared_fast = 0;
     }
+    if (h->shared_fast) {  // persistent cooperative path
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+      cudaError_t e3 = coop ? cudaSuccess : cudaErrorNotSupported;
+      if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(shared_train_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(shared_train_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(shared_train_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(shared_train_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+      if (e3 == cudaSuccess) e3 = cudaMalloc(&h->d_coop, (size_t)3 * n_ent * 16);
+      if (e3 == cudaSuccess) e3 = cudaMemset(h->d_coop, 0, (size_t)3 * n_ent * 16);
+      h->coop_ok = e3 == cudaSuccess;
+      cudaGetLastError();
+    }
   }
   *out = h;
   return RLRM_OK;
@@ -298,6 +316,11 @@ extern "C" int rlrm_destroy(rlrm_handle_t* h) {
   if (!h) return RLRM_OK;
   cudaSetDevice(h->device);
   if (h->d_blob) cudaFree(h->d_blob);
+  if (h->d_coop) cudaFree(h->d_coop);
+  if (h->pipe_ready) {
+    for (int k = 0; k < 2; k++) cudaStreamDestroy(h->pipe_stream[k]);
+    for (int k = 0; k < 3 * 8; k++) cudaEventDestroy(h->pipe_event[k]);
+  }
   delete h;
   return RLRM_OK;
 }
@@ -622,6 +645,27 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
   if (h->kp.shared_q) {
     // synchronous iterations: one propose launch over all instances + one apply launch per lockstep iteration
     const size_t stride = (size_t)st->n_instances * h->kp.A;
+    if (h->shared_fast && h->coop_ok && !st->visits && learn && !trace && !(h->cfg.reserved & 2)) {
+      // persistent path: all n_iters iterations in one cooperative launch (see shared_train_kernel)
+      const long long threads = st->n_instances * h->kp.G;
+      long long want = (threads + SHARED_BLOCK - 1) / SHARED_BLOCK;
+      const unsigned grid = (unsigned)(want < h->num_sms ? want : h->num_sms);
+      KP kp = h->kp;
+      DState d = dstate(st);
+      unsigned long long tt = t0;
+      int ni = n_iters;
+      const size_t n_ent = (size_t)kp.A * (size_t)kp.S4;
+      unsigned long long* g_sum = reinterpret_cast<unsigned long long*>(h->d_coop);
+      int* g_cnt = reinterpret_cast<int*>(h->d_coop + 3 * n_ent * 8);
+      float* g_last = reinterpret_cast<float*>(h->d_coop + 3 * n_ent * 12);
+      void* args[] = {&kp, &d, &tt, &ni, &g_sum, &g_cnt, &g_last};
+      const void* fn;
+      if (kp.env_kind == RLRM_ENV_FROZEN_LAKE) fn = kp.algo == RLRM_ALGO_QRM ? (const void*)shared_train_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM> : (const void*)shared_train_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL>;
+      else fn = kp.algo == RLRM_ALGO_QRM ? (const void*)shared_train_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM> : (const void*)shared_train_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>;
+      CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SHARED_BLOCK), args, (size_t)h->shared_smem_bytes, s));
+      LAUNCH_CHECK(h);
+      return RLRM_OK;
+    }
     for (int it = 0; it < n_iters; it++) {
       uint32_t* tr = trace ? trace + (size_t)it * stride : nullptr;
       if (h->shared_fast && !st->visits) {
@@ -682,27 +726,95 @@ extern "C" int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st
   return RLRM_OK;
 }
 
+// rlrm_state_t restricted to instances [start, start + count): every per-slot / per-table array is offset, so a kernel launched
+// on the view with kp.instance_offset advanced by `start` computes exactly what the full launch computes for those instances
+// (instances never interact and the Philox counters are keyed on the global instance id).
+static rlrm_state_t sub_state(const rlrm_handle_t* h, const rlrm_state_t* st, long long start, long long count) {
+  rlrm_state_t v = *st;
+  const KP& kp = h->kp;
+  const size_t slots = (size_t)start * kp.A;
+  const size_t ent = kp.per_agent ? (size_t)start * (size_t)kp.sum4 : slots * (size_t)kp.S4;  // table entries before `start`
+  const size_t esz = h->f64 ? 8 : 4;
+  v.n_instances = count;
+  v.slot = st->slot + slots;
+  v.epsilon = st->epsilon + slots;
+  v.q = (char*)st->q + ent * esz;
+  if (st->e) v.e = (char*)st->e + ent * esz;
+  if (st->visits) v.visits = st->visits + ent;
+  if (st->ep_return) v.ep_return = st->ep_return + slots;
+  if (st->stats) v.stats = st->stats + slots;
+  if (st->tr_pos) v.tr_pos = st->tr_pos + slots * (size_t)kp.S4;
+  if (st->tr_idx) v.tr_idx = st->tr_idx + slots * (size_t)st->tr_cap;
+  if (st->tr_eq) v.tr_eq = (char*)st->tr_eq + slots * (size_t)st->tr_cap * 2 * esz;
+  if (st->tr_len) v.tr_len = st->tr_len + slots;
+  if (st->tr_work) v.tr_work = st->tr_work + slots;
+  return v;
+}
+
 extern "C" int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, int32_t n_iters, int32_t learn,
                                uint64_t* host_slot, double* host_epsilon, rlrm_stats_t* host_stats, void* stream) {
   int rc = check_state(h, st, true);
   if (rc) return rc;
+  if (host_stats && !st->stats) return fail(RLRM_ERR_ARG, "host_stats requested but state.stats is null");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)st->n_instances * h->kp.A;
-  if (host_slot) CUDA_TRY(cudaMemcpyAsync(st->slot, host_slot, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(st->epsilon, host_epsilon, n * sizeof(double), cudaMemcpyHostToDevice, s));
-  rc = rlrm_train(h, st, t0, n_iters, learn, nullptr, stream);
-  if (rc) return rc;
-  if (host_stats) {
-    if (!st->stats) return fail(RLRM_ERR_ARG, "host_stats requested but state.stats is null");
-    CUDA_TRY(cudaMemcpyAsync(host_stats, st->stats, n * sizeof(rlrm_stats_t), cudaMemcpyDeviceToHost, s));
+  const size_t bytes = n * ((host_slot ? 16 : 0) + (host_epsilon ? 16 : 0) + (host_stats ? sizeof(rlrm_stats_t) : 0));
+  // Independent instances and enough bytes to matter: split the instance range into chunks and pipeline them over two extra
+  // streams — chunk c's upload, chunk c-1's kernel and chunk c-2's download overlap. Results are bit-identical to the
+  // single launch (sub_state). The shared learner's iterations are synchronous over ALL instances, so it cannot be chunked.
+  // Every chunk must still fill the GPU on its own (>= 512 Ki slots), otherwise the chunk kernels would run one after the other
+  // at a fraction of the occupancy of the single launch.
+  int chunks = 1;
+  if (!h->kp.shared_q && n_iters > 0 && bytes >= (8u << 20)) {
+    const size_t fit = n / (512u * 1024u);
+    chunks = fit >= 8 ? 8 : (fit >= 2 ? (int)fit : 1);
   }
-  if (host_slot) CUDA_TRY(cudaMemcpyAsync(host_slot, st->slot, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-  if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(host_epsilon, st->epsilon, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (chunks == 1) {
+    if (host_slot) CUDA_TRY(cudaMemcpyAsync(st->slot, host_slot, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(st->epsilon, host_epsilon, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = rlrm_train(h, st, t0, n_iters, learn, nullptr, stream);
+    if (rc) return rc;
+    if (host_stats) CUDA_TRY(cudaMemcpyAsync(host_stats, st->stats, n * sizeof(rlrm_stats_t), cudaMemcpyDeviceToHost, s));
+    if (host_slot) CUDA_TRY(cudaMemcpyAsync(host_slot, st->slot, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(host_epsilon, st->epsilon, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return RLRM_OK;
+  }
+  if (!h->pipe_ready) {
+    for (int k = 0; k < 2; k++) CUDA_TRY(cudaStreamCreateWithFlags(&h->pipe_stream[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 3 * 8; k++) CUDA_TRY(cudaEventCreateWithFlags(&h->pipe_event[k], cudaEventDisableTiming));
+    h->pipe_ready = 1;
+  }
+  cudaStream_t up = h->pipe_stream[0], down = h->pipe_stream[1];
+  cudaEvent_t* ev = h->pipe_event;  // [c]: caller's stream reached this call; [8 + c]: chunk c uploaded; [16 + c]: chunk c computed
+  CUDA_TRY(cudaEventRecord(ev[0], s));
+  CUDA_TRY(cudaStreamWaitEvent(up, ev[0], 0));  // earlier work of the caller's stream may still use the state arrays
+  const unsigned base_offset = h->kp.instance_offset;
+  const long long per = (st->n_instances + chunks - 1) / chunks;
+  for (int c = 0; c < chunks; c++) {
+    const long long start = (long long)c * per, count = (start + per <= st->n_instances) ? per : st->n_instances - start;
+    if (count <= 0) break;
+    const rlrm_state_t v = sub_state(h, st, start, count);
+    const size_t off = (size_t)start * h->kp.A, m = (size_t)count * h->kp.A;
+    if (host_slot) CUDA_TRY(cudaMemcpyAsync(v.slot, host_slot + off, m * sizeof(uint64_t), cudaMemcpyHostToDevice, up));
+    if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(v.epsilon, host_epsilon + off, m * sizeof(double), cudaMemcpyHostToDevice, up));
+    CUDA_TRY(cudaEventRecord(ev[8 + c], up));
+    CUDA_TRY(cudaStreamWaitEvent(s, ev[8 + c], 0));
+    h->kp.instance_offset = base_offset + (unsigned)start;
+    rc = rlrm_train(h, &v, t0, n_iters, learn, nullptr, stream);
+    h->kp.instance_offset = base_offset;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ev[16 + c], s));
+    CUDA_TRY(cudaStreamWaitEvent(down, ev[16 + c], 0));
+    if (host_stats) CUDA_TRY(cudaMemcpyAsync(host_stats + off, v.stats, m * sizeof(rlrm_stats_t), cudaMemcpyDeviceToHost, down));
+    if (host_slot) CUDA_TRY(cudaMemcpyAsync(host_slot + off, v.slot, m * sizeof(uint64_t), cudaMemcpyDeviceToHost, down));
+    if (host_epsilon) CUDA_TRY(cudaMemcpyAsync(host_epsilon + off, v.epsilon, m * sizeof(double), cudaMemcpyDeviceToHost, down));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaStreamSynchronize(down));
   return RLRM_OK;
 }
-
 
 extern "C" int rlrm_iterate(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t, int32_t learn, uint32_t* record, double* reward,
                             void* stream) {

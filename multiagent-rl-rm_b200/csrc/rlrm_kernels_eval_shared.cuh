@@ -1,5 +1,7 @@
 // rlrm_kernels_eval_shared.cuh: greedy evaluation and the shared-learner kernels — part of the single translation unit csrc/rlrm_b200.cu (see its header comment).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "rlrm_kernels_train.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -181,6 +183,141 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_propose_kernel(KP p, D
         atomicAdd(reinterpret_cast<unsigned long long*>(st.acc_sum) + j, s_sum[j]);
         st.acc_last[j] = s_last[j];  // only read back when the GLOBAL count is 1, i.e. exactly one block wrote it
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared learner, persistent path: n_iters synchronous lockstep iterations in ONE cooperative launch (one block per SM). The
+// per-agent tables stay in shared memory for the whole launch; per iteration every block proposes into its shared-memory
+// accumulators, flushes the non-empty ones into a GLOBAL accumulator set with integer atomics, the grid synchronises ONCE,
+// and every block then folds the global sums into its own table copy (apply_shared_kernel's arithmetic, evaluated redundantly
+// by all blocks from the same integers => identical copies). Three global accumulator sets are used round-robin: set
+// it % 3 is filled in iteration it, read after that iteration's grid barrier, and cleared during iteration it + 1's read phase —
+// its next fill (it + 3) is separated from the clearing by the barrier of it + 2, so one barrier per iteration suffices.
+// Replaces 2 launches per iteration (shared_propose_kernel + apply_shared_kernel); results are bit-identical to them.
+// ------------------------------------------------------------------------------------------------
+template <int ENV, int ALGO>
+__global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DState st, unsigned long long t0, int n_iters,
+                                                                      unsigned long long* g_sum, int* g_cnt, float* g_last) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  Tab tb = stage_tables(p);
+  const int n_ent = p.A * (int)p.S4;
+  float* Qs = reinterpret_cast<float*>(smem_raw + p.blob_bytes);
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(Qs + n_ent);
+  int* s_cnt = reinterpret_cast<int*>(s_sum + n_ent);
+  float* s_last = reinterpret_cast<float*>(s_cnt + n_ent);
+  float* s_rmax = s_last + n_ent;
+  for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(st.q) + j);
+    reinterpret_cast<float4*>(Qs)[j] = v;
+    s_rmax[j] = row_max(v);
+  }
+  for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+    s_sum[j] = 0ull;
+    s_cnt[j] = 0;
+  }
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+  const long long total = st.N << p.g_shift;
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    // ---- propose: same per-slot code as shared_propose_kernel ----
+    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += (long long)gridDim.x * blockDim.x) {
+      const long long tid = b0 + threadIdx.x;
+      const long long i = tid >> p.g_shift;
+      const int a = (int)(tid & (p.G - 1));
+      const bool valid = (i < st.N) && (a < p.A);
+      const long long k = i * p.A + a;
+      bool term = true, trunc = true;
+      Slot s = {0, 0, 0, 0, 0};
+      double eps = 0.0;
+      Rec r;
+      r.reward = 0.0;
+      if (valid) {
+        s = unpack_slot(st.slot[k]);
+        eps = st.epsilon[k];
+        unsigned w[4];
+        RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+        float* Q = Qs + (size_t)a * (size_t)p.S4;
+        const float4 row = *reinterpret_cast<const float4*>(Q + (size_t)(s.cell * p.nQ + s.rm) * 4);
+        const int action = select_action(row, explore_threshold(eps), w, false, p.n_actions);
+        const unsigned before = s.cell;
+        const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+        agent_step<ENV>(p, tb, s, action, w[3], true, r);
+        const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+        const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+        Acc acc = {reinterpret_cast<long long*>(s_sum) + (size_t)a * (size_t)p.S4, s_cnt + (size_t)a * (size_t)p.S4,
+                   s_last + (size_t)a * (size_t)p.S4, true, s_rmax + (size_t)a * (size_t)(p.S4 / 4)};
+        agent_update<ALGO, float>(p, tb, Q, nullptr, obs, action, term_arg, r, acc);
+        term = r.term;
+        trunc = r.trunc;
+        if (r.reward != 0.0 && st.ep_return) st.ep_return[k] = __dadd_rn(st.ep_return[k], r.reward);
+      }
+      const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+      const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+      if (valid) {
+        if (over) {
+          const double ret = st.ep_return ? st.ep_return[k] : 0.0;
+          if (st.stats) {
+            rlrm_stats_t z = st.stats[k];
+            z.episodes++;
+            z.active_steps += s.steps;
+            z.successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+            z.last_return = __double2float_rn(ret);
+            z.return_sum = __dadd_rn(z.return_sum, ret);
+            z.last_length = s.time;
+            st.stats[k] = z;
+          }
+          if (st.ep_return) st.ep_return[k] = 0.0;
+          reset_slot(p, tb, i, a, t + 1, s, eps);
+          st.epsilon[k] = eps;
+        }
+        st.slot[k] = pack_slot(s);
+      }
+    }
+    __syncthreads();
+    // ---- flush this block's proposals into global accumulator set `it % 3` (integer atomics: order-independent) ----
+    const size_t cur = (size_t)(it % 3) * (size_t)n_ent, prev = (size_t)((it + 2) % 3) * (size_t)n_ent;
+    for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+      const int c = s_cnt[j];
+      if (c) {
+        atomicAdd(g_cnt + cur + j, c);
+        atomicAdd(g_sum + cur + j, s_sum[j]);
+        g_last[cur + j] = s_last[j];  // only read back when the GLOBAL count is 1, i.e. exactly one block wrote it
+        s_cnt[j] = 0;
+        s_sum[j] = 0ull;
+      }
+    }
+    grid.sync();
+    // ---- apply: fold the global sums into this block's table copy (apply_shared_kernel's arithmetic) ----
+    for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
+      const int c = __ldcg(g_cnt + cur + j);
+      if (c == 1) Qs[j] = __ldcg(g_last + cur + j);
+      else if (c > 1) Qs[j] = __double2float_rn(__dmul_rn(__ddiv_rn((double)(long long)__ldcg(g_sum + cur + j), (double)c), 9.5367431640625e-07));
+    }
+    // the set filled in the PREVIOUS iteration has been read by every block (before this iteration's barrier): clear it
+    if (it > 0)
+      for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_ent; j += (long long)gridDim.x * blockDim.x) {
+        g_cnt[prev + j] = 0;
+        g_sum[prev + j] = 0ull;
+      }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) s_rmax[j] = row_max(reinterpret_cast<const float4*>(Qs)[j]);
+    __syncthreads();
+  }
+  // leave the tables in global memory and every accumulator set clean
+  grid.sync();
+  if (blockIdx.x == 0)
+    for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) reinterpret_cast<float4*>(st.q)[j] = reinterpret_cast<const float4*>(Qs)[j];
+  if (n_iters > 0) {
+    const size_t last = (size_t)((n_iters - 1) % 3) * (size_t)n_ent;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_ent; j += (long long)gridDim.x * blockDim.x) {
+      g_cnt[last + j] = 0;
+      g_sum[last + j] = 0ull;
     }
   }
 }

@@ -39,6 +39,40 @@ def loop(rm_env, env, agents, fl, seed, seconds, max_iters=10**9):
             "active_agent_steps_per_s": active / dt, "us_per_iteration": dt / max(iters, 1) * 1e6}
 
 
+def breakdown(rm_env, env, agents, fl, seed, n_iters=4000):
+    """Where one driver-loop iteration goes: wall time inside select_action / rm_env.step / update_policy / the rest."""
+    acc = {"select_action": 0.0, "step": 0.0, "update_policy": 0.0}
+    pc = time.perf_counter
+    iters, t_all = 0, pc()
+    while iters < n_iters:
+        states, _ = rm_env.reset(seed)
+        if not fl:
+            states = copy.deepcopy(states)
+        while True:
+            t0 = pc()
+            actions = {ag.name: ag.select_action(rm_env.env.get_state(ag)) for ag in rm_env.agents}
+            t1 = pc()
+            new_states, rewards, term, trunc, infos = rm_env.step(actions)
+            t2 = pc()
+            for ag in rm_env.agents:
+                ta = (term[ag.name] or trunc[ag.name]) if fl else term[ag.name]
+                ag.update_policy(state=states[ag.name], action=actions[ag.name], reward=rewards[ag.name],
+                                 next_state=new_states[ag.name], terminated=ta, infos=infos[ag.name])
+            t3 = pc()
+            acc["select_action"] += t1 - t0
+            acc["step"] += t2 - t1
+            acc["update_policy"] += t3 - t2
+            states = copy.deepcopy(new_states)
+            iters += 1
+            if all(term.values()) or all(trunc.values()):
+                break
+    total = pc() - t_all
+    out = {k: v / iters * 1e6 for k, v in acc.items()}
+    out["other (reset, deepcopy, loop)"] = (total - sum(acc.values())) / iters * 1e6
+    out["total_us_per_iteration"] = total / iters * 1e6
+    return out
+
+
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 5.0
     out = {}
@@ -50,6 +84,8 @@ def main():
         rm_env, env, agents = build_b200(d)
         loop(rm_env, env, agents, fl, d["seed"], 1.0)  # warm
         res = {"b200_dropin": loop(rm_env, env, agents, fl, d["seed"], seconds)}
+        if "--breakdown" in sys.argv:
+            res["b200_dropin_breakdown_us"] = breakdown(rm_env, env, agents, fl, d["seed"])
         if "--profile" in sys.argv and name == "cfg1":
             import cProfile
             import pstats
@@ -67,6 +103,8 @@ def main():
                 r_env, r_e, r_agents = H.build_reference(d, np.float64)
                 loop(r_env, r_e, r_agents, fl, d["seed"], 0.5)
                 res["python_reference"] = loop(r_env, r_e, r_agents, fl, d["seed"], seconds)
+                if "--breakdown" in sys.argv:
+                    res["python_reference_breakdown_us"] = breakdown(r_env, r_e, r_agents, fl, d["seed"])
         except Exception as exc:  # the reference is optional here
             res["python_reference"] = {"unavailable": repr(exc)}
         out[name] = res

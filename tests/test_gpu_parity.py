@@ -262,6 +262,47 @@ def test_shared_learner_matches_oracle(cuda_device):
     assert int(eng.acc_cnt.abs().sum()) == 0 and int(eng.acc_sum.abs().sum()) == 0  # accumulators are left clean
 
 
+@pytest.mark.parametrize("n,chunks", [(1, (1, 2, 3, 7)), (37, (5, 1, 64)), (3000, (160,)), (200000, (3, 40))])
+def test_shared_learner_persistent_kernel_equals_two_launch_path_and_oracle(n, chunks, cuda_device):
+    """rlrm_train runs the shared learner's iterations in one cooperative launch (shared_train_kernel: tables in shared
+    memory for the whole launch, three global accumulator sets used round-robin, one grid barrier per iteration). It must
+    equal the two-launches-per-iteration path (config.reserved bit 1) and the oracle for any launch length and grid size."""
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    sc = P.scenario_config5(shared=True)
+    c_coop, c_two = P.compile_scenario(sc), P.compile_scenario(sc)
+    c_two.config.reserved = 2
+    a, b = _engine(c_coop, n), _engine(c_two, n)
+    o = O.Oracle(c_coop, n, "f32") if n <= 3000 else None
+    a.reset(); b.reset()
+    if o:
+        o.reset()
+    t0 = 0
+    for chunk in chunks:
+        a.train(chunk); b.train(chunk)
+        if o:
+            o.train(t0, chunk)
+        t0 += chunk
+        assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy()), f"Q after {t0} iterations"
+        assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
+    assert a.launches == len(chunks) + 1 and b.launches > a.launches       # reset + ONE launch per train call
+    assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy()) and np.array_equal(a.epsilon.cpu().numpy(), b.epsilon.cpu().numpy())
+    assert np.array_equal(a.ep_return.cpu().numpy(), b.ep_return.cpu().numpy())
+    assert int(a.acc_cnt.abs().sum()) == 0 and int(a.acc_sum.abs().sum()) == 0
+    if o:
+        _compare_with_oracle(a, o, "persistent shared learner")
+    # the OfficeWorld shared learner (plain QL on the 5-state A->C->B->D task) takes the same path
+    sc = P.scenario_config2(True)
+    sc.shared_q, sc.starts = True, [(2, 7), (6, 3)]
+    c1, c2 = P.compile_scenario(sc), P.compile_scenario(sc)
+    c2.config.reserved = 2
+    a, b = _engine(c1, min(n, 5000)), _engine(c2, min(n, 5000))
+    a.reset(); b.reset()
+    a.train(90); b.train(90)
+    assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy()) and np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
+
+
 def test_shared_learner_with_one_instance_is_the_reference_learner(cuda_device):
     """Degenerate tie to the reference: N = 1 shared == per-instance tables (which equal the reference trace)."""
     import multiagent_rlrm_b200 as P

@@ -153,6 +153,55 @@ def test_checkpoint_resume_is_bit_identical(name, cuda_device, tmp_path):
         Engine(c, 95, **kw).load_state_dict(first.state_dict())
 
 
+@pytest.mark.parametrize("name,n,kw", [("cfg5_tables", 300000, {}), ("cfg4_sparse", 270000, {"qlambda_sparse": True}),
+                                        ("cfg3_f64", 600000, {}), ("fl_per_agent", 400000, {})])
+def test_pipelined_train_host_equals_train(name, n, kw, cuda_device):
+    """Above 1 Mi slots rlrm_train_host splits the instance range into chunks and pipelines upload / kernel / download over two
+    extra streams (rlrm_b200.cu sub_state): every array view, the Philox instance offset and the host buffers must line up so
+    that the result is bit-identical to one resident launch — for float32 / float64 tables, sparse trace lists and per-agent
+    table sections."""
+    import torch
+
+    from multiagent_rlrm_b200.engine import Engine
+
+    free, _total = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~50 GB of free device memory")
+    if name == "cfg5_tables":
+        sc = P.scenario_config5(False)
+    elif name == "cfg4_sparse":
+        sc = P.scenario_config4()
+    elif name == "cfg3_f64":
+        sc = P.scenario_config3(False)
+        sc.table_dtype = "f64"
+    else:
+        g = P.frozen_lake_grid("map1").goals
+        sc = P.scenario_config3(True)
+        sc.starts, sc.detector_positions = [(5, 0), (0, 0), (9, 9)], sorted(g.values())
+        sc.rm_transitions_per_agent = [P.tables.frozen_lake_abc_transitions(), [("p0", g["C"], "p1", 3.0), ("p1", g["A"], "p2", 7.0)],
+                                       [("w0", g["B"], "w1", 1.0), ("w1", g["A"], "w2", 1.0), ("w2", g["C"], "w3", 1.0)]]
+    c = P.compile_scenario(sc, instance_offset=12345)
+    resident, hosted = Engine(c, n, **kw), Engine(c, n, **kw)
+    resident.reset(); hosted.reset()
+    n_slots = n * c.n_agents
+    assert n_slots >= 2 * 512 * 1024  # at least two chunks
+    host_slot = torch.empty(n_slots, dtype=torch.int64).pin_memory()
+    host_eps = torch.empty(n_slots, dtype=torch.float64).pin_memory()
+    host_stats = torch.empty((n_slots, 32), dtype=torch.uint8).pin_memory()
+    host_slot.copy_(hosted.slot); host_eps.copy_(hosted.epsilon)
+    for chunk in (3, 40):
+        resident.train(chunk)
+        hosted.train_host(chunk, host_stats, host_slot, host_eps)
+    resident.sync_tables(); hosted.sync_tables()
+    assert torch.equal(hosted.slot, resident.slot) and torch.equal(hosted.epsilon, resident.epsilon)
+    assert torch.equal(hosted.q, resident.q) and torch.equal(hosted.stats, resident.stats) and torch.equal(hosted.ep_return, resident.ep_return)
+    assert torch.equal(host_slot, resident.slot.cpu()) and torch.equal(host_eps, resident.epsilon.cpu()) and torch.equal(host_stats, resident.stats.cpu())
+    if hosted.sparse:
+        assert torch.equal(hosted.tr_len, resident.tr_len) and torch.equal(hosted.tr_work, resident.tr_work)
+    del resident, hosted
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg2_ql", "cfg4_sparse"])
 def test_train_host_equals_train(name, cuda_device):
     """rlrm_train_host (the end-to-end entry point bench.py's `e2e` times: host slot / epsilon in, fused iterations, host slot /
