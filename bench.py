@@ -82,6 +82,11 @@ WORKLOADS = {
                     "(2,7),(6,3), slip hp=.8, QLearning lr=.1 gamma=.9 eps=.1 init=2 use_qrm=True, per-instance Q tables",
                     "office_main --experiment exp6 batched (not a BASELINE configuration; the largest built-in machine)",
                     65536, 1024, 2 * 10 * 16 + 4 * 9, "train_qrm_block_kernel<OfficeWorld,10>"),
+    "ow12_shared": ("OfficeWorld map1 (12x9), 2 agents at (2,7),(6,3), slip hp=.8, synthetic 12-state completed chain RM, QLearning lr=.1 "
+                    "gamma=.9 eps=.1 init=2 use_qrm=True, ONE table per agent index per GPU (shared learner; 10,368 entries: 218 KB of "
+                    "tables + accumulators in shared memory)",
+                    "configs[3]'s environment and machine with configs[4]'s shared learner (not a BASELINE configuration)",
+                    262144, 64, 2 * 12 * 16 + 4 * 11, "shared_train_kernel<OfficeWorld,QRM> (persistent cooperative; shared-memory wavefront bound)"),
     "cfg5_tables": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, per-instance Q tables",
                     "configs[4] HBM-bound companion: 1M FrozenLake instances x 4 agents, per-instance tables",
                     1048576, 256, 140, "train_qrm4_kernel<FrozenLake>"),
@@ -110,7 +115,12 @@ def scenario(workload):
                                          stochastic=True, high_prob=0.8, epsilon_start=0.1, epsilon_end=0.1, epsilon_decay=1.0,
                                          q_init=2.0, seed=1234)
 
-    return {"cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
+    def ow12_shared():
+        sc = cfg4_qrm()
+        sc.starts, sc.shared_q = sc.starts[:1] + [(6, 3)], True
+        return sc
+
+    return {"ow12_shared": ow12_shared, "cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
             "cfg2_batch": lambda: cfg2(False), "cfg2_batch_qrm": lambda: cfg2(True),
             "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg4_qrm": cfg4_qrm, "ow_exp6_qrm": exp6, "cfg5_tables": lambda: P.scenario_config5(False),
             "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
@@ -308,6 +318,7 @@ BOUND = {
     "ow_exp6_qrm": "latency on the block fetch after a move, then shared-memory wavefronts",
     "cfg5_tables": "issue/latency",
     "cfg5_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
+    "ow12_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
 }
 
 

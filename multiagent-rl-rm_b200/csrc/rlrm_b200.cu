@@ -132,8 +132,6 @@ static int validate_tables(const rlrm_config_t* cfg, const rlrm_tables_t* tb) {
           cfg->agent_rm_final[a] >= cfg->agent_n_rm_states[a])
         return fail(RLRM_ERR_ARG, "per-agent reward machine sizes out of range");
     }
-  if (cfg->per_agent_rm && (cfg->algo == RLRM_ALGO_QLAMBDA || (cfg->use_rsh && tb->phi)))
-    return fail(RLRM_ERR_UNSUPPORTED, "per-agent reward machines are supported for QL / QRM without shaping");
   if (cfg->max_steps < 0 || cfg->max_steps > 65534) return fail(RLRM_ERR_ARG, "max_steps must be in 0..65534 (16-bit step counters)");
   return RLRM_OK;
 }
@@ -197,6 +195,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
   kp.per_agent = cfg->per_agent_rm ? 1 : 0;
   kp.nd = kp.nQ * (kp.nEv + 1);
+  kp.phi_row = kp.nQ;
   kp.sum4 = 0;
   for (int a = 0; a < kp.A; a++) {
     kp.a_nQ[a] = kp.per_agent ? cfg->agent_n_rm_states[a] : kp.nQ;
@@ -219,7 +218,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   const int sec = kp.per_agent ? kp.A : 1;  // machine-dependent tables have one section per agent
   const int nd = kp.nQ * (kp.nEv + 1) * sec;
   int off = 0;
-  kp.off_phi = off; off = align16(off + 2 * RLRM_MAX_RM_STATES * 8);
+  kp.off_phi = off; off = align16(off + sec * 2 * RLRM_MAX_RM_STATES * 8);
   kp.off_rq = off; off = align16(off + nd * 8);
   kp.off_rcf = off; off = align16(off + nd * 8);
   kp.off_next = off; off = align16(off + ncell * 4 * 2);
@@ -237,7 +236,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   unsigned char* host = new (std::nothrow) unsigned char[off];
   if (!host) { delete h; return fail(RLRM_ERR_ARG, "out of host memory"); }
   memset(host, 0, off);
-  if (tb->phi) memcpy(host + kp.off_phi, tb->phi, (size_t)kp.nQ * 2 * 8);
+  if (tb->phi) memcpy(host + kp.off_phi, tb->phi, (size_t)sec * kp.nQ * 2 * 8);
   memcpy(host + kp.off_rq, tb->rq, (size_t)nd * 8);
   memcpy(host + kp.off_rcf, tb->rcf, (size_t)nd * 8);
   memcpy(host + kp.off_next, tb->next_cell, (size_t)ncell * 8);
@@ -282,7 +281,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     const long long n_ent = (long long)kp.A * kp.S4;
     const long long need = (long long)off + n_ent * 21;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry + row max 4 B per 4 entries
     h->shared_smem_bytes = (int)need;
-    h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 200 * 1024 &&
+    h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 227 * 1024 &&
                       !(cfg->reserved & 1));
     if (need > h->max_smem) h->shared_fast = 0;
     if (h->shared_fast) {
@@ -398,7 +397,7 @@ extern "C" int rlrm_reset_at(rlrm_handle_t* h, const rlrm_state_t* st, const uin
   reset_kernel<<<blocks_for(n, 256), 256, h->smem_bytes, s>>>(h->kp, dstate(st), mask, t);
   LAUNCH_CHECK(h);
   if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->e) {
-    RLRM_BY_T(h, clear_traces_kernel<T><<<blocks_for(n * (h->kp.S4 / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask));
+    RLRM_BY_T(h, clear_traces_kernel<T><<<blocks_for(st->n_instances * ((h->kp.per_agent ? h->kp.sum4 : (long long)h->kp.A * h->kp.S4) / 4), 256), 256, 0, s>>>(h->kp, dstate(st), mask));
     LAUNCH_CHECK(h);
   } else if (h->cfg.algo == RLRM_ALGO_QLAMBDA && st->tr_pos && st->q) {
     RLRM_BY_T(h, qlambda_sparse_reset_kernel<T><<<blocks_for(n * 32, 256), 256, 0, s>>>(h->kp, dstate(st), mask));

@@ -28,6 +28,7 @@ struct KP {
   int per_agent, a_nQ[RLRM_MAX_AGENTS], a_final[RLRM_MAX_AGENTS], a_nqrm[RLRM_MAX_AGENTS];
   long long a_prefix4[RLRM_MAX_AGENTS], sum4;  // float offset of agent a's table inside one instance, floats per instance
   int nd;                                       // nQmax * (nEv + 1): one agent's delta / rq / rcf section
+  int phi_row;                                  // nQmax: row stride of phi ([2][nQmax] per machine)
   unsigned seed_lo, seed_hi, instance_offset, n_actions;
   unsigned rk[20];  // Philox round keys: rk[2r] = seed_lo + r*0x9E3779B9, rk[2r+1] = seed_hi + r*0xBB67AE85
   long long S4;  // W*H*nQ*4 floats per table
@@ -408,7 +409,7 @@ __device__ __forceinline__ void agent_update(const KP& p, const Tab& tb, T* Q, u
     }
   } else {
     double rew = r.reward;
-    if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.nQ + r.q]), tb.phi[p.nQ + r.prev_q]));  // qlearning.py:51-66
+    if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.phi_row + r.q]), tb.phi[p.phi_row + r.prev_q]));  // qlearning.py:51-66
     update_q(p, Q, V, obs_cell * p.nQ + r.prev_q, action, rew, r.cell * p.nQ + r.q, term_arg, acc);
   }
 }
@@ -464,6 +465,7 @@ __device__ __forceinline__ void agent_view(const KP& p_in, KP& p, Tab& tb, int a
   tb.rq += (size_t)a * p_in.nd;
   tb.rcf += (size_t)a * p_in.nd;
   tb.qrm_states += (size_t)a * p_in.nQ;
+  tb.phi += (size_t)a * 2 * p_in.nQ;
 }
 __device__ __forceinline__ Acc make_acc(const KP& p, const DState& st, size_t base) {
   Acc acc = {nullptr, nullptr, nullptr, false, nullptr};

@@ -23,11 +23,10 @@ __global__ void __launch_bounds__(256) reset_kernel(KP p, DState st, const unsig
 // Q(lambda): reset_e_table for the masked instances (ma_frozen_lake.py:80-81 ; ma_office.py:101-102)
 template <typename T>
 __global__ void __launch_bounds__(256) clear_traces_kernel(KP p, DState st, const unsigned char* mask) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 of one slot's table
-  const long long per = p.S4 / 4;
-  if (g >= st.N * p.A * per) return;
-  const long long slot = g / per;
-  if (mask && !mask[slot / p.A]) return;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one row (4 entries) of one instance's tables
+  const long long per_inst = (p.per_agent ? p.sum4 : (long long)p.A * p.S4) / 4;
+  if (g >= st.N * per_inst) return;
+  if (mask && !mask[g / per_inst]) return;
   reinterpret_cast<typename RT<T>::row_t*>(st.e)[g] = RT<T>::zero_row();
 }
 
@@ -298,12 +297,17 @@ __device__ __forceinline__ void qlambda_sweep(const KP& p, T* Q, T* E, unsigned 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) update_qlambda_kernel(KP p, DState st, const unsigned short* obs_cell,
+__global__ void __launch_bounds__(256) update_qlambda_kernel(KP p_in, DState st, const unsigned short* obs_cell,
                                                             const unsigned char* actions, const unsigned char* term_arg, DOut o) {
+  KP p = p_in;
   const long long k = blockIdx.x;
   const long long i = k / p.A;
   const int a = (int)(k - i * p.A);
-  const size_t base = table_base(p, i, a);
+  const size_t base = table_base(p_in, i, a);
+  if (p_in.per_agent) {  // agent a's machine: its own state count and table size
+    p.nQ = p_in.a_nQ[a];
+    p.S4 = (long long)p_in.ncell * p.nQ * 4;
+  }
   // caller memory: clamp what indexes a table
   const unsigned cmax = (unsigned)p.ncell - 1u, qmax = (unsigned)p.nQ - 1u;
   const unsigned s_idx = min((unsigned)obs_cell[k], cmax) * p.nQ + min((unsigned)o.prev_q[k], qmax);

@@ -226,7 +226,21 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
   for (int it = 0; it < n_iters; it++) {
     const unsigned long long t = t0 + (unsigned long long)it;
     // ---- propose: same per-slot code as shared_propose_kernel ----
-    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += (long long)gridDim.x * blockDim.x) {
+    // the slot word / epsilon of the NEXT slot this thread handles are fetched while the current one is processed (the
+    // streamed state is the only HBM traffic of this kernel; unprefetched, its latency was the top stall: ncu source page)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long w_next = 0ull;
+    double eps_next = 0.0;
+    {
+      const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+      const long long i = tid >> p.g_shift;
+      const int a = (int)(tid & (p.G - 1));
+      if (tid < total && i < st.N && a < p.A) {
+        w_next = st.slot[i * p.A + a];
+        eps_next = st.epsilon[i * p.A + a];
+      }
+    }
+    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += stride) {
       const long long tid = b0 + threadIdx.x;
       const long long i = tid >> p.g_shift;
       const int a = (int)(tid & (p.G - 1));
@@ -237,9 +251,19 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
       double eps = 0.0;
       Rec r;
       r.reward = 0.0;
+      const unsigned long long w_cur = w_next;
+      const double eps_cur = eps_next;
+      {
+        const long long tn = tid + stride, in = tn >> p.g_shift;
+        const int an = (int)(tn & (p.G - 1));
+        if (b0 + stride < total && in < st.N && an < p.A) {
+          w_next = st.slot[in * p.A + an];
+          eps_next = st.epsilon[in * p.A + an];
+        }
+      }
       if (valid) {
-        s = unpack_slot(st.slot[k]);
-        eps = st.epsilon[k];
+        s = unpack_slot(w_cur);
+        eps = eps_cur;
         unsigned w[4];
         RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
         float* Q = Qs + (size_t)a * (size_t)p.S4;

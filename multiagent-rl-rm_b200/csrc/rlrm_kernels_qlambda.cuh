@@ -4,20 +4,22 @@
 #include "rlrm_kernels_train.cuh"
 
 template <int ENV, typename T>
-__global__ void __launch_bounds__(256) train_qlambda_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+__global__ void __launch_bounds__(256) train_qlambda_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                            unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
   __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
   const long long i = blockIdx.x;
   const int a = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long k = i * p.A + a;
+  if (p_in.per_agent) agent_view(p_in, p, tb, a);  // this warp's agent has its own machine: nQ, final state, table size
   Slot s = unpack_slot(st.slot[k]);
   double eps = st.epsilon[k];
   double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
-  const size_t base = table_base(p, i, a);
+  const size_t base = table_base(p_in, i, a);
   T* Q = tab<T>(st.q) + base;
   T* E = tab<T>(st.e) + base;
   unsigned* V = st.visits ? st.visits + base : nullptr;  // QLearningLambda counts visits on every update (qlearning_lambda.py:44)
@@ -160,12 +162,13 @@ __device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigne
 // instruction issue, not by HBM. Episode-over detection is two warp ballots; no shared memory, no block barrier.
 #define QLS_BLOCK 128
 template <int ENV, typename T>
-__global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+__global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                                         unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
   typedef typename R::pair_t pair_t;
-  Tab tb = stage_tables(p);
+  KP p = p_in;
+  Tab tb = stage_tables(p_in);
   const long long i = (long long)blockIdx.x * (QLS_BLOCK / 32) + (threadIdx.x >> 5);
   if (i >= st.N) return;  // whole warps leave; nothing below synchronises across warps
   const unsigned FULL = 0xFFFFFFFFu;
@@ -175,12 +178,13 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p, D
   const int gl = lane - a * LG;    // lane within the agent's group
   const bool valid = a < p.A;
   const long long k = i * p.A + (valid ? a : 0);
+  if (p_in.per_agent) agent_view(p_in, p, tb, valid ? a : 0);  // this lane group's agent has its own machine
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
-  T* Q = tab<T>(st.q) + table_base(p, i, valid ? a : 0);
-  unsigned* V = st.visits ? st.visits + table_base(p, i, valid ? a : 0) : nullptr;
+  T* Q = tab<T>(st.q) + table_base(p_in, i, valid ? a : 0);
+  unsigned* V = st.visits ? st.visits + table_base(p_in, i, valid ? a : 0) : nullptr;
   TraceList<T> L;
-  L.pos = st.tr_pos + (size_t)k * (size_t)p.S4;
+  L.pos = st.tr_pos + (size_t)k * (size_t)p_in.S4;  // list arrays are strided by the LARGEST table (per-agent machines)
   L.idx = st.tr_idx + (size_t)k * (size_t)st.tr_cap;
   L.eq = pairs<T>(st.tr_eq) + (size_t)k * (size_t)st.tr_cap;
   unsigned len = 0;
@@ -334,14 +338,14 @@ __global__ void __launch_bounds__(256) qlambda_materialize_kernel(KP p, DState s
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= st.N * p.A) return;
-  T* Q = tab<T>(st.q) + (size_t)warp * (size_t)p.S4;
+  T* Q = tab<T>(st.q) + table_base(p, warp / p.A, (int)(warp % p.A));
   const unsigned short* idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
   const typename RT<T>::pair_t* leq = pairs<T>(st.tr_eq) + (size_t)warp * (size_t)st.tr_cap;
   const unsigned len = st.tr_len[warp];
   for (unsigned j = lane; j < len; j += 32) {
     const typename RT<T>::pair_t eq = leq[j];
     Q[idx[j]] = eq.y;
-    if (e_dense) e_dense[(size_t)warp * (size_t)p.S4 + idx[j]] = eq.x;
+    if (e_dense) e_dense[table_base(p, warp / p.A, (int)(warp % p.A)) + idx[j]] = eq.x;
   }
 }
 
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(256) qlambda_sparse_reset_kernel(KP p, DState 
   L.pos = st.tr_pos + (size_t)warp * (size_t)p.S4;
   L.idx = st.tr_idx + (size_t)warp * (size_t)st.tr_cap;
   L.eq = pairs<T>(st.tr_eq) + (size_t)warp * (size_t)st.tr_cap;
-  trace_flush<T>(tab<T>(st.q) + (size_t)warp * (size_t)p.S4, L, st.tr_len[warp], lane);
+  trace_flush<T>(tab<T>(st.q) + table_base(p, warp / p.A, (int)(warp % p.A)), L, st.tr_len[warp], lane);
   __syncwarp();
   if (lane == 0) st.tr_len[warp] = 0;
 }

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, sizeof(T) == 4 ? 7 : 5) train_ker
           const T cur = (sidx == row_idx) ? get_component(row, action)
                                                : ((sidx == snidx) ? get_component(nrow, action) : Q[(size_t)sidx * 4 + action]);
           double rew = r.reward;
-          if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.nQ + r.q]), tb.phi[p.nQ + r.prev_q]));
+          if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.phi_row + r.q]), tb.phi[p.phi_row + r.prev_q]));
           const T mf = R::mul(term_arg ? (T)0 : (T)1, row_max(nrow));
           const T inner = R::add(R::cvt(rew), R::mul(R::gamma(p), mf));
           const T out = R::add(R::mul(R::one_minus_lr(p), cur), R::mul(R::lr(p), inner));

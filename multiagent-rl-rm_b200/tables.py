@@ -359,8 +359,17 @@ def compile_scenario(sc: Scenario, grid: Optional[GridSpec] = None, rm: Optional
         cfg.per_agent_rm, cfg.n_rm_states, cfg.n_events = 1, nq_max, n_ev
         cfg.n_qrm_states, cfg.rm_final = max(len(p["qrm_states"]) for p in parts), parts[0]["final"]
         t = dict(t, label=label, delta=delta, rq=rqa, rcf=rcfa, qrm_states=qrm, events=parts[0]["events"])
-        if phi is not None:
-            raise NotImplementedError("reward shaping with per-agent reward machines")
+        if phi is not None:  # every agent's machine carries its own potentials: one [2][nQmax] section per agent
+            phi = np.zeros((A, 2, nq_max), dtype=np.float64)
+            for a, m in enumerate(rms):
+                if getattr(m, "potentials", None) is None:
+                    if sc.rs_kind == "distance":
+                        m.add_distance_reward_shaping(sc.gamma, sc.rs_gamma, sc.rs_alpha)
+                    else:
+                        m.add_reward_shaping(sc.gamma, sc.rs_gamma)
+                for state, idx in m.state_indices.items():
+                    phi[a, 0, idx] = m.potentials.get(state, 0)
+                    phi[a, 1, idx] = m.potentials.get(idx, 0)
     start_cell = np.array([y * W + x for (x, y) in sc.starts], dtype=np.uint16)
     free_cells = None
     if sc.random_start_positions:

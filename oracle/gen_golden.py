@@ -74,6 +74,20 @@ def scenarios():
         sc.detector_positions = sorted(gl.values())
         sc.rm_transitions_per_agent = [frozen_lake_abc_transitions(), other, third]
         S[f"fl_per_agent_rms_{algo}"] = (sc, 2, 700, "f32", 1)
+    import copy
+
+    # agents with different machines under Q(lambda) and under potential-based shaping (frozen_lake_main.py allows
+    # --rm-spec-a1 / --rm-spec-a2 with any learner, :97-98, 228-252)
+    sc = copy.deepcopy(S["fl_per_agent_rms_ql"][0])
+    sc.algo, sc.lambd, sc.learning_rate, sc.q_init, sc.seed = "qlambda", 0.8, 0.2, 0.0, 63
+    S["fl_per_agent_rms_qlambda"] = (sc, 2, 500, "f32", 1)
+    S["fl_per_agent_rms_qlambda_f64"] = (sc, 1, 500, "f64", 1)
+    sc = copy.deepcopy(S["fl_per_agent_rms_qrm"][0])
+    sc.use_rsh, sc.rs_kind, sc.learning_rate, sc.seed = True, "vi", 0.5, 64
+    S["fl_per_agent_rms_shaping_qrm"] = (sc, 2, 700, "f32", 1)
+    sc = copy.deepcopy(S["fl_per_agent_rms_ql"][0])
+    sc.use_rsh, sc.rs_kind, sc.rs_alpha, sc.seed = True, "distance", 7, 65
+    S["fl_per_agent_rms_shaping_ql"] = (sc, 2, 600, "f32", 1)
 
     S["cfg5_fl_4agents_qrm"] = (P.scenario_config5(False), 2, 500, "f32", 1)
 

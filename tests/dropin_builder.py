@@ -46,7 +46,10 @@ def build_b200(sc, table_dtype=None):
         ag.set_reward_machine(rm)
         env.add_agent(ag)
         n_states = env.grid_width * env.grid_height * rm.numbers_state()
-        common = dict(state_space_size=n_states, action_space_size=4, learning_rate=sc["learning_rate"], gamma=sc["gamma"],
+        import numpy as np
+
+        common = dict(table_dtype="f64" if table_dtype is np.float64 else "f32",
+                      state_space_size=n_states, action_space_size=4, learning_rate=sc["learning_rate"], gamma=sc["gamma"],
                       action_selection="greedy", epsilon_start=sc["epsilon_start"], epsilon_end=sc["epsilon_end"],
                       epsilon_decay=sc["epsilon_decay"])
         if sc["algo"] == "qlambda":

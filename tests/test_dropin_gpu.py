@@ -16,7 +16,11 @@ DROPIN_CASES = [
     ("ow_terminate_plants_walls_ql", 250), ("cfg4_office_chain12_qlambda", 60), ("fl_shaping_vi_ql", 150),
     ("fl_shaping_distance_qrm", 150), ("ow_shaping_vi_exp3_qrm", 150), ("ow_map2_walls_qrm", 120), ("ow_map3_walls_qrm", 100),
     ("ow_map4_walls_qrm", 60), ("fl_random_starts_3agents_qrm", 200), ("fl_random_starts_6agents_ql", 120),
-    ("fl_per_agent_rms_qrm", 200), ("fl_per_agent_rms_ql", 200),
+    ("fl_per_agent_rms_qrm", 200), ("fl_per_agent_rms_ql", 200), ("fl_per_agent_rms_qlambda", 150),
+    ("fl_per_agent_rms_shaping_qrm", 200), ("fl_per_agent_rms_shaping_ql", 200),
+    # the reference's NATIVE float64 tables: learners built with table_dtype="f64" reproduce the unmodified reference
+    ("cfg1_det_qrm_f64", 160), ("cfg3_slip_ql_f64", 200), ("fl_qlambda_lr_none_f64", 120), ("cfg4_office_chain12_qlambda_f64", 40),
+    ("fl_lr_none_qrm_f64", 160), ("cfg2_office_slip_ql_f64", 200), ("fl_shaping_vi_ql_f64", 150),
 ]
 
 
@@ -27,12 +31,15 @@ def test_reference_driver_loop_over_dropin_classes(name, iters, cuda_device):
 
     meta, ref = load_golden(name)
     n = min(2, meta["n_instances"])
-    out = H.run_reference(meta["scenario"], n, iters, pre_resets=meta["pre_resets"], builder=build_b200)
+    f64 = meta["real"] == "f64"
+    out = H.run_reference(meta["scenario"], n, iters, table_dtype=np.float64 if f64 else np.float32, pre_resets=meta["pre_resets"],
+                          builder=build_b200)
     for k in ("action", "cell", "prev_cell", "q", "prev_q", "event_cell", "env_term", "rm_term", "term", "trunc", "active",
               "fail", "agent_steps", "timestep", "renv", "rq", "reward", "epsilon"):
         assert np.array_equal(out[k], ref[k][:iters, :n]), f"{name}: {k}"
-    # Q value written by each update (float32): pins the learner arithmetic step by step
-    assert np.array_equal(out["q_sa"].astype(np.float32), ref["q_sa"][:iters, :n].astype(np.float32)), f"{name}: q_sa"
+    # Q value written by each update: pins the learner arithmetic step by step (float64 fixtures: all 64 bits)
+    cast = np.float64 if f64 else np.float32
+    assert np.array_equal(out["q_sa"].astype(cast), ref["q_sa"][:iters, :n].astype(cast)), f"{name}: q_sa"
     assert np.array_equal(out["episode_end"], ref["episode_end"][:iters, :n])
 
 

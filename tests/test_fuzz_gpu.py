@@ -48,7 +48,7 @@ def random_scenario(seed):
     A = int(rng.integers(1, 5))
     starts = [free[i] for i in rng.choice(len(free), size=A, replace=False)]
     algo = str(rng.choice(["ql", "qrm", "qlambda"]))
-    per_agent = algo != "qlambda" and A > 1 and rng.random() < 0.25
+    per_agent = A > 1 and rng.random() < 0.25
     if per_agent:
         machines = [random_machine(rng, free, f"m{a}_") for a in range(A)]
         rm, per = machines[0][0], [m[0] for m in machines]
@@ -82,7 +82,7 @@ def random_scenario(seed):
             sc.learning_rate = None  # 1 / visits, float64 arithmetic (qlearning_lambda.py:44-49)
     else:
         sc.learning_rate = None if rng.random() < 0.2 else float(rng.choice([1.0, 0.1, 0.37]))
-        if not per_agent and rng.random() < 0.25:
+        if rng.random() < 0.25:
             sc.use_rsh, sc.rs_kind = True, str(rng.choice(["vi", "distance"]))
             sc.rs_gamma, sc.rs_alpha = float(rng.choice([0.9, 0.99])), float(rng.choice([100, 7]))
     sc.random_start_positions = bool(env == "frozen_lake" and rng.random() < 0.25)
@@ -90,6 +90,8 @@ def random_scenario(seed):
     opts = {"n": int(rng.choice([1, 3, 17, 64, 129])), "iters": int(rng.choice([150, 400, 700])),
             "track_visits": bool(not sc.shared_q and rng.random() < 0.25),
             "sparse": bool(algo == "qlambda" and rng.random() < 0.5), "chunks": int(rng.choice([1, 1, 3]))}
+    if not sc.shared_q and rng.random() < 0.3:
+        sc.table_dtype = "f64"  # the reference's native float64 tables (RLRM_TABLE_F64)
     return sc, opts
 
 
@@ -104,7 +106,7 @@ def test_random_scenario_matches_oracle(seed, cuda_device):
     if opts["sparse"]:
         kw["qlambda_sparse"] = True
     eng = Engine(c, opts["n"], **kw)
-    o = O.Oracle(c, opts["n"], "f32", track_visits=opts["track_visits"])
+    o = O.Oracle(c, opts["n"], sc.table_dtype, track_visits=opts["track_visits"])
     eng.reset(); o.reset()
     done = 0
     for part in np.array_split(np.arange(opts["iters"]), opts["chunks"]):  # launch boundaries must not matter
@@ -159,7 +161,7 @@ def test_random_scenario_greedy_evaluation_equals_oracle(seed, cuda_device):
     eng = Engine(c, opts["n"])
     eng.reset()
     eng.train(opts["iters"])
-    o = O.Oracle(c, opts["n"], "f32")
+    o = O.Oracle(c, opts["n"], sc.table_dtype)
     o.reset()
     o.q[...] = eng.q.cpu().numpy().reshape(o.q.shape)
     o.slot[...] = eng.slot.cpu().numpy().view(np.uint64)
@@ -182,7 +184,7 @@ def test_random_scenario_product_mdp_equals_oracle(seed, cuda_device):
     sc, _opts = random_scenario(seed)
     sc.shared_q = False
     c = P.compile_scenario(sc)
-    eng, o = Engine(c, 1), O.Oracle(c, 1, "f32")
+    eng, o = Engine(c, 1), O.Oracle(c, 1, sc.table_dtype)
     sub, _probs = mdp_action_distribution(sc)
     for k in range(len(sc.starts)):
         for rm_terminal in (True, False):

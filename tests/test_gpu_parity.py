@@ -89,6 +89,18 @@ def _scenarios_medium():
                                        [("w0", g["B"], "w1", 1.0), ("w1", g["A"], "w2", 1.0), ("w2", g["C"], "w3", 1.0),
                                         ("w3", g["B"], "w4", 5.0), ("w1", g["C"], "w0", -1.0)]]
         out[f"fl_per_agent_rms_{algo}"] = (sc, 700, 1300)
+        if algo == "qrm":  # agents with different machines + potential-based shaping (one phi section per agent)
+            import copy
+
+            sh = copy.deepcopy(sc)
+            sh.use_rsh, sh.rs_kind, sh.learning_rate = True, "vi", 0.5
+            out["fl_per_agent_rms_shaping_qrm"] = (sh, 300, 1300)
+        else:      # agents with different machines + Q(lambda) (per-agent table sizes in the trace sweeps)
+            import copy
+
+            ql = copy.deepcopy(sc)
+            ql.algo, ql.lambd, ql.learning_rate, ql.q_init = "qlambda", 0.8, 0.2, 0.0
+            out["fl_per_agent_rms_qlambda"] = (ql, 40, 1100)
     return out
 
 
@@ -168,7 +180,7 @@ def test_generic_kernel_equals_specialised(name, cuda_device):
 
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda", "fl_per_agent_rms_qrm",
-                                  "fl_per_agent_rms_ql", "fl_random_starts_qrm"])
+                                  "fl_per_agent_rms_ql", "fl_random_starts_qrm", "fl_per_agent_rms_qlambda", "fl_per_agent_rms_shaping_qrm"])
 def test_unfused_entry_points_equal_fused(name, dtype, cuda_device):
     """select -> step -> update -> reset through the separate C-ABI calls == the fused persistent kernel."""
     import multiagent_rlrm_b200 as P
