@@ -553,9 +553,11 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
   const KP& kp = h->kp;
   const bool fast_ok = reward_out == nullptr;  // the per-step reward output exists in the generic kernels only
   if (kp.algo == RLRM_ALGO_QLAMBDA && !st->e) {
-    RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
+    if (kp.per_agent) RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T, true><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
+    else RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T, false><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
   } else if (kp.algo == RLRM_ALGO_QLAMBDA) {
-    RLRM_BY_T(h, train_qlambda_kernel<ENV, T><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
+    if (kp.per_agent) RLRM_BY_T(h, train_qlambda_kernel<ENV, T, true><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
+    else RLRM_BY_T(h, train_qlambda_kernel<ENV, T, false><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
   } else {
     const long long threads = st->n_instances * kp.G;
     const unsigned grid = blocks_for(threads, TRAIN_BLOCK);

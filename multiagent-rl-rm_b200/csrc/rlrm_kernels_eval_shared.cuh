@@ -304,33 +304,55 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
       }
     }
     __syncthreads();
-    // ---- flush this block's proposals into global accumulator set `it % 3` (integer atomics: order-independent) ----
+    // ---- flush this block's proposals into global accumulator set `it % 3` (integer atomics: order-independent). All three
+    // phases below work on whole table rows (4 entries, one 16-byte access per array) so that a thread's few rows are
+    // independent vector accesses instead of a chain of dependent scalar ones ----
     const size_t cur = (size_t)(it % 3) * (size_t)n_ent, prev = (size_t)((it + 2) % 3) * (size_t)n_ent;
-    for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
-      const int c = s_cnt[j];
-      if (c) {
-        atomicAdd(g_cnt + cur + j, c);
-        atomicAdd(g_sum + cur + j, s_sum[j]);
-        g_last[cur + j] = s_last[j];  // only read back when the GLOBAL count is 1, i.e. exactly one block wrote it
-        s_cnt[j] = 0;
-        s_sum[j] = 0ull;
+    for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) {
+      const int4 c = reinterpret_cast<const int4*>(s_cnt)[j];
+      if (c.x | c.y | c.z | c.w) {
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (cc[e]) {
+            atomicAdd(g_cnt + cur + 4 * j + e, cc[e]);
+            atomicAdd(g_sum + cur + 4 * j + e, s_sum[4 * j + e]);
+            g_last[cur + 4 * j + e] = s_last[4 * j + e];  // only read back when the GLOBAL count is 1, i.e. exactly one block wrote it
+            s_sum[4 * j + e] = 0ull;
+          }
+        reinterpret_cast<int4*>(s_cnt)[j] = make_int4(0, 0, 0, 0);
       }
     }
     grid.sync();
-    // ---- apply: fold the global sums into this block's table copy (apply_shared_kernel's arithmetic) ----
-    for (int j = threadIdx.x; j < n_ent; j += blockDim.x) {
-      const int c = __ldcg(g_cnt + cur + j);
-      if (c == 1) Qs[j] = __ldcg(g_last + cur + j);
-      else if (c > 1) Qs[j] = __double2float_rn(__dmul_rn(__ddiv_rn((double)(long long)__ldcg(g_sum + cur + j), (double)c), 9.5367431640625e-07));
+    // ---- apply: fold the global sums into this block's table copy (apply_shared_kernel's arithmetic) and refresh the row maxima ----
+    for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) {
+      const int4 c = __ldcg(reinterpret_cast<const int4*>(g_cnt + cur) + j);
+      if (c.x | c.y | c.z | c.w) {
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+        const float4 last = __ldcg(reinterpret_cast<const float4*>(g_last + cur) + j);
+        const ulonglong2 s01 = __ldcg(reinterpret_cast<const ulonglong2*>(g_sum + cur) + 2 * j);
+        const ulonglong2 s23 = __ldcg(reinterpret_cast<const ulonglong2*>(g_sum + cur) + 2 * j + 1);
+        const float ll[4] = {last.x, last.y, last.z, last.w};
+        const unsigned long long ss[4] = {s01.x, s01.y, s23.x, s23.y};
+        float4 q = reinterpret_cast<const float4*>(Qs)[j];
+        float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (cc[e] == 1) qq[e] = ll[e];
+          else if (cc[e] > 1) qq[e] = __double2float_rn(__dmul_rn(__ddiv_rn((double)(long long)ss[e], (double)cc[e]), 9.5367431640625e-07));
+        }
+        q = make_float4(qq[0], qq[1], qq[2], qq[3]);
+        reinterpret_cast<float4*>(Qs)[j] = q;
+        s_rmax[j] = row_max(q);
+      }
     }
     // the set filled in the PREVIOUS iteration has been read by every block (before this iteration's barrier): clear it
     if (it > 0)
-      for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_ent; j += (long long)gridDim.x * blockDim.x) {
-        g_cnt[prev + j] = 0;
-        g_sum[prev + j] = 0ull;
+      for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_ent / 4; j += (long long)gridDim.x * blockDim.x) {
+        reinterpret_cast<int4*>(g_cnt + prev)[j] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<ulonglong2*>(g_sum + prev)[2 * j] = make_ulonglong2(0ull, 0ull);
+        reinterpret_cast<ulonglong2*>(g_sum + prev)[2 * j + 1] = make_ulonglong2(0ull, 0ull);
       }
-    __syncthreads();
-    for (int j = threadIdx.x; j < n_ent / 4; j += blockDim.x) s_rmax[j] = row_max(reinterpret_cast<const float4*>(Qs)[j]);
     __syncthreads();
   }
   // leave the tables in global memory and every accumulator set clean

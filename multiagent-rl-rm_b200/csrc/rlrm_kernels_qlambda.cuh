@@ -3,19 +3,23 @@
 #include "rlrm_kernels_api.cuh"
 #include "rlrm_kernels_train.cuh"
 
-template <int ENV, typename T>
+// PA = agents carry different reward machines: the warp's agent gets its own view of the parameters (a private copy); with
+// PA = false the parameter block stays in the constant bank
+template <int ENV, typename T, bool PA>
 __global__ void __launch_bounds__(256) train_qlambda_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                            unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
-  KP p = p_in;
+  KP p_view;
+  if (PA) p_view = p_in;
+  const KP& p = PA ? p_view : p_in;
   Tab tb = stage_tables(p_in);
   __shared__ int sh_term[RLRM_MAX_AGENTS], sh_trunc[RLRM_MAX_AGENTS];
   const long long i = blockIdx.x;
   const int a = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long k = i * p.A + a;
-  if (p_in.per_agent) agent_view(p_in, p, tb, a);  // this warp's agent has its own machine: nQ, final state, table size
+  const long long k = i * p_in.A + a;
+  if (PA) agent_view(p_in, p_view, tb, a);  // this warp's agent has its own machine: nQ, final state, table size
   Slot s = unpack_slot(st.slot[k]);
   double eps = st.epsilon[k];
   double ep_ret = st.ep_return ? st.ep_return[k] : 0.0;
@@ -161,13 +165,15 @@ __device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigne
 // profiles/r01_sparse_qlambda_ncu.csv): the lists stay L1-resident for the n_iters of a launch, so the kernel is bound by
 // instruction issue, not by HBM. Episode-over detection is two warp ballots; no shared memory, no block barrier.
 #define QLS_BLOCK 128
-template <int ENV, typename T>
+template <int ENV, typename T, bool PA>
 __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                                         unsigned* trace, double* reward_out) {
   typedef RT<T> R;
   typedef typename R::row_t row_t;
   typedef typename R::pair_t pair_t;
-  KP p = p_in;
+  KP p_view;
+  if (PA) p_view = p_in;
+  const KP& p = PA ? p_view : p_in;
   Tab tb = stage_tables(p_in);
   const long long i = (long long)blockIdx.x * (QLS_BLOCK / 32) + (threadIdx.x >> 5);
   if (i >= st.N) return;  // whole warps leave; nothing below synchronises across warps
@@ -177,8 +183,8 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in
   const int a = lane / LG;         // this lane's agent (slot a >= A idles when A is not a power of two)
   const int gl = lane - a * LG;    // lane within the agent's group
   const bool valid = a < p.A;
-  const long long k = i * p.A + (valid ? a : 0);
-  if (p_in.per_agent) agent_view(p_in, p, tb, valid ? a : 0);  // this lane group's agent has its own machine
+  const long long k = i * p_in.A + (valid ? a : 0);
+  if (PA) agent_view(p_in, p_view, tb, valid ? a : 0);  // this lane group's agent has its own machine
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
   T* Q = tab<T>(st.q) + table_base(p_in, i, valid ? a : 0);
