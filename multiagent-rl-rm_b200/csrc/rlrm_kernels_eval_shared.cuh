@@ -228,23 +228,27 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
     // ---- propose: same per-slot code as shared_propose_kernel ----
     // the slot word / epsilon of the NEXT slot this thread handles are fetched while the current one is processed (the
     // streamed state is the only HBM traffic of this kernel; unprefetched, its latency was the top stall: ncu source page)
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    // every block owns one contiguous, warp-aligned chunk of the slots (equal work per block: the grid barrier below waits
+    // for the slowest block) and walks it with a block-wide stride
+    const long long stride = blockDim.x;
+    const long long chunk = (((total + gridDim.x - 1) / gridDim.x) + 31) & ~31ll;
+    const long long lo = (long long)blockIdx.x * chunk, hi = (lo + chunk < total) ? lo + chunk : total;
     unsigned long long w_next = 0ull;
     double eps_next = 0.0;
     {
-      const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+      const long long tid = lo + threadIdx.x;
       const long long i = tid >> p.g_shift;
       const int a = (int)(tid & (p.G - 1));
-      if (tid < total && i < st.N && a < p.A) {
+      if (tid < hi && i < st.N && a < p.A) {
         w_next = st.slot[i * p.A + a];
         eps_next = st.epsilon[i * p.A + a];
       }
     }
-    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += stride) {
+    for (long long b0 = lo; b0 < hi; b0 += stride) {
       const long long tid = b0 + threadIdx.x;
       const long long i = tid >> p.g_shift;
       const int a = (int)(tid & (p.G - 1));
-      const bool valid = (i < st.N) && (a < p.A);
+      const bool valid = (tid < hi) && (i < st.N) && (a < p.A);
       const long long k = i * p.A + a;
       bool term = true, trunc = true;
       Slot s = {0, 0, 0, 0, 0};
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
       {
         const long long tn = tid + stride, in = tn >> p.g_shift;
         const int an = (int)(tn & (p.G - 1));
-        if (b0 + stride < total && in < st.N && an < p.A) {
+        if (tn < hi && in < st.N && an < p.A) {
           w_next = st.slot[in * p.A + an];
           eps_next = st.epsilon[in * p.A + an];
         }
