@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -192,6 +193,10 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   kp.eps_end = cfg->epsilon_end; kp.eps_decay = cfg->epsilon_decay;
   fill_learner(kp, cfg->learning_rate, cfg->gamma, cfg->lambd);
   kp.decay_on_reset = cfg->decay_on_reset; kp.shared_q = cfg->shared_q;
+  {
+    const char* e = getenv("RLRM_SHARED_BALANCED");  // tuning switch, see shared_train_kernel
+    kp.shared_balanced = e ? atoi(e) : 0;
+  }
   kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
   kp.per_agent = cfg->per_agent_rm ? 1 : 0;
   kp.nd = kp.nQ * (kp.nEv + 1);

@@ -228,11 +228,12 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
     // ---- propose: same per-slot code as shared_propose_kernel ----
     // the slot word / epsilon of the NEXT slot this thread handles are fetched while the current one is processed (the
     // streamed state is the only HBM traffic of this kernel; unprefetched, its latency was the top stall: ncu source page)
-    // every block owns one contiguous, warp-aligned chunk of the slots (equal work per block: the grid barrier below waits
-    // for the slowest block) and walks it with a block-wide stride
-    const long long stride = blockDim.x;
+    // slots -> blocks: either one contiguous, warp-aligned chunk per block walked with a block-wide stride (equal work per
+    // block) or the classic grid-stride walk; p.shared_balanced picks (measured)
     const long long chunk = (((total + gridDim.x - 1) / gridDim.x) + 31) & ~31ll;
-    const long long lo = (long long)blockIdx.x * chunk, hi = (lo + chunk < total) ? lo + chunk : total;
+    const long long stride = p.shared_balanced ? (long long)blockDim.x : (long long)gridDim.x * blockDim.x;
+    const long long lo = p.shared_balanced ? (long long)blockIdx.x * chunk : (long long)blockIdx.x * blockDim.x;
+    const long long hi = p.shared_balanced ? ((lo + chunk < total) ? lo + chunk : total) : total;
     unsigned long long w_next = 0ull;
     double eps_next = 0.0;
     {
