@@ -308,14 +308,14 @@ def ncu_capture(workload):
 # what bounds the dominant kernel of each workload (ncu evidence under profiles/); `frac` is always
 # computed against the HBM peak with SURVEY 8d's algorithmic bytes — it is an HBM-utilisation figure only where bound = hbm
 BOUND = {
-    "cfg3": "issue/latency (carried cell block: most algorithmic bytes never leave registers; DRAM ~30 % of peak)",
+    "cfg3": "issue/latency (carried cell block: most algorithmic bytes never leave registers; issue slots 58 %, DRAM 27 % of peak)",
     "cfg3_ql": "latency (one dependent 16-byte gather per step at 6.9 warps per scheduler)",
     "cfg2_batch": "latency (one dependent 16-byte gather per step)",
     "cfg2_batch_qrm": "latency on the row loads after a move, then L1 wavefronts",
     "cfg4": "issue (trace lists stay L1/L2-resident)",
     "cfg4_dense": "hbm",
-    "cfg4_qrm": "latency on the block fetch after a move, then shared-memory wavefronts",
-    "ow_exp6_qrm": "latency on the block fetch after a move, then shared-memory wavefronts",
+    "cfg4_qrm": "smem-wavefront (cell block in shared memory: short scoreboard 60 % of the stalls, L1 wavefront pipe 68 %), then the block fetch after a move",
+    "ow_exp6_qrm": "smem-wavefront (cell block in shared memory: short scoreboard 50 % of the stalls, L1 wavefront pipe 73 %), then the block fetch after a move",
     "cfg5_tables": "issue/latency",
     "cfg5_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
     "ow12_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
