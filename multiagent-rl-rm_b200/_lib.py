@@ -14,7 +14,8 @@ from . import _abi as abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "librlrm_b200.so")
+# RLRM_LIB_PATH: load an alternative build of the library (kernel tuning A/B runs); the default is the in-tree build
+LIB_PATH = os.environ.get("RLRM_LIB_PATH") or os.path.join(_PKG, "librlrm_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", "rlrm_b200.cu")]
 HEADERS = [os.path.join(_ROOT, "include", "rlrm_b200.h")] + sorted(
     os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc")) if f.endswith(".cuh"))

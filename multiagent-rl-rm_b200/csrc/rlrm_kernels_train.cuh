@@ -472,6 +472,32 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+// the nQ rows of one cell block: global -> shared. QRMB_FETCH = 0 (default): one cp.async per row — all rows in flight, no
+// registers; the data lands in shared memory per global sector (14 wavefronts per row, profiles/r02b). QRMB_FETCH = NB > 0:
+// batches of NB 16-byte loads through registers + conflict-free 16-byte shared stores (4 wavefronts per row). Measured on
+// exp6 / chain-12: cp.async 1.55e10 / 1.11e10; NB = 2: 1.31e10 / 0.93e10; NB = 4: 0.96e10 / 0.75e10 (one global latency per
+// batch and, from NB = 3 on, spills under the 72-register budget) — the wavefronts cp.async wastes cost less than latency.
+#ifndef QRMB_FETCH
+#define QRMB_FETCH 0
+#endif
+__device__ __forceinline__ void fetch_cell_block(float4* blk, const float* src, int nQ) {
+#if QRMB_FETCH == 0
+  for (int r = 0; r < nQ; r++) cp_async16(blk + r * TRAIN_BLOCK, src + 4 * r);
+  cp_async_wait_all();
+#else
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  constexpr int NB = QRMB_FETCH;  // rows per batch
+  for (int r0 = 0; r0 < nQ; r0 += NB) {
+    float4 v[NB];
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+      if (r0 + k < nQ) v[k] = s4[r0 + k];
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+      if (r0 + k < nQ) blk[(r0 + k) * TRAIN_BLOCK] = v[k];
+  }
+#endif
+}
 
 template <int ENV, int NU>
 __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
@@ -497,10 +523,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
     if (st.ep_return) ep_ret = st.ep_return[k];
     if (st.stats) return_sum = st.stats[k].return_sum;
     Q = st.q + table_base(p, i, a);
-    const float* src = Q + (size_t)s.cell * (size_t)(nQ * 4);
-    for (int r = 0; r < nQ; r++) cp_async16(blk + r * TRAIN_BLOCK, src + 4 * r);
+    fetch_cell_block(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ);
   }
-  cp_async_wait_all();
   unsigned long long explore_thr = explore_threshold(eps);
   bool had_episode = false;
 
@@ -523,11 +547,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
           const float4 v = blk[(j < p.n_qrm ? tb.qrm_states[j] : 0) * TRAIN_BLOCK];
           cur[j] = sel4(v.x, v.y, v.z, v.w, (unsigned)action);
         }
-        if (moved) {  // the shared block becomes the NEXT cell's block: one asynchronous 16-byte copy per row
-          const float* src = Q + (size_t)r.cell * (size_t)(nQ * 4);
-          for (int rr = 0; rr < nQ; rr++) cp_async16(blk + rr * TRAIN_BLOCK, src + 4 * rr);
-          cp_async_wait_all();
-        }
+        if (moved) fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ);  // the shared block becomes the NEXT cell's block
         // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106) in
         // get_all_states()[:-1] order. The next state's row maximum comes from the shared block: the new cell's block when
         // the agent moved, else the live one including this step's earlier updates.
@@ -551,9 +571,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
           }
         }
       } else if (moved) {
-        const float* src = Q + (size_t)r.cell * (size_t)(nQ * 4);
-        for (int rr = 0; rr < nQ; rr++) cp_async16(blk + rr * TRAIN_BLOCK, src + 4 * rr);
-        cp_async_wait_all();
+        fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ);
       }
       term = r.term;
       trunc = r.trunc;
@@ -578,11 +596,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
       const unsigned old_cell = s.cell;
       reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
-      if (s.cell != old_cell) {
-        const float* src = Q + (size_t)s.cell * (size_t)(nQ * 4);
-        for (int rr = 0; rr < nQ; rr++) cp_async16(blk + rr * TRAIN_BLOCK, src + 4 * rr);
-        cp_async_wait_all();
-      }
+      if (s.cell != old_cell) fetch_cell_block(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ);
     }
   }
   if (valid) {

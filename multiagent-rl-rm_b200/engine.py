@@ -226,7 +226,7 @@ class Engine:
                 self._it_record = torch.zeros(n, dtype=torch.int32).pin_memory()
                 self._it_reward = torch.zeros(n, dtype=torch.float64).pin_memory()
             record = self._it_record
-            if want_reward and reward is None:
+            if want_reward and reward is None and not self.cfg.shared_q:  # the shared learner's launch has no per-step reward output
                 reward = self._it_reward
         check(self.L.rlrm_iterate(self.h, C.byref(self.state), self.t, int(learn), _ptr(record), _ptr(reward), self._stream()))
         self.t += 1

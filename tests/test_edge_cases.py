@@ -138,7 +138,8 @@ def test_create_rejects_bad_arguments():
                          (lambda cfg, t: setattr(cfg, "algo", 7), "algo"),
                          (lambda cfg, t: setattr(t, "delta", None), "null table"),
                          (lambda cfg, t: setattr(cfg, "rm_final", 4), "rm_final"),
-                         (lambda cfg, t: setattr(cfg, "max_steps", 70000), "max_steps")):
+                         (lambda cfg, t: setattr(cfg, "max_steps", 70000), "max_steps"),
+                         (lambda cfg, t: setattr(cfg, "table_dtype", 2), "table_dtype")):
         rc, msg = create(mutate)
         assert rc == -1 and text in msg, (rc, msg)
 
@@ -189,6 +190,49 @@ def test_value_iteration_rejects_bad_arguments():
     for kw, text in (({"prob": None}, "null"), ({"work": None}, "null"), ({"n": 0}, "n_states"), ({"n_out": 0}, "n_states"),
                      ({"theta": 0.0}, "theta"), ({"sweeps": 0}, "theta")):
         assert call(**kw) == -1 and text in L.rlrm_last_error().decode(), kw
+
+
+@pytest.mark.gpu
+def test_round2_entry_points_reject_bad_arguments(cuda_device):
+    """rlrm_iterate / rlrm_update_list / rlrm_merge_replicas and the float64 table mode: error codes, never a crash."""
+    import torch
+
+    from multiagent_rlrm_b200._lib import RlrmError
+    from multiagent_rlrm_b200.engine import Engine
+
+    sc = P.scenario_config5(True)
+    sc.table_dtype = "f64"
+    with pytest.raises(RlrmError, match="float32"):     # the shared learner is specified on float32 tables
+        Engine(P.compile_scenario(sc), 4)
+    eng = Engine(P.compile_scenario(P.scenario_config5(True)), 8)
+    eng.reset()
+    L, st, stream = eng.L, C.byref(eng.state), eng._stream()
+    rew = torch.zeros(8 * 4, dtype=torch.float64).pin_memory()
+    assert L.rlrm_iterate(eng.h, st, 0, 1, None, rew.data_ptr(), stream) == -3 and "shared" in L.rlrm_last_error().decode()
+    rec, none = eng.iterate()                           # record only: fine
+    assert none is None and rec.shape == (32,)
+    ex = (C.c_uint8 * 24)()
+    assert L.rlrm_update_list(eng.h, st, 0, 1, C.addressof(ex), stream) == -3   # proposals need the synchronous iteration
+    g = torch.zeros(2 * eng.q.numel(), device="cuda:0")
+    assert L.rlrm_merge_replicas(eng.h, None, 2, eng.q.numel(), eng.q.data_ptr(), stream) == -1
+    assert L.rlrm_merge_replicas(eng.h, g.data_ptr(), 0, eng.q.numel(), eng.q.data_ptr(), stream) == -1
+    assert L.rlrm_merge_replicas(eng.h, g.data_ptr(), 2, eng.q.numel(), eng.q.data_ptr(), stream) == 0
+    assert L.rlrm_stream_sync(None, stream) == -1 and L.rlrm_stream_sync(eng.h, stream) == 0
+    assert float(eng.q.abs().sum()) == 0.0              # mean of two zero replicas
+    plain = Engine(P.compile_scenario(P.scenario_config3(False)), 8)
+    plain.reset()
+    st2 = C.byref(plain.state)
+    assert L.rlrm_update_list(plain.h, st2, 16, 1, C.addressof(ex), stream) == -1 and "slot" in L.rlrm_last_error().decode()
+    assert L.rlrm_update_list(plain.h, st2, 0, 1, None, stream) == -1
+    assert L.rlrm_update_list(plain.h, st2, 0, 0, None, stream) == 0            # an empty list is a no-op
+    sp = Engine(P.compile_scenario(P.scenario_config4()), 2, qlambda_sparse=True)
+    assert L.rlrm_update_list(sp.h, C.byref(sp.state), 0, 1, C.addressof(ex), stream) == -3  # needs dense traces
+    with pytest.raises(RuntimeError, match="host_control"):
+        plain.step_host([0] * 16)
+    with pytest.raises(ValueError, match="table_dtype"):
+        P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=0.1, state_space_size=4, action_space_size=4, table_dtype="f16")
+    big = P.scenario_config4()                          # 8 agents x 32-state machines x 60 events would exceed the 48 KB table blob
+    assert P.compile_scenario(big).config.table_dtype == 0
 
 
 @pytest.mark.gpu
