@@ -87,6 +87,11 @@ WORKLOADS = {
                     "tables + accumulators in shared memory)",
                     "configs[3]'s environment and machine with configs[4]'s shared learner (not a BASELINE configuration)",
                     262144, 64, 2 * 12 * 16 + 4 * 11, "shared_train_kernel<OfficeWorld,QRM> (persistent cooperative; shared-memory wavefront bound)"),
+    "ow12x4_shared": ("OfficeWorld map1 (12x9), 4 agents, slip hp=.8, synthetic 12-state completed chain RM, QLearning lr=.1 gamma=.9 eps=.1 "
+                      "init=2 use_qrm=True, ONE table per agent index per GPU (shared learner; 20,736 entries = 435 KB of tables + "
+                      "accumulators: partitioned over the distributed shared memory of 2-block clusters)",
+                      "configs[3]'s environment, machine and agent count with configs[4]'s shared learner (not a BASELINE configuration)",
+                      262144, 64, 2 * 12 * 16 + 4 * 11, "shared_train_cluster_kernel<OfficeWorld,QRM,2> (persistent cooperative, DSMEM)"),
     "cfg5_tables": ("FrozenLake map1, 4 agents, slippery, RM A->B->C, QLearning use_qrm=True, per-instance Q tables",
                     "configs[4] HBM-bound companion: 1M FrozenLake instances x 4 agents, per-instance tables",
                     1048576, 256, 140, "train_qrm4_kernel<FrozenLake>"),
@@ -120,7 +125,12 @@ def scenario(workload):
         sc.starts, sc.shared_q = sc.starts[:1] + [(6, 3)], True
         return sc
 
-    return {"ow12_shared": ow12_shared, "cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
+    def ow12x4_shared():
+        sc = cfg4_qrm()
+        sc.shared_q = True
+        return sc
+
+    return {"ow12_shared": ow12_shared, "ow12x4_shared": ow12x4_shared, "cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
             "cfg2_batch": lambda: cfg2(False), "cfg2_batch_qrm": lambda: cfg2(True),
             "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg4_qrm": cfg4_qrm, "ow_exp6_qrm": exp6, "cfg5_tables": lambda: P.scenario_config5(False),
             "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
@@ -319,6 +329,7 @@ BOUND = {
     "cfg5_tables": "issue/latency",
     "cfg5_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
     "ow12_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
+    "ow12x4_shared": "distributed-shared-memory latency / wavefronts (half of the row gathers and proposal atomics go to the peer SM); tables live on chip, not HBM",
 }
 
 

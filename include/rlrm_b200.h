@@ -132,7 +132,9 @@ typedef struct rlrm_config {
   int32_t use_rsh;             /* QLearning.use_rsh: potential-based shaping R' = R + gamma*Phi(q') - Phi(q) (qlearning.py:51-66, 93-105) */
   int32_t n_actions;           /* 1..4 usable actions (exploration draws (w1*n_actions)>>32); tables are always 4 wide */
   int32_t reserved;            /* testing switches (paths that must agree bit for bit): bit 0 forces the generic kernels, bit 1 forces the
-                                  shared learner's two-launches-per-iteration path instead of the persistent cooperative kernel */
+                                  shared learner's two-launches-per-iteration path instead of the persistent cooperative kernel, bit 2
+                                  forces its thread-block-cluster variant (tables partitioned over distributed shared memory) even
+                                  when the tables fit in one SM */
   int32_t table_dtype;         /* RLRM_TABLE_F32 / RLRM_TABLE_F64: element type of rlrm_state_t.q / e / tr_eq */
 } rlrm_config_t;
 
@@ -326,8 +328,9 @@ int rlrm_update(rlrm_handle_t* h, const rlrm_state_t* st, const uint16_t* obs_ce
  * integers, so the result does not depend on thread order or on how instances are spread over blocks/GPUs.
  * With a single instance this is exactly the per-instance learner (for reward machines whose counterfactual updates
  * do not read each other's writes, e.g. chains). rlrm_train runs all n_iters iterations of this mode in ONE persistent
- * cooperative launch (tables and proposal accumulators in shared memory, one grid barrier per iteration); with a trace
- * buffer, learn = 0 or tables that do not fit in shared memory it falls back to two launches per iteration.
+ * cooperative launch (tables and proposal accumulators in shared memory, one grid barrier per iteration; tables too large for
+ * one SM's 227 KB are partitioned over the distributed shared memory of a thread-block cluster of 2 / 4 / 8 blocks); with a
+ * trace buffer, learn = 0 or tables beyond 8 x 227 KB it falls back to two launches per iteration.
  * Inter-GPU merging (every K iterations) is the caller's step: average the replicas of `q` (dist.merge_replicas gathers
  * them over NCCL and sums in rank order, so the result does not depend on the collective's reduction order). */
 

@@ -47,6 +47,8 @@ struct rlrm_handle {
   int shared_smem_bytes;
   unsigned char* d_coop;  // shared learner, persistent path: three global accumulator sets (sum i64 | count i32 | last f32), zeroed
   int coop_ok;            // cooperative launch is supported and the kernel attributes were set
+  int shared_cluster;     // tables partitioned over a thread-block cluster of this many blocks (shared_train_cluster_kernel), 0 = not used
+  int shared_cluster_smem;
   int num_sms;
   cudaStream_t pipe_stream[2];  // rlrm_train_host: copy-in / copy-out streams of the chunk pipeline (created on first use)
   cudaEvent_t pipe_event[3 * 8];
@@ -136,6 +138,46 @@ static int validate_tables(const rlrm_config_t* cfg, const rlrm_tables_t* tb) {
   if (cfg->max_steps < 0 || cfg->max_steps > 65534) return fail(RLRM_ERR_ARG, "max_steps must be in 0..65534 (16-bit step counters)");
   return RLRM_OK;
 }
+
+// shared_train_cluster_kernel: attributes + cooperative cluster launch
+template <int ENV, int ALGO, int CL>
+static cudaError_t cluster_kernel_setup(int max_smem) {
+  return cudaFuncSetAttribute(shared_train_cluster_kernel<ENV, ALGO, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+template <int ENV, int ALGO, int CL>
+static cudaError_t cluster_kernel_launch(const rlrm_handle* h, const KP& kp, const DState& d, unsigned long long t0, int n_iters, long long want_blocks,
+                                         unsigned long long* g_sum, int* g_cnt, float* g_last, cudaStream_t s) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CL; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.blockDim = dim3(SHARED_BLOCK);
+  cfg.dynamicSmemBytes = (size_t)h->shared_cluster_smem;
+  cfg.stream = s;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  cfg.gridDim = dim3(CL);
+  int max_clusters = 0;  // clusters that can be co-resident (a cooperative launch needs the whole grid resident)
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, shared_train_cluster_kernel<ENV, ALGO, CL>, &cfg);
+  if (e != cudaSuccess) return e;
+  if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+  long long clusters = (want_blocks + CL - 1) / CL;
+  if (clusters > max_clusters) clusters = max_clusters;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  return cudaLaunchKernelEx(&cfg, shared_train_cluster_kernel<ENV, ALGO, CL>, kp, d, t0, n_iters, g_sum, g_cnt, g_last);
+}
+#define RLRM_CLUSTER_DISPATCH(FN, ...)                                                                                        \
+  (h->kp.env_kind == RLRM_ENV_FROZEN_LAKE                                                                                    \
+       ? (h->kp.algo == RLRM_ALGO_QRM ? RLRM_CLUSTER_CL(FN, RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM, __VA_ARGS__)                \
+                                      : RLRM_CLUSTER_CL(FN, RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL, __VA_ARGS__))                 \
+       : (h->kp.algo == RLRM_ALGO_QRM ? RLRM_CLUSTER_CL(FN, RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM, __VA_ARGS__)               \
+                                      : RLRM_CLUSTER_CL(FN, RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL, __VA_ARGS__)))
+#define RLRM_CLUSTER_CL(FN, ENV, ALGO, ...) \
+  (h->shared_cluster == 2 ? FN<ENV, ALGO, 2>(__VA_ARGS__) : (h->shared_cluster == 4 ? FN<ENV, ALGO, 4>(__VA_ARGS__) : FN<ENV, ALGO, 8>(__VA_ARGS__)))
 
 extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, int device, rlrm_handle_t** out) {
   if (!cfg || !tb || !out) return fail(RLRM_ERR_ARG, "null argument");
@@ -310,6 +352,29 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
       if (e3 == cudaSuccess) e3 = cudaMemset(h->d_coop, 0, (size_t)3 * n_ent * 16);
       h->coop_ok = e3 == cudaSuccess;
       cudaGetLastError();
+    }
+    // tables too large for one SM (or bit 2 of `reserved`: testing): partition them over a thread-block cluster
+    const bool cluster_ok = kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && !h->f64 && !(cfg->reserved & 1);
+    if (cluster_ok && (!h->shared_fast || (cfg->reserved & 4))) {
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+      const long long rows = n_ent / 4;
+      for (int cl = 2; cl <= 8 && coop && !h->shared_cluster; cl *= 2) {
+        const long long smem = align16(off) + ((rows + cl - 1) / cl) * 84;  // per row: Q 16 + sums 32 + counts 16 + last 16 + row max 4
+        if (smem <= h->max_smem) {
+          h->shared_cluster = cl;
+          h->shared_cluster_smem = (int)smem;
+        }
+      }
+      if (h->shared_cluster) {
+        cudaError_t e4 = RLRM_CLUSTER_DISPATCH(cluster_kernel_setup, h->max_smem);
+        if (e4 == cudaSuccess && !h->d_coop) {
+          e4 = cudaMalloc(&h->d_coop, (size_t)3 * n_ent * 16);
+          if (e4 == cudaSuccess) e4 = cudaMemset(h->d_coop, 0, (size_t)3 * n_ent * 16);
+        }
+        if (e4 != cudaSuccess) h->shared_cluster = 0;
+        cudaGetLastError();
+      }
     }
   }
   *out = h;
@@ -651,7 +716,7 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
   if (h->kp.shared_q) {
     // synchronous iterations: one propose launch over all instances + one apply launch per lockstep iteration
     const size_t stride = (size_t)st->n_instances * h->kp.A;
-    if (h->shared_fast && h->coop_ok && !st->visits && learn && !trace && !(h->cfg.reserved & 2)) {
+    if (h->shared_fast && h->coop_ok && !st->visits && learn && !trace && !(h->cfg.reserved & 2) && !((h->cfg.reserved & 4) && h->shared_cluster)) {
       // persistent path: all n_iters iterations in one cooperative launch (see shared_train_kernel)
       const long long threads = st->n_instances * h->kp.G;
       long long want = (threads + SHARED_BLOCK - 1) / SHARED_BLOCK;
@@ -669,6 +734,19 @@ extern "C" int rlrm_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0,
       if (kp.env_kind == RLRM_ENV_FROZEN_LAKE) fn = kp.algo == RLRM_ALGO_QRM ? (const void*)shared_train_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QRM> : (const void*)shared_train_kernel<RLRM_ENV_FROZEN_LAKE, RLRM_ALGO_QL>;
       else fn = kp.algo == RLRM_ALGO_QRM ? (const void*)shared_train_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QRM> : (const void*)shared_train_kernel<RLRM_ENV_OFFICE_WORLD, RLRM_ALGO_QL>;
       CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(SHARED_BLOCK), args, (size_t)h->shared_smem_bytes, s));
+      LAUNCH_CHECK(h);
+      return RLRM_OK;
+    }
+    if (h->shared_cluster && !(h->shared_fast && !(h->cfg.reserved & 4)) && !st->visits && learn && !trace && !(h->cfg.reserved & 2)) {
+      // persistent path with the tables partitioned over a thread-block cluster (see shared_train_cluster_kernel)
+      const long long threads = st->n_instances * h->kp.G;
+      const long long want = (threads + SHARED_BLOCK - 1) / SHARED_BLOCK;
+      const DState d = dstate(st);
+      const size_t n_ent = (size_t)h->kp.A * (size_t)h->kp.S4;
+      unsigned long long* g_sum = reinterpret_cast<unsigned long long*>(h->d_coop);
+      int* g_cnt = reinterpret_cast<int*>(h->d_coop + 3 * n_ent * 8);
+      float* g_last = reinterpret_cast<float*>(h->d_coop + 3 * n_ent * 12);
+      CUDA_TRY(RLRM_CLUSTER_DISPATCH(cluster_kernel_launch, h, h->kp, d, (unsigned long long)t0, (int)n_iters, want, g_sum, g_cnt, g_last, s));
       LAUNCH_CHECK(h);
       return RLRM_OK;
     }

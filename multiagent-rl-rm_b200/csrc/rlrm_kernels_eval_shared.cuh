@@ -373,6 +373,201 @@ __global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_kernel(KP p, DSt
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// shared learner, persistent path for tables that do NOT fit in one SM's shared memory (21 bytes per entry: e.g. the 12-state
+// OfficeWorld machine with four agents, 20,736 entries = 435 KB): the same algorithm as shared_train_kernel with the table rows,
+// row maxima and proposal accumulators PARTITIONED over the CL thread blocks of a cluster — row R lives in block (R mod CL) at
+// local row R / CL — and reached through distributed shared memory (cluster.map_shared_rank: remote LDS / atomics over the
+// SM-to-SM network, ~215 cycles). Every cluster holds one complete copy; a block flushes / folds only the rows it owns, so the
+// per-iteration reduction work is split CL ways. Barriers per iteration: cluster (proposals of all peers are in) -> grid (global
+// sums complete) -> cluster (folded values visible to the peers). Launched cooperatively with a cluster dimension.
+// ------------------------------------------------------------------------------------------------
+template <int ENV, int ALGO, int CL>
+__global__ void __launch_bounds__(SHARED_BLOCK, 1) shared_train_cluster_kernel(KP p, DState st, unsigned long long t0, int n_iters,
+                                                                              unsigned long long* g_sum, int* g_cnt, float* g_last) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr unsigned LOG = CL == 2 ? 1 : (CL == 4 ? 2 : 3);
+  const unsigned rank = cluster.block_rank();
+  Tab tb = stage_tables(p);
+  const int n_ent = p.A * (int)p.S4;
+  const int rows = n_ent / 4, rows_loc = (rows + CL - 1) / CL;
+  float* Qs = reinterpret_cast<float*>(smem_raw + ((p.blob_bytes + 15) & ~15));                 // [rows_loc][4]
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(Qs + rows_loc * 4);          // [rows_loc][4]
+  int* s_cnt = reinterpret_cast<int*>(s_sum + rows_loc * 4);
+  float* s_last = reinterpret_cast<float*>(s_cnt + rows_loc * 4);
+  float* s_rmax = s_last + rows_loc * 4;                                                         // [rows_loc]
+  for (int lr = threadIdx.x; lr < rows_loc; lr += blockDim.x) {
+    const int R = lr * CL + (int)rank;
+    const float4 v = R < rows ? __ldcg(reinterpret_cast<const float4*>(st.q) + R) : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(Qs)[lr] = v;
+    s_rmax[lr] = row_max(v);
+    reinterpret_cast<int4*>(s_cnt)[lr] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<ulonglong2*>(s_sum)[2 * lr] = make_ulonglong2(0ull, 0ull);
+    reinterpret_cast<ulonglong2*>(s_sum)[2 * lr + 1] = make_ulonglong2(0ull, 0ull);
+  }
+  cluster.sync();
+
+  // row R of a partitioned array whose local part starts at `base` (elements per row: `per`)
+#define CL_ROW(base, R, per) cluster.map_shared_rank((base) + (size_t)((R) >> LOG) * (per), (R) & (CL - 1))
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned group_mask = (p.G == 32 ? 0xFFFFFFFFu : ((1u << p.G) - 1u)) << (lane & ~(unsigned)(p.G - 1));
+  const long long total = st.N << p.g_shift;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const unsigned rows_per_agent = (unsigned)(p.S4 / 4);
+  for (int it = 0; it < n_iters; it++) {
+    const unsigned long long t = t0 + (unsigned long long)it;
+    for (long long b0 = (long long)blockIdx.x * blockDim.x; b0 < total; b0 += stride) {
+      const long long tid = b0 + threadIdx.x;
+      const long long i = tid >> p.g_shift;
+      const int a = (int)(tid & (p.G - 1));
+      const bool valid = (i < st.N) && (a < p.A);
+      const long long k = i * p.A + a;
+      bool term = true, trunc = true;
+      Slot s = {0, 0, 0, 0, 0};
+      double eps = 0.0;
+      Rec r;
+      r.reward = 0.0;
+      if (valid) {
+        s = unpack_slot(st.slot[k]);
+        eps = st.epsilon[k];
+        unsigned w[4];
+        RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+        const unsigned R0 = (unsigned)a * rows_per_agent;  // first row of agent a's table
+        const float4 row = *reinterpret_cast<const float4*>(CL_ROW(Qs, R0 + s.cell * p.nQ + s.rm, 4));
+        const int action = select_action(row, explore_threshold(eps), w, false, p.n_actions);
+        const unsigned before = s.cell;
+        const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
+        agent_step<ENV>(p, tb, s, action, w[3], true, r);
+        // update_q as a proposal (rlrm_device.cuh update_q, shared-memory branch) on partitioned rows
+        auto propose = [&](unsigned Rs, double rew, unsigned Rsn, bool terminated) {
+          const float cur = CL_ROW(Qs, Rs, 4)[action];
+          const float mx = *CL_ROW(s_rmax, Rsn, 1);
+          const float mf = __fmul_rn(terminated ? 0.0f : 1.0f, mx);
+          const float inner = __fadd_rn(__double2float_rn(rew), __fmul_rn(p.gamma_f, mf));
+          const float out = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur), __fmul_rn(p.lr_f, inner));
+          const unsigned long long v = (unsigned long long)__float2ll_rn(__fmul_rn(out, 1048576.0f));
+          unsigned* wsum = reinterpret_cast<unsigned*>(CL_ROW(s_sum, Rs, 4) + action);
+          const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+          const unsigned old = atomicAdd(wsum, lo);
+          const unsigned up = hi + ((old + lo) < old ? 1u : 0u);
+          if (up) atomicAdd(wsum + 1, up);
+          atomicAdd(CL_ROW(s_cnt, Rs, 4) + action, 1);
+          CL_ROW(s_last, Rs, 4)[action] = out;
+        };
+        if (ALGO == RLRM_ALGO_QRM) {
+          const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
+          for (int j = 0; j < p.n_qrm; j++) {
+            const unsigned u = tb.qrm_states[j];
+            const unsigned d = tb.delta[u * (p.nEv + 1) + col];
+            const unsigned un = d == RLRM_NO_TRANSITION ? u : d;
+            const double ru = d == RLRM_NO_TRANSITION ? 0.0 : tb.rcf[u * (p.nEv + 1) + col];
+            const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
+            double rew = __dadd_rn(r.renv, ru);
+            if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[un]), tb.phi[u]));
+            propose(R0 + r.prev_cell * p.nQ + u, rew, R0 + r.cell * p.nQ + un, done);
+          }
+        } else {
+          const unsigned obs = (p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN && first) ? r.cell : before;
+          const bool term_arg = p.driver == RLRM_DRIVER_FROZEN_LAKE_MAIN ? (r.term || r.trunc) : r.term;
+          double rew = r.reward;
+          if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[p.phi_row + r.q]), tb.phi[p.phi_row + r.prev_q]));
+          propose(R0 + obs * p.nQ + r.prev_q, rew, R0 + r.cell * p.nQ + r.q, term_arg);
+        }
+        term = r.term;
+        trunc = r.trunc;
+        if (r.reward != 0.0 && st.ep_return) st.ep_return[k] = __dadd_rn(st.ep_return[k], r.reward);
+      }
+      const unsigned bt = __ballot_sync(0xFFFFFFFFu, term), bc = __ballot_sync(0xFFFFFFFFu, trunc);
+      const bool over = ((bt & group_mask) == group_mask) || ((bc & group_mask) == group_mask);
+      if (valid) {
+        if (over) {
+          const double ret = st.ep_return ? st.ep_return[k] : 0.0;
+          if (st.stats) {
+            rlrm_stats_t z = st.stats[k];
+            z.episodes++;
+            z.active_steps += s.steps;
+            z.successes += (p.rm_final >= 0 && (int)s.rm == p.rm_final) ? 1u : 0u;
+            z.last_return = __double2float_rn(ret);
+            z.return_sum = __dadd_rn(z.return_sum, ret);
+            z.last_length = s.time;
+            st.stats[k] = z;
+          }
+          if (st.ep_return) st.ep_return[k] = 0.0;
+          reset_slot(p, tb, i, a, t + 1, s, eps);
+          st.epsilon[k] = eps;
+        }
+        st.slot[k] = pack_slot(s);
+      }
+    }
+    cluster.sync();  // every peer's proposals for the rows this block owns are in
+    const size_t cur = (size_t)(it % 3) * (size_t)n_ent, prev = (size_t)((it + 2) % 3) * (size_t)n_ent;
+    for (int lr = threadIdx.x; lr < rows_loc; lr += blockDim.x) {
+      const int4 c = reinterpret_cast<const int4*>(s_cnt)[lr];
+      if (c.x | c.y | c.z | c.w) {
+        const size_t R = (size_t)lr * CL + rank;
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (cc[e]) {
+            atomicAdd(g_cnt + cur + 4 * R + e, cc[e]);
+            atomicAdd(g_sum + cur + 4 * R + e, s_sum[4 * lr + e]);
+            g_last[cur + 4 * R + e] = s_last[4 * lr + e];
+            s_sum[4 * lr + e] = 0ull;
+          }
+        reinterpret_cast<int4*>(s_cnt)[lr] = make_int4(0, 0, 0, 0);
+      }
+    }
+    grid.sync();
+    for (int lr = threadIdx.x; lr < rows_loc; lr += blockDim.x) {
+      const size_t R = (size_t)lr * CL + rank;
+      if (R >= (size_t)rows) continue;
+      const int4 c = __ldcg(reinterpret_cast<const int4*>(g_cnt + cur) + R);
+      if (c.x | c.y | c.z | c.w) {
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+        const float4 last = __ldcg(reinterpret_cast<const float4*>(g_last + cur) + R);
+        const ulonglong2 s01 = __ldcg(reinterpret_cast<const ulonglong2*>(g_sum + cur) + 2 * R);
+        const ulonglong2 s23 = __ldcg(reinterpret_cast<const ulonglong2*>(g_sum + cur) + 2 * R + 1);
+        const float ll[4] = {last.x, last.y, last.z, last.w};
+        const unsigned long long ss[4] = {s01.x, s01.y, s23.x, s23.y};
+        float4 q = reinterpret_cast<const float4*>(Qs)[lr];
+        float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (cc[e] == 1) qq[e] = ll[e];
+          else if (cc[e] > 1) qq[e] = __double2float_rn(__dmul_rn(__ddiv_rn((double)(long long)ss[e], (double)cc[e]), 9.5367431640625e-07));
+        }
+        q = make_float4(qq[0], qq[1], qq[2], qq[3]);
+        reinterpret_cast<float4*>(Qs)[lr] = q;
+        s_rmax[lr] = row_max(q);
+      }
+    }
+    if (it > 0)
+      for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_ent / 4; j += (long long)gridDim.x * blockDim.x) {
+        reinterpret_cast<int4*>(g_cnt + prev)[j] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<ulonglong2*>(g_sum + prev)[2 * j] = make_ulonglong2(0ull, 0ull);
+        reinterpret_cast<ulonglong2*>(g_sum + prev)[2 * j + 1] = make_ulonglong2(0ull, 0ull);
+      }
+    cluster.sync();  // the folded values of this block's rows are visible to its peers before they select / propose again
+  }
+#undef CL_ROW
+  grid.sync();
+  if (blockIdx.x < CL)  // the first cluster writes the tables back: every block its own rows
+    for (int lr = threadIdx.x; lr < rows_loc; lr += blockDim.x) {
+      const int R = lr * CL + (int)rank;
+      if (R < rows) reinterpret_cast<float4*>(st.q)[R] = reinterpret_cast<const float4*>(Qs)[lr];
+    }
+  if (n_iters > 0) {
+    const size_t last = (size_t)((n_iters - 1) % 3) * (size_t)n_ent;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_ent; j += (long long)gridDim.x * blockDim.x) {
+      g_cnt[last + j] = 0;
+      g_sum[last + j] = 0ull;
+    }
+  }
+  cluster.sync();  // no block leaves while a peer could still address its shared memory
+}
+
 // shared learner: every touched entry becomes the mean of this iteration's proposals; accumulators are cleared
 __global__ void __launch_bounds__(256) apply_shared_kernel(KP p, DState st) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;

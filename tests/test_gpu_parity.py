@@ -315,6 +315,49 @@ def test_shared_learner_persistent_kernel_equals_two_launch_path_and_oracle(n, c
     assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy()) and np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
 
 
+@pytest.mark.parametrize("name", ["cfg5_forced_cluster", "office12_4agents", "office12_8agents", "office_acbd_ql_forced"])
+def test_shared_learner_cluster_kernel_equals_two_launch_path_and_oracle(name, cuda_device):
+    """Shared tables that do not fit in one SM's shared memory are partitioned over the distributed shared memory of a
+    thread-block cluster (shared_train_cluster_kernel, 2 / 4 / 8 blocks). It must equal the two-launches-per-iteration path
+    (config.reserved bit 1; global-memory proposals for these sizes) and the oracle; `reserved` bit 2 forces it for tables that
+    would fit in one SM, where it must also equal the single-block persistent kernel."""
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    if name == "cfg5_forced_cluster":
+        sc, n, force = P.scenario_config5(shared=True), 3000, True
+    elif name == "office_acbd_ql_forced":
+        sc, n, force = P.scenario_config2(True), 2500, True
+        sc.shared_q, sc.starts = True, [(2, 7), (6, 3), (0, 0)]
+    else:
+        sc, n, force = P.scenario_config4(), 2000, False
+        sc.algo, sc.learning_rate, sc.q_init, sc.shared_q = "qrm", 0.1, 2.0, True
+        if name == "office12_8agents":
+            sc.starts = sc.starts + [(5, 5), (8, 2), (1, 1), (10, 7)]
+    c_cl, c_two = P.compile_scenario(sc), P.compile_scenario(sc)
+    c_cl.config.reserved = 4 if force else 0
+    c_two.config.reserved = 2
+    a, b = _engine(c_cl, n), _engine(c_two, n)
+    o = O.Oracle(c_cl, n, "f32")
+    a.reset(); b.reset(); o.reset()
+    t0 = 0
+    for chunk in (1, 2, 3, 70):
+        a.train(chunk); b.train(chunk); o.train(t0, chunk)
+        t0 += chunk
+        assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy()), f"{name}: Q after {t0} iterations"
+    assert a.launches == 5 and b.launches > a.launches                      # reset + ONE launch per train call
+    assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy()) and np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+    assert np.array_equal(a.ep_return.cpu().numpy(), b.ep_return.cpu().numpy())
+    assert int(a.acc_cnt.abs().sum()) == 0 and int(a.acc_sum.abs().sum()) == 0
+    _compare_with_oracle(a, o, name)
+    if force:  # the single-block persistent kernel on the same scenario
+        c1 = P.compile_scenario(sc)
+        e1 = _engine(c1, n)
+        e1.reset()
+        e1.train(76)
+        assert np.array_equal(e1.q.cpu().numpy(), a.q.cpu().numpy()) and np.array_equal(e1.slot.cpu().numpy(), a.slot.cpu().numpy())
+
+
 def test_shared_learner_with_one_instance_is_the_reference_learner(cuda_device):
     """Degenerate tie to the reference: N = 1 shared == per-instance tables (which equal the reference trace)."""
     import multiagent_rlrm_b200 as P
