@@ -847,11 +847,12 @@ extern "C" int rlrm_train_host(rlrm_handle_t* h, const rlrm_state_t* st, uint64_
   // Independent instances and enough bytes to matter: split the instance range into chunks and pipeline them over two extra
   // streams — chunk c's upload, chunk c-1's kernel and chunk c-2's download overlap. Results are bit-identical to the
   // single launch (sub_state). The shared learner's iterations are synchronous over ALL instances, so it cannot be chunked.
-  // Every chunk must still fill the GPU on its own (>= 512 Ki slots), otherwise the chunk kernels would run one after the other
-  // at a fraction of the occupancy of the single launch.
+  // Every chunk must still fill the GPU on its own, otherwise the chunk kernels would run one after the other at a fraction of
+  // the occupancy of the single launch: >= 512 Ki slots for the thread-per-agent kernels, >= 64 Ki for the Q(lambda) kernels
+  // (a warp per agent / a lane group per agent).
   int chunks = 1;
   if (!h->kp.shared_q && n_iters > 0 && bytes >= (8u << 20)) {
-    const size_t fit = n / (512u * 1024u);
+    const size_t fit = n / ((h->kp.algo == RLRM_ALGO_QLAMBDA ? 64u : 512u) * 1024u);
     chunks = fit >= 8 ? 8 : (fit >= 2 ? (int)fit : 1);
   }
   if (chunks == 1) {

@@ -85,10 +85,16 @@ class RewardMachine:
         return self.state_indices[rm_state]
 
     def get_state_from_index(self, rm_state_index):
-        for state, idx in self.state_indices.items():
-            if idx == rm_state_index:
-                return state
-        raise ValueError(f"Index {rm_state_index} not present in RewardMachine.state_indices")
+        """Inverse of state_indices (reward_machine.py:41-43 scans the dict on every call; here the inverse is cached and
+        rebuilt when state_indices was replaced or changed size)."""
+        si = self.state_indices
+        cached = self.__dict__.get("_inverse_cache")
+        if cached is None or cached[0] is not si or cached[1] != len(si):
+            cached = self.__dict__["_inverse_cache"] = (si, len(si), {idx: state for state, idx in reversed(list(si.items()))})
+        try:
+            return cached[2][rm_state_index]
+        except (KeyError, TypeError):
+            raise ValueError(f"Index {rm_state_index} not present in RewardMachine.state_indices") from None
 
     def get_all_states(self):
         return list(self._states_in_order())

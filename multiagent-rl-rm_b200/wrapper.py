@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import torch
 
+from .encoders import _GridStateEncoder
 from .envs import _A2I, _num
 
 
@@ -157,10 +158,27 @@ class RMEnvironmentWrapper:
         final = rm.get_final_state()
         a_idx = agent.actions_idx(action)
         out = []
+        enc = agent.encoder
+        if type(enc).encode is _GridStateEncoder.encode:  # the stock grid encoders: enc = (y*W + x)*nQ + index(q), inlined
+            W, _H, n_rm = enc._dims()
+            s_cur = current_state["pos_y"] * W + current_state["pos_x"]
+            s_nxt = next_state["pos_y"] * W + next_state["pos_x"]
+            limit = W * _H * n_rm
+            index = rm.state_indices
+            for k, s in enumerate(states):
+                qn = int(q_out[k])
+                nxt = rm.get_state_from_index(qn)
+                qs = index[s]
+                enc_s, enc_n = s_cur * n_rm + qs, s_nxt * n_rm + qn
+                if enc_s >= limit or enc_n >= limit:
+                    raise ValueError("Encoded state index exceeds total state space size.")
+                ru = _num(r[k])
+                out.append((enc_s, a_idx, env_reward + ru, enc_n, env_termination or nxt == final, s_cur, qs, s_nxt, qn, ru))
+            return out
         for k, s in enumerate(states):
             nxt = rm.get_state_from_index(int(q_out[k]))
-            enc_s, info_s = agent.encoder.encode(current_state, s)
-            enc_n, info_n = agent.encoder.encode(next_state, nxt)
+            enc_s, info_s = enc.encode(current_state, s)
+            enc_n, info_n = enc.encode(next_state, nxt)
             ru = _num(r[k])
             out.append((enc_s, a_idx, env_reward + ru, enc_n, env_termination or nxt == final, info_s["s"], info_s["q"],
                         info_n["s"], info_n["q"], ru))
