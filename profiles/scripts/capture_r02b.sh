@@ -30,5 +30,5 @@ cap r02b_shared_ow12       shared_train_kernel    1 $B --workload ow12_shared
 cap r02b_eval_cfg3         eval_kernel            1 python profiles/scripts/run_eval.py
 # shared_train_cluster_kernel (cooperative launch WITH a cluster dimension) is not captured: ncu's kernel replay relaunches it without
 # the cluster attribute ("LaunchFailed", then an illegal address in map_shared_rank) — its numbers come from bench lines only
-cap r02b_iterate_cfg3      "train_kernel<"        100 python profiles/scripts/run_iterate.py
+cap r02b_iterate_cfg3      "^train_kernel$"       100 python profiles/scripts/run_iterate.py
 ls -la gpurun_out | head -60
