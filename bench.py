@@ -454,6 +454,43 @@ class Runner:
                 "e2e": e2e, "clocks": clocks, "merge_ms_total": merge_total, "n_merges": len(merge_ms), "steps": steps}
 
 
+def random_gather_peak(eng, block_bytes, reps=5):
+    """What this GPU's memory system delivers for the ACCESS PATTERN of the per-instance-table kernels: independent gathers of random,
+    aligned `block_bytes` blocks spread over the engine's whole resident Q table, eight in flight per thread, read-only and with a
+    4-byte write-back per gather (rlrm_probe_random_gather, a measurement aid of the library; it rewrites values it has just read,
+    so it runs on a scratch copy of the tables). The streaming copy peak of MEASURED_PEAKS.json is not reachable by scattered
+    16-64-byte accesses; this is the second denominator the kernel's DRAM traffic is read against."""
+    import ctypes as C
+
+    import torch
+
+    from multiagent_rlrm_b200._lib import check
+
+    dev = eng.q.device
+    scratch = eng.q.clone()
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    n_bytes = scratch.numel() * scratch.element_size()
+    n_gathers = min(1 << 26, max(1 << 22, 4 * (n_bytes // block_bytes)))
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    out = {"block_bytes": block_bytes, "gathers": n_gathers, "table_bytes": n_bytes,
+           "how": "rlrm_probe_random_gather on a copy of the engine's Q tables: 64 gathers per thread, 8 in flight, best of 5 (CUDA events); "
+                  "GB/s counts the gathered blocks only (32-byte sector granularity makes the DRAM traffic of 16-byte blocks twice that)"}
+    for write, key in ((0, "read_GBps"), (1, "read_write_GBps")):
+        best = None
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(eng.L.rlrm_probe_random_gather(dev.index or 0, scratch.data_ptr(), n_bytes, block_bytes, n_gathers, write, sink.data_ptr(), stream))
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out[key] = n_gathers * block_bytes / (best * 1e-3) / 1e9
+        out[key.replace("GBps", "gathers_per_s")] = n_gathers / (best * 1e-3)
+    del scratch
+    return out
+
+
 def summarise(workload, r, res, world, peak, peak_src):
     """One measured entry (headline or `configs` block) from Runner.run's numbers."""
     steps, iters = res["steps"], r.iters
@@ -624,6 +661,16 @@ def run_gpu_arm(args):
     r = Runner(args.workload, args.instances, args.iters, rank, world, dev, sync_every=64 if shared else 0)
     res = r.run(args.steps, args.warmup, max(3, args.steps // 2), (lambda: ClockSampler(local_rank)) if rank == 0 else None)
     head = summarise(args.workload, r, res, world, peak, peak_src)
+    if not r.sc.shared_q and r.sc.algo != "qlambda":  # per-instance tables read by scattered row / cell-block gathers
+        try:
+            blk = 16 if r.sc.algo == "ql" else min(64, 16 * r.c.n_rm_states)  # a row, or (up to) a 64-byte cell block
+            g = random_gather_peak(r.eng, blk)
+            head["roofline"]["random_gather"] = g
+            steps_per_s = head["value"] / world
+            g["kernel_gathers_per_s"] = steps_per_s  # one row / cell-block gather (+ write-back) per active agent-step
+            g["kernel_over_probe"] = steps_per_s / g["read_write_gathers_per_s"]
+        except Exception as exc:  # a yardstick, never fatal
+            head["roofline"]["random_gather"] = {"error": repr(exc)[:200]}
     stepwise = unfused = None
     if world == 1 and args.workload in ("cfg3", "cfg3_ql") and not args.no_call_by_call:
         stepwise, unfused = call_by_call(r.c, r.sc, args.instances, dev)

@@ -398,6 +398,14 @@ int rlrm_evaluate(rlrm_handle_t* h, const rlrm_state_t* st, rlrm_eval_t* ev, uin
  * (device, [N*A*S*4], zeroed by the caller), scatter the traces into it — the dense view of learner.q_table / e_table. */
 int rlrm_qlambda_materialize(rlrm_handle_t* h, const rlrm_state_t* st, void* e_dense, void* stream);
 
+/* MEASUREMENT AID, not part of the path (bench.py's roofline block): launches `n_gathers` (rounded up to 64 per thread) independent
+ * gathers of random aligned `block_bytes` (16 / 32 / 64) blocks of the device buffer `table` (64-byte aligned), eight in flight per
+ * thread, each optionally followed by a 4-byte store into the block that rewrites a value just read (`write` != 0). Timed by the
+ * caller with CUDA events it gives the ceiling of the memory system for the access pattern of the per-instance-table kernels, which
+ * the streaming copy peak does not describe. `sink`: 4 writable device bytes. Needs no handle. */
+int rlrm_probe_random_gather(int device, void* table, int64_t table_bytes, int32_t block_bytes, int64_t n_gathers, int32_t write,
+                             void* sink, void* stream);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t rlrm_launch_count(const rlrm_handle_t* h);
 

@@ -198,6 +198,7 @@ EXPORTED_SYMBOLS = (
     "rlrm_update_list",
     "rlrm_merge_replicas",
     "rlrm_stream_sync",
+    "rlrm_probe_random_gather",
 )
 
 

@@ -948,3 +948,21 @@ extern "C" int rlrm_stream_sync(rlrm_handle_t* h, void* stream) {
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return RLRM_OK;
 }
+
+extern "C" int rlrm_probe_random_gather(int device, void* table, int64_t table_bytes, int32_t block_bytes, int64_t n_gathers, int32_t write,
+                                        void* sink, void* stream) {
+  if (!table || !sink) return fail(RLRM_ERR_ARG, "null argument");
+  if (block_bytes != 16 && block_bytes != 32 && block_bytes != 64) return fail(RLRM_ERR_ARG, "block_bytes must be 16, 32 or 64");
+  if (table_bytes < block_bytes || n_gathers < 1 || ((uintptr_t)table & 63u)) return fail(RLRM_ERR_ARG, "table too small / misaligned or n_gathers < 1");
+  CUDA_TRY(cudaSetDevice(device));
+  const unsigned long long n_blocks = (unsigned long long)table_bytes / (unsigned)block_bytes;
+  const int per_thread = 64;
+  const long long threads = (n_gathers + per_thread - 1) / per_thread;
+  const unsigned grid = blocks_for(threads, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (block_bytes == 16) probe_gather_kernel<1><<<grid, 256, 0, s>>>((uint4*)table, n_blocks, per_thread, 12345u, write, (unsigned*)sink);
+  else if (block_bytes == 32) probe_gather_kernel<2><<<grid, 256, 0, s>>>((uint4*)table, n_blocks, per_thread, 12345u, write, (unsigned*)sink);
+  else probe_gather_kernel<4><<<grid, 256, 0, s>>>((uint4*)table, n_blocks, per_thread, 12345u, write, (unsigned*)sink);
+  CUDA_TRY(cudaGetLastError());
+  return RLRM_OK;
+}

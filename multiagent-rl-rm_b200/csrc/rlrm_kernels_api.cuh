@@ -369,3 +369,36 @@ __global__ void __launch_bounds__(256) merge_replicas_kernel(const float* gather
   for (int r = 1; r < world; r++) acc = __fadd_rn(acc, gathered[(size_t)r * (size_t)n + j]);
   q[j] = __fdiv_rn(acc, (float)world);
 }
+
+// MEASUREMENT AID (bench.py's roofline block; not on the hot path): what the memory system delivers for the ACCESS PATTERN of the
+// per-instance-table kernels — independent gathers of random, aligned 16 / 32 / 64-byte blocks spread over a resident table,
+// optionally each followed by a 4-byte store into the block (the Q-learning write-back). Every thread keeps UNROLL independent
+// gathers in flight (far more memory-level parallelism than a serial agent chain has), so the result is the pattern's ceiling.
+template <int VEC>  // 16-byte vectors per block
+__global__ void __launch_bounds__(256) probe_gather_kernel(uint4* tab, unsigned long long n_blocks, int per_thread, unsigned seed, int write,
+                                                          unsigned* sink) {
+  constexpr int UNROLL = 8;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long x = (tid + 1) * 0x9E3779B97F4A7C15ull ^ ((unsigned long long)seed << 32);
+  unsigned acc = 0;
+  for (int k = 0; k < per_thread; k += UNROLL) {
+    unsigned long long idx[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; j++) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+      idx[j] = __umul64hi(x, n_blocks);
+    }
+    uint4 v[UNROLL][VEC];
+#pragma unroll
+    for (int j = 0; j < UNROLL; j++)
+#pragma unroll
+      for (int c = 0; c < VEC; c++) v[j][c] = tab[idx[j] * VEC + c];
+#pragma unroll
+    for (int j = 0; j < UNROLL; j++) {
+#pragma unroll
+      for (int c = 0; c < VEC; c++) acc += v[j][c].x ^ v[j][c].y ^ v[j][c].z ^ v[j][c].w;
+      if (write) reinterpret_cast<unsigned*>(tab + idx[j] * VEC)[(acc >> 3) & (4 * VEC - 1)] = v[j][0].x;  // rewrites a value it just read: contents stay valid floats
+    }
+  }
+  if (acc == 0x12345678u) sink[0] = acc;  // keeps the loads alive
+}
