@@ -1,6 +1,7 @@
-"""AgentRL — mirrors multi_agent/agent_rl.py:11-401 (the parts the hot path touches; message passing is not part of
-it). The agent is a host-side record (name, position, state dict, RM, encoders, learner); selecting and updating go to
-the learner, whose arithmetic runs on the device."""
+"""AgentRL — the host-side agent record of the drop-in API (reference: multi_agent/agent_rl.py:11-401, the parts the hot
+path touches; message passing is not part of it). Attribute and method names are the reference's because the boundary is
+duck-typed — its own tests poke `_name`, `actions_`, `actions_dix()` — but the agent holds no arithmetic: `select_action` and
+`update_policy` only encode states and forward to the learner, whose selection / update kernels run on the device."""
 from __future__ import annotations
 
 
@@ -8,144 +9,122 @@ class UPValueError(Exception):
     """Raised for an undefined action name (unified_planning.exceptions.UPValueError in the reference, agent_rl.py:55)."""
 
 
+def _plain_getter(attr):
+    return lambda self: getattr(self, attr)
+
+
+def _plain_setter(attr):
+    def setter(self, value):
+        setattr(self, attr, value)
+
+    return setter
+
+
 class AgentRL:
+    # attribute -> factory of its initial value (agent_rl.py:19-40 lists the same attributes one by one)
+    _INITIAL = (("actions_dict", dict), ("learning_algorithm", type(None)), ("message_conditions", type(None)), ("messages", dict),
+                ("message_sent", bool), ("position", type(None)), ("state", dict), ("actions_", list), ("initial_position", dict),
+                ("initial_state", dict), ("rm_state", type(None)), ("next_rm_state", type(None)), ("encoder", type(None)),
+                ("action_encoder", type(None)))
+
     def __init__(self, name: str, ma_problem, reward_machine=None):
-        self._name = name
-        self.reward_machine = reward_machine
-        self.ma_problem = ma_problem
-        self.actions_dict = {}
-        self.learning_algorithm = None
-        self.message_conditions = None
-        self.messages = {}
-        self.message_sent = False
-        self.position = None
-        self.state = {}
-        self.actions_ = []
-        self.initial_position = {}
-        self.initial_state = {}
-        self.rm_state = None
-        self.next_rm_state = None
-        self.encoder = None
-        self.action_encoder = None
+        self._name, self.ma_problem, self.reward_machine = name, ma_problem, reward_machine
+        for attr, factory in self._INITIAL:
+            setattr(self, attr, factory())
 
-    @property
-    def name(self):
-        return self._name
+    name = property(_plain_getter("_name"))
 
-    # -- actions ---------------------------------------------------------------------------------
+    # -- actions -----------------------------------------------------------------------------------------------------
     def action(self, name: str):
-        for a in self.actions_:
-            if a.name == name:
-                return a
-        raise UPValueError(f"Action of name: {name} is not defined!")
+        found = next((a for a in self.actions_ if a.name == name), None)
+        if found is None:
+            raise UPValueError(f"Action of name: {name} is not defined!")
+        return found
 
     def add_action(self, action):
         self.actions_.append(action)
 
     add_rl_action = add_action
-
-    def get_actions(self):
-        return self.actions_
+    get_actions = _plain_getter("actions_")
 
     def actions_dix(self):
-        for idx, act in enumerate(self.actions_):
-            self.actions_dict[idx] = act
+        """index -> action; entries are (re)written on every call and never dropped, like the reference's dict."""
+        self.actions_dict.update(enumerate(self.actions_))
         return self.actions_dict
 
     def actions_idx(self, action):
-        for key, value in self.actions_dix().items():
-            if value == action:
-                return key
-        return None
+        return next((k for k, v in self.actions_dix().items() if v == action), None)
 
-    # -- wiring ----------------------------------------------------------------------------------
-    def add_state_encoder(self, encoder):
-        self.encoder = encoder
+    # -- wiring ------------------------------------------------------------------------------------------------------
+    add_state_encoder = _plain_setter("encoder")
+    set_reward_machine = _plain_setter("reward_machine")
+    get_reward_machine = _plain_getter("reward_machine")
+    set_learning_algorithm = _plain_setter("learning_algorithm")
+    get_learning_algorithm = _plain_getter("learning_algorithm")
 
     def add_action_encoder(self, encoder):
         self.action_encoder = encoder
         encoder.build_actions()
 
-    def set_reward_machine(self, reward_machine):
-        self.reward_machine = reward_machine
-
-    def get_reward_machine(self):
-        return self.reward_machine
-
     def get_reward(self, event):
-        return self.reward_machine.get_reward(event) if self.reward_machine else 0
+        rm = self.reward_machine
+        return rm.get_reward(event) if rm else 0
 
-    def set_learning_algorithm(self, algorithm):
-        self.learning_algorithm = algorithm
+    # -- policy: encode, then hand over to the learner (device) ---------------------------------------------------------
+    def _need(self, what, present, doing):
+        if not present:
+            raise Exception(f"{what} not set. " + doing)
 
-    def get_learning_algorithm(self):
-        return self.learning_algorithm
-
-    # -- policy ----------------------------------------------------------------------------------
     def select_action(self, state, best=False):
-        if not self.encoder:
-            raise Exception("Encoder not set. Please add an encoder before selecting actions.")
-        encoded_state, info = self.encoder.encode(state)
-        idx = self.get_learning_algorithm().choose_action(encoded_state, best, info=info)
-        action = self.actions_dix()[idx]
-        if action is None:
+        self._need("Encoder", self.encoder, "Please add an encoder before selecting actions.")
+        enc, info = self.encoder.encode(state)
+        idx = self.learning_algorithm.choose_action(enc, best, info=info)
+        chosen = self.actions_dix()[idx]
+        if chosen is None:
             raise ValueError(f"Action index {idx} not found in actions dictionary.")
-        return action
+        return chosen
 
     def update_policy(self, state, action, reward, next_state, terminated, **kwargs):
-        infos = kwargs.get("infos", {})
-        if not self.encoder:
-            raise Exception("Encoder not set. Please add an encoder before updating policy.")
-        if not self.reward_machine:
-            raise Exception("Reward Machine not set. Cannot update policy without Reward Machine.")
-        state_rm = infos.get("prev_q", 0)
-        next_state_rm = infos.get("q", 0)
-        enc_s, cur_info = self.encoder.encode(state, state_rm)
-        enc_sn, nxt_info = self.encoder.encode(next_state, next_state_rm)
-        rm = self.reward_machine
-        info = {
-            "prev_s": cur_info["s"],
-            "s": nxt_info["s"],
-            "prev_q": rm.get_state_index(state_rm) if state_rm != 0 else 0,
-            "q": rm.get_state_index(next_state_rm) if next_state_rm != 0 else 0,
-            "Renv": infos.get("Renv", 0),
-            "RQ": infos.get("RQ", 0),
-            "qrm_experience": infos.get("qrm_experience", []),
-            "reward_machine": infos.get("reward_machine", []),
-        }
-        return self.get_learning_algorithm().update(enc_s, enc_sn, self.actions_idx(action), reward, terminated, info=info)
+        step = kwargs.get("infos", {})
+        self._need("Encoder", self.encoder, "Please add an encoder before updating policy.")
+        self._need("Reward Machine", self.reward_machine, "Cannot update policy without Reward Machine.")
+        rm, q_before, q_after = self.reward_machine, step.get("prev_q", 0), step.get("q", 0)
+        (enc_s, at_s), (enc_n, at_n) = self.encoder.encode(state, q_before), self.encoder.encode(next_state, q_after)
+        # what QLearning.update reads from `info` (agent_rl.py:158-172): cell indices, RM state INDICES, the two reward parts,
+        # the counterfactual list and the machine itself; a missing RM label (0) stays 0
+        info = dict(prev_s=at_s["s"], s=at_n["s"],
+                    prev_q=rm.get_state_index(q_before) if q_before != 0 else 0,
+                    q=rm.get_state_index(q_after) if q_after != 0 else 0,
+                    Renv=step.get("Renv", 0), RQ=step.get("RQ", 0),
+                    qrm_experience=step.get("qrm_experience", []), reward_machine=step.get("reward_machine", []))
+        return self.learning_algorithm.update(enc_s, enc_n, self.actions_idx(action), reward, terminated, info=info)
 
-    # -- position / state --------------------------------------------------------------------------
+    # -- position / state ----------------------------------------------------------------------------------------------
+    get_position = _plain_getter("position")
+    get_state = _plain_getter("state")
+
+    def set_position(self, pos_x, pos_y):
+        self.position = (pos_x, pos_y)
+        for key, value in (("pos_x", pos_x), ("pos_y", pos_y)):
+            self.add_to_state(key, value)
+
     def set_initial_position(self, pos_x, pos_y):
         self.initial_position = (pos_x, pos_y)
         self.set_position(pos_x, pos_y)
 
-    def set_position(self, pos_x, pos_y):
-        self.position = (pos_x, pos_y)
-        self.add_to_state("pos_x", pos_x)
-        self.add_to_state("pos_y", pos_y)
-
-    def get_position(self):
-        return self.position
-
     def add_to_state(self, key, value):
-        self.state[key] = value
-        self.initial_state[key] = value
+        self.state[key] = self.initial_state[key] = value
+
+    def set_state(self, **kwargs):
+        self.state.update(kwargs)
+
+    def reset_messages(self):
+        self.messages, self.message_conditions = {}, None
 
     def reset(self):
+        """Back to the initial position and state; the reward machine returns to its initial state (agent_rl.py:372-384)."""
         self.set_position(*self.initial_position)
-        self.state = self.initial_state.copy()
+        self.state = dict(self.initial_state)
         self.reset_messages()
         if self.reward_machine:
             self.reward_machine.reset_to_initial_state()
-
-    def reset_messages(self):
-        self.messages = {}
-        self.message_conditions = None
-
-    def set_state(self, **kwargs):
-        for key, value in kwargs.items():
-            self.state[key] = value
-
-    def get_state(self):
-        return self.state
