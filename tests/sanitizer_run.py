@@ -21,12 +21,26 @@ def main():
              ("cfg2 office", P.scenario_config2(True), {}), ("office chain12 qrm", sc4q, {}),
              ("cfg4 qlambda dense", P.scenario_config4(), {}), ("cfg4 qlambda sparse", P.scenario_config4(), {"qlambda_sparse": True}),
              ("cfg5 shared", P.scenario_config5(True), {}), ("cfg5 tables", P.scenario_config5(False), {})]
+    # round 2: float64 tables, the thread-block-cluster shared learner (forced), per-agent machines under Q(lambda)
+    f64 = P.scenario_config3(False)
+    f64.table_dtype = "f64"
+    g = P.frozen_lake_grid("map1").goals
+    pa = P.scenario_config3(False)
+    pa.algo, pa.lambd, pa.learning_rate, pa.q_init = "qlambda", 0.8, 0.2, 0.0
+    pa.starts, pa.detector_positions = [(5, 0), (0, 0)], sorted(g.values())
+    pa.rm_transitions_per_agent = [P.tables.frozen_lake_abc_transitions(), [("p0", g["C"], "p1", 3.0), ("p1", g["A"], "p2", 7.0)]]
+    cases += [("cfg3 ql float64", f64, {}), ("cfg5 shared, cluster kernel", P.scenario_config5(True), {"_reserved": 4}),
+              ("per-agent machines qlambda", pa, {}), ("per-agent machines qlambda sparse", pa, {"qlambda_sparse": True})]
     for name, sc, kw in cases:
         n = 37
-        eng = Engine(P.compile_scenario(sc), n, **kw)
+        kw = dict(kw)
+        c = P.compile_scenario(sc)
+        c.config.reserved = kw.pop("_reserved", 0)
+        eng = Engine(c, n, **kw)
         eng.reset()
         eng.train(40, trace=True)
         eng.train(25)
+        eng.iterate()                      # rlrm_iterate: record (and reward) into page-locked host memory
         if not kw.get("qlambda_sparse"):
             for _ in range(6):
                 eng.iterate_unfused()
@@ -38,6 +52,12 @@ def main():
         q, ev, r = eng.rm_step(torch.zeros(8, dtype=torch.uint8), torch.arange(8, dtype=torch.int16))
         torch.cuda.synchronize()
         print("ok", name, eng.launches, "launches")
+    # the N = 1 learner path: rlrm_select_action / rlrm_update_list on a page-locked staging block
+    ql = P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=0.1, state_space_size=50, action_space_size=4, use_qrm=True)
+    ql.update(0, 0, 0, 0.0, False, info={"qrm_experience": [(s, s % 4, 1.0, (s + 1) % 50, False, 0, 0, 0, 0, 0.0) for s in range(40)]})
+    ql.choose_action(3)
+    torch.cuda.synchronize()
+    print("ok learners")
 
 
 if __name__ == "__main__":
