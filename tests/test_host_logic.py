@@ -284,6 +284,28 @@ def test_agent_select_and_update_plumbing():
         P.AgentRL("x", _Problem()).select_action({"pos_x": 0, "pos_y": 0})
 
 
+def test_reward_machine_caches_follow_mutation_of_the_transition_dict():
+    """_states_in_order / get_state_from_index are cached (the reference re-derives them on every call); configuration code
+    builds machines by inserting transitions and by replacing the dicts, and the caches must follow both."""
+    from multiagent_rlrm_b200.reward_machine import PositionEventDetector, RewardMachine
+
+    rm = RewardMachine({("a", (0, 0)): ("b", 1.0)}, PositionEventDetector({(0, 0), (1, 1)}))
+    assert rm.numbers_state() == 2 and rm.get_all_states() == ["a", "b"] and rm.get_state_from_index(1) == "b"
+    rm.transitions[("b", (1, 1))] = ("c", 2.0)                      # grown in place
+    assert rm.numbers_state() == 3 and rm.get_all_states() == ["a", "b", "c"] and rm.get_final_state() == "c"
+    rm.state_indices = rm._generate_state_indices()
+    assert rm.get_state_from_index(2) == "c"
+    rm.transitions = {("x", (0, 0)): ("y", 0.5), ("y", (1, 1)): ("z", 0.5), ("z", (0, 0)): ("x", 0.0)}   # replaced, same size
+    assert rm.get_all_states() == ["x", "y", "z"] and rm.numbers_state() == 3
+    rm.state_indices = {"x": 0, "y": 1, "z": 2}                     # replaced, same size as before
+    assert rm.get_state_from_index(2) == "z" and rm.get_state_from_index(0) == "x"
+    with pytest.raises(ValueError):
+        rm.get_state_from_index(7)
+    states = rm.get_all_states()
+    states.append("junk")                                            # callers own the list they get
+    assert rm.get_all_states() == ["x", "y", "z"]
+
+
 # ---------------------------------------------------------------------------------------------- table compiler
 def test_slip_thresholds_equal_numpy_searchsorted():
     rng = np.random.default_rng(0)
