@@ -517,7 +517,9 @@ def summarise(workload, r, res, world, peak, peak_src):
                      "dense_equivalent_GBps": (4 * 1296 * 4 * 4) * active_per_launch_rank / (kernel_ms * 1e-3) / 1e9,
                      "sparse_note": "achieved uses the sparse algorithm's own bytes (32 + 16*L, SURVEY 8d); dense_equivalent is what the "
                                     "reference's dense sweep would have moved for the same steps, NOT achieved bandwidth; the lists stay "
-                                    "cache-resident across the iterations of a launch, so frac can exceed 1"})
+                                    "cache-resident across the iterations of a launch, so frac can exceed 1. The e2e window runs AFTER the "
+                                    "device-timed one, i.e. later in training with a different mean list length, so e2e_over_value mixes "
+                                    "the copy cost with that drift"})
     out = {"value": value, "unit": UNIT, "ms_per_step": res["elapsed_ms"] / steps, "steps": steps, "instances_per_gpu": r.instances,
            "agents": r.c.n_agents, "iters_per_step": iters, "gpu_launches": res["launches"],
            "slot_steps_per_s": world * r.n_slots * iters * steps / (res["elapsed_ms"] * 1e-3),
