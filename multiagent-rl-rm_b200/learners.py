@@ -284,9 +284,10 @@ class _TabularBase(BaseLearningAlgorithm):
     def __setstate__(self, d):
         tables = d.pop("_tables")
         self.__dict__.update(d)
+        self.__dict__.setdefault("table_dtype", "f32")  # pickles written before the float64 table mode existed
         self.device = torch.device(self.device)
         self._setup(0.0, getattr(self, "lambd", 0.0))
-        self._q.copy_(torch.from_numpy(tables["q"]))
+        self._q.copy_(torch.from_numpy(tables["q"]).to(self._q.dtype))
         self._visits.copy_(torch.from_numpy(tables["visits"]))
         if self._e is not None and tables["e"] is not None:
             self._e.copy_(torch.from_numpy(tables["e"]))

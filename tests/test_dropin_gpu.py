@@ -239,14 +239,17 @@ def test_wrapper_merges_env_and_rm_reward(cuda_device):
     assert rewards["a1"] == 1.0 and infos["a1"]["RQ"] == 0.5
 
 
-def test_learner_pickle_round_trip_and_table_export(cuda_device, tmp_path):
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_learner_pickle_round_trip_and_table_export(dtype, cuda_device, tmp_path):
     """office_main.py --save/--load pickles the learner; evaluation_metrics.save_q_tables writes q_table_<agent>.npz."""
     import pickle
 
     import multiagent_rlrm_b200 as P
     from multiagent_rlrm_b200.engine import Engine
 
-    ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=0.5, state_space_size=6, action_space_size=4)
+    ql = P.QLearningLambda(gamma=0.9, lambd=0.5, action_selection="greedy", learning_rate=0.5, state_space_size=6, action_space_size=4,
+                           table_dtype=dtype)
+    assert np.asarray(ql.q_table).dtype == (np.float64 if dtype == "f64" else np.float32)
     ql.update(0, 1, 2, 1.0, False)
     ql.update(1, 2, 0, -1.0, False)
     ql.epsilon = 0.123
@@ -257,7 +260,9 @@ def test_learner_pickle_round_trip_and_table_export(cuda_device, tmp_path):
     ql.update(2, 3, 1, 0.5, True)
     assert np.array_equal(np.asarray(clone.q_table), np.asarray(ql.q_table))
 
-    c = P.compile_scenario(P.scenario_config3())
+    sc = P.scenario_config3()
+    sc.table_dtype = dtype
+    c = P.compile_scenario(sc)
     eng = Engine(c, 8)
     eng.reset(); eng.train(300)
     path = P.save_q_tables(eng, path=str(tmp_path / "data" / "q_tables.npz"))
