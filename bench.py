@@ -437,7 +437,7 @@ class Runner:
                 one()
             torch.cuda.synchronize(self.dev)
             e2e_s = time.perf_counter() - t0
-            e2e = {"active": host_active() - a0, "seconds": e2e_s, "h2d": host_slot.numel() * 8 + host_eps.numel() * 8,
+            e2e = {"active": host_active() - a0, "seconds": e2e_s, "steps": e2e_steps, "h2d": host_slot.numel() * 8 + host_eps.numel() * 8,
                    "d2h": host_stats.numel() + host_slot.numel() * 8 + host_eps.numel() * 8}
 
         merge_total = sum(merge_ms)
@@ -530,6 +530,10 @@ def summarise(workload, r, res, world, peak, peak_src):
         out["e2e"] = {"value": e["active"] / e["seconds"], "unit": UNIT, "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
                       "api": "Engine.train_host -> rlrm_train_host (pinned host slot/epsilon in+out, stats out)"}
         out["e2e_over_value"] = out["e2e"]["value"] / value
+        # the e2e window runs after the device-timed one, i.e. later in training, where the share of active (not waiting) agents
+        # and, for sparse Q(lambda), the list lengths differ: the TIME ratio isolates what the host copies cost
+        out["e2e"]["ms_per_step"] = e["seconds"] * 1e3 / e["steps"]
+        out["e2e_time_ratio"] = out["ms_per_step"] / out["e2e"]["ms_per_step"]
     if r.sync_every:
         out["collective"] = {"op": "NCCL all_gather_into_tensor of the replicas + rank-ordered reduce kernel (rlrm_merge_replicas)",
                              "sync_every": r.sync_every, "merges": res["n_merges"],
