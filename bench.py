@@ -58,6 +58,13 @@ WORKLOADS = {
     "cfg3_ql": ("FrozenLake map1, 2 agents, slippery, RM A->B->C, QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False, "
                 "per-instance Q tables, auto-reset",
                 "configs[2] companion (plain Q-learning variant, SURVEY.md §8d)", 65536, 2048, 36, "train_ql_fast_kernel<FrozenLake>"),
+    "cfg3_f64": ("FrozenLake map1 (10x10), 2 agents, slippery 80/10/10, RM A->B->C (10/15/20), QLearning lr=1 gamma=.99 eps=.01 "
+                 "init=2 use_qrm=True, per-instance Q tables in FLOAT64 (the reference's own np.zeros arithmetic: bit-identical to the "
+                 "unmodified reference), auto-reset",
+                 "configs[2] on the reference's native float64 tables", 65536, 2048, 2 * 128 + 3 * 8, "train_qrm_block_kernel<FrozenLake,double>"),
+    "cfg3_ql_f64": ("FrozenLake map1, 2 agents, slippery, RM A->B->C, QLearning lr=.1 gamma=.99 eps=.01 init=2 use_qrm=False, "
+                    "per-instance Q tables in FLOAT64, auto-reset",
+                    "configs[2] companion (plain Q-learning) on float64 tables", 65536, 2048, 32 + 32 + 8, "train_kernel<FrozenLake,QL,double>"),
     "cfg2_batch": ("OfficeWorld map1 (12x9), 1 agent at (2,7), slip hp=.8, RM 'A -> C -> B -> D, reward on D' (5 states, the --rm-spec "
                    "fixture of configs[1]), QLearning lr=.1 gamma=.9 eps=.1 init=2 use_qrm=False, per-instance Q tables, auto-reset",
                    "configs[1] batched (the reference case itself is N=1 and is a parity test, not a bench line)",
@@ -130,7 +137,12 @@ def scenario(workload):
         sc.shared_q = True
         return sc
 
-    return {"ow12_shared": ow12_shared, "ow12x4_shared": ow12x4_shared, "cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
+    def f64(sc):
+        sc.table_dtype = "f64"
+        return sc
+
+    return {"cfg3_f64": lambda: f64(P.scenario_config3(True)), "cfg3_ql_f64": lambda: f64(P.scenario_config3(False)),
+            "ow12_shared": ow12_shared, "ow12x4_shared": ow12x4_shared, "cfg3": lambda: P.scenario_config3(True), "cfg3_ql": lambda: P.scenario_config3(False),
             "cfg2_batch": lambda: cfg2(False), "cfg2_batch_qrm": lambda: cfg2(True),
             "cfg4": P.scenario_config4, "cfg4_dense": P.scenario_config4, "cfg4_qrm": cfg4_qrm, "ow_exp6_qrm": exp6, "cfg5_tables": lambda: P.scenario_config5(False),
             "cfg5_shared": lambda: P.scenario_config5(True)}[workload]()
@@ -151,7 +163,7 @@ def workload_config(args, world):
     agents = len(sc.starts)
     g = sc.grid()
     n_rm = sc.reward_machine().numbers_state()
-    table_bytes = g.width * g.height * n_rm * 4 * 4 * (2 if sc.algo == "qlambda" else 1)
+    table_bytes = g.width * g.height * n_rm * 4 * (8 if sc.table_dtype == "f64" else 4) * (2 if sc.algo == "qlambda" else 1)
     per_gpu = table_bytes * agents * (1 if sc.shared_q else args.instances)
     return {
         "workload": desc,
@@ -178,7 +190,7 @@ def _cpu_worker(job):
     import oracle as O
 
     c = P.compile_scenario(scenario(algo), instance_offset=offset)
-    o = O.Oracle(c, n_inst, "f32")
+    o = O.Oracle(c, n_inst, scenario(algo).table_dtype)
     o.reset()
     t0 = time.perf_counter()
     o.train(0, iters)
@@ -241,7 +253,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1), "cpu_baseline": last,
+        "dtype": scenario(args.workload).table_dtype, "data": "synthetic", "config": workload_config(args, 1), "cpu_baseline": last,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is pure Python/NumPy (≈1e4 agent-steps/s/core, BASELINE.md §2) and cannot travel to the GPU box; "
                 "this arm times its bit-exact plain-C restatement on all host cores",
@@ -320,6 +332,8 @@ def ncu_capture(workload):
 BOUND = {
     "cfg3": "issue/latency (carried cell block: most algorithmic bytes never leave registers; issue slots 58 %, DRAM 27 % of peak)",
     "cfg3_ql": "latency (one dependent 16-byte gather per step at 6.9 warps per scheduler)",
+    "cfg3_f64": "latency (128-byte cell block fetched after every move) / fp64 pipe",
+    "cfg3_ql_f64": "latency (one dependent 32-byte gather per step)",
     "cfg2_batch": "latency (one dependent 16-byte gather per step)",
     "cfg2_batch_qrm": "latency on the row loads after a move, then L1 wavefronts",
     "cfg4": "issue (trace lists stay L1/L2-resident)",
@@ -689,6 +703,7 @@ def run_gpu_arm(args):
         n_total5 = 1048576
         off5, n5 = shard_range(n_total5, rank, world)
         plan = [  # name, workload, instances on this rank, global offset (None = rank * instances), iters, steps, sync_every, scaling
+            ("cfg3_f64", "cfg3_f64", 65536, None, 2048, 5, 0, "weak"),  # the headline workload on the reference's own float64 tables
             ("cfg2_batch", "cfg2_batch", 131072, None, 2048, 5, 0, "weak"),
             ("cfg4_sparse", "cfg4", 262144, None, 64, 5, 0, "weak"),
             ("cfg4_dense", "cfg4_dense", 262144, None, 4, 3, 0, "weak"),
@@ -726,7 +741,7 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": cfgd,
+            "dtype": scenario(args.workload).table_dtype, "data": "synthetic", "config": cfgd,
             "slot_steps_per_s": head["slot_steps_per_s"], "active_fraction": head["active_fraction"],
             "clocks": res["clocks"], "e2e": head.get("e2e"), "e2e_call_by_call": stepwise, "e2e_call_by_call_unfused": unfused,
             "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": cpu, "configs": configs,

@@ -211,6 +211,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   if (!h) return fail(RLRM_ERR_ARG, "out of host memory");
   memset(h, 0, sizeof(*h));
   h->cfg = *cfg;
+  if (getenv("RLRM_FORCE_GENERIC")) h->cfg.reserved |= 1;  // measurement switch: generic kernels only (same as reserved bit 0)
   h->device = device;
   h->f64 = cfg->table_dtype == RLRM_TABLE_F64;
   KP& kp = h->kp;
@@ -301,26 +302,31 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   h->smem_bytes = off;
   const bool f32 = !h->f64;  // the specialised kernels exist for float32 tables
   h->qrm4_fast = (f32 && kp.algo == RLRM_ALGO_QRM && kp.nQ == 4 && kp.n_qrm == 3 && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
-                  !(cfg->reserved & 1));
+                  !(h->cfg.reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrm4_fast = 0;
   h->qrmn_fast = (f32 && kp.algo == RLRM_ALGO_QRM && (kp.nQ == 3 || kp.nQ == 5) && kp.n_qrm == kp.nQ - 1 && !kp.shared_q && !kp.use_rsh &&
-                  !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 && !(cfg->reserved & 1));
+                  !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 && !(h->cfg.reserved & 1));
   for (int j = 0; j < kp.n_qrm; j++)
     if (!tb->qrm_states || tb->qrm_states[j] != j) h->qrmn_fast = 0;
   h->ql_fast = (f32 && kp.algo == RLRM_ALGO_QL && !kp.shared_q && !kp.use_rsh && !kp.random_starts && !kp.per_agent && cfg->learning_rate >= 0.0 &&
-                !(cfg->reserved & 1));
+                !(h->cfg.reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  h->qrmb_smem = align16(off) + kp.nQ * 16 * TRAIN_BLOCK;
-  h->qrmb_fast = (f32 && kp.algo == RLRM_ALGO_QRM && !h->qrm4_fast && !h->qrmn_fast && kp.nQ >= 2 && kp.nQ <= 16 && kp.n_qrm >= 1 && kp.n_qrm <= 15 &&
-                  !kp.shared_q && !kp.per_agent && cfg->learning_rate >= 0.0 && h->qrmb_smem <= h->max_smem && !(cfg->reserved & 1));
+  h->qrmb_smem = align16(off) + kp.nQ * (h->f64 ? 32 : 16) * TRAIN_BLOCK;
+  // float64 tables: the block kernel is the one specialised QRM kernel (the register-carried ones are float32-only)
+  h->qrmb_fast = (kp.algo == RLRM_ALGO_QRM && !h->qrm4_fast && !h->qrmn_fast && kp.nQ >= 2 && kp.nQ <= 16 && kp.n_qrm >= 1 && kp.n_qrm <= 15 &&
+                  !kp.shared_q && !kp.per_agent && cfg->learning_rate >= 0.0 && h->qrmb_smem <= h->max_smem && !(h->cfg.reserved & 1));
   if (h->qrmb_fast) {  // opt in to the device maximum (per function, only ever raised)
     cudaError_t e2 = cudaSuccess;
 #define RLRM_OPTIN(K) if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 7>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 11>));
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 15>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 7>));
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 11>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 15>));
+#define RLRM_OPTIN_T(T)                                                                                                                          \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 3, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 3, T>));          \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 7, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 11, T>));         \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 15, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 7, T>));        \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 11, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 15, T>))
+    if (h->f64) { RLRM_OPTIN_T(double); } else { RLRM_OPTIN_T(float); }
+#undef RLRM_OPTIN_T
 #undef RLRM_OPTIN
     if (e2 != cudaSuccess) h->qrmb_fast = 0;
   }
@@ -329,7 +335,7 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     const long long need = (long long)off + n_ent * 21;  // Q 4 B + sum 8 B + count 4 B + last 4 B per entry + row max 4 B per 4 entries
     h->shared_smem_bytes = (int)need;
     h->shared_fast = (kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && need <= 227 * 1024 &&
-                      !(cfg->reserved & 1));
+                      !(h->cfg.reserved & 1));
     if (need > h->max_smem) h->shared_fast = 0;
     if (h->shared_fast) {
       // opt every instantiation in to the DEVICE maximum: the attribute is per function, not per handle, so a later handle
@@ -354,12 +360,17 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
       cudaGetLastError();
     }
     // tables too large for one SM (or bit 2 of `reserved`: testing): partition them over a thread-block cluster
-    const bool cluster_ok = kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && !h->f64 && !(cfg->reserved & 1);
-    if (cluster_ok && (!h->shared_fast || (cfg->reserved & 4))) {
+    const bool cluster_ok = kp.shared_q && !kp.per_agent && kp.algo != RLRM_ALGO_QLAMBDA && cfg->learning_rate >= 0.0 && !h->f64 && !(h->cfg.reserved & 1);
+    int cl_min = 2;
+    {
+      const char* e = getenv("RLRM_SHARED_CLUSTER");  // tuning switch: force the cluster kernel with at least this many blocks per cluster
+      if (e && atoi(e) >= 2) { cl_min = atoi(e) >= 8 ? 8 : (atoi(e) >= 4 ? 4 : 2); h->cfg.reserved |= 4; }
+    }
+    if (cluster_ok && (!h->shared_fast || (h->cfg.reserved & 4))) {
       int coop = 0;
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
       const long long rows = n_ent / 4;
-      for (int cl = 2; cl <= 8 && coop && !h->shared_cluster; cl *= 2) {
+      for (int cl = cl_min; cl <= 8 && coop && !h->shared_cluster; cl *= 2) {
         const long long smem = align16(off) + ((rows + cl - 1) / cl) * 84;  // per row: Q 16 + sums 32 + counts 16 + last 16 + row max 4
         if (smem <= h->max_smem) {
           h->shared_cluster = cl;
@@ -676,9 +687,10 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
     }
     else if (fast_ok && kp.algo == RLRM_ALGO_QRM && h->qrmb_fast && !st->visits) {
       const DState d = dstate(st);
-      if (kp.n_qrm <= 7) train_qrm_block_kernel<ENV, 7><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace);
-      else if (kp.n_qrm <= 11) train_qrm_block_kernel<ENV, 11><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace);
-      else train_qrm_block_kernel<ENV, 15><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace);
+      if (kp.n_qrm <= 3) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 3, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
+      else if (kp.n_qrm <= 7) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 7, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
+      else if (kp.n_qrm <= 11) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 11, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
+      else RLRM_BY_T(h, train_qrm_block_kernel<ENV, 15, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
     }
     else if (fast_ok && kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
       const DState d = dstate(st);

@@ -466,6 +466,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrmn_kernel(KP p, DState
 // index free, so qrm_states may be any permutation (the 12-state chain's index map is lexicographic: q10 < q2).
 // NU = compile-time bound on the number of counterfactual states (the values they overwrite are read into registers before
 // the block is replaced). Supports shaping and random starts; per-agent machines / lr=None / shared tables stay generic.
+// Also THE specialised QRM kernel of the float64 table mode (T = double, any 2..16 states incl. BASELINE config 3's four): a row is
+// then two 16-byte chunks (8 cp.async per move for nQ = 4); config 3 on float64 tables: 1.45e10 (generic kernel) -> 2.16e10.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -480,30 +482,65 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 #ifndef QRMB_FETCH
 #define QRMB_FETCH 0
 #endif
-__device__ __forceinline__ void fetch_cell_block(float4* blk, const float* src, int nQ) {
+#ifndef QRMB_MINB_F64
+#define QRMB_MINB_F64 7
+#endif
+#define QRMB_MINB(T) (sizeof(T) == 4 ? 7 : QRMB_MINB_F64)  // resident blocks per SM the register allocation is sized for
+__device__ __forceinline__ void fetch_cell_block(uint4* blk, const void* src_, int n_chunks) {  // n_chunks 16-byte pieces: nQ rows of float4, 2 * nQ of double4r
+  const uint4* src = reinterpret_cast<const uint4*>(src_);
 #if QRMB_FETCH == 0
-  for (int r = 0; r < nQ; r++) cp_async16(blk + r * TRAIN_BLOCK, src + 4 * r);
+  for (int c = 0; c < n_chunks; c++) cp_async16(blk + c * TRAIN_BLOCK, src + c);
   cp_async_wait_all();
 #else
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-  constexpr int NB = QRMB_FETCH;  // rows per batch
-  for (int r0 = 0; r0 < nQ; r0 += NB) {
-    float4 v[NB];
+  constexpr int NB = QRMB_FETCH;  // chunks per batch
+  for (int r0 = 0; r0 < n_chunks; r0 += NB) {
+    uint4 v[NB];
 #pragma unroll
     for (int k = 0; k < NB; k++)
-      if (r0 + k < nQ) v[k] = s4[r0 + k];
+      if (r0 + k < n_chunks) v[k] = src[r0 + k];
 #pragma unroll
     for (int k = 0; k < NB; k++)
-      if (r0 + k < nQ) blk[(r0 + k) * TRAIN_BLOCK] = v[k];
+      if (r0 + k < n_chunks) blk[(r0 + k) * TRAIN_BLOCK] = v[k];
   }
 #endif
 }
+// one table row of the shared-memory cell block: a float4 is one 16-byte chunk, a double4r two (chunk c of this thread lives at
+// blk[c * TRAIN_BLOCK], so a warp's access to one chunk index is 32 consecutive 16-byte words: conflict-free)
+template <typename T>
+struct BlkRow;
+template <>
+struct BlkRow<float> {
+  static constexpr int CH = 1;
+  static __device__ __forceinline__ float4 load(const uint4* blk, unsigned r) { return *reinterpret_cast<const float4*>(blk + r * TRAIN_BLOCK); }
+  static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, float v) { reinterpret_cast<float*>(blk + r * TRAIN_BLOCK)[a] = v; }
+};
+template <>
+struct BlkRow<double> {
+  static constexpr int CH = 2;
+  static __device__ __forceinline__ double4r load(const uint4* blk, unsigned r) {
+    const double2 lo = *reinterpret_cast<const double2*>(blk + (2 * r) * TRAIN_BLOCK), hi = *reinterpret_cast<const double2*>(blk + (2 * r + 1) * TRAIN_BLOCK);
+    return double4r{lo.x, lo.y, hi.x, hi.y};
+  }
+  static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, double v) {
+    reinterpret_cast<double*>(blk + (2 * r + ((unsigned)a >> 1)) * TRAIN_BLOCK)[a & 1] = v;
+  }
+};
+template <typename T>
+__device__ __forceinline__ T sel4t(T a, T b, T c, T d, unsigned k) {
+  const T lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
+  return (k & 2u) ? hi : lo;
+}
 
-template <int ENV, int NU>
-__global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
-                                                                      unsigned* trace) {
+// T = table type: float, or double for the reference's native float64 tables (a row is then two 16-byte chunks; BASELINE config 3's
+// four-state machine in float64 takes this kernel too: 128 bytes of block per thread)
+template <int ENV, int NU, typename T>
+__global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
+                                                                                unsigned* trace) {
+  typedef RT<T> R;
+  typedef BlkRow<T> BR;
+  typedef typename R::row_t row_t;
   Tab tb = stage_tables(p);
-  float4* blk = reinterpret_cast<float4*>(smem_raw + ((p.blob_bytes + 15) & ~15)) + threadIdx.x;  // row r of this thread: blk[r * TRAIN_BLOCK]
+  uint4* blk = reinterpret_cast<uint4*>(smem_raw + ((p.blob_bytes + 15) & ~15)) + threadIdx.x;  // 16-byte chunk c of this thread: blk[c * TRAIN_BLOCK]
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = tid >> p.g_shift;
   const int a = (int)(tid & (p.G - 1));
@@ -513,7 +550,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
 
   Slot s = {0, 0, 0, 0, 0};
   double eps = 0.0, ep_ret = 0.0, return_sum = 0.0;
-  float* Q = st.q;
+  T* Q = tab<T>(st.q);
   unsigned long long active_steps = 0;
   unsigned episodes = 0, successes = 0, last_length = 0;
   float last_return = 0.f;
@@ -522,8 +559,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
     eps = st.epsilon[k];
     if (st.ep_return) ep_ret = st.ep_return[k];
     if (st.stats) return_sum = st.stats[k].return_sum;
-    Q = st.q + table_base(p, i, a);
-    fetch_cell_block(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ);
+    Q = tab<T>(st.q) + table_base(p, i, a);
+    fetch_cell_block(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ * BR::CH);
   }
   unsigned long long explore_thr = explore_threshold(eps);
   bool had_episode = false;
@@ -534,25 +571,25 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
     if (valid) {
       unsigned w[4];
       RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
-      const float4 row = blk[s.rm * TRAIN_BLOCK];
+      const row_t row = BR::load(blk, s.rm);
       const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
       const unsigned before = s.cell;
       Rec r;
       agent_step<ENV>(p, tb, s, action, w[3], true, r);
       const bool moved = r.cell != before;
       if (learn) {
-        float cur[NU];  // values the updates overwrite, read before the block is replaced
+        T cur[NU];  // values the updates overwrite, read before the block is replaced
 #pragma unroll
         for (int j = 0; j < NU; j++) {
-          const float4 v = blk[(j < p.n_qrm ? tb.qrm_states[j] : 0) * TRAIN_BLOCK];
-          cur[j] = sel4(v.x, v.y, v.z, v.w, (unsigned)action);
+          const row_t v = BR::load(blk, j < p.n_qrm ? tb.qrm_states[j] : 0);
+          cur[j] = sel4t<T>(v.x, v.y, v.z, v.w, (unsigned)action);
         }
-        if (moved) fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ);  // the shared block becomes the NEXT cell's block
+        if (moved) fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ * BR::CH);  // the shared block becomes the NEXT cell's block
         // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106) in
         // get_all_states()[:-1] order. The next state's row maximum comes from the shared block: the new cell's block when
         // the agent moved, else the live one including this step's earlier updates.
         const int col = r.event == RLRM_EVENT_NONE ? p.nEv : (int)r.event;
-        float* dst = Q + (size_t)before * (size_t)(nQ * 4) + action;  // infos["prev_s"] is the position before the move
+        T* dst = Q + (size_t)before * (size_t)(nQ * 4) + action;  // infos["prev_s"] is the position before the move
 #pragma unroll
         for (int j = 0; j < NU; j++) {
           if (j < p.n_qrm) {
@@ -563,15 +600,15 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
             const bool done = r.env_term || (p.rm_final >= 0 && (int)un == p.rm_final);
             double rew = __dadd_rn(r.renv, ru);
             if (p.use_rsh) rew = __dadd_rn(rew, __dsub_rn(__dmul_rn(p.gamma, tb.phi[un]), tb.phi[u]));  // qlearning.py:93-105
-            const float mf = __fmul_rn(done ? 0.0f : 1.0f, row_max(blk[un * TRAIN_BLOCK]));
-            const float inner = __fadd_rn(__double2float_rn(rew), __fmul_rn(p.gamma_f, mf));
-            const float nv = __fadd_rn(__fmul_rn(p.one_minus_lr_f, cur[j]), __fmul_rn(p.lr_f, inner));
-            if (__float_as_uint(nv) != __float_as_uint(cur[j])) dst[4 * u] = nv;  // a bit-identical value needs no store
-            if (!moved) reinterpret_cast<float*>(blk + u * TRAIN_BLOCK)[action] = nv;  // same cell: the shared block is the one just written
+            const T mf = R::mul(done ? (T)0 : (T)1, row_max(BR::load(blk, un)));
+            const T inner = R::add(R::cvt(rew), R::mul(R::gamma(p), mf));
+            const T nv = R::add(R::mul(R::one_minus_lr(p), cur[j]), R::mul(R::lr(p), inner));
+            if (!R::same_bits(nv, cur[j])) dst[4 * u] = nv;  // a bit-identical value needs no store
+            if (!moved) BR::set(blk, u, action, nv);  // same cell: the shared block is the one just written
           }
         }
       } else if (moved) {
-        fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ);
+        fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ * BR::CH);
       }
       term = r.term;
       trunc = r.trunc;
@@ -596,7 +633,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrm_block_kernel(KP p, D
       const unsigned old_cell = s.cell;
       reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
-      if (s.cell != old_cell) fetch_cell_block(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ);
+      if (s.cell != old_cell) fetch_cell_block(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ * BR::CH);
     }
   }
   if (valid) {

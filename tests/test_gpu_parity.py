@@ -178,6 +178,45 @@ def test_generic_kernel_equals_specialised(name, cuda_device):
     assert int(o.stats["episodes"].sum()) > 0
 
 
+@pytest.mark.parametrize("name", ["cfg3_qrm", "cfg5_qrm_4agents", "office_exp1_qrm", "office_exp3_qrm", "office_exp6_qrm", "office_chain12_qrm",
+                                  "fl_random_starts_qrm", "fl_shaping_qrm"])
+def test_float64_block_kernel_equals_generic_and_oracle(name, cuda_device):
+    """Float64 tables (the reference's own arithmetic): QRM takes train_qrm_block_kernel<.., double> (cell block of two 16-byte
+    chunks per row in shared memory); it must agree bit-for-bit with the generic float64 kernel (config.reserved bit 0) and
+    with the float64 oracle — traces, tables, slot words and statistics."""
+    import copy
+
+    import torch
+
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    if name == "fl_shaping_qrm":
+        sc, n, t = _shaped_qrm(), 400, 1500
+    elif name.startswith("office_exp"):
+        sc, n, t = _office_task(name.split("_")[1], "qrm"), 300, 1500
+    else:
+        sc, n, t = _scenarios_medium()[name]
+    sc = copy.deepcopy(sc)
+    sc.table_dtype = "f64"
+    c_fast, c_gen = P.compile_scenario(sc), P.compile_scenario(sc)
+    c_gen.config.reserved = 1
+    a, b = _engine(c_fast, n), _engine(c_gen, n)
+    a.reset(); b.reset()
+    ta, tb = a.train(t, trace=True), b.train(t, trace=True)
+    a.train(137); b.train(137)  # a second launch picks the state up from memory
+    assert a.q.dtype == torch.float64
+    assert np.array_equal(ta.cpu().numpy(), tb.cpu().numpy())
+    assert np.array_equal(a.q.cpu().numpy(), b.q.cpu().numpy())
+    assert np.array_equal(a.slot.cpu().numpy(), b.slot.cpu().numpy())
+    assert np.array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+    o = O.Oracle(c_fast, n, "f64")
+    o.reset()
+    o.train(0, t + 137)
+    assert np.array_equal(a.q.cpu().numpy().reshape(-1), o.q.reshape(-1)) and np.array_equal(a.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert int(o.stats["episodes"].sum()) > 0
+
+
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda", "fl_per_agent_rms_qrm",
                                   "fl_per_agent_rms_ql", "fl_random_starts_qrm", "fl_per_agent_rms_qlambda", "fl_per_agent_rms_shaping_qrm"])
