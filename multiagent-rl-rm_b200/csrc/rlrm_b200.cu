@@ -231,6 +231,8 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
   }
   for (int a = 0; a < 4; a++)
     for (int j = 0; j < 4; j++) kp.slip_outcome[a * 4 + j] = cfg->slip_outcome[a][j];
+  kp.slip_nib = 0ull;
+  for (int k = 0; k < 16; k++) kp.slip_nib |= (unsigned long long)(kp.slip_outcome[k] & 0xF) << (4 * k);
   kp.terminate_on_plants = cfg->terminate_on_plants; kp.terminate_hit_walls = cfg->terminate_hit_walls;
   kp.hole_penalty = cfg->hole_penalty; kp.wall_penalty = cfg->wall_penalty;
   kp.eps_end = cfg->epsilon_end; kp.eps_decay = cfg->epsilon_decay;

@@ -18,6 +18,7 @@ struct KP {
   unsigned slip_thr32[3];
   unsigned long long slip_thr[3];
   unsigned char slip_outcome[16];
+  unsigned long long slip_nib;  // slip_outcome as 16 nibbles: outcome of (intended a, threshold index k) at bits 4*(4a+k)
   int terminate_on_plants, terminate_hit_walls;
   double hole_penalty, wall_penalty;
   double lr, gamma, eps_end, eps_decay;
@@ -253,9 +254,36 @@ struct Rec {
 // its own (the shared env.timestep is replicated per agent), so lanes never exchange data here.
 // WAIT_OK: the caller may pass RLRM_ACTION_WAIT itself (env.wait_action through the call-by-call API and the "wait"
 // sub-action of get_mdp); the fused kernels only ever select 0..3 and skip the test.
-template <int ENV, int STOCH = -1, bool WAIT_OK = false>  // STOCH: -1 = read p.stochastic at run time, 0/1 = compile-time
-__device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, int action, unsigned w3, bool with_rm, Rec& r) {
+// PRE: the move-table row of the current cell (`nrow`, four u16 targets) and the slip threshold index (`sidx`) were fetched /
+// computed BEFORE the action was selected, so that action -> executed action -> new cell is pure ALU work (two shifts) instead
+// of a dependent constant-bank lookup followed by a dependent shared-memory lookup: the new cell is what the Q-block load after a
+// move waits for, i.e. this chain sits on the per-iteration critical path of the fused kernels.
+struct PreStep {
+  unsigned long long nrow;
+  unsigned sidx;
+};
+__device__ __forceinline__ unsigned slip_index(const KP& p, unsigned k) {
+  unsigned idx = 0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) idx += (j < p.slip_cnt) && (k >= p.slip_thr32[j]);
+  return idx;
+}
+__device__ __forceinline__ PreStep pre_step(const KP& p, const Tab& tb, unsigned cell, unsigned w3, bool stochastic) {
+  PreStep ps;
+  ps.nrow = *reinterpret_cast<const unsigned long long*>(tb.next_cell + cell * 4);
+  ps.sidx = stochastic ? slip_index(p, w3) : 0u;
+  return ps;
+}
+template <int ENV, int STOCH = -1, bool WAIT_OK = false, bool PRE = false>  // STOCH: -1 = read p.stochastic at run time, 0/1 = compile-time
+__device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, int action, unsigned w3, bool with_rm, Rec& r,
+                                           PreStep ps = PreStep{0ull, 0u}) {
   const bool stochastic = STOCH < 0 ? (p.stochastic != 0) : (STOCH != 0);
+  auto next_of = [&](int ex) -> unsigned {
+    return PRE ? ((unsigned)(ps.nrow >> (ex * 16)) & 0xFFFFu) : (unsigned)tb.next_cell[s.cell * 4 + ex];
+  };
+  auto slip_of = [&](int a) -> int {
+    return PRE ? (int)((unsigned)(p.slip_nib >> ((a * 4 + (int)ps.sidx) * 4)) & 0xFu) : slip_outcome(p, a, w3);
+  };
   r.prev_cell = s.cell;
   r.executed = 5;
   r.stepped = false;
@@ -266,8 +294,8 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
     const bool rm_done = p.rm_final >= 0 && (int)s.rm == p.rm_final;  // ma_frozen_lake.py:107-115
     if (active && !rm_done) {
       int ex = action;
-      if (stochastic && (!WAIT_OK || action != RLRM_ACTION_WAIT)) ex = slip_outcome(p, action, w3);
-      if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
+      if (stochastic && (!WAIT_OK || action != RLRM_ACTION_WAIT)) ex = slip_of(action);
+      if (ex != RLRM_ACTION_WAIT) s.cell = next_of(ex);
       if (tb.cell_flags[s.cell] & 1) {  // holes_in_the_ice
         s.flags |= RLRM_FLAG_FAIL;
         r.renv = p.hole_penalty;
@@ -281,13 +309,13 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
       int ex = action;
       double wall_pen = 0.0;
       // is_wall_collision("wait") is False (ma_office.py:299-300)
-      if ((!WAIT_OK || action != RLRM_ACTION_WAIT) && tb.next_cell[s.cell * 4 + action] == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
+      if ((!WAIT_OK || action != RLRM_ACTION_WAIT) && next_of(action) == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
         if (p.terminate_hit_walls) s.flags |= RLRM_FLAG_FAIL;
         wall_pen = p.wall_penalty;
         ex = RLRM_ACTION_WAIT;
       }
-      if (stochastic && ex != RLRM_ACTION_WAIT) ex = slip_outcome(p, ex, w3);
-      if (ex != RLRM_ACTION_WAIT) s.cell = tb.next_cell[s.cell * 4 + ex];
+      if (stochastic && ex != RLRM_ACTION_WAIT) ex = slip_of(ex);
+      if (ex != RLRM_ACTION_WAIT) s.cell = next_of(ex);
       double plant = 0.0;
       if (tb.cell_flags[s.cell] & 1) {  // plants_in_the_office
         if (p.terminate_on_plants) s.flags |= RLRM_FLAG_FAIL;

@@ -9,6 +9,15 @@
 #ifndef QLF_MINB
 #define QLF_MINB 8
 #endif
+// RLRM_PRESTEP(ENV): the specialised kernels fetch the current cell's move-table row and the slip index before the selection
+// (agent_step<.., PRE = true>, see rlrm_device.cuh) so that action -> new cell is ALU-only. Measured A/B (profiles/r02c/
+// r02c_prestep_ab.txt): OfficeWorld, where the chain is blocked-check -> slip -> move, gains 0.3-1.4 %; FrozenLake LOSES 0.2-1.5 %
+// (config 3 headline 4.125e10 -> 4.065e10), so it is on for OfficeWorld only. -DRLRM_PRESTEP_ALL=0/1 forces it off / on.
+#ifdef RLRM_PRESTEP_ALL
+#define RLRM_PRESTEP(ENV) (RLRM_PRESTEP_ALL != 0)
+#else
+#define RLRM_PRESTEP(ENV) ((ENV) == RLRM_ENV_OFFICE_WORLD)
+#endif
 
 // T = table arithmetic type (float: float32 tables; double: the reference's native float64 tables, see RT<T>)
 template <int ENV, int ALGO, bool PA, typename T>
@@ -223,6 +232,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, MINB) train_qrm4_kernel(KP p, DSt
     if (valid) {
       unsigned w[4];
       RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      const PreStep ps = RLRM_PRESTEP(ENV) ? pre_step(p, tb, s.cell, w[3], STOCH) : PreStep{0ull, 0u};
       float4 row;
       row.x = sel4(B[0], B[4], B[8], B[12], s.rm);
       row.y = sel4(B[1], B[5], B[9], B[13], s.rm);
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, MINB) train_qrm4_kernel(KP p, DSt
       const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);
       const unsigned before = s.cell;
       Rec r;
-      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
+      agent_step<ENV, STOCH, false, RLRM_PRESTEP(ENV)>(p, tb, s, action, w[3], true, r, ps);
       const bool moved = r.cell != before;
       // values the updates overwrite, read before the carried block is replaced
       const float cur0 = sel4(B[0], B[1], B[2], B[3], (unsigned)action);
@@ -375,6 +385,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrmn_kernel(KP p, DState
     if (valid) {
       unsigned w[4];
       RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      const PreStep ps = RLRM_PRESTEP(ENV) ? pre_step(p, tb, s.cell, w[3], STOCH) : PreStep{0ull, 0u};
       float4 row;
       row.x = sel_state<NQ>(B + 0, 4, s.rm);
       row.y = sel_state<NQ>(B + 1, 4, s.rm);
@@ -383,7 +394,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrmn_kernel(KP p, DState
       const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);
       const unsigned before = s.cell;
       Rec r;
-      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
+      agent_step<ENV, STOCH, false, RLRM_PRESTEP(ENV)>(p, tb, s, action, w[3], true, r, ps);
       const bool moved = r.cell != before;
       float cur[NQ - 1];  // values the updates overwrite, read before the carried block is replaced
 #pragma unroll
@@ -571,11 +582,12 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
     if (valid) {
       unsigned w[4];
       RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      const PreStep ps = RLRM_PRESTEP(ENV) ? pre_step(p, tb, s.cell, w[3], p.stochastic != 0) : PreStep{0ull, 0u};
       const row_t row = BR::load(blk, s.rm);
       const int action = select_action(row, explore_thr, w, learn == 0, p.n_actions);
       const unsigned before = s.cell;
       Rec r;
-      agent_step<ENV>(p, tb, s, action, w[3], true, r);
+      agent_step<ENV, -1, false, RLRM_PRESTEP(ENV)>(p, tb, s, action, w[3], true, r, ps);
       const bool moved = r.cell != before;
       if (learn) {
         T cur[NU];  // values the updates overwrite, read before the block is replaced
@@ -697,11 +709,12 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QLF_MINB) train_ql_fast_kernel(KP
     if (valid) {
       unsigned w[4];
       RLRM_PHILOX((unsigned)t, (unsigned)(t >> 32), p.instance_offset + (unsigned)i, (unsigned)a, p, w);
+      const PreStep ps = RLRM_PRESTEP(ENV) ? pre_step(p, tb, s.cell, w[3], STOCH) : PreStep{0ull, 0u};
       const int action = select_action(row, explore_thr, w, !LEARN, p.n_actions);  // row_idx == enc(current state) here
       const unsigned before = s.cell;
       const bool first = (s.flags & RLRM_FLAG_FIRST) != 0;
       Rec r;
-      agent_step<ENV, STOCH>(p, tb, s, action, w[3], true, r);
+      agent_step<ENV, STOCH, false, RLRM_PRESTEP(ENV)>(p, tb, s, action, w[3], true, r, ps);
       const unsigned snidx = r.cell * p.nQ + r.q;
       float4 nrow = row;
       if (snidx != row_idx) nrow = *reinterpret_cast<const float4*>(Q + (size_t)snidx * 4);
