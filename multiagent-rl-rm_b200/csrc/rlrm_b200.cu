@@ -242,6 +242,13 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
     const char* e = getenv("RLRM_SHARED_BALANCED");  // tuning switch, see shared_train_kernel
     kp.shared_balanced = e ? atoi(e) : 0;
   }
+  {  // sparse Q(lambda): lanes per agent (see train_qlambda_sparse_kernel); RLRM_QLS_LG overrides the default for A/B runs
+    const int lg_max = 32 >> kp.g_shift;
+    int lg = RLRM_QLS_LG_DEFAULT < lg_max ? RLRM_QLS_LG_DEFAULT : lg_max;
+    const char* e = getenv("RLRM_QLS_LG");
+    if (e && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) lg = atoi(e) < lg_max ? atoi(e) : lg_max;
+    kp.qls_lg = lg < 4 ? 4 : lg;
+  }
   kp.use_rsh = (cfg->use_rsh && tb->phi) ? 1 : 0;
   kp.per_agent = cfg->per_agent_rm ? 1 : 0;
   kp.nd = kp.nQ * (kp.nEv + 1);
@@ -636,8 +643,10 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
   const KP& kp = h->kp;
   const bool fast_ok = reward_out == nullptr;  // the per-step reward output exists in the generic kernels only
   if (kp.algo == RLRM_ALGO_QLAMBDA && !st->e) {
-    if (kp.per_agent) RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T, true><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
-    else RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T, false><<<blocks_for(st->n_instances * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
+    const long long ipw = 32 / (kp.qls_lg << kp.g_shift);  // instances per warp
+    const long long qls_warps = (st->n_instances + ipw - 1) / ipw;
+    if (kp.per_agent) RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T, true><<<blocks_for(qls_warps * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
+    else RLRM_BY_T(h, train_qlambda_sparse_kernel<ENV, T, false><<<blocks_for(qls_warps * 32, QLS_BLOCK), QLS_BLOCK, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
   } else if (kp.algo == RLRM_ALGO_QLAMBDA) {
     if (kp.per_agent) RLRM_BY_T(h, train_qlambda_kernel<ENV, T, true><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));
     else RLRM_BY_T(h, train_qlambda_kernel<ENV, T, false><<<(unsigned)st->n_instances, kp.A * 32, h->smem_bytes, s>>>(kp, dstate(st), t0, n_iters, learn, trace, reward_out));

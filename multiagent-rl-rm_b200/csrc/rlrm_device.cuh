@@ -26,6 +26,7 @@ struct KP {
   double one_minus_lr, trace_decay;                    // 1 - lr and gamma*lambda as doubles (float64 tables)
   int decay_on_reset, shared_q, use_rsh, random_starts, n_free;
   int shared_balanced;  // shared_train_kernel: contiguous equal chunks per block (1) or grid-stride (0)
+  int qls_lg;           // train_qlambda_sparse_kernel: lanes per agent (power of two, 4 .. 32 / G)
   // agents with different reward machines (rlrm_config_t.per_agent_rm): per-agent scalars and table strides
   int per_agent, a_nQ[RLRM_MAX_AGENTS], a_final[RLRM_MAX_AGENTS], a_nqrm[RLRM_MAX_AGENTS];
   long long a_prefix4[RLRM_MAX_AGENTS], sum4;  // float offset of agent a's table inside one instance, floats per instance

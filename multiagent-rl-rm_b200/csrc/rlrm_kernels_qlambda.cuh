@@ -158,13 +158,17 @@ __device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigne
   }
 }
 
-// One WARP per instance, one lane GROUP per agent (LG = 32 / next_pow2(A) lanes: 32, 16, 8 or 4). The scalar part of a step
+// One lane GROUP per agent (LG = p.qls_lg lanes, 4 .. 32 / next_pow2(A)), the groups of an instance adjacent, 32 / (LG * G)
+// instances per warp (LG = 32 / G: one warp per instance). The scalar part of a step
 // (Philox, epsilon-greedy, env / RM step, TD error) is computed per lane for the lane's own agent — redundantly inside a
 // group, but once per warp-instruction for all agents of the instance — and each group sweeps its own agent's list. The
 // previous one-warp-per-agent layout spent ~550 warp-instructions per agent-step at 79 % issue utilisation (ncu,
 // profiles/r01_sparse_qlambda_ncu.csv): the lists stay L1-resident for the n_iters of a launch, so the kernel is bound by
 // instruction issue, not by HBM. Episode-over detection is two warp ballots; no shared memory, no block barrier.
 #define QLS_BLOCK 128
+#ifndef RLRM_QLS_LG_DEFAULT
+#define RLRM_QLS_LG_DEFAULT 32  // lanes per agent (capped at 32 / G): 32 = one warp per instance
+#endif
 template <int ENV, typename T, bool PA>
 __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,
                                                                         unsigned* trace, double* reward_out) {
@@ -175,14 +179,20 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in
   if (PA) p_view = p_in;
   const KP& p = PA ? p_view : p_in;
   Tab tb = stage_tables(p_in);
-  const long long i = (long long)blockIdx.x * (QLS_BLOCK / 32) + (threadIdx.x >> 5);
-  if (i >= st.N) return;  // whole warps leave; nothing below synchronises across warps
+  // lanes per agent LG (p.qls_lg: 4 .. 32 / G) -> lanes per instance LI = LG * G -> 32 / LI instances per warp
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  const int LG = 32 >> p.g_shift;  // lanes per agent
-  const int a = lane / LG;         // this lane's agent (slot a >= A idles when A is not a power of two)
-  const int gl = lane - a * LG;    // lane within the agent's group
-  const bool valid = a < p.A;
+  const int LG = p_in.qls_lg, LI = LG << p_in.g_shift;
+  const long long warp = (long long)blockIdx.x * (QLS_BLOCK / 32) + (threadIdx.x >> 5);
+  const long long i_first = warp * (32 / LI);
+  if (i_first >= st.N) return;  // whole warps leave; nothing below synchronises across warps
+  const long long i_raw = i_first + lane / LI;
+  const bool inst_ok = i_raw < st.N;
+  const long long i = inst_ok ? i_raw : st.N - 1;  // lanes past the last instance idle on valid addresses
+  const int a = (lane & (LI - 1)) / LG;  // this lane's agent (slot a >= A idles when A is not a power of two)
+  const int gl = lane & (LG - 1);        // lane within the agent's group
+  const bool valid = inst_ok && a < p.A;
+  const unsigned inst_mask = (LI == 32 ? FULL : ((1u << LI) - 1u)) << (lane & ~(LI - 1));  // the lanes of this lane's instance
   const long long k = i * p_in.A + (valid ? a : 0);
   if (PA) agent_view(p_in, p_view, tb, valid ? a : 0);  // this lane group's agent has its own machine
   Slot s = {0, 0, 0, 0, 0};
@@ -299,7 +309,8 @@ __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in
                                                            ((unsigned)r.stepped << 23);
     if (reward_out && valid && gl == 0) reward_out[(size_t)it * (size_t)(st.N * p.A) + (size_t)k] = r.reward;
     // episode over <=> every agent of the instance terminated, or every agent truncated (idle lanes vote yes)
-    const bool over = __all_sync(FULL, !valid || r.term) || __all_sync(FULL, !valid || r.trunc);
+    const unsigned bt = __ballot_sync(FULL, !valid || r.term), bc = __ballot_sync(FULL, !valid || r.trunc);
+    const bool over = ((bt & inst_mask) == inst_mask) || ((bc & inst_mask) == inst_mask);
     if (valid && over) {
       episodes++;
       active_steps += s.steps;
