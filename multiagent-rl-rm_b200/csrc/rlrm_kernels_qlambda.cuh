@@ -158,8 +158,8 @@ __device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigne
   }
 }
 
-// One lane GROUP per agent (LG = p.qls_lg lanes, 4 .. 32 / next_pow2(A)), the groups of an instance adjacent, 32 / (LG * G)
-// instances per warp (LG = 32 / G: one warp per instance). The scalar part of a step
+// One lane GROUP per agent (LG = p.qls_lg lanes: 8, or 4 with more than four agents), the groups of an instance adjacent,
+// 32 / (LG * G) instances per warp — four agents' lists per warp whatever the agent count. The scalar part of a step
 // (Philox, epsilon-greedy, env / RM step, TD error) is computed per lane for the lane's own agent — redundantly inside a
 // group, but once per warp-instruction for all agents of the instance — and each group sweeps its own agent's list. The
 // previous one-warp-per-agent layout spent ~550 warp-instructions per agent-step at 79 % issue utilisation (ncu,
@@ -167,7 +167,9 @@ __device__ __forceinline__ void trace_flush(T* Q, const TraceList<T>& L, unsigne
 // instruction issue, not by HBM. Episode-over detection is two warp ballots; no shared memory, no block barrier.
 #define QLS_BLOCK 128
 #ifndef RLRM_QLS_LG_DEFAULT
-#define RLRM_QLS_LG_DEFAULT 32  // lanes per agent (capped at 32 / G): 32 = one warp per instance
+#define RLRM_QLS_LG_DEFAULT 8  // lanes per agent (capped at 32 / G): four lists per warp. Measured (profiles/r02c/r02c_qls_lanes_per_agent.json,
+                               // config 4's scenario with 1 / 2 / 4 agents): 1 agent 32 -> 8 lanes 1.82e9 -> 3.81e9, 2 agents 16 -> 8 lanes 3.05e9 -> 3.95e9;
+                               // 4 lanes halve the rate everywhere (the visited entry's lookup needs a second round, a sweep waits for the longest of 8 lists)
 #endif
 template <int ENV, typename T, bool PA>
 __global__ void __launch_bounds__(QLS_BLOCK) train_qlambda_sparse_kernel(KP p_in, DState st, unsigned long long t0, int n_iters, int learn,

@@ -531,6 +531,34 @@ def test_sparse_exact_qlambda_equals_dense_and_oracle(name, n, iters, cuda_devic
     assert int(sp.tr_len.view(n, -1)[::2].sum()) == 0
 
 
+@pytest.mark.parametrize("agents", [1, 2, 3, 4])
+@pytest.mark.parametrize("n", [1, 3, 5, 37])
+def test_sparse_qlambda_lane_layout_ragged_instance_counts(agents, n, cuda_device):
+    """The sparse Q(lambda) kernel packs several instances into one warp (eight lanes per agent: 4 / 2 / 1 / 1 instances per warp
+    for 1 / 2 / 3 / 4 agents). Instance counts that leave the last warp partly empty, and agent counts that are not a power of
+    two, must not change anything: traces, tables, slot words and trace lists against the oracle."""
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    sc = P.scenario_config4()
+    sc.starts = sc.starts[:agents]
+    sc.max_steps = 60
+    c = P.compile_scenario(sc)
+    sp = _engine(c, n, qlambda_sparse=True)
+    o = O.Oracle(c, n, "f32")
+    sp.reset(); o.reset()
+    t0 = 0
+    for chunk in (1, 130, 400):
+        ts = sp.train(chunk, trace=True)
+        to = o.train(t0, chunk, trace=True)
+        assert np.array_equal(ts.cpu().numpy().view(np.uint32), to)
+        t0 += chunk
+    e_dense = sp.sync_tables(with_traces=True)
+    assert np.array_equal(sp.q.cpu().numpy(), o.q) and np.array_equal(e_dense.cpu().numpy(), o.e)
+    assert np.array_equal(sp.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert np.array_equal(sp.stats_numpy()["episodes"], o.stats["episodes"]) and int(o.stats["episodes"].sum()) > 0
+
+
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip"])
 def test_batched_reference_style_driver_loop_equals_fused(name, cuda_device):
     """The reference driver loop written with the batched API (vec.BatchedRMEnvironment: reset / select_action / step /
