@@ -370,6 +370,27 @@ typedef struct rlrm_experience {
 int rlrm_update_list(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
                      void* stream);
 
+/* The same list update FOLLOWED, in the same launch, by the selection a driver loop makes next on that table
+ * (frozen_lake_main.py:345-367: update_policy(.., next_state, ..) of iteration t, then select_action(next_state) of iteration
+ * t + 1): QLearning.choose_action (qlearning.py:112-143) on encoded state `sel->state` with `sel->epsilon` and the four injected
+ * words `sel->draws` (w0 explore, w1 random action, w2 tie-break; best != 0: argmax). `sel` is PAGE-LOCKED HOST memory: its
+ * input fields are read by the host at call time (so the caller may overwrite them for the next request as soon as the call
+ * returns), the kernel writes `sel->action`, then `sel->done_seq = seq` behind a system-scope fence, so the host can read the
+ * result without a stream synchronisation once done_seq == seq. The table is not modified by the selection; a caller that ends
+ * up selecting on another state / epsilon simply ignores the answer. n may be 0 (selection only). 48 bytes. */
+typedef struct rlrm_select_req {
+  uint32_t state;     /* encoded state (enc = cell*nQ + q) to select in */
+  uint32_t best;      /* != 0: first argmax, no randomness */
+  double epsilon;
+  uint32_t draws[4];
+  uint32_t seq;       /* in: any value that differs from the previous request's */
+  uint32_t action;    /* out: 0..3 */
+  uint32_t done_seq;  /* out: = seq once `action` is valid */
+  uint32_t pad;
+} rlrm_select_req_t;
+int rlrm_update_list_select(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
+                            rlrm_select_req_t* sel, void* stream);
+
 /* Shared learner, inter-GPU merge: q[j] = (gathered[0][j] + gathered[1][j] + ... + gathered[world-1][j]) / world for j < n,
  * added in rank order (float32, round to nearest), so every rank gets the same bits whatever collective produced
  * `gathered` ([world][n] floats, device; e.g. the output of one NCCL all-gather of the replicas). */

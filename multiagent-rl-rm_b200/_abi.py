@@ -196,10 +196,16 @@ EXPORTED_SYMBOLS = (
     "rlrm_launch_count",
     "rlrm_iterate",
     "rlrm_update_list",
+    "rlrm_update_list_select",
     "rlrm_merge_replicas",
     "rlrm_stream_sync",
     "rlrm_probe_random_gather",
 )
+
+
+class SelectReq(C.Structure):  # rlrm_select_req_t
+    _fields_ = [("state", C.c_uint32), ("best", C.c_uint32), ("epsilon", C.c_double), ("draws", C.c_uint32 * 4), ("seq", C.c_uint32),
+                ("action", C.c_uint32), ("done_seq", C.c_uint32), ("pad", C.c_uint32)]
 
 
 class Experience(C.Structure):

@@ -99,6 +99,7 @@ def load():
     L.rlrm_qlambda_materialize.argtypes = [vp, C.POINTER(abi.State), vp, vp]
     L.rlrm_iterate.argtypes = [vp, C.POINTER(abi.State), u64, i32, vp, vp, vp]
     L.rlrm_update_list.argtypes = [vp, C.POINTER(abi.State), i64, i32, vp, vp]
+    L.rlrm_update_list_select.argtypes = [vp, C.POINTER(abi.State), i64, i32, vp, vp, vp]
     L.rlrm_merge_replicas.argtypes = [vp, vp, i32, i64, vp, vp]
     L.rlrm_stream_sync.argtypes = [vp, vp]
     L.rlrm_probe_random_gather.argtypes = [C.c_int, vp, i64, i32, i64, i32, vp, vp]
@@ -106,7 +107,7 @@ def load():
     L.rlrm_launch_count.restype = i64
     for name in ("rlrm_create", "rlrm_destroy", "rlrm_set_learner", "rlrm_reset", "rlrm_reset_at", "rlrm_select_action", "rlrm_step",
                  "rlrm_rm_step", "rlrm_rm_step_agent", "rlrm_mdp", "rlrm_value_iteration", "rlrm_update", "rlrm_train", "rlrm_train_host", "rlrm_evaluate", "rlrm_qlambda_materialize",
-                 "rlrm_iterate", "rlrm_update_list", "rlrm_merge_replicas", "rlrm_stream_sync", "rlrm_probe_random_gather"):
+                 "rlrm_iterate", "rlrm_update_list", "rlrm_update_list_select", "rlrm_merge_replicas", "rlrm_stream_sync", "rlrm_probe_random_gather"):
         getattr(L, name).restype = C.c_int
     if L.rlrm_abi_version() != abi.ABI_VERSION:
         raise RuntimeError("librlrm_b200.so ABI version mismatch: rebuild")

@@ -940,19 +940,36 @@ extern "C" int rlrm_iterate(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t
   return RLRM_OK;
 }
 
-extern "C" int rlrm_update_list(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
-                                void* stream) {
+static int update_list_impl(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
+                            rlrm_select_req_t* sel, void* stream) {
   int rc = check_state(h, st, true);
   if (rc) return rc;
   if (n < 0 || (n > 0 && !experiences)) return fail(RLRM_ERR_ARG, "rlrm_update_list: bad experience list");
   if (slot < 0 || slot >= st->n_instances * h->kp.A) return fail(RLRM_ERR_ARG, "rlrm_update_list: slot out of range");
   if (h->kp.shared_q) return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update_list on a shared table (proposals need the synchronous iteration of rlrm_train)");
   if (h->kp.algo == RLRM_ALGO_QLAMBDA && !st->e) return fail(RLRM_ERR_UNSUPPORTED, "rlrm_update_list on Q(lambda) needs dense traces (state.e)");
-  if (n == 0) return RLRM_OK;
+  if (n == 0 && !sel) return RLRM_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  RLRM_BY_T(h, update_list_kernel<T><<<1, h->kp.algo == RLRM_ALGO_QLAMBDA ? 256 : 32, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), slot, n, experiences));
+  SelArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  if (sel) {  // page-locked host memory: the request is read here, the answer is written by the kernel
+    sa.state = sel->state; sa.best = sel->best; sa.epsilon = sel->epsilon; sa.seq = sel->seq;
+    for (int j = 0; j < 4; j++) sa.draws[j] = sel->draws[j];
+  }
+  RLRM_BY_T(h, update_list_kernel<T><<<1, (h->kp.algo == RLRM_ALGO_QLAMBDA && n > 0) ? 256 : 32, 0, (cudaStream_t)stream>>>(h->kp, dstate(st), slot, n, experiences, sel, sa));
   LAUNCH_CHECK(h);
   return RLRM_OK;
+}
+
+extern "C" int rlrm_update_list(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
+                                void* stream) {
+  return update_list_impl(h, st, slot, n, experiences, nullptr, stream);
+}
+
+extern "C" int rlrm_update_list_select(rlrm_handle_t* h, const rlrm_state_t* st, int64_t slot, int32_t n, const rlrm_experience_t* experiences,
+                                       rlrm_select_req_t* sel, void* stream) {
+  if (!sel) return fail(RLRM_ERR_ARG, "rlrm_update_list_select: null selection request");
+  return update_list_impl(h, st, slot, n, experiences, sel, stream);
 }
 
 extern "C" int rlrm_merge_replicas(rlrm_handle_t* h, const float* gathered, int32_t world, int64_t n, float* q, void* stream) {

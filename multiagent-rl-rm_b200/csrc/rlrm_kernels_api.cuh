@@ -328,8 +328,15 @@ __global__ void __launch_bounds__(256) update_qlambda_kernel(KP p_in, DState st,
 // QLearning.update (qlearning.py:82-106) hands its experiences over as one list instead of one launch per experience.
 // Q-learning / QRM: thread 0 applies them one after the other (each update may read what the previous one wrote);
 // Q(lambda): the whole block sweeps the table once per experience.
+struct SelArgs {  // the input half of rlrm_select_req_t, passed by value (read on the host at call time)
+  unsigned state, best;
+  double epsilon;
+  unsigned draws[4];
+  unsigned seq;
+};
 template <typename T>
-__global__ void __launch_bounds__(256) update_list_kernel(KP p, DState st, long long slot, int n, const rlrm_experience_t* ex) {
+__global__ void __launch_bounds__(256) update_list_kernel(KP p, DState st, long long slot, int n, const rlrm_experience_t* ex,
+                                                         rlrm_select_req_t* sel, SelArgs sa) {
   const long long i = slot / p.A;
   const int a = (int)(slot - i * p.A);
   const size_t base = table_base(p, i, a);
@@ -357,6 +364,15 @@ __global__ void __launch_bounds__(256) update_list_kernel(KP p, DState st, long 
     for (int j = 0; j < n; j++)
       update_q<T>(p, Q, V, min(ex[j].s, rows - 1u), min((int)ex[j].action, RLRM_N_ACTIONS - 1), ex[j].reward, min(ex[j].sn, rows - 1u),
                   ex[j].terminated != 0, none);
+  }
+  // rlrm_update_list_select: the next selection on the updated table (thread 0 is also the thread that wrote the QL / QRM
+  // updates; the Q(lambda) sweeps ended with a block barrier)
+  if (sel && threadIdx.x == 0) {
+    const unsigned w[4] = {sa.draws[0], sa.draws[1], sa.draws[2], sa.draws[3]};
+    const typename RT<T>::row_t row = load_row<T>(Q, min(sa.state, rows - 1u));
+    *reinterpret_cast<volatile unsigned*>(&sel->action) = (unsigned)select_action(row, explore_threshold(sa.epsilon), w, sa.best != 0, p.n_actions);
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(&sel->done_seq) = sa.seq;
   }
 }
 

@@ -164,8 +164,12 @@ class BaseLearningAlgorithm:
 class _TabularBase(BaseLearningAlgorithm):
     _ALGO = abi.ALGO_QL
     # staging block layout (bytes): 0 slot u64 | 8 epsilon f64 | 16 draws 4 x u32 | 59 selected action (output) u8 |
+    # 64..111 one rlrm_select_req_t (the look-ahead selection of rlrm_update_list_select) |
     # 1024.. a ring of _RING blocks of _BLOCK rlrm_experience_t (24 bytes each) for rlrm_update_list
-    _RING, _BLOCK, _EXP_OFF = 8, 16, 1024
+    _RING, _BLOCK, _EXP_OFF, _SEL_OFF = 8, 16, 1024, 64
+    _LOOKAHEAD = True  # class-wide switch of the look-ahead selection (tests compare on / off: identical decisions and tables)
+    lookahead_hits = 0  # per learner: choose_action calls answered by the look-ahead / launched on their own
+    lookahead_misses = 0
     _STAGE_BYTES = 1024 + 8 * 16 * 24
 
     def _setup(self, q_init, lambd=0.0):
@@ -190,10 +194,17 @@ class _TabularBase(BaseLearningAlgorithm):
         self._st = abi.State(1, self._base, self._base + 8, self._q.data_ptr(), None if self._e is None else self._e.data_ptr(),
                              self._visits.data_ptr(), None, None, None, None, None)
         self._hp = (self.learning_rate, self.gamma, lambd)
+        # look-ahead selection (see _device_update_list): key of the request in flight, its sequence number, and the four
+        # words already taken from self.rng for the NEXT choose_action call (consumed by it whether or not the look-ahead hits)
+        self._spec = None
+        self._spec_seq = 0
+        self.__dict__.setdefault("_pending_words", None)
+        self._pending_rng = self.rng if self._pending_words is not None else None
 
     # tables as views of exactly (S, A)
     @property
     def q_table(self):
+        self._spec = None  # the caller may write through the view: a selection computed ahead of that write is void
         return DeviceTable(self._q[: self.state_space_size, : self.action_space_size])
 
     @q_table.setter
@@ -219,28 +230,64 @@ class _TabularBase(BaseLearningAlgorithm):
     def _sync(self):
         check(self._th.L.rlrm_stream_sync(self._th.h, self._th.stream()))
 
-    def _device_update_list(self, experiences):
+    def _device_update_list(self, experiences, next_enc=None):
         """update_q / the Q(lambda) update for a list of (s, a, r, s', terminated) experiences, applied in order on the device
         by ONE launch per _BLOCK experiences (rlrm_update_list). Asynchronous: the next selection (or any read of the
-        tables through torch, which runs on the same stream) is ordered after it."""
+        tables through torch, which runs on the same stream) is ordered after it.
+
+        next_enc: the encoded state the driver loop will select in next (update_policy's next_state). When given, the LAST
+        launch also evaluates that selection on the updated table (rlrm_update_list_select) with the four words the next
+        choose_action call would draw from self.rng — taken now, kept as the pending words of that call — so that the call
+        finds its answer in page-locked memory instead of launching and synchronising. Any other outcome (another state,
+        another epsilon, a caller-supplied rng, a table write in between) falls back to the ordinary launch with the SAME
+        words, so the stream of random words and every decision are identical with and without the look-ahead."""
         self._sync_hyper()
         S, L, th = self.state_space_size, self._th.L, self._th
-        for lo in range(0, len(experiences), self._BLOCK):
+        self._spec = None
+        look = (self._LOOKAHEAD and next_enc is not None and self.action_selection == "greedy" and type(self.rng) is np.random.Generator
+                and 0 <= int(next_enc) < S)
+        last = len(experiences) - self._BLOCK if experiences else 0
+        for lo in range(0, max(len(experiences), 1), self._BLOCK):
             chunk = experiences[lo:lo + self._BLOCK]
-            blk = self._ring % self._RING
-            if blk == 0 and self._ring:
-                self._sync()  # the ring wrapped: make sure the launches that read these blocks have finished
-            off = self._EXP_OFF + blk * self._BLOCK * 24
-            for j, (s_, a_, r_, sn_, done_) in enumerate(chunk):
-                s_, sn_ = int(s_), int(sn_)
-                if not (0 <= s_ < S and 0 <= sn_ < S):
-                    raise IndexError(f"encoded state {s_ if not 0 <= s_ < S else sn_} out of range for state_space_size {S}")
-                struct.pack_into("<IIBB6xd", self._stage_mv, off + 24 * j, s_, sn_, int(a_), int(bool(done_)), float(r_))
-            check(L.rlrm_update_list(th.h, C.byref(self._st), 0, len(chunk), self._base + off, th.stream()))
-            self._ring += 1
+            off = self._EXP_OFF
+            if chunk:
+                blk = self._ring % self._RING
+                if blk == 0 and self._ring:
+                    self._sync()  # the ring wrapped: make sure the launches that read these blocks have finished
+                off = self._EXP_OFF + blk * self._BLOCK * 24
+                for j, (s_, a_, r_, sn_, done_) in enumerate(chunk):
+                    s_, sn_ = int(s_), int(sn_)
+                    if not (0 <= s_ < S and 0 <= sn_ < S):
+                        raise IndexError(f"encoded state {s_ if not 0 <= s_ < S else sn_} out of range for state_space_size {S}")
+                    struct.pack_into("<IIBB6xd", self._stage_mv, off + 24 * j, s_, sn_, int(a_), int(bool(done_)), float(r_))
+                self._ring += 1
+            if look and lo >= last:
+                if self._pending_words is None or self._pending_rng is not self.rng:
+                    self._pending_words = self._own_words()
+                    self._pending_rng = self.rng
+                self._spec_seq = (self._spec_seq + 1) & 0xFFFFFFFF
+                eps = float(self.epsilon)
+                struct.pack_into("<IIdIIIII", self._stage_mv, self._SEL_OFF, int(next_enc), 0, eps, *self._pending_words, self._spec_seq)
+                check(L.rlrm_update_list_select(th.h, C.byref(self._st), 0, len(chunk), self._base + off, self._base + self._SEL_OFF, th.stream()))
+                self._spec = (int(next_enc), eps)
+            elif chunk:
+                check(L.rlrm_update_list(th.h, C.byref(self._st), 0, len(chunk), self._base + off, th.stream()))
 
     def _device_update(self, s, sn, action, reward, terminated):
-        self._device_update_list([(s, action, reward, sn, terminated)])
+        self._device_update_list([(s, action, reward, sn, terminated)], next_enc=sn)
+
+    _WORD_BLOCK = 64  # words taken from self.rng per numpy call (16 selections' worth)
+
+    def _own_words(self):
+        """The next four 32-bit words of self.rng's stream. They are fetched _WORD_BLOCK at a time — numpy fills an array with
+        the same per-element routine as a scalar request, so the sequence of words is that of four-word requests — and handed
+        out in order; a block drawn from a generator that has since been replaced is dropped."""
+        buf = self.__dict__.get("_word_buf")
+        if buf is None or buf[0] is not self.rng or buf[2] >= len(buf[1]):
+            buf = self.__dict__["_word_buf"] = [self.rng, self.rng.integers(0, 1 << 32, size=self._WORD_BLOCK, dtype=np.uint64).tolist(), 0]
+        k = buf[2]
+        buf[2] = k + 4
+        return buf[1][k:k + 4]
 
     @staticmethod
     def _raw_words(rng):
@@ -256,7 +303,27 @@ class _TabularBase(BaseLearningAlgorithm):
                 raise NotImplementedError("softmax selection is out of scope (no reference driver uses it; DESIGN.md §8)")
             raise ValueError("Unsupported action selection method")
         cell, q = self._split(encoded_state)
-        words = [0, 0, 0, 0] if best else [int(x) & 0xFFFFFFFF for x in self._raw_words(self.rng if rng is None else rng)]
+        own = rng is None or rng is self.rng
+        spec, self._spec = self._spec, None
+        if spec is not None and own and not best and self._pending_rng is self.rng and spec == (int(encoded_state), float(self.epsilon)):
+            # the look-ahead selection launched with the last update answers this call (same state, epsilon, words, table)
+            if int(self._stage_np[self._SEL_OFF + 40:self._SEL_OFF + 44].view(np.uint32)[0]) != self._spec_seq:
+                self._sync()
+            self._pending_words = None
+            self.lookahead_hits += 1
+            return int(self._stage_np[self._SEL_OFF + 36])
+        self.lookahead_misses += 1
+        if best:
+            words = [0, 0, 0, 0]
+        elif own and self._pending_words is not None and self._pending_rng is self.rng:
+            words, self._pending_words = self._pending_words, None  # drawn ahead for this very call
+        else:
+            if own:
+                self._pending_words = None  # self.rng was replaced since: words of the old generator are void
+            if own and type(self.rng) is np.random.Generator:
+                words = self._own_words()
+            else:
+                words = [int(x) & 0xFFFFFFFF for x in self._raw_words(self.rng if rng is None else rng)]
         struct.pack_into("<QdIIII", self._stage_mv, 0, (cell << abi.SLOT_CELL_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT), float(self.epsilon), *words)
         th = self._th
         check(th.L.rlrm_select_action(th.h, C.byref(self._st), None if best else self._base + 16, 0, int(bool(best)), self._base + 59,
@@ -275,7 +342,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_base", "_ring")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_base", "_ring", "_spec", "_spec_seq", "_pending_rng")}
         d["device"] = str(self.device)
         d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
                         "visits": self._visits.cpu().numpy()}
@@ -335,8 +402,7 @@ class QLearning(_TabularBase):
                     _r += self.gamma * rm.potentials.get(rm.get_state_from_index(nxt_q), 0) - rm.potentials.get(
                         rm.get_state_from_index(cur_q), 0)
                 todo.append((_s, _a, _r, _sn, _done))
-            if todo:
-                self._device_update_list(todo)
+            self._device_update_list(todo, next_enc=encoded_next_state)
         else:
             self._device_update(encoded_state, encoded_next_state, action, reward, terminated)
         return False

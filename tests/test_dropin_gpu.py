@@ -274,3 +274,127 @@ def test_learner_pickle_round_trip_and_table_export(dtype, cuda_device, tmp_path
     single = Engine(c, 3)
     P.load_q_tables_into(single, {"a1": tables["a1"][0], "a2": tables["a2"][0]})
     assert np.array_equal(single.q.cpu().numpy().reshape(3, 2, 400, 4)[2], eng.q.cpu().numpy().reshape(8, 2, 400, 4)[0])
+
+
+# ---------------------------------------------------------------------------------------------- look-ahead selection
+def _genuine_rng_loop(sc_dict, iters, lookahead, seed=77):
+    """The reference driver loop over the drop-in classes with GENUINE numpy generators (no injected words): the only
+    configuration in which the learners' look-ahead selection (rlrm_update_list_select) is active."""
+    import copy
+
+    from multiagent_rlrm_b200.learners import _TabularBase
+
+    from dropin_builder import build_b200
+
+    old = _TabularBase._LOOKAHEAD
+    _TabularBase._LOOKAHEAD = lookahead
+    try:
+        rm_env, env, agents = build_b200(sc_dict)
+        for k, ag in enumerate(agents):
+            ag.get_learning_algorithm().rng = np.random.default_rng(1000 * seed + k)
+        fl = sc_dict["driver"] == "frozen_lake_main"
+        log, it, ep = [], 0, 0
+        while it < iters:
+            states, _ = rm_env.reset(seed + ep)
+            ep += 1
+            if not fl:
+                states = copy.deepcopy(states)
+            while it < iters:
+                actions = {ag.name: ag.select_action(rm_env.env.get_state(ag)) for ag in rm_env.agents}
+                new_states, rewards, term, trunc, infos = rm_env.step(actions)
+                log.append((tuple(actions[a.name].name for a in agents), tuple(rewards[a.name] for a in agents),
+                            tuple(tuple(sorted(new_states[a.name].items())) for a in agents)))
+                for ag in rm_env.agents:
+                    ta = (term[ag.name] or trunc[ag.name]) if fl else term[ag.name]
+                    ag.update_policy(state=states[ag.name], action=actions[ag.name], reward=rewards[ag.name],
+                                     next_state=new_states[ag.name], terminated=ta, infos=infos[ag.name])
+                states = copy.deepcopy(new_states)
+                it += 1
+                if all(term.values()) or all(trunc.values()):
+                    break
+        tables = [np.array(ag.get_learning_algorithm().q_table) for ag in agents]
+        hits = sum(ag.get_learning_algorithm().lookahead_hits for ag in agents)
+        misses = sum(ag.get_learning_algorithm().lookahead_misses for ag in agents)
+        tail = []  # where every learner's word stream stands: eight forced explorations (action = f(next words))
+        for ag in agents:
+            la = ag.get_learning_algorithm()
+            la.epsilon = 1.0
+            tail.append([la.choose_action(0) for _ in range(8)])
+        return log, tables, hits, misses, tail
+    finally:
+        _TabularBase._LOOKAHEAD = old
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3_ql", "cfg2_office_slip", "office_qlambda"])
+def test_lookahead_selection_changes_nothing(name, cuda_device):
+    """update_policy launches the NEXT selection together with the update (rlrm_update_list_select) and select_action then
+    reads the answer from page-locked memory. Decisions, rewards, positions, Q tables and the state of every learner's
+    generator must be identical with the look-ahead switched off — and the look-ahead must actually be used."""
+    import multiagent_rlrm_b200 as P
+
+    if name == "office_qlambda":
+        sc = P.scenario_config4()
+        sc.starts, sc.max_steps = sc.starts[:2], 80
+    else:
+        sc = {"cfg1": P.scenario_config1, "cfg3_ql": lambda: P.scenario_config3(False), "cfg2_office_slip": lambda: P.scenario_config2(True)}[name]()
+    d = sc.to_dict()
+    on = _genuine_rng_loop(d, 700, True)
+    off = _genuine_rng_loop(d, 700, False)
+    assert on[0] == off[0]
+    for a, b in zip(on[1], off[1]):
+        assert np.array_equal(a, b)
+    assert on[4] == off[4]  # every learner's word stream stands at the same position
+    assert off[2] == 0 and on[2] > 0.8 * (on[2] + on[3]), (on[2], on[3])
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_update_list_select_equals_update_list_then_select(dtype, cuda_device):
+    """C ABI: rlrm_update_list_select == rlrm_update_list followed by rlrm_select_action (same table, same action), for
+    random experience lists (also empty ones), states, epsilons, words, with and without best."""
+    import ctypes as C
+
+    import torch
+
+    import multiagent_rlrm_b200 as P
+    from multiagent_rlrm_b200 import _abi as abi
+    from multiagent_rlrm_b200._lib import check
+
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        a = P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=0.3, state_space_size=97, action_space_size=4,
+                        table_dtype=dtype)
+        b = P.QLearning(gamma=0.9, action_selection="greedy", learning_rate=0.3, state_space_size=97, action_space_size=4,
+                        table_dtype=dtype)
+        init = rng.integers(0, 4, size=(97, 4)).astype(np.float64)  # plenty of ties
+        a.q_table[:] = init
+        b.q_table[:] = init
+        for step in range(20):
+            n = int(rng.integers(0, 6))
+            exps = [(int(rng.integers(0, 97)), int(rng.integers(0, 4)), float(rng.integers(-2, 3)), int(rng.integers(0, 97)),
+                     bool(rng.integers(0, 2))) for _ in range(n)]
+            state, best = int(rng.integers(0, 97)), bool(rng.integers(0, 4) == 0)
+            eps = float(rng.choice([0.0, 0.3, 1.0]))
+            words = [int(x) for x in rng.integers(0, 1 << 32, size=4, dtype=np.uint64)]
+            # (1) two calls
+            if exps:
+                b._device_update_list(exps)
+            b.epsilon = eps
+
+            class _W:
+                def words(self):
+                    return words
+
+            want = b.choose_action(state, best=best, rng=_W())
+            # (2) one call
+            req = abi.SelectReq.from_buffer(a._stage_np, a._SEL_OFF)
+            req.state, req.best, req.epsilon, req.seq = state, int(best), eps, 1000 + step
+            for j in range(4):
+                req.draws[j] = words[j]
+            for j, (s_, a_, r_, sn_, done_) in enumerate(exps):
+                e = abi.Experience.from_buffer(a._stage_np, a._EXP_OFF + 24 * j)
+                e.s, e.sn, e.action, e.terminated, e.reward = s_, sn_, a_, int(done_), r_
+            check(a._th.L.rlrm_update_list_select(a._th.h, C.byref(a._st), 0, len(exps), a._base + a._EXP_OFF, a._base + a._SEL_OFF,
+                                                  a._th.stream()))
+            torch.cuda.synchronize()
+            assert req.done_seq == 1000 + step and req.action == want, (trial, step)
+            assert np.array_equal(np.array(a.q_table), np.array(b.q_table))

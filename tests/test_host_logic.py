@@ -30,6 +30,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "rlrm_state_t": [f for f, _ in abi.State._fields_],
         "rlrm_step_out_t": [f for f, _ in abi.StepOut._fields_],
         "rlrm_eval_t": [f for f, _ in abi.Eval._fields_],
+        "rlrm_select_req_t": [f for f, _ in abi.SelectReq._fields_],
+        "rlrm_experience_t": [f for f, _ in abi.Experience._fields_],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for st, fs in fields.items():
@@ -43,11 +45,12 @@ def test_ctypes_structs_match_the_header(tmp_path):
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
     out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     for st, cls in (("rlrm_config_t", abi.Config), ("rlrm_tables_t", abi.Tables), ("rlrm_stats_t", abi.Stats),
-                    ("rlrm_state_t", abi.State), ("rlrm_step_out_t", abi.StepOut), ("rlrm_eval_t", abi.Eval)):
+                    ("rlrm_state_t", abi.State), ("rlrm_step_out_t", abi.StepOut), ("rlrm_eval_t", abi.Eval),
+                    ("rlrm_select_req_t", abi.SelectReq), ("rlrm_experience_t", abi.Experience)):
         assert int(out[st]) == C.sizeof(cls), st
         for f, _ in cls._fields_:
             assert int(out[f"{st}.{f}"]) == getattr(cls, f).offset, f"{st}.{f}"
-    assert C.sizeof(abi.Stats) == 32
+    assert C.sizeof(abi.Stats) == 32 and C.sizeof(abi.SelectReq) == 48 and C.sizeof(abi.Experience) == 24
 
 
 def test_library_loads_and_exports_every_declared_symbol():
