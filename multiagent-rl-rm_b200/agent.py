@@ -10,14 +10,17 @@ class UPValueError(Exception):
 
 
 def _plain_getter(attr):
-    return lambda self: getattr(self, attr)
+    """Accessor method `lambda self: self.<attr>` compiled with the attribute name in its bytecode (no getattr call: the
+    accessors are called ~100 times per driver-loop iteration of the one-instance classes)."""
+    scope = {}
+    exec(f"def get(self):\n    return self.{attr}", scope)
+    return scope["get"]
 
 
 def _plain_setter(attr):
-    def setter(self, value):
-        setattr(self, attr, value)
-
-    return setter
+    scope = {}
+    exec(f"def put(self, value):\n    self.{attr} = value", scope)
+    return scope["put"]
 
 
 class AgentRL:
@@ -53,6 +56,24 @@ class AgentRL:
         return self.actions_dict
 
     def actions_idx(self, action):
+        """index of `action` in actions_dix() (first match, None when absent) — looked up through a reverse map that is rebuilt
+        whenever the action list or the index dict changed"""
+        acts, known = self.actions_, self.actions_dict
+        cache = self.__dict__.get("_idx_cache")
+        if cache is None or cache[0] != tuple(acts) or cache[1] != len(known):
+            table = {}
+            for k, v in self.actions_dix().items():
+                try:
+                    table.setdefault(v, k)
+                except TypeError:  # unhashable action objects: keep the linear scan
+                    table = None
+                    break
+            cache = self.__dict__["_idx_cache"] = (tuple(acts), len(self.actions_dict), None, table)
+        if cache[3] is not None:
+            try:
+                return cache[3].get(action)
+            except TypeError:
+                pass
         return next((k for k, v in self.actions_dix().items() if v == action), None)
 
     # -- wiring ------------------------------------------------------------------------------------------------------

@@ -23,11 +23,13 @@ class _GridStateEncoder(StateEncoder):
         return p.grid_width, p.grid_height, self.agent.get_reward_machine().numbers_state()
 
     def encode(self, state, state_rm=None):
-        width, height, n_rm = self._dims()
-        q = self.encode_rm_state(state_rm)
+        agent = self.agent
+        p, rm = agent.ma_problem, agent.get_reward_machine()
+        width, n_rm = p.grid_width, rm.numbers_state()
+        q = rm.get_state_index(rm.get_current_state() if state_rm is None else state_rm)  # encode_rm_state, inlined
         s = state["pos_y"] * width + state["pos_x"]
         enc = s * n_rm + q
-        if enc >= width * height * n_rm:
+        if enc >= width * p.grid_height * n_rm:
             raise ValueError("Encoded state index exceeds total state space size.")
         return enc, {"s": s, "q": q}
 

@@ -259,7 +259,9 @@ class Engine:
                 off += -(-nbytes // 16) * 16
             so = abi.StepOut(*[ptrs[k] for k in abi.STEP_OUT_FIELDS], None, None)
             so_cf = abi.StepOut(*[ptrs[k] for k in abi.STEP_OUT_FIELDS], ptrs["cf_q"], ptrs["cf_r"])
-            self._hio = {"buf": buf, "v": views, "p": ptrs, "so": so, "so_cf": so_cf, "n_qrm": nq}
+            self._hio = {"buf": buf, "v": views, "p": ptrs, "so": so, "so_cf": so_cf, "n_qrm": nq, "so_ref": C.byref(so), "so_cf_ref": C.byref(so_cf),
+                         "stream": torch.cuda.Stream(device=self.device)}
+            self._state_ref = C.byref(self.state)
         return self._hio
 
     def step_host(self, actions, draws=None, with_rm: bool = True, counterfactuals: bool = False):
@@ -269,13 +271,16 @@ class Engine:
         one launch, one synchronisation. Returns numpy views of the record, valid until the next call."""
         if not self.host_control:
             raise RuntimeError("step_host needs an Engine built with host_control=True")
-        io = self._host_io()
+        io = self._hio or self._host_io()
         io["v"]["actions"][:] = actions
-        if draws is not None:
+        if draws is not None and draws is not True:  # True: the caller wrote the words into io["v"]["draws"] itself
             io["v"]["draws"][:] = draws
-        check(self.L.rlrm_step(self.h, C.byref(self.state), io["p"]["actions"], io["p"]["draws"] if draws is not None else None, 0,
-                               int(with_rm), C.byref(io["so_cf"] if counterfactuals else io["so"]), self._stream()))
-        self.sync()
+        # the step touches nothing but this engine's page-locked control block, so it runs on a stream of its own: it does not
+        # queue behind the learners' update launches on torch's current stream, and the synchronisation waits for it alone
+        stream = io["stream"].cuda_stream
+        check(self.L.rlrm_step(self.h, self._state_ref, io["p"]["actions"], io["p"]["draws"] if draws is not None else None, 0,
+                               int(with_rm), io["so_cf_ref"] if counterfactuals else io["so_ref"], stream))
+        check(self.L.rlrm_stream_sync(self.h, stream))
         return io["v"]
 
     def train_host(self, n_iters: int, host_stats: torch.Tensor, host_slot: Optional[torch.Tensor] = None,

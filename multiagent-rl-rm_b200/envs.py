@@ -107,27 +107,35 @@ class BaseEnvironment:
         return self._engine
 
     def _pack_slots(self, out):
-        W = self.grid_width
-        for i, a in enumerate(self.agents):
+        W, first, t = self.grid_width, (abi.FLAG_FIRST if self._first else 0), int(self.timestep) << abi.SLOT_TIME_SHIFT
+        active, fail, steps = self.active_agents, self.agent_fail, self.agent_steps
+        for i, a in enumerate(self._agents):
             x, y = a.get_position()
             rm = getattr(a, "reward_machine", None)
             q = rm.get_state_index(rm.get_current_state()) if rm is not None else 0
-            flags = (abi.FLAG_ACTIVE if self.active_agents.get(a.name, True) else 0) | \
-                    (abi.FLAG_FAIL if self.agent_fail.get(a.name, False) else 0) | (abi.FLAG_FIRST if self._first else 0)
-            out[i] = ((y * W + x) << abi.SLOT_CELL_SHIFT) | (int(self.agent_steps.get(a.name, 0)) << abi.SLOT_STEPS_SHIFT) \
-                | (int(self.timestep) << abi.SLOT_TIME_SHIFT) | (q << abi.SLOT_RMSTATE_SHIFT) | (flags << abi.SLOT_FLAGS_SHIFT)
+            name = a.name
+            flags = (abi.FLAG_ACTIVE if active.get(name, True) else 0) | (abi.FLAG_FAIL if fail.get(name, False) else 0) | first
+            out[i] = ((y * W + x) << abi.SLOT_CELL_SHIFT) | (int(steps.get(name, 0)) << abi.SLOT_STEPS_SHIFT) | t \
+                | (q << abi.SLOT_RMSTATE_SHIFT) | (flags << abi.SLOT_FLAGS_SHIFT)
 
-    def _slip_words(self):
-        """One 32-bit slip word per agent from env.rng (`rng.words(i)` hook = trace injection): uint32 [A*4]."""
-        n = len(self.agents)
-        w = np.zeros((n, 4), dtype=np.uint32)
+    _WORD_BLOCK = 64  # slip words taken from env.rng per numpy call
+
+    def _slip_words(self, out):
+        """One 32-bit slip word per agent from env.rng (`rng.words(i)` hook = trace injection) written into the uint32 [A*4]
+        draw block `out` (word 3 of every agent). A genuine numpy generator is read _WORD_BLOCK words at a time — the same
+        sequence as per-step requests; a block belongs to the generator object it was drawn from (reset() installs a new one)."""
+        n = len(self._agents)
         rng = self.rng if self.rng is not None else np.random.default_rng()
         if hasattr(rng, "words"):
             for i in range(n):
-                w[i] = [int(v) & 0xFFFFFFFF for v in rng.words(i)]
-        else:
-            w[:, 3] = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
-        return w.reshape(-1)
+                out[4 * i:4 * i + 4] = [int(v) & 0xFFFFFFFF for v in rng.words(i)]
+            return
+        buf = self.__dict__.get("_slip_buf")
+        if buf is None or buf[0] is not rng or buf[2] + n > len(buf[1]):
+            buf = self.__dict__["_slip_buf"] = [rng, rng.integers(0, 1 << 32, size=max(self._WORD_BLOCK, n), dtype=np.uint64).astype(np.uint32), 0]
+        k = buf[2]
+        buf[2] = k + n
+        out[3::4] = buf[1][k:k + n]
 
     def _device_step(self, actions, with_rm: bool, reward_modifier=1, counterfactuals=False):
         """rlrm_step on the packed host state: ONE launch that reads the slot words / actions / slip words from page-locked
@@ -136,7 +144,8 @@ class BaseEnvironment:
         eng = self._get_engine(reward_modifier)
         acts = []
         stochastic_fl = getattr(self, "frozen_lake_stochastic", False)
-        for a in self.agents:
+        agents = self._agents
+        for a in agents:
             act = actions[a.name]
             name = act if isinstance(act, str) else act.name
             if name not in _A2I:
@@ -146,21 +155,30 @@ class BaseEnvironment:
             acts.append(_A2I[name])
         slot = self._slot_np
         self._pack_slots(slot)
-        draws = self._slip_words() if eng.cfg.stochastic else None
+        draws = None
+        if eng.cfg.stochastic:
+            self._slip_words((eng._hio or eng._host_io())["v"]["draws"])
+            draws = True  # written in place
         out = eng.step_host(acts, draws, with_rm=with_rm, counterfactuals=counterfactuals)
         W = self.grid_width
         timestep = self.timestep + 1
-        for i, a in enumerate(self.agents):
-            w = int(slot[i])
+        active, fail, steps = self.active_agents, self.agent_fail, self.agent_steps
+        words = slot[:len(agents)].tolist()
+        for i, a in enumerate(agents):
+            w = words[i]
             cell = w & 0xFFFF
-            if (cell % W, cell // W) != tuple(a.get_position()):
-                a.set_position(cell % W, cell // W)
+            x, y = cell % W, cell // W
+            if (x, y) != tuple(a.get_position()):
+                a.set_position(x, y)
             fl = (w >> abi.SLOT_FLAGS_SHIFT) & 0xFF
-            self.active_agents[a.name] = bool(fl & abi.FLAG_ACTIVE)
-            self.agent_fail[a.name] = bool(fl & abi.FLAG_FAIL)
-            self.agent_steps[a.name] = (w >> abi.SLOT_STEPS_SHIFT) & 0xFFFF
-            if with_rm and getattr(a, "reward_machine", None) is not None:
-                a.reward_machine.current_state = a.reward_machine.get_state_from_index((w >> abi.SLOT_RMSTATE_SHIFT) & 0xFF)
+            name = a.name
+            active[name] = bool(fl & abi.FLAG_ACTIVE)
+            fail[name] = bool(fl & abi.FLAG_FAIL)
+            steps[name] = (w >> abi.SLOT_STEPS_SHIFT) & 0xFFFF
+            if with_rm:
+                rm = getattr(a, "reward_machine", None)
+                if rm is not None:
+                    rm.current_state = rm.get_state_from_index((w >> abi.SLOT_RMSTATE_SHIFT) & 0xFF)
             if i == 0:
                 timestep = (w >> abi.SLOT_TIME_SHIFT) & 0xFFFF
         self.timestep = timestep
@@ -260,15 +278,23 @@ class MultiAgentFrozenLake(BaseEnvironment):
 
     def _step(self, actions, with_rm, reward_modifier=1, counterfactuals=False):
         rec = self._device_step(actions, with_rm, reward_modifier, counterfactuals)
-        self.rewards = {a.name: 0 for a in self.agents}
-        infos, terms, truncs = {}, {}, {}
-        for i, a in enumerate(self.agents):
-            infos[a.name] = {"prev_s": self._pos(rec["prev_cell"][i]), "s": self._pos(rec["cell"][i]),
-                             "Renv": _num(rec["renv"][i])}
-            self.rewards[a.name] += _num(rec["renv"][i])
-            terms[a.name] = bool(rec["env_term"][i])
-            truncs[a.name] = bool(rec["trunc"][i])
-        return {a.name: a.state for a in self.agents}, self.rewards, terms, truncs, infos, rec
+        agents, W = self._agents, self.grid_width
+        n = len(agents)
+        prev, cell, renv = rec["prev_cell"][:n].tolist(), rec["cell"][:n].tolist(), rec["renv"][:n].tolist()
+        env_term, trunc = rec["env_term"][:n].tolist(), rec["trunc"][:n].tolist()
+        rewards, infos, terms, truncs, obs = {}, {}, {}, {}, {}
+        for i, a in enumerate(agents):
+            name = a.name
+            r = renv[i]
+            r = int(r) if r == int(r) else r  # _num
+            p, c = prev[i], cell[i]
+            infos[name] = {"prev_s": {"pos_x": p % W, "pos_y": p // W}, "s": {"pos_x": c % W, "pos_y": c // W}, "Renv": r}
+            rewards[name] = 0 + r
+            terms[name] = bool(env_term[i])
+            truncs[name] = bool(trunc[i])
+            obs[name] = a.state
+        self.rewards = rewards
+        return obs, rewards, terms, truncs, infos, rec
 
     def holes_in_the_ice(self, state, agent_name):
         if (state["pos_x"], state["pos_y"]) in self.holes:
@@ -374,18 +400,27 @@ class MultiAgentOfficeWorld(BaseEnvironment):
     def _step(self, actions, with_rm, reward_modifier=1, counterfactuals=False):
         was_active = dict(self.active_agents)
         rec = self._device_step(actions, with_rm, reward_modifier, counterfactuals)
-        self.rewards = {a.name: 0 for a in self.agents}
-        infos, terms, truncs = {}, {}, {}
-        for i, a in enumerate(self.agents):
-            if was_active.get(a.name, True):  # inactive agents are skipped and keep an empty info dict (ma_office.py:143-144)
-                infos[a.name] = {"prev_s": self._pos(rec["prev_cell"][i]), "s": self._pos(rec["cell"][i]),
-                                 "Renv": _num(rec["renv"][i])}
-                self.rewards[a.name] += _num(rec["renv"][i])
+        agents, W = self._agents, self.grid_width
+        n = len(agents)
+        prev, cell, renv = rec["prev_cell"][:n].tolist(), rec["cell"][:n].tolist(), rec["renv"][:n].tolist()
+        env_term, trunc = rec["env_term"][:n].tolist(), rec["trunc"][:n].tolist()
+        rewards, infos, terms, truncs, obs = {}, {}, {}, {}, {}
+        for i, a in enumerate(agents):
+            name = a.name
+            rewards[name] = 0
+            if was_active.get(name, True):  # inactive agents are skipped and keep an empty info dict (ma_office.py:143-144)
+                r = renv[i]
+                r = int(r) if r == int(r) else r  # _num
+                p, c = prev[i], cell[i]
+                infos[name] = {"prev_s": {"pos_x": p % W, "pos_y": p // W}, "s": {"pos_x": c % W, "pos_y": c // W}, "Renv": r}
+                rewards[name] += r
             else:
-                infos[a.name] = {}
-            terms[a.name] = bool(rec["env_term"][i])
-            truncs[a.name] = bool(rec["trunc"][i])
-        return {a.name: a.state for a in self.agents}, self.rewards, terms, truncs, infos, rec
+                infos[name] = {}
+            terms[name] = bool(env_term[i])
+            truncs[name] = bool(trunc[i])
+            obs[name] = a.state
+        self.rewards = rewards
+        return obs, rewards, terms, truncs, infos, rec
 
     def plants_in_the_office(self, state, agent_name):
         if (state["pos_x"], state["pos_y"]) in self.plants:

@@ -22,6 +22,10 @@ from . import _abi as abi
 from ._lib import check, load
 
 
+_EXP_STRUCT = struct.Struct("<IIBB6xd")   # rlrm_experience_t
+_SEL_STRUCT = struct.Struct("<IIdIIIII")  # the input half of rlrm_select_req_t
+
+
 class DeviceTable:
     """(S, A) view of a learner table living in GPU memory, with numpy-style indexing so reference-style code such as
     ``learner.q_table[s] = np.array([...])`` or ``np.isclose(learner.q_table[s, a], x)`` keeps working.
@@ -193,6 +197,7 @@ class _TabularBase(BaseLearningAlgorithm):
         self._ring = 0
         self._st = abi.State(1, self._base, self._base + 8, self._q.data_ptr(), None if self._e is None else self._e.data_ptr(),
                              self._visits.data_ptr(), None, None, None, None, None)
+        self._st_ref = C.byref(self._st)
         self._hp = (self.learning_rate, self.gamma, lambd)
         # look-ahead selection (see _device_update_list): key of the request in flight, its sequence number, and the four
         # words already taken from self.rng for the NEXT choose_action call (consumed by it whether or not the look-ahead hits)
@@ -241,37 +246,44 @@ class _TabularBase(BaseLearningAlgorithm):
         finds its answer in page-locked memory instead of launching and synchronising. Any other outcome (another state,
         another epsilon, a caller-supplied rng, a table write in between) falls back to the ordinary launch with the SAME
         words, so the stream of random words and every decision are identical with and without the look-ahead."""
-        self._sync_hyper()
-        S, L, th = self.state_space_size, self._th.L, self._th
+        hp = (self.learning_rate, self.gamma, getattr(self, "lambd", 0.0))
+        if hp != self._hp:
+            self._sync_hyper()
+        S, th, mv, base = self.state_space_size, self._th, self._stage_mv, self._base
+        L, st_ref = th.L, self._st_ref
+        stream = torch._C._cuda_getCurrentRawStream(th._dev_index)
         self._spec = None
         look = (self._LOOKAHEAD and next_enc is not None and self.action_selection == "greedy" and type(self.rng) is np.random.Generator
-                and 0 <= int(next_enc) < S)
-        last = len(experiences) - self._BLOCK if experiences else 0
-        for lo in range(0, max(len(experiences), 1), self._BLOCK):
-            chunk = experiences[lo:lo + self._BLOCK]
+                and 0 <= next_enc < S)
+        n_exp = len(experiences)
+        last = n_exp - self._BLOCK
+        pack_exp = _EXP_STRUCT.pack_into
+        for lo in range(0, max(n_exp, 1), self._BLOCK):
+            chunk = experiences[lo:lo + self._BLOCK] if n_exp > self._BLOCK else experiences
             off = self._EXP_OFF
             if chunk:
                 blk = self._ring % self._RING
                 if blk == 0 and self._ring:
                     self._sync()  # the ring wrapped: make sure the launches that read these blocks have finished
-                off = self._EXP_OFF + blk * self._BLOCK * 24
-                for j, (s_, a_, r_, sn_, done_) in enumerate(chunk):
+                off = o = self._EXP_OFF + blk * self._BLOCK * 24
+                for s_, a_, r_, sn_, done_ in chunk:
                     s_, sn_ = int(s_), int(sn_)
                     if not (0 <= s_ < S and 0 <= sn_ < S):
                         raise IndexError(f"encoded state {s_ if not 0 <= s_ < S else sn_} out of range for state_space_size {S}")
-                    struct.pack_into("<IIBB6xd", self._stage_mv, off + 24 * j, s_, sn_, int(a_), int(bool(done_)), float(r_))
+                    pack_exp(mv, o, s_, sn_, int(a_), 1 if done_ else 0, float(r_))
+                    o += 24
                 self._ring += 1
             if look and lo >= last:
                 if self._pending_words is None or self._pending_rng is not self.rng:
                     self._pending_words = self._own_words()
                     self._pending_rng = self.rng
-                self._spec_seq = (self._spec_seq + 1) & 0xFFFFFFFF
+                seq = self._spec_seq = (self._spec_seq + 1) & 0xFFFFFFFF
                 eps = float(self.epsilon)
-                struct.pack_into("<IIdIIIII", self._stage_mv, self._SEL_OFF, int(next_enc), 0, eps, *self._pending_words, self._spec_seq)
-                check(L.rlrm_update_list_select(th.h, C.byref(self._st), 0, len(chunk), self._base + off, self._base + self._SEL_OFF, th.stream()))
+                _SEL_STRUCT.pack_into(mv, self._SEL_OFF, int(next_enc), 0, eps, *self._pending_words, seq)
+                check(L.rlrm_update_list_select(th.h, st_ref, 0, len(chunk), base + off, base + self._SEL_OFF, stream))
                 self._spec = (int(next_enc), eps)
             elif chunk:
-                check(L.rlrm_update_list(th.h, C.byref(self._st), 0, len(chunk), self._base + off, th.stream()))
+                check(L.rlrm_update_list(th.h, st_ref, 0, len(chunk), base + off, stream))
 
     def _device_update(self, s, sn, action, reward, terminated):
         self._device_update_list([(s, action, reward, sn, terminated)], next_enc=sn)
@@ -342,7 +354,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_base", "_ring", "_spec", "_spec_seq", "_pending_rng")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_st_ref", "_base", "_ring", "_spec", "_spec_seq", "_pending_rng")}
         d["device"] = str(self.device)
         d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
                         "visits": self._visits.cpu().numpy()}

@@ -45,37 +45,44 @@ class RMEnvironmentWrapper:
                 for a in self.agents}
 
     def step(self, actions):
-        prev_q = {a.name: a.get_reward_machine().get_current_state() for a in self.agents}
-        qrm_agents = [getattr(a.get_learning_algorithm(), "use_qrm", False) for a in self.agents]
+        agents = self.agents
+        rms = [a.get_reward_machine() for a in agents]
+        prev_q = [rm.get_current_state() for rm in rms]
+        qrm_agents = [getattr(a.get_learning_algorithm(), "use_qrm", False) for a in agents]
+        any_qrm = any(qrm_agents)
         # the same launch also evaluates the hypothetical RM transitions on the new position (cf_q / cf_r of rlrm_step)
         observations, rewards, env_term, env_trunc, infos, rec = self.env._step(actions, with_rm=True,
                                                                                 reward_modifier=self.reward_modifier,
-                                                                                counterfactuals=any(qrm_agents))
+                                                                                counterfactuals=any_qrm)
+        n = len(agents)
         terminations = {}
         self._cf_cache = {}
-        if any(qrm_agents):
+        if any_qrm:
             stride = max(1, int(self.env._engine.cfg.n_qrm_states))
-            for i, agent in enumerate(self.agents):
-                n = len(agent.get_reward_machine().get_all_states()) - 1
-                if qrm_agents[i] and n > 0:
-                    self._cf_cache[agent.name] = (rec["cf_q"][i * stride:i * stride + n], rec["cf_r"][i * stride:i * stride + n])
-        for i, agent in enumerate(self.agents):
-            rm = agent.get_reward_machine()
-            info = infos[agent.name]
-            current_state = info.get("prev_s", observations[agent.name])
-            reward_rm = _num(rec["rq"][i])
+            cf_q, cf_r = rec["cf_q"][:n * stride].tolist(), rec["cf_r"][:n * stride].tolist()
+            for i, agent in enumerate(agents):
+                k = rms[i].numbers_state() - 1
+                if qrm_agents[i] and k > 0:
+                    self._cf_cache[agent.name] = (cf_q[i * stride:i * stride + k], cf_r[i * stride:i * stride + k])
+        rq, rm_term, term = rec["rq"][:n].tolist(), rec["rm_term"][:n].tolist(), rec["term"][:n].tolist()
+        for i, agent in enumerate(agents):
+            rm, name = rms[i], agent.name
+            info = infos[name]
+            current_state = info.get("prev_s", observations[name])
+            reward_rm = rq[i]
+            reward_rm = int(reward_rm) if reward_rm == int(reward_rm) else reward_rm  # _num
             info["RQ"] = reward_rm
-            info["prev_q"] = prev_q[agent.name]
-            info["q"] = rm.get_current_state()
+            info["prev_q"] = prev_q[i]
+            q_now = rm.get_current_state()
+            info["q"] = q_now
             info["reward_machine"] = rm
-            if getattr(agent.get_learning_algorithm(), "use_qrm", False):
-                info["qrm_experience"] = self._get_qrm_experiences(agent, current_state, observations[agent.name],
-                                                                   actions[agent.name], rewards[agent.name],
-                                                                   rm.get_current_state(), env_term[agent.name])
-            rewards[agent.name] += reward_rm
-            info["env_terminated"] = env_term[agent.name]
-            info["rm_terminated"] = bool(rec["rm_term"][i])
-            terminations[agent.name] = bool(rec["term"][i])
+            if qrm_agents[i]:
+                info["qrm_experience"] = self._get_qrm_experiences(agent, current_state, observations[name], actions[name],
+                                                                   rewards[name], q_now, env_term[name])
+            rewards[name] += reward_rm
+            info["env_terminated"] = env_term[name]
+            info["rm_terminated"] = bool(rm_term[i])
+            terminations[name] = bool(term[i])
         return observations, rewards, terminations, env_trunc, infos
 
     def get_mdp(self, seed, repaired=False):
@@ -165,14 +172,16 @@ class RMEnvironmentWrapper:
             s_nxt = next_state["pos_y"] * W + next_state["pos_x"]
             limit = W * _H * n_rm
             index = rm.state_indices
+            from_index = rm.get_state_from_index
             for k, s in enumerate(states):
                 qn = int(q_out[k])
-                nxt = rm.get_state_from_index(qn)
+                nxt = from_index(qn)
                 qs = index[s]
                 enc_s, enc_n = s_cur * n_rm + qs, s_nxt * n_rm + qn
                 if enc_s >= limit or enc_n >= limit:
                     raise ValueError("Encoded state index exceeds total state space size.")
-                ru = _num(r[k])
+                ru = float(r[k])
+                ru = int(ru) if ru == int(ru) else ru  # _num
                 out.append((enc_s, a_idx, env_reward + ru, enc_n, env_termination or nxt == final, s_cur, qs, s_nxt, qn, ru))
             return out
         for k, s in enumerate(states):
