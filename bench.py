@@ -660,6 +660,41 @@ def reference_python_throughput(workload, seconds, procs):
         return {"unavailable": repr(exc)[:200]}
 
 
+def dropin_n1(seconds=2.0):
+    """BASELINE configs[0] (frozen_lake_main --map map1: 2 agents, built-in RM, QRM learner) through the reference's OWN driver loop
+    on this repo's reference-shaped N = 1 classes (device-backed: one launch per step, look-ahead selection in the update launch)
+    and, when the reference sources are staged (oracle/_ref), on the live Python reference — same host, same process, own PCG64
+    randomness. One object instance per call: this is the compatibility layer, not the throughput path."""
+    try:
+        here = os.path.dirname(os.path.abspath(__file__))
+        for sub in ("tests", os.path.join("profiles", "scripts")):
+            if os.path.join(here, sub) not in sys.path:
+                sys.path.insert(0, os.path.join(here, sub))
+        import multiagent_rlrm_b200 as P
+        import time_dropin_n1 as T
+        from dropin_builder import build_b200
+
+        d = P.scenario_config1().to_dict()
+        rm_env, env, agents = build_b200(d)
+        T.loop(rm_env, env, agents, True, d["seed"], 0.5)  # warm
+        out = {"workload": "configs[0]: frozen_lake_main map1, 2 agents, built-in RM A->B->C, QLearning use_qrm=True, one instance",
+               "b200_dropin": T.loop(rm_env, env, agents, True, d["seed"], seconds)}
+        try:
+            import numpy as np
+            import ref_harness as H
+
+            if H.reference_available():
+                r_env, r_e, r_agents = H.build_reference(d, np.float64)
+                T.loop(r_env, r_e, r_agents, True, d["seed"], 0.3)
+                out["python_reference"] = T.loop(r_env, r_e, r_agents, True, d["seed"], seconds)
+                out["dropin_over_reference"] = out["b200_dropin"]["active_agent_steps_per_s"] / out["python_reference"]["active_agent_steps_per_s"]
+        except Exception as exc:  # the staged reference is optional
+            out["python_reference"] = {"unavailable": repr(exc)[:200]}
+        return out
+    except Exception as exc:  # never fatal for the bench line
+        return {"error": repr(exc)[:300]}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -691,9 +726,10 @@ def run_gpu_arm(args):
             g["kernel_over_probe"] = steps_per_s / g["read_write_gathers_per_s"]
         except Exception as exc:  # a yardstick, never fatal
             head["roofline"]["random_gather"] = {"error": repr(exc)[:200]}
-    stepwise = unfused = None
+    stepwise = unfused = n1 = None
     if world == 1 and args.workload in ("cfg3", "cfg3_ql") and not args.no_call_by_call:
         stepwise, unfused = call_by_call(r.c, r.sc, args.instances, dev)
+        n1 = dropin_n1()
     del r
     torch.cuda.empty_cache()
 
@@ -743,7 +779,7 @@ def run_gpu_arm(args):
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": scenario(args.workload).table_dtype, "data": "synthetic", "config": cfgd,
             "slot_steps_per_s": head["slot_steps_per_s"], "active_fraction": head["active_fraction"],
-            "clocks": res["clocks"], "e2e": head.get("e2e"), "e2e_call_by_call": stepwise, "e2e_call_by_call_unfused": unfused,
+            "clocks": res["clocks"], "e2e": head.get("e2e"), "e2e_call_by_call": stepwise, "e2e_call_by_call_unfused": unfused, "dropin_n1": n1,
             "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": cpu, "configs": configs,
         }
         if "collective" in head:
