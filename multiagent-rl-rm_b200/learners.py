@@ -203,6 +203,7 @@ class _TabularBase(BaseLearningAlgorithm):
         # words already taken from self.rng for the NEXT choose_action call (consumed by it whether or not the look-ahead hits)
         self._spec = None
         self._spec_seq = 0
+        self._spec_stream = None
         self.__dict__.setdefault("_pending_words", None)
         self._pending_rng = self.rng if self._pending_words is not None else None
 
@@ -281,7 +282,7 @@ class _TabularBase(BaseLearningAlgorithm):
                 eps = float(self.epsilon)
                 _SEL_STRUCT.pack_into(mv, self._SEL_OFF, int(next_enc), 0, eps, *self._pending_words, seq)
                 check(L.rlrm_update_list_select(th.h, st_ref, 0, len(chunk), base + off, base + self._SEL_OFF, stream))
-                self._spec = (int(next_enc), eps)
+                self._spec, self._spec_stream = (int(next_enc), eps), stream
             elif chunk:
                 check(L.rlrm_update_list(th.h, st_ref, 0, len(chunk), base + off, stream))
 
@@ -320,7 +321,7 @@ class _TabularBase(BaseLearningAlgorithm):
         if spec is not None and own and not best and self._pending_rng is self.rng and spec == (int(encoded_state), float(self.epsilon)):
             # the look-ahead selection launched with the last update answers this call (same state, epsilon, words, table)
             if int(self._stage_np[self._SEL_OFF + 40:self._SEL_OFF + 44].view(np.uint32)[0]) != self._spec_seq:
-                self._sync()
+                check(self._th.L.rlrm_stream_sync(self._th.h, self._spec_stream))  # the stream that launch went to
             self._pending_words = None
             self.lookahead_hits += 1
             return int(self._stage_np[self._SEL_OFF + 36])
@@ -354,7 +355,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_st_ref", "_base", "_ring", "_spec", "_spec_seq", "_pending_rng")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_st_ref", "_base", "_ring", "_spec", "_spec_seq", "_spec_stream", "_pending_rng")}
         d["device"] = str(self.device)
         d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
                         "visits": self._visits.cpu().numpy()}
