@@ -279,12 +279,10 @@ template <int ENV, int STOCH = -1, bool WAIT_OK = false, bool PRE = false>  // S
 __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, int action, unsigned w3, bool with_rm, Rec& r,
                                            PreStep ps = PreStep{0ull, 0u}) {
   const bool stochastic = STOCH < 0 ? (p.stochastic != 0) : (STOCH != 0);
-  auto next_of = [&](int ex) -> unsigned {
-    return PRE ? ((unsigned)(ps.nrow >> (ex * 16)) & 0xFFFFu) : (unsigned)tb.next_cell[s.cell * 4 + ex];
-  };
-  auto slip_of = [&](int a) -> int {
-    return PRE ? (int)((unsigned)(p.slip_nib >> ((a * 4 + (int)ps.sidx) * 4)) & 0xFu) : slip_outcome(p, a, w3);
-  };
+  // (plain expressions, not lambdas: a by-reference closure over `p` makes the kernels' private copy of the parameter block
+  // address-taken and sends all 656 bytes of it to local memory — +13 us on every one-iteration launch of rlrm_iterate)
+#define RLRM_NEXT_OF(ex) (PRE ? ((unsigned)(ps.nrow >> ((ex) * 16)) & 0xFFFFu) : (unsigned)tb.next_cell[s.cell * 4 + (ex)])
+#define RLRM_SLIP_OF(a) (PRE ? (int)((unsigned)(p.slip_nib >> (((a) * 4 + (int)ps.sidx) * 4)) & 0xFu) : slip_outcome(p, (a), w3))
   r.prev_cell = s.cell;
   r.executed = 5;
   r.stepped = false;
@@ -295,8 +293,8 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
     const bool rm_done = p.rm_final >= 0 && (int)s.rm == p.rm_final;  // ma_frozen_lake.py:107-115
     if (active && !rm_done) {
       int ex = action;
-      if (stochastic && (!WAIT_OK || action != RLRM_ACTION_WAIT)) ex = slip_of(action);
-      if (ex != RLRM_ACTION_WAIT) s.cell = next_of(ex);
+      if (stochastic && (!WAIT_OK || action != RLRM_ACTION_WAIT)) ex = RLRM_SLIP_OF(action);
+      if (ex != RLRM_ACTION_WAIT) s.cell = RLRM_NEXT_OF(ex);
       if (tb.cell_flags[s.cell] & 1) {  // holes_in_the_ice
         s.flags |= RLRM_FLAG_FAIL;
         r.renv = p.hole_penalty;
@@ -310,13 +308,13 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
       int ex = action;
       double wall_pen = 0.0;
       // is_wall_collision("wait") is False (ma_office.py:299-300)
-      if ((!WAIT_OK || action != RLRM_ACTION_WAIT) && next_of(action) == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
+      if ((!WAIT_OK || action != RLRM_ACTION_WAIT) && RLRM_NEXT_OF(action) == s.cell) {  // apply_wall_penalty: blocked -> "wait", no slip draw
         if (p.terminate_hit_walls) s.flags |= RLRM_FLAG_FAIL;
         wall_pen = p.wall_penalty;
         ex = RLRM_ACTION_WAIT;
       }
-      if (stochastic && ex != RLRM_ACTION_WAIT) ex = slip_of(ex);
-      if (ex != RLRM_ACTION_WAIT) s.cell = next_of(ex);
+      if (stochastic && ex != RLRM_ACTION_WAIT) ex = RLRM_SLIP_OF(ex);
+      if (ex != RLRM_ACTION_WAIT) s.cell = RLRM_NEXT_OF(ex);
       double plant = 0.0;
       if (tb.cell_flags[s.cell] & 1) {  // plants_in_the_office
         if (p.terminate_on_plants) s.flags |= RLRM_FLAG_FAIL;
@@ -359,6 +357,8 @@ __device__ __forceinline__ void agent_step(const KP& p, const Tab& tb, Slot& s, 
   s.flags &= ~(RLRM_FLAG_DONE | RLRM_FLAG_TRUNC | RLRM_FLAG_FIRST);
   if (r.term) s.flags |= RLRM_FLAG_DONE;
   if (r.trunc) s.flags |= RLRM_FLAG_TRUNC;
+#undef RLRM_NEXT_OF
+#undef RLRM_SLIP_OF
 }
 
 template <typename R, typename T>
