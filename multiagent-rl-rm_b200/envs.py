@@ -132,7 +132,7 @@ class BaseEnvironment:
             return
         buf = self.__dict__.get("_slip_buf")
         if buf is None or buf[0] is not rng or buf[2] + n > len(buf[1]):
-            buf = self.__dict__["_slip_buf"] = [rng, rng.integers(0, 1 << 32, size=max(self._WORD_BLOCK, n), dtype=np.uint64).astype(np.uint32), 0]
+            buf = self.__dict__["_slip_buf"] = [rng, rng.integers(0, 1 << 32, size=n * max(1, self._WORD_BLOCK // n), dtype=np.uint64).astype(np.uint32), 0]  # a whole number of steps: no word is dropped
         k = buf[2]
         buf[2] = k + n
         out[3::4] = buf[1][k:k + n]
