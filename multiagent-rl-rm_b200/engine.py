@@ -96,6 +96,7 @@ class Engine:
         self.t = 0  # lockstep iteration counter (Philox counter word)
         self._it_record = self._it_reward = None
         self._hio = None
+        self._ctl_dirty = True
 
     def __del__(self):
         try:
@@ -107,7 +108,9 @@ class Engine:
 
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
-        """torch's current stream on this device as a raw cudaStream_t (one C call; the Stream object is not built)."""
+        """torch's current stream on this device as a raw cudaStream_t (one C call; the Stream object is not built). Every launch
+        of this engine except step_host asks for it, which is how step_host (own stream) learns that it has to wait for them."""
+        self._ctl_dirty = True
         return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def set_learner(self, learning_rate, gamma, lambd=0.0):
@@ -278,6 +281,9 @@ class Engine:
         # the step touches nothing but this engine's page-locked control block, so it runs on a stream of its own: it does not
         # queue behind the learners' update launches on torch's current stream, and the synchronisation waits for it alone
         stream = io["stream"].cuda_stream
+        if self._ctl_dirty:  # another call of this engine (reset, select, update, ...) went to torch's current stream: finish it first
+            check(self.L.rlrm_stream_sync(self.h, torch._C._cuda_getCurrentRawStream(self._dev_index)))
+            self._ctl_dirty = False
         check(self.L.rlrm_step(self.h, self._state_ref, io["p"]["actions"], io["p"]["draws"] if draws is not None else None, 0,
                                int(with_rm), io["so_cf_ref"] if counterfactuals else io["so_ref"], stream))
         check(self.L.rlrm_stream_sync(self.h, stream))
