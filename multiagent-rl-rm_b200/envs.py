@@ -76,13 +76,14 @@ class BaseEnvironment:
         # cheap fingerprint first: the behaviour flags are plain attributes the caller may change between calls (as the
         # reference's drivers do), so they are looked at on every call; the reward machines are identified by object and size
         fields = self._scenario_fields()
-        agents = self.agents
-        starts = tuple(tuple(getattr(a, "initial_position", None) or a.position) for a in agents)
-        quick = (tuple(fields.values()), starts, reward_modifier,
-                 tuple((id(getattr(a, "reward_machine", None)), len(getattr(getattr(a, "reward_machine", None), "transitions", ())))
-                       for a in agents))
+        agents = self._agents
+        quick = [reward_modifier, *fields.values()]
+        for a in agents:
+            rm = getattr(a, "reward_machine", None)
+            quick += (tuple(getattr(a, "initial_position", None) or a.position), rm, len(getattr(rm, "transitions", ())))
         if self._engine is not None and quick == self._engine_quick:
             return self._engine
+        starts = tuple(tuple(getattr(a, "initial_position", None) or a.position) for a in agents)
         rm = self._shared_rm()
         grid = self._grid()
         rm_list = rm if isinstance(rm, list) else ([] if rm is None else [rm])

@@ -192,6 +192,7 @@ class _TabularBase(BaseLearningAlgorithm):
         # selection) one stream synchronisation. No staging copies, no torch ops on the call path.
         self._stage = torch.zeros(self._STAGE_BYTES, dtype=torch.uint8).pin_memory()
         self._stage_np = self._stage.numpy()
+        self._stage_u32 = self._stage_np.view(np.uint32)
         self._stage_mv = memoryview(self._stage_np)
         self._base = self._stage.data_ptr()
         self._ring = 0
@@ -315,16 +316,17 @@ class _TabularBase(BaseLearningAlgorithm):
             if self.action_selection == "softmax":
                 raise NotImplementedError("softmax selection is out of scope (no reference driver uses it; DESIGN.md §8)")
             raise ValueError("Unsupported action selection method")
-        cell, q = self._split(encoded_state)
         own = rng is None or rng is self.rng
         spec, self._spec = self._spec, None
-        if spec is not None and own and not best and self._pending_rng is self.rng and spec == (int(encoded_state), float(self.epsilon)):
-            # the look-ahead selection launched with the last update answers this call (same state, epsilon, words, table)
-            if int(self._stage_np[self._SEL_OFF + 40:self._SEL_OFF + 44].view(np.uint32)[0]) != self._spec_seq:
+        if spec is not None and own and not best and self._pending_rng is self.rng and spec == (encoded_state, self.epsilon):
+            # the look-ahead selection launched with the last update answers this call (same state — hence in range —, epsilon,
+            # words, table)
+            if self._stage_u32[(self._SEL_OFF + 40) >> 2] != self._spec_seq:
                 check(self._th.L.rlrm_stream_sync(self._th.h, self._spec_stream))  # the stream that launch went to
             self._pending_words = None
             self.lookahead_hits += 1
             return int(self._stage_np[self._SEL_OFF + 36])
+        cell, q = self._split(encoded_state)
         self.lookahead_misses += 1
         if best:
             words = [0, 0, 0, 0]
@@ -355,7 +357,7 @@ class _TabularBase(BaseLearningAlgorithm):
 
     # -- pickling: office_main.py:1611-1613, 1922-1925 save / load the whole learner object with pickle ---------------
     def __getstate__(self):
-        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_mv", "_st", "_st_ref", "_base", "_ring", "_spec", "_spec_seq", "_spec_stream", "_pending_rng")}
+        d = {k: v for k, v in self.__dict__.items() if k not in ("_th", "_q", "_e", "_visits", "_stage", "_stage_np", "_stage_u32", "_stage_mv", "_st", "_st_ref", "_base", "_ring", "_spec", "_spec_seq", "_spec_stream", "_pending_rng")}
         d["device"] = str(self.device)
         d["_tables"] = {"q": self._q.cpu().numpy(), "e": None if self._e is None else self._e.cpu().numpy(),
                         "visits": self._visits.cpu().numpy()}
