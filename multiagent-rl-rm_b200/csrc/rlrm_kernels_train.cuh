@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, 7) train_qrmn_kernel(KP p, DState
 // NU = compile-time bound on the number of counterfactual states (the values they overwrite are read into registers before
 // the block is replaced). Supports shaping and random starts; per-agent machines / lr=None / shared tables stay generic.
 // Also THE specialised QRM kernel of the float64 table mode (T = double, any 2..16 states incl. BASELINE config 3's four): a row is
-// then two 16-byte chunks (8 cp.async per move for nQ = 4); config 3 on float64 tables: 1.45e10 (generic kernel) -> 2.16e10.
+// then two 16-byte chunks (8 cp.async per move for nQ = 4); config 3 on float64 tables: 1.45e10 (generic kernel) -> 2.27e10.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -518,12 +518,21 @@ __device__ __forceinline__ void fetch_cell_block(uint4* blk, const void* src_, i
 // one table row of the shared-memory cell block: a float4 is one 16-byte chunk, a double4r two (chunk c of this thread lives at
 // blk[c * TRAIN_BLOCK], so a warp's access to one chunk index is 32 consecutive 16-byte words: conflict-free)
 template <typename T>
+__device__ __forceinline__ T sel4t(T a, T b, T c, T d, unsigned k) {
+  const T lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
+  return (k & 2u) ? hi : lo;
+}
+template <typename T>
 struct BlkRow;
 template <>
 struct BlkRow<float> {
   static constexpr int CH = 1;
   static __device__ __forceinline__ float4 load(const uint4* blk, unsigned r) { return *reinterpret_cast<const float4*>(blk + r * TRAIN_BLOCK); }
   static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, float v) { reinterpret_cast<float*>(blk + r * TRAIN_BLOCK)[a] = v; }
+  static __device__ __forceinline__ float get(const uint4* blk, unsigned r, int a) {  // one element: the whole row is one 16-byte access anyway
+    const float4 v = load(blk, r);
+    return sel4t<float>(v.x, v.y, v.z, v.w, (unsigned)a);
+  }
 };
 template <>
 struct BlkRow<double> {
@@ -535,12 +544,10 @@ struct BlkRow<double> {
   static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, double v) {
     reinterpret_cast<double*>(blk + (2 * r + ((unsigned)a >> 1)) * TRAIN_BLOCK)[a & 1] = v;
   }
+  static __device__ __forceinline__ double get(const uint4* blk, unsigned r, int a) {  // one 8-byte access instead of the row's two 16-byte ones
+    return reinterpret_cast<const double*>(blk + (2 * r + ((unsigned)a >> 1)) * TRAIN_BLOCK)[a & 1];
+  }
 };
-template <typename T>
-__device__ __forceinline__ T sel4t(T a, T b, T c, T d, unsigned k) {
-  const T lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
-  return (k & 2u) ? hi : lo;
-}
 
 // T = table type: float, or double for the reference's native float64 tables (a row is then two 16-byte chunks; BASELINE config 3's
 // four-state machine in float64 takes this kernel too: 128 bytes of block per thread)
@@ -592,10 +599,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
       if (learn) {
         T cur[NU];  // values the updates overwrite, read before the block is replaced
 #pragma unroll
-        for (int j = 0; j < NU; j++) {
-          const row_t v = BR::load(blk, j < p.n_qrm ? tb.qrm_states[j] : 0);
-          cur[j] = sel4t<T>(v.x, v.y, v.z, v.w, (unsigned)action);
-        }
+        for (int j = 0; j < NU; j++) cur[j] = BR::get(blk, j < p.n_qrm ? tb.qrm_states[j] : 0, action);
         if (moved) fetch_cell_block(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ * BR::CH);  // the shared block becomes the NEXT cell's block
         // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106) in
         // get_all_states()[:-1] order. The next state's row maximum comes from the shared block: the new cell's block when
