@@ -13,5 +13,5 @@ cap() {
   rm -f gpurun_out/${name}.ncu-rep
   echo "$name done"
 }
-cap r02c_generic_ql_cfg3_f64 "^train_kernel$"  1 $B --workload cfg3_ql_f64
-cap r02c_iterate_cfg3      "^train_kernel$"       100 python profiles/scripts/run_iterate.py
+cap r02c_qrm_block_cfg3_f64 train_qrm_block 1 $B --workload cfg3_f64
+
