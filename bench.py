@@ -8,7 +8,13 @@ Multi-GPU (`torchrun`, one rank per GPU) shards independent instances: no data-p
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--iters T] [--instances N] [--impl reference]
 
-Prints ONE JSON line (see the keys in main()).
+Prints ONE JSON line (see the keys in main()). Besides the headline it carries: `configs` (every other BASELINE configuration,
+measured in the same run: config 3 on float64 tables, config 2 batched, config 4 sparse-exact / dense-faithful, config 5 with
+per-instance tables and with the shared learner — 1,048,576 instances in TOTAL sharded over the ranks, K sweep and merge time at
+N > 1), `e2e` (host buffers through rlrm_train_host), `e2e_call_by_call` (one launch per driver-loop iteration, rlrm_iterate),
+`dropin_n1` (BASELINE configs[0] through the reference's driver loop on the N = 1 drop-in classes next to the live Python
+reference), `roofline` (frac = algorithmic bytes, dram_frac = ncu DRAM bytes, bound per workload) and `cpu_baseline` (the C port
+and the live Python reference on the box's host cores). `--workload` runs any single workload of WORKLOADS as the headline.
 """
 from __future__ import annotations
 
