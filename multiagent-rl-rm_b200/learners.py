@@ -268,8 +268,8 @@ class _TabularBase(BaseLearningAlgorithm):
                 if blk == 0 and self._ring:
                     self._sync()  # the ring wrapped: make sure the launches that read these blocks have finished
                 off = o = self._EXP_OFF + blk * self._BLOCK * 24
-                for s_, a_, r_, sn_, done_ in chunk:
-                    s_, sn_ = int(s_), int(sn_)
+                for e in chunk:  # (s, a, r, s', terminated, ...): the wrapper's ten-field QRM tuples are taken as they are
+                    s_, a_, r_, sn_, done_ = int(e[0]), e[1], e[2], int(e[3]), e[4]
                     if not (0 <= s_ < S and 0 <= sn_ < S):
                         raise IndexError(f"encoded state {s_ if not 0 <= s_ < S else sn_} out of range for state_space_size {S}")
                     pack_exp(mv, o, s_, sn_, int(a_), 1 if done_ else 0, float(r_))
@@ -410,13 +410,17 @@ class QLearning(_TabularBase):
             if pq is not None and nq is not None:
                 reward += self.gamma * rm.potentials.get(nq, 0) - rm.potentials.get(pq, 0)
         if self.use_qrm:  # only the counterfactual list is applied (qlearning.py:82-106): one launch for the whole list
-            todo = []
-            for exp in info.get("qrm_experience", []):
-                _s, _a, _r, _sn, _done, _, cur_q, _, nxt_q, _ = exp
-                if shaping:
+            todo = info.get("qrm_experience", [])
+            if not isinstance(todo, (list, tuple)):
+                todo = list(todo)
+            if shaping:
+                shaped = []
+                for exp in todo:
+                    _s, _a, _r, _sn, _done, _, cur_q, _, nxt_q, _ = exp
                     _r += self.gamma * rm.potentials.get(rm.get_state_from_index(nxt_q), 0) - rm.potentials.get(
                         rm.get_state_from_index(cur_q), 0)
-                todo.append((_s, _a, _r, _sn, _done))
+                    shaped.append((_s, _a, _r, _sn, _done))
+                todo = shaped
             self._device_update_list(todo, next_enc=encoded_next_state)
         else:
             self._device_update(encoded_state, encoded_next_state, action, reward, terminated)
