@@ -322,7 +322,11 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
                 !(h->cfg.reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+#if QRMB_TMA
+  h->qrmb_smem = align16(off) + TRAIN_BLOCK * 8 + TRAIN_BLOCK * qrmb_slot_bytes(kp.nQ * (h->f64 ? 32 : 16));
+#else
   h->qrmb_smem = align16(off) + kp.nQ * (h->f64 ? 32 : 16) * TRAIN_BLOCK;
+#endif
   // float64 tables: the block kernel is the one specialised QRM kernel (the register-carried ones are float32-only)
   h->qrmb_fast = (kp.algo == RLRM_ALGO_QRM && !h->qrm4_fast && !h->qrmn_fast && kp.nQ >= 2 && kp.nQ <= 16 && kp.n_qrm >= 1 && kp.n_qrm <= 15 &&
                   !kp.shared_q && !kp.per_agent && cfg->learning_rate >= 0.0 && h->qrmb_smem <= h->max_smem && !(h->cfg.reserved & 1));
