@@ -41,6 +41,7 @@ struct rlrm_handle {
   int qrm4_fast;  // train_qrm4_kernel is applicable (see its header comment)
   int ql_fast;    // train_ql_fast_kernel is applicable (see its header comment)
   int qrmn_fast;  // train_qrmn_kernel<NQ = 3 or 5> is applicable (see its header comment)
+  int qrmb_tma;   // train_qrm_block_kernel fetches the cell block with per-thread bulk copies (blocks of 192 bytes and more)
   int qrmb_fast;  // train_qrm_block_kernel is applicable (QRM, any state order, 6..16 RM states; see its header comment)
   int qrmb_smem;  // its dynamic shared memory: table blob + 16*nQ bytes per thread
   int shared_fast;       // shared_propose_kernel is applicable (tables + accumulators fit in shared memory)
@@ -322,23 +323,26 @@ extern "C" int rlrm_create(const rlrm_config_t* cfg, const rlrm_tables_t* tb, in
                 !(h->cfg.reserved & 1));
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-#if QRMB_TMA
-  h->qrmb_smem = align16(off) + TRAIN_BLOCK * 8 + TRAIN_BLOCK * qrmb_slot_bytes(kp.nQ * (h->f64 ? 32 : 16));
-#else
-  h->qrmb_smem = align16(off) + kp.nQ * (h->f64 ? 32 : 16) * TRAIN_BLOCK;
-#endif
+  {  // cell-block fetch through per-thread bulk copies (TMA) from 192-byte blocks on: measured, see train_qrm_block_kernel
+    const int block_bytes = kp.nQ * (h->f64 ? 32 : 16);
+    h->qrmb_tma = block_bytes >= 192;
+    const char* e = getenv("RLRM_QRMB_TMA");  // measurement switch
+    if (e) h->qrmb_tma = atoi(e) != 0;
+    h->qrmb_smem = h->qrmb_tma ? align16(off) + TRAIN_BLOCK * 8 + TRAIN_BLOCK * qrmb_slot_bytes(block_bytes) : align16(off) + block_bytes * TRAIN_BLOCK;
+  }
   // float64 tables: the block kernel is the one specialised QRM kernel (the register-carried ones are float32-only)
   h->qrmb_fast = (kp.algo == RLRM_ALGO_QRM && !h->qrm4_fast && !h->qrmn_fast && kp.nQ >= 2 && kp.nQ <= 16 && kp.n_qrm >= 1 && kp.n_qrm <= 15 &&
                   !kp.shared_q && !kp.per_agent && cfg->learning_rate >= 0.0 && h->qrmb_smem <= h->max_smem && !(h->cfg.reserved & 1));
   if (h->qrmb_fast) {  // opt in to the device maximum (per function, only ever raised)
     cudaError_t e2 = cudaSuccess;
 #define RLRM_OPTIN(K) if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem)
-#define RLRM_OPTIN_T(T)                                                                                                                          \
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 3, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 3, T>));          \
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 7, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 11, T>));         \
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 15, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 7, T>));        \
-    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 11, T>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 15, T>))
-    if (h->f64) { RLRM_OPTIN_T(double); } else { RLRM_OPTIN_T(float); }
+#define RLRM_OPTIN_T(T, M)                                                                                                                             \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 3, T, M>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 3, T, M>));          \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 7, T, M>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 11, T, M>));         \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_FROZEN_LAKE, 15, T, M>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 7, T, M>));        \
+    RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 11, T, M>)); RLRM_OPTIN((train_qrm_block_kernel<RLRM_ENV_OFFICE_WORLD, 15, T, M>))
+    if (h->f64) { if (h->qrmb_tma) { RLRM_OPTIN_T(double, true); } else { RLRM_OPTIN_T(double, false); } }
+    else { if (h->qrmb_tma) { RLRM_OPTIN_T(float, true); } else { RLRM_OPTIN_T(float, false); } }
 #undef RLRM_OPTIN_T
 #undef RLRM_OPTIN
     if (e2 != cudaSuccess) h->qrmb_fast = 0;
@@ -702,10 +706,15 @@ static void launch_train(rlrm_handle_t* h, const rlrm_state_t* st, uint64_t t0, 
     }
     else if (fast_ok && kp.algo == RLRM_ALGO_QRM && h->qrmb_fast && !st->visits) {
       const DState d = dstate(st);
-      if (kp.n_qrm <= 3) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 3, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
-      else if (kp.n_qrm <= 7) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 7, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
-      else if (kp.n_qrm <= 11) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 11, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
-      else RLRM_BY_T(h, train_qrm_block_kernel<ENV, 15, T><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));
+#define RLRM_QRMB(M)                                                                                                                       \
+  do {                                                                                                                                   \
+    if (kp.n_qrm <= 3) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 3, T, M><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));        \
+    else if (kp.n_qrm <= 7) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 7, T, M><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));   \
+    else if (kp.n_qrm <= 11) RLRM_BY_T(h, train_qrm_block_kernel<ENV, 11, T, M><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace)); \
+    else RLRM_BY_T(h, train_qrm_block_kernel<ENV, 15, T, M><<<grid, TRAIN_BLOCK, h->qrmb_smem, s>>>(kp, d, t0, n_iters, learn, trace));                     \
+  } while (0)
+      if (h->qrmb_tma) RLRM_QRMB(true); else RLRM_QRMB(false);
+#undef RLRM_QRMB
     }
     else if (fast_ok && kp.algo == RLRM_ALGO_QL && h->ql_fast && !st->visits) {
       const DState d = dstate(st);

@@ -497,15 +497,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 #define QRMB_MINB_F64 7
 #endif
 #define QRMB_MINB(T) (sizeof(T) == 4 ? 7 : QRMB_MINB_F64)  // resident blocks per SM the register allocation is sized for
-// QRMB_TMA = 1 (experiment): the cell block is fetched by ONE bulk copy per thread (cp.async.bulk, the TMA engine:
-// no LSU wavefronts for the fetch) into a per-thread contiguous slot, completion through a per-thread mbarrier. The slot stride
-// is the block size rounded up to 16 (mod 32) bytes, so that eight consecutive lanes' 16-byte accesses to one chunk index
-// cover all 32 banks. Default 0: one cp.async per 16-byte chunk into the [chunk][thread] layout.
-#ifndef QRMB_TMA
-#define QRMB_TMA 0
-#endif
-#if QRMB_TMA
-#define QRMB_CS 1  // distance (in 16-byte units) between consecutive chunks of one thread
+// TMA = true: the cell block is fetched by ONE bulk copy per thread (cp.async.bulk, the TMA engine: no LSU / shared-memory wavefronts
+// for the fetch) into a per-thread contiguous slot, completion through a per-thread mbarrier with expect_tx. The slot stride is the
+// block size rounded up to 16 (mod 32) bytes, so that eight consecutive lanes' 16-byte accesses to one chunk index cover all 32
+// banks. A bulk copy issues from the uniform datapath (per-lane copies become an ELECT / R2UR / UBLKCP loop, ~9 instructions per
+// lane) and goes past the L1, so it only pays for LARGE blocks: measured +13.5 % at 192 bytes (12 states, float32), -8 % at 160,
+// -50 % at 128 (profiles/r02c/r02c_tma_fetch_ab.txt, r02c_tma_dense.txt); the host picks it from 192 bytes on (RLRM_QRMB_TMA=0/1
+// overrides). TMA = false: one cp.async per 16-byte chunk into the [chunk][thread] layout.
 __host__ __device__ __forceinline__ int qrmb_slot_bytes(int block_bytes) { return ((block_bytes + 31) & ~31) | 16; }
 __device__ __forceinline__ void fetch_cell_block_tma(uint4* blk, const void* src, int bytes, unsigned bar, unsigned& phase) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(blk);
@@ -518,11 +516,6 @@ __device__ __forceinline__ void fetch_cell_block_tma(uint4* blk, const void* src
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
   phase ^= 1u;
 }
-#define QRMB_FETCH_BLOCK(blk, src, n_chunks) fetch_cell_block_tma(blk, src, (n_chunks) * 16, bar, phase)
-#else
-#define QRMB_CS TRAIN_BLOCK
-#define QRMB_FETCH_BLOCK(blk, src, n_chunks) fetch_cell_block(blk, src, n_chunks)
-#endif
 __device__ __forceinline__ void fetch_cell_block(uint4* blk, const void* src_, int n_chunks) {  // n_chunks 16-byte pieces: nQ rows of float4, 2 * nQ of double4r
   const uint4* src = reinterpret_cast<const uint4*>(src_);
 #if QRMB_FETCH == 0
@@ -548,53 +541,61 @@ __device__ __forceinline__ T sel4t(T a, T b, T c, T d, unsigned k) {
   const T lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
   return (k & 2u) ? hi : lo;
 }
-template <typename T>
+template <typename T, int CS>  // CS: distance (in 16-byte units) between consecutive chunks of one thread
 struct BlkRow;
-template <>
-struct BlkRow<float> {
+template <int CS>
+struct BlkRow<float, CS> {
   static constexpr int CH = 1;
-  static __device__ __forceinline__ float4 load(const uint4* blk, unsigned r) { return *reinterpret_cast<const float4*>(blk + r * QRMB_CS); }
-  static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, float v) { reinterpret_cast<float*>(blk + r * QRMB_CS)[a] = v; }
+  static __device__ __forceinline__ float4 load(const uint4* blk, unsigned r) { return *reinterpret_cast<const float4*>(blk + r * CS); }
+  static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, float v) { reinterpret_cast<float*>(blk + r * CS)[a] = v; }
   static __device__ __forceinline__ float get(const uint4* blk, unsigned r, int a) {  // one element: the whole row is one 16-byte access anyway
     const float4 v = load(blk, r);
     return sel4t<float>(v.x, v.y, v.z, v.w, (unsigned)a);
   }
 };
-template <>
-struct BlkRow<double> {
+template <int CS>
+struct BlkRow<double, CS> {
   static constexpr int CH = 2;
   static __device__ __forceinline__ double4r load(const uint4* blk, unsigned r) {
-    const double2 lo = *reinterpret_cast<const double2*>(blk + (2 * r) * QRMB_CS), hi = *reinterpret_cast<const double2*>(blk + (2 * r + 1) * QRMB_CS);
+    const double2 lo = *reinterpret_cast<const double2*>(blk + (2 * r) * CS), hi = *reinterpret_cast<const double2*>(blk + (2 * r + 1) * CS);
     return double4r{lo.x, lo.y, hi.x, hi.y};
   }
   static __device__ __forceinline__ void set(uint4* blk, unsigned r, int a, double v) {
-    reinterpret_cast<double*>(blk + (2 * r + ((unsigned)a >> 1)) * QRMB_CS)[a & 1] = v;
+    reinterpret_cast<double*>(blk + (2 * r + ((unsigned)a >> 1)) * CS)[a & 1] = v;
   }
   static __device__ __forceinline__ double get(const uint4* blk, unsigned r, int a) {  // one 8-byte access instead of the row's two 16-byte ones
-    return reinterpret_cast<const double*>(blk + (2 * r + ((unsigned)a >> 1)) * QRMB_CS)[a & 1];
+    return reinterpret_cast<const double*>(blk + (2 * r + ((unsigned)a >> 1)) * CS)[a & 1];
   }
 };
 
 // T = table type: float, or double for the reference's native float64 tables (a row is then two 16-byte chunks; BASELINE config 3's
 // four-state machine in float64 takes this kernel too: 128 bytes of block per thread)
-template <int ENV, int NU, typename T>
+template <int ENV, int NU, typename T, bool TMA>
 __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_kernel(KP p, DState st, unsigned long long t0, int n_iters, int learn,
                                                                                 unsigned* trace) {
   typedef RT<T> R;
-  typedef BlkRow<T> BR;
+  typedef BlkRow<T, TMA ? 1 : TRAIN_BLOCK> BR;
   typedef typename R::row_t row_t;
   Tab tb = stage_tables(p);
-#if QRMB_TMA
-  unsigned char* area = smem_raw + ((p.blob_bytes + 15) & ~15);  // [TRAIN_BLOCK] mbarriers, then [TRAIN_BLOCK] slots
-  const unsigned bar = (unsigned)__cvta_generic_to_shared(area + threadIdx.x * 8);
-  uint4* blk = reinterpret_cast<uint4*>(area + TRAIN_BLOCK * 8 + (size_t)threadIdx.x * qrmb_slot_bytes(p.nQ * 4 * (int)sizeof(T)));
-  unsigned phase = 0;
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-#else
-  uint4* blk = reinterpret_cast<uint4*>(smem_raw + ((p.blob_bytes + 15) & ~15)) + threadIdx.x;  // 16-byte chunk c of this thread: blk[c * TRAIN_BLOCK]
-#endif
+  unsigned char* area = smem_raw + ((p.blob_bytes + 15) & ~15);
+  unsigned bar = 0, phase = 0;
+  uint4* blk;
+  if constexpr (TMA) {  // [TRAIN_BLOCK] mbarriers, then [TRAIN_BLOCK] per-thread slots
+    bar = (unsigned)__cvta_generic_to_shared(area + threadIdx.x * 8);
+    blk = reinterpret_cast<uint4*>(area + TRAIN_BLOCK * 8 + (size_t)threadIdx.x * qrmb_slot_bytes(p.nQ * 4 * (int)sizeof(T)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  } else {
+    blk = reinterpret_cast<uint4*>(area) + threadIdx.x;  // 16-byte chunk c of this thread: blk[c * TRAIN_BLOCK]
+  }
+  const int blk_bytes = p.nQ * 4 * (int)sizeof(T);
+  // (a macro, not a by-reference lambda: see the note in agent_step)
+#define QRMB_FETCH_BLOCK(src)                                                         \
+  do {                                                                               \
+    if constexpr (TMA) fetch_cell_block_tma(blk, (src), blk_bytes, bar, phase);      \
+    else fetch_cell_block(blk, (src), blk_bytes / 16);                               \
+  } while (0)
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = tid >> p.g_shift;
   const int a = (int)(tid & (p.G - 1));
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
     if (st.ep_return) ep_ret = st.ep_return[k];
     if (st.stats) return_sum = st.stats[k].return_sum;
     Q = tab<T>(st.q) + table_base(p, i, a);
-    QRMB_FETCH_BLOCK(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ * BR::CH);
+    QRMB_FETCH_BLOCK(Q + (size_t)s.cell * (size_t)(nQ * 4));
   }
   unsigned long long explore_thr = explore_threshold(eps);
   bool had_episode = false;
@@ -636,7 +637,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
         T cur[NU];  // values the updates overwrite, read before the block is replaced
 #pragma unroll
         for (int j = 0; j < NU; j++) cur[j] = BR::get(blk, j < p.n_qrm ? tb.qrm_states[j] : 0, action);
-        if (moved) QRMB_FETCH_BLOCK(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ * BR::CH);  // the shared block becomes the NEXT cell's block
+        if (moved) QRMB_FETCH_BLOCK(Q + (size_t)r.cell * (size_t)(nQ * 4));  // the shared block becomes the NEXT cell's block
         // QRM counterfactual experiences (rm_environment_wrapper.py:122-183) applied by update_q (qlearning.py:70-106) in
         // get_all_states()[:-1] order. The next state's row maximum comes from the shared block: the new cell's block when
         // the agent moved, else the live one including this step's earlier updates.
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
           }
         }
       } else if (moved) {
-        QRMB_FETCH_BLOCK(blk, Q + (size_t)r.cell * (size_t)(nQ * 4), nQ * BR::CH);
+        QRMB_FETCH_BLOCK(Q + (size_t)r.cell * (size_t)(nQ * 4));
       }
       term = r.term;
       trunc = r.trunc;
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
       const unsigned old_cell = s.cell;
       reset_slot(p, tb, i, a, t + 1, s, eps);
       explore_thr = explore_threshold(eps);
-      if (s.cell != old_cell) QRMB_FETCH_BLOCK(blk, Q + (size_t)s.cell * (size_t)(nQ * 4), nQ * BR::CH);
+      if (s.cell != old_cell) QRMB_FETCH_BLOCK(Q + (size_t)s.cell * (size_t)(nQ * 4));
     }
   }
   if (valid) {
@@ -706,6 +707,8 @@ __global__ void __launch_bounds__(TRAIN_BLOCK, QRMB_MINB(T)) train_qrm_block_ker
     }
   }
 }
+
+#undef QRMB_FETCH_BLOCK
 
 // ------------------------------------------------------------------------------------------------
 // fast path: plain Q-learning with a private table per (instance, agent), fixed learning rate, no visit counts, no shaping

@@ -217,6 +217,41 @@ def test_float64_block_kernel_equals_generic_and_oracle(name, cuda_device):
     assert int(o.stats["episodes"].sum()) > 0
 
 
+@pytest.mark.parametrize("tma", ["0", "1"])
+@pytest.mark.parametrize("name,dtype", [("cfg3_qrm", "f64"), ("office_exp3_qrm", "f64"), ("office_exp6_qrm", "f32"), ("office_chain12_qrm", "f32"),
+                                        ("office_chain12_qrm", "f64"), ("fl_shaping_qrm", "f32"), ("fl_random_starts_qrm", "f64")])
+def test_block_kernel_fetch_variants_equal_oracle(name, dtype, tma, cuda_device, monkeypatch):
+    """train_qrm_block_kernel fetches the cell block either with one cp.async per 16-byte chunk or with ONE bulk copy per thread
+    (cp.async.bulk + mbarrier; the library picks it from 192-byte blocks on). RLRM_QRMB_TMA forces either variant for every
+    block size and table type: traces, tables, slot words and statistics must equal the oracle in both."""
+    import copy
+
+    import multiagent_rlrm_b200 as P
+    import oracle as O
+
+    monkeypatch.setenv("RLRM_QRMB_TMA", tma)
+    if name == "fl_shaping_qrm":
+        sc, n, t = _shaped_qrm(), 300, 900
+    elif name.startswith("office_exp"):
+        sc, n, t = _office_task(name.split("_")[1], "qrm"), 300, 900
+    else:
+        sc, n, t = _scenarios_medium()[name]
+    sc = copy.deepcopy(sc)
+    sc.table_dtype = dtype
+    c = P.compile_scenario(sc)
+    a = _engine(c, n)
+    a.reset()
+    ta = a.train(t, trace=True)
+    a.train(77)
+    o = O.Oracle(c, n, dtype)
+    o.reset()
+    to = o.train(0, t, trace=True)
+    o.train(t, 77)
+    assert np.array_equal(ta.cpu().numpy().view(np.uint32), to)
+    assert np.array_equal(a.q.cpu().numpy().reshape(-1), o.q.reshape(-1)) and np.array_equal(a.slot.cpu().numpy().view(np.uint64), o.slot)
+    assert np.array_equal(a.stats_numpy()["episodes"], o.stats["episodes"]) and int(o.stats["episodes"].sum()) > 0
+
+
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
 @pytest.mark.parametrize("name", ["cfg3_qrm", "cfg3_ql", "cfg2_office_slip", "cfg4_qlambda", "fl_per_agent_rms_qrm",
                                   "fl_per_agent_rms_ql", "fl_random_starts_qrm", "fl_per_agent_rms_qlambda", "fl_per_agent_rms_shaping_qrm"])
