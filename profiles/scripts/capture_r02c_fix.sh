@@ -13,5 +13,5 @@ cap() {
   rm -f gpurun_out/${name}.ncu-rep
   echo "$name done"
 }
-cap r02c_qrm_block_cfg3_f64 train_qrm_block 1 $B --workload cfg3_f64
+cap r02c_qrm_block_chain12 train_qrm_block 1 $B --workload cfg4_qrm
 
