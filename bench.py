@@ -344,7 +344,7 @@ BOUND = {
     "cfg2_batch_qrm": "latency on the row loads after a move, then L1 wavefronts",
     "cfg4": "issue (trace lists stay L1/L2-resident)",
     "cfg4_dense": "hbm",
-    "cfg4_qrm": "smem-wavefront (cell block in shared memory: short scoreboard 60 % of the stalls, L1 wavefront pipe 68 %), then the block fetch after a move",
+    "cfg4_qrm": "smem-latency (cell block in shared memory, fetched by one TMA bulk copy per thread + mbarrier: short scoreboard 47 % of the stalls, L1 wavefront pipe 52 %)",
     "ow_exp6_qrm": "smem-wavefront (cell block in shared memory: short scoreboard 50 % of the stalls, L1 wavefront pipe 73 %), then the block fetch after a move",
     "cfg5_tables": "issue/latency",
     "cfg5_shared": "smem-wavefront (random 16-byte shared-memory gathers + proposal atomics); tables live on chip, not HBM",
