@@ -463,3 +463,52 @@ def test_potentials_equal_live_reference():
         with contextlib.redirect_stdout(io.StringIO()):
             v_ref = ref_rm.value_iteration(list(ref_rm.state_indices), ref_rm.get_delta_u(), dr_ref, ref_rm.get_final_state(), 0.8)
         assert mine.value_iteration(list(mine.state_indices), mine.get_delta_u(), dr_mine, mine.get_final_state(), 0.8) == v_ref
+
+
+# ---------------------------------------------------------------------------------------------- N = 1 host plumbing (no device)
+def test_learner_word_blocks_follow_the_generator_stream():
+    """_own_words hands out self.rng's 32-bit words four at a time from 64-word blocks: the sequence equals four-word requests on
+    an identical generator, across block boundaries, and a block drawn from a generator that was replaced is dropped."""
+    from multiagent_rlrm_b200.learners import _TabularBase
+
+    obj = object.__new__(_TabularBase)  # no device: only the word plumbing is exercised
+    obj.rng = np.random.default_rng(42)
+    ref = np.random.default_rng(42)
+    for _ in range(40):  # 160 words = 2.5 blocks
+        assert obj._own_words() == ref.integers(0, 1 << 32, size=4, dtype=np.uint64).tolist()
+    obj.rng = np.random.default_rng(7)  # reseeded: the rest of the old block must not be used
+    ref = np.random.default_rng(7)
+    assert obj._own_words() == ref.integers(0, 1 << 32, size=4, dtype=np.uint64).tolist()
+
+
+def test_env_slip_words_are_buffered_without_changing_the_stream():
+    """BaseEnvironment._slip_words reads env.rng in blocks holding a whole number of steps: word 3 of every agent's draw block
+    equals per-step requests of n words on an identical generator; reset() installs a new generator and a new block."""
+    env = P.MultiAgentFrozenLake(width=4, height=4, holes=[])
+    for k in range(3):
+        env.add_agent(P.AgentRL(f"a{k}", env))
+    env.rng = np.random.default_rng(5)
+    ref = np.random.default_rng(5)
+    out = np.zeros(12, dtype=np.uint32)
+    for _ in range(50):  # 150 words: several blocks of 63
+        env._slip_words(out)
+        assert out[3::4].tolist() == ref.integers(0, 1 << 32, size=3, dtype=np.uint64).astype(np.uint32).tolist()
+    env.rng = np.random.default_rng(6)
+    ref = np.random.default_rng(6)
+    env._slip_words(out)
+    assert out[3::4].tolist() == ref.integers(0, 1 << 32, size=3, dtype=np.uint64).astype(np.uint32).tolist()
+
+
+def test_agent_action_index_cache_follows_the_action_list():
+    from multiagent_rlrm_b200.actions import ActionRL
+
+    ag = P.AgentRL("a", None)
+    up, down, left = ActionRL("up"), ActionRL("down"), ActionRL("left")
+    ag.add_action(up)
+    ag.add_action(down)
+    assert (ag.actions_idx(up), ag.actions_idx(down), ag.actions_idx(left)) == (0, 1, None)
+    ag.add_action(left)                      # the list grew
+    assert ag.actions_idx(left) == 2
+    ag.actions_[0], ag.actions_[1] = down, up  # same length, other order
+    assert (ag.actions_idx(up), ag.actions_idx(down)) == (1, 0)
+    assert ag.name == "a" and ag.get_reward_machine() is None and ag.get_actions() is ag.actions_
